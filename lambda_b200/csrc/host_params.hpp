@@ -1,0 +1,378 @@
+// Host-side option handling, scoring tables and BLAST statistics.
+//
+// Mirrors the parts of the reference the hot path reads:
+//   per-domain defaults + profiles  src/search_options.hpp:263,290-337,631-682
+//   prepareScoring                  src/search_algo.hpp:166-234
+//   Karlin-Altschul values          SQ/blast/blast_statistics.h:92-361, _selectSet :560-624
+//   _lengthAdjustment               SQ/blast/blast_statistics.h:903-982
+//   computeBitScore / _computeEValue  :1027-1030 / :1081-1087
+//   computeEValueThreadSafe         src/search_misc.hpp:57-80
+// All floating point of the path lives here, on the host, in double like the reference; the device
+// only ever sees integer score thresholds derived from these functions.
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+
+#include "../../include/lambda_b200.h"
+
+namespace lgpu
+{
+
+#include "tables_generated.inc"
+
+inline int paramsDefault(lgpu_params & p, uint32_t domain, char const * profileC)
+{
+    std::string const profile = profileC ? profileC : "none";
+    std::memset(&p, 0, sizeof(p));
+    p.domain             = domain;
+    p.seed_half_exact    = 1;
+    p.adaptive_seeding   = 1;
+    p.iterative_search   = 1;
+    p.max_matches        = 25;
+    p.pre_scoring        = 2;
+    p.pre_scoring_thresh = 2.0;
+    p.scoring_method     = 62;
+    p.match              = 2;
+    p.mismatch           = -3;
+    p.min_bit_score      = -1;
+    p.max_evalue         = 1e-2;
+    p.id_cutoff          = 0;
+    p.finalize           = 1;
+    switch (domain)
+    {
+        case LGPU_DOMAIN_PROTEIN:
+            p.gap_open   = -11;
+            p.gap_extend = -1;
+            p.opts0      = {10, 0, 5};
+            p.opts       = {11, 1, 3};
+            break;
+        case LGPU_DOMAIN_NUCLEOTIDE:
+            p.gap_open           = -5;
+            p.gap_extend         = -2;
+            p.opts0              = {14, 0, 9};
+            p.opts               = {14, 1, 7};
+            p.pre_scoring_thresh = 1.4;
+            break;
+        case LGPU_DOMAIN_BISULFITE:
+            p.gap_open           = -5;
+            p.gap_extend         = -2;
+            p.max_evalue         = 1e-9;
+            p.opts0              = {17, 0, 10};
+            p.opts               = {17, 1, 10};
+            p.pre_scoring_thresh = 1.5;
+            break;
+        default: return LGPU_ERR_ARG;
+    }
+
+    if (profile == "none" || profile.empty())
+    {
+    }
+    else if (profile == "fast")
+    {
+        if (domain != LGPU_DOMAIN_PROTEIN)
+        {
+            p.iterative_search   = 0;
+            p.opts.max_seed_dist = 0;
+            if (domain == LGPU_DOMAIN_NUCLEOTIDE)
+                p.opts.seed_offset = 9;
+        }
+        else
+        {
+            p.opts0.seed_length  = 12;
+            p.opts0.seed_offset  = 8;
+            p.opts.seed_length   = 10;
+            p.opts.seed_offset   = 5;
+            p.opts.max_seed_dist = 0;
+        }
+    }
+    else if (profile == "sensitive" || profile.rfind("pairs", 0) == 0)
+    {
+        if (profile != "sensitive" && profile != "pairs-default" && profile != "pairs-sensitive")
+            return LGPU_ERR_ARG;
+        switch (domain)
+        {
+            case LGPU_DOMAIN_PROTEIN:
+                p.opts0.seed_length  = 9;
+                p.opts0.seed_offset  = 4;
+                p.opts.seed_length   = 8;
+                p.opts.seed_offset   = 3;
+                p.pre_scoring        = 3;
+                p.pre_scoring_thresh = 1.9;
+                break;
+            case LGPU_DOMAIN_NUCLEOTIDE:
+                p.opts0.seed_offset = 3;
+                p.opts.seed_offset  = 3;
+                break;
+            case LGPU_DOMAIN_BISULFITE:
+                p.opts0.seed_length = 16;
+                p.opts0.seed_offset = 8;
+                p.opts.seed_length  = 15;
+                p.opts.seed_offset  = 10;
+                break;
+        }
+        if (profile.rfind("pairs", 0) == 0)
+            p.iterative_search = 0;
+        if (profile == "pairs-sensitive")
+            --p.opts.seed_length;
+    }
+    else
+    {
+        return LGPU_ERR_ARG;
+    }
+    return LGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// scoring
+// ---------------------------------------------------------------------------------------------
+
+struct KarlinAltschul
+{
+    double lambda = 0, K = 0, H = 0, alpha = 0, beta = 0;
+    bool   valid = false;
+};
+
+// Scoring as the device consumes it: a dense int8 matrix over the *translated* alphabet in BioC++
+// rank order (27x27 amino acids, 5x5 dna5), SeqAn-convention gap scores, and the KA parameters.
+struct Scoring
+{
+    int            alphSize = 0;      // 27 or 5
+    int8_t         matrix[32 * 32]{}; // [a * 32 + b]
+    int            gapOpenSeqan = 0;  // cost of the first gap character = gapOpen + gapExtend
+    int            gapExtend    = 0;
+    KarlinAltschul ka;
+};
+
+inline KarlinAltschul selectKA(lgpu_params const & p)
+{
+    KarlinAltschul ka;
+    if (p.domain == LGPU_DOMAIN_PROTEIN)
+    {
+        double const(*tab)[8] = nullptr;
+        int n                 = 0;
+        switch (p.scoring_method)
+        {
+            case 45: tab = kKaBlosum45; n = sizeof(kKaBlosum45) / sizeof(kKaBlosum45[0]); break;
+            case 62: tab = kKaBlosum62; n = sizeof(kKaBlosum62) / sizeof(kKaBlosum62[0]); break;
+            case 80: tab = kKaBlosum80; n = sizeof(kKaBlosum80) / sizeof(kKaBlosum80[0]); break;
+            default: return ka;
+        }
+        for (int i = 0; i < n; ++i)
+            if (tab[i][0] == -p.gap_open && tab[i][1] == -p.gap_extend)
+            {
+                ka = {tab[i][3], tab[i][4], tab[i][5], tab[i][6], tab[i][7], true};
+                break;
+            }
+    }
+    else
+    {
+        int const n = sizeof(kKaNucl) / sizeof(kKaNucl[0]);
+        for (int i = 0; i < n; ++i)
+            if (kKaNucl[i][0] == p.match && kKaNucl[i][1] == -p.mismatch && kKaNucl[i][2] == -p.gap_open &&
+                kKaNucl[i][3] == -p.gap_extend)
+            {
+                ka = {kKaNucl[i][4], kKaNucl[i][5], kKaNucl[i][6], kKaNucl[i][7], kKaNucl[i][8], true};
+                break;
+            }
+    }
+    return ka;
+}
+
+inline int makeScoring(Scoring & s, lgpu_params const & p)
+{
+    s = Scoring{};
+    if (p.domain == LGPU_DOMAIN_PROTEIN)
+    {
+        int8_t const(*m)[27] = nullptr;
+        switch (p.scoring_method)
+        {
+            case 45: m = kBlosum45; break;
+            case 62: m = kBlosum62; break;
+            case 80: m = kBlosum80; break;
+            default: return LGPU_ERR_ARG;
+        }
+        s.alphSize = 27;
+        for (int a = 0; a < 27; ++a)
+            for (int b = 0; b < 27; ++b)
+                s.matrix[a * 32 + b] = m[a][b];
+    }
+    else if (p.domain == LGPU_DOMAIN_NUCLEOTIDE)
+    {
+        // plain nucleotide scoring compares ranks: N vs N is a match
+        // (SQ/score/score_simd_wrapper.h:149-154; scalar Score<int,Simple>)
+        s.alphSize = 5;
+        for (int a = 0; a < 5; ++a)
+            for (int b = 0; b < 5; ++b)
+                s.matrix[a * 32 + b] = static_cast<int8_t>(a == b ? p.match : p.mismatch);
+    }
+    else
+    {
+        return LGPU_ERR_UNSUPPORTED;
+    }
+    s.gapOpenSeqan = p.gap_open + p.gap_extend; // src/search_algo.hpp:226
+    s.gapExtend    = p.gap_extend;
+    s.ka           = selectKA(p);
+    if (!s.ka.valid)
+        return LGPU_ERR_ARG; // "Could not compute Karlin-Altschul-Values for Scoring Scheme."
+    return LGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// statistics
+// ---------------------------------------------------------------------------------------------
+
+// NCBI's length-adjustment iteration as SeqAn ships it, including the early return that makes the
+// final refinement unreachable (blast_statistics.h:962).
+inline uint64_t lengthAdjustment(uint64_t dbLength, uint64_t queryLength, KarlinAltschul const & ka)
+{
+    double const logK          = std::log(ka.K);
+    double const alphaByLambda = ka.alpha / ka.lambda;
+    double const n             = static_cast<double>(dbLength);
+    double const m             = static_cast<double>(queryLength);
+    double       val = 0, valMin = 0, valMax;
+
+    double const mb = m + n;
+    double const c  = n * m - std::max(m, n) / ka.K;
+    if (c < 0)
+        return 0;
+    valMax = 2 * c / (mb + std::sqrt(mb * mb - 4 * c));
+
+    for (int i = 1; i <= 20; ++i)
+    {
+        double const totalLen = (m - val) * (n - val);
+        double const valNew   = alphaByLambda * (logK + std::log(totalLen)) + ka.beta;
+        if (valNew >= val)
+        {
+            valMin = val;
+            if (valNew - valMin <= 1.0)
+                break; // converged
+            if (valMin == valMax)
+                break;
+        }
+        else
+        {
+            valMax = val;
+        }
+        if (valMin <= valNew && valNew <= valMax)
+            val = valNew;
+        else
+            val = (i == 1) ? valMax : (valMin + valMax) / 2;
+    }
+    return static_cast<uint64_t>(valMin);
+}
+
+inline double bitScore(KarlinAltschul const & ka, double rawScore)
+{
+    return (ka.lambda * rawScore - std::log(ka.K)) / std::log(2);
+}
+
+// computeEValueThreadSafe with its per-length cache; `queryLen` is the ORIGINAL query length
+// (bm.qLength), divided by 3 for translated queries.
+class EValueComputer
+{
+public:
+    EValueComputer(KarlinAltschul const & ka, uint64_t dbTotalLength, bool qIsTranslated) :
+      ka_(ka), dbLen_(dbTotalLength), div_(qIsTranslated ? 3 : 1)
+    {}
+
+    uint64_t adjustment(uint64_t queryLen)
+    {
+        uint64_t const ql = queryLen / div_;
+        auto           it = cache_.find(ql);
+        if (it == cache_.end())
+            it = cache_.emplace(ql, lengthAdjustment(dbLen_, ql, ka_)).first;
+        return it->second;
+    }
+
+    double evalue(int32_t rawScore, uint64_t queryLen)
+    {
+        uint64_t const ql  = queryLen / div_;
+        uint64_t const adj = adjustment(queryLen);
+        // unsigned subtraction, then conversion to double -- as in the reference
+        double const m = static_cast<double>(ql - adj);
+        double const n = static_cast<double>(dbLen_ - adj);
+        return ka_.K * m * n * std::exp(-ka_.lambda * static_cast<double>(rawScore));
+    }
+
+    KarlinAltschul const & ka() const { return ka_; }
+    uint64_t               dbLen() const { return dbLen_; }
+
+private:
+    KarlinAltschul                         ka_;
+    uint64_t                               dbLen_;
+    uint64_t                               div_;
+    std::unordered_map<uint64_t, uint64_t> cache_;
+};
+
+// Integer thresholds that reproduce the reference's two pass-1 filters exactly
+// (src/search_algo.hpp:1256-1278): a hit is dropped by the bit-score test iff score < minBit, else
+// by the e-value test iff score < minEval.  Both tests are monotone in the raw score for a fixed
+// query length, so each reduces to one integer compare on the device.
+struct ScoreThresholds
+{
+    int32_t minBit;  // smallest S with bitScore(S) >= minBitScore   (INT32_MIN if test disabled)
+    int32_t minEval; // smallest S with evalue(S)  <= maxEValue      (INT32_MIN if test disabled)
+};
+
+inline ScoreThresholds scoreThresholds(lgpu_params const & p, EValueComputer & ev, uint64_t queryLen)
+{
+    constexpr int32_t kMaxScore = 1 << 20;
+    ScoreThresholds   t{INT32_MIN, INT32_MIN};
+    if (p.min_bit_score >= 0)
+    {
+        int32_t lo = 0, hi = kMaxScore; // first S in [lo,hi] with bits >= min
+        while (lo < hi)
+        {
+            int32_t const mid = lo + (hi - lo) / 2;
+            if (bitScore(ev.ka(), mid) < p.min_bit_score)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        t.minBit = lo;
+    }
+    if (p.max_evalue >= 0)
+    {
+        int32_t lo = 0, hi = kMaxScore;
+        while (lo < hi)
+        {
+            int32_t const mid = lo + (hi - lo) / 2;
+            if (ev.evalue(mid, queryLen) > p.max_evalue)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        t.minEval = lo;
+    }
+    return t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// domain-derived constants
+// ---------------------------------------------------------------------------------------------
+
+struct DomainInfo
+{
+    uint32_t qryNumFrames = 1;
+    uint32_t sbjNumFrames = 1;
+    bool     qIsTranslated = false;
+    uint8_t  unknownRank   = 23; // 'X' in aa27, 'N' (3) in dna5  (src/search_algo.hpp:652-656)
+};
+
+inline DomainInfo domainInfo(uint32_t domain)
+{
+    DomainInfo d;
+    switch (domain)
+    {
+        case LGPU_DOMAIN_PROTEIN: d = {1, 1, false, 23}; break;
+        case LGPU_DOMAIN_NUCLEOTIDE: d = {2, 1, false, 3}; break;
+        case LGPU_DOMAIN_BISULFITE: d = {4, 2, false, 3}; break;
+    }
+    return d;
+}
+
+} // namespace lgpu

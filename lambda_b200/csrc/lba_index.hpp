@@ -1,0 +1,207 @@
+// Host-side reader for the reference's `.lba` index files.
+//
+// The file is a cereal BinaryOutputArchive of index_file<> (reference
+// src/shared_definitions.hpp:330-379): little-endian, no padding between fields, vectors as
+// `u64 count` + raw payload.  The field order below was validated against real indexes to exact
+// EOF.  We do not link cereal: the big blobs (occ blocks, sampled SA,
+// sequences) are raw in the file, so the loader just maps the file and records pointers -- loading
+// a multi-GB index costs one mmap instead of a streamed parse.
+#pragma once
+
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include "../../include/lambda_b200.h"
+
+namespace lgpu
+{
+
+struct LbaError : std::runtime_error
+{
+    using std::runtime_error::runtime_error;
+};
+
+// sigma (= reduced alphabet size + 1) per AlphabetEnum, FMC occtable parameters derived from it
+inline uint32_t alphabetSize(uint32_t alph)
+{
+    switch (alph)
+    {
+        case LGPU_ALPH_DNA3BS: return 6;   // semialphabet_any<6>
+        case LGPU_ALPH_DNA4: return 4;
+        case LGPU_ALPH_DNA5: return 5;
+        case LGPU_ALPH_AMINO_ACID: return 27;
+        case LGPU_ALPH_MURPHY10: return 10;
+        case LGPU_ALPH_LI10: return 10;
+        default: throw LbaError("unknown alphabet id in index header");
+    }
+}
+
+inline uint32_t bitLength(uint32_t v) // required_bits(): number of bits to represent v
+{
+    uint32_t b = 0;
+    while (v) { ++b; v >>= 1; }
+    return b;
+}
+
+class LbaFile
+{
+public:
+    explicit LbaFile(std::string const & path)
+    {
+        if (path.size() >= 3 && path.compare(path.size() - 3, 3, ".gz") == 0)
+            throw LbaError("compressed indexes (.gz) are not supported; decompress first");
+        if (path.size() >= 4 && path.compare(path.size() - 4, 4, ".lta") == 0)
+            throw LbaError("JSON indexes (.lta) are not supported; use the binary .lba format");
+        fd_ = ::open(path.c_str(), O_RDONLY);
+        if (fd_ < 0)
+            throw LbaError("cannot open index file " + path);
+        struct stat st;
+        if (fstat(fd_, &st) != 0)
+            throw LbaError("cannot stat index file " + path);
+        size_ = static_cast<size_t>(st.st_size);
+        base_ = static_cast<uint8_t const *>(mmap(nullptr, size_, PROT_READ, MAP_PRIVATE, fd_, 0));
+        if (base_ == MAP_FAILED)
+        {
+            base_ = nullptr;
+            throw LbaError("cannot mmap index file " + path);
+        }
+        madvise(const_cast<uint8_t *>(base_), size_, MADV_SEQUENTIAL);
+        parse();
+    }
+
+    ~LbaFile()
+    {
+        if (base_)
+            munmap(const_cast<uint8_t *>(base_), size_);
+        if (fd_ >= 0)
+            ::close(fd_);
+    }
+
+    LbaFile(LbaFile const &)             = delete;
+    LbaFile & operator=(LbaFile const &) = delete;
+
+    lgpu_index_desc desc{};
+    uint64_t        generation  = 0;
+    uint8_t         geneticCode = 0;
+    // taxonomy is carried along but unused on the hot path
+    uint32_t const * sTaxIds = nullptr;
+    uint64_t         nSTaxIds = 0;
+    uint64_t const * sTaxDelims = nullptr;
+    uint64_t         nSTaxDelims = 0;
+
+private:
+    int             fd_   = -1;
+    uint8_t const * base_ = nullptr;
+    size_t          size_ = 0;
+    size_t          pos_  = 0;
+
+    template <typename T>
+    T get()
+    {
+        if (pos_ + sizeof(T) > size_)
+            throw LbaError("index file truncated");
+        T v;
+        std::memcpy(&v, base_ + pos_, sizeof(T));
+        pos_ += sizeof(T);
+        return v;
+    }
+
+    uint8_t const * blob(uint64_t bytes)
+    {
+        if (bytes > size_ - pos_)
+            throw LbaError("index file truncated");
+        uint8_t const * p = base_ + pos_;
+        pos_ += bytes;
+        return p;
+    }
+
+    // `u64 n` + n * elem bytes
+    uint8_t const * vec(uint64_t elem, uint64_t & n)
+    {
+        n = get<uint64_t>();
+        if (elem && n > (size_ - pos_) / elem)
+            throw LbaError("index file truncated");
+        return blob(n * elem);
+    }
+
+    void parse()
+    {
+        // index_file_options (shared_definitions.hpp:316-343)
+        generation      = get<uint64_t>();
+        if (generation != 0)
+            throw LbaError("unsupported index generation " + std::to_string(generation) +
+                           " (this build reads generation 0)");
+        desc.index_type = get<uint8_t>();
+        desc.orig_alph  = get<uint8_t>();
+        desc.trans_alph = get<uint8_t>();
+        desc.red_alph   = get<uint8_t>();
+        geneticCode     = get<uint8_t>();
+        if (desc.index_type != LGPU_INDEX_FM)
+            throw LbaError("bidirectional FM indexes are out of scope (LAMBDA_WITH_BIFM is off by default)");
+
+        uint64_t n;
+        // ids: concatenated_sequences<std::string> = data string + delimiters
+        desc.ids       = reinterpret_cast<char const *>(vec(1, n));
+        desc.id_delims = reinterpret_cast<uint64_t const *>(vec(8, n));
+        uint64_t const nIdDelims = n;
+        // seqs: custom save (shared_definitions.hpp:290-307) = u64 n + n bytes; then delimiters
+        desc.seqs       = vec(1, n);
+        desc.n_residues = n;
+        desc.seq_delims = reinterpret_cast<uint64_t const *>(vec(8, n));
+        if (n == 0 || n != nIdDelims)
+            throw LbaError("index file corrupt: id/sequence delimiter count mismatch");
+        desc.n_seqs = n - 1;
+        if (desc.seq_delims[desc.n_seqs] != desc.n_residues)
+            throw LbaError("index file corrupt: last sequence delimiter != residue count");
+        // sTaxIds, taxonParentIDs, taxonHeights, taxonNames
+        sTaxIds    = reinterpret_cast<uint32_t const *>(vec(4, nSTaxIds));
+        sTaxDelims = reinterpret_cast<uint64_t const *>(vec(8, nSTaxDelims));
+        vec(4, n); // taxonParentIDs
+        vec(1, n); // taxonHeights
+        vec(1, n); // taxonNames data
+        vec(8, n); // taxonNames delimiters
+
+        // index.occ (InterleavedEPRV2.h:272-306)
+        uint32_t const redSize = alphabetSize(desc.red_alph);
+        desc.sigma             = redSize + 1;
+        desc.sigma_bits        = bitLength(desc.sigma - 1);
+        desc.planes_offset     = (4 * desc.sigma + 7) / 8 * 8;
+        desc.block_bytes       = desc.planes_offset + 8 * desc.sigma_bits;
+        int32_t version        = get<int32_t>();
+        if (version != 1)
+            throw LbaError("occ table was not written with cereal's binary fast path (version != 1)");
+        desc.n_blocks     = get<uint64_t>();
+        desc.occ_blocks   = blob(desc.n_blocks * desc.block_bytes);
+        desc.n_super      = get<uint64_t>();
+        desc.super_blocks = reinterpret_cast<uint64_t const *>(blob(desc.n_super * desc.sigma * 8));
+        desc.C            = reinterpret_cast<uint64_t const *>(blob((desc.sigma + 1) * 8));
+
+        // index.csa (CSA.h:115-118, BitvectorCompact.h:112-143)
+        desc.ssa = reinterpret_cast<uint64_t const *>(vec(8, desc.n_ssa));
+        version  = get<int32_t>();
+        if (version != 1)
+            throw LbaError("csa bit vector was not written with cereal's binary fast path");
+        desc.n_csa_sb          = get<uint64_t>();
+        desc.csa_bv            = blob(desc.n_csa_sb * 48);
+        desc.sampling_rate     = get<uint64_t>();
+        desc.bits_for_position = get<uint64_t>();
+        uint64_t const mask    = get<uint64_t>();
+        if (desc.bits_for_position == 0 || desc.bits_for_position >= 64 ||
+            mask != ((1ull << desc.bits_for_position) - 1))
+            throw LbaError("index file corrupt: bad CSA position mask");
+        if (pos_ != size_)
+            throw LbaError("index file has " + std::to_string(size_ - pos_) + " trailing bytes");
+        // size() of the index = C.back() must be addressable in the block array
+        if (desc.C[desc.sigma] / 64 >= desc.n_blocks)
+            throw LbaError("index file corrupt: occ blocks do not cover the BWT");
+    }
+};
+
+} // namespace lgpu
