@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""Benchmark of the seed-and-extend hot path (BASELINE.json metric: query-seqs/s + GCUPS, searchp).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): searchp, 100 000 synthetic 300-aa queries against a
+5 000 000-sequence synthetic protein index (Li10 FM index, BLOSUM62, default profile), per GPU.
+One "step" = one pass of the whole hot path (seeding -> merge -> DP score pass -> filter -> DP trace
+pass -> hits) over the rank's 100k-query batch.  Queries shard naturally, so N GPUs = N independent
+shards of 100k queries (weak scaling) + one NCCL all-gather of the hit records at the end of the step.
+
+The index is built ONCE per box by the unmodified reference (oracle/_ref/lambda3 mkindexp -- indexing
+is out of scope) and cached under $LAMBDA_B200_CACHE (default /tmp/lambda_b200_cache).
+
+JSON line (rank 0): see the contract in the task description; extra keys: gcups_score, gcups_trace,
+stage_ms, hits, funnel, parity_sample.
+"""
+from __future__ import annotations
+
+import argparse
+import hashlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+REF = os.path.join(ROOT, "oracle", "_ref", "lambda3")
+CACHE = os.environ.get("LAMBDA_B200_CACHE", "/tmp/lambda_b200_cache")
+
+
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------
+
+def workload_dir(n_seqs, seed):
+    key = hashlib.sha1(f"protein-flat-{n_seqs}-{seed}-v2".encode()).hexdigest()[:12]
+    return os.path.join(CACHE, f"searchp_{n_seqs}_{key}")
+
+
+def ensure_index(n_seqs, seed=1):
+    """database FASTA + reference-built .lba, cached; safe against concurrent ranks"""
+    from lambda_b200 import synth
+    d = workload_dir(n_seqs, seed)
+    done = os.path.join(d, "READY")
+    if os.path.exists(done):
+        return d
+    os.makedirs(d, exist_ok=True)
+    lock = os.path.join(d, "LOCK")
+    try:
+        fd = os.open(lock, os.O_CREAT | os.O_EXCL | os.O_WRONLY)
+        os.close(fd)
+    except FileExistsError:
+        log("waiting for another process to build the index ...")
+        t0 = time.time()
+        while not os.path.exists(done):
+            time.sleep(2)
+            if time.time() - t0 > 3600:
+                raise RuntimeError("timed out waiting for the index build")
+        return d
+    try:
+        if not os.path.exists(REF):
+            raise RuntimeError(f"{REF} missing: run `python -c 'import __graft_entry__ as g; g.build()'` where "
+                               "/root/reference is available (the binary travels with the repo snapshot)")
+        t0 = time.time()
+        db, offs = synth.protein_db(n_seqs, seed=seed)
+        synth.write_fasta(os.path.join(d, "db.fasta"), db, offs, "S")
+        np.save(os.path.join(d, "db_offsets.npy"), offs)
+        log(f"database: {n_seqs} seqs, {int(offs[-1])} residues generated in {time.time() - t0:.1f}s")
+        t0 = time.time()
+        lba = os.path.join(d, "db.lba")
+        if os.path.exists(lba):
+            os.remove(lba)
+        subprocess.check_call([REF, "mkindexp", "-d", os.path.join(d, "db.fasta"), "-i", lba, "-v", "0",
+                               "-t", str(os.cpu_count() or 1)])
+        log(f"reference mkindexp: {time.time() - t0:.1f}s, {os.path.getsize(lba) / 1e9:.2f} GB")
+        open(done, "w").write("ok\n")
+    finally:
+        os.remove(lock)
+    return d
+
+
+def make_queries(d, n_queries, qlen, seed):
+    """mutated windows of database sequences; returns (ascii residues, offsets)"""
+    from lambda_b200 import synth
+    offs = np.load(os.path.join(d, "db_offsets.npy"))
+    fa = np.memmap(os.path.join(d, "db.fasta"), dtype=np.uint8, mode="r")
+    # recover residue positions inside the FASTA: record i = ">S<i>\n" + seq + "\n"
+    n = len(offs) - 1
+    idlen = np.char.str_len(np.arange(n).astype(str)).astype(np.int64) + 3
+    rec_start = np.zeros(n + 1, np.int64)
+    np.cumsum(idlen + np.diff(offs) + 1, out=rec_start[1:])
+    seq_start = rec_start[:-1] + idlen
+    rng = np.random.default_rng(seed)
+    lens = np.diff(offs)
+    elig = np.nonzero(lens >= qlen)[0]
+    pick = elig[rng.integers(0, len(elig), n_queries)]
+    start = seq_start[pick] + (rng.random(n_queries) * (lens[pick] - qlen + 1)).astype(np.int64)
+    q = np.asarray(fa[start[:, None] + np.arange(qlen)[None, :]])
+    rate = rng.uniform(0.15, 0.20, n_queries)[:, None]
+    m = rng.random(q.shape, dtype=np.float32) < rate
+    q[m] = synth._random_residues(rng, int(m.sum()))
+    ev = rng.random(q.shape, dtype=np.float32) < 0.01
+    rows, cols = np.nonzero(ev)
+    kinds = rng.random(len(rows)) < 0.5
+    fill = synth._random_residues(rng, len(rows))
+    for r, c, k, f in zip(rows, cols, kinds, fill):
+        if k:
+            q[r, c:-1] = q[r, c + 1:]
+            q[r, -1] = f
+        else:
+            q[r, c + 1:] = q[r, c:-1]
+            q[r, c] = f
+    return q.reshape(-1), np.arange(n_queries + 1, dtype=np.uint64) * qlen
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+
+class ClockSampler(threading.Thread):
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        sm = [int(r[0]) for r in self.rows if len(r) >= 6 and r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if len(r) >= 6 and r[1].isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 6:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline
+# ------------------------------------------------------------------------------------------------
+
+def run_reference_search(d, q_ascii, qoffs, n_sample, threads, tag):
+    """time the unmodified reference (searchp, OpenMP) on the first n_sample queries; returns
+    (queries/s over the reference's own 'Runtime total' search phase, wall seconds, hits)"""
+    import re
+    import tempfile
+    from lambda_b200 import synth
+    with tempfile.TemporaryDirectory() as tmp:
+        qf = os.path.join(tmp, "q.fasta")
+        synth.write_fasta(qf, q_ascii[: int(qoffs[n_sample])], qoffs[: n_sample + 1].astype(np.int64), "Q")
+        out = os.path.join(tmp, "out.m8")
+        t0 = time.time()
+        txt = subprocess.run([REF, "searchp", "-q", qf, "-i", os.path.join(d, "db.lba"), "-o", out, "-t", str(threads),
+                              "--version-to-outputfile", "0", "-v", "2"], check=True, capture_output=True, text=True).stdout
+        wall = time.time() - t0
+        m = re.search(r"Runtime total: ([0-9.eE+-]+)s", txt)
+        phase = float(m.group(1)) if m else wall
+        lines = open(out).read().splitlines(True)
+    return n_sample / phase, wall, phase, lines
+
+
+# ------------------------------------------------------------------------------------------------
+# main
+# ------------------------------------------------------------------------------------------------
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-seqs", type=int, default=int(os.environ.get("LAMBDA_B200_NSEQS", 5_000_000)))
+    ap.add_argument("--n-queries", type=int, default=int(os.environ.get("LAMBDA_B200_NQUERIES", 100_000)))
+    ap.add_argument("--qlen", type=int, default=300)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="queries for the CPU baseline (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if world > 1 and args.gpus != world:
+        log(f"--gpus {args.gpus} != WORLD_SIZE {world}; using WORLD_SIZE")
+    n_gpus = world
+    workload = (f"searchp: {args.n_queries}x{args.qlen}aa synthetic queries vs {args.n_seqs}-seq synthetic protein "
+                f"index (Li10), BLOSUM62, default profile")
+    cfg = {"workload": workload, "queries_per_gpu": args.n_queries, "query_len": args.qlen, "index_seqs": args.n_seqs,
+           "profile": "none", "sharding": f"queries x{n_gpus}, index replicated",
+           "l2_policy": "inputs larger than L2 (index and per-step trace/DP working sets are GBs)"}
+    cores = os.cpu_count() or 1
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        d = ensure_index(args.n_seqs)
+        q_ascii, qoffs = make_queries(d, args.n_queries, args.qlen, seed=1000)
+        n_sample = args.cpu_sample or min(args.n_queries, max(500, 150 * cores))
+        for _ in range(args.warmup):
+            run_reference_search(d, q_ascii, qoffs, min(n_sample, 200), cores, "warm")
+        qps, walls = [], []
+        for _ in range(args.steps):
+            v, wall, phase, _ = run_reference_search(d, q_ascii, qoffs, n_sample, cores, "step")
+            qps.append(n_sample / phase)
+            walls.append(phase)
+        value = n_sample * len(walls) / sum(walls)
+        sample = f"first {n_sample} of the {args.n_queries} queries per step, lambda3 searchp -t {cores}, search phase"
+        print(json.dumps({"impl": "reference", "metric": "searchp_query_seqs_per_s", "value": value, "unit": "queries/s",
+                          "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": 1e3 * sum(walls) / len(walls), "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "int16", "data": "synthetic", "config": cfg,
+                          "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "reference",
+                                           "sample": sample},
+                          "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import lambda_b200
+    from lambda_b200._abi import HIT_DT
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    d = ensure_index(args.n_seqs)
+    if world > 1:
+        dist.barrier()
+    t0 = time.time()
+    ix = lambda_b200.Index.load(os.path.join(d, "db.lba"), device=local_rank, keep_ids=(rank == 0))
+    log(f"rank {rank}: index in HBM: {ix.device_bytes / 1e9:.2f} GB, load {time.time() - t0:.1f}s")
+    s = lambda_b200.Searcher(ix, "protein")
+    q_ascii, qoffs = make_queries(d, args.n_queries, args.qlen, seed=1000 + rank)
+    res = lambda_b200.encode(q_ascii, 0)
+    h_res = torch.from_numpy(res).pin_memory()
+    h_offs = torch.from_numpy(qoffs.view(np.int64)).pin_memory()
+    d_res = h_res.cuda()
+    d_offs = h_offs.cuda()
+
+    def gather_hits(hits):
+        """the path's only collective: all ranks exchange their hit records (NCCL all-gather)"""
+        if world == 1:
+            return len(hits)
+        cnt = torch.tensor([len(hits)], device="cuda", dtype=torch.int64)
+        cnts = [torch.zeros_like(cnt) for _ in range(world)]
+        dist.all_gather(cnts, cnt)
+        mx = int(max(int(c) for c in cnts))
+        buf = torch.zeros(mx * HIT_DT.itemsize, dtype=torch.uint8, device="cuda")
+        raw = torch.from_numpy(hits.view(np.uint8).reshape(-1))
+        buf[: raw.numel()] = raw.cuda()
+        out = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(out, buf)
+        return int(sum(int(c) for c in cnts))
+
+    def step(resident):
+        if resident:
+            hits, st = s.search(d_res, d_offs)
+        else:
+            hits, st = s.search(res, qoffs)  # host buffers: H2D of queries + D2H of hits inside
+        g_ms = 0.0
+        if world > 1:
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            total = gather_hits(hits)
+            g1.record()
+            g1.synchronize()
+            g_ms = g0.elapsed_time(g1)
+        else:
+            total = len(hits)
+        return hits, st, total, g_ms
+
+    def timed(resident, k):
+        """K steps.  Device time = CUDA events recorded by the library on ITS stream around every
+        lgpu_search_batch call (ms_total; torch.cuda.Event only sees torch's stream) + torch events around
+        the NCCL gather; max over ranks.  Host wall-clock around the same region is reported next to it."""
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        acc, ms = None, 0.0
+        for _ in range(k):
+            hits, st, total, g_ms = step(resident)
+            ms += float(st["ms_total"]) + g_ms
+            acc = st.copy() if acc is None else _acc(acc, st)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        if world > 1:
+            t = torch.tensor([ms, wall], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, wall = float(t[0]), float(t[1])
+        return ms, wall, acc, hits, total
+
+    def _acc(a, b):
+        for n in a.dtype.names:
+            a[n] += b[n]
+        return a
+
+    for _ in range(args.warmup):
+        step(True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_res, wall_res, st, hits, total_hits = timed(True, args.steps)
+    ms_e2e, wall_e2e, st_e2e, _, _ = timed(False, args.steps)
+    clocks = sampler.summary() if rank == 0 else None
+
+    nq_total = args.n_queries * n_gpus * args.steps
+    value = nq_total / (ms_res * 1e-3)
+    e2e = nq_total / (ms_e2e * 1e-3)
+    cells_score, cells_trace = float(st["cells_score"]), float(st["cells_trace"])
+    if world > 1:
+        t = torch.tensor([cells_score, cells_trace], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
+        cells_score_all, cells_trace_all = float(t[0]), float(t[1])
+    else:
+        cells_score_all, cells_trace_all = cells_score, cells_trace
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # roofline of the dominant kernel (DP score pass): integer-ALU bound, SURVEY §8(d)
+    peaks_path = os.path.join(ROOT, "profiles", "INT_PEAKS.json")
+    peak_gops, peak_src = None, "unmeasured"
+    if os.path.exists(peaks_path):
+        pk = json.load(open(peaks_path))
+        # one VIADDMNMX.S16x2 warp-instruction = 32 lanes x 2 halves x (add + max) = 128 int16 ops
+        peak_gops = pk["viaddmnmx_s16x2"] * 128.0
+        peak_src = "profiles/INT_PEAKS.json (bin/int16_peak on this pool's B200)"
+    ms_score = float(st["ms_extend_score"]) / args.steps
+    gcups_score = cells_score / args.steps / (ms_score * 1e-3) / 1e9 if ms_score > 0 else 0.0
+    ms_trace = float(st["ms_extend_trace"]) / args.steps
+    gcups_trace = cells_trace / args.steps / (ms_trace * 1e-3) / 1e9 if ms_trace > 0 else 0.0
+    achieved = gcups_score * 10.0  # 10 int16 ops per cell update (5 add + 5 max), SURVEY §8(d)
+    roofline = {"kernel": "swWavefrontKernel<score> (DP pass 1)", "bound": "int16-alu", "achieved": achieved,
+                "peak": peak_gops, "unit": "Gop/s (int16)", "frac": (achieved / peak_gops) if peak_gops else None,
+                "peak_source": peak_src, "traffic": None, "gcups": gcups_score}
+
+    out = {"metric": "searchp_query_seqs_per_s", "value": value, "unit": "queries/s", "n_gpus": n_gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "wall_ms_per_step": wall_res / args.steps,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic", "config": cfg,
+           "gcups": (cells_score_all + cells_trace_all) / (ms_res * 1e-3) / 1e9,
+           "gcups_score_kernel": gcups_score, "gcups_trace_kernel": gcups_trace,
+           "stage_ms": {k: float(st[k]) / args.steps for k in ("ms_seed", "ms_sort_merge", "ms_extend_score",
+                                                               "ms_extend_trace", "ms_h2d", "ms_total")},
+           "funnel": {k: int(st[k]) // args.steps for k in ("hits_after_seeding", "hits_failed_pre_extend",
+                                                            "hits_duplicate", "hits_failed_evalue", "hits_final",
+                                                            "n_extensions_score", "n_extensions_trace")},
+           "hits_per_step_all_ranks": total_hits,
+           "clocks": clocks, "roofline": roofline,
+           "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": int(res.nbytes + qoffs.nbytes),
+                   "d2h_bytes_per_step": int(len(hits) * HIT_DT.itemsize), "ms_per_step": ms_e2e / args.steps,
+                   "wall_ms_per_step": wall_e2e / args.steps},
+           "gpu_launches": int(st["kernel_launches"])}
+
+    # CPU baseline: the unmodified reference on this box's host cores, bounded sample of the same queries
+    if not args.no_cpu_baseline and n_gpus == 1 and os.path.exists(REF):
+        n_sample = args.cpu_sample or min(args.n_queries, max(500, 150 * cores))
+        qps, wall, phase, ref_lines = run_reference_search(d, q_ascii, qoffs, n_sample, cores, "cpu")
+        out["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "reference",
+                               "sample": f"first {n_sample} of the {args.n_queries} queries, lambda3 searchp -t {cores} "
+                                         f"(SSE4 build), reference's own search-phase timer {phase:.2f}s, wall {wall:.2f}s"}
+        # parity on the sample: our tabular lines for the same queries must equal the reference's
+        ids = [f"Q{i}" for i in range(args.n_queries)]
+        mine = sorted(s.m8(hits[hits["q_id"] < n_sample], ids))
+        out["parity_sample"] = {"queries": n_sample, "reference_lines": len(ref_lines), "our_lines": len(mine),
+                                "identical": mine == sorted(ref_lines)}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,1080 @@
+// lambda_b200 engine: device-resident index, per-context pipeline, C ABI (include/lambda_b200.h).
+//
+// One lgpu_search_batch() call = the reference's batch loop body (src/search.cpp:428-457) for an
+// arbitrarily large batch:
+//
+//   H2D queries -> prepQueries (frames, reduction)
+//   phase 1 (searchOpts0) on all queries, phase 2 (searchOpts) on the queries without a hit:
+//     seedKernel            search()                         src/search_algo.hpp:607-762
+//     widen/sort/merge      _widenAndPreprocessMatches       :1137-1175
+//     swWavefront<score>    _performAlignment<false>         :1246
+//     filterKernel          bit-score / e-value thresholds   :1252-1281 (integer thresholds from host)
+//     swWavefront<trace>    _performAlignment<true>          :1296
+//     tracebackKernel       _expandAlign + computeAlignmentStats :1306-1308
+//   D2H hits -> host: bit score / e-value doubles, identity cut-off, phase bookkeeping
+//   (iterativeSearchPre/Post :1391-1460), optional _writeRecord finalisation (:821-913).
+//
+// No CPU fallback exists: if CUDA is unavailable every entry point fails with LGPU_ERR_CUDA.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cuda_runtime.h>
+
+#include "../../include/lambda_b200.h"
+#include "host_finalize.hpp"
+#include "host_params.hpp"
+#include "kernels_extend.cuh"
+#include "kernels_fm.cuh"
+#include "lba_index.hpp"
+
+namespace lgpu
+{
+
+struct CudaError : std::runtime_error
+{
+    using std::runtime_error::runtime_error;
+};
+struct ArgError : std::runtime_error
+{
+    using std::runtime_error::runtime_error;
+};
+struct UnsupportedError : std::runtime_error
+{
+    using std::runtime_error::runtime_error;
+};
+
+#define LGPU_CUDA(expr)                                                                                               \
+    do                                                                                                                \
+    {                                                                                                                 \
+        cudaError_t const e_ = (expr);                                                                                \
+        if (e_ != cudaSuccess)                                                                                        \
+            throw ::lgpu::CudaError(std::string(#expr) + ": " + cudaGetErrorString(e_));                              \
+    } while (0)
+
+static thread_local std::string g_lastError;
+
+// growable device buffer
+template <typename T>
+struct DevBuf
+{
+    T *    p   = nullptr;
+    size_t cap = 0;
+    ~DevBuf() { release(); }
+    DevBuf()                           = default;
+    DevBuf(DevBuf const &)             = delete;
+    DevBuf & operator=(DevBuf const &) = delete;
+    void     release()
+    {
+        if (p)
+            cudaFree(p);
+        p   = nullptr;
+        cap = 0;
+    }
+    void reserve(size_t n)
+    {
+        if (n <= cap)
+            return;
+        release();
+        size_t const want = std::max<size_t>(n + n / 4, 256);
+        LGPU_CUDA(cudaMalloc(reinterpret_cast<void **>(&p), want * sizeof(T)));
+        cap = want;
+    }
+};
+
+template <typename T>
+static T * uploadNew(T const * host, size_t n)
+{
+    T * d = nullptr;
+    LGPU_CUDA(cudaMalloc(reinterpret_cast<void **>(&d), std::max<size_t>(n, 1) * sizeof(T)));
+    if (n)
+        LGPU_CUDA(cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice));
+    return d;
+}
+
+static inline unsigned int gridFor(unsigned long long n, unsigned int block)
+{
+    return static_cast<unsigned int>((n + block - 1) / block);
+}
+
+} // namespace lgpu
+
+using namespace lgpu;
+
+// -------------------------------------------------------------------------------------------------
+// index
+// -------------------------------------------------------------------------------------------------
+
+struct lgpu_lba
+{
+    std::unique_ptr<LbaFile> file;
+};
+
+struct lgpu_index
+{
+    int                      device = 0;
+    DevIndex                 dev{};
+    lgpu_index_desc          meta{}; // scalar fields only (host pointers cleared)
+    std::vector<void *>      allocs;
+    uint64_t                 bytes         = 0;
+    uint64_t                 dbTotalLength = 0;
+    std::vector<uint64_t>    seqDelimsHost; // kept on the host for subject lengths
+    ~lgpu_index()
+    {
+        cudaSetDevice(device);
+        for (void * p : allocs)
+            cudaFree(p);
+    }
+};
+
+struct lgpu_ctx
+{
+    lgpu_index const * index = nullptr;
+    lgpu_params        params{};
+    Scoring            scoring;
+    DomainInfo         di;
+    cudaStream_t       stream = nullptr;
+    std::string        err;
+    int                numSMs = 148;
+
+    // device buffers
+    DevBuf<signed char>        dMatrix;
+    DevBuf<unsigned char>      dQOrig, dQTrans, dQRed;
+    DevBuf<unsigned long long> dQOffs;
+    DevBuf<unsigned int>       dActive;
+    DevBuf<lgpu_match>         dMatches, dMerged, dTasks2, dUserMatches;
+    DevBuf<unsigned long long> dCounters;
+    DevBuf<unsigned long long> dKey1, dKey2, dKey1b, dKey2b;
+    DevBuf<unsigned int>       dPerm, dPermB, dHead, dScan;
+    DevBuf<unsigned char>      dCubTemp;
+    DevBuf<int>                dScores, dScores2, dMinBit, dMinEval;
+    DevBuf<unsigned int>       dWork, dBestPos, dBoundary;
+    DevBuf<unsigned char>      dTrace;
+    DevBuf<unsigned long long> dTraceOff;
+    DevBuf<lgpu_hit>           dHits;
+
+    // host results
+    std::vector<lgpu_hit>   hits;
+    std::vector<lgpu_match> matchesHost;
+    cudaEvent_t             ev[8]{};
+
+    DevQueries Q{};
+    uint64_t   nQueries = 0, totalResidues = 0;
+    std::vector<uint64_t> qOffsHost;
+
+    ~lgpu_ctx()
+    {
+        if (index)
+            cudaSetDevice(index->device);
+        for (auto & e : ev)
+            if (e)
+                cudaEventDestroy(e);
+        if (stream)
+            cudaStreamDestroy(stream);
+    }
+};
+
+namespace lgpu
+{
+
+// -------------------------------------------------------------------------------------------------
+// pipeline stages
+// -------------------------------------------------------------------------------------------------
+
+struct StageTimer
+{
+    lgpu_ctx & c;
+    float *    acc;
+    StageTimer(lgpu_ctx & ctx, float * a) : c(ctx), acc(a) { cudaEventRecord(c.ev[0], c.stream); }
+    ~StageTimer()
+    {
+        cudaEventRecord(c.ev[1], c.stream);
+        cudaEventSynchronize(c.ev[1]);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c.ev[0], c.ev[1]);
+        if (acc)
+            *acc += ms;
+    }
+};
+
+static void checkParams(lgpu_params const & p, lgpu_index_desc const & d)
+{
+    if (p.domain == LGPU_DOMAIN_BISULFITE)
+        throw UnsupportedError("bisulfite search (searchbs) is not implemented yet");
+    if (p.domain == LGPU_DOMAIN_PROTEIN)
+    {
+        if (d.trans_alph != LGPU_ALPH_AMINO_ACID)
+            throw ArgError("Attempting to use nucleotide or bisulfite index for protein search.");
+        if (d.orig_alph != LGPU_ALPH_AMINO_ACID)
+            throw UnsupportedError("translated subjects (TBLASTN/TBLASTX) are not implemented yet");
+    }
+    else if (p.domain == LGPU_DOMAIN_NUCLEOTIDE)
+    {
+        if (d.trans_alph != LGPU_ALPH_DNA5)
+            throw ArgError("Attempting to use protein index for nucleotide search.");
+        if (d.red_alph != LGPU_ALPH_DNA4)
+            throw ArgError("Attempting to use bisulfite index for nucleotide search.");
+    }
+    else
+        throw ArgError("unknown domain");
+    for (lgpu_search_opts const * o : {&p.opts0, &p.opts})
+    {
+        if (o->seed_length == 0 || o->seed_length > 2 * kMaxHalf2 || o->seed_offset == 0)
+            throw ArgError("seed length must be in [1,32] and seed offset > 0");
+        if (o->max_seed_dist > 1)
+            throw UnsupportedError("seed distances > 1 are not implemented (reference default profiles use 0 or 1)");
+        if (o->max_seed_dist == 1 && !p.seed_half_exact)
+            throw UnsupportedError("max_seed_dist = 1 requires seed_half_exact (the reference default)");
+    }
+    if (p.max_matches == 0)
+        throw ArgError("max_matches must be > 0");
+}
+
+static void uploadQueries(lgpu_ctx & c, lgpu_query_batch const & qb, lgpu_stats * st)
+{
+    lgpu_index const & ix = *c.index;
+    c.nQueries            = qb.n_queries;
+    if (qb.n_queries == 0)
+        return;
+    if (qb.n_queries >= (1ull << 31) / c.di.qryNumFrames)
+        throw ArgError("too many queries in one batch");
+    c.qOffsHost.resize(qb.n_queries + 1);
+    if (qb.on_device)
+        LGPU_CUDA(cudaMemcpyAsync(c.qOffsHost.data(), qb.offsets, (qb.n_queries + 1) * 8, cudaMemcpyDeviceToHost, c.stream));
+    else
+        std::memcpy(c.qOffsHost.data(), qb.offsets, (qb.n_queries + 1) * 8);
+    LGPU_CUDA(cudaStreamSynchronize(c.stream));
+    if (c.qOffsHost[0] != 0)
+        throw ArgError("query offsets must start at 0");
+    c.totalResidues      = c.qOffsHost[qb.n_queries];
+    unsigned int const F = c.di.qryNumFrames;
+    c.dQOrig.reserve(c.totalResidues);
+    c.dQOffs.reserve(qb.n_queries + 1);
+    c.dQTrans.reserve(c.totalResidues * F);
+    c.dQRed.reserve(c.totalResidues * F);
+    {
+        StageTimer t(c, st ? &st->ms_h2d : nullptr);
+        auto const kind = qb.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        LGPU_CUDA(cudaMemcpyAsync(c.dQOrig.p, qb.residues, c.totalResidues, kind, c.stream));
+        LGPU_CUDA(cudaMemcpyAsync(c.dQOffs.p, qb.offsets, (qb.n_queries + 1) * 8, kind, c.stream));
+    }
+    DevQueries & Q = c.Q;
+    Q.orig         = c.dQOrig.p;
+    Q.offs         = c.dQOffs.p;
+    Q.trans        = c.dQTrans.p;
+    Q.red          = c.dQRed.p;
+    Q.n            = static_cast<unsigned int>(qb.n_queries);
+    Q.F            = F;
+    std::memset(Q.redTab, 0, sizeof(Q.redTab));
+    std::memset(Q.compTab, 0, sizeof(Q.compTab));
+    switch (ix.meta.red_alph)
+    {
+        case LGPU_ALPH_LI10: std::memcpy(Q.redTab, kAa27ToLi10, 27); break;
+        case LGPU_ALPH_MURPHY10: std::memcpy(Q.redTab, kAa27ToMurphy10, 27); break;
+        case LGPU_ALPH_AMINO_ACID:
+            for (int i = 0; i < 27; ++i)
+                Q.redTab[i] = static_cast<unsigned char>(i);
+            break;
+        case LGPU_ALPH_DNA4:
+        {
+            // dna5 (A,C,G,N,T) -> dna4 (A,C,G,T).  The reference replaces N by a pseudo-random base whose
+            // value depends on its internal access pattern; we map N to A.
+            unsigned char const t[5] = {0, 1, 2, 0, 3};
+            std::memcpy(Q.redTab, t, 5);
+            break;
+        }
+        default: throw UnsupportedError("unsupported reduced alphabet");
+    }
+    std::memcpy(Q.compTab, kDna5Complement, 5);
+    prepQueriesKernel<<<std::min<unsigned int>(Q.n, 65535u * 8u), 128, 0, c.stream>>>(Q);
+    LGPU_CUDA(cudaGetLastError());
+    if (st)
+        st->kernel_launches += 1;
+}
+
+// search(): returns number of matches now in c.dMatches
+static uint64_t runSeeding(lgpu_ctx & c, lgpu_search_opts const & so, unsigned int const * dActive, unsigned int nActive,
+                           lgpu_stats * st)
+{
+    if (nActive == 0)
+        return 0;
+    StageTimer t(c, st ? &st->ms_seed : nullptr);
+    c.dCounters.reserve(8);
+    size_t cap = std::max<size_t>(c.dMatches.cap, std::max<size_t>(1u << 20, static_cast<size_t>(nActive) * 64));
+    for (int attempt = 0; attempt < 3; ++attempt)
+    {
+        c.dMatches.reserve(cap);
+        LGPU_CUDA(cudaMemsetAsync(c.dCounters.p, 0, 8 * sizeof(unsigned long long), c.stream));
+        SeedParams P;
+        P.ix               = c.index->dev;
+        P.Q                = c.Q;
+        P.active           = dActive;
+        P.nActive          = nActive;
+        P.seedLength       = so.seed_length;
+        P.seedOffset       = so.seed_offset;
+        P.maxSeedDist      = so.max_seed_dist;
+        P.halfExact        = c.params.seed_half_exact;
+        P.adaptive         = c.params.adaptive_seeding;
+        P.maxMatches       = c.params.max_matches;
+        P.preScoring       = c.params.pre_scoring;
+        P.preScoringThresh = c.params.pre_scoring_thresh;
+        P.unknownRank      = c.di.unknownRank;
+        P.matrix           = c.dMatrix.p;
+        P.out              = c.dMatches.p;
+        P.cap              = c.dMatches.cap;
+        P.counters         = c.dCounters.p;
+        seedKernel<<<gridFor(nActive, 128), 128, 0, c.stream>>>(P);
+        LGPU_CUDA(cudaGetLastError());
+        if (st)
+            st->kernel_launches += 1;
+        unsigned long long cnt[3];
+        LGPU_CUDA(cudaMemcpyAsync(cnt, c.dCounters.p, sizeof(cnt), cudaMemcpyDeviceToHost, c.stream));
+        LGPU_CUDA(cudaStreamSynchronize(c.stream));
+        if (cnt[0] <= c.dMatches.cap)
+        {
+            if (st)
+            {
+                st->hits_after_seeding += cnt[1];
+                st->hits_failed_pre_extend += cnt[2];
+            }
+            return cnt[0];
+        }
+        cap = cnt[0]; // the buffer was too small: the count is exact, so one retry suffices
+    }
+    throw CudaError("seeding output buffer overflow");
+}
+
+// _widenAndPreprocessMatches on dIn[0..n); result in c.dMerged, returns the merged count
+static uint64_t runMerge(lgpu_ctx & c, lgpu_match const * dIn, uint64_t n, lgpu_stats * st)
+{
+    if (n == 0)
+        return 0;
+    if (n >= (1ull << 32))
+        throw CudaError("more than 2^32 seed matches in one batch; use smaller query batches");
+    StageTimer t(c, st ? &st->ms_sort_merge : nullptr);
+    c.dKey1.reserve(n);
+    c.dKey2.reserve(n);
+    c.dKey1b.reserve(n);
+    c.dKey2b.reserve(n);
+    c.dPerm.reserve(n);
+    c.dPermB.reserve(n);
+    c.dHead.reserve(n);
+    c.dScan.reserve(n);
+    unsigned int const g = gridFor(n, 256);
+    widenKernel<<<g, 256, 0, c.stream>>>(dIn, n, c.Q, c.index->dev, c.di.sbjNumFrames, c.dKey1.p, c.dKey2.p);
+    iotaKernel<<<g, 256, 0, c.stream>>>(c.dPerm.p, n);
+    // LSD: stable sort by the minor key (window start/end), then by the major key (qry, subj)
+    size_t tmp1 = 0, tmp2 = 0, tmp3 = 0;
+    int const nI = static_cast<int>(n);
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp1, c.dKey2.p, c.dKey2b.p, c.dPerm.p, c.dPermB.p, nI, 0, 64, c.stream);
+    cub::DeviceScan::InclusiveSum(nullptr, tmp3, c.dHead.p, c.dScan.p, nI, c.stream);
+    tmp2 = std::max(tmp1, tmp3);
+    c.dCubTemp.reserve(tmp2);
+    size_t tb = c.dCubTemp.cap;
+    LGPU_CUDA(cub::DeviceRadixSort::SortPairs(c.dCubTemp.p, tb, c.dKey2.p, c.dKey2b.p, c.dPerm.p, c.dPermB.p, nI, 0, 64,
+                                              c.stream));
+    gatherKernel<<<g, 256, 0, c.stream>>>(c.dKey1.p, c.dPermB.p, n, c.dKey1b.p); // key1 in minor-sorted order
+    tb = c.dCubTemp.cap;
+    // sort (key1b -> key1) carrying key2b -> key2
+    LGPU_CUDA(cub::DeviceRadixSort::SortPairs(c.dCubTemp.p, tb, c.dKey1b.p, c.dKey1.p, c.dKey2b.p, c.dKey2.p, nI, 0, 64,
+                                              c.stream));
+    chainHeadKernel<<<g, 256, 0, c.stream>>>(c.dKey1.p, c.dKey2.p, n, c.dHead.p);
+    tb = c.dCubTemp.cap;
+    LGPU_CUDA(cub::DeviceScan::InclusiveSum(c.dCubTemp.p, tb, c.dHead.p, c.dScan.p, nI, c.stream));
+    unsigned int nChains = 0;
+    LGPU_CUDA(cudaMemcpyAsync(&nChains, c.dScan.p + (n - 1), 4, cudaMemcpyDeviceToHost, c.stream));
+    LGPU_CUDA(cudaStreamSynchronize(c.stream));
+    c.dMerged.reserve(nChains);
+    chainEmitKernel<<<g, 256, 0, c.stream>>>(c.dKey1.p, c.dKey2.p, c.dHead.p, c.dScan.p, n, c.Q, c.dMerged.p);
+    LGPU_CUDA(cudaGetLastError());
+    if (st)
+    {
+        st->kernel_launches += 5 + 3; // ours + the three CUB primitives
+        st->hits_duplicate += n - nChains;
+    }
+    return nChains;
+}
+
+static int chooseK(unsigned int maxQ)
+{
+    unsigned int const k = (maxQ + 31) / 32;
+    if (k <= 4) return 4;
+    if (k <= 8) return 8;
+    if (k <= 12) return 12;
+    return 16;
+}
+
+template <bool TRACE>
+static void launchWavefront(int K, ExtParams const & P, unsigned int grid, cudaStream_t s)
+{
+    switch (K)
+    {
+        case 4: swWavefrontKernel<4, TRACE><<<grid, 128, 0, s>>>(P); break;
+        case 8: swWavefrontKernel<8, TRACE><<<grid, 128, 0, s>>>(P); break;
+        case 12: swWavefrontKernel<12, TRACE><<<grid, 128, 0, s>>>(P); break;
+        default: swWavefrontKernel<16, TRACE><<<grid, 128, 0, s>>>(P); break;
+    }
+}
+
+struct TaskDims
+{
+    unsigned int maxQ = 0, maxT = 0;
+    uint64_t     cells = 0;
+};
+
+// host copy of the task list (needed for trace-buffer layout and work statistics)
+static TaskDims taskDims(std::vector<lgpu_match> const & tasks)
+{
+    TaskDims d;
+    for (lgpu_match const & m : tasks)
+    {
+        unsigned int const nq = m.qry_end - m.qry_start, nt = m.subj_end - m.subj_start;
+        d.maxQ                = std::max(d.maxQ, nq);
+        d.maxT                = std::max(d.maxT, nt);
+        d.cells += static_cast<uint64_t>(nq) * nt;
+    }
+    return d;
+}
+
+static ExtParams baseExtParams(lgpu_ctx & c, lgpu_match const * dTasks, unsigned int n, unsigned int grid, TaskDims const & dims,
+                               int K)
+{
+    ExtParams P{};
+    P.ix          = c.index->dev;
+    P.Q           = c.Q;
+    P.tasks       = dTasks;
+    P.nTasks      = n;
+    P.sbjFrames   = c.di.sbjNumFrames;
+    P.matrix      = c.dMatrix.p;
+    P.go          = c.scoring.gapOpenSeqan;
+    P.ge          = c.scoring.gapExtend;
+    c.dWork.reserve(4);
+    P.workCounter = c.dWork.p;
+    P.maxRows     = std::max(dims.maxT, 1u);
+    if (dims.maxQ > static_cast<unsigned int>(32 * K))
+        c.dBoundary.reserve(static_cast<size_t>(grid) * 4 * P.maxRows);
+    else
+        c.dBoundary.reserve(1);
+    P.boundary = c.dBoundary.p;
+    return P;
+}
+
+// DP pass 1: scores into dScores[0..n)
+static void runScorePass(lgpu_ctx & c, lgpu_match const * dTasks, unsigned int n, TaskDims const & dims, int * dScores,
+                         lgpu_stats * st)
+{
+    if (n == 0)
+        return;
+    StageTimer         t(c, st ? &st->ms_extend_score : nullptr);
+    int const          K    = chooseK(dims.maxQ);
+    unsigned int const grid = std::min<unsigned int>((n + 3) / 4, static_cast<unsigned int>(c.numSMs) * 16);
+    ExtParams          P    = baseExtParams(c, dTasks, n, grid, dims, K);
+    P.scores                = dScores;
+    LGPU_CUDA(cudaMemsetAsync(c.dWork.p, 0, 4, c.stream));
+    launchWavefront<false>(K, P, grid, c.stream);
+    LGPU_CUDA(cudaGetLastError());
+    if (st)
+    {
+        st->kernel_launches += 1;
+        st->n_extensions_score += n;
+        st->cells_score += dims.cells;
+    }
+}
+
+// DP pass 2 + traceback for tasks (host copy `tasks`, device copy dTasks); hits appended to `out`
+static void runTracePass(lgpu_ctx & c, std::vector<lgpu_match> const & tasks, lgpu_match const * dTasks, lgpu_hit * hostOut,
+                         lgpu_stats * st)
+{
+    size_t const n = tasks.size();
+    if (n == 0)
+        return;
+    StageTimer     t(c, st ? &st->ms_extend_trace : nullptr);
+    TaskDims const dims = taskDims(tasks);
+    int const      K    = chooseK(dims.maxQ);
+    unsigned int const cols = 32 * K;
+    // chunk so that the trace matrices of one launch stay below ~4 GiB
+    constexpr uint64_t kMaxTraceBytes = 4ull << 30;
+    std::vector<unsigned long long> offs(n);
+    c.dScores2.reserve(n);
+    c.dBestPos.reserve(2 * n);
+    c.dTraceOff.reserve(n);
+    c.dHits.reserve(n);
+    size_t begin = 0;
+    while (begin < n)
+    {
+        uint64_t bytes = 0;
+        size_t   end   = begin;
+        while (end < n)
+        {
+            unsigned int const nq = tasks[end].qry_end - tasks[end].qry_start, nt = tasks[end].subj_end - tasks[end].subj_start;
+            uint64_t const     sz = static_cast<uint64_t>((nq + cols - 1) / cols * cols) * nt;
+            if (end > begin && bytes + sz > kMaxTraceBytes)
+                break;
+            offs[end] = bytes;
+            bytes += (sz + 15) / 16 * 16;
+            ++end;
+        }
+        unsigned int const cnt = static_cast<unsigned int>(end - begin);
+        c.dTrace.reserve(bytes);
+        LGPU_CUDA(cudaMemcpyAsync(c.dTraceOff.p, offs.data() + begin, cnt * 8ull, cudaMemcpyHostToDevice, c.stream));
+        unsigned int const grid = std::min<unsigned int>((cnt + 3) / 4, static_cast<unsigned int>(c.numSMs) * 16);
+        ExtParams          P    = baseExtParams(c, dTasks + begin, cnt, grid, dims, K);
+        P.scores                = c.dScores2.p;
+        P.bestPos               = c.dBestPos.p;
+        P.trace                 = c.dTrace.p;
+        P.traceOff              = c.dTraceOff.p;
+        LGPU_CUDA(cudaMemsetAsync(c.dWork.p, 0, 4, c.stream));
+        launchWavefront<true>(K, P, grid, c.stream);
+        LGPU_CUDA(cudaGetLastError());
+        TracebackParams TP{};
+        TP.ix           = c.index->dev;
+        TP.Q            = c.Q;
+        TP.tasks        = dTasks + begin;
+        TP.nTasks       = cnt;
+        TP.sbjFrames    = c.di.sbjNumFrames;
+        TP.domain       = c.params.domain;
+        TP.matrix       = c.dMatrix.p;
+        TP.scores       = c.dScores2.p;
+        TP.bestPos      = c.dBestPos.p;
+        TP.trace        = c.dTrace.p;
+        TP.traceOff     = c.dTraceOff.p;
+        TP.colsPerBlock = cols;
+        TP.out          = c.dHits.p;
+        tracebackKernel<<<gridFor(cnt, 128), 128, 0, c.stream>>>(TP);
+        LGPU_CUDA(cudaGetLastError());
+        LGPU_CUDA(cudaMemcpyAsync(hostOut + begin, c.dHits.p, cnt * sizeof(lgpu_hit), cudaMemcpyDeviceToHost, c.stream));
+        LGPU_CUDA(cudaStreamSynchronize(c.stream));
+        if (st)
+            st->kernel_launches += 2;
+        begin = end;
+    }
+    if (st)
+    {
+        st->n_extensions_trace += n;
+        st->cells_trace += dims.cells;
+    }
+}
+
+// iterateMatches for one phase: c.dMatches[0..nMatches) -> hits appended to c.hits
+static void runExtension(lgpu_ctx & c, uint64_t nMatches, uint8_t phase, EValueComputer & ev, lgpu_stats * st)
+{
+    uint64_t const nTasks = runMerge(c, c.dMatches.p, nMatches, st);
+    if (nTasks == 0)
+        return;
+    // the task list is small (16-24 B per alignment): keep a host copy for scheduling decisions
+    std::vector<lgpu_match> tasks(nTasks);
+    LGPU_CUDA(cudaMemcpyAsync(tasks.data(), c.dMerged.p, nTasks * sizeof(lgpu_match), cudaMemcpyDeviceToHost, c.stream));
+    LGPU_CUDA(cudaStreamSynchronize(c.stream));
+    TaskDims const dims = taskDims(tasks);
+    c.dScores.reserve(nTasks);
+    runScorePass(c, c.dMerged.p, static_cast<unsigned int>(nTasks), dims, c.dScores.p, st);
+
+    // filter on the device with per-query integer thresholds
+    c.dHead.reserve(nTasks);
+    c.dScan.reserve(nTasks);
+    c.dTasks2.reserve(nTasks);
+    LGPU_CUDA(cudaMemsetAsync(c.dCounters.p, 0, 8 * sizeof(unsigned long long), c.stream));
+    unsigned int const g = gridFor(nTasks, 256);
+    filterKernel<<<g, 256, 0, c.stream>>>(c.dMerged.p, c.dScores.p, static_cast<unsigned int>(nTasks), c.Q.F, c.dMinBit.p,
+                                          c.dMinEval.p, c.dHead.p, c.dCounters.p);
+    size_t tmp = 0;
+    cub::DeviceScan::InclusiveSum(nullptr, tmp, c.dHead.p, c.dScan.p, static_cast<int>(nTasks), c.stream);
+    c.dCubTemp.reserve(tmp);
+    size_t tb = c.dCubTemp.cap;
+    LGPU_CUDA(cub::DeviceScan::InclusiveSum(c.dCubTemp.p, tb, c.dHead.p, c.dScan.p, static_cast<int>(nTasks), c.stream));
+    compactKernel<<<g, 256, 0, c.stream>>>(c.dMerged.p, c.dHead.p, c.dScan.p, static_cast<unsigned int>(nTasks), c.dTasks2.p);
+    LGPU_CUDA(cudaGetLastError());
+    unsigned int       nKeep = 0;
+    unsigned long long cnt[2];
+    LGPU_CUDA(cudaMemcpyAsync(&nKeep, c.dScan.p + (nTasks - 1), 4, cudaMemcpyDeviceToHost, c.stream));
+    LGPU_CUDA(cudaMemcpyAsync(cnt, c.dCounters.p, sizeof(cnt), cudaMemcpyDeviceToHost, c.stream));
+    LGPU_CUDA(cudaStreamSynchronize(c.stream));
+    if (st)
+    {
+        st->kernel_launches += 3;
+        st->hits_failed_bitscore += cnt[0];
+        st->hits_failed_evalue += cnt[1];
+    }
+    if (nKeep == 0)
+        return;
+    std::vector<lgpu_match> keepTasks(nKeep);
+    LGPU_CUDA(cudaMemcpyAsync(keepTasks.data(), c.dTasks2.p, nKeep * sizeof(lgpu_match), cudaMemcpyDeviceToHost, c.stream));
+    LGPU_CUDA(cudaStreamSynchronize(c.stream));
+    size_t const base = c.hits.size();
+    c.hits.resize(base + nKeep);
+    runTracePass(c, keepTasks, c.dTasks2.p, c.hits.data() + base, st);
+
+    // host: doubles, identity cut-off (src/search_algo.hpp:1308-1322)
+    size_t out = base;
+    for (size_t i = base; i < base + nKeep; ++i)
+    {
+        lgpu_hit h = c.hits[i];
+        float const identity = static_cast<float>(100.0 * static_cast<float>(h.n_match) / static_cast<float>(h.aln_len));
+        if (identity < c.params.id_cutoff)
+        {
+            if (st)
+                ++st->hits_failed_identity;
+            continue;
+        }
+        h.phase     = phase;
+        h.bit_score = bitScore(c.scoring.ka, h.score);
+        h.evalue    = ev.evalue(h.score, h.q_len);
+        c.hits[out++] = h;
+    }
+    c.hits.resize(out);
+}
+
+static void setThresholds(lgpu_ctx & c, EValueComputer & ev)
+{
+    uint64_t const   n = c.nQueries;
+    std::vector<int> minBit(n), minEval(n);
+    std::unordered_map<uint64_t, ScoreThresholds> cache;
+    for (uint64_t q = 0; q < n; ++q)
+    {
+        uint64_t const len = c.qOffsHost[q + 1] - c.qOffsHost[q];
+        auto           it  = cache.find(len);
+        if (it == cache.end())
+            it = cache.emplace(len, scoreThresholds(c.params, ev, len)).first;
+        minBit[q]  = it->second.minBit;
+        minEval[q] = it->second.minEval;
+    }
+    c.dMinBit.reserve(n);
+    c.dMinEval.reserve(n);
+    LGPU_CUDA(cudaMemcpyAsync(c.dMinBit.p, minBit.data(), n * 4, cudaMemcpyHostToDevice, c.stream));
+    LGPU_CUDA(cudaMemcpyAsync(c.dMinEval.p, minEval.data(), n * 4, cudaMemcpyHostToDevice, c.stream));
+    LGPU_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+static void uploadActive(lgpu_ctx & c, std::vector<unsigned int> const & active)
+{
+    c.dActive.reserve(active.size());
+    LGPU_CUDA(cudaMemcpyAsync(c.dActive.p, active.data(), active.size() * 4, cudaMemcpyHostToDevice, c.stream));
+    LGPU_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+static void searchBatch(lgpu_ctx & c, lgpu_query_batch const & qb, lgpu_hits * out, lgpu_stats * st)
+{
+    LGPU_CUDA(cudaSetDevice(c.index->device));
+    cudaEventRecord(c.ev[2], c.stream);
+    c.hits.clear();
+    uploadQueries(c, qb, st);
+    if (c.nQueries)
+    {
+        EValueComputer ev(c.scoring.ka, c.index->dbTotalLength, c.di.qIsTranslated);
+        setThresholds(c, ev);
+        std::vector<unsigned int> active(c.nQueries);
+        for (uint64_t i = 0; i < c.nQueries; ++i)
+            active[i] = static_cast<unsigned int>(i);
+        uploadActive(c, active);
+        if (c.params.iterative_search)
+        {
+            uint64_t nM = runSeeding(c, c.params.opts0, c.dActive.p, static_cast<unsigned int>(active.size()), st);
+            runExtension(c, nM, 1, ev, st);
+            // iterativeSearchPre/Post: queries with at least one surviving hit are done
+            std::vector<uint8_t> ok(c.nQueries, 0);
+            for (lgpu_hit const & h : c.hits)
+                ok[h.q_id] = 1;
+            active.clear();
+            for (uint64_t i = 0; i < c.nQueries; ++i)
+                if (!ok[i])
+                    active.push_back(static_cast<unsigned int>(i));
+            if (!active.empty())
+            {
+                uploadActive(c, active);
+                nM = runSeeding(c, c.params.opts, c.dActive.p, static_cast<unsigned int>(active.size()), st);
+                runExtension(c, nM, 2, ev, st);
+            }
+        }
+        else
+        {
+            uint64_t const nM = runSeeding(c, c.params.opts, c.dActive.p, static_cast<unsigned int>(active.size()), st);
+            runExtension(c, nM, 2, ev, st);
+        }
+        lgpu_stats dummy{};
+        if (c.params.finalize)
+            finalizeRecords(c.hits, c.params.max_matches, st ? *st : dummy);
+    }
+    cudaEventRecord(c.ev[3], c.stream);
+    cudaEventSynchronize(c.ev[3]);
+    if (st)
+    {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c.ev[2], c.ev[3]);
+        st->ms_total += ms;
+    }
+    out->hits = c.hits.data();
+    out->n    = c.hits.size();
+}
+
+} // namespace lgpu
+
+// -------------------------------------------------------------------------------------------------
+// C ABI
+// -------------------------------------------------------------------------------------------------
+
+template <typename F>
+static int guarded(std::string * err, F && f)
+{
+    try
+    {
+        f();
+        return LGPU_OK;
+    }
+    catch (LbaError const & e)
+    {
+        (err ? *err : g_lastError) = e.what();
+        g_lastError                = e.what();
+        return LGPU_ERR_IO;
+    }
+    catch (CudaError const & e)
+    {
+        (err ? *err : g_lastError) = e.what();
+        g_lastError                = e.what();
+        return LGPU_ERR_CUDA;
+    }
+    catch (ArgError const & e)
+    {
+        (err ? *err : g_lastError) = e.what();
+        g_lastError                = e.what();
+        return LGPU_ERR_ARG;
+    }
+    catch (UnsupportedError const & e)
+    {
+        (err ? *err : g_lastError) = e.what();
+        g_lastError                = e.what();
+        return LGPU_ERR_UNSUPPORTED;
+    }
+    catch (std::exception const & e)
+    {
+        (err ? *err : g_lastError) = e.what();
+        g_lastError                = e.what();
+        return LGPU_ERR_INTERNAL;
+    }
+}
+
+extern "C"
+{
+
+int lgpu_version(void) { return LGPU_VERSION; }
+
+int lgpu_lba_open(lgpu_lba ** out, char const * path)
+{
+    if (!out || !path)
+        return LGPU_ERR_ARG;
+    *out = nullptr;
+    return guarded(nullptr, [&] {
+        auto l  = std::make_unique<lgpu_lba>();
+        l->file = std::make_unique<LbaFile>(path);
+        *out    = l.release();
+    });
+}
+
+lgpu_index_desc const * lgpu_lba_desc(lgpu_lba const * l) { return l ? &l->file->desc : nullptr; }
+
+void lgpu_lba_close(lgpu_lba * l) { delete l; }
+
+int lgpu_index_create(lgpu_index ** out, lgpu_index_desc const * d, int device)
+{
+    if (!out || !d)
+        return LGPU_ERR_ARG;
+    *out = nullptr;
+    return guarded(nullptr, [&] {
+        if (d->index_type != LGPU_INDEX_FM)
+            throw UnsupportedError("only unidirectional FM indexes are supported");
+        if (d->sigma < 2 || d->sigma > 31 || d->sigma_bits > 5)
+            throw ArgError("bad alphabet size in index descriptor");
+        int nDev = 0;
+        if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0)
+            throw CudaError("no CUDA device available (lambda_b200 has no CPU fallback)");
+        LGPU_CUDA(cudaSetDevice(device));
+        auto ix    = std::make_unique<lgpu_index>();
+        ix->device = device;
+        auto up    = [&](void const * p, uint64_t bytes) -> void * {
+            void * dp = uploadNew(static_cast<unsigned char const *>(p), bytes);
+            ix->allocs.push_back(dp);
+            ix->bytes += bytes;
+            return dp;
+        };
+        DevIndex & dv  = ix->dev;
+        dv.occ         = static_cast<unsigned char const *>(up(d->occ_blocks, d->n_blocks * d->block_bytes));
+        dv.super       = static_cast<unsigned long long const *>(up(d->super_blocks, d->n_super * d->sigma * 8));
+        dv.ssa         = static_cast<unsigned long long const *>(up(d->ssa, d->n_ssa * 8));
+        dv.csa         = static_cast<CsaSuperDev const *>(up(d->csa_bv, d->n_csa_sb * 48));
+        dv.seqs        = static_cast<unsigned char const *>(up(d->seqs, d->n_residues));
+        dv.seqDelims   = static_cast<unsigned long long const *>(up(d->seq_delims, (d->n_seqs + 1) * 8));
+        dv.nSeqs       = d->n_seqs;
+        dv.nRows       = d->C[d->sigma];
+        dv.bitsForPos  = static_cast<unsigned int>(d->bits_for_position);
+        dv.posMask     = (1ull << d->bits_for_position) - 1;
+        dv.blockBytes  = d->block_bytes;
+        dv.planesOff   = d->planes_offset;
+        dv.sigma       = d->sigma;
+        dv.sigmaBits   = d->sigma_bits;
+        dv.singleSuper = d->n_super == 1;
+        for (unsigned int s = 0; s < 32; ++s)
+            dv.Cbase[s] = 0;
+        for (unsigned int s = 0; s < d->sigma; ++s)
+            dv.Cbase[s] = d->C[s] + (dv.singleSuper ? d->super_blocks[s] : 0);
+        ix->meta              = *d;
+        ix->meta.occ_blocks   = nullptr;
+        ix->meta.super_blocks = nullptr;
+        ix->meta.C            = nullptr;
+        ix->meta.ssa          = nullptr;
+        ix->meta.csa_bv       = nullptr;
+        ix->meta.seqs         = nullptr;
+        ix->meta.seq_delims   = nullptr;
+        ix->meta.ids          = nullptr;
+        ix->meta.id_delims    = nullptr;
+        ix->seqDelimsHost.assign(d->seq_delims, d->seq_delims + d->n_seqs + 1);
+        // dbTotalLength = sum of reduced subject lengths (src/search_algo.hpp:317-318)
+        ix->dbTotalLength = d->n_residues * (d->red_alph == LGPU_ALPH_DNA3BS ? 2 : 1);
+        LGPU_CUDA(cudaDeviceSynchronize());
+        *out = ix.release();
+    });
+}
+
+void lgpu_index_destroy(lgpu_index * ix) { delete ix; }
+
+uint64_t lgpu_index_device_bytes(lgpu_index const * ix) { return ix ? ix->bytes : 0; }
+uint64_t lgpu_index_db_total_length(lgpu_index const * ix) { return ix ? ix->dbTotalLength : 0; }
+uint64_t lgpu_index_db_num_seqs(lgpu_index const * ix) { return ix ? ix->meta.n_seqs : 0; }
+
+int lgpu_params_default(lgpu_params * out, uint32_t domain, char const * profile)
+{
+    if (!out)
+        return LGPU_ERR_ARG;
+    return paramsDefault(*out, domain, profile);
+}
+
+int lgpu_ctx_create(lgpu_ctx ** out, lgpu_index const * ix, lgpu_params const * p)
+{
+    if (!out || !ix || !p)
+        return LGPU_ERR_ARG;
+    *out = nullptr;
+    return guarded(nullptr, [&] {
+        checkParams(*p, ix->meta);
+        auto c    = std::make_unique<lgpu_ctx>();
+        c->index  = ix;
+        c->params = *p;
+        c->di     = domainInfo(p->domain);
+        int rc    = makeScoring(c->scoring, *p);
+        if (rc == LGPU_ERR_ARG)
+            throw ArgError("Could not compute Karlin-Altschul-Values for Scoring Scheme.");
+        if (rc != LGPU_OK)
+            throw UnsupportedError("unsupported scoring configuration");
+        LGPU_CUDA(cudaSetDevice(ix->device));
+        LGPU_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        for (auto & e : c->ev)
+            LGPU_CUDA(cudaEventCreate(&e));
+        LGPU_CUDA(cudaDeviceGetAttribute(&c->numSMs, cudaDevAttrMultiProcessorCount, ix->device));
+        c->dMatrix.reserve(1024);
+        LGPU_CUDA(cudaMemcpy(c->dMatrix.p, c->scoring.matrix, 1024, cudaMemcpyHostToDevice));
+        c->dCounters.reserve(8);
+        *out = c.release();
+    });
+}
+
+void lgpu_ctx_destroy(lgpu_ctx * c) { delete c; }
+
+char const * lgpu_last_error(lgpu_ctx const * c) { return (c && !c->err.empty()) ? c->err.c_str() : g_lastError.c_str(); }
+
+int lgpu_search_batch(lgpu_ctx * c, lgpu_query_batch const * q, lgpu_hits * out, lgpu_stats * stats)
+{
+    if (!c || !q || !out)
+        return LGPU_ERR_ARG;
+    return guarded(&c->err, [&] { searchBatch(*c, *q, out, stats); });
+}
+
+int lgpu_seed_batch(lgpu_ctx * c, lgpu_query_batch const * q, int phase, lgpu_match const ** matches, uint64_t * n,
+                    lgpu_stats * stats)
+{
+    if (!c || !q || !matches || !n || (phase != 1 && phase != 2))
+        return LGPU_ERR_ARG;
+    return guarded(&c->err, [&] {
+        LGPU_CUDA(cudaSetDevice(c->index->device));
+        uploadQueries(*c, *q, stats);
+        std::vector<unsigned int> active(c->nQueries);
+        for (uint64_t i = 0; i < c->nQueries; ++i)
+            active[i] = static_cast<unsigned int>(i);
+        uploadActive(*c, active);
+        uint64_t const nM = runSeeding(*c, phase == 1 ? c->params.opts0 : c->params.opts, c->dActive.p,
+                                       static_cast<unsigned int>(active.size()), stats);
+        c->matchesHost.resize(nM);
+        if (nM)
+            LGPU_CUDA(cudaMemcpyAsync(c->matchesHost.data(), c->dMatches.p, nM * sizeof(lgpu_match), cudaMemcpyDeviceToHost,
+                                      c->stream));
+        LGPU_CUDA(cudaStreamSynchronize(c->stream));
+        *matches = c->matchesHost.data();
+        *n       = nM;
+    });
+}
+
+int lgpu_merge_matches(lgpu_ctx * c, lgpu_query_batch const * q, lgpu_match const * in, uint64_t nIn,
+                       lgpu_match const ** merged, uint64_t * nMerged, lgpu_stats * stats)
+{
+    if (!c || !q || !merged || !nMerged || (nIn && !in))
+        return LGPU_ERR_ARG;
+    return guarded(&c->err, [&] {
+        LGPU_CUDA(cudaSetDevice(c->index->device));
+        uploadQueries(*c, *q, stats);
+        c->dUserMatches.reserve(nIn);
+        if (nIn)
+            LGPU_CUDA(cudaMemcpyAsync(c->dUserMatches.p, in, nIn * sizeof(lgpu_match), cudaMemcpyHostToDevice, c->stream));
+        uint64_t const nOut = runMerge(*c, c->dUserMatches.p, nIn, stats);
+        c->matchesHost.resize(nOut);
+        if (nOut)
+            LGPU_CUDA(cudaMemcpyAsync(c->matchesHost.data(), c->dMerged.p, nOut * sizeof(lgpu_match), cudaMemcpyDeviceToHost,
+                                      c->stream));
+        LGPU_CUDA(cudaStreamSynchronize(c->stream));
+        *merged  = c->matchesHost.data();
+        *nMerged = nOut;
+    });
+}
+
+static void checkWindows(lgpu_ctx & c, lgpu_match const * w, uint64_t n)
+{
+    for (uint64_t i = 0; i < n; ++i)
+    {
+        uint64_t const q = w[i].qry_id / c.di.qryNumFrames;
+        if (q >= c.nQueries || w[i].subj_id / c.di.sbjNumFrames >= c.index->meta.n_seqs)
+            throw ArgError("window refers to a query/subject that does not exist");
+        uint64_t const qLen = c.qOffsHost[q + 1] - c.qOffsHost[q];
+        uint64_t const sId  = w[i].subj_id / c.di.sbjNumFrames;
+        uint64_t const sLen = c.index->seqDelimsHost[sId + 1] - c.index->seqDelimsHost[sId];
+        if (w[i].qry_start > w[i].qry_end || w[i].qry_end > qLen || w[i].subj_start > w[i].subj_end ||
+            w[i].subj_end > sLen)
+            throw ArgError("window coordinates out of range");
+    }
+}
+
+int lgpu_extend_scores(lgpu_ctx * c, lgpu_query_batch const * q, lgpu_match const * win, uint64_t n, int32_t * scores,
+                       lgpu_stats * stats)
+{
+    if (!c || !q || (n && (!win || !scores)))
+        return LGPU_ERR_ARG;
+    return guarded(&c->err, [&] {
+        LGPU_CUDA(cudaSetDevice(c->index->device));
+        uploadQueries(*c, *q, stats);
+        if (n == 0)
+            return;
+        checkWindows(*c, win, n);
+        std::vector<lgpu_match> tasks(win, win + n);
+        c->dUserMatches.reserve(n);
+        LGPU_CUDA(cudaMemcpyAsync(c->dUserMatches.p, win, n * sizeof(lgpu_match), cudaMemcpyHostToDevice, c->stream));
+        c->dScores.reserve(n);
+        runScorePass(*c, c->dUserMatches.p, static_cast<unsigned int>(n), taskDims(tasks), c->dScores.p, stats);
+        LGPU_CUDA(cudaMemcpyAsync(scores, c->dScores.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+        LGPU_CUDA(cudaStreamSynchronize(c->stream));
+    });
+}
+
+int lgpu_extend_trace(lgpu_ctx * c, lgpu_query_batch const * q, lgpu_match const * win, uint64_t n, lgpu_hit * out,
+                      lgpu_stats * stats)
+{
+    if (!c || !q || (n && (!win || !out)))
+        return LGPU_ERR_ARG;
+    return guarded(&c->err, [&] {
+        LGPU_CUDA(cudaSetDevice(c->index->device));
+        uploadQueries(*c, *q, stats);
+        if (n == 0)
+            return;
+        checkWindows(*c, win, n);
+        std::vector<lgpu_match> tasks(win, win + n);
+        c->dUserMatches.reserve(n);
+        LGPU_CUDA(cudaMemcpyAsync(c->dUserMatches.p, win, n * sizeof(lgpu_match), cudaMemcpyHostToDevice, c->stream));
+        runTracePass(*c, tasks, c->dUserMatches.p, out, stats);
+    });
+}
+
+int lgpu_fm_rank(lgpu_index const * ix, uint64_t const * idx, uint8_t const * symb, uint64_t n, uint64_t * out)
+{
+    if (!ix || (n && (!idx || !symb || !out)))
+        return LGPU_ERR_ARG;
+    return guarded(nullptr, [&] {
+        LGPU_CUDA(cudaSetDevice(ix->device));
+        for (uint64_t i = 0; i < n; ++i)
+            if (idx[i] > ix->dev.nRows || symb[i] >= ix->dev.sigma)
+                throw ArgError("rank query out of range");
+        DevBuf<unsigned long long> dIdx, dOut;
+        DevBuf<unsigned char>      dSym;
+        dIdx.reserve(n);
+        dOut.reserve(n);
+        dSym.reserve(n);
+        LGPU_CUDA(cudaMemcpy(dIdx.p, idx, n * 8, cudaMemcpyHostToDevice));
+        LGPU_CUDA(cudaMemcpy(dSym.p, symb, n, cudaMemcpyHostToDevice));
+        fmRankKernel<<<gridFor(n, 128), 128>>>(ix->dev, dIdx.p, dSym.p, n, dOut.p);
+        LGPU_CUDA(cudaGetLastError());
+        LGPU_CUDA(cudaMemcpy(out, dOut.p, n * 8, cudaMemcpyDeviceToHost));
+    });
+}
+
+int lgpu_fm_locate(lgpu_index const * ix, uint64_t const * rows, uint64_t n, uint64_t * subj, uint64_t * pos)
+{
+    if (!ix || (n && (!rows || !subj || !pos)))
+        return LGPU_ERR_ARG;
+    return guarded(nullptr, [&] {
+        LGPU_CUDA(cudaSetDevice(ix->device));
+        for (uint64_t i = 0; i < n; ++i)
+            if (rows[i] >= ix->dev.nRows)
+                throw ArgError("locate row out of range");
+        DevBuf<unsigned long long> dRows, dSubj, dPos;
+        dRows.reserve(n);
+        dSubj.reserve(n);
+        dPos.reserve(n);
+        LGPU_CUDA(cudaMemcpy(dRows.p, rows, n * 8, cudaMemcpyHostToDevice));
+        fmLocateKernel<<<gridFor(n, 128), 128>>>(ix->dev, dRows.p, n, dSubj.p, dPos.p);
+        LGPU_CUDA(cudaGetLastError());
+        LGPU_CUDA(cudaMemcpy(subj, dSubj.p, n * 8, cudaMemcpyDeviceToHost));
+        LGPU_CUDA(cudaMemcpy(pos, dPos.p, n * 8, cudaMemcpyDeviceToHost));
+    });
+}
+
+int lgpu_bit_score(lgpu_params const * p, int32_t raw, double * out)
+{
+    if (!p || !out)
+        return LGPU_ERR_ARG;
+    KarlinAltschul const ka = selectKA(*p);
+    if (!ka.valid)
+        return LGPU_ERR_ARG;
+    *out = bitScore(ka, raw);
+    return LGPU_OK;
+}
+
+int lgpu_evalue(lgpu_params const * p, int32_t raw, uint64_t qLen, uint64_t dbLen, double * out)
+{
+    if (!p || !out)
+        return LGPU_ERR_ARG;
+    KarlinAltschul const ka = selectKA(*p);
+    if (!ka.valid)
+        return LGPU_ERR_ARG;
+    EValueComputer ev(ka, dbLen, domainInfo(p->domain).qIsTranslated);
+    *out = ev.evalue(raw, qLen);
+    return LGPU_OK;
+}
+
+int lgpu_min_raw_score(lgpu_params const * p, uint64_t qLen, uint64_t dbLen, int32_t * out)
+{
+    if (!p || !out)
+        return LGPU_ERR_ARG;
+    KarlinAltschul const ka = selectKA(*p);
+    if (!ka.valid)
+        return LGPU_ERR_ARG;
+    EValueComputer        ev(ka, dbLen, domainInfo(p->domain).qIsTranslated);
+    ScoreThresholds const t = scoreThresholds(*p, ev, qLen);
+    *out                    = std::max(t.minBit, t.minEval);
+    return LGPU_OK;
+}
+
+int lgpu_format_m8(lgpu_params const * p, lgpu_hit const * h, char const * qId, char const * sId, char * buf, size_t cap)
+{
+    if (!p || !h || !qId || !sId || !buf)
+        return LGPU_ERR_ARG;
+    return formatM8(p->domain, *h, qId, std::strlen(qId), sId, std::strlen(sId), buf, cap);
+}
+
+} // extern "C"

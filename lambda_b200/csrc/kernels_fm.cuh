@@ -1,0 +1,479 @@
+// FM-index primitives and the seeding kernel (sm_100a).
+//
+// Device restatement of
+//   rank            FMC occtable/InterleavedEPRV2.h:81-86,211-216
+//   extendRight     FMC ReverseFMIndexCursor.h:30-34
+//   rank_symbol     FMC occtable/InterleavedEPRV2.h:121-138,264-270
+//   CSA / bitvector FMC CSA.h:104-113, BitvectorCompact.h:26-72
+//   locate          FMC ReverseFMIndex.h:62-91, locate.h:28-35
+//   search()        reference src/search_algo.hpp:607-762 (+ searchHalfExactImpl :538-604,
+//                   seedLooksPromising :427-481)
+//
+// Work decomposition: seeding has a serial dependency inside one query (`hitsThisSeq` steers the
+// adaptive seed elongation of every later seed, search_algo.hpp:695-703), so the unit of
+// parallelism is the query: one thread walks one query's frames/seeds in the reference's order.
+// The index (GBs) lives in HBM; every LF step is two dependent random block reads, so throughput
+// comes from the >10^5 independent chains in flight, not from bandwidth.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/lambda_b200.h"
+
+namespace lgpu
+{
+
+struct CsaSuperDev
+{
+    unsigned long long entry;
+    unsigned char      blocks[4];
+    unsigned char      pad[4];
+    unsigned long long bits[4];
+};
+static_assert(sizeof(CsaSuperDev) == 48, "csa superblock layout");
+
+struct DevIndex
+{
+    unsigned char const *      occ;
+    unsigned long long const * super;
+    unsigned long long const * ssa;
+    CsaSuperDev const *        csa;
+    unsigned char const *      seqs;
+    unsigned long long const * seqDelims;
+    unsigned long long         nSeqs;
+    unsigned long long         nRows;      // C[sigma] = length of the BWT
+    unsigned long long         posMask;
+    unsigned int               bitsForPos;
+    unsigned int               blockBytes, planesOff, sigma, sigmaBits;
+    unsigned int               singleSuper; // 1: only one super block -> folded into Cbase
+    unsigned long long         Cbase[32];   // C[s] (+ superBlocks[0][s] if singleSuper)
+};
+
+__device__ __forceinline__ unsigned long long ldg64(void const * p)
+{
+    return __ldg(reinterpret_cast<unsigned long long const *>(p));
+}
+
+__device__ __forceinline__ unsigned long long fmSymbolMask(DevIndex const & ix, unsigned char const * b, unsigned int symb)
+{
+    unsigned long long mask = ~0ull;
+#pragma unroll
+    for (unsigned int p = 0; p < 5; ++p)
+        if (p < ix.sigmaBits)
+        {
+            unsigned long long const plane = ldg64(b + ix.planesOff + 8 * p);
+            mask &= ((symb >> p) & 1u) ? plane : ~plane;
+        }
+    return mask;
+}
+
+__device__ __forceinline__ unsigned long long fmRank(DevIndex const & ix, unsigned long long idx, unsigned int symb)
+{
+    unsigned char const *    b    = ix.occ + (idx >> 6) * ix.blockBytes;
+    unsigned int const       cnt  = __ldg(reinterpret_cast<unsigned int const *>(b) + symb);
+    unsigned long long const mask = fmSymbolMask(ix, b, symb);
+    unsigned int const       bit  = static_cast<unsigned int>(idx) & 63u;
+    // std::bitset<64> << 64 yields 0 in the reference; a 64-bit shift by 64 would be undefined here
+    unsigned int const pc = bit ? __popcll(mask << (64u - bit)) : 0u;
+    unsigned long long r  = static_cast<unsigned long long>(cnt) + pc + ix.Cbase[symb];
+    if (!ix.singleSuper)
+        r += __ldg(ix.super + (idx >> 32) * ix.sigma + symb);
+    return r;
+}
+
+// one LF step from BWT row idx: rank of the symbol found at idx
+__device__ __forceinline__ unsigned long long fmRankSymbol(DevIndex const & ix, unsigned long long idx)
+{
+    unsigned char const * b    = ix.occ + (idx >> 6) * ix.blockBytes;
+    unsigned int const    bit  = static_cast<unsigned int>(idx) & 63u;
+    unsigned int          symb = 0;
+    unsigned long long    mask = ~0ull;
+#pragma unroll
+    for (unsigned int p = 0; p < 5; ++p)
+        if (p < ix.sigmaBits)
+        {
+            unsigned long long const plane = ldg64(b + ix.planesOff + 8 * p);
+            unsigned int const       v     = static_cast<unsigned int>(plane >> bit) & 1u;
+            symb |= v << p;
+            mask &= v ? plane : ~plane;
+        }
+    unsigned int const cnt = __ldg(reinterpret_cast<unsigned int const *>(b) + symb);
+    unsigned int const pc  = bit ? __popcll(mask << (64u - bit)) : 0u;
+    unsigned long long r   = static_cast<unsigned long long>(cnt) + pc + ix.Cbase[symb];
+    if (!ix.singleSuper)
+        r += __ldg(ix.super + (idx >> 32) * ix.sigma + symb);
+    return r;
+}
+
+__device__ __forceinline__ void fmLocate(DevIndex const & ix, unsigned long long row, unsigned long long & subj,
+                                         unsigned long long & pos)
+{
+    unsigned long long steps = 0;
+    for (;;)
+    {
+        unsigned long long const i  = row + 1; // bit i of the vector is stored at position i + 1
+        CsaSuperDev const *      sb = ix.csa + (i >> 8);
+        unsigned long long const w  = ldg64(&sb->bits[(i & 255u) >> 6]);
+        if ((w >> (i & 63u)) & 1ull)
+            break;
+        row = fmRankSymbol(ix, row);
+        ++steps;
+    }
+    CsaSuperDev const *      sb  = ix.csa + (row >> 8);
+    unsigned int const       blk = static_cast<unsigned int>(row & 255u) >> 6;
+    unsigned int const       bit = static_cast<unsigned int>(row) & 63u;
+    unsigned long long const w   = ldg64(&sb->bits[blk]);
+    unsigned long long const r   = ldg64(&sb->entry) + __ldg(&sb->blocks[blk]) + __popcll(w << (63u - bit));
+    unsigned long long const v   = __ldg(ix.ssa + r);
+    subj                         = v >> ix.bitsForPos;
+    pos                          = (v & ix.posMask) - steps;
+}
+
+struct Cursor
+{
+    unsigned long long lb, len;
+};
+
+__device__ __forceinline__ Cursor fmExtendRight(DevIndex const & ix, Cursor c, unsigned int symb)
+{
+    unsigned long long const lb = fmRank(ix, c.lb, symb);
+    Cursor                   n;
+    n.lb  = lb;
+    n.len = fmRank(ix, c.lb + c.len, symb) - lb;
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// known-answer test kernels
+// ---------------------------------------------------------------------------------------------
+
+__global__ void fmRankKernel(DevIndex ix, unsigned long long const * idx, unsigned char const * symb, unsigned long long n,
+                             unsigned long long * out)
+{
+    unsigned long long const i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+    if (i < n)
+        out[i] = fmRank(ix, idx[i], symb[i]);
+}
+
+__global__ void fmLocateKernel(DevIndex ix, unsigned long long const * rows, unsigned long long n, unsigned long long * subj,
+                               unsigned long long * pos)
+{
+    unsigned long long const i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+    if (i < n)
+        fmLocate(ix, rows[i], subj[i], pos[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// query preparation: frames (reverse complement) and alphabet reduction
+// ---------------------------------------------------------------------------------------------
+
+// Frame-expanded layout: frame f of query q starts at F * offs[q] + f * len(q).
+struct DevQueries
+{
+    unsigned char const *      orig;  // original ranks
+    unsigned long long const * offs;  // n + 1
+    unsigned char *            trans; // F * total
+    unsigned char *            red;   // F * total
+    unsigned int               n, F;
+    unsigned char              redTab[32];
+    unsigned char              compTab[8];
+};
+
+__global__ void prepQueriesKernel(DevQueries Q)
+{
+    // one block per query keeps the index math trivial; residues are strided over the block
+    for (unsigned int q = blockIdx.x; q < Q.n; q += gridDim.x)
+    {
+        unsigned long long const b   = Q.offs[q];
+        unsigned int const       len = static_cast<unsigned int>(Q.offs[q + 1] - b);
+        for (unsigned int f = 0; f < Q.F; ++f)
+        {
+            unsigned long long const o = Q.F * b + static_cast<unsigned long long>(f) * len;
+            for (unsigned int k = threadIdx.x; k < len; k += blockDim.x)
+            {
+                // frame 0 = forward, frame 1 = reverse complement (bio::views::add_reverse_complement)
+                unsigned char const r = (f & 1u) ? Q.compTab[Q.orig[b + len - 1 - k]] : Q.orig[b + k];
+                Q.trans[o + k]        = r;
+                Q.red[o + k]          = Q.redTab[r];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// seeding
+// ---------------------------------------------------------------------------------------------
+
+struct SeedParams
+{
+    DevIndex             ix;
+    DevQueries           Q;
+    unsigned int const * active; // list of query ids to seed
+    unsigned int         nActive;
+    unsigned int         seedLength, seedOffset, maxSeedDist, halfExact, adaptive;
+    unsigned int         maxMatches;
+    int                  preScoring;
+    double               preScoringThresh;
+    unsigned int         unknownRank;
+    signed char const *  matrix; // 32 x 32 int8, translated-alphabet ranks
+    lgpu_match *         out;
+    unsigned long long   cap;
+    unsigned long long * counters; // [0] matches emitted, [1] hitsAfterSeeding, [2] hitsFailedPreExtendTest
+};
+
+constexpr int kMaxHalf2 = 16; // longest supported second seed half (seed length <= 32)
+
+__global__ void __launch_bounds__(128) seedKernel(SeedParams P)
+{
+    __shared__ signed char sM[1024];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x)
+        sM[i] = P.matrix[i];
+    __syncthreads();
+
+    unsigned int const t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P.nActive)
+        return;
+    unsigned int const       q    = P.active[t];
+    DevIndex const &         ix   = P.ix;
+    unsigned int const       F    = P.Q.F;
+    unsigned long long const qb   = P.Q.offs[q];
+    unsigned int const       len  = static_cast<unsigned int>(P.Q.offs[q + 1] - qb);
+    unsigned int const       L    = P.seedLength;
+    unsigned int const       redN = ix.sigma - 1;
+
+    unsigned long long nAfter = 0, nFailed = 0;
+    if (len >= L) // all frames of a query have the same length in the supported (non-translated) modes
+    {
+        unsigned long long       hitsThisSeq = 0;
+        unsigned long long const needlesSum  = static_cast<unsigned long long>(F) * len;
+        unsigned long long       needlesPos  = 0;
+        bool const               half        = P.halfExact && P.maxSeedDist != 0;
+        unsigned int const       h1          = half ? L / 2 : L;
+        unsigned int const       n2          = L - h1;
+
+        for (unsigned int f = 0; f < F; ++f)
+        {
+            unsigned int const    qryId = q * F + f;
+            unsigned char const * trans = P.Q.trans + F * qb + static_cast<unsigned long long>(f) * len;
+            unsigned char const * red   = P.Q.red + F * qb + static_cast<unsigned long long>(f) * len;
+
+            for (unsigned int seedBegin = 0;; seedBegin += P.seedOffset)
+            {
+                while (seedBegin < len - L &&
+                       (trans[seedBegin] == P.unknownRank || trans[seedBegin] == trans[seedBegin + 1]))
+                    ++seedBegin;
+                if (seedBegin > len - L)
+                    break;
+
+                // exact chain E[0..K]: E[0] = cursor after the exactly matched first half
+                Cursor E[kMaxHalf2 + 1];
+                int    K = -1;
+                {
+                    Cursor c;
+                    c.lb  = 0;
+                    c.len = ix.nRows;
+                    bool ok = true;
+                    for (unsigned int i = 0; i < h1; ++i)
+                    {
+                        c = fmExtendRight(ix, c, red[seedBegin + i] + 1u);
+                        if (c.len == 0)
+                        {
+                            ok = false;
+                            break;
+                        }
+                    }
+                    if (ok)
+                    {
+                        E[0] = c;
+                        K    = 0;
+                        for (unsigned int i = 0; i < n2; ++i)
+                        {
+                            c = fmExtendRight(ix, c, red[seedBegin + h1 + i] + 1u);
+                            if (c.len == 0)
+                                break;
+                            E[i + 1] = c;
+                            K        = static_cast<int>(i) + 1;
+                        }
+                    }
+                }
+                if (K < 0)
+                    continue;
+
+                // Enumerate the half-exact cursors in the reference's BFS order (= leaf order of the
+                // search tree): mismatches below the seed symbol per level going down, the exact
+                // cursor, then mismatches above the seed symbol per level going back up.
+                int const    kMax  = (K < static_cast<int>(n2) - 1) ? K : static_cast<int>(n2) - 1;
+                int          stage = 0, lvl = 0;
+                unsigned int r     = 0;
+                for (;;)
+                {
+                    Cursor cursor;
+                    bool   have = false;
+                    while (!have)
+                    {
+                        if (stage == 0)
+                        {
+                            if (lvl > kMax)
+                            {
+                                stage = 1;
+                                continue;
+                            }
+                            unsigned int const want = red[seedBegin + h1 + lvl];
+                            if (r >= want)
+                            {
+                                ++lvl;
+                                r = 0;
+                                continue;
+                            }
+                        }
+                        else if (stage == 1)
+                        {
+                            stage = 2;
+                            lvl   = kMax;
+                            r     = (lvl >= 0) ? red[seedBegin + h1 + lvl] + 1u : 0u;
+                            if (K == static_cast<int>(n2))
+                            {
+                                cursor = E[n2];
+                                have   = true;
+                            }
+                            continue;
+                        }
+                        else
+                        {
+                            if (lvl < 0)
+                                break;
+                            if (r >= redN)
+                            {
+                                --lvl;
+                                r = (lvl >= 0) ? red[seedBegin + h1 + lvl] + 1u : 0u;
+                                continue;
+                            }
+                        }
+                        // mismatch r at level lvl, then the rest of the seed exactly
+                        Cursor c = fmExtendRight(ix, E[lvl], r + 1u);
+                        ++r;
+                        for (unsigned int l = lvl + 1; c.len != 0 && l < n2; ++l)
+                            c = fmExtendRight(ix, c, red[seedBegin + h1 + l] + 1u);
+                        if (c.len != 0)
+                        {
+                            cursor = c;
+                            have   = true;
+                        }
+                    }
+                    if (!have)
+                        break;
+
+                    // ---- adaptive elongation (search_algo.hpp:679-726) ----
+                    unsigned int seedLen = L;
+                    if (P.adaptive)
+                    {
+                        unsigned long long desired = 1;
+                        if (hitsThisSeq < P.maxMatches)
+                        {
+                            unsigned long long remaining = (needlesSum - needlesPos - seedBegin) / P.seedOffset;
+                            if (remaining < 1)
+                                remaining = 1;
+                            desired = (P.maxMatches - hitsThisSeq) * 10ull / remaining;
+                            if (desired == 0)
+                                desired = 1;
+                        }
+                        unsigned long long oldCount = cursor.len;
+                        while (seedBegin + seedLen < len)
+                        {
+                            Cursor const n = fmExtendRight(ix, cursor, red[seedBegin + seedLen] + 1u);
+                            if (n.len < desired && n.len < oldCount)
+                                break; // keep the previous cursor
+                            cursor   = n;
+                            oldCount = n.len;
+                            ++seedLen;
+                        }
+                    }
+                    // over-abundant seeds are dropped (search_algo.hpp:729)
+                    if (cursor.len > 10ull * P.maxMatches)
+                        continue;
+
+                    // ---- locate + pre-scoring ----
+                    for (unsigned long long row = cursor.lb; row < cursor.lb + cursor.len; ++row)
+                    {
+                        unsigned long long subj, pos;
+                        fmLocate(ix, row, subj, pos);
+                        pos -= seedLen; // the reversed-text cursor reports the seed's end
+                        ++nAfter;
+
+                        // seedLooksPromising
+                        long long                qB     = seedBegin;
+                        long long                sB     = static_cast<long long>(pos);
+                        unsigned long long const actual = seedLen;
+                        unsigned long long       eff    = static_cast<unsigned long long>(L * P.preScoring);
+                        if (eff < actual)
+                            eff = actual;
+                        unsigned long long const sBase = __ldg(ix.seqDelims + subj);
+                        unsigned long long const sLen  = __ldg(ix.seqDelims + subj + 1) - sBase;
+                        if (eff > actual)
+                        {
+                            qB -= static_cast<long long>((eff - actual) / 2);
+                            sB -= static_cast<long long>((eff - actual) / 2);
+                            long long const mn = qB < sB ? qB : sB;
+                            if (mn < 0)
+                            {
+                                qB -= mn;
+                                sB -= mn;
+                                eff += mn;
+                            }
+                            unsigned long long const qRem = static_cast<unsigned long long>(len) - qB;
+                            unsigned long long const sRem = sLen - sB;
+                            if (qRem < eff)
+                                eff = qRem;
+                            if (sRem < eff)
+                                eff = sRem;
+                        }
+                        int const             thresh = static_cast<int>(P.preScoringThresh * static_cast<double>(eff));
+                        unsigned char const * qs     = trans + qB;
+                        unsigned char const * ss     = ix.seqs + sBase + sB;
+                        int                   s = 0, mx = 0;
+                        bool                  pass = false;
+                        for (unsigned long long i = 0; i < eff; ++i)
+                        {
+                            s += sM[qs[i] * 32 + __ldg(ss + i)];
+                            if (s < 0)
+                                s = 0;
+                            else if (s > mx)
+                                mx = s;
+                            if (mx >= thresh)
+                            {
+                                pass = true;
+                                break;
+                            }
+                        }
+                        if (!pass)
+                        {
+                            ++nFailed;
+                            continue;
+                        }
+                        ++hitsThisSeq;
+                        unsigned long long const slot = atomicAdd(&P.counters[0], 1ull);
+                        if (slot < P.cap)
+                        {
+                            lgpu_match m;
+                            m.qry_id     = qryId;
+                            m.subj_id    = static_cast<unsigned int>(subj);
+                            m.qry_start  = seedBegin;
+                            m.qry_end    = seedBegin + seedLen;
+                            m.subj_start = static_cast<unsigned int>(pos);
+                            m.subj_end   = static_cast<unsigned int>(pos) + seedLen;
+                            P.out[slot]  = m;
+                        }
+                    }
+                }
+            }
+            needlesPos += len;
+        }
+    }
+    if (nAfter)
+        atomicAdd(&P.counters[1], nAfter);
+    if (nFailed)
+        atomicAdd(&P.counters[2], nFailed);
+}
+
+} // namespace lgpu

@@ -25,10 +25,26 @@ def _protein_lengths(rng, n, lo=50, hi=2000):
     return np.clip(rng.lognormal(5.6, 0.55, n).astype(np.int64), lo, hi)
 
 
+def _residue_table():
+    # 256-entry lookup table whose letter counts approximate AA_FREQ to 1/256: one random byte per
+    # residue makes the 1.6 G-residue benchmark database cheap to generate
+    counts = np.floor(AA_FREQ * 256).astype(int)
+    rest = 256 - counts.sum()
+    order = np.argsort(-(AA_FREQ * 256 - counts))
+    counts[order[:rest]] += 1
+    return np.repeat(AA, counts)
+
+
+_RES_TABLE = _residue_table()
+
+
 def _random_residues(rng, n):
-    cdf = np.cumsum(AA_FREQ)
-    cdf[-1] = 1.0
-    return AA[np.searchsorted(cdf, rng.random(n, dtype=np.float32), side="right").clip(0, 19)]
+    out = np.empty(n, np.uint8)
+    step = 1 << 26
+    for b in range(0, n, step):
+        e = min(n, b + step)
+        out[b:e] = _RES_TABLE[rng.integers(0, 256, e - b, dtype=np.uint8)]
+    return out
 
 
 def protein_db(n_seqs: int, seed: int = 1, family: bool = False):

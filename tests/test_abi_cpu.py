@@ -1,0 +1,125 @@
+"""CPU-only checks of the boundary: the CUDA library loads, exports every symbol the header declares,
+its host-side helpers agree with the reference's numbers, and compute calls fail loudly without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import lambda_b200
+from lambda_b200 import api
+from lambda_b200._abi import HIT_DT, Params
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_library_exports_every_declared_symbol():
+    lib = lambda_b200.load_library()
+    hdr = open(os.path.join(ROOT, "include", "lambda_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(lgpu_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 20
+    for n in sorted(names):
+        assert hasattr(lib, n), f"{n} declared in include/lambda_b200.h but not exported"
+    assert lib.lgpu_version() == 100
+
+
+def test_struct_sizes_match_header():
+    # compile-time layout of the PODs as the C compiler sees them
+    import subprocess
+    import tempfile
+    src = ('#include "lambda_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu\\n",'
+           'sizeof(lgpu_hit),sizeof(lgpu_match),sizeof(lgpu_stats),sizeof(lgpu_params),sizeof(lgpu_index_desc));}')
+    with tempfile.TemporaryDirectory() as t:
+        open(f"{t}/a.c", "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), f"{t}/a.c", "-o", f"{t}/a"])
+        out = subprocess.check_output([f"{t}/a"]).split()
+    from lambda_b200._abi import MATCH_DT, STATS_DT, IndexDesc
+    assert [int(x) for x in out] == [HIT_DT.itemsize, MATCH_DT.itemsize, STATS_DT.itemsize, C.sizeof(Params),
+                                     C.sizeof(IndexDesc)]
+
+
+def test_default_params_follow_reference_defaults():
+    # src/search_options.hpp:309-337 and profiles :631-682
+    p = api.default_params("protein")
+    assert (p.opts0.seed_length, p.opts0.seed_offset, p.opts0.max_seed_dist) == (10, 5, 0)
+    assert (p.opts.seed_length, p.opts.seed_offset, p.opts.max_seed_dist) == (11, 3, 1)
+    assert (p.gap_open, p.gap_extend, p.max_matches, p.pre_scoring) == (-11, -1, 25, 2)
+    assert p.pre_scoring_thresh == 2.0 and p.max_evalue == 1e-2
+    n = api.default_params("nucleotide")
+    assert (n.opts0.seed_length, n.opts0.seed_offset) == (14, 9) and n.pre_scoring_thresh == 1.4
+    assert (n.gap_open, n.gap_extend, n.match, n.mismatch) == (-5, -2, 2, -3)
+    s = api.default_params("protein", "pairs-sensitive")
+    assert (s.opts0.seed_length, s.opts.seed_length, s.iterative_search, s.pre_scoring) == (9, 7, 0, 3)
+    with pytest.raises(lambda_b200.LambdaError):
+        api.default_params("protein", "no-such-profile")
+
+
+def test_statistics_known_answers():
+    lib = lambda_b200.load_library()
+    p = api.default_params("protein")
+    bits = C.c_double()
+    assert lib.lgpu_bit_score(C.byref(p), 100, C.byref(bits)) == 0
+    # (lambda * S - ln K) / ln 2 with BLOSUM62 11/1: lambda 0.267, K 0.041
+    assert abs(bits.value - (0.267 * 100 - np.log(0.041)) / np.log(2)) < 1e-12
+    ev = C.c_double()
+    assert lib.lgpu_evalue(C.byref(p), 100, 150, 955200, C.byref(ev)) == 0
+    assert 0 < ev.value < 1e-3
+    mn = C.c_int32()
+    assert lib.lgpu_min_raw_score(C.byref(p), 150, 955200, C.byref(mn)) == 0
+    e_lo, e_hi = C.c_double(), C.c_double()
+    lib.lgpu_evalue(C.byref(p), mn.value - 1, 150, 955200, C.byref(e_lo))
+    lib.lgpu_evalue(C.byref(p), mn.value, 150, 955200, C.byref(e_hi))
+    assert e_lo.value > p.max_evalue >= e_hi.value
+
+
+def test_m8_formatting_matches_golden_line():
+    lib = lambda_b200.load_library()
+    p = api.default_params("protein")
+    h = np.zeros(1, HIT_DT)
+    h["q_start"], h["q_end"], h["s_start"], h["s_end"] = 0, 150, 70, 220
+    h["aln_len"], h["n_match"], h["n_mismatch"], h["n_gap_open"] = 151, 121, 28, 2
+    h["evalue"], h["bit_score"], h["q_len"] = 6.2e-58, 216.4, 150
+    buf = C.create_string_buffer(512)
+    n = lib.lgpu_format_m8(C.byref(p), C.c_void_p(h.ctypes.data), b"Q0 descr", b"S1856", buf, 512)
+    assert buf.raw[:n].decode() == "Q0\tS1856\t80.13\t151\t28\t2\t1\t150\t71\t220\t6e-58\t 216\n"
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
+def test_compute_fails_loudly_without_gpu(golden_dir):
+    with pytest.raises(lambda_b200.LambdaError) as e:
+        lambda_b200.Index.load(os.path.join(golden_dir, "prot_flat", "db.lba"))
+    assert e.value.code == -3 and "no CPU fallback" in str(e.value)
+
+
+def test_lba_reader_rejects_garbage(tmp_path):
+    bad = tmp_path / "x.lba"
+    bad.write_bytes(b"\x01" + b"\0" * 100)
+    lib = lambda_b200.load_library()
+    h = C.c_void_p()
+    assert lib.lgpu_lba_open(C.byref(h), str(bad).encode()) == -2
+    assert b"generation" in lib.lgpu_last_error(None)
+    assert lib.lgpu_lba_open(C.byref(h), b"/nonexistent.lba") == -2
+
+
+def test_lba_reader_parses_golden_index(golden_dir):
+    lib = lambda_b200.load_library()
+    h = C.c_void_p()
+    assert lib.lgpu_lba_open(C.byref(h), os.path.join(golden_dir, "prot_flat", "db.lba").encode()) == 0
+    d = lib.lgpu_lba_desc(h).contents
+    assert (d.sigma, d.sigma_bits, d.block_bytes, d.planes_offset) == (11, 4, 80, 48)
+    assert d.n_seqs == 500 and d.sampling_rate == 5 and d.red_alph == 6
+    lib.lgpu_lba_close(h)
+    assert lib.lgpu_lba_open(C.byref(h), os.path.join(golden_dir, "nucl", "db.lba").encode()) == 0
+    d = lib.lgpu_lba_desc(h).contents
+    assert (d.sigma, d.sigma_bits, d.block_bytes, d.planes_offset) == (5, 3, 48, 24)
+    lib.lgpu_lba_close(h)

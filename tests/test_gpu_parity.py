@@ -1,0 +1,172 @@
+"""Parity of the CUDA path with the CPU oracle and the reference's golden outputs (B200 only).
+Everything goes through the C ABI (lambda_b200/liblambda_b200.so)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import lambda_b200
+import orc
+from cases import CASE_PROFILES, CASES, FUNNEL, load_golden
+from lambda_b200 import synth
+from lambda_b200._abi import MATCH_DT
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref", "lambda3")
+HIT_INT_FIELDS = ["q_id", "s_id", "q_start", "q_end", "s_start", "s_end", "q_len", "s_len", "score", "n_match",
+                  "n_mismatch", "n_gap_open", "n_gap_ext", "n_positive", "aln_len", "q_frame", "s_frame"]
+
+
+def _load(gdir, case, domain):
+    path = os.path.join(gdir, case, "db.lba")
+    ids, data, offs = lambda_b200.read_fasta(os.path.join(gdir, case, "q.fasta"))
+    return path, ids, lambda_b200.encode(data, domain), offs
+
+
+def _sorted(m):
+    return np.sort(m, order=list(m.dtype.names))
+
+
+@pytest.mark.parametrize("case,domain", [(c, d) for c, d, _ in CASES])
+def test_fm_rank_and_locate(golden_dir, case, domain):
+    path = os.path.join(golden_dir, case, "db.lba")
+    o = orc.Oracle(path)
+    ix = lambda_b200.Index.load(path)
+    rng = np.random.default_rng(1)
+    n_rows = ix.desc["n_residues"] + 5 * ix.desc["n_seqs"]  # upper bound; clip below
+    import ctypes as C
+    Cv = np.ctypeslib.as_array(C.cast(o.desc.C, C.POINTER(C.c_uint64)), (o.desc.sigma + 1,))
+    n_rows = int(Cv[-1])
+    idx = np.concatenate([rng.integers(0, n_rows + 1, 5000), [0, n_rows, 64, 63, 128]]).astype(np.uint64)
+    symb = rng.integers(0, o.desc.sigma, len(idx)).astype(np.uint8)
+    assert (ix.rank(idx, symb) == o.rank(idx, symb)).all()
+    rows = rng.integers(0, n_rows, 3000).astype(np.uint64)
+    s1, p1 = ix.locate(rows)
+    s2, p2 = o.locate(rows)
+    assert (s1 == s2).all() and (p1 == p2).all()
+    o.close()
+    ix.close()
+
+
+@pytest.mark.parametrize("case,domain,profile", CASE_PROFILES)
+def test_seeding_matches_oracle(golden_dir, case, domain, profile):
+    path, ids, res, offs = _load(golden_dir, case, domain)
+    o = orc.Oracle(path)
+    ix = lambda_b200.Index.load(path)
+    s = lambda_b200.Searcher(ix, domain, profile)
+    p = o.params(domain, profile)
+    for phase in (1, 2):
+        m_gpu, st_gpu = s.seed(res, offs, phase)
+        m_cpu, st_cpu = o.seed(p, res, offs, phase)
+        assert len(m_gpu) == len(m_cpu)
+        assert (_sorted(m_gpu) == _sorted(m_cpu)).all()
+        for k in ("hits_after_seeding", "hits_failed_pre_extend"):
+            assert int(st_gpu[k]) == int(st_cpu[k]), k
+        # widen / sort / merge / unique on the same matches
+        if len(m_cpu):
+            w_gpu, wst_gpu = s.merge(res, offs, m_cpu)
+            w_cpu, wst_cpu = o.merge(p, res, offs, m_cpu)
+            assert len(w_gpu) == len(w_cpu) and (w_gpu == w_cpu).all()  # same order: both sorted
+            assert int(wst_gpu["hits_duplicate"]) == int(wst_cpu["hits_duplicate"])
+    s.close(); ix.close(); o.close()
+
+
+@pytest.mark.parametrize("case,domain", [(c, d) for c, d, _ in CASES])
+def test_extension_matches_oracle(golden_dir, case, domain):
+    path, ids, res, offs = _load(golden_dir, case, domain)
+    o = orc.Oracle(path)
+    ix = lambda_b200.Index.load(path)
+    s = lambda_b200.Searcher(ix, domain)
+    p = o.params(domain)
+    m, _ = o.seed(p, res, offs, 2)
+    win, _ = o.merge(p, res, offs, m)
+    # add ragged / degenerate windows: partial queries, 1-row windows, windows at subject ends
+    extra = win[: min(len(win), 20)].copy()
+    extra["qry_start"] = np.minimum(extra["qry_end"] - 1, 7)
+    extra["subj_end"] = extra["subj_start"] + np.minimum(extra["subj_end"] - extra["subj_start"], 13)
+    one = win[: min(len(win), 5)].copy()
+    one["subj_end"] = one["subj_start"] + 1
+    win = np.concatenate([win, extra, one]).astype(MATCH_DT)
+    sc_gpu, _ = s.extend_scores(res, offs, win)
+    sc_cpu, h_cpu = o.extend(p, res, offs, win, True)
+    assert (sc_gpu == sc_cpu).all()
+    h_gpu, _ = s.extend_trace(res, offs, win)
+    for f in HIT_INT_FIELDS:
+        assert (h_gpu[f] == h_cpu[f]).all(), f
+    s.close(); ix.close(); o.close()
+
+
+def test_extension_long_queries_multi_block(golden_dir):
+    """queries longer than one 32*K column block (boundary row path) and long merged windows"""
+    path = os.path.join(golden_dir, "prot_flat", "db.lba")
+    o = orc.Oracle(path)
+    ix = lambda_b200.Index.load(path)
+    rng = np.random.default_rng(5)
+    db, offs = synth.protein_db(500, seed=101)
+    lens = np.diff(offs)
+    long_ids = np.argsort(lens)[-6:]
+    qs, qo = [], [0]
+    for sid in long_ids:  # queries = mutated copies of the longest subjects (up to 2000 aa)
+        qs.append(synth.mutate_protein(rng, db[offs[sid]:offs[sid + 1]], 0.2, 0.02))
+        qo.append(qo[-1] + len(qs[-1]))
+    res = lambda_b200.encode(np.concatenate(qs), 0)
+    qo = np.array(qo, np.uint64)
+    win = np.zeros(len(long_ids), MATCH_DT)
+    win["qry_id"] = np.arange(len(long_ids))
+    win["subj_id"] = long_ids
+    win["qry_end"] = np.diff(qo)
+    win["subj_end"] = lens[long_ids]
+    s = lambda_b200.Searcher(ix, "protein")
+    p = o.params(0)
+    sc_gpu, _ = s.extend_scores(res, qo, win)
+    sc_cpu, h_cpu = o.extend(p, res, qo, win, True)
+    assert (sc_gpu == sc_cpu).all() and (sc_cpu > 500).all()
+    h_gpu, _ = s.extend_trace(res, qo, win)
+    for f in HIT_INT_FIELDS:
+        assert (h_gpu[f] == h_cpu[f]).all(), f
+    s.close(); ix.close(); o.close()
+
+
+@pytest.mark.parametrize("case,domain,profile", CASE_PROFILES)
+def test_search_reproduces_reference_output(golden_dir, case, domain, profile):
+    path, ids, res, offs = _load(golden_dir, case, domain)
+    ix = lambda_b200.Index.load(path)
+    s = lambda_b200.Searcher(ix, domain, profile)
+    hits, st = s.search(res, offs)
+    ref, funnel = load_golden(golden_dir, case, profile)
+    assert sorted(s.m8(hits, ids)) == sorted(ref)
+    for k in FUNNEL:
+        assert int(st[k]) == funnel[k], k
+    assert int(st["kernel_launches"]) > 0
+    # empty batch and a batch where nothing can seed
+    h0, _ = s.search(np.zeros(0, np.uint8), np.zeros(1, np.uint64))
+    assert len(h0) == 0
+    h1, _ = s.search(np.zeros(3, np.uint8), np.array([0, 3], np.uint64))
+    assert len(h1) == 0
+    # idempotence: the same batch again gives the same records
+    hits2, _ = s.search(res, offs)
+    assert (hits2 == hits).all()
+    s.close(); ix.close()
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="reference binary (oracle/_ref/lambda3) not built")
+@pytest.mark.parametrize("family", [False, True])
+def test_search_vs_live_reference_binary(tmp_path, family):
+    """BASELINE config[0]-shaped case at reduced size, checked against the reference run on this box"""
+    db, offs = synth.protein_db(8000, seed=31, family=family)
+    q, qo = synth.protein_queries(db, offs, 400, 150, seed=32)
+    synth.write_fasta(str(tmp_path / "db.fasta"), db, offs, "S")
+    synth.write_fasta(str(tmp_path / "q.fasta"), q, qo, "Q")
+    subprocess.check_call([REF, "mkindexp", "-d", str(tmp_path / "db.fasta"), "-i", str(tmp_path / "db.lba"),
+                           "-v", "0"])
+    subprocess.check_call([REF, "searchp", "-q", str(tmp_path / "q.fasta"), "-i", str(tmp_path / "db.lba"),
+                           "-o", str(tmp_path / "ref.m8"), "--version-to-outputfile", "0", "-v", "0"])
+    ix = lambda_b200.Index.load(str(tmp_path / "db.lba"))
+    s = lambda_b200.Searcher(ix, "protein")
+    ids, hits, st = s.search_fasta(str(tmp_path / "q.fasta"))
+    ref = open(tmp_path / "ref.m8").read().splitlines(True)
+    assert len(ref) >= 400
+    assert sorted(s.m8(hits, ids)) == sorted(ref)
+    s.close(); ix.close()
