@@ -372,9 +372,9 @@ static uint64_t runMerge(lgpu_ctx & c, lgpu_match const * dIn, uint64_t n, lgpu_
     size_t tmp1 = 0, tmp2 = 0, tmp3 = 0;
     int const nI = static_cast<int>(n);
     cub::DeviceRadixSort::SortPairs(nullptr, tmp1, c.dKey2.p, c.dKey2b.p, c.dPerm.p, c.dPermB.p, nI, 0, 64, c.stream);
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp2, c.dKey1b.p, c.dKey1.p, c.dKey2b.p, c.dKey2.p, nI, 0, 64, c.stream);
     cub::DeviceScan::InclusiveSum(nullptr, tmp3, c.dHead.p, c.dScan.p, nI, c.stream);
-    tmp2 = std::max(tmp1, tmp3);
-    c.dCubTemp.reserve(tmp2);
+    c.dCubTemp.reserve(std::max(tmp1, std::max(tmp2, tmp3)));
     size_t tb = c.dCubTemp.cap;
     LGPU_CUDA(cub::DeviceRadixSort::SortPairs(c.dCubTemp.p, tb, c.dKey2.p, c.dKey2b.p, c.dPerm.p, c.dPermB.p, nI, 0, 64,
                                               c.stream));
