@@ -29,6 +29,7 @@
 #include "../../include/lambda_b200.h"
 #include "host_finalize.hpp"
 #include "host_params.hpp"
+#include "kernels_dpx.cuh"
 #include "kernels_extend.cuh"
 #include "kernels_fm.cuh"
 #include "lba_index.hpp"
@@ -153,7 +154,9 @@ struct lgpu_ctx
     DevBuf<unsigned int>       dPerm, dPermB, dHead, dScan;
     DevBuf<unsigned char>      dCubTemp;
     DevBuf<int>                dScores, dScores2, dMinBit, dMinEval;
-    DevBuf<unsigned int>       dWork, dBestPos, dBoundary;
+    DevBuf<unsigned int>       dWork, dBestPos, dBoundary, dOrder, dOrderB, dClassInfo;
+    DevBuf<unsigned long long> dClassKeys, dClassKeysB;
+    bool                       dpxOk = false; // scoring fits the int8 profile of the DPX kernel
     DevBuf<unsigned char>      dTrace;
     DevBuf<unsigned long long> dTraceOff;
     DevBuf<lgpu_hit>           dHits;
@@ -453,8 +456,9 @@ static ExtParams baseExtParams(lgpu_ctx & c, lgpu_match const * dTasks, unsigned
     P.matrix      = c.dMatrix.p;
     P.go          = c.scoring.gapOpenSeqan;
     P.ge          = c.scoring.gapExtend;
-    c.dWork.reserve(4);
+    c.dWork.reserve(kNumDpxClasses + 2);
     P.workCounter = c.dWork.p;
+    P.order       = nullptr;
     P.maxRows     = std::max(dims.maxT, 1u);
     if (dims.maxQ > static_cast<unsigned int>(32 * K))
         c.dBoundary.reserve(static_cast<size_t>(grid) * 4 * P.maxRows);
@@ -464,25 +468,114 @@ static ExtParams baseExtParams(lgpu_ctx & c, lgpu_match const * dTasks, unsigned
     return P;
 }
 
-// DP pass 1: scores into dScores[0..n)
+template <int T, int K>
+static void launchDpx(lgpu_ctx & c, DpxParams P, unsigned int maxNt)
+{
+    constexpr int G = 32 / T;
+    P.winCap        = (maxNt + 4 * T + 15) / 16 * 16;
+    size_t const smem = static_cast<size_t>(G) * (static_cast<size_t>(P.nCodes) * dpxRowWords(T, K) * 4 + P.winCap);
+    LGPU_CUDA(cudaFuncSetAttribute(swScoreDpxKernel<T, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (smem > 227 * 1024)
+        throw CudaError("DPX score kernel: window too long for shared memory");
+    unsigned int const need = (P.nTasks + G - 1) / G;
+    unsigned int const grid = std::min<unsigned int>(need, static_cast<unsigned int>(c.numSMs) * 24);
+    swScoreDpxKernel<T, K><<<grid, 32, smem, c.stream>>>(P);
+    LGPU_CUDA(cudaGetLastError());
+}
+
+// DP pass 1: scores into dScores[0..n).  Tasks are bucketed by query length into (T, K) classes of the
+// packed DPX kernel and sorted by window length inside a class; whatever does not fit (queries > 2048,
+// windows > 8192, exotic scoring) runs on the scalar wavefront kernel.
 static void runScorePass(lgpu_ctx & c, lgpu_match const * dTasks, unsigned int n, TaskDims const & dims, int * dScores,
                          lgpu_stats * st)
 {
     if (n == 0)
         return;
-    StageTimer         t(c, st ? &st->ms_extend_score : nullptr);
-    int const          K    = chooseK(dims.maxQ);
-    unsigned int const grid = std::min<unsigned int>((n + 3) / 4, static_cast<unsigned int>(c.numSMs) * 16);
-    ExtParams          P    = baseExtParams(c, dTasks, n, grid, dims, K);
-    P.scores                = dScores;
-    LGPU_CUDA(cudaMemsetAsync(c.dWork.p, 0, 4, c.stream));
-    launchWavefront<false>(K, P, grid, c.stream);
-    LGPU_CUDA(cudaGetLastError());
+    StageTimer t(c, st ? &st->ms_extend_score : nullptr);
+    constexpr int NC = kNumDpxClasses + 1;
+    c.dClassKeys.reserve(n);
+    c.dClassKeysB.reserve(n);
+    c.dOrder.reserve(n);
+    c.dOrderB.reserve(n);
+    c.dClassInfo.reserve(2 * NC + 4);
+    c.dCounters.reserve(8);
+    c.dWork.reserve(NC + 1);
+    LGPU_CUDA(cudaMemsetAsync(c.dClassInfo.p, 0, (2 * NC + 4) * 4, c.stream));
+    LGPU_CUDA(cudaMemsetAsync(c.dCounters.p, 0, 8 * sizeof(unsigned long long), c.stream));
+    LGPU_CUDA(cudaMemsetAsync(c.dWork.p, 0, (NC + 1) * 4, c.stream));
+    classifyKernel<<<gridFor(n, 256), 256, 0, c.stream>>>(dTasks, n, c.dClassKeys.p, c.dOrder.p, c.dClassInfo.p,
+                                                          c.dClassInfo.p + NC, c.dCounters.p);
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, c.dClassKeys.p, c.dClassKeysB.p, c.dOrder.p, c.dOrderB.p, static_cast<int>(n), 0,
+                                    40, c.stream);
+    c.dCubTemp.reserve(tmp);
+    size_t tb = c.dCubTemp.cap;
+    LGPU_CUDA(cub::DeviceRadixSort::SortPairs(c.dCubTemp.p, tb, c.dClassKeys.p, c.dClassKeysB.p, c.dOrder.p, c.dOrderB.p,
+                                              static_cast<int>(n), 0, 40, c.stream));
+    unsigned int       info[2 * NC];
+    unsigned long long cells = 0;
+    LGPU_CUDA(cudaMemcpyAsync(info, c.dClassInfo.p, sizeof(info), cudaMemcpyDeviceToHost, c.stream));
+    LGPU_CUDA(cudaMemcpyAsync(&cells, c.dCounters.p, 8, cudaMemcpyDeviceToHost, c.stream));
+    LGPU_CUDA(cudaStreamSynchronize(c.stream));
+    unsigned int launches = 2;
+    unsigned int off      = 0;
+    for (int cls = 0; cls < NC; ++cls)
+    {
+        unsigned int const cnt = info[cls], maxNt = info[NC + cls];
+        if (cnt == 0)
+            continue;
+        bool const scalar = (cls == kNumDpxClasses) || !c.dpxOk;
+        if (!scalar)
+        {
+            DpxParams P{};
+            P.ix          = c.index->dev;
+            P.Q           = c.Q;
+            P.tasks       = dTasks;
+            P.order       = c.dOrderB.p + off;
+            P.nTasks      = cnt;
+            P.sbjFrames   = c.di.sbjNumFrames;
+            P.matrix      = c.dMatrix.p;
+            P.go          = c.scoring.gapOpenSeqan;
+            P.ge          = c.scoring.gapExtend;
+            P.nCodes      = static_cast<unsigned int>(c.scoring.alphSize) + 1;
+            P.workCounter = c.dWork.p + cls;
+            P.scores      = dScores;
+            switch (cls)
+            {
+                case 0: launchDpx<8, 4>(c, P, maxNt); break;
+                case 1: launchDpx<8, 8>(c, P, maxNt); break;
+                case 2: launchDpx<8, 12>(c, P, maxNt); break;
+                case 3: launchDpx<8, 16>(c, P, maxNt); break;
+                case 4: launchDpx<8, 20>(c, P, maxNt); break;
+                case 5: launchDpx<8, 24>(c, P, maxNt); break;
+                case 6: launchDpx<8, 32>(c, P, maxNt); break;
+                case 7: launchDpx<16, 24>(c, P, maxNt); break;
+                case 8: launchDpx<16, 32>(c, P, maxNt); break;
+                case 9: launchDpx<32, 24>(c, P, maxNt); break;
+                default: launchDpx<32, 32>(c, P, maxNt); break;
+            }
+        }
+        else
+        {
+            TaskDims d2 = dims;
+            d2.maxT     = std::max(d2.maxT, maxNt);
+            int const          K    = chooseK(dims.maxQ);
+            unsigned int const grid = std::min<unsigned int>((cnt + 3) / 4, static_cast<unsigned int>(c.numSMs) * 16);
+            ExtParams          P    = baseExtParams(c, dTasks, cnt, grid, d2, K);
+            P.order                 = c.dOrderB.p + off;
+            P.workCounter           = c.dWork.p + cls;
+            P.scores                = dScores;
+            launchWavefront<false>(K, P, grid, c.stream);
+            LGPU_CUDA(cudaGetLastError());
+        }
+        ++launches;
+        off += cnt;
+    }
     if (st)
     {
-        st->kernel_launches += 1;
+        st->kernel_launches += launches;
         st->n_extensions_score += n;
-        st->cells_score += dims.cells;
+        st->cells_score += cells;
     }
 }
 
@@ -875,6 +968,15 @@ int lgpu_ctx_create(lgpu_ctx ** out, lgpu_index const * ix, lgpu_params const * 
         c->dMatrix.reserve(1024);
         LGPU_CUDA(cudaMemcpy(c->dMatrix.p, c->scoring.matrix, 1024, cudaMemcpyHostToDevice));
         c->dCounters.reserve(8);
+        // the packed kernel stores (score - gapOpen) as int8 profile bytes with -128 reserved for "null"
+        c->dpxOk = c->scoring.alphSize < 32 && c->scoring.gapOpenSeqan <= c->scoring.gapExtend && c->scoring.gapExtend <= 0;
+        for (int a = 0; a < c->scoring.alphSize; ++a)
+            for (int b = 0; b < c->scoring.alphSize; ++b)
+            {
+                int const v = c->scoring.matrix[a * 32 + b] - c->scoring.gapOpenSeqan;
+                if (v < -127 || v > 127)
+                    c->dpxOk = false;
+            }
         *out = c.release();
     });
 }

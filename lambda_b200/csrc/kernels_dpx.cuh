@@ -1,0 +1,302 @@
+// DP pass 1 (score only) on Blackwell's packed-int16 DPX instructions.
+//
+// Same recurrence as the reference's SIMD pass (_performAlignment<withTrace=false>,
+// src/search_algo.hpp:1246; SQ/align/dp_formula_affine.h:66-126), restated so that one cell update is
+// five VIADDMNMX/VIADD.16x2 + one VIMNMX on two int16 lanes, plus one PRMT that builds the operand:
+//
+//   W     = H + go                         ("tmp": the only form H is stored in)
+//   t     = max(Wdiag + sub'', E, 0)       VIADDMNMX.S16x2.RELU   sub'' = M[q][s] - go   (one int8 profile byte)
+//   u     = t + go                         VIADD.16x2
+//   W     = max(F + go, u)                 VIADDMNMX.S16x2        (= max(t, F) + go = H + go)
+//   F'    = max(F + ge, u)                 VIADDMNMX.S16x2        (valid because go <= ge)
+//   E'    = max(E + ge, W)                 VIADDMNMX.S16x2
+//   best  = max(best, W)                   VIMNMX.S16x2           score = best - go
+//
+// Work decomposition: a group of T threads (8/16/32) owns one alignment.  The query is cut into 2T
+// strips of K columns; thread p holds strip p in the low int16 half and strip p + T in the high half
+// of every register, so both halves are always busy on different cells of the SAME alignment (no
+// pairing of alignments, no length mismatch).  Strip v works on subject row j = s - v at step s: the
+// 2T strips form an anti-diagonal wavefront, and the only communication per step is the rotation of
+// (W, F) of a strip's last column to the next strip (two shuffles).  Rows outside the window and
+// columns past the query end use a "null" profile entry of -128: it can never raise a cell above a
+// value that already exists, so no masking is needed anywhere in the inner loop and all groups of a
+// warp can simply run for the longest window among them.
+//
+// Shared memory per group: the query profile P[code][word][strip] (int8, row stride a multiple of 32
+// words so the 4-byte loads of a warp are bank-conflict free) and the padded subject window.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/lambda_b200.h"
+#include "kernels_fm.cuh"
+
+namespace lgpu
+{
+
+struct DpxParams
+{
+    DevIndex             ix;
+    DevQueries           Q;
+    lgpu_match const *   tasks;
+    unsigned int const * order; // task indices of this class, sorted by window length
+    unsigned int         nTasks; // entries in `order`
+    unsigned int         sbjFrames;
+    signed char const *  matrix; // 32 x 32
+    int                  go, ge;
+    unsigned int         nCodes; // alphabet size + 1 (last row = null)
+    unsigned int         winCap; // bytes reserved per group for the padded window
+    unsigned int *       workCounter;
+    int *                scores;
+};
+
+__device__ __forceinline__ unsigned int prmt(unsigned int a, unsigned int b, unsigned int sel)
+{
+    unsigned int d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
+__host__ __device__ constexpr int dpxRowWords(int T, int K)
+{
+    return (((K + 3) / 4) * 2 * T + 31) / 32 * 32;
+}
+
+template <int T, int K>
+__global__ void __launch_bounds__(32) swScoreDpxKernel(DpxParams P)
+{
+    constexpr int G    = 32 / T;       // alignments per warp
+    constexpr int KW   = (K + 3) / 4;  // profile words per strip
+    constexpr int ROWW = dpxRowWords(T, K);
+    constexpr int PAD  = 2 * T;        // null rows in front of the window
+
+    extern __shared__ unsigned int smem[];
+    unsigned int const lane = threadIdx.x;
+    unsigned int const grp  = lane / T;
+    unsigned int const gl   = lane % T;
+    unsigned int const profWords = P.nCodes * ROWW;
+    unsigned int const grpWords  = profWords + P.winCap / 4;
+    unsigned int *     prof = smem + grp * grpWords;
+    unsigned char *    win  = reinterpret_cast<unsigned char *>(prof + profWords);
+    unsigned int const nullCode = P.nCodes - 1;
+    unsigned int const grpMask  = (T == 32) ? 0xffffffffu : (((1u << T) - 1u) << (grp * T));
+
+    unsigned int const go2  = (static_cast<unsigned int>(P.go) & 0xffffu) * 0x10001u;
+    unsigned int const ge2  = (static_cast<unsigned int>(P.ge) & 0xffffu) * 0x10001u;
+    unsigned int const neg2 = 0xC000C000u; // -16384 in both halves
+
+    for (;;)
+    {
+        unsigned int base = 0;
+        if (lane == 0)
+            base = atomicAdd(P.workCounter, static_cast<unsigned int>(G));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= P.nTasks)
+            break;
+        unsigned int const slot  = base + grp;
+        bool const         valid = slot < P.nTasks;
+        unsigned int       task  = 0, nq = 0, nt = 0;
+        unsigned char const *qs = nullptr, *ts = nullptr;
+        if (valid)
+        {
+            task                          = P.order[slot];
+            lgpu_match const         m    = P.tasks[task];
+            unsigned int const       q    = m.qry_id / P.Q.F;
+            unsigned int const       f    = m.qry_id % P.Q.F;
+            unsigned long long const qb   = P.Q.offs[q];
+            unsigned int const       qLen = static_cast<unsigned int>(P.Q.offs[q + 1] - qb);
+            qs = P.Q.trans + P.Q.F * qb + static_cast<unsigned long long>(f) * qLen + m.qry_start;
+            nq = m.qry_end - m.qry_start;
+            ts = P.ix.seqs + P.ix.seqDelims[m.subj_id / P.sbjFrames] + m.subj_start;
+            nt = m.subj_end - m.subj_start;
+        }
+        // the warp runs for its longest window; extra steps are null rows for the shorter ones
+        unsigned int ntMax = nt;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1)
+            ntMax = max(ntMax, __shfl_xor_sync(0xffffffffu, ntMax, off));
+        unsigned int const nSteps = ntMax + 2 * T - 1;
+
+        __syncwarp();
+        // ---- query profile: P[c][w][v], byte r%4 of word w = r/4 of strip v <-> column i = v*K + r ----
+        for (unsigned int idx = gl; idx < profWords; idx += T)
+        {
+            unsigned int const c   = idx / ROWW;
+            unsigned int const rem = idx % ROWW;
+            unsigned int const w   = rem / (2 * T);
+            unsigned int const v   = rem % (2 * T);
+            unsigned int       word = 0x80808080u; // null = -128
+            if (c != nullCode && w < KW)
+            {
+                word = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                {
+                    unsigned int const r = w * 4 + b;
+                    unsigned int const i = v * K + r;
+                    int                val = -128;
+                    if (r < K && i < nq)
+                        val = static_cast<int>(P.matrix[c * 32 + qs[i]]) - P.go;
+                    word |= (static_cast<unsigned int>(val) & 0xffu) << (8 * b);
+                }
+            }
+            prof[idx] = word;
+        }
+        // ---- subject window, null-padded on both sides ----
+        for (unsigned int idx = gl; idx < P.winCap; idx += T)
+        {
+            int const     j = static_cast<int>(idx) - PAD;
+            unsigned char c = static_cast<unsigned char>(nullCode);
+            if (j >= 0 && j < static_cast<int>(nt))
+                c = ts[j];
+            win[idx] = c;
+        }
+        __syncwarp();
+
+        unsigned int E[K], W[K];
+#pragma unroll
+        for (int r = 0; r < K; ++r)
+        {
+            E[r] = neg2;
+            W[r] = go2; // H = 0
+        }
+        unsigned int best = go2;
+        unsigned int outW = go2, outF = neg2, diagIn = go2;
+
+        // profile words of the current step (software pipelined one step ahead)
+        unsigned int wl[KW], wh[KW];
+        {
+            unsigned int const cLo = win[PAD - gl];           // row 0 - gl  (null for gl > 0)
+            unsigned int const cHi = win[PAD - gl - T];
+#pragma unroll
+            for (int k = 0; k < KW; ++k)
+            {
+                wl[k] = prof[cLo * ROWW + k * 2 * T + gl];
+                wh[k] = prof[cHi * ROWW + k * 2 * T + T + gl];
+            }
+        }
+        for (unsigned int s = 0; s < nSteps; ++s)
+        {
+            // prefetch the next step's operands (the window buffer is padded, so s + 1 is always in range)
+            unsigned int nl[KW], nh[KW];
+            {
+                unsigned int const cLo = win[PAD + s + 1 - gl];
+                unsigned int const cHi = win[PAD + s + 1 - gl - T];
+#pragma unroll
+                for (int k = 0; k < KW; ++k)
+                {
+                    nl[k] = prof[cLo * ROWW + k * 2 * T + gl];
+                    nh[k] = prof[cHi * ROWW + k * 2 * T + T + gl];
+                }
+            }
+            // (W, F) of the left strip's last column for the row this strip works on now
+            unsigned int inW = __shfl_sync(0xffffffffu, outW, (lane - 1) & (T - 1), T);
+            unsigned int inF = __shfl_sync(0xffffffffu, outF, (lane - 1) & (T - 1), T);
+            if (gl == 0)
+            {
+                // strip 0 sees the matrix border (H = 0, no horizontal gap); strip T continues strip T-1
+                inW = prmt(go2, inW, 0x5410);
+                inF = prmt(neg2, inF, 0x5410);
+            }
+            unsigned int diag = diagIn; // W of the left strip at the previous row
+            diagIn            = inW;
+            unsigned int F    = inF;
+#pragma unroll
+            for (int r = 0; r < K; ++r)
+            {
+                // {sext(lo byte), sext(hi byte)} of column r: selector nibble bit 3 replicates the sign
+                unsigned int const b   = r & 3;
+                unsigned int const sel = ((0xCu + b) << 12) | ((4u + b) << 8) | ((8u + b) << 4) | b;
+                unsigned int const sub = prmt(wl[r >> 2], wh[r >> 2], sel);
+                unsigned int const t   = __viaddmax_s16x2_relu(diag, sub, E[r]);
+                unsigned int const u   = __vadd2(t, go2);
+                unsigned int const w   = __viaddmax_s16x2(F, go2, u);
+                F                      = __viaddmax_s16x2(F, ge2, u);
+                E[r]                   = __viaddmax_s16x2(E[r], ge2, w);
+                diag                   = W[r];
+                W[r]                   = w;
+                best                   = __vmaxs2(best, w);
+            }
+            outW = W[K - 1];
+            outF = F;
+#pragma unroll
+            for (int k = 0; k < KW; ++k)
+            {
+                wl[k] = nl[k];
+                wh[k] = nh[k];
+            }
+        }
+        // reduce over the group: both halves, all T threads
+        int b = max(static_cast<int>(static_cast<short>(best & 0xffffu)), static_cast<int>(best) >> 16);
+#pragma unroll
+        for (int off = T / 2; off > 0; off >>= 1)
+            b = max(b, __shfl_xor_sync(0xffffffffu, b, off));
+        if (valid && gl == 0)
+            P.scores[task] = b - P.go;
+        (void) grpMask;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// classification of tasks into (T, K) classes
+// ---------------------------------------------------------------------------------------------
+
+constexpr int kNumDpxClasses = 11;
+// columns covered by class c = 2 * T * K
+__host__ __device__ inline int dpxClassOf(unsigned int nq)
+{
+    if (nq <= 64) return 0;    // T=8  K=4
+    if (nq <= 128) return 1;   // T=8  K=8
+    if (nq <= 192) return 2;   // T=8  K=12
+    if (nq <= 256) return 3;   // T=8  K=16
+    if (nq <= 320) return 4;   // T=8  K=20
+    if (nq <= 384) return 5;   // T=8  K=24
+    if (nq <= 512) return 6;   // T=8  K=32
+    if (nq <= 768) return 7;   // T=16 K=24
+    if (nq <= 1024) return 8;  // T=16 K=32
+    if (nq <= 1536) return 9;  // T=32 K=24
+    if (nq <= 2048) return 10; // T=32 K=32
+    return kNumDpxClasses;     // too long: scalar wavefront kernel
+}
+
+constexpr unsigned int kDpxMaxWindow = 8192; // longer windows go to the scalar kernel
+
+// key = class << 32 | nt ; also per-class counts / max window / total cells
+__global__ void classifyKernel(lgpu_match const * tasks, unsigned int n, unsigned long long * keys, unsigned int * idx,
+                               unsigned int * classCount, unsigned int * classMaxNt, unsigned long long * cells)
+{
+    unsigned int const t = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long myCells = 0;
+    if (t < n)
+    {
+        unsigned int const nq = tasks[t].qry_end - tasks[t].qry_start;
+        unsigned int const nt = tasks[t].subj_end - tasks[t].subj_start;
+        int                c  = dpxClassOf(nq);
+        if (nt > kDpxMaxWindow)
+            c = kNumDpxClasses;
+        keys[t] = (static_cast<unsigned long long>(c) << 32) | nt;
+        idx[t]  = t;
+        atomicAdd(&classCount[c], 1u);
+        atomicMax(&classMaxNt[c], nt);
+        myCells = static_cast<unsigned long long>(nq) * nt;
+    }
+    // block-level reduction of the cell count
+    __shared__ unsigned long long sh[8];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+        myCells += __shfl_down_sync(0xffffffffu, myCells, off);
+    if ((threadIdx.x & 31) == 0)
+        sh[threadIdx.x >> 5] = myCells;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        unsigned long long s = 0;
+        for (unsigned int w = 0; w < blockDim.x / 32; ++w)
+            s += sh[w];
+        if (s)
+            atomicAdd(cells, s);
+    }
+}
+
+} // namespace lgpu

@@ -147,7 +147,8 @@ struct ExtParams
     DevIndex              ix;
     DevQueries            Q;
     lgpu_match const *    tasks;
-    unsigned int          nTasks;
+    unsigned int const *  order;        // optional indirection: work item t is task order[t]
+    unsigned int          nTasks;       // number of work items
     unsigned int          sbjFrames;
     signed char const *   matrix; // 32 x 32
     int                   go, ge;
@@ -196,6 +197,8 @@ __global__ void __launch_bounds__(128) swWavefrontKernel(ExtParams P)
         task = __shfl_sync(0xffffffffu, task, 0);
         if (task >= P.nTasks)
             break;
+        if (P.order)
+            task = P.order[task];
 
         lgpu_match const         m    = P.tasks[task];
         unsigned int const       q    = m.qry_id / P.Q.F;

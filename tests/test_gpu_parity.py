@@ -129,6 +129,57 @@ def test_extension_long_queries_multi_block(golden_dir):
     s.close(); ix.close(); o.close()
 
 
+def test_score_kernel_all_length_classes(golden_dir):
+    """DP pass 1 over every (T, K) class of the packed DPX kernel plus the scalar fallback (> 2048),
+    with ragged windows (1 .. 2000 rows), related and unrelated pairs"""
+    path = os.path.join(golden_dir, "prot_flat", "db.lba")
+    o = orc.Oracle(path)
+    ix = lambda_b200.Index.load(path)
+    rng = np.random.default_rng(7)
+    db, offs = synth.protein_db(500, seed=101)
+    lens = np.diff(offs)
+    qlens = [1, 2, 7, 33, 64, 65, 100, 128, 129, 190, 192, 193, 250, 256, 257, 300, 320, 321, 384, 385, 500, 512,
+             513, 700, 768, 769, 1000, 1024, 1025, 1500, 1536, 1537, 2000, 2048, 2049, 2300]
+    qs, qo, wins = [], [0], []
+    for qi, L in enumerate(qlens):
+        sid = int(rng.integers(0, len(lens)))
+        src = db[offs[sid]:offs[sid + 1]]
+        reps = -(-L // len(src))
+        seq = synth.mutate_protein(rng, np.tile(src, reps)[:L + 20], 0.15, 0.02)[:L]
+        if len(seq) < L:
+            seq = np.concatenate([seq, synth._random_residues(rng, L - len(seq))])
+        qs.append(seq)
+        qo.append(qo[-1] + L)
+        for k in range(6):  # the source subject (related) + random subjects, random windows
+            s2 = sid if k < 2 else int(rng.integers(0, len(lens)))
+            a = int(rng.integers(0, lens[s2]))
+            b = int(rng.integers(a + 1, lens[s2] + 1)) if k % 2 else int(lens[s2])
+            if k == 0:
+                a = 0
+            wins.append((qi, s2, 0, L, a, b))
+    res = lambda_b200.encode(np.concatenate(qs), 0)
+    qo = np.array(qo, np.uint64)
+    win = np.array(wins, dtype=MATCH_DT)
+    s = lambda_b200.Searcher(ix, "protein")
+    p = o.params(0)
+    sc_gpu, st = s.extend_scores(res, qo, win)
+    sc_cpu, _ = o.extend(p, res, qo, win, False)
+    bad = np.nonzero(sc_gpu != sc_cpu)[0]
+    assert len(bad) == 0, (win[bad[:5]], sc_gpu[bad[:5]], sc_cpu[bad[:5]])
+    assert sc_cpu.max() > 1000
+    # other scoring schemes through the same kernels
+    for kw in (dict(scoring_method=45, gap_open=-14, gap_extend=-2), dict(scoring_method=80, gap_open=-10, gap_extend=-1)):
+        s2 = lambda_b200.Searcher(ix, "protein", **kw)
+        p2 = o.params(0)
+        for k, v in kw.items():
+            setattr(p2, k, v)
+        g, _ = s2.extend_scores(res, qo, win[:60])
+        c, _ = o.extend(p2, res, qo, win[:60], False)
+        assert (g == c).all()
+        s2.close()
+    s.close(); ix.close(); o.close()
+
+
 @pytest.mark.parametrize("case,domain,profile", CASE_PROFILES)
 def test_search_reproduces_reference_output(golden_dir, case, domain, profile):
     path, ids, res, offs = _load(golden_dir, case, domain)
