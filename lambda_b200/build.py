@@ -20,15 +20,26 @@ def sources():
     return deps
 
 
+CLI = os.path.join(os.path.dirname(HERE), "bin", "lambda3_b200")
+
+
 def build(force=False, verbose=False):
     deps = sources()
-    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= _newest(deps):
-        return OUT
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, os.path.join(SRC, "engine.cu"), "-o", OUT]
-    if verbose:
-        print(" ".join(cmd), file=sys.stderr)
-    subprocess.check_call(cmd)
+    if force or not os.path.exists(OUT) or os.path.getmtime(OUT) < _newest(deps):
+        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+        cmd = [nvcc, *NVCC_FLAGS, os.path.join(SRC, "engine.cu"), "-o", OUT]
+        if verbose:
+            print(" ".join(cmd), file=sys.stderr)
+        subprocess.check_call(cmd)
+    # host program with the lambda3 search command line, linked against the C ABI only
+    main = os.path.join(SRC, "main.cpp")
+    if force or not os.path.exists(CLI) or os.path.getmtime(CLI) < max(os.path.getmtime(main), os.path.getmtime(OUT)):
+        os.makedirs(os.path.dirname(CLI), exist_ok=True)
+        cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-Wextra", main, "-o", CLI, "-L" + HERE, "-llambda_b200",
+               "-Wl,-rpath,$ORIGIN/../lambda_b200", "-pthread"]
+        if verbose:
+            print(" ".join(cmd), file=sys.stderr)
+        subprocess.check_call(cmd)
     return OUT
 
 

@@ -17,6 +17,7 @@
 // No CPU fallback exists: if CUDA is unavailable every entry point fails with LGPU_ERR_CUDA.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -154,9 +155,10 @@ struct lgpu_ctx
     DevBuf<unsigned int>       dPerm, dPermB, dHead, dScan;
     DevBuf<unsigned char>      dCubTemp;
     DevBuf<int>                dScores, dScores2, dMinBit, dMinEval;
-    DevBuf<unsigned int>       dWork, dBestPos, dBoundary, dOrder, dOrderB, dClassInfo;
+    DevBuf<unsigned int>       dWork, dBestPos, dBoundary, dOrder, dOrderB, dClassInfo, dSegStart, dSegStartB, dJobHead, dJobPos, dJobs;
     DevBuf<unsigned long long> dClassKeys, dClassKeysB;
     bool                       dpxOk = false; // scoring fits the int8 profile of the DPX kernel
+    bool                       forceWarpSeeding = false; // LAMBDA_B200_SEED=warp: warp-per-query seeding in every phase
     DevBuf<unsigned char>      dTrace;
     DevBuf<unsigned long long> dTraceOff;
     DevBuf<lgpu_hit>           dHits;
@@ -331,7 +333,13 @@ static uint64_t runSeeding(lgpu_ctx & c, lgpu_search_opts const & so, unsigned i
         P.out              = c.dMatches.p;
         P.cap              = c.dMatches.cap;
         P.counters         = c.dCounters.p;
-        seedKernel<<<gridFor(nActive, 128), 128, 0, c.stream>>>(P);
+        // phase-2 style seeds (one mismatch, half-exact) have a wide search tree per seed: one warp per
+        // query; exact seeds keep one thread per query (more independent chains in flight)
+        bool const warpPerQuery = (so.max_seed_dist != 0 && c.params.seed_half_exact) || c.forceWarpSeeding;
+        if (warpPerQuery)
+            seedWarpKernel<<<gridFor(static_cast<unsigned long long>(nActive) * 32, 128), 128, 0, c.stream>>>(P);
+        else
+            seedKernel<<<gridFor(nActive, 128), 128, 0, c.stream>>>(P);
         LGPU_CUDA(cudaGetLastError());
         if (st)
             st->kernel_launches += 1;
@@ -472,19 +480,24 @@ template <int T, int K>
 static void launchDpx(lgpu_ctx & c, DpxParams P, unsigned int maxNt)
 {
     constexpr int G = 32 / T;
-    P.winCap        = (maxNt + 4 * T + 15) / 16 * 16;
-    size_t const smem = static_cast<size_t>(G) * (static_cast<size_t>(P.nCodes) * dpxRowWords(T, K) * 4 + P.winCap);
+    P.winCap        = (maxNt + 4 * T + 127) / 128 * 128;
+    size_t const smem = static_cast<size_t>(P.nCodes) * dpxRowWords(T, K) * 4 + static_cast<size_t>(G) * (P.winCap + 32);
     LGPU_CUDA(cudaFuncSetAttribute(swScoreDpxKernel<T, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if (smem > 227 * 1024)
         throw CudaError("DPX score kernel: window too long for shared memory");
-    unsigned int const need = (P.nTasks + G - 1) / G;
-    unsigned int const grid = std::min<unsigned int>(need, static_cast<unsigned int>(c.numSMs) * 24);
+    unsigned int const grid = std::min<unsigned int>(P.nJobs, static_cast<unsigned int>(c.numSMs) * 32);
     swScoreDpxKernel<T, K><<<grid, 32, smem, c.stream>>>(P);
     LGPU_CUDA(cudaGetLastError());
 }
 
-// DP pass 1: scores into dScores[0..n).  Tasks are bucketed by query length into (T, K) classes of the
-// packed DPX kernel and sorted by window length inside a class; whatever does not fit (queries > 2048,
+struct MaxOp
+{
+    __host__ __device__ unsigned int operator()(unsigned int a, unsigned int b) const { return a > b ? a : b; }
+};
+
+// DP pass 1: scores into dScores[0..n).  Alignments are sorted by (length class of the query, query,
+// window length); up to 32/T consecutive alignments of one query form a job of the packed DPX kernel
+// (one shared query profile per warp).  Whatever does not fit the packed kernel (queries > 2048,
 // windows > 8192, exotic scoring) runs on the scalar wavefront kernel.
 static void runScorePass(lgpu_ctx & c, lgpu_match const * dTasks, unsigned int n, TaskDims const & dims, int * dScores,
                          lgpu_stats * st)
@@ -497,31 +510,47 @@ static void runScorePass(lgpu_ctx & c, lgpu_match const * dTasks, unsigned int n
     c.dClassKeysB.reserve(n);
     c.dOrder.reserve(n);
     c.dOrderB.reserve(n);
-    c.dClassInfo.reserve(2 * NC + 4);
+    c.dSegStart.reserve(n);
+    c.dSegStartB.reserve(n);
+    c.dJobHead.reserve(n);
+    c.dJobPos.reserve(n);
+    c.dJobs.reserve(n);
+    c.dClassInfo.reserve(3 * NC + 4);
     c.dCounters.reserve(8);
     c.dWork.reserve(NC + 1);
-    LGPU_CUDA(cudaMemsetAsync(c.dClassInfo.p, 0, (2 * NC + 4) * 4, c.stream));
+    LGPU_CUDA(cudaMemsetAsync(c.dClassInfo.p, 0, (3 * NC + 4) * 4, c.stream));
     LGPU_CUDA(cudaMemsetAsync(c.dCounters.p, 0, 8 * sizeof(unsigned long long), c.stream));
     LGPU_CUDA(cudaMemsetAsync(c.dWork.p, 0, (NC + 1) * 4, c.stream));
-    classifyKernel<<<gridFor(n, 256), 256, 0, c.stream>>>(dTasks, n, c.dClassKeys.p, c.dOrder.p, c.dClassInfo.p,
-                                                          c.dClassInfo.p + NC, c.dCounters.p);
-    size_t tmp = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp, c.dClassKeys.p, c.dClassKeysB.p, c.dOrder.p, c.dOrderB.p, static_cast<int>(n), 0,
-                                    40, c.stream);
-    c.dCubTemp.reserve(tmp);
+    unsigned int const g = gridFor(n, 256);
+    int const          nI = static_cast<int>(n);
+    classifyKernel<<<g, 256, 0, c.stream>>>(dTasks, n, c.dClassKeys.p, c.dOrder.p, c.dClassInfo.p, c.dClassInfo.p + NC,
+                                            c.dCounters.p);
+    size_t t1 = 0, t2 = 0, t3 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, t1, c.dClassKeys.p, c.dClassKeysB.p, c.dOrder.p, c.dOrderB.p, nI, 0, 64, c.stream);
+    cub::DeviceScan::InclusiveScan(nullptr, t2, c.dSegStart.p, c.dSegStartB.p, MaxOp(), nI, c.stream);
+    cub::DeviceScan::InclusiveSum(nullptr, t3, c.dJobHead.p, c.dJobPos.p, nI, c.stream);
+    c.dCubTemp.reserve(std::max(t1, std::max(t2, t3)));
     size_t tb = c.dCubTemp.cap;
-    LGPU_CUDA(cub::DeviceRadixSort::SortPairs(c.dCubTemp.p, tb, c.dClassKeys.p, c.dClassKeysB.p, c.dOrder.p, c.dOrderB.p,
-                                              static_cast<int>(n), 0, 40, c.stream));
-    unsigned int       info[2 * NC];
+    LGPU_CUDA(cub::DeviceRadixSort::SortPairs(c.dCubTemp.p, tb, c.dClassKeys.p, c.dClassKeysB.p, c.dOrder.p, c.dOrderB.p, nI, 0, 64,
+                                              c.stream));
+    segFlagKernel<<<g, 256, 0, c.stream>>>(c.dClassKeysB.p, n, c.dSegStart.p);
+    tb = c.dCubTemp.cap;
+    LGPU_CUDA(cub::DeviceScan::InclusiveScan(c.dCubTemp.p, tb, c.dSegStart.p, c.dSegStartB.p, MaxOp(), nI, c.stream));
+    jobHeadKernel<<<g, 256, 0, c.stream>>>(c.dClassKeysB.p, c.dSegStartB.p, n, c.dJobHead.p, c.dClassInfo.p + 2 * NC);
+    tb = c.dCubTemp.cap;
+    LGPU_CUDA(cub::DeviceScan::InclusiveSum(c.dCubTemp.p, tb, c.dJobHead.p, c.dJobPos.p, nI, c.stream));
+    jobEmitKernel<<<g, 256, 0, c.stream>>>(c.dJobHead.p, c.dJobPos.p, n, c.dJobs.p);
+    LGPU_CUDA(cudaGetLastError());
+    unsigned int       info[3 * NC];
     unsigned long long cells = 0;
     LGPU_CUDA(cudaMemcpyAsync(info, c.dClassInfo.p, sizeof(info), cudaMemcpyDeviceToHost, c.stream));
     LGPU_CUDA(cudaMemcpyAsync(&cells, c.dCounters.p, 8, cudaMemcpyDeviceToHost, c.stream));
     LGPU_CUDA(cudaStreamSynchronize(c.stream));
-    unsigned int launches = 2;
-    unsigned int off      = 0;
+    unsigned int launches = 7;
+    unsigned int taskOff = 0, jobOff = 0;
     for (int cls = 0; cls < NC; ++cls)
     {
-        unsigned int const cnt = info[cls], maxNt = info[NC + cls];
+        unsigned int const cnt = info[cls], maxNt = info[NC + cls], nJobs = info[2 * NC + cls];
         if (cnt == 0)
             continue;
         bool const scalar = (cls == kNumDpxClasses) || !c.dpxOk;
@@ -531,8 +560,11 @@ static void runScorePass(lgpu_ctx & c, lgpu_match const * dTasks, unsigned int n
             P.ix          = c.index->dev;
             P.Q           = c.Q;
             P.tasks       = dTasks;
-            P.order       = c.dOrderB.p + off;
-            P.nTasks      = cnt;
+            P.order       = c.dOrderB.p;
+            P.keys        = c.dClassKeysB.p;
+            P.nSorted     = n;
+            P.jobs        = c.dJobs.p + jobOff;
+            P.nJobs       = nJobs;
             P.sbjFrames   = c.di.sbjNumFrames;
             P.matrix      = c.dMatrix.p;
             P.go          = c.scoring.gapOpenSeqan;
@@ -562,14 +594,15 @@ static void runScorePass(lgpu_ctx & c, lgpu_match const * dTasks, unsigned int n
             int const          K    = chooseK(dims.maxQ);
             unsigned int const grid = std::min<unsigned int>((cnt + 3) / 4, static_cast<unsigned int>(c.numSMs) * 16);
             ExtParams          P    = baseExtParams(c, dTasks, cnt, grid, d2, K);
-            P.order                 = c.dOrderB.p + off;
+            P.order                 = c.dOrderB.p + taskOff;
             P.workCounter           = c.dWork.p + cls;
             P.scores                = dScores;
             launchWavefront<false>(K, P, grid, c.stream);
             LGPU_CUDA(cudaGetLastError());
         }
         ++launches;
-        off += cnt;
+        taskOff += cnt;
+        jobOff += nJobs;
     }
     if (st)
     {
@@ -968,6 +1001,8 @@ int lgpu_ctx_create(lgpu_ctx ** out, lgpu_index const * ix, lgpu_params const * 
         c->dMatrix.reserve(1024);
         LGPU_CUDA(cudaMemcpy(c->dMatrix.p, c->scoring.matrix, 1024, cudaMemcpyHostToDevice));
         c->dCounters.reserve(8);
+        if (char const * e = std::getenv("LAMBDA_B200_SEED"))
+            c->forceWarpSeeding = std::strcmp(e, "warp") == 0;
         // the packed kernel stores (score - gapOpen) as int8 profile bytes with -128 reserved for "null"
         c->dpxOk = c->scoring.alphSize < 32 && c->scoring.gapOpenSeqan <= c->scoring.gapExtend && c->scoring.gapExtend <= 0;
         for (int a = 0; a < c->scoring.alphSize; ++a)

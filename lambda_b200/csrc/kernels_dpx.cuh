@@ -39,10 +39,13 @@ struct DpxParams
 {
     DevIndex             ix;
     DevQueries           Q;
-    lgpu_match const *   tasks;
-    unsigned int const * order; // task indices of this class, sorted by window length
-    unsigned int         nTasks; // entries in `order`
-    unsigned int         sbjFrames;
+    lgpu_match const *         tasks;
+    unsigned int const *       order;   // task indices sorted by (class, query, window length)
+    unsigned long long const * keys;    // the sort keys belonging to `order`
+    unsigned int               nSorted; // entries in order / keys
+    unsigned int const *       jobs;    // first sorted slot of every job of this class
+    unsigned int               nJobs;
+    unsigned int               sbjFrames;
     signed char const *  matrix; // 32 x 32
     int                  go, ge;
     unsigned int         nCodes; // alphabet size + 1 (last row = null)
@@ -58,11 +61,17 @@ __device__ __forceinline__ unsigned int prmt(unsigned int a, unsigned int b, uns
     return d;
 }
 
+// words per profile row: ((K+3)/4) * 2T rounded up to a multiple of 32, plus 8, so that rows of
+// different residue codes start 8 banks apart (the groups of a warp read different rows at once)
 __host__ __device__ constexpr int dpxRowWords(int T, int K)
 {
-    return (((K + 3) / 4) * 2 * T + 31) / 32 * 32;
+    return (((K + 3) / 4) * 2 * T + 31) / 32 * 32 + ((T == 32) ? 0 : 8);
 }
 
+constexpr unsigned int kDpxSegShift = 20; // sort key = class << 60 | qryId << 20 | min(nt, 2^20 - 1)
+
+// A job = up to G = 32/T consecutive (sorted) alignments of the SAME query: the warp builds the query
+// profile once in shared memory and its G groups run one alignment each against it.
 template <int T, int K>
 __global__ void __launch_bounds__(32) swScoreDpxKernel(DpxParams P)
 {
@@ -76,11 +85,10 @@ __global__ void __launch_bounds__(32) swScoreDpxKernel(DpxParams P)
     unsigned int const grp  = lane / T;
     unsigned int const gl   = lane % T;
     unsigned int const profWords = P.nCodes * ROWW;
-    unsigned int const grpWords  = profWords + P.winCap / 4;
-    unsigned int *     prof = smem + grp * grpWords;
-    unsigned char *    win  = reinterpret_cast<unsigned char *>(prof + profWords);
+    unsigned int *     prof = smem;
+    // window buffers of the groups start 8 banks apart as well (winCap is a multiple of 128 bytes)
+    unsigned char *    win  = reinterpret_cast<unsigned char *>(smem + profWords) + grp * (P.winCap + 32);
     unsigned int const nullCode = P.nCodes - 1;
-    unsigned int const grpMask  = (T == 32) ? 0xffffffffu : (((1u << T) - 1u) << (grp * T));
 
     unsigned int const go2  = (static_cast<unsigned int>(P.go) & 0xffffu) * 0x10001u;
     unsigned int const ge2  = (static_cast<unsigned int>(P.ge) & 0xffffu) * 0x10001u;
@@ -88,28 +96,32 @@ __global__ void __launch_bounds__(32) swScoreDpxKernel(DpxParams P)
 
     for (;;)
     {
-        unsigned int base = 0;
+        unsigned int job = 0;
         if (lane == 0)
-            base = atomicAdd(P.workCounter, static_cast<unsigned int>(G));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= P.nTasks)
+            job = atomicAdd(P.workCounter, 1u);
+        job = __shfl_sync(0xffffffffu, job, 0);
+        if (job >= P.nJobs)
             break;
-        unsigned int const slot  = base + grp;
-        bool const         valid = slot < P.nTasks;
-        unsigned int       task  = 0, nq = 0, nt = 0;
-        unsigned char const *qs = nullptr, *ts = nullptr;
+        unsigned int const       slot0 = P.jobs[job];
+        unsigned long long const seg   = P.keys[slot0] >> kDpxSegShift;
+        unsigned int const       slot  = slot0 + grp;
+        bool const               valid = slot < P.nSorted && (P.keys[slot] >> kDpxSegShift) == seg;
+        // all alignments of a job share the query (frame): take it from the first one
+        lgpu_match const         m0   = P.tasks[P.order[slot0]];
+        unsigned int const       q    = m0.qry_id / P.Q.F;
+        unsigned int const       f    = m0.qry_id % P.Q.F;
+        unsigned long long const qb   = P.Q.offs[q];
+        unsigned int const       qLen = static_cast<unsigned int>(P.Q.offs[q + 1] - qb);
+        unsigned char const *    qs   = P.Q.trans + P.Q.F * qb + static_cast<unsigned long long>(f) * qLen + m0.qry_start;
+        unsigned int const       nq   = m0.qry_end - m0.qry_start;
+        unsigned int             task = 0, nt = 0;
+        unsigned char const *    ts   = nullptr;
         if (valid)
         {
-            task                          = P.order[slot];
-            lgpu_match const         m    = P.tasks[task];
-            unsigned int const       q    = m.qry_id / P.Q.F;
-            unsigned int const       f    = m.qry_id % P.Q.F;
-            unsigned long long const qb   = P.Q.offs[q];
-            unsigned int const       qLen = static_cast<unsigned int>(P.Q.offs[q + 1] - qb);
-            qs = P.Q.trans + P.Q.F * qb + static_cast<unsigned long long>(f) * qLen + m.qry_start;
-            nq = m.qry_end - m.qry_start;
-            ts = P.ix.seqs + P.ix.seqDelims[m.subj_id / P.sbjFrames] + m.subj_start;
-            nt = m.subj_end - m.subj_start;
+            task               = P.order[slot];
+            lgpu_match const m = P.tasks[task];
+            ts                 = P.ix.seqs + P.ix.seqDelims[m.subj_id / P.sbjFrames] + m.subj_start;
+            nt                 = m.subj_end - m.subj_start;
         }
         // the warp runs for its longest window; extra steps are null rows for the shorter ones
         unsigned int ntMax = nt;
@@ -120,7 +132,7 @@ __global__ void __launch_bounds__(32) swScoreDpxKernel(DpxParams P)
 
         __syncwarp();
         // ---- query profile: P[c][w][v], byte r%4 of word w = r/4 of strip v <-> column i = v*K + r ----
-        for (unsigned int idx = gl; idx < profWords; idx += T)
+        for (unsigned int idx = lane; idx < profWords; idx += 32)
         {
             unsigned int const c   = idx / ROWW;
             unsigned int const rem = idx % ROWW;
@@ -234,7 +246,6 @@ __global__ void __launch_bounds__(32) swScoreDpxKernel(DpxParams P)
             b = max(b, __shfl_xor_sync(0xffffffffu, b, off));
         if (valid && gl == 0)
             P.scores[task] = b - P.go;
-        (void) grpMask;
     }
 }
 
@@ -262,7 +273,13 @@ __host__ __device__ inline int dpxClassOf(unsigned int nq)
 
 constexpr unsigned int kDpxMaxWindow = 8192; // longer windows go to the scalar kernel
 
-// key = class << 32 | nt ; also per-class counts / max window / total cells
+// alignments per job (= groups per warp) of each class; the scalar class has one alignment per job
+__host__ __device__ inline unsigned int dpxGroupsOf(int cls)
+{
+    return cls <= 6 ? 4u : (cls <= 8 ? 2u : 1u);
+}
+
+// key = class << 60 | qryId << 20 | min(nt, 2^20-1) ; also per-class counts / max window / total cells
 __global__ void classifyKernel(lgpu_match const * tasks, unsigned int n, unsigned long long * keys, unsigned int * idx,
                                unsigned int * classCount, unsigned int * classMaxNt, unsigned long long * cells)
 {
@@ -275,7 +292,8 @@ __global__ void classifyKernel(lgpu_match const * tasks, unsigned int n, unsigne
         int                c  = dpxClassOf(nq);
         if (nt > kDpxMaxWindow)
             c = kNumDpxClasses;
-        keys[t] = (static_cast<unsigned long long>(c) << 32) | nt;
+        keys[t] = (static_cast<unsigned long long>(c) << 60) | (static_cast<unsigned long long>(tasks[t].qry_id) << kDpxSegShift) |
+                  (nt < (1u << kDpxSegShift) ? nt : (1u << kDpxSegShift) - 1u);
         idx[t]  = t;
         atomicAdd(&classCount[c], 1u);
         atomicMax(&classMaxNt[c], nt);
@@ -297,6 +315,35 @@ __global__ void classifyKernel(lgpu_match const * tasks, unsigned int n, unsigne
         if (s)
             atomicAdd(cells, s);
     }
+}
+
+// segStart[t] = t if sorted slot t opens a new (class, query) segment else 0  (max-scanned afterwards)
+__global__ void segFlagKernel(unsigned long long const * keys, unsigned int n, unsigned int * segStart)
+{
+    unsigned int const t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n)
+        segStart[t] = (t == 0 || (keys[t] >> kDpxSegShift) != (keys[t - 1] >> kDpxSegShift)) ? t : 0u;
+}
+
+// head[t] = 1 iff slot t is the first alignment of a job; counts the jobs per class
+__global__ void jobHeadKernel(unsigned long long const * keys, unsigned int const * segStart, unsigned int n, unsigned int * head,
+                              unsigned int * classJobs)
+{
+    unsigned int const t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n)
+        return;
+    int const          cls = static_cast<int>(keys[t] >> 60);
+    unsigned int const h   = ((t - segStart[t]) % dpxGroupsOf(cls)) == 0 ? 1u : 0u;
+    head[t]                = h;
+    if (h)
+        atomicAdd(&classJobs[cls], 1u);
+}
+
+__global__ void jobEmitKernel(unsigned int const * head, unsigned int const * posIncl, unsigned int n, unsigned int * jobs)
+{
+    unsigned int const t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n && head[t])
+        jobs[posIncl[t] - 1] = t;
 }
 
 } // namespace lgpu

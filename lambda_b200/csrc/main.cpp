@@ -1,0 +1,368 @@
+// lambda3_b200 -- host program with the lambda3 searchp / searchn command line.
+//
+// Replaces the loop body of the reference's realMain() (src/search.cpp:345-477) by calls through the C
+// ABI (include/lambda_b200.h): load the reference's own .lba index, read the query FASTA, hand large
+// query blocks to the device engine, write BLAST tabular (.m8).  Flags, defaults and profiles follow
+// src/search_options.hpp; only the options that influence the hot path are accepted (output formats
+// other than .m8, taxonomy/LCA and lazy query loading stay with the reference).
+//
+// Record order: the reference with -t 1 processes batches of `records_per_batch` queries
+// (src/search_algo.hpp:354-356) and writes, per batch, the phase-1 successes in query order followed by
+// that batch's phase-2 hits (src/search.cpp:449-457).  We reproduce exactly that order, so the file is
+// byte-identical to `lambda3 search* -t 1`, not merely equal as a multiset.
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/lambda_b200.h"
+
+namespace
+{
+
+struct Options
+{
+    uint32_t    domain = LGPU_DOMAIN_PROTEIN;
+    std::string query, index, output = "output.m8", profile = "none";
+    int         verbosity = 1;
+    int         threads   = 1; // only used for the reference's records_per_batch formula
+    int         gpus      = 1;
+    uint64_t    blockSize = 100000;
+    lgpu_params params{};
+};
+
+[[noreturn]] void die(std::string const & msg)
+{
+    std::fprintf(stderr, "ERROR: %s\n", msg.c_str());
+    std::exit(255); // the reference returns -1
+}
+
+bool endsWith(std::string const & s, char const * suf)
+{
+    size_t const n = std::strlen(suf);
+    return s.size() >= n && s.compare(s.size() - n, n, suf) == 0;
+}
+
+void usage()
+{
+    std::puts("lambda3_b200 searchp|searchn -q QUERY.fasta -i INDEX.lba [-o output.m8] [OPTIONS]\n"
+              "  -p, --profile          none|fast|sensitive|pairs-default|pairs-sensitive\n"
+              "  -e, --e-value          maximum e-value (default 0.01; -1 = off)\n"
+              "      --bit-score        minimum bit score (default -1 = off)\n"
+              "      --percent-identity minimum identity in percent (default 0)\n"
+              "  -n, --num-matches      maximum matches per query (default 25)\n"
+              "      --seed-length / --seed-offset / --seed-delta           phase-2 seeds\n"
+              "      --seed-length0 / --seed-offset0 / --seed-delta0        phase-1 seeds\n"
+              "      --adaptive-seeding 0|1   --seed-half-exact 0|1   --iterative-search 0|1\n"
+              "      --pre-scoring N    --pre-scoring-threshold X\n"
+              "  -s, --scoring-scheme   45|62|80 (searchp)   --score-gap  --score-gap-open\n"
+              "      --score-match / --score-mismatch (searchn)\n"
+              "  -t, --threads          accepted for compatibility (affects record order only)\n"
+              "      --gpus N           shard the queries over N GPUs (default 1)\n"
+              "      --block-size N     queries per device batch (default 100000)\n"
+              "  -v, --verbosity        0|1|2\n");
+}
+
+void parse(int argc, char ** argv, Options & o)
+{
+    if (argc < 2)
+    {
+        usage();
+        std::exit(255);
+    }
+    std::string const cmd = argv[1];
+    if (cmd == "searchp")
+        o.domain = LGPU_DOMAIN_PROTEIN;
+    else if (cmd == "searchn")
+        o.domain = LGPU_DOMAIN_NUCLEOTIDE;
+    else if (cmd == "searchbs")
+        die("searchbs is not implemented by the GPU path yet; use the reference binary");
+    else if (cmd == "-h" || cmd == "--help")
+    {
+        usage();
+        std::exit(0);
+    }
+    else
+        die("unknown sub-command '" + cmd + "' (mkindex* stays with the reference's lambda3)");
+
+    // first pass: profile (defaults depend on it), then explicit overrides in order
+    for (int i = 2; i + 1 < argc; ++i)
+        if (!std::strcmp(argv[i], "-p") || !std::strcmp(argv[i], "--profile"))
+            o.profile = argv[i + 1];
+    if (lgpu_params_default(&o.params, o.domain, o.profile.c_str()) != LGPU_OK)
+        die("invalid profile '" + o.profile + "'");
+
+    auto need = [&](int & i) -> char const * {
+        if (i + 1 >= argc)
+            die(std::string("missing value for ") + argv[i]);
+        return argv[++i];
+    };
+    for (int i = 2; i < argc; ++i)
+    {
+        std::string const a = argv[i];
+        if (a == "-q" || a == "--query") o.query = need(i);
+        else if (a == "-i" || a == "--index") o.index = need(i);
+        else if (a == "-o" || a == "--output") o.output = need(i);
+        else if (a == "-p" || a == "--profile") need(i);
+        else if (a == "-e" || a == "--e-value") o.params.max_evalue = std::atof(need(i));
+        else if (a == "--bit-score") o.params.min_bit_score = std::atoi(need(i));
+        else if (a == "--percent-identity") o.params.id_cutoff = std::atoi(need(i));
+        else if (a == "-n" || a == "--num-matches") o.params.max_matches = static_cast<uint32_t>(std::atoi(need(i)));
+        else if (a == "--seed-length") o.params.opts.seed_length = static_cast<uint32_t>(std::atoi(need(i)));
+        else if (a == "--seed-offset") o.params.opts.seed_offset = static_cast<uint32_t>(std::atoi(need(i)));
+        else if (a == "--seed-delta") o.params.opts.max_seed_dist = static_cast<uint32_t>(std::atoi(need(i)));
+        else if (a == "--seed-length0") o.params.opts0.seed_length = static_cast<uint32_t>(std::atoi(need(i)));
+        else if (a == "--seed-offset0") o.params.opts0.seed_offset = static_cast<uint32_t>(std::atoi(need(i)));
+        else if (a == "--seed-delta0") o.params.opts0.max_seed_dist = static_cast<uint32_t>(std::atoi(need(i)));
+        else if (a == "--adaptive-seeding") o.params.adaptive_seeding = static_cast<uint32_t>(std::atoi(need(i)));
+        else if (a == "--seed-half-exact") o.params.seed_half_exact = static_cast<uint32_t>(std::atoi(need(i)));
+        else if (a == "--iterative-search") o.params.iterative_search = static_cast<uint32_t>(std::atoi(need(i)));
+        else if (a == "--pre-scoring") o.params.pre_scoring = std::atoi(need(i));
+        else if (a == "--pre-scoring-threshold") o.params.pre_scoring_thresh = std::atof(need(i));
+        else if (a == "-s" || a == "--scoring-scheme") o.params.scoring_method = std::atoi(need(i));
+        else if (a == "--score-gap") o.params.gap_extend = std::atoi(need(i));
+        else if (a == "--score-gap-open") o.params.gap_open = std::atoi(need(i));
+        else if (a == "--score-match") o.params.match = std::atoi(need(i));
+        else if (a == "--score-mismatch") o.params.mismatch = std::atoi(need(i));
+        else if (a == "-t" || a == "--threads") o.threads = std::max(1, std::atoi(need(i)));
+        else if (a == "--gpus") o.gpus = std::max(1, std::atoi(need(i)));
+        else if (a == "--block-size") o.blockSize = std::max<uint64_t>(1, std::strtoull(need(i), nullptr, 10));
+        else if (a == "-v" || a == "--verbosity") o.verbosity = std::atoi(need(i));
+        else if (a == "--version-to-outputfile") need(i); // only affects m9/m0/sam headers
+        else if (a == "-h" || a == "--help") { usage(); std::exit(0); }
+        else die("unknown option '" + a + "'");
+    }
+    if (o.query.empty() || o.index.empty())
+        die("-q and -i are required");
+    if (!endsWith(o.output, ".m8"))
+        die("only BLAST tabular output (.m8) is produced by the GPU path; other formats stay with the reference");
+    if (std::ifstream(o.output).good())
+        die("the output file already exists: " + o.output); // sharg's create_new validator
+}
+
+struct Fasta
+{
+    std::vector<std::string> ids;
+    std::vector<uint8_t>     residues;
+    std::vector<uint64_t>    offsets{0};
+};
+
+Fasta readFasta(std::string const & path, uint32_t domain)
+{
+    std::ifstream in(path, std::ios::binary);
+    if (!in)
+        die("cannot open query file " + path);
+    // char -> rank like BioC++ (aa27: unknown -> X; dna5: unknown -> N, U -> T)
+    uint8_t tab[256];
+    if (domain == LGPU_DOMAIN_PROTEIN)
+    {
+        std::memset(tab, 23, sizeof(tab));
+        char const * alph = "ABCDEFGHIJKLMNOPQRSTUVWXYZ*";
+        for (int r = 0; alph[r]; ++r)
+        {
+            tab[static_cast<uint8_t>(alph[r])] = static_cast<uint8_t>(r);
+            if (alph[r] >= 'A' && alph[r] <= 'Z')
+                tab[static_cast<uint8_t>(alph[r] - 'A' + 'a')] = static_cast<uint8_t>(r);
+        }
+    }
+    else
+    {
+        std::memset(tab, 3, sizeof(tab));
+        char const * alph = "ACGNT";
+        for (int r = 0; alph[r]; ++r)
+        {
+            tab[static_cast<uint8_t>(alph[r])]             = static_cast<uint8_t>(r);
+            tab[static_cast<uint8_t>(alph[r] - 'A' + 'a')] = static_cast<uint8_t>(r);
+        }
+        tab[static_cast<uint8_t>('U')] = tab[static_cast<uint8_t>('u')] = 4;
+    }
+    Fasta       f;
+    std::string line;
+    bool        have = false;
+    while (std::getline(in, line))
+    {
+        if (!line.empty() && line.back() == '\r')
+            line.pop_back();
+        if (line.empty())
+            continue;
+        if (line[0] == '>')
+        {
+            if (have)
+                f.offsets.push_back(f.residues.size());
+            f.ids.push_back(line.substr(1));
+            have = true;
+        }
+        else if (have)
+        {
+            for (char c : line)
+                if (c != ' ' && c != '\t')
+                    f.residues.push_back(tab[static_cast<uint8_t>(c)]);
+        }
+    }
+    if (have)
+        f.offsets.push_back(f.residues.size());
+    return f;
+}
+
+double now()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+struct ShardResult
+{
+    std::vector<lgpu_hit> hits; // q_id already global
+    lgpu_stats            stats{};
+    std::string           error;
+};
+
+void runShard(Options const & o, lgpu_index_desc const * desc, int device, Fasta const & f, uint64_t qBegin, uint64_t qEnd,
+              ShardResult & out)
+{
+    lgpu_index * ix = nullptr;
+    if (lgpu_index_create(&ix, desc, device) != LGPU_OK)
+    {
+        out.error = lgpu_last_error(nullptr);
+        return;
+    }
+    lgpu_ctx * ctx = nullptr;
+    if (lgpu_ctx_create(&ctx, ix, &o.params) != LGPU_OK)
+    {
+        out.error = lgpu_last_error(nullptr);
+        lgpu_index_destroy(ix);
+        return;
+    }
+    std::vector<uint64_t> offs;
+    for (uint64_t b = qBegin; b < qEnd; b += o.blockSize)
+    {
+        uint64_t const e = std::min(qEnd, b + o.blockSize);
+        offs.assign(f.offsets.begin() + b, f.offsets.begin() + e + 1);
+        uint64_t const base = offs[0];
+        for (auto & x : offs)
+            x -= base;
+        lgpu_query_batch qb{f.residues.data() + base, offs.data(), e - b, 0};
+        lgpu_hits        hits{};
+        if (lgpu_search_batch(ctx, &qb, &hits, &out.stats) != LGPU_OK)
+        {
+            out.error = lgpu_last_error(ctx);
+            break;
+        }
+        size_t const old = out.hits.size();
+        out.hits.insert(out.hits.end(), hits.hits, hits.hits + hits.n);
+        for (size_t i = old; i < out.hits.size(); ++i)
+            out.hits[i].q_id += static_cast<uint32_t>(b);
+    }
+    lgpu_ctx_destroy(ctx);
+    lgpu_index_destroy(ix);
+}
+
+} // namespace
+
+int main(int argc, char ** argv)
+{
+    Options o;
+    parse(argc, argv, o);
+    double const t0 = now();
+    if (o.verbosity >= 1)
+        std::printf("LAMBDA (B200 engine) - the Local Aligner for Massive Biological DatA\n\n");
+
+    lgpu_lba * lba = nullptr;
+    if (lgpu_lba_open(&lba, o.index.c_str()) != LGPU_OK)
+        die(lgpu_last_error(nullptr));
+    lgpu_index_desc const * desc = lgpu_lba_desc(lba);
+    double const            t1   = now();
+    Fasta const             f    = readFasta(o.query, o.domain);
+    uint64_t const          nQ   = f.ids.size();
+    double const            t2   = now();
+    if (o.verbosity >= 2)
+        std::printf("Index mapped in %.3fs (%llu subjects), %llu queries read in %.3fs\n", t1 - t0,
+                    static_cast<unsigned long long>(desc->n_seqs), static_cast<unsigned long long>(nQ), t2 - t1);
+
+    int const                nShards = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(o.gpus), std::max<uint64_t>(nQ, 1)));
+    std::vector<ShardResult> res(nShards);
+    std::vector<std::thread> th;
+    for (int g = 0; g < nShards; ++g)
+        th.emplace_back(runShard, std::cref(o), desc, g, std::cref(f), nQ * g / nShards, nQ * (g + 1) / nShards, std::ref(res[g]));
+    for (auto & t : th)
+        t.join();
+    lgpu_stats total{};
+    for (auto & r : res)
+    {
+        if (!r.error.empty())
+            die(r.error);
+        uint64_t const * s = reinterpret_cast<uint64_t const *>(&r.stats);
+        uint64_t *       d = reinterpret_cast<uint64_t *>(&total);
+        for (int k = 0; k < 16; ++k)
+            d[k] += s[k];
+        total.ms_total += r.stats.ms_total;
+    }
+    double const t3 = now();
+
+    // --- write records in the reference's -t 1 order ---
+    std::vector<std::vector<lgpu_hit const *>> perQuery(nQ);
+    for (auto const & r : res)
+        for (auto const & h : r.hits)
+            perQuery[h.q_id].push_back(&h);
+    uint64_t const rpb = std::max<uint64_t>(std::min<uint64_t>(nQ / (static_cast<uint64_t>(o.threads) * 10), 10), 1);
+    FILE *         fo  = std::fopen(o.output.c_str(), "wb");
+    if (!fo)
+        die("cannot create output file " + o.output);
+    std::vector<char> line(1 << 16);
+    auto              subjectId = [&](uint32_t s) {
+        return std::string(desc->ids + desc->id_delims[s], desc->ids + desc->id_delims[s + 1]);
+    };
+    // the reference chunks the queries per thread first (src/search.cpp:384-385), then into batches
+    for (int t = 0; t < o.threads; ++t)
+    {
+        uint64_t const cb = nQ * t / o.threads, ce = nQ * (t + 1) / o.threads;
+        for (uint64_t b = cb; b < ce; b += rpb)
+        {
+            uint64_t const e = std::min(ce, b + rpb);
+            for (int phase = 1; phase <= 2; ++phase)
+                for (uint64_t q = b; q < e; ++q)
+                    for (lgpu_hit const * h : perQuery[q])
+                        if (h->phase == phase)
+                        {
+                            int const n = lgpu_format_m8(&o.params, h, f.ids[q].c_str(), subjectId(h->s_id).c_str(),
+                                                         line.data(), line.size());
+                            if (n > 0)
+                                std::fwrite(line.data(), 1, static_cast<size_t>(n), fo);
+                        }
+        }
+    }
+    std::fclose(fo);
+    lgpu_lba_close(lba);
+    double const t4 = now();
+
+    if (o.verbosity >= 2)
+    {
+        std::printf("Runtime total: %.3fs (search %.3fs incl. index upload, output %.3fs)\n\n", t4 - t0, t3 - t2, t4 - t3);
+        std::printf("   HITS                             Remaining\n");
+        uint64_t rem = total.hits_after_seeding;
+        std::printf("   after Seeding               %10llu\n", static_cast<unsigned long long>(rem));
+        auto row = [&](char const * name, uint64_t v) {
+            rem -= v;
+            std::printf(" - %-24s %10llu = %10llu\n", name, static_cast<unsigned long long>(v),
+                        static_cast<unsigned long long>(rem));
+        };
+        row("failed pre-extend test", total.hits_failed_pre_extend);
+        row("failed e-value test", total.hits_failed_evalue);
+        row("failed bitScore test", total.hits_failed_bitscore);
+        row("failed %-identity test", total.hits_failed_identity);
+        row("duplicates", total.hits_duplicate);
+        row("late duplicates", total.hits_duplicate2);
+        row("abundant", total.hits_abundant);
+        std::printf("\nNumber of total hits:                           %llu\n", static_cast<unsigned long long>(total.hits_final));
+        std::printf("Number of Query-Subject pairs:                  %llu\n", static_cast<unsigned long long>(total.pairs));
+        std::printf("Number of Queries with at least one valid hit:  %llu\n", static_cast<unsigned long long>(total.qrys_with_hit));
+        std::printf("GPU: %llu kernel launches, %.1f ms device time, %.2f Gcells pass 1, %.2f Gcells pass 2\n",
+                    static_cast<unsigned long long>(total.kernel_launches), total.ms_total, total.cells_score / 1e9,
+                    total.cells_trace / 1e9);
+    }
+    return 0;
+}

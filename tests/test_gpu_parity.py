@@ -221,3 +221,24 @@ def test_search_vs_live_reference_binary(tmp_path, family):
     assert len(ref) >= 400
     assert sorted(s.m8(hits, ids)) == sorted(ref)
     s.close(); ix.close()
+
+
+CLI = os.path.join(ROOT, "bin", "lambda3_b200")
+
+
+@pytest.mark.skipif(not os.path.exists(CLI), reason="bin/lambda3_b200 not built")
+@pytest.mark.parametrize("case,domain,profile", [("prot_flat", 0, "none"), ("prot_diverged", 0, "none"),
+                                                 ("prot_family", 0, "sensitive"), ("nucl", 1, "none")])
+def test_cli_output_is_byte_identical_to_reference(golden_dir, tmp_path, case, domain, profile):
+    """the host program keeps the lambda3 command line and reproduces the reference's -t 1 file, in order"""
+    out = tmp_path / "out.m8"
+    cmd = [CLI, "searchp" if domain == 0 else "searchn", "-q", os.path.join(golden_dir, case, "q.fasta"), "-i",
+           os.path.join(golden_dir, case, "db.lba"), "-o", str(out), "-t", "1", "--version-to-outputfile", "0", "-v", "2"]
+    if profile != "none":
+        cmd += ["-p", profile]
+    txt = subprocess.run(cmd, check=True, capture_output=True, text=True).stdout
+    ref, funnel = load_golden(golden_dir, case, profile)
+    assert open(out).read() == "".join(ref)
+    assert f"Number of total hits:                           {funnel['hits_final']}" in txt
+    # refuses to overwrite, like the reference's create_new validator
+    assert subprocess.run(cmd, capture_output=True).returncode != 0
