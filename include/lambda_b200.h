@@ -220,7 +220,7 @@ typedef struct
     uint64_t kernel_launches;    /* kernels launched by this library           */
     /* CUDA-event times on the context's stream, milliseconds */
     float ms_seed, ms_sort_merge, ms_extend_score, ms_extend_trace, ms_h2d, ms_d2h, ms_total;
-    float reserved;
+    float ms_host; /* host-only work inside the call: score thresholds, e-values, record finalisation */
 } lgpu_stats;
 
 /* search() + iterateMatches() + iterativeSearchPre/Post [+ writeRecords] for one batch.  Blocking.

@@ -50,7 +50,7 @@ STATS_U64 = ("hits_after_seeding", "hits_failed_pre_extend", "hits_failed_evalue
              "qrys_with_hit", "n_extensions_score", "n_extensions_trace", "cells_score", "cells_trace",
              "kernel_launches")
 STATS_F32 = ("ms_seed", "ms_sort_merge", "ms_extend_score", "ms_extend_trace", "ms_h2d", "ms_d2h", "ms_total",
-             "reserved")
+             "ms_host")
 STATS_DT = np.dtype([(n, "<u8") for n in STATS_U64] + [(n, "<f4") for n in STATS_F32])
 assert STATS_DT.itemsize == 160
 

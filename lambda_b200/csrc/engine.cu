@@ -16,6 +16,7 @@
 //
 // No CPU fallback exists: if CUDA is unavailable every entry point fails with LGPU_ERR_CUDA.
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -86,6 +87,46 @@ struct DevBuf
         size_t const want = std::max<size_t>(n + n / 4, 256);
         LGPU_CUDA(cudaMalloc(reinterpret_cast<void **>(&p), want * sizeof(T)));
         cap = want;
+    }
+};
+
+// growable pinned host staging buffer (async copies from/to pageable memory are staged and slow)
+template <typename T>
+struct PinnedBuf
+{
+    T *    p   = nullptr;
+    size_t cap = 0;
+    ~PinnedBuf()
+    {
+        if (p)
+            cudaFreeHost(p);
+    }
+    PinnedBuf()                              = default;
+    PinnedBuf(PinnedBuf const &)             = delete;
+    PinnedBuf & operator=(PinnedBuf const &) = delete;
+    void        reserve(size_t n)
+    {
+        if (n <= cap)
+            return;
+        if (p)
+            cudaFreeHost(p);
+        p                 = nullptr;
+        cap               = 0;
+        size_t const want = std::max<size_t>(n + n / 4, 256);
+        LGPU_CUDA(cudaMallocHost(reinterpret_cast<void **>(&p), want * sizeof(T)));
+        cap = want;
+    }
+};
+
+struct HostTimer
+{
+    float *                               acc;
+    std::chrono::steady_clock::time_point t0;
+    explicit HostTimer(float * a) : acc(a), t0(std::chrono::steady_clock::now()) {}
+    ~HostTimer()
+    {
+        if (acc)
+            *acc += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
 };
 
@@ -162,6 +203,11 @@ struct lgpu_ctx
     DevBuf<unsigned char>      dTrace;
     DevBuf<unsigned long long> dTraceOff;
     DevBuf<lgpu_hit>           dHits;
+
+    // pinned staging
+    PinnedBuf<lgpu_match> hTasks;
+    PinnedBuf<lgpu_hit>   hHits;
+    PinnedBuf<int>        hThresh;
 
     // host results
     std::vector<lgpu_hit>   hits;
@@ -438,13 +484,13 @@ struct TaskDims
     uint64_t     cells = 0;
 };
 
-// host copy of the task list (needed for trace-buffer layout and work statistics)
-static TaskDims taskDims(std::vector<lgpu_match> const & tasks)
+// dimensions of a host-side task list (trace-buffer layout, work statistics)
+static TaskDims taskDims(lgpu_match const * tasks, size_t n)
 {
     TaskDims d;
-    for (lgpu_match const & m : tasks)
+    for (size_t i = 0; i < n; ++i)
     {
-        unsigned int const nq = m.qry_end - m.qry_start, nt = m.subj_end - m.subj_start;
+        unsigned int const nq = tasks[i].qry_end - tasks[i].qry_start, nt = tasks[i].subj_end - tasks[i].subj_start;
         d.maxQ                = std::max(d.maxQ, nq);
         d.maxT                = std::max(d.maxT, nt);
         d.cells += static_cast<uint64_t>(nq) * nt;
@@ -499,8 +545,7 @@ struct MaxOp
 // window length); up to 32/T consecutive alignments of one query form a job of the packed DPX kernel
 // (one shared query profile per warp).  Whatever does not fit the packed kernel (queries > 2048,
 // windows > 8192, exotic scoring) runs on the scalar wavefront kernel.
-static void runScorePass(lgpu_ctx & c, lgpu_match const * dTasks, unsigned int n, TaskDims const & dims, int * dScores,
-                         lgpu_stats * st)
+static void runScorePass(lgpu_ctx & c, lgpu_match const * dTasks, unsigned int n, int * dScores, lgpu_stats * st)
 {
     if (n == 0)
         return;
@@ -524,7 +569,7 @@ static void runScorePass(lgpu_ctx & c, lgpu_match const * dTasks, unsigned int n
     unsigned int const g = gridFor(n, 256);
     int const          nI = static_cast<int>(n);
     classifyKernel<<<g, 256, 0, c.stream>>>(dTasks, n, c.dClassKeys.p, c.dOrder.p, c.dClassInfo.p, c.dClassInfo.p + NC,
-                                            c.dCounters.p);
+                                            c.dClassInfo.p + 3 * NC, c.dCounters.p);
     size_t t1 = 0, t2 = 0, t3 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, t1, c.dClassKeys.p, c.dClassKeysB.p, c.dOrder.p, c.dOrderB.p, nI, 0, 64, c.stream);
     cub::DeviceScan::InclusiveScan(nullptr, t2, c.dSegStart.p, c.dSegStartB.p, MaxOp(), nI, c.stream);
@@ -533,7 +578,7 @@ static void runScorePass(lgpu_ctx & c, lgpu_match const * dTasks, unsigned int n
     size_t tb = c.dCubTemp.cap;
     LGPU_CUDA(cub::DeviceRadixSort::SortPairs(c.dCubTemp.p, tb, c.dClassKeys.p, c.dClassKeysB.p, c.dOrder.p, c.dOrderB.p, nI, 0, 64,
                                               c.stream));
-    segFlagKernel<<<g, 256, 0, c.stream>>>(c.dClassKeysB.p, n, c.dSegStart.p);
+    segFlagKernel<<<g, 256, 0, c.stream>>>(c.dClassKeysB.p, c.dOrderB.p, dTasks, n, c.dSegStart.p);
     tb = c.dCubTemp.cap;
     LGPU_CUDA(cub::DeviceScan::InclusiveScan(c.dCubTemp.p, tb, c.dSegStart.p, c.dSegStartB.p, MaxOp(), nI, c.stream));
     jobHeadKernel<<<g, 256, 0, c.stream>>>(c.dClassKeysB.p, c.dSegStartB.p, n, c.dJobHead.p, c.dClassInfo.p + 2 * NC);
@@ -541,7 +586,7 @@ static void runScorePass(lgpu_ctx & c, lgpu_match const * dTasks, unsigned int n
     LGPU_CUDA(cub::DeviceScan::InclusiveSum(c.dCubTemp.p, tb, c.dJobHead.p, c.dJobPos.p, nI, c.stream));
     jobEmitKernel<<<g, 256, 0, c.stream>>>(c.dJobHead.p, c.dJobPos.p, n, c.dJobs.p);
     LGPU_CUDA(cudaGetLastError());
-    unsigned int       info[3 * NC];
+    unsigned int       info[3 * NC + 1];
     unsigned long long cells = 0;
     LGPU_CUDA(cudaMemcpyAsync(info, c.dClassInfo.p, sizeof(info), cudaMemcpyDeviceToHost, c.stream));
     LGPU_CUDA(cudaMemcpyAsync(&cells, c.dCounters.p, 8, cudaMemcpyDeviceToHost, c.stream));
@@ -589,9 +634,10 @@ static void runScorePass(lgpu_ctx & c, lgpu_match const * dTasks, unsigned int n
         }
         else
         {
-            TaskDims d2 = dims;
-            d2.maxT     = std::max(d2.maxT, maxNt);
-            int const          K    = chooseK(dims.maxQ);
+            TaskDims d2;
+            d2.maxQ = info[3 * NC];
+            d2.maxT = maxNt;
+            int const          K    = chooseK(d2.maxQ);
             unsigned int const grid = std::min<unsigned int>((cnt + 3) / 4, static_cast<unsigned int>(c.numSMs) * 16);
             ExtParams          P    = baseExtParams(c, dTasks, cnt, grid, d2, K);
             P.order                 = c.dOrderB.p + taskOff;
@@ -612,24 +658,24 @@ static void runScorePass(lgpu_ctx & c, lgpu_match const * dTasks, unsigned int n
     }
 }
 
-// DP pass 2 + traceback for tasks (host copy `tasks`, device copy dTasks); hits appended to `out`
-static void runTracePass(lgpu_ctx & c, std::vector<lgpu_match> const & tasks, lgpu_match const * dTasks, lgpu_hit * hostOut,
+// DP pass 2 + traceback for `n` tasks (host copy `tasks`, device copy dTasks); hostOut[i] <-> tasks[i]
+static void runTracePass(lgpu_ctx & c, lgpu_match const * tasks, size_t n, lgpu_match const * dTasks, lgpu_hit * hostOut,
                          lgpu_stats * st)
 {
-    size_t const n = tasks.size();
     if (n == 0)
         return;
     StageTimer     t(c, st ? &st->ms_extend_trace : nullptr);
-    TaskDims const dims = taskDims(tasks);
+    TaskDims const dims = taskDims(tasks, n);
     int const      K    = chooseK(dims.maxQ);
     unsigned int const cols = 32 * K;
-    // chunk so that the trace matrices of one launch stay below ~4 GiB
-    constexpr uint64_t kMaxTraceBytes = 4ull << 30;
+    // chunk so that the trace matrices of one launch stay below 16 GiB of the 180 GB HBM
+    constexpr uint64_t kMaxTraceBytes = 16ull << 30;
     std::vector<unsigned long long> offs(n);
     c.dScores2.reserve(n);
     c.dBestPos.reserve(2 * n);
     c.dTraceOff.reserve(n);
     c.dHits.reserve(n);
+    c.hHits.reserve(n);
     size_t begin = 0;
     while (begin < n)
     {
@@ -673,12 +719,13 @@ static void runTracePass(lgpu_ctx & c, std::vector<lgpu_match> const & tasks, lg
         TP.out          = c.dHits.p;
         tracebackKernel<<<gridFor(cnt, 128), 128, 0, c.stream>>>(TP);
         LGPU_CUDA(cudaGetLastError());
-        LGPU_CUDA(cudaMemcpyAsync(hostOut + begin, c.dHits.p, cnt * sizeof(lgpu_hit), cudaMemcpyDeviceToHost, c.stream));
+        LGPU_CUDA(cudaMemcpyAsync(c.hHits.p + begin, c.dHits.p, cnt * sizeof(lgpu_hit), cudaMemcpyDeviceToHost, c.stream));
         LGPU_CUDA(cudaStreamSynchronize(c.stream));
         if (st)
             st->kernel_launches += 2;
         begin = end;
     }
+    std::memcpy(hostOut, c.hHits.p, n * sizeof(lgpu_hit));
     if (st)
     {
         st->n_extensions_trace += n;
@@ -692,13 +739,8 @@ static void runExtension(lgpu_ctx & c, uint64_t nMatches, uint8_t phase, EValueC
     uint64_t const nTasks = runMerge(c, c.dMatches.p, nMatches, st);
     if (nTasks == 0)
         return;
-    // the task list is small (16-24 B per alignment): keep a host copy for scheduling decisions
-    std::vector<lgpu_match> tasks(nTasks);
-    LGPU_CUDA(cudaMemcpyAsync(tasks.data(), c.dMerged.p, nTasks * sizeof(lgpu_match), cudaMemcpyDeviceToHost, c.stream));
-    LGPU_CUDA(cudaStreamSynchronize(c.stream));
-    TaskDims const dims = taskDims(tasks);
     c.dScores.reserve(nTasks);
-    runScorePass(c, c.dMerged.p, static_cast<unsigned int>(nTasks), dims, c.dScores.p, st);
+    runScorePass(c, c.dMerged.p, static_cast<unsigned int>(nTasks), c.dScores.p, st);
 
     // filter on the device with per-query integer thresholds
     c.dHead.reserve(nTasks);
@@ -728,15 +770,17 @@ static void runExtension(lgpu_ctx & c, uint64_t nMatches, uint8_t phase, EValueC
     }
     if (nKeep == 0)
         return;
-    std::vector<lgpu_match> keepTasks(nKeep);
-    LGPU_CUDA(cudaMemcpyAsync(keepTasks.data(), c.dTasks2.p, nKeep * sizeof(lgpu_match), cudaMemcpyDeviceToHost, c.stream));
+    // the survivors are few (one per reported hit): a host copy of their descriptors lays out the trace buffer
+    c.hTasks.reserve(nKeep);
+    LGPU_CUDA(cudaMemcpyAsync(c.hTasks.p, c.dTasks2.p, nKeep * sizeof(lgpu_match), cudaMemcpyDeviceToHost, c.stream));
     LGPU_CUDA(cudaStreamSynchronize(c.stream));
     size_t const base = c.hits.size();
     c.hits.resize(base + nKeep);
-    runTracePass(c, keepTasks, c.dTasks2.p, c.hits.data() + base, st);
+    runTracePass(c, c.hTasks.p, nKeep, c.dTasks2.p, c.hits.data() + base, st);
 
     // host: doubles, identity cut-off (src/search_algo.hpp:1308-1322)
-    size_t out = base;
+    HostTimer ht(st ? &st->ms_host : nullptr);
+    size_t    out = base;
     for (size_t i = base; i < base + nKeep; ++i)
     {
         lgpu_hit h = c.hits[i];
@@ -755,8 +799,9 @@ static void runExtension(lgpu_ctx & c, uint64_t nMatches, uint8_t phase, EValueC
     c.hits.resize(out);
 }
 
-static void setThresholds(lgpu_ctx & c, EValueComputer & ev)
+static void setThresholds(lgpu_ctx & c, EValueComputer & ev, lgpu_stats * st)
 {
+    HostTimer        ht(st ? &st->ms_host : nullptr);
     uint64_t const   n = c.nQueries;
     std::vector<int> minBit(n), minEval(n);
     std::unordered_map<uint64_t, ScoreThresholds> cache;
@@ -792,7 +837,7 @@ static void searchBatch(lgpu_ctx & c, lgpu_query_batch const & qb, lgpu_hits * o
     if (c.nQueries)
     {
         EValueComputer ev(c.scoring.ka, c.index->dbTotalLength, c.di.qIsTranslated);
-        setThresholds(c, ev);
+        setThresholds(c, ev, st);
         std::vector<unsigned int> active(c.nQueries);
         for (uint64_t i = 0; i < c.nQueries; ++i)
             active[i] = static_cast<unsigned int>(i);
@@ -823,7 +868,10 @@ static void searchBatch(lgpu_ctx & c, lgpu_query_batch const & qb, lgpu_hits * o
         }
         lgpu_stats dummy{};
         if (c.params.finalize)
+        {
+            HostTimer ht(st ? &st->ms_host : nullptr);
             finalizeRecords(c.hits, c.params.max_matches, st ? *st : dummy);
+        }
     }
     cudaEventRecord(c.ev[3], c.stream);
     cudaEventSynchronize(c.ev[3]);
@@ -1100,11 +1148,10 @@ int lgpu_extend_scores(lgpu_ctx * c, lgpu_query_batch const * q, lgpu_match cons
         if (n == 0)
             return;
         checkWindows(*c, win, n);
-        std::vector<lgpu_match> tasks(win, win + n);
         c->dUserMatches.reserve(n);
         LGPU_CUDA(cudaMemcpyAsync(c->dUserMatches.p, win, n * sizeof(lgpu_match), cudaMemcpyHostToDevice, c->stream));
         c->dScores.reserve(n);
-        runScorePass(*c, c->dUserMatches.p, static_cast<unsigned int>(n), taskDims(tasks), c->dScores.p, stats);
+        runScorePass(*c, c->dUserMatches.p, static_cast<unsigned int>(n), c->dScores.p, stats);
         LGPU_CUDA(cudaMemcpyAsync(scores, c->dScores.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
         LGPU_CUDA(cudaStreamSynchronize(c->stream));
     });
@@ -1121,10 +1168,9 @@ int lgpu_extend_trace(lgpu_ctx * c, lgpu_query_batch const * q, lgpu_match const
         if (n == 0)
             return;
         checkWindows(*c, win, n);
-        std::vector<lgpu_match> tasks(win, win + n);
         c->dUserMatches.reserve(n);
         LGPU_CUDA(cudaMemcpyAsync(c->dUserMatches.p, win, n * sizeof(lgpu_match), cudaMemcpyHostToDevice, c->stream));
-        runTracePass(*c, tasks, c->dUserMatches.p, out, stats);
+        runTracePass(*c, win, n, c->dUserMatches.p, out, stats);
     });
 }
 

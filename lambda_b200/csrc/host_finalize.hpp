@@ -24,7 +24,9 @@ inline size_t finalizeRecords(std::vector<lgpu_hit> & hits, uint32_t maxMatches,
 {
     // group by query, keeping the arrival order inside a group irrelevant: the comparators below
     // define a total order up to fully identical records
-    std::stable_sort(hits.begin(), hits.end(), [](lgpu_hit const & a, lgpu_hit const & b) { return a.q_id < b.q_id; });
+    auto const byQuery = [](lgpu_hit const & a, lgpu_hit const & b) { return a.q_id < b.q_id; };
+    if (!std::is_sorted(hits.begin(), hits.end(), byQuery)) // the device emits hits grouped by query already
+        std::stable_sort(hits.begin(), hits.end(), byQuery);
     size_t out = 0;
     size_t i   = 0;
     std::vector<lgpu_hit>        rec;

@@ -75,7 +75,6 @@ constexpr unsigned int kDpxSegShift = 20; // sort key = class << 60 | qryId << 2
 template <int T, int K>
 __global__ void __launch_bounds__(32) swScoreDpxKernel(DpxParams P)
 {
-    constexpr int G    = 32 / T;       // alignments per warp
     constexpr int KW   = (K + 3) / 4;  // profile words per strip
     constexpr int ROWW = dpxRowWords(T, K);
     constexpr int PAD  = 2 * T;        // null rows in front of the window
@@ -105,9 +104,20 @@ __global__ void __launch_bounds__(32) swScoreDpxKernel(DpxParams P)
         unsigned int const       slot0 = P.jobs[job];
         unsigned long long const seg   = P.keys[slot0] >> kDpxSegShift;
         unsigned int const       slot  = slot0 + grp;
-        bool const               valid = slot < P.nSorted && (P.keys[slot] >> kDpxSegShift) == seg;
-        // all alignments of a job share the query (frame): take it from the first one
+        // all alignments of a job share the query (frame) and the query range: take them from the first
         lgpu_match const         m0   = P.tasks[P.order[slot0]];
+        bool                     valid = slot < P.nSorted && (P.keys[slot] >> kDpxSegShift) == seg;
+        if (valid)
+        {
+            lgpu_match const m = P.tasks[P.order[slot]];
+            valid              = m.qry_start == m0.qry_start && m.qry_end == m0.qry_end;
+        }
+        {
+            // a job ends at the first slot that differs (same rule as segFlagKernel)
+            unsigned int const eq = __ballot_sync(0xffffffffu, valid);
+            for (unsigned int g2 = 0; g2 < grp; ++g2)
+                valid = valid && ((eq >> (g2 * T)) & 1u);
+        }
         unsigned int const       q    = m0.qry_id / P.Q.F;
         unsigned int const       f    = m0.qry_id % P.Q.F;
         unsigned long long const qb   = P.Q.offs[q];
@@ -281,7 +291,8 @@ __host__ __device__ inline unsigned int dpxGroupsOf(int cls)
 
 // key = class << 60 | qryId << 20 | min(nt, 2^20-1) ; also per-class counts / max window / total cells
 __global__ void classifyKernel(lgpu_match const * tasks, unsigned int n, unsigned long long * keys, unsigned int * idx,
-                               unsigned int * classCount, unsigned int * classMaxNt, unsigned long long * cells)
+                               unsigned int * classCount, unsigned int * classMaxNt, unsigned int * maxNq,
+                               unsigned long long * cells)
 {
     unsigned int const t = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long myCells = 0;
@@ -297,6 +308,7 @@ __global__ void classifyKernel(lgpu_match const * tasks, unsigned int n, unsigne
         idx[t]  = t;
         atomicAdd(&classCount[c], 1u);
         atomicMax(&classMaxNt[c], nt);
+        atomicMax(maxNq, nq);
         myCells = static_cast<unsigned long long>(nq) * nt;
     }
     // block-level reduction of the cell count
@@ -318,11 +330,20 @@ __global__ void classifyKernel(lgpu_match const * tasks, unsigned int n, unsigne
 }
 
 // segStart[t] = t if sorted slot t opens a new (class, query) segment else 0  (max-scanned afterwards)
-__global__ void segFlagKernel(unsigned long long const * keys, unsigned int n, unsigned int * segStart)
+__global__ void segFlagKernel(unsigned long long const * keys, unsigned int const * order, lgpu_match const * tasks,
+                              unsigned int n, unsigned int * segStart)
 {
     unsigned int const t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n)
-        segStart[t] = (t == 0 || (keys[t] >> kDpxSegShift) != (keys[t - 1] >> kDpxSegShift)) ? t : 0u;
+    if (t >= n)
+        return;
+    bool head = (t == 0) || (keys[t] >> kDpxSegShift) != (keys[t - 1] >> kDpxSegShift);
+    if (!head)
+    {
+        // the search path always aligns whole queries; the stage API may pass partial query ranges
+        lgpu_match const a = tasks[order[t]], b = tasks[order[t - 1]];
+        head               = a.qry_start != b.qry_start || a.qry_end != b.qry_end;
+    }
+    segStart[t] = head ? t : 0u;
 }
 
 // head[t] = 1 iff slot t is the first alignment of a job; counts the jobs per class

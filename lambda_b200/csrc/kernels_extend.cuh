@@ -188,6 +188,8 @@ __global__ void __launch_bounds__(128) swWavefrontKernel(ExtParams P)
     unsigned int const warpId = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     unsigned int *     bnd    = P.boundary + static_cast<unsigned long long>(warpId) * P.maxRows;
     int const          go = P.go, ge = P.ge;
+    constexpr int      kColBits = 9; // 32 * K <= 512 columns per block
+    static_assert(32 * K <= (1 << kColBits), "column block too wide for the packed maximum key");
 
     for (;;)
     {
@@ -213,22 +215,27 @@ __global__ void __launch_bounds__(128) swWavefrontKernel(ExtParams P)
         unsigned int const       stride = (nq + 32 * K - 1) / (32 * K) * (32 * K);
         unsigned char *          T      = TRACE ? P.trace + P.traceOff[task] : nullptr;
 
-        int          best = 0;
+        // The running maximum is one integer: (score << 9) | (511 - column inside the block).  A strictly
+        // greater key = higher score, or the same score in a smaller column; rows are visited in
+        // increasing order, so the first row of that column wins -- the reference's "first strict
+        // maximum in column-major order".  Keys of earlier column blocks get the best possible low bits.
+        int          bestKey = 0;
         unsigned int bi = 0, bj = 0;
 
         for (unsigned int c0 = 0; c0 < nq; c0 += 32 * K)
         {
             unsigned int const colBase = c0 + lane * K;
-            int                qoff[K]; // 32 * query residue, or -1 for columns past the query end
+            int                qoff[K]; // 32 * query residue (0 for columns past the query end, masked below)
             int                S[K], V[K];
 #pragma unroll
             for (int r = 0; r < K; ++r)
             {
                 unsigned int const i = colBase + r;
-                qoff[r]              = (i < nq) ? 32 * static_cast<int>(qs[i]) : -1;
+                qoff[r]              = (i < nq) ? 32 * static_cast<int>(qs[i]) : 0;
                 S[r]                 = 0;       // row 0
                 V[r]                 = kNegInf; // vertical gap above row 1
             }
+            bestKey |= (1 << kColBits) - 1;
             bool const firstBlock = (c0 == 0);
             int        dLeft      = 0;           // S(i0-1, j-1)
             unsigned int outPrev  = packSH(0, kNegInf);
@@ -255,47 +262,37 @@ __global__ void __launch_bounds__(128) swWavefrontKernel(ExtParams P)
 #pragma unroll
                 for (int r = 0; r < K; ++r)
                 {
-                    int const    sub = (qoff[r] >= 0) ? static_cast<int>(sM[qoff[r] + tOff]) : 0;
-                    int const    diag = diagS + sub;
-                    int          a = hLeft + ge, b = sLeft + go;
-                    int          h;
-                    unsigned int tv;
-                    if (a == b) { h = a; tv = T_HORI | T_HOPEN; }
-                    else if (a < b) { h = b; tv = T_HOPEN; }
-                    else { h = a; tv = T_HORI; }
-                    a = V[r] + ge;
-                    b = S[r] + go;
-                    int v;
-                    if (a == b) { v = a; tv |= T_VERT | T_VOPEN; }
-                    else if (a < b) { v = b; tv |= T_VOPEN; }
-                    else { v = a; tv |= T_VERT; }
-                    int          g;
-                    unsigned int t2;
-                    if (v == h) { g = v; t2 = T_MAXV | T_MAXH; }
-                    else if (v < h) { g = h; t2 = T_MAXH; }
-                    else { g = v; t2 = T_MAXV; }
-                    int cur;
-                    if (diag == g) { cur = diag; tv |= T_DIAG | t2; }
-                    else if (diag < g) { cur = g; tv |= t2; }
-                    else { cur = diag; tv |= T_DIAG; }
-                    if (cur <= 0) { cur = 0; tv = 0; }
+                    bool const colActive = colBase + r < nq;
+                    int const  sub  = static_cast<int>(sM[qoff[r] + tOff]);
+                    int const  diag = diagS + sub;
+                    int const  a1 = hLeft + ge, b1 = sLeft + go; // horizontal: extend / open
+                    int const  a2 = V[r] + ge, b2 = S[r] + go;   // vertical:   extend / open
+                    int const  h = max(a1, b1);
+                    int const  v = max(a2, b2);
+                    int const  g = max(v, h);
+                    int        cur = max(diag, g);
+                    if (TRACE)
+                    {
+                        // CompleteTrace: ties set both bits (SQ/align/dp_formula.h:210-222)
+                        unsigned int tv = (a1 >= b1 ? T_HORI : 0u) | (b1 >= a1 ? T_HOPEN : 0u) | (a2 >= b2 ? T_VERT : 0u) |
+                                          (b2 >= a2 ? T_VOPEN : 0u);
+                        unsigned int const t2 = (v >= h ? T_MAXV : 0u) | (h >= v ? T_MAXH : 0u);
+                        tv |= (diag >= g ? T_DIAG : 0u) | (g >= diag ? t2 : 0u);
+                        tv = (cur <= 0) ? 0u : tv;
+                        traceWord[r / 4] |= tv << (8 * (r % 4));
+                    }
+                    cur   = max(cur, 0);
                     diagS = S[r]; // S(i, j-1) is the diagonal of column i+1
                     S[r]  = cur;
                     V[r]  = v;
                     sLeft = cur;
                     hLeft = h;
-                    if (TRACE)
-                        traceWord[r / 4] |= tv << (8 * (r % 4));
-                    if (qoff[r] >= 0)
+                    int const key = colActive ? ((cur << kColBits) | ((1 << kColBits) - 1 - static_cast<int>(lane * K + r))) : 0;
+                    if (key > bestKey)
                     {
-                        unsigned int const i1 = colBase + r + 1;
-                        // first strict maximum in column-major order: smaller column wins ties
-                        if (cur > best || (TRACE && cur == best && cur > 0 && i1 < bi))
-                        {
-                            best = cur;
-                            bi   = i1;
-                            bj   = static_cast<unsigned int>(j) + 1;
-                        }
+                        bestKey = key;
+                        bi      = colBase + r + 1;
+                        bj      = static_cast<unsigned int>(j) + 1;
                     }
                 }
                 outPrev = packSH(sLeft, hLeft);
@@ -313,6 +310,7 @@ __global__ void __launch_bounds__(128) swWavefrontKernel(ExtParams P)
         }
 
         // warp reduction: highest score; ties -> smallest column, then smallest row
+        int best = bestKey >> kColBits;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1)
         {
