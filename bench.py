@@ -259,20 +259,11 @@ def main():
     d_res = h_res.cuda()
     d_offs = h_offs.cuda()
 
+    from lambda_b200.dist import all_gather_hits
+
     def gather_hits(hits):
         """the path's only collective: all ranks exchange their hit records (NCCL all-gather)"""
-        if world == 1:
-            return len(hits)
-        cnt = torch.tensor([len(hits)], device="cuda", dtype=torch.int64)
-        cnts = [torch.zeros_like(cnt) for _ in range(world)]
-        dist.all_gather(cnts, cnt)
-        mx = int(max(int(c) for c in cnts))
-        buf = torch.zeros(mx * HIT_DT.itemsize, dtype=torch.uint8, device="cuda")
-        raw = torch.from_numpy(hits.view(np.uint8).reshape(-1))
-        buf[: raw.numel()] = raw.cuda()
-        out = [torch.empty_like(buf) for _ in range(world)]
-        dist.all_gather(out, buf)
-        return int(sum(int(c) for c in cnts))
+        return all_gather_hits(hits, first_query=rank * args.n_queries, to_host=False)[1]
 
     def step(resident):
         if resident:
