@@ -188,6 +188,14 @@ def run_reference_search(d, q_ascii, qoffs, n_sample, threads, tag):
 # ------------------------------------------------------------------------------------------------
 
 def main():
+    # libraries (NCCL's version banner, ...) may print to stdout; the contract is ONE JSON line there
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+    def emit(obj):
+        real_stdout.write(json.dumps(obj) + "\n")
+        real_stdout.flush()
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -218,7 +226,7 @@ def main():
             return
         d = ensure_index(args.n_seqs)
         q_ascii, qoffs = make_queries(d, args.n_queries, args.qlen, seed=1000)
-        n_sample = args.cpu_sample or min(args.n_queries, max(500, 150 * cores))
+        n_sample = args.cpu_sample or min(args.n_queries, max(2000, 2000 * cores))
         for _ in range(args.warmup):
             run_reference_search(d, q_ascii, qoffs, min(n_sample, 200), cores, "warm")
         qps, walls = [], []
@@ -228,7 +236,7 @@ def main():
             walls.append(phase)
         value = n_sample * len(walls) / sum(walls)
         sample = f"first {n_sample} of the {args.n_queries} queries per step, lambda3 searchp -t {cores}, search phase"
-        print(json.dumps({"impl": "reference", "metric": "searchp_query_seqs_per_s", "value": value, "unit": "queries/s",
+        emit(({"impl": "reference", "metric": "searchp_query_seqs_per_s", "value": value, "unit": "queries/s",
                           "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": 1e3 * sum(walls) / len(walls), "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "int16", "data": "synthetic", "config": cfg,
@@ -370,7 +378,7 @@ def main():
 
     # CPU baseline: the unmodified reference on this box's host cores, bounded sample of the same queries
     if not args.no_cpu_baseline and n_gpus == 1 and os.path.exists(REF):
-        n_sample = args.cpu_sample or min(args.n_queries, max(500, 150 * cores))
+        n_sample = args.cpu_sample or min(args.n_queries, max(2000, 2000 * cores))
         qps, wall, phase, ref_lines = run_reference_search(d, q_ascii, qoffs, n_sample, cores, "cpu")
         out["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "reference",
                                "sample": f"first {n_sample} of the {args.n_queries} queries, lambda3 searchp -t {cores} "
@@ -380,7 +388,7 @@ def main():
         mine = sorted(s.m8(hits[hits["q_id"] < n_sample], ids))
         out["parity_sample"] = {"queries": n_sample, "reference_lines": len(ref_lines), "our_lines": len(mine),
                                 "identical": mine == sorted(ref_lines)}
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
