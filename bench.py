@@ -365,7 +365,7 @@ def main():
            "gcups": (cells_score_all + cells_trace_all) / (ms_res * 1e-3) / 1e9,
            "gcups_score_kernel": gcups_score, "gcups_trace_kernel": gcups_trace,
            "stage_ms": {k: float(st[k]) / args.steps for k in ("ms_seed", "ms_sort_merge", "ms_extend_score",
-                                                               "ms_extend_trace", "ms_h2d", "ms_total")},
+                                                               "ms_extend_trace", "ms_h2d", "ms_host", "ms_total")},
            "funnel": {k: int(st[k]) // args.steps for k in ("hits_after_seeding", "hits_failed_pre_extend",
                                                             "hits_duplicate", "hits_failed_evalue", "hits_final",
                                                             "n_extensions_score", "n_extensions_trace")},

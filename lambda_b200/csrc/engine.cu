@@ -199,7 +199,9 @@ struct lgpu_ctx
     DevBuf<unsigned int>       dWork, dBestPos, dBoundary, dOrder, dOrderB, dClassInfo, dSegStart, dSegStartB, dJobHead, dJobPos, dJobs;
     DevBuf<unsigned long long> dClassKeys, dClassKeysB;
     bool                       dpxOk = false; // scoring fits the int8 profile of the DPX kernel
-    bool                       forceWarpSeeding = false; // LAMBDA_B200_SEED=warp: warp-per-query seeding in every phase
+    int                        seedMode = 0; // LAMBDA_B200_SEED=thread|warp|block forces one seeding kernel (tests); 0 = auto
+    DevBuf<unsigned long long> dSeedCursors;
+    DevBuf<unsigned int>       dSeedCounts;
     DevBuf<unsigned char>      dTrace;
     DevBuf<unsigned long long> dTraceOff;
     DevBuf<lgpu_hit>           dHits;
@@ -350,7 +352,7 @@ static void uploadQueries(lgpu_ctx & c, lgpu_query_batch const & qb, lgpu_stats 
 
 // search(): returns number of matches now in c.dMatches
 static uint64_t runSeeding(lgpu_ctx & c, lgpu_search_opts const & so, unsigned int const * dActive, unsigned int nActive,
-                           lgpu_stats * st)
+                           unsigned int maxActiveLen, lgpu_stats * st)
 {
     if (nActive == 0)
         return 0;
@@ -379,10 +381,34 @@ static uint64_t runSeeding(lgpu_ctx & c, lgpu_search_opts const & so, unsigned i
         P.out              = c.dMatches.p;
         P.cap              = c.dMatches.cap;
         P.counters         = c.dCounters.p;
-        // phase-2 style seeds (one mismatch, half-exact) have a wide search tree per seed: one warp per
-        // query; exact seeds keep one thread per query (more independent chains in flight)
-        bool const warpPerQuery = (so.max_seed_dist != 0 && c.params.seed_half_exact) || c.forceWarpSeeding;
-        if (warpPerQuery)
+        // Few queries (typically the phase-2 leftovers): latency matters -> one block per query, the seeds
+        // of a query searched by 16 warps in parallel.  Many queries: throughput matters -> one warp per
+        // query for half-exact seeds (wide search tree per seed), one thread per query for exact seeds
+        // (most independent chains in flight).
+        bool const         halfMode  = so.max_seed_dist != 0 && c.params.seed_half_exact;
+        unsigned int const n2        = halfMode ? so.seed_length - so.seed_length / 2 : 0;
+        unsigned int const maxLeaves = (c.index->dev.sigma - 2) * n2 + 1;
+        unsigned int const maxSeeds  = maxActiveLen >= so.seed_length
+                                         ? c.di.qryNumFrames * ((maxActiveLen - so.seed_length) / so.seed_offset + 1)
+                                         : 1;
+        size_t const scratchCursors = static_cast<size_t>(nActive) * maxSeeds * maxLeaves;
+        bool const   blockPerQuery  = c.seedMode != 1 && c.seedMode != 2 && nActive <= 4096 &&
+                                   maxSeeds <= static_cast<unsigned int>(kSeedBlockMaxSeeds) && maxActiveLen < (1u << 24) &&
+                                   scratchCursors * sizeof(Cursor) <= (1ull << 30);
+        if (blockPerQuery || c.seedMode == 3)
+        {
+            if (!blockPerQuery)
+                throw ArgError("LAMBDA_B200_SEED=block: batch too large for the block-per-query kernel");
+            c.dSeedCursors.reserve(scratchCursors * 2);
+            c.dSeedCounts.reserve(static_cast<size_t>(nActive) * maxSeeds);
+            SeedScratch S;
+            S.cursors   = reinterpret_cast<Cursor *>(c.dSeedCursors.p);
+            S.counts    = c.dSeedCounts.p;
+            S.maxSeeds  = maxSeeds;
+            S.maxLeaves = maxLeaves;
+            seedBlockKernel<<<nActive, 32 * kSeedBlockWarps, 0, c.stream>>>(P, S);
+        }
+        else if ((halfMode && c.seedMode != 1) || c.seedMode == 2)
             seedWarpKernel<<<gridFor(static_cast<unsigned long long>(nActive) * 32, 128), 128, 0, c.stream>>>(P);
         else
             seedKernel<<<gridFor(nActive, 128), 128, 0, c.stream>>>(P);
@@ -457,13 +483,13 @@ static uint64_t runMerge(lgpu_ctx & c, lgpu_match const * dIn, uint64_t n, lgpu_
     return nChains;
 }
 
+// columns per lane of the wavefront kernel: the smallest even K with 32 * K >= longest query, capped at 16
 static int chooseK(unsigned int maxQ)
 {
     unsigned int const k = (maxQ + 31) / 32;
-    if (k <= 4) return 4;
-    if (k <= 8) return 8;
-    if (k <= 12) return 12;
-    return 16;
+    if (k <= 2) return 2;
+    if (k >= 16) return 16;
+    return static_cast<int>((k + 1) / 2 * 2);
 }
 
 template <bool TRACE>
@@ -471,9 +497,13 @@ static void launchWavefront(int K, ExtParams const & P, unsigned int grid, cudaS
 {
     switch (K)
     {
+        case 2: swWavefrontKernel<2, TRACE><<<grid, 128, 0, s>>>(P); break;
         case 4: swWavefrontKernel<4, TRACE><<<grid, 128, 0, s>>>(P); break;
+        case 6: swWavefrontKernel<6, TRACE><<<grid, 128, 0, s>>>(P); break;
         case 8: swWavefrontKernel<8, TRACE><<<grid, 128, 0, s>>>(P); break;
+        case 10: swWavefrontKernel<10, TRACE><<<grid, 128, 0, s>>>(P); break;
         case 12: swWavefrontKernel<12, TRACE><<<grid, 128, 0, s>>>(P); break;
+        case 14: swWavefrontKernel<14, TRACE><<<grid, 128, 0, s>>>(P); break;
         default: swWavefrontKernel<16, TRACE><<<grid, 128, 0, s>>>(P); break;
     }
 }
@@ -667,7 +697,7 @@ static void runTracePass(lgpu_ctx & c, lgpu_match const * tasks, size_t n, lgpu_
     StageTimer     t(c, st ? &st->ms_extend_trace : nullptr);
     TaskDims const dims = taskDims(tasks, n);
     int const      K    = chooseK(dims.maxQ);
-    unsigned int const cols = 32 * K;
+    unsigned int const cols = 32 * K, colBytes = 32 * ((K + 3) / 4 * 4);
     // chunk so that the trace matrices of one launch stay below 16 GiB of the 180 GB HBM
     constexpr uint64_t kMaxTraceBytes = 16ull << 30;
     std::vector<unsigned long long> offs(n);
@@ -684,7 +714,7 @@ static void runTracePass(lgpu_ctx & c, lgpu_match const * tasks, size_t n, lgpu_
         while (end < n)
         {
             unsigned int const nq = tasks[end].qry_end - tasks[end].qry_start, nt = tasks[end].subj_end - tasks[end].subj_start;
-            uint64_t const     sz = static_cast<uint64_t>((nq + cols - 1) / cols * cols) * nt;
+            uint64_t const     sz = static_cast<uint64_t>((nq + cols - 1) / cols * colBytes) * nt;
             if (end > begin && bytes + sz > kMaxTraceBytes)
                 break;
             offs[end] = bytes;
@@ -715,7 +745,7 @@ static void runTracePass(lgpu_ctx & c, lgpu_match const * tasks, size_t n, lgpu_
         TP.bestPos      = c.dBestPos.p;
         TP.trace        = c.dTrace.p;
         TP.traceOff     = c.dTraceOff.p;
-        TP.colsPerBlock = cols;
+        TP.K            = static_cast<unsigned int>(K);
         TP.out          = c.dHits.p;
         tracebackKernel<<<gridFor(cnt, 128), 128, 0, c.stream>>>(TP);
         LGPU_CUDA(cudaGetLastError());
@@ -842,9 +872,15 @@ static void searchBatch(lgpu_ctx & c, lgpu_query_batch const & qb, lgpu_hits * o
         for (uint64_t i = 0; i < c.nQueries; ++i)
             active[i] = static_cast<unsigned int>(i);
         uploadActive(c, active);
+        auto const maxLen = [&](std::vector<unsigned int> const & a) {
+            uint64_t m = 0;
+            for (unsigned int q : a)
+                m = std::max(m, c.qOffsHost[q + 1] - c.qOffsHost[q]);
+            return static_cast<unsigned int>(m);
+        };
         if (c.params.iterative_search)
         {
-            uint64_t nM = runSeeding(c, c.params.opts0, c.dActive.p, static_cast<unsigned int>(active.size()), st);
+            uint64_t nM = runSeeding(c, c.params.opts0, c.dActive.p, static_cast<unsigned int>(active.size()), maxLen(active), st);
             runExtension(c, nM, 1, ev, st);
             // iterativeSearchPre/Post: queries with at least one surviving hit are done
             std::vector<uint8_t> ok(c.nQueries, 0);
@@ -857,13 +893,13 @@ static void searchBatch(lgpu_ctx & c, lgpu_query_batch const & qb, lgpu_hits * o
             if (!active.empty())
             {
                 uploadActive(c, active);
-                nM = runSeeding(c, c.params.opts, c.dActive.p, static_cast<unsigned int>(active.size()), st);
+                nM = runSeeding(c, c.params.opts, c.dActive.p, static_cast<unsigned int>(active.size()), maxLen(active), st);
                 runExtension(c, nM, 2, ev, st);
             }
         }
         else
         {
-            uint64_t const nM = runSeeding(c, c.params.opts, c.dActive.p, static_cast<unsigned int>(active.size()), st);
+            uint64_t const nM = runSeeding(c, c.params.opts, c.dActive.p, static_cast<unsigned int>(active.size()), maxLen(active), st);
             runExtension(c, nM, 2, ev, st);
         }
         lgpu_stats dummy{};
@@ -1050,7 +1086,7 @@ int lgpu_ctx_create(lgpu_ctx ** out, lgpu_index const * ix, lgpu_params const * 
         LGPU_CUDA(cudaMemcpy(c->dMatrix.p, c->scoring.matrix, 1024, cudaMemcpyHostToDevice));
         c->dCounters.reserve(8);
         if (char const * e = std::getenv("LAMBDA_B200_SEED"))
-            c->forceWarpSeeding = std::strcmp(e, "warp") == 0;
+            c->seedMode = !std::strcmp(e, "thread") ? 1 : !std::strcmp(e, "warp") ? 2 : !std::strcmp(e, "block") ? 3 : 0;
         // the packed kernel stores (score - gapOpen) as int8 profile bytes with -128 reserved for "null"
         c->dpxOk = c->scoring.alphSize < 32 && c->scoring.gapOpenSeqan <= c->scoring.gapExtend && c->scoring.gapExtend <= 0;
         for (int a = 0; a < c->scoring.alphSize; ++a)
@@ -1087,8 +1123,11 @@ int lgpu_seed_batch(lgpu_ctx * c, lgpu_query_batch const * q, int phase, lgpu_ma
         for (uint64_t i = 0; i < c->nQueries; ++i)
             active[i] = static_cast<unsigned int>(i);
         uploadActive(*c, active);
+        uint64_t maxLen = 0;
+        for (uint64_t i = 0; i < c->nQueries; ++i)
+            maxLen = std::max(maxLen, c->qOffsHost[i + 1] - c->qOffsHost[i]);
         uint64_t const nM = runSeeding(*c, phase == 1 ? c->params.opts0 : c->params.opts, c->dActive.p,
-                                       static_cast<unsigned int>(active.size()), stats);
+                                       static_cast<unsigned int>(active.size()), static_cast<unsigned int>(maxLen), stats);
         c->matchesHost.resize(nM);
         if (nM)
             LGPU_CUDA(cudaMemcpyAsync(c->matchesHost.data(), c->dMatches.p, nM * sizeof(lgpu_match), cudaMemcpyDeviceToHost,

@@ -36,8 +36,16 @@ inline size_t finalizeRecords(std::vector<lgpu_hit> & hits, uint32_t maxMatches,
         size_t j = i;
         while (j < hits.size() && hits[j].q_id == hits[i].q_id)
             ++j;
-        rec.assign(hits.begin() + i, hits.begin() + j);
         ++st.qrys_with_hit;
+        if (j - i == 1) // the common case: nothing to sort, deduplicate or truncate
+        {
+            ++st.hits_final;
+            ++st.pairs;
+            hits[out++] = hits[i];
+            i           = j;
+            continue;
+        }
+        rec.assign(hits.begin() + i, hits.begin() + j);
         size_t const before = rec.size();
         // bitScore compared inverted so that larger scores come first among equal coordinates
         std::stable_sort(rec.begin(), rec.end(), [](lgpu_hit const & m1, lgpu_hit const & m2) {

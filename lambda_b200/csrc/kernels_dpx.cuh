@@ -296,20 +296,48 @@ __global__ void classifyKernel(lgpu_match const * tasks, unsigned int n, unsigne
 {
     unsigned int const t = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long myCells = 0;
+    int                c  = -1;
+    unsigned int       nq = 0, nt = 0;
     if (t < n)
     {
-        unsigned int const nq = tasks[t].qry_end - tasks[t].qry_start;
-        unsigned int const nt = tasks[t].subj_end - tasks[t].subj_start;
-        int                c  = dpxClassOf(nq);
+        nq = tasks[t].qry_end - tasks[t].qry_start;
+        nt = tasks[t].subj_end - tasks[t].subj_start;
+        c  = dpxClassOf(nq);
         if (nt > kDpxMaxWindow)
             c = kNumDpxClasses;
         keys[t] = (static_cast<unsigned long long>(c) << 60) | (static_cast<unsigned long long>(tasks[t].qry_id) << kDpxSegShift) |
                   (nt < (1u << kDpxSegShift) ? nt : (1u << kDpxSegShift) - 1u);
         idx[t]  = t;
-        atomicAdd(&classCount[c], 1u);
-        atomicMax(&classMaxNt[c], nt);
-        atomicMax(maxNq, nq);
         myCells = static_cast<unsigned long long>(nq) * nt;
+    }
+    // one atomic per warp instead of one per alignment when the whole warp is of one class (the usual
+    // case: alignments arrive sorted by query); otherwise every lane reports for itself
+    {
+        unsigned int const validMask = __ballot_sync(0xffffffffu, c >= 0);
+        unsigned int const peers     = __match_any_sync(0xffffffffu, c);
+        bool const         uniform   = __all_sync(0xffffffffu, c < 0 || peers == validMask);
+        if (uniform)
+        {
+            unsigned int mt = nt, mq = nq;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1)
+            {
+                mt = max(mt, __shfl_xor_sync(0xffffffffu, mt, off));
+                mq = max(mq, __shfl_xor_sync(0xffffffffu, mq, off));
+            }
+            if (validMask && (threadIdx.x & 31u) == static_cast<unsigned int>(__ffs(validMask) - 1))
+            {
+                atomicAdd(&classCount[c], static_cast<unsigned int>(__popc(validMask)));
+                atomicMax(&classMaxNt[c], mt);
+                atomicMax(maxNq, mq);
+            }
+        }
+        else if (c >= 0)
+        {
+            atomicAdd(&classCount[c], 1u);
+            atomicMax(&classMaxNt[c], nt);
+            atomicMax(maxNq, nq);
+        }
     }
     // block-level reduction of the cell count
     __shared__ unsigned long long sh[8];
@@ -357,7 +385,12 @@ __global__ void jobHeadKernel(unsigned long long const * keys, unsigned int cons
     unsigned int const h   = ((t - segStart[t]) % dpxGroupsOf(cls)) == 0 ? 1u : 0u;
     head[t]                = h;
     if (h)
-        atomicAdd(&classJobs[cls], 1u);
+    {
+        // aggregate the lanes of one class into a single atomic
+        unsigned int const peers = __match_any_sync(__activemask(), cls);
+        if ((threadIdx.x & 31u) == static_cast<unsigned int>(__ffs(peers) - 1))
+            atomicAdd(&classJobs[cls], static_cast<unsigned int>(__popc(peers)));
+    }
 }
 
 __global__ void jobEmitKernel(unsigned int const * head, unsigned int const * posIncl, unsigned int n, unsigned int * jobs)

@@ -212,7 +212,9 @@ __global__ void __launch_bounds__(128) swWavefrontKernel(ExtParams P)
         unsigned char const *    ts   = P.ix.seqs + P.ix.seqDelims[m.subj_id / P.sbjFrames] + m.subj_start;
         unsigned int const       nt   = m.subj_end - m.subj_start;
 
-        unsigned int const       stride = (nq + 32 * K - 1) / (32 * K) * (32 * K);
+        // trace storage: every lane owns KS = roundup4(K) bytes per row and column block (word stores)
+        constexpr unsigned int   KS     = (K + 3) / 4 * 4;
+        unsigned int const       stride = (nq + 32 * K - 1) / (32 * K) * (32 * KS);
         unsigned char *          T      = TRACE ? P.trace + P.traceOff[task] : nullptr;
 
         // The running maximum is one integer: (score << 9) | (511 - column inside the block).  A strictly
@@ -300,7 +302,8 @@ __global__ void __launch_bounds__(128) swWavefrontKernel(ExtParams P)
                     bnd[j] = outPrev; // right edge of this column block, read by lane 0 of the next block
                 if (TRACE)
                 {
-                    unsigned int * dst = reinterpret_cast<unsigned int *>(T + static_cast<unsigned long long>(j) * stride + colBase);
+                    unsigned int * dst = reinterpret_cast<unsigned int *>(T + static_cast<unsigned long long>(j) * stride +
+                                                                          (c0 / K) * KS + lane * KS);
 #pragma unroll
                     for (int w = 0; w < (K + 3) / 4; ++w)
                         dst[w] = traceWord[w];
@@ -354,7 +357,7 @@ struct TracebackParams
     unsigned int const *       bestPos;
     unsigned char const *      trace;
     unsigned long long const * traceOff;
-    unsigned int               colsPerBlock; // 32 * K used by the fill kernel (row stride granularity)
+    unsigned int               K;            // columns per lane used by the fill kernel (storage: roundup4(K) bytes)
     lgpu_hit *                 out;
 };
 
@@ -373,7 +376,8 @@ __global__ void __launch_bounds__(128) tracebackKernel(TracebackParams P)
     unsigned int const       sId  = m.subj_id / P.sbjFrames;
     unsigned long long const sb   = P.ix.seqDelims[sId];
     unsigned char const *    ts   = P.ix.seqs + sb + m.subj_start;
-    unsigned int const       stride = (nq + P.colsPerBlock - 1) / P.colsPerBlock * P.colsPerBlock;
+    unsigned int const       KS     = (P.K + 3) / 4 * 4;
+    unsigned int const       stride = (nq + 32 * P.K - 1) / (32 * P.K) * (32 * KS);
     unsigned char const *    T      = P.trace + P.traceOff[task];
 
     unsigned int       i = P.bestPos[2 * task], j = P.bestPos[2 * task + 1];
@@ -381,7 +385,8 @@ __global__ void __launch_bounds__(128) tracebackKernel(TracebackParams P)
     unsigned int nMatch = 0, nMismatch = 0, nPositive = 0, nGapOpen = 0, nGapExt = 0, alnLen = 0;
 
     auto tr = [&](unsigned int ii, unsigned int jj) -> unsigned int {
-        return (ii > 0 && jj > 0) ? T[static_cast<unsigned long long>(jj - 1) * stride + (ii - 1)] : 0u;
+        // column i-1 lives in strip (i-1) / K at byte (i-1) % K of that strip's KS-byte slot
+        return (ii > 0 && jj > 0) ? T[static_cast<unsigned long long>(jj - 1) * stride + ((ii - 1) / P.K) * KS + (ii - 1) % P.K] : 0u;
     };
 
     if (P.scores[task] > 0)

@@ -477,6 +477,243 @@ __global__ void __launch_bounds__(128) seedKernel(SeedParams P)
 }
 
 // ---------------------------------------------------------------------------------------------
+// warp-cooperative building blocks (shared by the warp-per-query and block-per-query kernels)
+// ---------------------------------------------------------------------------------------------
+
+// Exact chain of one seed: E[0] = cursor after the exactly matched first half, E[i+1] = E[i] extended by
+// the (h1+i)-th seed symbol.  Returns the deepest non-empty level K (-1: the first half does not occur).
+__device__ __forceinline__ int seedExactChain(DevIndex const & ix, unsigned char const * red, unsigned int seedBegin,
+                                              unsigned int h1, unsigned int n2, Cursor * E)
+{
+    Cursor c;
+    c.lb  = 0;
+    c.len = ix.nRows;
+    for (unsigned int i = 0; i < h1; ++i)
+    {
+        c = fmExtendRight(ix, c, red[seedBegin + i] + 1u);
+        if (c.len == 0)
+            return -1;
+    }
+    E[0]  = c;
+    int K = 0;
+    for (unsigned int i = 0; i < n2; ++i)
+    {
+        c = fmExtendRight(ix, c, red[seedBegin + h1 + i] + 1u);
+        if (c.len == 0)
+            break;
+        E[i + 1] = c;
+        K        = static_cast<int>(i) + 1;
+    }
+    return K;
+}
+
+// Leaf `idx` of the half-exact search tree in the reference's (BFS = leaf) order: mismatches below the
+// seed symbol per level going down, the exact cursor, mismatches above the seed symbol going back up.
+__device__ __forceinline__ Cursor seedLeaf(DevIndex const & ix, Cursor const * E, unsigned char const * red,
+                                           unsigned int seedBegin, unsigned int h1, unsigned int n2, int kMax, bool hasExact,
+                                           unsigned int redN, unsigned int idx)
+{
+    Cursor mine;
+    mine.lb  = 0;
+    mine.len = 0;
+    unsigned int i     = idx;
+    int          lvl   = -1;
+    unsigned int r     = 0;
+    bool         exact = false;
+    for (int l = 0; l <= kMax; ++l)
+    {
+        unsigned int const want = red[seedBegin + h1 + l];
+        if (i < want)
+        {
+            lvl = l;
+            r   = i;
+            break;
+        }
+        i -= want;
+    }
+    if (lvl < 0 && hasExact)
+    {
+        if (i == 0)
+            exact = true;
+        else
+            --i;
+    }
+    if (lvl < 0 && !exact)
+        for (int l = kMax; l >= 0; --l)
+        {
+            unsigned int const want = red[seedBegin + h1 + l];
+            unsigned int const cnt  = redN - 1 - want;
+            if (i < cnt)
+            {
+                lvl = l;
+                r   = want + 1 + i;
+                break;
+            }
+            i -= cnt;
+        }
+    if (exact)
+        mine = E[n2];
+    else if (lvl >= 0)
+    {
+        Cursor c = fmExtendRight(ix, E[lvl], r + 1u);
+        for (unsigned int l = lvl + 1; c.len != 0 && l < n2; ++l)
+            c = fmExtendRight(ix, c, red[seedBegin + h1 + l] + 1u);
+        mine = c;
+    }
+    return mine;
+}
+
+// Everything the reference does with one cursor of one seed (src/search_algo.hpp:674-757), executed by a
+// full warp: adaptive elongation (uniform), abundance cut, then locate + pre-scoring 32 rows at a time.
+__device__ __forceinline__ void seedConsumeCursor(SeedParams const & P, signed char const * sM, unsigned int lane,
+                                                  unsigned int qryId, unsigned char const * trans, unsigned char const * red,
+                                                  unsigned int len, unsigned int seedBegin, Cursor cursor,
+                                                  unsigned long long & hitsThisSeq, unsigned long long needlesSum,
+                                                  unsigned long long needlesPos, unsigned long long & nAfter,
+                                                  unsigned long long & nFailed)
+{
+    DevIndex const &   ix      = P.ix;
+    unsigned int const L       = P.seedLength;
+    unsigned int const ltMask  = (1u << lane) - 1u;
+    unsigned int       seedLen = L;
+    if (P.adaptive)
+    {
+        unsigned long long desired = 1;
+        if (hitsThisSeq < P.maxMatches)
+        {
+            unsigned long long remaining = (needlesSum - needlesPos - seedBegin) / P.seedOffset;
+            if (remaining < 1)
+                remaining = 1;
+            desired = (P.maxMatches - hitsThisSeq) * 10ull / remaining;
+            if (desired == 0)
+                desired = 1;
+        }
+        unsigned long long oldCount = cursor.len;
+        while (seedBegin + seedLen < len)
+        {
+            Cursor const n = fmExtendRight(ix, cursor, red[seedBegin + seedLen] + 1u);
+            if (n.len < desired && n.len < oldCount)
+                break;
+            cursor   = n;
+            oldCount = n.len;
+            ++seedLen;
+        }
+    }
+    if (cursor.len > 10ull * P.maxMatches)
+        return;
+
+    for (unsigned long long row0 = 0; row0 < cursor.len; row0 += 32)
+    {
+        bool const         act  = row0 + lane < cursor.len;
+        bool               pass = false;
+        unsigned long long subj = 0, pos = 0;
+        if (act)
+        {
+            fmLocate(ix, cursor.lb + row0 + lane, subj, pos);
+            pos -= seedLen;
+            ++nAfter;
+            long long                qB     = seedBegin;
+            long long                sB     = static_cast<long long>(pos);
+            unsigned long long const actual = seedLen;
+            unsigned long long       eff    = static_cast<unsigned long long>(L * P.preScoring);
+            if (eff < actual)
+                eff = actual;
+            unsigned long long const sBase = __ldg(ix.seqDelims + subj);
+            unsigned long long const sLen  = __ldg(ix.seqDelims + subj + 1) - sBase;
+            if (eff > actual)
+            {
+                qB -= static_cast<long long>((eff - actual) / 2);
+                sB -= static_cast<long long>((eff - actual) / 2);
+                long long const mn = qB < sB ? qB : sB;
+                if (mn < 0)
+                {
+                    qB -= mn;
+                    sB -= mn;
+                    eff += mn;
+                }
+                unsigned long long const qRem = static_cast<unsigned long long>(len) - qB;
+                unsigned long long const sRem = sLen - sB;
+                if (qRem < eff)
+                    eff = qRem;
+                if (sRem < eff)
+                    eff = sRem;
+            }
+            int const             thresh = static_cast<int>(P.preScoringThresh * static_cast<double>(eff));
+            unsigned char const * qs     = trans + qB;
+            unsigned char const * ss     = ix.seqs + sBase + sB;
+            int                   sc = 0, mx = 0;
+            for (unsigned long long i = 0; i < eff; ++i)
+            {
+                sc += sM[qs[i] * 32 + __ldg(ss + i)];
+                if (sc < 0)
+                    sc = 0;
+                else if (sc > mx)
+                    mx = sc;
+                if (mx >= thresh)
+                {
+                    pass = true;
+                    break;
+                }
+            }
+            if (!pass)
+                ++nFailed;
+        }
+        unsigned int const passMask = __ballot_sync(0xffffffffu, pass);
+        unsigned int const cnt      = __popc(passMask);
+        if (cnt)
+        {
+            unsigned long long slot0 = 0;
+            if (lane == 0)
+                slot0 = atomicAdd(&P.counters[0], static_cast<unsigned long long>(cnt));
+            slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+            if (pass)
+            {
+                unsigned long long const slot = slot0 + __popc(passMask & ltMask);
+                if (slot < P.cap)
+                {
+                    lgpu_match m;
+                    m.qry_id     = qryId;
+                    m.subj_id    = static_cast<unsigned int>(subj);
+                    m.qry_start  = seedBegin;
+                    m.qry_end    = seedBegin + seedLen;
+                    m.subj_start = static_cast<unsigned int>(pos);
+                    m.subj_end   = static_cast<unsigned int>(pos) + seedLen;
+                    P.out[slot]  = m;
+                }
+            }
+            hitsThisSeq += cnt;
+        }
+    }
+}
+
+__device__ __forceinline__ void seedFlushCounters(SeedParams const & P, unsigned int lane, unsigned long long nAfter,
+                                                  unsigned long long nFailed)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+    {
+        nAfter += __shfl_down_sync(0xffffffffu, nAfter, off);
+        nFailed += __shfl_down_sync(0xffffffffu, nFailed, off);
+    }
+    if (lane == 0)
+    {
+        if (nAfter)
+            atomicAdd(&P.counters[1], nAfter);
+        if (nFailed)
+            atomicAdd(&P.counters[2], nFailed);
+    }
+}
+
+// next seed start at or after `seedBegin` (src/search_algo.hpp:652-656); false = no more seeds
+__device__ __forceinline__ bool seedNextStart(unsigned char const * trans, unsigned int len, unsigned int L,
+                                              unsigned int unknownRank, unsigned int & seedBegin)
+{
+    while (seedBegin < len - L && (trans[seedBegin] == unknownRank || trans[seedBegin] == trans[seedBegin + 1]))
+        ++seedBegin;
+    return seedBegin <= len - L;
+}
+
+// ---------------------------------------------------------------------------------------------
 // seeding, one WARP per query
 // ---------------------------------------------------------------------------------------------
 // Same semantics and emission rules as seedKernel, but the work inside one query is spread over the
@@ -484,9 +721,7 @@ __global__ void __launch_bounds__(128) seedKernel(SeedParams P)
 //   * the half-exact search tree of a seed (up to (sigma-1) * L/2 mismatch branches, each a chain of
 //     dependent LF steps) is evaluated 32 branches at a time, then consumed in the reference's order;
 //   * the occurrences of a cursor are located and pre-scored 32 rows at a time.
-// Only the exact chain, the adaptive elongation and the running `hitsThisSeq` stay serial.  This is
-// what phase 2 (searchOpts, one mismatch allowed) needs: a handful of leftover queries would otherwise
-// each be a single thread walking ~20 000 dependent index reads.
+// Only the exact chain, the adaptive elongation and the running `hitsThisSeq` stay serial.
 __global__ void __launch_bounds__(128) seedWarpKernel(SeedParams P)
 {
     __shared__ signed char sM[1024];
@@ -505,14 +740,12 @@ __global__ void __launch_bounds__(128) seedWarpKernel(SeedParams P)
     unsigned int const       len  = static_cast<unsigned int>(P.Q.offs[q + 1] - qb);
     unsigned int const       L    = P.seedLength;
     unsigned int const       redN = ix.sigma - 1;
-    unsigned int const       ltMask = (1u << lane) - 1u;
 
     unsigned long long nAfter = 0, nFailed = 0; // per lane
     if (len >= L)
     {
         unsigned long long       hitsThisSeq = 0;
         unsigned long long const needlesSum  = static_cast<unsigned long long>(F) * len;
-        unsigned long long       needlesPos  = 0;
         bool const               half        = P.halfExact && P.maxSeedDist != 0;
         unsigned int const       h1          = half ? L / 2 : L;
         unsigned int const       n2          = L - h1;
@@ -522,107 +755,27 @@ __global__ void __launch_bounds__(128) seedWarpKernel(SeedParams P)
             unsigned int const    qryId = q * F + f;
             unsigned char const * trans = P.Q.trans + F * qb + static_cast<unsigned long long>(f) * len;
             unsigned char const * red   = P.Q.red + F * qb + static_cast<unsigned long long>(f) * len;
+            unsigned long long const needlesPos = static_cast<unsigned long long>(f) * len;
 
             for (unsigned int seedBegin = 0;; seedBegin += P.seedOffset)
             {
-                while (seedBegin < len - L &&
-                       (trans[seedBegin] == P.unknownRank || trans[seedBegin] == trans[seedBegin + 1]))
-                    ++seedBegin;
-                if (seedBegin > len - L)
+                if (!seedNextStart(trans, len, L, P.unknownRank, seedBegin))
                     break;
-
                 // exact chain, computed redundantly by all lanes (same addresses -> one transaction)
-                Cursor E[kMaxHalf2 + 1];
-                int    K = -1;
-                {
-                    Cursor c;
-                    c.lb    = 0;
-                    c.len   = ix.nRows;
-                    bool ok = true;
-                    for (unsigned int i = 0; i < h1; ++i)
-                    {
-                        c = fmExtendRight(ix, c, red[seedBegin + i] + 1u);
-                        if (c.len == 0)
-                        {
-                            ok = false;
-                            break;
-                        }
-                    }
-                    if (ok)
-                    {
-                        E[0] = c;
-                        K    = 0;
-                        for (unsigned int i = 0; i < n2; ++i)
-                        {
-                            c = fmExtendRight(ix, c, red[seedBegin + h1 + i] + 1u);
-                            if (c.len == 0)
-                                break;
-                            E[i + 1] = c;
-                            K        = static_cast<int>(i) + 1;
-                        }
-                    }
-                }
+                Cursor    E[kMaxHalf2 + 1];
+                int const K = seedExactChain(ix, red, seedBegin, h1, n2, E);
                 if (K < 0)
                     continue;
-                int const          kMax    = (K < static_cast<int>(n2) - 1) ? K : static_cast<int>(n2) - 1;
+                int const          kMax     = (K < static_cast<int>(n2) - 1) ? K : static_cast<int>(n2) - 1;
                 bool const         hasExact = (K == static_cast<int>(n2));
-                unsigned int const nLeaves = static_cast<unsigned int>(kMax + 1) * (redN - 1) + (hasExact ? 1u : 0u);
-
+                unsigned int const nLeaves  = static_cast<unsigned int>(kMax + 1) * (redN - 1) + (hasExact ? 1u : 0u);
                 for (unsigned int base = 0; base < nLeaves; base += 32)
                 {
-                    // leaf `idx` of the search tree in the reference's order: mismatches below the seed
-                    // symbol per level going down, the exact cursor, mismatches above going back up
-                    unsigned int const idx = base + lane;
-                    Cursor             mine;
+                    Cursor mine;
                     mine.lb  = 0;
                     mine.len = 0;
-                    if (idx < nLeaves)
-                    {
-                        unsigned int i     = idx;
-                        int          lvl   = -1;
-                        unsigned int r     = 0;
-                        bool         exact = false;
-                        for (int l = 0; l <= kMax; ++l)
-                        {
-                            unsigned int const want = red[seedBegin + h1 + l];
-                            if (i < want)
-                            {
-                                lvl = l;
-                                r   = i;
-                                break;
-                            }
-                            i -= want;
-                        }
-                        if (lvl < 0 && hasExact)
-                        {
-                            if (i == 0)
-                                exact = true;
-                            else
-                                --i;
-                        }
-                        if (lvl < 0 && !exact)
-                            for (int l = kMax; l >= 0; --l)
-                            {
-                                unsigned int const want = red[seedBegin + h1 + l];
-                                unsigned int const cnt  = redN - 1 - want;
-                                if (i < cnt)
-                                {
-                                    lvl = l;
-                                    r   = want + 1 + i;
-                                    break;
-                                }
-                                i -= cnt;
-                            }
-                        if (exact)
-                            mine = E[n2];
-                        else if (lvl >= 0)
-                        {
-                            Cursor c = fmExtendRight(ix, E[lvl], r + 1u);
-                            for (unsigned int l = lvl + 1; c.len != 0 && l < n2; ++l)
-                                c = fmExtendRight(ix, c, red[seedBegin + h1 + l] + 1u);
-                            mine = c;
-                        }
-                    }
+                    if (base + lane < nLeaves)
+                        mine = seedLeaf(ix, E, red, seedBegin, h1, n2, kMax, hasExact, redN, base + lane);
                     unsigned int live = __ballot_sync(0xffffffffu, mine.len != 0);
                     while (live)
                     {
@@ -631,135 +784,133 @@ __global__ void __launch_bounds__(128) seedWarpKernel(SeedParams P)
                         Cursor cursor;
                         cursor.lb  = __shfl_sync(0xffffffffu, mine.lb, src);
                         cursor.len = __shfl_sync(0xffffffffu, mine.len, src);
-
-                        unsigned int seedLen = L;
-                        if (P.adaptive)
-                        {
-                            unsigned long long desired = 1;
-                            if (hitsThisSeq < P.maxMatches)
-                            {
-                                unsigned long long remaining = (needlesSum - needlesPos - seedBegin) / P.seedOffset;
-                                if (remaining < 1)
-                                    remaining = 1;
-                                desired = (P.maxMatches - hitsThisSeq) * 10ull / remaining;
-                                if (desired == 0)
-                                    desired = 1;
-                            }
-                            unsigned long long oldCount = cursor.len;
-                            while (seedBegin + seedLen < len)
-                            {
-                                Cursor const n = fmExtendRight(ix, cursor, red[seedBegin + seedLen] + 1u);
-                                if (n.len < desired && n.len < oldCount)
-                                    break;
-                                cursor   = n;
-                                oldCount = n.len;
-                                ++seedLen;
-                            }
-                        }
-                        if (cursor.len > 10ull * P.maxMatches)
-                            continue;
-
-                        for (unsigned long long row0 = 0; row0 < cursor.len; row0 += 32)
-                        {
-                            bool const         act  = row0 + lane < cursor.len;
-                            bool               pass = false;
-                            unsigned long long subj = 0, pos = 0;
-                            if (act)
-                            {
-                                fmLocate(ix, cursor.lb + row0 + lane, subj, pos);
-                                pos -= seedLen;
-                                ++nAfter;
-                                long long                qB     = seedBegin;
-                                long long                sB     = static_cast<long long>(pos);
-                                unsigned long long const actual = seedLen;
-                                unsigned long long       eff    = static_cast<unsigned long long>(L * P.preScoring);
-                                if (eff < actual)
-                                    eff = actual;
-                                unsigned long long const sBase = __ldg(ix.seqDelims + subj);
-                                unsigned long long const sLen  = __ldg(ix.seqDelims + subj + 1) - sBase;
-                                if (eff > actual)
-                                {
-                                    qB -= static_cast<long long>((eff - actual) / 2);
-                                    sB -= static_cast<long long>((eff - actual) / 2);
-                                    long long const mn = qB < sB ? qB : sB;
-                                    if (mn < 0)
-                                    {
-                                        qB -= mn;
-                                        sB -= mn;
-                                        eff += mn;
-                                    }
-                                    unsigned long long const qRem = static_cast<unsigned long long>(len) - qB;
-                                    unsigned long long const sRem = sLen - sB;
-                                    if (qRem < eff)
-                                        eff = qRem;
-                                    if (sRem < eff)
-                                        eff = sRem;
-                                }
-                                int const             thresh = static_cast<int>(P.preScoringThresh * static_cast<double>(eff));
-                                unsigned char const * qs     = trans + qB;
-                                unsigned char const * ss     = ix.seqs + sBase + sB;
-                                int                   sc = 0, mx = 0;
-                                for (unsigned long long i = 0; i < eff; ++i)
-                                {
-                                    sc += sM[qs[i] * 32 + __ldg(ss + i)];
-                                    if (sc < 0)
-                                        sc = 0;
-                                    else if (sc > mx)
-                                        mx = sc;
-                                    if (mx >= thresh)
-                                    {
-                                        pass = true;
-                                        break;
-                                    }
-                                }
-                                if (!pass)
-                                    ++nFailed;
-                            }
-                            unsigned int const passMask = __ballot_sync(0xffffffffu, pass);
-                            unsigned int const cnt      = __popc(passMask);
-                            if (cnt)
-                            {
-                                unsigned long long slot0 = 0;
-                                if (lane == 0)
-                                    slot0 = atomicAdd(&P.counters[0], static_cast<unsigned long long>(cnt));
-                                slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-                                if (pass)
-                                {
-                                    unsigned long long const slot = slot0 + __popc(passMask & ltMask);
-                                    if (slot < P.cap)
-                                    {
-                                        lgpu_match m;
-                                        m.qry_id     = qryId;
-                                        m.subj_id    = static_cast<unsigned int>(subj);
-                                        m.qry_start  = seedBegin;
-                                        m.qry_end    = seedBegin + seedLen;
-                                        m.subj_start = static_cast<unsigned int>(pos);
-                                        m.subj_end   = static_cast<unsigned int>(pos) + seedLen;
-                                        P.out[slot]  = m;
-                                    }
-                                }
-                                hitsThisSeq += cnt;
-                            }
-                        }
+                        seedConsumeCursor(P, sM, lane, qryId, trans, red, len, seedBegin, cursor, hitsThisSeq, needlesSum,
+                                          needlesPos, nAfter, nFailed);
                     }
                 }
             }
-            needlesPos += len;
         }
     }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1)
+    seedFlushCounters(P, lane, nAfter, nFailed);
+}
+
+// ---------------------------------------------------------------------------------------------
+// seeding, one BLOCK per query (few queries: latency matters, not throughput)
+// ---------------------------------------------------------------------------------------------
+// The cursors of different seeds do not depend on each other -- only their consumption does (through
+// `hitsThisSeq`).  Phase A: the warps of the block search the seeds of the query in parallel and park
+// the non-empty cursors of every seed, in the reference's order, in a scratch list.  Phase B: warp 0
+// consumes the lists seed by seed exactly like the warp kernel.  With W warps the dependent-load chain
+// of a query shrinks from (#seeds x tree depth) to (#seeds / W x tree depth) + consumption.
+constexpr int kSeedBlockWarps = 16;
+constexpr int kSeedBlockMaxSeeds = 2048;
+
+struct SeedScratch
+{
+    Cursor *       cursors;  // [nActive][maxSeeds][maxLeaves]
+    unsigned int * counts;   // [nActive][maxSeeds]
+    unsigned int   maxSeeds; // seeds per query the scratch was sized for
+    unsigned int   maxLeaves;
+};
+
+__global__ void __launch_bounds__(32 * kSeedBlockWarps) seedBlockKernel(SeedParams P, SeedScratch S)
+{
+    __shared__ signed char  sM[1024];
+    __shared__ unsigned int sSeed[kSeedBlockMaxSeeds]; // frame << 24 | seedBegin
+    __shared__ unsigned int sNumSeeds;
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x)
+        sM[i] = P.matrix[i];
+
+    unsigned int const lane = threadIdx.x & 31u;
+    unsigned int const warp = threadIdx.x >> 5;
+    unsigned int const b    = blockIdx.x;
+    unsigned int const       q    = P.active[b];
+    DevIndex const &         ix   = P.ix;
+    unsigned int const       F    = P.Q.F;
+    unsigned long long const qb   = P.Q.offs[q];
+    unsigned int const       len  = static_cast<unsigned int>(P.Q.offs[q + 1] - qb);
+    unsigned int const       L    = P.seedLength;
+    unsigned int const       redN = ix.sigma - 1;
+    bool const               half = P.halfExact && P.maxSeedDist != 0;
+    unsigned int const       h1   = half ? L / 2 : L;
+    unsigned int const       n2   = L - h1;
+
+    if (threadIdx.x == 0)
     {
-        nAfter += __shfl_down_sync(0xffffffffu, nAfter, off);
-        nFailed += __shfl_down_sync(0xffffffffu, nFailed, off);
+        unsigned int n = 0;
+        if (len >= L)
+            for (unsigned int f = 0; f < F; ++f)
+            {
+                unsigned char const * trans = P.Q.trans + F * qb + static_cast<unsigned long long>(f) * len;
+                for (unsigned int seedBegin = 0;; seedBegin += P.seedOffset)
+                {
+                    if (!seedNextStart(trans, len, L, P.unknownRank, seedBegin))
+                        break;
+                    if (n < kSeedBlockMaxSeeds)
+                        sSeed[n] = (f << 24) | seedBegin;
+                    ++n;
+                }
+            }
+        sNumSeeds = n; // the host only routes queries here whose seed count fits (checked again below)
     }
-    if (lane == 0)
+    __syncthreads();
+    unsigned int const nSeeds = min(sNumSeeds, min(static_cast<unsigned int>(kSeedBlockMaxSeeds), S.maxSeeds));
+    Cursor *           myCur  = S.cursors + static_cast<unsigned long long>(b) * S.maxSeeds * S.maxLeaves;
+    unsigned int *     myCnt  = S.counts + static_cast<unsigned long long>(b) * S.maxSeeds;
+
+    // ---- phase A: all warps, seeds round-robin ----
+    for (unsigned int k = warp; k < nSeeds; k += kSeedBlockWarps)
     {
-        if (nAfter)
-            atomicAdd(&P.counters[1], nAfter);
-        if (nFailed)
-            atomicAdd(&P.counters[2], nFailed);
+        unsigned int const    f         = sSeed[k] >> 24;
+        unsigned int const    seedBegin = sSeed[k] & 0xffffffu;
+        unsigned char const * red       = P.Q.red + F * qb + static_cast<unsigned long long>(f) * len;
+        Cursor                E[kMaxHalf2 + 1];
+        int const             K   = seedExactChain(ix, red, seedBegin, h1, n2, E);
+        unsigned int          out = 0;
+        if (K >= 0)
+        {
+            int const          kMax     = (K < static_cast<int>(n2) - 1) ? K : static_cast<int>(n2) - 1;
+            bool const         hasExact = (K == static_cast<int>(n2));
+            unsigned int const nLeaves  = static_cast<unsigned int>(kMax + 1) * (redN - 1) + (hasExact ? 1u : 0u);
+            for (unsigned int base = 0; base < nLeaves; base += 32)
+            {
+                Cursor mine;
+                mine.lb  = 0;
+                mine.len = 0;
+                if (base + lane < nLeaves)
+                    mine = seedLeaf(ix, E, red, seedBegin, h1, n2, kMax, hasExact, redN, base + lane);
+                unsigned int const live = __ballot_sync(0xffffffffu, mine.len != 0);
+                if (mine.len != 0)
+                    myCur[static_cast<unsigned long long>(k) * S.maxLeaves + out + __popc(live & ((1u << lane) - 1u))] = mine;
+                out += __popc(live);
+            }
+        }
+        if (lane == 0)
+            myCnt[k] = out;
     }
+    __syncthreads();
+
+    // ---- phase B: warp 0 consumes the seeds in order ----
+    if (warp != 0)
+        return;
+    unsigned long long nAfter = 0, nFailed = 0;
+    unsigned long long hitsThisSeq = 0;
+    unsigned long long const needlesSum = static_cast<unsigned long long>(F) * len;
+    for (unsigned int k = 0; k < nSeeds; ++k)
+    {
+        unsigned int const    f         = sSeed[k] >> 24;
+        unsigned int const    seedBegin = sSeed[k] & 0xffffffu;
+        unsigned char const * trans     = P.Q.trans + F * qb + static_cast<unsigned long long>(f) * len;
+        unsigned char const * red       = P.Q.red + F * qb + static_cast<unsigned long long>(f) * len;
+        unsigned int const    n         = myCnt[k];
+        for (unsigned int ci = 0; ci < n; ++ci)
+        {
+            Cursor const cursor = myCur[static_cast<unsigned long long>(k) * S.maxLeaves + ci];
+            seedConsumeCursor(P, sM, lane, q * F + f, trans, red, len, seedBegin, cursor, hitsThisSeq, needlesSum,
+                              static_cast<unsigned long long>(f) * len, nAfter, nFailed);
+        }
+    }
+    seedFlushCounters(P, lane, nAfter, nFailed);
 }
 
 } // namespace lgpu
