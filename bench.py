@@ -217,7 +217,7 @@ def main():
     workload = (f"searchp: {args.n_queries}x{args.qlen}aa synthetic queries vs {args.n_seqs}-seq synthetic protein "
                 f"index (Li10), BLOSUM62, default profile")
     cfg = {"workload": workload, "queries_per_gpu": args.n_queries, "query_len": args.qlen, "index_seqs": args.n_seqs,
-           "profile": "none", "sharding": f"queries x{n_gpus}, index replicated",
+           "profile": "none", "sharding": f"queries x{n_gpus}, index replicated", "streams_per_gpu": 2,
            "l2_policy": "inputs larger than L2 (index and per-step trace/DP working sets are GBs)"}
     cores = os.cpu_count() or 1
 
@@ -259,7 +259,8 @@ def main():
     t0 = time.time()
     ix = lambda_b200.Index.load(os.path.join(d, "db.lba"), device=local_rank, keep_ids=(rank == 0))
     log(f"rank {rank}: index in HBM: {ix.device_bytes / 1e9:.2f} GB, load {time.time() - t0:.1f}s")
-    s = lambda_b200.Searcher(ix, "protein")
+    s = lambda_b200.Searcher(ix, "protein")              # default: 2 sub-batches in flight
+    s_serial = lambda_b200.Searcher(ix, "protein", streams=1)  # strictly serial: per-kernel timing / roofline
     q_ascii, qoffs = make_queries(d, args.n_queries, args.qlen, seed=1000 + rank)
     res = lambda_b200.encode(q_ascii, 0)
     h_res = torch.from_numpy(res).pin_memory()
@@ -273,11 +274,12 @@ def main():
         """the path's only collective: all ranks exchange their hit records (NCCL all-gather)"""
         return all_gather_hits(hits, first_query=rank * args.n_queries, to_host=False)[1]
 
-    def step(resident):
+    def step(resident, searcher=None):
+        searcher = searcher or s
         if resident:
-            hits, st = s.search(d_res, d_offs)
+            hits, st = searcher.search(d_res, d_offs)
         else:
-            hits, st = s.search(res, qoffs)  # host buffers: H2D of queries + D2H of hits inside
+            hits, st = searcher.search(res, qoffs)  # host buffers: H2D of queries + D2H of hits inside
         g_ms = 0.0
         if world > 1:
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -290,7 +292,7 @@ def main():
             total = len(hits)
         return hits, st, total, g_ms
 
-    def timed(resident, k):
+    def timed(resident, k, searcher=None):
         """K steps.  Device time = CUDA events recorded by the library on ITS stream around every
         lgpu_search_batch call (ms_total; torch.cuda.Event only sees torch's stream) + torch events around
         the NCCL gather; max over ranks.  Host wall-clock around the same region is reported next to it."""
@@ -300,7 +302,7 @@ def main():
         t0 = time.perf_counter()
         acc, ms = None, 0.0
         for _ in range(k):
-            hits, st, total, g_ms = step(resident)
+            hits, st, total, g_ms = step(resident, searcher)
             ms += float(st["ms_total"]) + g_ms
             acc = st.copy() if acc is None else _acc(acc, st)
         torch.cuda.synchronize()
@@ -320,11 +322,14 @@ def main():
 
     for _ in range(args.warmup):
         step(True)
+        step(True, s_serial)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_res, wall_res, st, hits, total_hits = timed(True, args.steps)
+    ms_res, wall_res, st_pipe, hits, total_hits = timed(True, args.steps)
     ms_e2e, wall_e2e, st_e2e, _, _ = timed(False, args.steps)
+    # same steps again strictly serial (one stream): per-stage / per-kernel device times for the roofline
+    ms_serial, _, st, _, _ = timed(True, args.steps, s_serial)
     clocks = sampler.summary() if rank == 0 else None
 
     nq_total = args.n_queries * n_gpus * args.steps
@@ -361,6 +366,7 @@ def main():
 
     out = {"metric": "searchp_query_seqs_per_s", "value": value, "unit": "queries/s", "n_gpus": n_gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "wall_ms_per_step": wall_res / args.steps,
+           "ms_per_step_serial_1_stream": ms_serial / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic", "config": cfg,
            "gcups": (cells_score_all + cells_trace_all) / (ms_res * 1e-3) / 1e9,
            "gcups_score_kernel": gcups_score, "gcups_trace_kernel": gcups_trace,

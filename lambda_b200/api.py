@@ -53,6 +53,7 @@ def load_library():
     lib.lgpu_params_default.argtypes = [C.POINTER(Params), C.c_uint32, C.c_char_p]
     lib.lgpu_ctx_create.argtypes = [C.POINTER(vp), vp, C.POINTER(Params)]
     lib.lgpu_ctx_destroy.argtypes = [vp]
+    lib.lgpu_ctx_set_streams.argtypes = [vp, C.c_uint32]
     lib.lgpu_last_error.restype = C.c_char_p
     lib.lgpu_last_error.argtypes = [vp]
     lib.lgpu_search_batch.argtypes = [vp, C.POINTER(QueryBatch), C.POINTER(Hits), vp]
@@ -162,11 +163,13 @@ def default_params(domain="protein", profile="none", **overrides) -> Params:
 class Searcher:
     """One search context = the reference's per-thread LocalDataHolder plus the batch loop body."""
 
-    def __init__(self, index: Index, domain="protein", profile="none", **overrides):
+    def __init__(self, index: Index, domain="protein", profile="none", streams=None, **overrides):
         self.index = index
         self.params = default_params(domain, profile, **overrides)
         self._h = C.c_void_p()
         _check(load_library().lgpu_ctx_create(C.byref(self._h), index._h, C.byref(self.params)))
+        if streams is not None:
+            _check(load_library().lgpu_ctx_set_streams(self._h, int(streams)), self._h)
 
     def close(self):
         if self._h:

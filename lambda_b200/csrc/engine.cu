@@ -22,6 +22,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -199,6 +200,8 @@ struct lgpu_ctx
     DevBuf<unsigned int>       dWork, dBestPos, dBoundary, dOrder, dOrderB, dClassInfo, dSegStart, dSegStartB, dJobHead, dJobPos, dJobs;
     DevBuf<unsigned long long> dClassKeys, dClassKeysB;
     bool                       dpxOk = false; // scoring fits the int8 profile of the DPX kernel
+    unsigned int               streams = 1;  // sub-batches in flight per lgpu_search_batch call (LAMBDA_B200_STREAMS)
+    std::vector<std::unique_ptr<lgpu_ctx>> workers;
     int                        seedMode = 0; // LAMBDA_B200_SEED=thread|warp|block forces one seeding kernel (tests); 0 = auto
     DevBuf<unsigned long long> dSeedCursors;
     DevBuf<unsigned int>       dSeedCounts;
@@ -288,40 +291,44 @@ static void checkParams(lgpu_params const & p, lgpu_index_desc const & d)
         throw ArgError("max_matches must be > 0");
 }
 
-static void uploadQueries(lgpu_ctx & c, lgpu_query_batch const & qb, lgpu_stats * st)
+// A batch as the pipeline sees it: residues in host or device memory, offsets on the host starting at 0.
+struct BatchView
+{
+    uint8_t const *  residues    = nullptr;
+    bool             resOnDevice = false;
+    uint64_t const * offsets     = nullptr; // host, n + 1 entries, offsets[0] == 0
+    uint64_t         n           = 0;
+};
+
+static void uploadQueries(lgpu_ctx & c, BatchView const & qb, lgpu_stats * st)
 {
     lgpu_index const & ix = *c.index;
-    c.nQueries            = qb.n_queries;
-    if (qb.n_queries == 0)
+    c.nQueries            = qb.n;
+    if (qb.n == 0)
         return;
-    if (qb.n_queries >= (1ull << 31) / c.di.qryNumFrames)
+    if (qb.n >= (1ull << 31) / c.di.qryNumFrames)
         throw ArgError("too many queries in one batch");
-    c.qOffsHost.resize(qb.n_queries + 1);
-    if (qb.on_device)
-        LGPU_CUDA(cudaMemcpyAsync(c.qOffsHost.data(), qb.offsets, (qb.n_queries + 1) * 8, cudaMemcpyDeviceToHost, c.stream));
-    else
-        std::memcpy(c.qOffsHost.data(), qb.offsets, (qb.n_queries + 1) * 8);
-    LGPU_CUDA(cudaStreamSynchronize(c.stream));
+    c.qOffsHost.assign(qb.offsets, qb.offsets + qb.n + 1);
     if (c.qOffsHost[0] != 0)
         throw ArgError("query offsets must start at 0");
-    c.totalResidues      = c.qOffsHost[qb.n_queries];
+    c.totalResidues      = c.qOffsHost[qb.n];
     unsigned int const F = c.di.qryNumFrames;
     c.dQOrig.reserve(c.totalResidues);
-    c.dQOffs.reserve(qb.n_queries + 1);
+    c.dQOffs.reserve(qb.n + 1);
     c.dQTrans.reserve(c.totalResidues * F);
     c.dQRed.reserve(c.totalResidues * F);
     {
         StageTimer t(c, st ? &st->ms_h2d : nullptr);
-        auto const kind = qb.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-        LGPU_CUDA(cudaMemcpyAsync(c.dQOrig.p, qb.residues, c.totalResidues, kind, c.stream));
-        LGPU_CUDA(cudaMemcpyAsync(c.dQOffs.p, qb.offsets, (qb.n_queries + 1) * 8, kind, c.stream));
+        LGPU_CUDA(cudaMemcpyAsync(c.dQOrig.p, qb.residues, c.totalResidues,
+                                  qb.resOnDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c.stream));
+        LGPU_CUDA(cudaMemcpyAsync(c.dQOffs.p, c.qOffsHost.data(), (qb.n + 1) * 8, cudaMemcpyHostToDevice, c.stream));
     }
     DevQueries & Q = c.Q;
     Q.orig         = c.dQOrig.p;
     Q.offs         = c.dQOffs.p;
     Q.trans        = c.dQTrans.p;
     Q.red          = c.dQRed.p;
-    Q.n            = static_cast<unsigned int>(qb.n_queries);
+    Q.n            = static_cast<unsigned int>(qb.n);
     Q.F            = F;
     std::memset(Q.redTab, 0, sizeof(Q.redTab));
     std::memset(Q.compTab, 0, sizeof(Q.compTab));
@@ -858,59 +865,171 @@ static void uploadActive(lgpu_ctx & c, std::vector<unsigned int> const & active)
     LGPU_CUDA(cudaStreamSynchronize(c.stream));
 }
 
+// the whole path for one batch on one context / one stream; hits end up in c.hits
+static void searchOne(lgpu_ctx & c, BatchView const & qb, lgpu_stats * st)
+{
+    LGPU_CUDA(cudaSetDevice(c.index->device));
+    c.hits.clear();
+    uploadQueries(c, qb, st);
+    if (!c.nQueries)
+        return;
+    EValueComputer ev(c.scoring.ka, c.index->dbTotalLength, c.di.qIsTranslated);
+    setThresholds(c, ev, st);
+    std::vector<unsigned int> active(c.nQueries);
+    for (uint64_t i = 0; i < c.nQueries; ++i)
+        active[i] = static_cast<unsigned int>(i);
+    uploadActive(c, active);
+    auto const maxLen = [&](std::vector<unsigned int> const & a) {
+        uint64_t m = 0;
+        for (unsigned int q : a)
+            m = std::max(m, c.qOffsHost[q + 1] - c.qOffsHost[q]);
+        return static_cast<unsigned int>(m);
+    };
+    if (c.params.iterative_search)
+    {
+        uint64_t nM = runSeeding(c, c.params.opts0, c.dActive.p, static_cast<unsigned int>(active.size()), maxLen(active), st);
+        runExtension(c, nM, 1, ev, st);
+        // iterativeSearchPre/Post: queries with at least one surviving hit are done
+        std::vector<uint8_t> ok(c.nQueries, 0);
+        for (lgpu_hit const & h : c.hits)
+            ok[h.q_id] = 1;
+        active.clear();
+        for (uint64_t i = 0; i < c.nQueries; ++i)
+            if (!ok[i])
+                active.push_back(static_cast<unsigned int>(i));
+        if (!active.empty())
+        {
+            uploadActive(c, active);
+            nM = runSeeding(c, c.params.opts, c.dActive.p, static_cast<unsigned int>(active.size()), maxLen(active), st);
+            runExtension(c, nM, 2, ev, st);
+        }
+    }
+    else
+    {
+        uint64_t const nM = runSeeding(c, c.params.opts, c.dActive.p, static_cast<unsigned int>(active.size()), maxLen(active), st);
+        runExtension(c, nM, 2, ev, st);
+    }
+    lgpu_stats dummy{};
+    if (c.params.finalize)
+    {
+        HostTimer ht(st ? &st->ms_host : nullptr);
+        finalizeRecords(c.hits, c.params.max_matches, st ? *st : dummy);
+    }
+}
+
+static std::unique_ptr<lgpu_ctx> makeContext(lgpu_index const * ix, lgpu_params const & p);
+
+static void addStats(lgpu_stats & dst, lgpu_stats const & src)
+{
+    uint64_t *       d = reinterpret_cast<uint64_t *>(&dst);
+    uint64_t const * s = reinterpret_cast<uint64_t const *>(&src);
+    for (int k = 0; k < 16; ++k)
+        d[k] += s[k];
+    dst.ms_seed += src.ms_seed;
+    dst.ms_sort_merge += src.ms_sort_merge;
+    dst.ms_extend_score += src.ms_extend_score;
+    dst.ms_extend_trace += src.ms_extend_trace;
+    dst.ms_h2d += src.ms_h2d;
+    dst.ms_d2h += src.ms_d2h;
+    dst.ms_host += src.ms_host;
+}
+
+// Host offsets of a public batch (D2H when the caller's arrays live on the device).
+static BatchView viewOf(lgpu_ctx & c, lgpu_query_batch const & qb, std::vector<uint64_t> & offs)
+{
+    offs.resize(qb.n_queries + 1);
+    if (qb.n_queries)
+    {
+        if (qb.on_device)
+        {
+            LGPU_CUDA(cudaMemcpyAsync(offs.data(), qb.offsets, (qb.n_queries + 1) * 8, cudaMemcpyDeviceToHost, c.stream));
+            LGPU_CUDA(cudaStreamSynchronize(c.stream));
+        }
+        else
+            std::memcpy(offs.data(), qb.offsets, (qb.n_queries + 1) * 8);
+    }
+    else
+        offs[0] = 0;
+    BatchView v;
+    v.residues    = qb.residues;
+    v.resOnDevice = qb.on_device != 0;
+    v.offsets     = offs.data();
+    v.n           = qb.n_queries;
+    return v;
+}
+
+// One public call.  Large batches are cut into `streams` contiguous sub-batches that run the whole
+// pipeline concurrently on their own CUDA stream and host thread: the host-only and latency-bound
+// stretches of one sub-batch (score thresholds, record finalisation, the phase-2 stragglers, every
+// device->host hand-over) overlap with the DP kernels of the other.  Results do not depend on the
+// split (every query is independent).
 static void searchBatch(lgpu_ctx & c, lgpu_query_batch const & qb, lgpu_hits * out, lgpu_stats * st)
 {
     LGPU_CUDA(cudaSetDevice(c.index->device));
-    cudaEventRecord(c.ev[2], c.stream);
-    c.hits.clear();
-    uploadQueries(c, qb, st);
-    if (c.nQueries)
+    std::vector<uint64_t> offs;
+    BatchView const       all = viewOf(c, qb, offs);
+    LGPU_CUDA(cudaEventRecord(c.ev[2], c.stream));
+    unsigned int const nW = (c.streams > 1 && all.n >= 4096) ? c.streams : 1;
+    if (nW == 1)
     {
-        EValueComputer ev(c.scoring.ka, c.index->dbTotalLength, c.di.qIsTranslated);
-        setThresholds(c, ev, st);
-        std::vector<unsigned int> active(c.nQueries);
-        for (uint64_t i = 0; i < c.nQueries; ++i)
-            active[i] = static_cast<unsigned int>(i);
-        uploadActive(c, active);
-        auto const maxLen = [&](std::vector<unsigned int> const & a) {
-            uint64_t m = 0;
-            for (unsigned int q : a)
-                m = std::max(m, c.qOffsHost[q + 1] - c.qOffsHost[q]);
-            return static_cast<unsigned int>(m);
-        };
-        if (c.params.iterative_search)
+        searchOne(c, all, st);
+    }
+    else
+    {
+        while (c.workers.size() < nW)
+            c.workers.push_back(makeContext(c.index, c.params));
+        std::vector<std::vector<uint64_t>> subOffs(nW);
+        std::vector<lgpu_stats>            wst(nW);
+        std::vector<std::string>           err(nW);
+        std::vector<std::thread>           th;
+        std::memset(wst.data(), 0, sizeof(lgpu_stats) * nW);
+        for (unsigned int w = 0; w < nW; ++w)
         {
-            uint64_t nM = runSeeding(c, c.params.opts0, c.dActive.p, static_cast<unsigned int>(active.size()), maxLen(active), st);
-            runExtension(c, nM, 1, ev, st);
-            // iterativeSearchPre/Post: queries with at least one surviving hit are done
-            std::vector<uint8_t> ok(c.nQueries, 0);
-            for (lgpu_hit const & h : c.hits)
-                ok[h.q_id] = 1;
-            active.clear();
-            for (uint64_t i = 0; i < c.nQueries; ++i)
-                if (!ok[i])
-                    active.push_back(static_cast<unsigned int>(i));
-            if (!active.empty())
-            {
-                uploadActive(c, active);
-                nM = runSeeding(c, c.params.opts, c.dActive.p, static_cast<unsigned int>(active.size()), maxLen(active), st);
-                runExtension(c, nM, 2, ev, st);
-            }
+            uint64_t const b = all.n * w / nW, e = all.n * (w + 1) / nW;
+            subOffs[w].assign(all.offsets + b, all.offsets + e + 1);
+            uint64_t const base = subOffs[w][0];
+            for (auto & x : subOffs[w])
+                x -= base;
+            BatchView v;
+            v.residues    = all.residues + base;
+            v.resOnDevice = all.resOnDevice;
+            v.offsets     = subOffs[w].data();
+            v.n           = e - b;
+            lgpu_ctx * wc = c.workers[w].get();
+            LGPU_CUDA(cudaStreamWaitEvent(wc->stream, c.ev[2], 0));
+            th.emplace_back([wc, v, w, &wst, &err] {
+                try
+                {
+                    searchOne(*wc, v, &wst[w]);
+                    LGPU_CUDA(cudaEventRecord(wc->ev[4], wc->stream));
+                }
+                catch (std::exception const & e)
+                {
+                    err[w] = e.what();
+                }
+            });
         }
-        else
+        for (auto & t : th)
+            t.join();
+        for (unsigned int w = 0; w < nW; ++w)
+            if (!err[w].empty())
+                throw CudaError("worker " + std::to_string(w) + ": " + err[w]);
+        c.hits.clear();
+        for (unsigned int w = 0; w < nW; ++w)
         {
-            uint64_t const nM = runSeeding(c, c.params.opts, c.dActive.p, static_cast<unsigned int>(active.size()), maxLen(active), st);
-            runExtension(c, nM, 2, ev, st);
-        }
-        lgpu_stats dummy{};
-        if (c.params.finalize)
-        {
-            HostTimer ht(st ? &st->ms_host : nullptr);
-            finalizeRecords(c.hits, c.params.max_matches, st ? *st : dummy);
+            lgpu_ctx &     wc   = *c.workers[w];
+            uint64_t const b    = all.n * w / nW;
+            size_t const   base = c.hits.size();
+            c.hits.insert(c.hits.end(), wc.hits.begin(), wc.hits.end());
+            for (size_t i = base; i < c.hits.size(); ++i)
+                c.hits[i].q_id += static_cast<uint32_t>(b);
+            LGPU_CUDA(cudaStreamWaitEvent(c.stream, wc.ev[4], 0));
+            if (st)
+                addStats(*st, wst[w]);
         }
     }
-    cudaEventRecord(c.ev[3], c.stream);
-    cudaEventSynchronize(c.ev[3]);
+    LGPU_CUDA(cudaEventRecord(c.ev[3], c.stream));
+    LGPU_CUDA(cudaEventSynchronize(c.ev[3]));
     if (st)
     {
         float ms = 0;
@@ -965,6 +1084,40 @@ static int guarded(std::string * err, F && f)
         g_lastError                = e.what();
         return LGPU_ERR_INTERNAL;
     }
+}
+
+static std::unique_ptr<lgpu_ctx> lgpu::makeContext(lgpu_index const * ix, lgpu_params const & p)
+{
+    checkParams(p, ix->meta);
+    auto c    = std::make_unique<lgpu_ctx>();
+    c->index  = ix;
+    c->params = p;
+    c->di     = domainInfo(p.domain);
+    int rc    = makeScoring(c->scoring, p);
+    if (rc == LGPU_ERR_ARG)
+        throw ArgError("Could not compute Karlin-Altschul-Values for Scoring Scheme.");
+    if (rc != LGPU_OK)
+        throw UnsupportedError("unsupported scoring configuration");
+    LGPU_CUDA(cudaSetDevice(ix->device));
+    LGPU_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto & e : c->ev)
+        LGPU_CUDA(cudaEventCreate(&e));
+    LGPU_CUDA(cudaDeviceGetAttribute(&c->numSMs, cudaDevAttrMultiProcessorCount, ix->device));
+    c->dMatrix.reserve(1024);
+    LGPU_CUDA(cudaMemcpy(c->dMatrix.p, c->scoring.matrix, 1024, cudaMemcpyHostToDevice));
+    c->dCounters.reserve(8);
+    if (char const * e = std::getenv("LAMBDA_B200_SEED"))
+        c->seedMode = !std::strcmp(e, "thread") ? 1 : !std::strcmp(e, "warp") ? 2 : !std::strcmp(e, "block") ? 3 : 0;
+    // the packed kernel stores (score - gapOpen) as int8 profile bytes with -128 reserved for "null"
+    c->dpxOk = c->scoring.alphSize < 32 && c->scoring.gapOpenSeqan <= c->scoring.gapExtend && c->scoring.gapExtend <= 0;
+    for (int a = 0; a < c->scoring.alphSize; ++a)
+        for (int b = 0; b < c->scoring.alphSize; ++b)
+        {
+            int const v = c->scoring.matrix[a * 32 + b] - c->scoring.gapOpenSeqan;
+            if (v < -127 || v > 127)
+                c->dpxOk = false;
+        }
+    return c;
 }
 
 extern "C"
@@ -1067,40 +1220,24 @@ int lgpu_ctx_create(lgpu_ctx ** out, lgpu_index const * ix, lgpu_params const * 
         return LGPU_ERR_ARG;
     *out = nullptr;
     return guarded(nullptr, [&] {
-        checkParams(*p, ix->meta);
-        auto c    = std::make_unique<lgpu_ctx>();
-        c->index  = ix;
-        c->params = *p;
-        c->di     = domainInfo(p->domain);
-        int rc    = makeScoring(c->scoring, *p);
-        if (rc == LGPU_ERR_ARG)
-            throw ArgError("Could not compute Karlin-Altschul-Values for Scoring Scheme.");
-        if (rc != LGPU_OK)
-            throw UnsupportedError("unsupported scoring configuration");
-        LGPU_CUDA(cudaSetDevice(ix->device));
-        LGPU_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-        for (auto & e : c->ev)
-            LGPU_CUDA(cudaEventCreate(&e));
-        LGPU_CUDA(cudaDeviceGetAttribute(&c->numSMs, cudaDevAttrMultiProcessorCount, ix->device));
-        c->dMatrix.reserve(1024);
-        LGPU_CUDA(cudaMemcpy(c->dMatrix.p, c->scoring.matrix, 1024, cudaMemcpyHostToDevice));
-        c->dCounters.reserve(8);
-        if (char const * e = std::getenv("LAMBDA_B200_SEED"))
-            c->seedMode = !std::strcmp(e, "thread") ? 1 : !std::strcmp(e, "warp") ? 2 : !std::strcmp(e, "block") ? 3 : 0;
-        // the packed kernel stores (score - gapOpen) as int8 profile bytes with -128 reserved for "null"
-        c->dpxOk = c->scoring.alphSize < 32 && c->scoring.gapOpenSeqan <= c->scoring.gapExtend && c->scoring.gapExtend <= 0;
-        for (int a = 0; a < c->scoring.alphSize; ++a)
-            for (int b = 0; b < c->scoring.alphSize; ++b)
-            {
-                int const v = c->scoring.matrix[a * 32 + b] - c->scoring.gapOpenSeqan;
-                if (v < -127 || v > 127)
-                    c->dpxOk = false;
-            }
+        auto c = makeContext(ix, *p);
+        // sub-batches in flight per search call; worker contexts are created on first use
+        c->streams = 2;
+        if (char const * e = std::getenv("LAMBDA_B200_STREAMS"))
+            c->streams = static_cast<unsigned int>(std::max(1, std::min(8, std::atoi(e))));
         *out = c.release();
     });
 }
 
 void lgpu_ctx_destroy(lgpu_ctx * c) { delete c; }
+
+int lgpu_ctx_set_streams(lgpu_ctx * c, uint32_t n)
+{
+    if (!c || n < 1 || n > 8)
+        return LGPU_ERR_ARG;
+    c->streams = n;
+    return LGPU_OK;
+}
 
 char const * lgpu_last_error(lgpu_ctx const * c) { return (c && !c->err.empty()) ? c->err.c_str() : g_lastError.c_str(); }
 
@@ -1118,7 +1255,10 @@ int lgpu_seed_batch(lgpu_ctx * c, lgpu_query_batch const * q, int phase, lgpu_ma
         return LGPU_ERR_ARG;
     return guarded(&c->err, [&] {
         LGPU_CUDA(cudaSetDevice(c->index->device));
-        uploadQueries(*c, *q, stats);
+        {
+            std::vector<uint64_t> offsTmp;
+            uploadQueries(*c, viewOf(*c, *q, offsTmp), stats);
+        }
         std::vector<unsigned int> active(c->nQueries);
         for (uint64_t i = 0; i < c->nQueries; ++i)
             active[i] = static_cast<unsigned int>(i);
@@ -1145,7 +1285,10 @@ int lgpu_merge_matches(lgpu_ctx * c, lgpu_query_batch const * q, lgpu_match cons
         return LGPU_ERR_ARG;
     return guarded(&c->err, [&] {
         LGPU_CUDA(cudaSetDevice(c->index->device));
-        uploadQueries(*c, *q, stats);
+        {
+            std::vector<uint64_t> offsTmp;
+            uploadQueries(*c, viewOf(*c, *q, offsTmp), stats);
+        }
         c->dUserMatches.reserve(nIn);
         if (nIn)
             LGPU_CUDA(cudaMemcpyAsync(c->dUserMatches.p, in, nIn * sizeof(lgpu_match), cudaMemcpyHostToDevice, c->stream));
@@ -1183,7 +1326,10 @@ int lgpu_extend_scores(lgpu_ctx * c, lgpu_query_batch const * q, lgpu_match cons
         return LGPU_ERR_ARG;
     return guarded(&c->err, [&] {
         LGPU_CUDA(cudaSetDevice(c->index->device));
-        uploadQueries(*c, *q, stats);
+        {
+            std::vector<uint64_t> offsTmp;
+            uploadQueries(*c, viewOf(*c, *q, offsTmp), stats);
+        }
         if (n == 0)
             return;
         checkWindows(*c, win, n);
@@ -1203,7 +1349,10 @@ int lgpu_extend_trace(lgpu_ctx * c, lgpu_query_batch const * q, lgpu_match const
         return LGPU_ERR_ARG;
     return guarded(&c->err, [&] {
         LGPU_CUDA(cudaSetDevice(c->index->device));
-        uploadQueries(*c, *q, stats);
+        {
+            std::vector<uint64_t> offsTmp;
+            uploadQueries(*c, viewOf(*c, *q, offsTmp), stats);
+        }
         if (n == 0)
             return;
         checkWindows(*c, win, n);

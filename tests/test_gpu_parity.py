@@ -247,3 +247,30 @@ def test_cli_output_is_byte_identical_to_reference(golden_dir, tmp_path, case, d
     assert f"Number of total hits:                           {funnel['hits_final']}" in txt
     # refuses to overwrite, like the reference's create_new validator
     assert subprocess.run(cmd, capture_output=True).returncode != 0
+
+
+def test_multi_stream_split_is_invisible(golden_dir):
+    """large batches are cut into sub-batches running concurrently on several streams / host threads:
+    hits, their order and every counter must equal the strictly serial run"""
+    path, ids, res, offs = _load(golden_dir, "prot_flat", 0)
+    reps = 90  # 57 queries x 90 = 5130 > the 4096-query split threshold
+    lens = np.diff(offs.astype(np.int64))
+    big_res = np.tile(res, reps)
+    big_offs = np.concatenate([[0], np.cumsum(np.tile(lens, reps))]).astype(np.uint64)
+    big_ids = [f"{i}_{q}" for i in range(reps) for q in ids]
+    ix = lambda_b200.Index.load(path)
+    ref = None
+    for streams in (1, 2, 3):
+        s = lambda_b200.Searcher(ix, "protein", streams=streams)
+        hits, st = s.search(big_res, big_offs)
+        cur = (hits.copy(), {k: int(st[k]) for k in FUNNEL})
+        if ref is None:
+            ref = cur
+            golden, funnel = load_golden(golden_dir, "prot_flat", "none")
+            first = hits[hits["q_id"] < len(ids)]
+            assert sorted(s.m8(first, ids)) == sorted(golden)
+            assert cur[1]["hits_final"] == funnel["hits_final"] * reps
+        else:
+            assert (cur[0] == ref[0]).all() and cur[1] == ref[1]
+        s.close()
+    ix.close()
