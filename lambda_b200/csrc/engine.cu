@@ -33,6 +33,7 @@
 #include "host_finalize.hpp"
 #include "host_params.hpp"
 #include "kernels_dpx.cuh"
+#include "kernels_dpx_trace.cuh"
 #include "kernels_extend.cuh"
 #include "kernels_fm.cuh"
 #include "lba_index.hpp"
@@ -208,6 +209,9 @@ struct lgpu_ctx
     DevBuf<unsigned char>      dTrace;
     DevBuf<unsigned long long> dTraceOff;
     DevBuf<lgpu_hit>           dHits;
+    DevBuf<unsigned int>       dPlanes;      // (H, dE|dF) planes of the packed trace kernel
+    DevBuf<lgpu_match>         dTasksScalar;
+    bool                       forceScalarTrace = false; // LAMBDA_B200_TRACE=scalar (tests)
 
     // pinned staging
     PinnedBuf<lgpu_match> hTasks;
@@ -695,13 +699,10 @@ static void runScorePass(lgpu_ctx & c, lgpu_match const * dTasks, unsigned int n
     }
 }
 
-// DP pass 2 + traceback for `n` tasks (host copy `tasks`, device copy dTasks); hostOut[i] <-> tasks[i]
-static void runTracePass(lgpu_ctx & c, lgpu_match const * tasks, size_t n, lgpu_match const * dTasks, lgpu_hit * hostOut,
-                         lgpu_stats * st)
+// DP pass 2 + traceback on the scalar wavefront kernel (1 trace byte per cell) for `n` tasks
+// (host copy `tasks`, device copy dTasks); results land in c.hHits[0..n)
+static void runTraceScalar(lgpu_ctx & c, lgpu_match const * tasks, size_t n, lgpu_match const * dTasks, lgpu_stats * st)
 {
-    if (n == 0)
-        return;
-    StageTimer     t(c, st ? &st->ms_extend_trace : nullptr);
     TaskDims const dims = taskDims(tasks, n);
     int const      K    = chooseK(dims.maxQ);
     unsigned int const cols = 32 * K, colBytes = 32 * ((K + 3) / 4 * 4);
@@ -762,11 +763,166 @@ static void runTracePass(lgpu_ctx & c, lgpu_match const * tasks, size_t n, lgpu_
             st->kernel_launches += 2;
         begin = end;
     }
-    std::memcpy(hostOut, c.hHits.p, n * sizeof(lgpu_hit));
+}
+
+template <int K>
+static void launchDpxTrace(lgpu_ctx & c, DpxTraceParams P, unsigned int maxNt)
+{
+    P.winCap          = (maxNt + 4 * 32 + 127) / 128 * 128;
+    size_t const smem = static_cast<size_t>(P.nCodes) * dpxRowWords(32, K) * 4 + P.winCap;
+    LGPU_CUDA(cudaFuncSetAttribute(swTraceDpxKernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (smem > 227 * 1024)
+        throw CudaError("DPX trace kernel: window too long for shared memory");
+    unsigned int const grid = std::min<unsigned int>(P.nTasks, static_cast<unsigned int>(c.numSMs) * 32);
+    swTraceDpxKernel<K><<<grid, 32, smem, c.stream>>>(P);
+    LGPU_CUDA(cudaGetLastError());
+}
+
+// DP pass 2 + traceback for `n` tasks (host copy `tasks`, device copy dTasks); hostOut[i] <-> tasks[i].
+// Alignments whose query fits 64 x 32 columns run on the packed DPX trace kernel (one warp each, planes
+// of (H, dE, dF) instead of trace bytes); the rest on the scalar wavefront kernel.
+static void runTracePass(lgpu_ctx & c, lgpu_match const * tasks, size_t n, lgpu_match const * dTasks, lgpu_hit * hostOut,
+                         lgpu_stats * st)
+{
+    if (n == 0)
+        return;
+    StageTimer t(c, st ? &st->ms_extend_trace : nullptr);
+    int const  D      = c.scoring.gapExtend - c.scoring.gapOpenSeqan;
+    bool const dpxOk  = c.dpxOk && D >= 0 && D <= 14 && !c.forceScalarTrace;
+    uint64_t   cells  = 0;
+    std::vector<std::vector<unsigned int>> lists(kNumTraceClasses + 1);
+    for (size_t i = 0; i < n; ++i)
+    {
+        unsigned int const nq = tasks[i].qry_end - tasks[i].qry_start, nt = tasks[i].subj_end - tasks[i].subj_start;
+        cells += static_cast<uint64_t>(nq) * nt;
+        int cls = dpxTraceClassOf(nq);
+        if (!dpxOk || nt > kDpxMaxWindow)
+            cls = kNumTraceClasses;
+        lists[cls].push_back(static_cast<unsigned int>(i));
+    }
+    c.dHits.reserve(n);
+    c.hHits.reserve(n);
+
+    // ---- packed classes ----
+    constexpr uint64_t kMaxPlaneWords = (16ull << 30) / 4;
+    std::vector<unsigned long long> planeOff(n, 0);
+    bool                            anyDpx = false;
+    for (int cls = 0; cls < kNumTraceClasses; ++cls)
+    {
+        std::vector<unsigned int> const & L = lists[cls];
+        if (L.empty())
+            continue;
+        anyDpx      = true;
+        int const K = dpxTraceK(cls);
+        c.dOrder.reserve(n);
+        c.dTraceOff.reserve(n);
+        c.dScores2.reserve(n);
+        c.dBestPos.reserve(n);
+        size_t begin = 0;
+        while (begin < L.size())
+        {
+            uint64_t     words = 0;
+            unsigned int maxNt = 0;
+            size_t       end   = begin;
+            while (end < L.size())
+            {
+                unsigned int const nt = tasks[L[end]].subj_end - tasks[L[end]].subj_start;
+                uint64_t const     w  = dpxTracePlaneWords(K, nt);
+                if (end > begin && words + w > kMaxPlaneWords)
+                    break;
+                planeOff[L[end]] = words;
+                words += w;
+                maxNt = std::max(maxNt, nt);
+                ++end;
+            }
+            unsigned int const cnt = static_cast<unsigned int>(end - begin);
+            c.dPlanes.reserve(words);
+            LGPU_CUDA(cudaMemcpyAsync(c.dOrder.p, L.data() + begin, cnt * 4ull, cudaMemcpyHostToDevice, c.stream));
+            LGPU_CUDA(cudaMemcpyAsync(c.dTraceOff.p, planeOff.data(), n * 8ull, cudaMemcpyHostToDevice, c.stream));
+            LGPU_CUDA(cudaMemsetAsync(c.dWork.p, 0, 4, c.stream));
+            DpxTraceParams P{};
+            P.ix          = c.index->dev;
+            P.Q           = c.Q;
+            P.tasks       = dTasks;
+            P.order       = c.dOrder.p;
+            P.nTasks      = cnt;
+            P.sbjFrames   = c.di.sbjNumFrames;
+            P.matrix      = c.dMatrix.p;
+            P.go          = c.scoring.gapOpenSeqan;
+            P.ge          = c.scoring.gapExtend;
+            P.nCodes      = static_cast<unsigned int>(c.scoring.alphSize) + 1;
+            P.workCounter = c.dWork.p;
+            P.planes      = c.dPlanes.p;
+            P.planeOff    = c.dTraceOff.p;
+            P.scores      = c.dScores2.p;
+            P.bestCol     = c.dBestPos.p;
+            switch (K)
+            {
+                case 1: launchDpxTrace<1>(c, P, maxNt); break;
+                case 2: launchDpxTrace<2>(c, P, maxNt); break;
+                case 3: launchDpxTrace<3>(c, P, maxNt); break;
+                case 4: launchDpxTrace<4>(c, P, maxNt); break;
+                case 5: launchDpxTrace<5>(c, P, maxNt); break;
+                case 6: launchDpxTrace<6>(c, P, maxNt); break;
+                case 8: launchDpxTrace<8>(c, P, maxNt); break;
+                case 10: launchDpxTrace<10>(c, P, maxNt); break;
+                case 12: launchDpxTrace<12>(c, P, maxNt); break;
+                case 16: launchDpxTrace<16>(c, P, maxNt); break;
+                case 24: launchDpxTrace<24>(c, P, maxNt); break;
+                default: launchDpxTrace<32>(c, P, maxNt); break;
+            }
+            TracebackDpxParams TP{};
+            TP.ix        = c.index->dev;
+            TP.Q         = c.Q;
+            TP.tasks     = dTasks;
+            TP.order     = c.dOrder.p;
+            TP.nTasks    = cnt;
+            TP.sbjFrames = c.di.sbjNumFrames;
+            TP.domain    = c.params.domain;
+            TP.matrix    = c.dMatrix.p;
+            TP.go        = c.scoring.gapOpenSeqan;
+            TP.ge        = c.scoring.gapExtend;
+            TP.K         = static_cast<unsigned int>(K);
+            TP.scores    = c.dScores2.p;
+            TP.bestCol   = c.dBestPos.p;
+            TP.planes    = c.dPlanes.p;
+            TP.planeOff  = c.dTraceOff.p;
+            TP.out       = c.dHits.p;
+            tracebackDpxKernel<<<gridFor(cnt, 128), 128, 0, c.stream>>>(TP);
+            LGPU_CUDA(cudaGetLastError());
+            LGPU_CUDA(cudaStreamSynchronize(c.stream)); // the order / offset staging arrays are reused by the next chunk
+            if (st)
+                st->kernel_launches += 2;
+            begin = end;
+        }
+    }
+    if (anyDpx)
+    {
+        LGPU_CUDA(cudaMemcpyAsync(c.hHits.p, c.dHits.p, n * sizeof(lgpu_hit), cudaMemcpyDeviceToHost, c.stream));
+        LGPU_CUDA(cudaStreamSynchronize(c.stream));
+        for (int cls = 0; cls < kNumTraceClasses; ++cls)
+            for (unsigned int i : lists[cls])
+                hostOut[i] = c.hHits.p[i];
+    }
+
+    // ---- scalar class ----
+    std::vector<unsigned int> const & LS = lists[kNumTraceClasses];
+    if (!LS.empty())
+    {
+        std::vector<lgpu_match> sub(LS.size());
+        for (size_t k = 0; k < LS.size(); ++k)
+            sub[k] = tasks[LS[k]];
+        c.dTasksScalar.reserve(sub.size());
+        LGPU_CUDA(cudaMemcpyAsync(c.dTasksScalar.p, sub.data(), sub.size() * sizeof(lgpu_match), cudaMemcpyHostToDevice, c.stream));
+        LGPU_CUDA(cudaStreamSynchronize(c.stream));
+        runTraceScalar(c, sub.data(), sub.size(), c.dTasksScalar.p, st);
+        for (size_t k = 0; k < LS.size(); ++k)
+            hostOut[LS[k]] = c.hHits.p[k];
+    }
     if (st)
     {
         st->n_extensions_trace += n;
-        st->cells_trace += dims.cells;
+        st->cells_trace += cells;
     }
 }
 
@@ -1108,6 +1264,8 @@ static std::unique_ptr<lgpu_ctx> lgpu::makeContext(lgpu_index const * ix, lgpu_p
     c->dCounters.reserve(8);
     if (char const * e = std::getenv("LAMBDA_B200_SEED"))
         c->seedMode = !std::strcmp(e, "thread") ? 1 : !std::strcmp(e, "warp") ? 2 : !std::strcmp(e, "block") ? 3 : 0;
+    if (char const * e = std::getenv("LAMBDA_B200_TRACE"))
+        c->forceScalarTrace = !std::strcmp(e, "scalar");
     // the packed kernel stores (score - gapOpen) as int8 profile bytes with -128 reserved for "null"
     c->dpxOk = c->scoring.alphSize < 32 && c->scoring.gapOpenSeqan <= c->scoring.gapExtend && c->scoring.gapExtend <= 0;
     for (int a = 0; a < c->scoring.alphSize; ++a)

@@ -76,8 +76,12 @@ def test_seeding_matches_oracle(golden_dir, case, domain, profile, mode, monkeyp
     s.close(); ix.close(); o.close()
 
 
+@pytest.mark.parametrize("trace", ["dpx", "scalar"])
 @pytest.mark.parametrize("case,domain", [(c, d) for c, d, _ in CASES])
-def test_extension_matches_oracle(golden_dir, case, domain):
+def test_extension_matches_oracle(golden_dir, case, domain, trace, monkeypatch):
+    """DP pass 1 scores and the full pass-2 records (coordinates + statistics) for both trace paths:
+    packed DPX planes and the scalar trace-byte kernel"""
+    monkeypatch.setenv("LAMBDA_B200_TRACE", trace)
     path, ids, res, offs = _load(golden_dir, case, domain)
     o = orc.Oracle(path)
     ix = lambda_b200.Index.load(path)
@@ -101,8 +105,10 @@ def test_extension_matches_oracle(golden_dir, case, domain):
     s.close(); ix.close(); o.close()
 
 
-def test_extension_long_queries_multi_block(golden_dir):
+@pytest.mark.parametrize("trace", ["dpx", "scalar"])
+def test_extension_long_queries_multi_block(golden_dir, trace, monkeypatch):
     """queries longer than one 32*K column block (boundary row path) and long merged windows"""
+    monkeypatch.setenv("LAMBDA_B200_TRACE", trace)
     path = os.path.join(golden_dir, "prot_flat", "db.lba")
     o = orc.Oracle(path)
     ix = lambda_b200.Index.load(path)
@@ -170,6 +176,12 @@ def test_score_kernel_all_length_classes(golden_dir):
     bad = np.nonzero(sc_gpu != sc_cpu)[0]
     assert len(bad) == 0, (win[bad[:5]], sc_gpu[bad[:5]], sc_cpu[bad[:5]])
     assert sc_cpu.max() > 1000
+    # pass 2 over the same ragged set: every K class of the packed trace kernel + the scalar fallback
+    _, h_cpu = o.extend(p, res, qo, win, True)
+    h_gpu, _ = s.extend_trace(res, qo, win)
+    for f in HIT_INT_FIELDS:
+        bad = np.nonzero(h_gpu[f] != h_cpu[f])[0]
+        assert len(bad) == 0, (f, win[bad[:3]], h_gpu[bad[:3]], h_cpu[bad[:3]])
     # other scoring schemes through the same kernels
     for kw in (dict(scoring_method=45, gap_open=-14, gap_extend=-2), dict(scoring_method=80, gap_open=-10, gap_extend=-1)):
         s2 = lambda_b200.Searcher(ix, "protein", **kw)
