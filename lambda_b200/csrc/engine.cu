@@ -802,6 +802,7 @@ static void runTracePass(lgpu_ctx & c, lgpu_match const * tasks, size_t n, lgpu_
     }
     c.dHits.reserve(n);
     c.hHits.reserve(n);
+    c.dWork.reserve(kNumDpxClasses + 2);
 
     // ---- packed classes ----
     constexpr uint64_t kMaxPlaneWords = (16ull << 30) / 4;
@@ -985,7 +986,7 @@ static void runExtension(lgpu_ctx & c, uint64_t nMatches, uint8_t phase, EValueC
             continue;
         }
         h.phase     = phase;
-        h.bit_score = bitScore(c.scoring.ka, h.score);
+        h.bit_score = ev.bits(h.score);
         h.evalue    = ev.evalue(h.score, h.q_len);
         c.hits[out++] = h;
     }

@@ -271,41 +271,62 @@ inline double bitScore(KarlinAltschul const & ka, double rawScore)
 }
 
 // computeEValueThreadSafe with its per-length cache; `queryLen` is the ORIGINAL query length
-// (bm.qLength), divided by 3 for translated queries.
+// (bm.qLength), divided by 3 for translated queries.  Per query length we cache, besides the length
+// adjustment, the prefix K * (m - adj) * (n - adj) in the reference's evaluation order, so an e-value is
+// one exp() and one multiplication with bit-identical results.
 class EValueComputer
 {
 public:
     EValueComputer(KarlinAltschul const & ka, uint64_t dbTotalLength, bool qIsTranslated) :
-      ka_(ka), dbLen_(dbTotalLength), div_(qIsTranslated ? 3 : 1)
+      ka_(ka), dbLen_(dbTotalLength), div_(qIsTranslated ? 3 : 1), lnK_(std::log(ka.K)), ln2_(std::log(2))
     {}
 
-    uint64_t adjustment(uint64_t queryLen)
-    {
-        uint64_t const ql = queryLen / div_;
-        auto           it = cache_.find(ql);
-        if (it == cache_.end())
-            it = cache_.emplace(ql, lengthAdjustment(dbLen_, ql, ka_)).first;
-        return it->second;
-    }
+    uint64_t adjustment(uint64_t queryLen) { return entry(queryLen).adj; }
 
     double evalue(int32_t rawScore, uint64_t queryLen)
     {
-        uint64_t const ql  = queryLen / div_;
-        uint64_t const adj = adjustment(queryLen);
-        // unsigned subtraction, then conversion to double -- as in the reference
-        double const m = static_cast<double>(ql - adj);
-        double const n = static_cast<double>(dbLen_ - adj);
-        return ka_.K * m * n * std::exp(-ka_.lambda * static_cast<double>(rawScore));
+        return entry(queryLen).prefix * std::exp(-ka_.lambda * static_cast<double>(rawScore));
     }
+
+    double bits(int32_t rawScore) const { return (ka_.lambda * static_cast<double>(rawScore) - lnK_) / ln2_; }
 
     KarlinAltschul const & ka() const { return ka_; }
     uint64_t               dbLen() const { return dbLen_; }
 
 private:
-    KarlinAltschul                         ka_;
-    uint64_t                               dbLen_;
-    uint64_t                               div_;
-    std::unordered_map<uint64_t, uint64_t> cache_;
+    struct Entry
+    {
+        uint64_t adj;
+        double   prefix; // (K * m) * n with m = ql - adj, n = dbLen - adj (unsigned subtraction, then double)
+    };
+
+    Entry const & entry(uint64_t queryLen)
+    {
+        if (queryLen == lastLen_)
+            return last_;
+        uint64_t const ql = queryLen / div_;
+        auto           it = cache_.find(ql);
+        if (it == cache_.end())
+        {
+            Entry e;
+            e.adj          = lengthAdjustment(dbLen_, ql, ka_);
+            double const m = static_cast<double>(ql - e.adj);
+            double const n = static_cast<double>(dbLen_ - e.adj);
+            e.prefix       = ka_.K * m * n;
+            it             = cache_.emplace(ql, e).first;
+        }
+        lastLen_ = queryLen;
+        last_    = it->second;
+        return last_;
+    }
+
+    KarlinAltschul                      ka_;
+    uint64_t                            dbLen_;
+    uint64_t                            div_;
+    double                              lnK_, ln2_;
+    std::unordered_map<uint64_t, Entry> cache_;
+    uint64_t                            lastLen_ = ~0ull;
+    Entry                               last_{};
 };
 
 // Integer thresholds that reproduce the reference's two pass-1 filters exactly

@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(128) tracebackDpxKernel(TracebackDpxParams P)
     };
 
     int const    score = P.scores[task];
-    unsigned int i = P.bestCol[task], j = 0;
+    unsigned int i = (score > 0) ? P.bestCol[task] : 0u, j = 0; // no positive cell: empty alignment at (0, 0)
     if (score > 0)
         for (unsigned int jj = 1; jj <= nt; ++jj) // first row of the best column that holds the best score
             if (cellH(i, jj) == score)
