@@ -42,15 +42,27 @@ def log(*a):
 # workload
 # ------------------------------------------------------------------------------------------------
 
-def workload_dir(n_seqs, seed):
-    key = hashlib.sha1(f"protein-flat-{n_seqs}-{seed}-v2".encode()).hexdigest()[:12]
-    return os.path.join(CACHE, f"searchp_{n_seqs}_{key}")
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the headline metric is quoted on
+    "searchp": dict(domain="protein", dom=0, mk="mkindexp", search="searchp", n_seqs=5_000_000, n_queries=100_000,
+                    qlen=300, unit="aa", what="synthetic protein index (Li10), BLOSUM62"),
+    # BASELINE.json configs[2]: n_seqs = chromosomes of 1 Mbp each (200 Mbp)
+    "searchn": dict(domain="nucleotide", dom=1, mk="mkindexn", search="searchn", n_seqs=200, n_queries=1_000_000,
+                    qlen=150, unit="bp", what="x1Mbp synthetic nucleotide index (dna4), match 2 / mismatch -3"),
+}
+CHROM_LEN = 1_000_000
 
 
-def ensure_index(n_seqs, seed=1):
+def workload_dir(wl, n_seqs, seed):
+    key = hashlib.sha1(f"{wl}-flat-{n_seqs}-{seed}-v2".encode()).hexdigest()[:12]
+    return os.path.join(CACHE, f"{wl}_{n_seqs}_{key}")
+
+
+def ensure_index(wl, n_seqs, seed=1):
     """database FASTA + reference-built .lba, cached; safe against concurrent ranks"""
     from lambda_b200 import synth
-    d = workload_dir(n_seqs, seed)
+    W = WORKLOADS[wl]
+    d = workload_dir(wl, n_seqs, seed)
     done = os.path.join(d, "READY")
     if os.path.exists(done):
         return d
@@ -72,7 +84,10 @@ def ensure_index(n_seqs, seed=1):
             raise RuntimeError(f"{REF} missing: run `python -c 'import __graft_entry__ as g; g.build()'` where "
                                "/root/reference is available (the binary travels with the repo snapshot)")
         t0 = time.time()
-        db, offs = synth.protein_db(n_seqs, seed=seed)
+        if wl == "searchp":
+            db, offs = synth.protein_db(n_seqs, seed=seed)
+        else:
+            db, offs = synth.nucl_db(n_seqs, CHROM_LEN, seed=seed)
         synth.write_fasta(os.path.join(d, "db.fasta"), db, offs, "S")
         np.save(os.path.join(d, "db_offsets.npy"), offs)
         log(f"database: {n_seqs} seqs, {int(offs[-1])} residues generated in {time.time() - t0:.1f}s")
@@ -80,16 +95,16 @@ def ensure_index(n_seqs, seed=1):
         lba = os.path.join(d, "db.lba")
         if os.path.exists(lba):
             os.remove(lba)
-        subprocess.check_call([REF, "mkindexp", "-d", os.path.join(d, "db.fasta"), "-i", lba, "-v", "0",
+        subprocess.check_call([REF, W["mk"], "-d", os.path.join(d, "db.fasta"), "-i", lba, "-v", "0",
                                "-t", str(os.cpu_count() or 1)])
-        log(f"reference mkindexp: {time.time() - t0:.1f}s, {os.path.getsize(lba) / 1e9:.2f} GB")
+        log(f"reference {W['mk']}: {time.time() - t0:.1f}s, {os.path.getsize(lba) / 1e9:.2f} GB")
         open(done, "w").write("ok\n")
     finally:
         os.remove(lock)
     return d
 
 
-def make_queries(d, n_queries, qlen, seed):
+def make_queries(wl, d, n_queries, qlen, seed):
     """mutated windows of database sequences; returns (ascii residues, offsets)"""
     from lambda_b200 import synth
     offs = np.load(os.path.join(d, "db_offsets.npy"))
@@ -105,7 +120,17 @@ def make_queries(d, n_queries, qlen, seed):
     elig = np.nonzero(lens >= qlen)[0]
     pick = elig[rng.integers(0, len(elig), n_queries)]
     start = seq_start[pick] + (rng.random(n_queries) * (lens[pick] - qlen + 1)).astype(np.int64)
-    q = np.asarray(fa[start[:, None] + np.arange(qlen)[None, :]])
+    q = np.empty((n_queries, qlen), np.uint8)
+    step = 1 << 16
+    for b in range(0, n_queries, step):
+        e = min(n_queries, b + step)
+        q[b:e] = fa[start[b:e, None] + np.arange(qlen)[None, :]]
+    if wl == "searchn":
+        m = rng.random(q.shape, dtype=np.float32) < 0.03
+        q[m] = synth.NT[rng.integers(0, 4, int(m.sum()), dtype=np.uint8)]
+        odd = np.arange(n_queries) % 2 == 1
+        q[odd] = synth._COMP[q[odd][:, ::-1]]
+        return q.reshape(-1), np.arange(n_queries + 1, dtype=np.uint64) * qlen
     rate = rng.uniform(0.15, 0.20, n_queries)[:, None]
     m = rng.random(q.shape, dtype=np.float32) < rate
     q[m] = synth._random_residues(rng, int(m.sum()))
@@ -163,7 +188,7 @@ class ClockSampler(threading.Thread):
 # reference arm / cpu baseline
 # ------------------------------------------------------------------------------------------------
 
-def run_reference_search(d, q_ascii, qoffs, n_sample, threads, tag):
+def run_reference_search(wl, d, q_ascii, qoffs, n_sample, threads, tag):
     """time the unmodified reference (searchp, OpenMP) on the first n_sample queries; returns
     (queries/s over the reference's own 'Runtime total' search phase, wall seconds, hits)"""
     import re
@@ -174,7 +199,7 @@ def run_reference_search(d, q_ascii, qoffs, n_sample, threads, tag):
         synth.write_fasta(qf, q_ascii[: int(qoffs[n_sample])], qoffs[: n_sample + 1].astype(np.int64), "Q")
         out = os.path.join(tmp, "out.m8")
         t0 = time.time()
-        txt = subprocess.run([REF, "searchp", "-q", qf, "-i", os.path.join(d, "db.lba"), "-o", out, "-t", str(threads),
+        txt = subprocess.run([REF, WORKLOADS[wl]["search"], "-q", qf, "-i", os.path.join(d, "db.lba"), "-o", out, "-t", str(threads),
                               "--version-to-outputfile", "0", "-v", "2"], check=True, capture_output=True, text=True).stdout
         wall = time.time() - t0
         m = re.search(r"Runtime total: ([0-9.eE+-]+)s", txt)
@@ -201,12 +226,18 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n-seqs", type=int, default=int(os.environ.get("LAMBDA_B200_NSEQS", 5_000_000)))
-    ap.add_argument("--n-queries", type=int, default=int(os.environ.get("LAMBDA_B200_NQUERIES", 100_000)))
-    ap.add_argument("--qlen", type=int, default=300)
+    ap.add_argument("--workload", default="searchp", choices=sorted(WORKLOADS))
+    ap.add_argument("--n-seqs", type=int, default=0, help="database sequences (0 = the workload's BASELINE size)")
+    ap.add_argument("--n-queries", type=int, default=0)
+    ap.add_argument("--qlen", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries for the CPU baseline (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    wl = args.workload
+    W = WORKLOADS[wl]
+    args.n_seqs = args.n_seqs or int(os.environ.get("LAMBDA_B200_NSEQS", W["n_seqs"]))
+    args.n_queries = args.n_queries or int(os.environ.get("LAMBDA_B200_NQUERIES", W["n_queries"]))
+    args.qlen = args.qlen or W["qlen"]
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -214,8 +245,8 @@ def main():
     if world > 1 and args.gpus != world:
         log(f"--gpus {args.gpus} != WORLD_SIZE {world}; using WORLD_SIZE")
     n_gpus = world
-    workload = (f"searchp: {args.n_queries}x{args.qlen}aa synthetic queries vs {args.n_seqs}-seq synthetic protein "
-                f"index (Li10), BLOSUM62, default profile")
+    workload = (f"{wl}: {args.n_queries}x{args.qlen}{W['unit']} synthetic queries vs {args.n_seqs}-seq {W['what']}, "
+                f"default profile")
     cfg = {"workload": workload, "queries_per_gpu": args.n_queries, "query_len": args.qlen, "index_seqs": args.n_seqs,
            "profile": "none", "sharding": f"queries x{n_gpus}, index replicated", "streams_per_gpu": 2,
            "l2_policy": "inputs larger than L2 (index and per-step trace/DP working sets are GBs)"}
@@ -224,19 +255,19 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        d = ensure_index(args.n_seqs)
-        q_ascii, qoffs = make_queries(d, args.n_queries, args.qlen, seed=1000)
+        d = ensure_index(wl, args.n_seqs)
+        q_ascii, qoffs = make_queries(wl, d, args.n_queries, args.qlen, seed=1000)
         n_sample = args.cpu_sample or min(args.n_queries, max(2000, 2000 * cores))
         for _ in range(args.warmup):
-            run_reference_search(d, q_ascii, qoffs, min(n_sample, 200), cores, "warm")
+            run_reference_search(wl, d, q_ascii, qoffs, min(n_sample, 200), cores, "warm")
         qps, walls = [], []
         for _ in range(args.steps):
-            v, wall, phase, _ = run_reference_search(d, q_ascii, qoffs, n_sample, cores, "step")
+            v, wall, phase, _ = run_reference_search(wl, d, q_ascii, qoffs, n_sample, cores, "step")
             qps.append(n_sample / phase)
             walls.append(phase)
         value = n_sample * len(walls) / sum(walls)
-        sample = f"first {n_sample} of the {args.n_queries} queries per step, lambda3 searchp -t {cores}, search phase"
-        emit(({"impl": "reference", "metric": "searchp_query_seqs_per_s", "value": value, "unit": "queries/s",
+        sample = f"first {n_sample} of the {args.n_queries} queries per step, lambda3 {wl} -t {cores}, search phase"
+        emit(({"impl": "reference", "metric": f"{wl}_query_seqs_per_s", "value": value, "unit": "queries/s",
                           "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": 1e3 * sum(walls) / len(walls), "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "int16", "data": "synthetic", "config": cfg,
@@ -253,16 +284,16 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    d = ensure_index(args.n_seqs)
+    d = ensure_index(wl, args.n_seqs)
     if world > 1:
         dist.barrier()
     t0 = time.time()
     ix = lambda_b200.Index.load(os.path.join(d, "db.lba"), device=local_rank, keep_ids=(rank == 0))
     log(f"rank {rank}: index in HBM: {ix.device_bytes / 1e9:.2f} GB, load {time.time() - t0:.1f}s")
-    s = lambda_b200.Searcher(ix, "protein")              # default: 2 sub-batches in flight
-    s_serial = lambda_b200.Searcher(ix, "protein", streams=1)  # strictly serial: per-kernel timing / roofline
-    q_ascii, qoffs = make_queries(d, args.n_queries, args.qlen, seed=1000 + rank)
-    res = lambda_b200.encode(q_ascii, 0)
+    s = lambda_b200.Searcher(ix, W["domain"])              # default: 2 sub-batches in flight
+    s_serial = lambda_b200.Searcher(ix, W["domain"], streams=1)  # strictly serial: per-kernel timing / roofline
+    q_ascii, qoffs = make_queries(wl, d, args.n_queries, args.qlen, seed=1000 + rank)
+    res = lambda_b200.encode(q_ascii, W["dom"])
     h_res = torch.from_numpy(res).pin_memory()
     h_offs = torch.from_numpy(qoffs.view(np.int64)).pin_memory()
     d_res = h_res.cuda()
@@ -364,7 +395,7 @@ def main():
                 "peak": peak_gops, "unit": "Gop/s (int16)", "frac": (achieved / peak_gops) if peak_gops else None,
                 "peak_source": peak_src, "traffic": None, "gcups": gcups_score}
 
-    out = {"metric": "searchp_query_seqs_per_s", "value": value, "unit": "queries/s", "n_gpus": n_gpus,
+    out = {"metric": f"{wl}_query_seqs_per_s", "value": value, "unit": "queries/s", "n_gpus": n_gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "wall_ms_per_step": wall_res / args.steps,
            "ms_per_step_serial_1_stream": ms_serial / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic", "config": cfg,
@@ -385,9 +416,9 @@ def main():
     # CPU baseline: the unmodified reference on this box's host cores, bounded sample of the same queries
     if not args.no_cpu_baseline and n_gpus == 1 and os.path.exists(REF):
         n_sample = args.cpu_sample or min(args.n_queries, max(2000, 2000 * cores))
-        qps, wall, phase, ref_lines = run_reference_search(d, q_ascii, qoffs, n_sample, cores, "cpu")
+        qps, wall, phase, ref_lines = run_reference_search(wl, d, q_ascii, qoffs, n_sample, cores, "cpu")
         out["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "reference",
-                               "sample": f"first {n_sample} of the {args.n_queries} queries, lambda3 searchp -t {cores} "
+                               "sample": f"first {n_sample} of the {args.n_queries} queries, lambda3 {wl} -t {cores} "
                                          f"(SSE4 build), reference's own search-phase timer {phase:.2f}s, wall {wall:.2f}s"}
         # parity on the sample: our tabular lines for the same queries must equal the reference's
         ids = [f"Q{i}" for i in range(args.n_queries)]
