@@ -365,7 +365,8 @@ def main():
 
     nq_total = args.n_queries * n_gpus * args.steps
     value = nq_total / (ms_res * 1e-3)
-    e2e = nq_total / (ms_e2e * 1e-3)
+    # end to end = host wall-clock around the public API call (host buffers in, host records out)
+    e2e = nq_total / (wall_e2e * 1e-3)
     cells_score, cells_trace = float(st["cells_score"]), float(st["cells_trace"])
     if world > 1:
         t = torch.tensor([cells_score, cells_trace], device="cuda", dtype=torch.float64)
@@ -391,9 +392,19 @@ def main():
     ms_trace = float(st["ms_extend_trace"]) / args.steps
     gcups_trace = cells_trace / args.steps / (ms_trace * 1e-3) / 1e9 if ms_trace > 0 else 0.0
     achieved = gcups_score * 10.0  # 10 int16 ops per cell update (5 add + 5 max), SURVEY §8(d)
-    roofline = {"kernel": "swWavefrontKernel<score> (DP pass 1)", "bound": "int16-alu", "achieved": achieved,
+    # DRAM traffic of that kernel from the committed `ncu --set full` capture of this workload (per launch)
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", f"r1_ncu_score_{wl}.json")
+    if os.path.exists(tp):
+        try:
+            t = json.load(open(tp))
+            traffic = {"dram_bytes": t["dram_bytes_read"] + t["dram_bytes_write"], "source": os.path.relpath(tp, ROOT)}
+        except Exception:
+            traffic = None
+    roofline = {"kernel": "swScoreDpxKernel<T,K> (DP pass 1, packed int16 DPX)", "bound": "int16-alu", "achieved": achieved,
                 "peak": peak_gops, "unit": "Gop/s (int16)", "frac": (achieved / peak_gops) if peak_gops else None,
-                "peak_source": peak_src, "traffic": None, "gcups": gcups_score}
+                "peak_source": peak_src, "traffic": traffic, "gcups": gcups_score,
+                "algorithmic": "10 int16 ops per DP cell x cells of the step / DP pass-1 stage time (CUDA events)"}
 
     out = {"metric": f"{wl}_query_seqs_per_s", "value": value, "unit": "queries/s", "n_gpus": n_gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "wall_ms_per_step": wall_res / args.steps,
@@ -409,8 +420,8 @@ def main():
            "hits_per_step_all_ranks": total_hits,
            "clocks": clocks, "roofline": roofline,
            "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": int(res.nbytes + qoffs.nbytes),
-                   "d2h_bytes_per_step": int(len(hits) * HIT_DT.itemsize), "ms_per_step": ms_e2e / args.steps,
-                   "wall_ms_per_step": wall_e2e / args.steps},
+                   "d2h_bytes_per_step": int(len(hits) * HIT_DT.itemsize), "ms_per_step": wall_e2e / args.steps,
+                   "device_ms_per_step": ms_e2e / args.steps, "timing": "host wall-clock around Searcher.search()"},
            "gpu_launches": int(st["kernel_launches"])}
 
     # CPU baseline: the unmodified reference on this box's host cores, bounded sample of the same queries

@@ -147,6 +147,11 @@ typedef struct
     uint32_t         finalize;          /* 1: apply writeRecords/_writeRecord (sort, unique,
                                            top max_matches) before returning hits; 0: return the
                                            raw lH.blastMatches multiset                          */
+    uint32_t         query_alph;        /* alphabet of the query batch: 0 = the domain's default
+                                           (amino acids for searchp, dna5 otherwise);
+                                           LGPU_ALPH_DNA5 with a protein index = translated query
+                                           (BLASTX / TBLASTX, --query-alphabet dna5);
+                                           LGPU_ALPH_AMINO_ACID = protein query (BLASTP / TBLASTN) */
 } lgpu_params;
 
 int lgpu_params_default(lgpu_params * out, uint32_t domain, char const * profile);
@@ -167,7 +172,8 @@ int          lgpu_ctx_set_streams(lgpu_ctx *, uint32_t n);
 char const * lgpu_last_error(lgpu_ctx const *); /* ctx may be NULL: error of the last failed
                                                    create/open call on this thread */
 
-/* Query batch: original-alphabet ranks (aa27 ranks for searchp, dna5 ranks for searchn), all
+/* Query batch: original-alphabet ranks (aa27 ranks for protein queries, dna5 ranks for nucleotide
+ * queries -- searchn, searchbs and translated searchp), all
  * sequences concatenated, offsets[n_queries + 1].  Pointers are HOST memory unless
  * `on_device` != 0 (then they are device pointers on the context's device and the H2D copy is
  * skipped -- used to time the resident-input path). */

@@ -193,20 +193,28 @@ class Searcher:
         return QueryBatch(residues.ctypes.data, offsets.ctypes.data, len(offsets) - 1, 0), (residues, offsets)
 
     # -- full path -----------------------------------------------------------------------------
-    def search(self, residues, offsets):
-        """residues: original-alphabet ranks (see encode()), offsets: uint64[n+1] -> (hits, stats)"""
+    def search(self, residues, offsets, copy=True):
+        """residues: original-alphabet ranks (see encode()), offsets: uint64[n+1] -> (hits, stats).
+        copy=False returns a view of the context's own host buffer, valid until the next call."""
         lib = load_library()
         qb, keep = self._batch(residues, offsets)
         out = Hits()
         st = np.zeros(1, STATS_DT)
         _check(lib.lgpu_search_batch(self._h, C.byref(qb), C.byref(out), _p(st)), self._h)
-        hits = (np.frombuffer(C.string_at(out.hits, out.n * HIT_DT.itemsize), HIT_DT).copy() if out.n
-                else np.zeros(0, HIT_DT))
-        return hits, st[0]
+        if not out.n:
+            return np.zeros(0, HIT_DT), st[0]
+        raw = (C.c_char * (out.n * HIT_DT.itemsize)).from_address(out.hits)
+        hits = np.frombuffer(raw, HIT_DT)
+        return (hits.copy() if copy else hits), st[0]
+
+    @property
+    def query_is_protein(self):
+        """protein queries (aa27 ranks) unless the domain or `query_alph` says nucleotides (dna5 ranks)"""
+        return self.params.domain == 0 and self.params.query_alph != 3
 
     def search_fasta(self, path):
         ids, data, offs = read_fasta(path)
-        hits, st = self.search(encode(data, self.params.domain), offs)
+        hits, st = self.search(encode(data, 0 if self.query_is_protein else 1), offs)
         return ids, hits, st
 
     def m8(self, hits, query_ids):

@@ -168,7 +168,7 @@ struct lgpu_index
     std::vector<void *>      allocs;
     uint64_t                 bytes         = 0;
     uint64_t                 dbTotalLength = 0;
-    std::vector<uint64_t>    seqDelimsHost; // kept on the host for subject lengths
+    std::vector<uint64_t>    sbjDelimsHost; // host copy of dev.seqDelims (window checks of the stage API)
     ~lgpu_index()
     {
         cudaSetDevice(device);
@@ -264,14 +264,15 @@ struct StageTimer
 
 static void checkParams(lgpu_params const & p, lgpu_index_desc const & d)
 {
-    if (p.domain == LGPU_DOMAIN_BISULFITE)
-        throw UnsupportedError("bisulfite search (searchbs) is not implemented yet");
+    // same checks and messages as argConv0 (src/search.cpp:190-207)
     if (p.domain == LGPU_DOMAIN_PROTEIN)
     {
         if (d.trans_alph != LGPU_ALPH_AMINO_ACID)
             throw ArgError("Attempting to use nucleotide or bisulfite index for protein search.");
-        if (d.orig_alph != LGPU_ALPH_AMINO_ACID)
-            throw UnsupportedError("translated subjects (TBLASTN/TBLASTX) are not implemented yet");
+        if (d.orig_alph != LGPU_ALPH_AMINO_ACID && d.orig_alph != LGPU_ALPH_DNA5)
+            throw ArgError("unknown original alphabet in index");
+        if (p.query_alph != 0 && p.query_alph != LGPU_ALPH_AMINO_ACID && p.query_alph != LGPU_ALPH_DNA5)
+            throw ArgError("query alphabet must be amino acid or dna5");
     }
     else if (p.domain == LGPU_DOMAIN_NUCLEOTIDE)
     {
@@ -279,6 +280,17 @@ static void checkParams(lgpu_params const & p, lgpu_index_desc const & d)
             throw ArgError("Attempting to use protein index for nucleotide search.");
         if (d.red_alph != LGPU_ALPH_DNA4)
             throw ArgError("Attempting to use bisulfite index for nucleotide search.");
+        if (p.query_alph != 0 && p.query_alph != LGPU_ALPH_DNA5)
+            throw ArgError("nucleotide searches take dna5 queries");
+    }
+    else if (p.domain == LGPU_DOMAIN_BISULFITE)
+    {
+        if (d.trans_alph != LGPU_ALPH_DNA5)
+            throw ArgError("Attempting to use protein index for bisulfite search.");
+        if (d.red_alph != LGPU_ALPH_DNA3BS)
+            throw ArgError("Attempting to use nucleotid index for bisulfite search.");
+        if (p.query_alph != 0 && p.query_alph != LGPU_ALPH_DNA5)
+            throw ArgError("bisulfite searches take dna5 queries");
     }
     else
         throw ArgError("unknown domain");
@@ -334,26 +346,38 @@ static void uploadQueries(lgpu_ctx & c, BatchView const & qb, lgpu_stats * st)
     Q.red          = c.dQRed.p;
     Q.n            = static_cast<unsigned int>(qb.n);
     Q.F            = F;
+    Q.frameMode    = c.di.qFrameMode;
     std::memset(Q.redTab, 0, sizeof(Q.redTab));
     std::memset(Q.compTab, 0, sizeof(Q.compTab));
     switch (ix.meta.red_alph)
     {
-        case LGPU_ALPH_LI10: std::memcpy(Q.redTab, kAa27ToLi10, 27); break;
-        case LGPU_ALPH_MURPHY10: std::memcpy(Q.redTab, kAa27ToMurphy10, 27); break;
+        case LGPU_ALPH_LI10: std::memcpy(Q.redTab[0], kAa27ToLi10, 27); break;
+        case LGPU_ALPH_MURPHY10: std::memcpy(Q.redTab[0], kAa27ToMurphy10, 27); break;
         case LGPU_ALPH_AMINO_ACID:
             for (int i = 0; i < 27; ++i)
-                Q.redTab[i] = static_cast<unsigned char>(i);
+                Q.redTab[0][i] = static_cast<unsigned char>(i);
             break;
         case LGPU_ALPH_DNA4:
         {
             // dna5 (A,C,G,N,T) -> dna4 (A,C,G,T).  The reference replaces N by a pseudo-random base whose
             // value depends on its internal access pattern; we map N to A.
             unsigned char const t[5] = {0, 1, 2, 0, 3};
-            std::memcpy(Q.redTab, t, 5);
+            std::memcpy(Q.redTab[0], t, 5);
+            break;
+        }
+        case LGPU_ALPH_DNA3BS:
+        {
+            // dna5 -> dna4 (N -> A, as above) -> bisulfite semialphabet: forward (C->T) ranks {A0,C1,G2,T1} for
+            // even frames, reverse (G->A) ranks {A3,C4,G3,T5} for odd frames (src/view_reduce_to_bisulfite.hpp:51-52)
+            unsigned char const fwd[5] = {0, 1, 2, 0, 1}, rev[5] = {3, 4, 3, 3, 5};
+            std::memcpy(Q.redTab[0], fwd, 5);
+            std::memcpy(Q.redTab[1], rev, 5);
             break;
         }
         default: throw UnsupportedError("unsupported reduced alphabet");
     }
+    if (ix.meta.red_alph != LGPU_ALPH_DNA3BS)
+        std::memcpy(Q.redTab[1], Q.redTab[0], 32);
     std::memcpy(Q.compTab, kDna5Complement, 5);
     prepQueriesKernel<<<std::min<unsigned int>(Q.n, 65535u * 8u), 128, 0, c.stream>>>(Q);
     LGPU_CUDA(cudaGetLastError());
@@ -460,7 +484,7 @@ static uint64_t runMerge(lgpu_ctx & c, lgpu_match const * dIn, uint64_t n, lgpu_
     c.dHead.reserve(n);
     c.dScan.reserve(n);
     unsigned int const g = gridFor(n, 256);
-    widenKernel<<<g, 256, 0, c.stream>>>(dIn, n, c.Q, c.index->dev, c.di.sbjNumFrames, c.dKey1.p, c.dKey2.p);
+    widenKernel<<<g, 256, 0, c.stream>>>(dIn, n, c.Q, c.index->dev, c.dKey1.p, c.dKey2.p);
     iotaKernel<<<g, 256, 0, c.stream>>>(c.dPerm.p, n);
     // LSD: stable sort by the minor key (window start/end), then by the major key (qry, subj)
     size_t tmp1 = 0, tmp2 = 0, tmp3 = 0;
@@ -547,7 +571,6 @@ static ExtParams baseExtParams(lgpu_ctx & c, lgpu_match const * dTasks, unsigned
     P.Q           = c.Q;
     P.tasks       = dTasks;
     P.nTasks      = n;
-    P.sbjFrames   = c.di.sbjNumFrames;
     P.matrix      = c.dMatrix.p;
     P.go          = c.scoring.gapOpenSeqan;
     P.ge          = c.scoring.gapExtend;
@@ -609,7 +632,7 @@ static void runScorePass(lgpu_ctx & c, lgpu_match const * dTasks, unsigned int n
     LGPU_CUDA(cudaMemsetAsync(c.dWork.p, 0, (NC + 1) * 4, c.stream));
     unsigned int const g = gridFor(n, 256);
     int const          nI = static_cast<int>(n);
-    classifyKernel<<<g, 256, 0, c.stream>>>(dTasks, n, c.dClassKeys.p, c.dOrder.p, c.dClassInfo.p, c.dClassInfo.p + NC,
+    classifyKernel<<<g, 256, 0, c.stream>>>(dTasks, n, c.index->dev.bsMode, c.dClassKeys.p, c.dOrder.p, c.dClassInfo.p, c.dClassInfo.p + NC,
                                             c.dClassInfo.p + 3 * NC, c.dCounters.p);
     size_t t1 = 0, t2 = 0, t3 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, t1, c.dClassKeys.p, c.dClassKeysB.p, c.dOrder.p, c.dOrderB.p, nI, 0, 64, c.stream);
@@ -651,7 +674,6 @@ static void runScorePass(lgpu_ctx & c, lgpu_match const * dTasks, unsigned int n
             P.nSorted     = n;
             P.jobs        = c.dJobs.p + jobOff;
             P.nJobs       = nJobs;
-            P.sbjFrames   = c.di.sbjNumFrames;
             P.matrix      = c.dMatrix.p;
             P.go          = c.scoring.gapOpenSeqan;
             P.ge          = c.scoring.gapExtend;
@@ -746,8 +768,6 @@ static void runTraceScalar(lgpu_ctx & c, lgpu_match const * tasks, size_t n, lgp
         TP.Q            = c.Q;
         TP.tasks        = dTasks + begin;
         TP.nTasks       = cnt;
-        TP.sbjFrames    = c.di.sbjNumFrames;
-        TP.domain       = c.params.domain;
         TP.matrix       = c.dMatrix.p;
         TP.scores       = c.dScores2.p;
         TP.bestPos      = c.dBestPos.p;
@@ -847,7 +867,6 @@ static void runTracePass(lgpu_ctx & c, lgpu_match const * tasks, size_t n, lgpu_
             P.tasks       = dTasks;
             P.order       = c.dOrder.p;
             P.nTasks      = cnt;
-            P.sbjFrames   = c.di.sbjNumFrames;
             P.matrix      = c.dMatrix.p;
             P.go          = c.scoring.gapOpenSeqan;
             P.ge          = c.scoring.gapExtend;
@@ -878,8 +897,6 @@ static void runTracePass(lgpu_ctx & c, lgpu_match const * tasks, size_t n, lgpu_
             TP.tasks     = dTasks;
             TP.order     = c.dOrder.p;
             TP.nTasks    = cnt;
-            TP.sbjFrames = c.di.sbjNumFrames;
-            TP.domain    = c.params.domain;
             TP.matrix    = c.dMatrix.p;
             TP.go        = c.scoring.gapOpenSeqan;
             TP.ge        = c.scoring.gapExtend;
@@ -1249,7 +1266,7 @@ static std::unique_ptr<lgpu_ctx> lgpu::makeContext(lgpu_index const * ix, lgpu_p
     auto c    = std::make_unique<lgpu_ctx>();
     c->index  = ix;
     c->params = p;
-    c->di     = domainInfo(p.domain);
+    c->di     = domainInfo(p.domain, ix->meta.orig_alph, p.query_alph);
     int rc    = makeScoring(c->scoring, p);
     if (rc == LGPU_ERR_ARG)
         throw ArgError("Could not compute Karlin-Altschul-Values for Scoring Scheme.");
@@ -1260,8 +1277,9 @@ static std::unique_ptr<lgpu_ctx> lgpu::makeContext(lgpu_index const * ix, lgpu_p
     for (auto & e : c->ev)
         LGPU_CUDA(cudaEventCreate(&e));
     LGPU_CUDA(cudaDeviceGetAttribute(&c->numSMs, cudaDevAttrMultiProcessorCount, ix->device));
-    c->dMatrix.reserve(1024);
+    c->dMatrix.reserve(2048);
     LGPU_CUDA(cudaMemcpy(c->dMatrix.p, c->scoring.matrix, 1024, cudaMemcpyHostToDevice));
+    LGPU_CUDA(cudaMemcpy(c->dMatrix.p + 1024, c->scoring.matrixRev, 1024, cudaMemcpyHostToDevice));
     c->dCounters.reserve(8);
     if (char const * e = std::getenv("LAMBDA_B200_SEED"))
         c->seedMode = !std::strcmp(e, "thread") ? 1 : !std::strcmp(e, "warp") ? 2 : !std::strcmp(e, "block") ? 3 : 0;
@@ -1273,7 +1291,8 @@ static std::unique_ptr<lgpu_ctx> lgpu::makeContext(lgpu_index const * ix, lgpu_p
         for (int b = 0; b < c->scoring.alphSize; ++b)
         {
             int const v = c->scoring.matrix[a * 32 + b] - c->scoring.gapOpenSeqan;
-            if (v < -127 || v > 127)
+            int const w = c->scoring.matrixRev[a * 32 + b] - c->scoring.gapOpenSeqan;
+            if (v < -127 || v > 127 || w < -127 || w > 127)
                 c->dpxOk = false;
         }
     return c;
@@ -1329,7 +1348,40 @@ int lgpu_index_create(lgpu_index ** out, lgpu_index_desc const * d, int device)
         dv.csa         = static_cast<CsaSuperDev const *>(up(d->csa_bv, d->n_csa_sb * 48));
         dv.seqs        = static_cast<unsigned char const *>(up(d->seqs, d->n_residues));
         dv.seqDelims   = static_cast<unsigned long long const *>(up(d->seq_delims, (d->n_seqs + 1) * 8));
+        dv.origDelims  = dv.seqDelims;
+        dv.sbjShift    = d->red_alph == LGPU_ALPH_DNA3BS ? 1 : 0;
+        dv.bsMode      = d->red_alph == LGPU_ALPH_DNA3BS ? 1 : 0;
+        dv.sbjFrames   = d->red_alph == LGPU_ALPH_DNA3BS ? 2 : 1;
         dv.nSeqs       = d->n_seqs;
+        LGPU_CUDA(cudaMemcpyToSymbol(cDna5Translate, kDna5Translate, 125));
+        // dbTotalLength = sum of reduced subject lengths (src/search_algo.hpp:317-318)
+        ix->dbTotalLength = d->n_residues * (d->red_alph == LGPU_ALPH_DNA3BS ? 2 : 1);
+        ix->sbjDelimsHost.assign(d->seq_delims, d->seq_delims + d->n_seqs + 1);
+        if (d->trans_alph == LGPU_ALPH_AMINO_ACID && d->orig_alph == LGPU_ALPH_DNA5)
+        {
+            // translated subjects (TBLASTN / TBLASTX): transSbjSeqs = seqs | translate_join
+            // (src/shared_definitions.hpp:246-255); made once here, 2 bytes per stored nucleotide
+            std::vector<uint64_t> & td = ix->sbjDelimsHost;
+            td.assign(d->n_seqs * 6 + 1, 0);
+            for (uint64_t sq = 0; sq < d->n_seqs; ++sq)
+                for (uint32_t f = 0; f < 6; ++f)
+                    td[sq * 6 + f + 1] = td[sq * 6 + f] + translatedFrameLength(d->seq_delims[sq + 1] - d->seq_delims[sq], f);
+            uint64_t const tTotal = td.back();
+            unsigned long long * dTd = static_cast<unsigned long long *>(up(td.data(), td.size() * 8));
+            unsigned char *      dT  = nullptr;
+            LGPU_CUDA(cudaMalloc(&dT, std::max<uint64_t>(tTotal, 1)));
+            ix->allocs.push_back(dT);
+            ix->bytes += tTotal;
+            unsigned char * dComp = static_cast<unsigned char *>(up(kDna5Complement, 5));
+            uint64_t const  nFr   = d->n_seqs * 6;
+            translateSubjectsKernel<<<static_cast<unsigned int>(std::min<uint64_t>(std::max<uint64_t>(nFr, 1), 1u << 20)), 128>>>(
+              dv.seqs, dv.origDelims, d->n_seqs, dComp, dTd, dT);
+            LGPU_CUDA(cudaGetLastError());
+            dv.seqs           = dT;
+            dv.seqDelims      = dTd;
+            dv.sbjFrames      = 6;
+            ix->dbTotalLength = tTotal;
+        }
         dv.nRows       = d->C[d->sigma];
         dv.bitsForPos  = static_cast<unsigned int>(d->bits_for_position);
         dv.posMask     = (1ull << d->bits_for_position) - 1;
@@ -1352,9 +1404,6 @@ int lgpu_index_create(lgpu_index ** out, lgpu_index_desc const * d, int device)
         ix->meta.seq_delims   = nullptr;
         ix->meta.ids          = nullptr;
         ix->meta.id_delims    = nullptr;
-        ix->seqDelimsHost.assign(d->seq_delims, d->seq_delims + d->n_seqs + 1);
-        // dbTotalLength = sum of reduced subject lengths (src/search_algo.hpp:317-318)
-        ix->dbTotalLength = d->n_residues * (d->red_alph == LGPU_ALPH_DNA3BS ? 2 : 1);
         LGPU_CUDA(cudaDeviceSynchronize());
         *out = ix.release();
     });
@@ -1469,9 +1518,11 @@ static void checkWindows(lgpu_ctx & c, lgpu_match const * w, uint64_t n)
         uint64_t const q = w[i].qry_id / c.di.qryNumFrames;
         if (q >= c.nQueries || w[i].subj_id / c.di.sbjNumFrames >= c.index->meta.n_seqs)
             throw ArgError("window refers to a query/subject that does not exist");
-        uint64_t const qLen = c.qOffsHost[q + 1] - c.qOffsHost[q];
-        uint64_t const sId  = w[i].subj_id / c.di.sbjNumFrames;
-        uint64_t const sLen = c.index->seqDelimsHost[sId + 1] - c.index->seqDelimsHost[sId];
+        uint64_t       qLen = c.qOffsHost[q + 1] - c.qOffsHost[q];
+        if (c.di.qIsTranslated)
+            qLen = translatedFrameLength(qLen, w[i].qry_id % 6);
+        uint64_t const sIdx = w[i].subj_id >> c.index->dev.sbjShift;
+        uint64_t const sLen = c.index->sbjDelimsHost[sIdx + 1] - c.index->sbjDelimsHost[sIdx];
         if (w[i].qry_start > w[i].qry_end || w[i].qry_end > qLen || w[i].subj_start > w[i].subj_end ||
             w[i].subj_end > sLen)
             throw ArgError("window coordinates out of range");
@@ -1582,7 +1633,7 @@ int lgpu_evalue(lgpu_params const * p, int32_t raw, uint64_t qLen, uint64_t dbLe
     KarlinAltschul const ka = selectKA(*p);
     if (!ka.valid)
         return LGPU_ERR_ARG;
-    EValueComputer ev(ka, dbLen, domainInfo(p->domain).qIsTranslated);
+    EValueComputer ev(ka, dbLen, domainInfo(p->domain, 0, p->query_alph).qIsTranslated);
     *out = ev.evalue(raw, qLen);
     return LGPU_OK;
 }
@@ -1594,7 +1645,7 @@ int lgpu_min_raw_score(lgpu_params const * p, uint64_t qLen, uint64_t dbLen, int
     KarlinAltschul const ka = selectKA(*p);
     if (!ka.valid)
         return LGPU_ERR_ARG;
-    EValueComputer        ev(ka, dbLen, domainInfo(p->domain).qIsTranslated);
+    EValueComputer        ev(ka, dbLen, domainInfo(p->domain, 0, p->query_alph).qIsTranslated);
     ScoreThresholds const t = scoreThresholds(*p, ev, qLen);
     *out                    = std::max(t.minBit, t.minEval);
     return LGPU_OK;

@@ -109,19 +109,35 @@ inline size_t idPrefixLen(char const * id, size_t len)
 inline int formatM8(uint32_t domain, lgpu_hit const & h, char const * qId, size_t qIdLen, char const * sId,
                     size_t sIdLen, char * buf, size_t cap)
 {
-    // reverse-strand query coordinates are flipped, starts are 1-based (blast_base.h:337-372)
+    // _untranslateQPositions / _untranslateSPositions (SQ/blast/blast_base.h:337-420): codon positions of
+    // translated frames back to nucleotides, reverse-strand coordinates flipped, starts 1-based.  Which
+    // program ran is visible from the hit: only translated queries / subjects of a protein search carry
+    // a non-zero frame, nucleotide and bisulfite queries have a strand (and BLASTN subjects none).
     uint64_t qs = h.q_start, qe = h.q_end, ss = h.s_start, se = h.s_end;
-    bool const qHasRevComp = domain != LGPU_DOMAIN_PROTEIN;
-    if (qHasRevComp && h.q_frame < 0)
-    {
-        qs = h.q_len - qs;
-        qe = h.q_len - qe + 1;
-    }
+    auto const untranslate = [](uint64_t & b, uint64_t & e, int frame, uint64_t len, bool hasFrames) {
+        if (hasFrames)
+        {
+            uint64_t const shift = static_cast<uint64_t>(frame < 0 ? -frame : frame) - 1;
+            b                    = b * 3 + shift;
+            e                    = e * 3 + shift;
+        }
+        if (frame > 0)
+            ++b;
+        else
+        {
+            b = len - b;
+            e = len - e + 1;
+        }
+    };
+    bool const qHasRevComp = domain != LGPU_DOMAIN_PROTEIN || h.q_frame != 0;
+    if (qHasRevComp)
+        untranslate(qs, qe, h.q_frame, h.q_len, domain == LGPU_DOMAIN_PROTEIN);
     else
-    {
         ++qs;
-    }
-    ++ss; // BLASTN / BLASTP subjects have neither frames nor reverse complement
+    if (domain == LGPU_DOMAIN_PROTEIN && h.s_frame != 0)
+        untranslate(ss, se, h.s_frame, h.s_len, true);
+    else
+        ++ss; // BLASTN / BLASTP / BLASTX subjects have neither frames nor reverse complement
     float const identity = static_cast<float>(100.0 * static_cast<float>(h.n_match) / static_cast<float>(h.aln_len));
     char        ev[64], bs[64];
     std::snprintf(ev, sizeof(ev), evalueFormat(h.evalue), h.evalue);

@@ -11,6 +11,7 @@
 // only ever sees integer score thresholds derived from these functions.
 #pragma once
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -141,7 +142,8 @@ struct KarlinAltschul
 struct Scoring
 {
     int            alphSize = 0;      // 27 or 5
-    int8_t         matrix[32 * 32]{}; // [a * 32 + b]
+    int8_t         matrix[32 * 32]{}; // [query residue * 32 + subject residue]
+    int8_t         matrixRev[32 * 32]{}; // bisulfite: matrix for reverse-converted (odd) subjects; else = matrix
     int            gapOpenSeqan = 0;  // cost of the first gap character = gapOpen + gapExtend
     int            gapExtend    = 0;
     KarlinAltschul ka;
@@ -209,10 +211,29 @@ inline int makeScoring(Scoring & s, lgpu_params const & p)
             for (int b = 0; b < 5; ++b)
                 s.matrix[a * 32 + b] = static_cast<int8_t>(a == b ? p.match : p.mismatch);
     }
+    else if (p.domain == LGPU_DOMAIN_BISULFITE)
+    {
+        // setScoreBisulfiteMatrix (src/bisulfite_scoring.hpp:67-93) is written over SeqAn's Dna5 order
+        // (A,C,G,T,N); our ranks are BioC++ dna5 (A,C,G,N,T; src/seqan2_to_biocpp.hpp:360-364).
+        // forward: a read T over a reference C is a match; reverse: a read A over a reference G; N never matches
+        s.alphSize              = 5;
+        int const toSeqan[5]    = {0, 1, 2, 4, 3};
+        for (int a = 0; a < 5; ++a)
+            for (int b = 0; b < 5; ++b)
+            {
+                int const i = toSeqan[a], j = toSeqan[b];
+                bool const fwd = ((i == j) || (i == 3 && j == 1)) && i != 4;
+                bool const rev = ((i == j) || (i == 0 && j == 2)) && i != 4;
+                s.matrix[a * 32 + b]    = static_cast<int8_t>(fwd ? p.match : p.mismatch);
+                s.matrixRev[a * 32 + b] = static_cast<int8_t>(rev ? p.match : p.mismatch);
+            }
+    }
     else
     {
-        return LGPU_ERR_UNSUPPORTED;
+        return LGPU_ERR_ARG;
     }
+    if (p.domain != LGPU_DOMAIN_BISULFITE)
+        std::memcpy(s.matrixRev, s.matrix, sizeof(s.matrix));
     s.gapOpenSeqan = p.gap_open + p.gap_extend; // src/search_algo.hpp:226
     s.gapExtend    = p.gap_extend;
     s.ka           = selectKA(p);
@@ -376,24 +397,44 @@ inline ScoreThresholds scoreThresholds(lgpu_params const & p, EValueComputer & e
 // domain-derived constants
 // ---------------------------------------------------------------------------------------------
 
+// Which BLAST program a (domain, index, query alphabet) combination is, and what follows from it
+// (GlobalDataHolder::blastProgram / qryNumFrames / sbjNumFrames, src/search_datastructures.hpp:326-385).
 struct DomainInfo
 {
-    uint32_t qryNumFrames = 1;
-    uint32_t sbjNumFrames = 1;
-    bool     qIsTranslated = false;
-    uint8_t  unknownRank   = 23; // 'X' in aa27, 'N' (3) in dna5  (src/search_algo.hpp:652-656)
+    uint32_t qryNumFrames  = 1;
+    uint32_t sbjNumFrames  = 1;
+    bool     qIsTranslated = false; // BLASTX / TBLASTX
+    bool     sIsTranslated = false; // TBLASTN / TBLASTX
+    uint8_t  unknownRank   = 23;    // 'X' in aa27, 'N' (3) in dna5  (src/search_algo.hpp:652-656)
+    uint32_t qFrameMode    = 0;     // DevQueries::frameMode
 };
 
-inline DomainInfo domainInfo(uint32_t domain)
+// `sbjOrigAlph` = alphabet of the sequences stored in the index (LGPU_ALPH_*), `qryAlph` = alphabet of the
+// query batch (0 = the domain's default: amino acids for protein searches, dna5 otherwise)
+inline DomainInfo domainInfo(uint32_t domain, uint32_t sbjOrigAlph = 0, uint32_t qryAlph = 0)
 {
     DomainInfo d;
     switch (domain)
     {
-        case LGPU_DOMAIN_PROTEIN: d = {1, 1, false, 23}; break;
-        case LGPU_DOMAIN_NUCLEOTIDE: d = {2, 1, false, 3}; break;
-        case LGPU_DOMAIN_BISULFITE: d = {4, 2, false, 3}; break;
+        case LGPU_DOMAIN_PROTEIN:
+            d.qIsTranslated = qryAlph == LGPU_ALPH_DNA5;
+            d.sIsTranslated = sbjOrigAlph == LGPU_ALPH_DNA5;
+            d.qryNumFrames  = d.qIsTranslated ? 6 : 1;
+            d.sbjNumFrames  = d.sIsTranslated ? 6 : 1;
+            d.unknownRank   = 23;
+            d.qFrameMode    = d.qIsTranslated ? 2 : 0;
+            break;
+        case LGPU_DOMAIN_NUCLEOTIDE: d = {2, 1, false, false, 3, 1}; break;
+        case LGPU_DOMAIN_BISULFITE: d = {4, 2, false, false, 3, 3}; break;
     }
     return d;
+}
+
+// translated-frame length (BIO ranges/views/translate_single.hpp:95-113)
+inline uint64_t translatedFrameLength(uint64_t len, uint32_t frame)
+{
+    uint64_t const o = frame % 3;
+    return (std::max(len, o) - o) / 3;
 }
 
 } // namespace lgpu

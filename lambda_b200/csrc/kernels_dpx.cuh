@@ -45,8 +45,7 @@ struct DpxParams
     unsigned int               nSorted; // entries in order / keys
     unsigned int const *       jobs;    // first sorted slot of every job of this class
     unsigned int               nJobs;
-    unsigned int               sbjFrames;
-    signed char const *  matrix; // 32 x 32
+    signed char const *  matrix; // 2 x (32 x 32)
     int                  go, ge;
     unsigned int         nCodes; // alphabet size + 1 (last row = null)
     unsigned int         winCap; // bytes reserved per group for the padded window
@@ -68,7 +67,10 @@ __host__ __device__ constexpr int dpxRowWords(int T, int K)
     return (((K + 3) / 4) * 2 * T + 31) / 32 * 32 + ((T == 32) ? 0 : 8);
 }
 
-constexpr unsigned int kDpxSegShift = 20; // sort key = class << 60 | qryId << 20 | min(nt, 2^20 - 1)
+// sort key = class << 60 | (qryId << 1 | matrix selector) << 20 | min(nt, 2^20 - 1); the selector is the
+// subject parity in bisulfite mode (reverse matrix for odd subjects), else 0: all alignments of a job
+// share one profile
+constexpr unsigned int kDpxSegShift = 20;
 
 // A job = up to G = 32/T consecutive (sorted) alignments of the SAME query: the warp builds the query
 // profile once in shared memory and its G groups run one alignment each against it.
@@ -124,13 +126,14 @@ __global__ void __launch_bounds__(32) swScoreDpxKernel(DpxParams P)
         unsigned int const       qLen = static_cast<unsigned int>(P.Q.offs[q + 1] - qb);
         unsigned char const *    qs   = P.Q.trans + P.Q.F * qb + static_cast<unsigned long long>(f) * qLen + m0.qry_start;
         unsigned int const       nq   = m0.qry_end - m0.qry_start;
+        signed char const *      M    = P.matrix + matrixOffset(P.ix, m0.subj_id);
         unsigned int             task = 0, nt = 0;
         unsigned char const *    ts   = nullptr;
         if (valid)
         {
             task               = P.order[slot];
             lgpu_match const m = P.tasks[task];
-            ts                 = P.ix.seqs + P.ix.seqDelims[m.subj_id / P.sbjFrames] + m.subj_start;
+            ts                 = P.ix.seqs + sbjBase(P.ix, m.subj_id) + m.subj_start;
             nt                 = m.subj_end - m.subj_start;
         }
         // the warp runs for its longest window; extra steps are null rows for the shorter ones
@@ -159,7 +162,7 @@ __global__ void __launch_bounds__(32) swScoreDpxKernel(DpxParams P)
                     unsigned int const i = v * K + r;
                     int                val = -128;
                     if (r < K && i < nq)
-                        val = static_cast<int>(P.matrix[c * 32 + qs[i]]) - P.go;
+                        val = static_cast<int>(M[qs[i] * 32 + c]) - P.go;
                     word |= (static_cast<unsigned int>(val) & 0xffu) << (8 * b);
                 }
             }
@@ -289,8 +292,8 @@ __host__ __device__ inline unsigned int dpxGroupsOf(int cls)
     return cls <= 6 ? 4u : (cls <= 8 ? 2u : 1u);
 }
 
-// key = class << 60 | qryId << 20 | min(nt, 2^20-1) ; also per-class counts / max window / total cells
-__global__ void classifyKernel(lgpu_match const * tasks, unsigned int n, unsigned long long * keys, unsigned int * idx,
+// key (see kDpxSegShift); also per-class counts / max window / total cells
+__global__ void classifyKernel(lgpu_match const * tasks, unsigned int n, unsigned int bsMode, unsigned long long * keys, unsigned int * idx,
                                unsigned int * classCount, unsigned int * classMaxNt, unsigned int * maxNq,
                                unsigned long long * cells)
 {
@@ -305,7 +308,8 @@ __global__ void classifyKernel(lgpu_match const * tasks, unsigned int n, unsigne
         c  = dpxClassOf(nq);
         if (nt > kDpxMaxWindow)
             c = kNumDpxClasses;
-        keys[t] = (static_cast<unsigned long long>(c) << 60) | (static_cast<unsigned long long>(tasks[t].qry_id) << kDpxSegShift) |
+        unsigned long long const seg = (static_cast<unsigned long long>(tasks[t].qry_id) << 1) | (tasks[t].subj_id & bsMode);
+        keys[t] = (static_cast<unsigned long long>(c) << 60) | (seg << kDpxSegShift) |
                   (nt < (1u << kDpxSegShift) ? nt : (1u << kDpxSegShift) - 1u);
         idx[t]  = t;
         myCells = static_cast<unsigned long long>(nq) * nt;

@@ -43,8 +43,7 @@ struct DpxTraceParams
     lgpu_match const *         tasks;
     unsigned int const *       order;    // tasks of this class (indices into `tasks`)
     unsigned int               nTasks;   // entries in `order`
-    unsigned int               sbjFrames;
-    signed char const *        matrix;   // 32 x 32
+    signed char const *        matrix;   // 2 x (32 x 32)
     int                        go, ge;
     unsigned int               nCodes;   // alphabet size + 1 (last row = null)
     unsigned int               winCap;   // bytes reserved for the padded window
@@ -102,7 +101,8 @@ __global__ void __launch_bounds__(32) swTraceDpxKernel(DpxTraceParams P)
         unsigned int const       qLen = static_cast<unsigned int>(P.Q.offs[q + 1] - qb);
         unsigned char const *    qs   = P.Q.trans + P.Q.F * qb + static_cast<unsigned long long>(f) * qLen + m.qry_start;
         unsigned int const       nq   = m.qry_end - m.qry_start;
-        unsigned char const *    ts   = P.ix.seqs + P.ix.seqDelims[m.subj_id / P.sbjFrames] + m.subj_start;
+        unsigned char const *    ts   = P.ix.seqs + sbjBase(P.ix, m.subj_id) + m.subj_start;
+        signed char const *      M    = P.matrix + matrixOffset(P.ix, m.subj_id);
         unsigned int const       nt   = m.subj_end - m.subj_start;
         unsigned int const       nSteps = nt + 2 * T - 1;
         unsigned int *           planeH = P.planes + P.planeOff[task];
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(32) swTraceDpxKernel(DpxTraceParams P)
                     unsigned int const i = v * K + r;
                     int                val = -128;
                     if (r < K && i < nq)
-                        val = static_cast<int>(P.matrix[c * 32 + qs[i]]) - P.go;
+                        val = static_cast<int>(M[qs[i] * 32 + c]) - P.go;
                     word |= (static_cast<unsigned int>(val) & 0xffu) << (8 * b);
                 }
             }
@@ -269,9 +269,7 @@ struct TracebackDpxParams
     lgpu_match const *         tasks;
     unsigned int const *       order;
     unsigned int               nTasks;
-    unsigned int               sbjFrames;
-    unsigned int               domain;
-    signed char const *        matrix;
+    signed char const *        matrix; // 2 x (32 x 32)
     int                        go, ge;
     unsigned int               K;
     int const *                scores;
@@ -293,9 +291,9 @@ __global__ void __launch_bounds__(128) tracebackDpxKernel(TracebackDpxParams P)
     unsigned long long const qb   = P.Q.offs[q];
     unsigned int const       qLen = static_cast<unsigned int>(P.Q.offs[q + 1] - qb);
     unsigned char const *    qs   = P.Q.trans + P.Q.F * qb + static_cast<unsigned long long>(f) * qLen + m.qry_start;
-    unsigned int const       sId  = m.subj_id / P.sbjFrames;
-    unsigned long long const sb   = P.ix.seqDelims[sId];
-    unsigned char const *    ts   = P.ix.seqs + sb + m.subj_start;
+    unsigned int const       sId  = m.subj_id / P.ix.sbjFrames;
+    unsigned char const *    ts   = P.ix.seqs + sbjBase(P.ix, m.subj_id) + m.subj_start;
+    signed char const *      M    = P.matrix + matrixOffset(P.ix, m.subj_id);
     unsigned int const       nt   = m.subj_end - m.subj_start;
     unsigned int const       K    = P.K, KN = (K + 1) / 2;
     unsigned int const       nSteps = nt + 63;
@@ -336,7 +334,7 @@ __global__ void __launch_bounds__(128) tracebackDpxKernel(TracebackDpxParams P)
         {
             tv |= (dE <= dF ? T_MAXV : 0u) | (dF <= dE ? T_MAXH : 0u);
             int const hd = (ii > 1 && jj > 1) ? cellH(ii - 1, jj - 1) : 0;
-            if (hd + static_cast<int>(P.matrix[qs[ii - 1] * 32 + ts[jj - 1]]) == H)
+            if (hd + static_cast<int>(M[qs[ii - 1] * 32 + ts[jj - 1]]) == H)
                 tv |= T_DIAG;
         }
         return tv;
@@ -387,8 +385,8 @@ __global__ void __launch_bounds__(128) tracebackDpxKernel(TracebackDpxParams P)
             {
                 switchTo(0);
                 unsigned int const a = qs[i - 1], b = ts[j - 1];
-                if (a == b) ++nMatch; else ++nMismatch;
-                if (P.matrix[a * 32 + b] > 0) ++nPositive;
+                if (alignedIdentical(P.ix, M, a, b)) ++nMatch; else ++nMismatch;
+                if (M[a * 32 + b] > 0) ++nPositive;
                 --i; --j; tv = tr(i, j); ++run;
             }
             else if ((tv & T_MAXV) && (tv & T_VERT))
@@ -433,7 +431,7 @@ __global__ void __launch_bounds__(128) tracebackDpxKernel(TracebackDpxParams P)
     h.s_start    = m.subj_start + j;
     h.s_end      = m.subj_start + bj;
     h.q_len      = qLen;
-    h.s_len      = static_cast<unsigned int>(P.ix.seqDelims[sId + 1] - sb);
+    h.s_len      = static_cast<unsigned int>(P.ix.origDelims[sId + 1] - P.ix.origDelims[sId]);
     h.score      = score;
     h.n_match    = nMatch;
     h.n_mismatch = nMismatch;
@@ -441,8 +439,7 @@ __global__ void __launch_bounds__(128) tracebackDpxKernel(TracebackDpxParams P)
     h.n_gap_ext  = nGapExt;
     h.n_positive = nPositive;
     h.aln_len    = alnLen;
-    h.q_frame    = (P.domain == LGPU_DOMAIN_NUCLEOTIDE) ? ((m.qry_id & 1u) ? -1 : 1) : 0;
-    h.s_frame    = 0;
+    setFrames(P.Q, P.ix, m.qry_id, m.subj_id, h.q_frame, h.s_frame);
     h.phase      = 0;
     h.reserved   = 0;
     h.bit_score  = 0.0;

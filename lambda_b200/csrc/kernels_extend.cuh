@@ -47,7 +47,7 @@ __device__ __forceinline__ unsigned int isqrtFloor(unsigned int x)
 
 // key1 = (qryId << 32) | subjId ; key2 = (subjStart << 32) | subjEnd   (qryStart/qryEnd are constant
 // per qryId after widening, so the reference's 6-field lexicographic order reduces to these two keys)
-__global__ void widenKernel(lgpu_match const * in, unsigned long long n, DevQueries Q, DevIndex ix, unsigned int sbjFrames,
+__global__ void widenKernel(lgpu_match const * in, unsigned long long n, DevQueries Q, DevIndex ix,
                             unsigned long long * key1, unsigned long long * key2)
 {
     unsigned long long const t = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
@@ -55,9 +55,9 @@ __global__ void widenKernel(lgpu_match const * in, unsigned long long n, DevQuer
         return;
     lgpu_match const         m    = in[t];
     unsigned int const       q    = m.qry_id / Q.F;
-    unsigned long long const qLen = Q.offs[q + 1] - Q.offs[q];
-    unsigned long long const sId  = m.subj_id / sbjFrames;
-    unsigned long long const sLen = ix.seqDelims[sId + 1] - ix.seqDelims[sId];
+    // lengths in translated space (src/search_algo.hpp:925-926)
+    unsigned long long const qLen = qryFrameLen(Q, static_cast<unsigned int>(Q.offs[q + 1] - Q.offs[q]), m.qry_id % Q.F);
+    unsigned long long const sLen = sbjLength(ix, m.subj_id);
     unsigned long long const s0   = (m.subj_start < m.qry_start) ? 0ull : static_cast<unsigned long long>(m.subj_start) - m.qry_start;
     unsigned long long const band = static_cast<unsigned long long>(isqrtFloor(static_cast<unsigned int>(qLen))) + 1ull;
     unsigned long long       e    = s0 + qLen + band;
@@ -120,7 +120,7 @@ __global__ void chainEmitKernel(unsigned long long const * key1, unsigned long l
         out[c].qry_id            = qryId;
         out[c].subj_id           = static_cast<unsigned int>(key1[t]);
         out[c].qry_start         = 0;
-        out[c].qry_end           = static_cast<unsigned int>(Q.offs[q + 1] - Q.offs[q]);
+        out[c].qry_end           = qryFrameLen(Q, static_cast<unsigned int>(Q.offs[q + 1] - Q.offs[q]), qryId % Q.F);
         out[c].subj_start        = static_cast<unsigned int>(key2[t] >> 32);
     }
     if (t + 1 == n || head[t + 1])
@@ -149,8 +149,7 @@ struct ExtParams
     lgpu_match const *    tasks;
     unsigned int const *  order;        // optional indirection: work item t is task order[t]
     unsigned int          nTasks;       // number of work items
-    unsigned int          sbjFrames;
-    signed char const *   matrix; // 32 x 32
+    signed char const *   matrix; // 2 x (32 x 32)
     int                   go, ge;
     unsigned int *        workCounter;  // dynamic task scheduler
     int *                 scores;       // out: best score per task
@@ -162,6 +161,13 @@ struct ExtParams
 };
 
 constexpr int kNegInf = -16384; // INT16_MIN / 2, SQ/align/dp_cell.h:144-146
+
+// "identical" column of computeAlignmentStats: equal residues (SQ/align/evaluate_alignment.h:270-277);
+// bisulfite: score(q, s) == score(q, q) under the direction's matrix (src/evaluate_bisulfite_alignment.hpp:97)
+__device__ __forceinline__ bool alignedIdentical(DevIndex const & ix, signed char const * M, unsigned int a, unsigned int b)
+{
+    return ix.bsMode ? (M[a * 32 + b] == M[a * 32 + a]) : (a == b);
+}
 
 __device__ __forceinline__ unsigned int packSH(int s, int h)
 {
@@ -179,9 +185,9 @@ __device__ __forceinline__ int unpackHi(unsigned int v)
 template <int K, bool TRACE>
 __global__ void __launch_bounds__(128) swWavefrontKernel(ExtParams P)
 {
-    __shared__ signed char sM[1024];
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x)
-        sM[i] = P.matrix[i];
+    __shared__ signed char sMM[2048];
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x)
+        sMM[i] = P.matrix[i];
     __syncthreads();
 
     unsigned int const lane   = threadIdx.x & 31u;
@@ -209,8 +215,9 @@ __global__ void __launch_bounds__(128) swWavefrontKernel(ExtParams P)
         unsigned int const       qLen = static_cast<unsigned int>(P.Q.offs[q + 1] - qb);
         unsigned char const *    qs   = P.Q.trans + P.Q.F * qb + static_cast<unsigned long long>(f) * qLen + m.qry_start;
         unsigned int const       nq   = m.qry_end - m.qry_start;
-        unsigned char const *    ts   = P.ix.seqs + P.ix.seqDelims[m.subj_id / P.sbjFrames] + m.subj_start;
+        unsigned char const *    ts   = P.ix.seqs + sbjBase(P.ix, m.subj_id) + m.subj_start;
         unsigned int const       nt   = m.subj_end - m.subj_start;
+        signed char const *      sM   = sMM + matrixOffset(P.ix, m.subj_id);
 
         // trace storage: every lane owns KS = roundup4(K) bytes per row and column block (word stores)
         constexpr unsigned int   KS     = (K + 3) / 4 * 4;
@@ -350,9 +357,7 @@ struct TracebackParams
     DevQueries                 Q;
     lgpu_match const *         tasks;
     unsigned int               nTasks;
-    unsigned int               sbjFrames;
-    unsigned int               domain;
-    signed char const *        matrix;
+    signed char const *        matrix; // 2 x (32 x 32)
     int const *                scores;
     unsigned int const *       bestPos;
     unsigned char const *      trace;
@@ -373,9 +378,9 @@ __global__ void __launch_bounds__(128) tracebackKernel(TracebackParams P)
     unsigned int const       qLen = static_cast<unsigned int>(P.Q.offs[q + 1] - qb);
     unsigned char const *    qs   = P.Q.trans + P.Q.F * qb + static_cast<unsigned long long>(f) * qLen + m.qry_start;
     unsigned int const       nq   = m.qry_end - m.qry_start;
-    unsigned int const       sId  = m.subj_id / P.sbjFrames;
-    unsigned long long const sb   = P.ix.seqDelims[sId];
-    unsigned char const *    ts   = P.ix.seqs + sb + m.subj_start;
+    unsigned int const       sId  = m.subj_id / P.ix.sbjFrames;
+    unsigned char const *    ts   = P.ix.seqs + sbjBase(P.ix, m.subj_id) + m.subj_start;
+    signed char const *      M    = P.matrix + matrixOffset(P.ix, m.subj_id);
     unsigned int const       KS     = (P.K + 3) / 4 * 4;
     unsigned int const       stride = (nq + 32 * P.K - 1) / (32 * P.K) * (32 * KS);
     unsigned char const *    T      = P.trace + P.traceOff[task];
@@ -422,8 +427,8 @@ __global__ void __launch_bounds__(128) tracebackKernel(TracebackParams P)
             {
                 switchTo(0);
                 unsigned int const a = qs[i - 1], b = ts[j - 1];
-                if (a == b) ++nMatch; else ++nMismatch;
-                if (P.matrix[a * 32 + b] > 0) ++nPositive;
+                if (alignedIdentical(P.ix, M, a, b)) ++nMatch; else ++nMismatch;
+                if (M[a * 32 + b] > 0) ++nPositive;
                 --i; --j; tv = tr(i, j); ++run;
             }
             else if ((tv & T_MAXV) && (tv & T_VERT))
@@ -468,7 +473,7 @@ __global__ void __launch_bounds__(128) tracebackKernel(TracebackParams P)
     h.s_start    = m.subj_start + j;
     h.s_end      = m.subj_start + bj;
     h.q_len      = qLen;
-    h.s_len      = static_cast<unsigned int>(P.ix.seqDelims[sId + 1] - sb);
+    h.s_len      = static_cast<unsigned int>(P.ix.origDelims[sId + 1] - P.ix.origDelims[sId]);
     h.score      = P.scores[task];
     h.n_match    = nMatch;
     h.n_mismatch = nMismatch;
@@ -476,8 +481,7 @@ __global__ void __launch_bounds__(128) tracebackKernel(TracebackParams P)
     h.n_gap_ext  = nGapExt;
     h.n_positive = nPositive;
     h.aln_len    = alnLen;
-    h.q_frame    = (P.domain == LGPU_DOMAIN_NUCLEOTIDE) ? ((m.qry_id & 1u) ? -1 : 1) : 0;
-    h.s_frame    = 0;
+    setFrames(P.Q, P.ix, m.qry_id, m.subj_id, h.q_frame, h.s_frame);
     h.phase      = 0;
     h.reserved   = 0;
     h.bit_score  = 0.0;

@@ -39,8 +39,17 @@ struct DevIndex
     unsigned long long const * super;
     unsigned long long const * ssa;
     CsaSuperDev const *        csa;
+    // Subject sequences the alignments run on (the reference's transSbjSeqs), translated-alphabet
+    // ranks, 1 B/residue: the stored sequences themselves, or -- for TBLASTN/TBLASTX -- their six-frame
+    // translations made once at index creation.  Frame-expanded subject id s lives at
+    // seqs[seqDelims[s >> sbjShift] ...): bisulfite subjects 2k and 2k+1 are the same sequence
+    // (views::duplicate, src/view_duplicate.hpp:50-53), translated frames have their own entries.
     unsigned char const *      seqs;
     unsigned long long const * seqDelims;
+    unsigned long long const * origDelims; // delimiters of the original (untranslated) sequences
+    unsigned int               sbjShift;   // 1: bisulfite, else 0
+    unsigned int               sbjFrames;  // sbjNumFrames: 1, 2 (bisulfite) or 6 (translated subjects)
+    unsigned int               bsMode;     // 1: odd subjects are scored with the reverse bisulfite matrix
     unsigned long long         nSeqs;
     unsigned long long         nRows;      // C[sigma] = length of the BWT
     unsigned long long         posMask;
@@ -54,6 +63,26 @@ __device__ __forceinline__ unsigned long long ldg64(void const * p)
 {
     return __ldg(reinterpret_cast<unsigned long long const *>(p));
 }
+
+// start of frame-expanded subject `subjId` inside ix.seqs, and its length
+__device__ __forceinline__ unsigned long long sbjBase(DevIndex const & ix, unsigned int subjId)
+{
+    return __ldg(ix.seqDelims + (subjId >> ix.sbjShift));
+}
+__device__ __forceinline__ unsigned long long sbjLength(DevIndex const & ix, unsigned int subjId)
+{
+    unsigned int const k = subjId >> ix.sbjShift;
+    return __ldg(ix.seqDelims + k + 1) - __ldg(ix.seqDelims + k);
+}
+// byte offset of the scoring matrix for this subject inside the 2 x (32 x 32) matrix block
+// (bisulfite: scoringSchemeAlignBSRev for odd subjects, src/search_algo.hpp:464-466,1098)
+__device__ __forceinline__ unsigned int matrixOffset(DevIndex const & ix, unsigned int subjId)
+{
+    return (subjId & ix.bsMode) << 10;
+}
+
+// canonical genetic code over dna5 ranks (uploaded from kDna5Translate at index creation)
+__constant__ unsigned char cDna5Translate[125];
 
 __device__ __forceinline__ unsigned long long fmSymbolMask(DevIndex const & ix, unsigned char const * b, unsigned int symb)
 {
@@ -168,7 +197,13 @@ __global__ void fmLocateKernel(DevIndex ix, unsigned long long const * rows, uns
 // query preparation: frames (reverse complement) and alphabet reduction
 // ---------------------------------------------------------------------------------------------
 
-// Frame-expanded layout: frame f of query q starts at F * offs[q] + f * len(q).
+// Frame-expanded layout: frame f of query q starts at F * offs[q] + f * len(q) (len = original length;
+// translated frames are shorter and leave the rest of their slot unused).
+//   frameMode 0  one frame (protein query)
+//             1  forward, reverse complement                      (bio::views::add_reverse_complement)
+//             2  six-frame translation                            (bio::views::translate_join)
+//             3  bisulfite: fwd, fwd, rc, rc; even frames reduced C->T, odd frames G->A
+//                (src/shared_definitions.hpp:257-281, src/view_reduce_to_bisulfite.hpp:51-52,133-135)
 struct DevQueries
 {
     unsigned char const *      orig;  // original ranks
@@ -176,9 +211,50 @@ struct DevQueries
     unsigned char *            trans; // F * total
     unsigned char *            red;   // F * total
     unsigned int               n, F;
-    unsigned char              redTab[32];
+    unsigned int               frameMode;
+    unsigned char              redTab[2][32]; // [frame & 1] (the two differ in bisulfite mode only)
     unsigned char              compTab[8];
 };
+
+// length of frame f of a query with `len` original residues (BIO ranges/views/translate_single.hpp:95-113)
+__device__ __forceinline__ unsigned int qryFrameLen(DevQueries const & Q, unsigned int len, unsigned int f)
+{
+    if (Q.frameMode != 2)
+        return len;
+    unsigned int const o = f % 3;
+    return (max(len, o) - o) / 3;
+}
+
+// _setFrames (src/search_algo.hpp:769-814)
+__device__ __forceinline__ void setFrames(DevQueries const & Q, DevIndex const & ix, unsigned int qryId, unsigned int subjId,
+                                          signed char & qFrame, signed char & sFrame)
+{
+    int qf = 0, sf = 0;
+    if (Q.frameMode == 2)
+    {
+        qf = static_cast<int>(qryId % 3) + 1;
+        if (qryId % 6 > 2)
+            qf = -qf;
+    }
+    else if (Q.frameMode == 3)
+    {
+        qf = static_cast<int>(qryId % 2) + 1;
+        if (qryId % 4 > 1)
+            qf = -qf;
+    }
+    else if (Q.frameMode == 1)
+        qf = (qryId % 2) ? -1 : 1;
+    if (ix.sbjFrames == 6)
+    {
+        sf = static_cast<int>(subjId % 3) + 1;
+        if (subjId % 6 > 2)
+            sf = -sf;
+    }
+    else if (ix.bsMode)
+        sf = static_cast<int>(subjId % 2) + 1;
+    qFrame = static_cast<signed char>(qf);
+    sFrame = static_cast<signed char>(sf);
+}
 
 __global__ void prepQueriesKernel(DevQueries Q)
 {
@@ -189,14 +265,67 @@ __global__ void prepQueriesKernel(DevQueries Q)
         unsigned int const       len = static_cast<unsigned int>(Q.offs[q + 1] - b);
         for (unsigned int f = 0; f < Q.F; ++f)
         {
-            unsigned long long const o = Q.F * b + static_cast<unsigned long long>(f) * len;
-            for (unsigned int k = threadIdx.x; k < len; k += blockDim.x)
+            unsigned long long const o    = Q.F * b + static_cast<unsigned long long>(f) * len;
+            unsigned int const       fLen = qryFrameLen(Q, len, f);
+            bool const               rc   = Q.frameMode == 1 ? (f & 1u) : Q.frameMode == 2 ? (f >= 3) : Q.frameMode == 3 ? (f >= 2) : false;
+            for (unsigned int k = threadIdx.x; k < fLen; k += blockDim.x)
             {
-                // frame 0 = forward, frame 1 = reverse complement (bio::views::add_reverse_complement)
-                unsigned char const r = (f & 1u) ? Q.compTab[Q.orig[b + len - 1 - k]] : Q.orig[b + k];
-                Q.trans[o + k]        = r;
-                Q.red[o + k]          = Q.redTab[r];
+                unsigned char r;
+                if (Q.frameMode == 2)
+                {
+                    unsigned int const p = 3 * k + f % 3;
+                    unsigned int       n1, n2, n3;
+                    if (!rc)
+                    {
+                        n1 = Q.orig[b + p];
+                        n2 = Q.orig[b + p + 1];
+                        n3 = Q.orig[b + p + 2];
+                    }
+                    else
+                    {
+                        n1 = Q.compTab[Q.orig[b + len - p - 1]];
+                        n2 = Q.compTab[Q.orig[b + len - p - 2]];
+                        n3 = Q.compTab[Q.orig[b + len - p - 3]];
+                    }
+                    r = cDna5Translate[(n1 * 5 + n2) * 5 + n3];
+                }
+                else
+                    r = rc ? Q.compTab[Q.orig[b + len - 1 - k]] : Q.orig[b + k];
+                Q.trans[o + k] = r;
+                Q.red[o + k]   = Q.redTab[f & 1u][r];
             }
+        }
+    }
+}
+
+// six-frame translation of the stored subjects (TBLASTN / TBLASTX), once per index: frame-expanded
+// subject 6 * s + f -> out[outDelims[6 * s + f] ...)
+__global__ void translateSubjectsKernel(unsigned char const * seqs, unsigned long long const * delims, unsigned long long nSeqs,
+                                        unsigned char const * compTab5, unsigned long long const * outDelims, unsigned char * out)
+{
+    for (unsigned long long sf = blockIdx.x; sf < nSeqs * 6; sf += gridDim.x)
+    {
+        unsigned long long const s = sf / 6;
+        unsigned int const       f = static_cast<unsigned int>(sf % 6);
+        unsigned long long const b = delims[s], len = delims[s + 1] - b;
+        unsigned long long const o = outDelims[sf], fLen = outDelims[sf + 1] - o;
+        for (unsigned long long k = threadIdx.x; k < fLen; k += blockDim.x)
+        {
+            unsigned long long const p = 3 * k + f % 3;
+            unsigned int             n1, n2, n3;
+            if (f < 3)
+            {
+                n1 = seqs[b + p];
+                n2 = seqs[b + p + 1];
+                n3 = seqs[b + p + 2];
+            }
+            else
+            {
+                n1 = compTab5[seqs[b + len - p - 1]];
+                n2 = compTab5[seqs[b + len - p - 2]];
+                n3 = compTab5[seqs[b + len - p - 3]];
+            }
+            out[o + k] = cDna5Translate[(n1 * 5 + n2) * 5 + n3];
         }
     }
 }
@@ -216,7 +345,7 @@ struct SeedParams
     int                  preScoring;
     double               preScoringThresh;
     unsigned int         unknownRank;
-    signed char const *  matrix; // 32 x 32 int8, translated-alphabet ranks
+    signed char const *  matrix; // 2 x (32 x 32) int8, translated-alphabet ranks (second: bisulfite reverse)
     lgpu_match *         out;
     unsigned long long   cap;
     unsigned long long * counters; // [0] matches emitted, [1] hitsAfterSeeding, [2] hitsFailedPreExtendTest
@@ -226,8 +355,8 @@ constexpr int kMaxHalf2 = 16; // longest supported second seed half (seed length
 
 __global__ void __launch_bounds__(128) seedKernel(SeedParams P)
 {
-    __shared__ signed char sM[1024];
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x)
+    __shared__ signed char sM[2048];
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x)
         sM[i] = P.matrix[i];
     __syncthreads();
 
@@ -238,25 +367,30 @@ __global__ void __launch_bounds__(128) seedKernel(SeedParams P)
     DevIndex const &         ix   = P.ix;
     unsigned int const       F    = P.Q.F;
     unsigned long long const qb   = P.Q.offs[q];
-    unsigned int const       len  = static_cast<unsigned int>(P.Q.offs[q + 1] - qb);
     unsigned int const       L    = P.seedLength;
     unsigned int const       redN = ix.sigma - 1;
 
     unsigned long long nAfter = 0, nFailed = 0;
-    if (len >= L) // all frames of a query have the same length in the supported (non-translated) modes
+    unsigned int const origLen = static_cast<unsigned int>(P.Q.offs[q + 1] - qb);
+    if (qryFrameLen(P.Q, origLen, 0) >= L) // frame 0 is the longest frame
     {
-        unsigned long long       hitsThisSeq = 0;
-        unsigned long long const needlesSum  = static_cast<unsigned long long>(F) * len;
-        unsigned long long       needlesPos  = 0;
-        bool const               half        = P.halfExact && P.maxSeedDist != 0;
-        unsigned int const       h1          = half ? L / 2 : L;
-        unsigned int const       n2          = L - h1;
+        unsigned long long hitsThisSeq = 0;
+        unsigned long long needlesSum  = 0;
+        for (unsigned int f = 0; f < F; ++f)
+            needlesSum += qryFrameLen(P.Q, origLen, f);
+        unsigned long long needlesPos = 0;
+        bool const         half       = P.halfExact && P.maxSeedDist != 0;
+        unsigned int const h1         = half ? L / 2 : L;
+        unsigned int const n2         = L - h1;
 
         for (unsigned int f = 0; f < F; ++f)
         {
+            unsigned int const len = qryFrameLen(P.Q, origLen, f);
+            if (len < L)
+                continue; // too short a frame is skipped without advancing needlesPos (search_algo.hpp:637)
             unsigned int const    qryId = q * F + f;
-            unsigned char const * trans = P.Q.trans + F * qb + static_cast<unsigned long long>(f) * len;
-            unsigned char const * red   = P.Q.red + F * qb + static_cast<unsigned long long>(f) * len;
+            unsigned char const * trans = P.Q.trans + F * qb + static_cast<unsigned long long>(f) * origLen;
+            unsigned char const * red   = P.Q.red + F * qb + static_cast<unsigned long long>(f) * origLen;
 
             for (unsigned int seedBegin = 0;; seedBegin += P.seedOffset)
             {
@@ -408,8 +542,9 @@ __global__ void __launch_bounds__(128) seedKernel(SeedParams P)
                         unsigned long long       eff    = static_cast<unsigned long long>(L * P.preScoring);
                         if (eff < actual)
                             eff = actual;
-                        unsigned long long const sBase = __ldg(ix.seqDelims + subj);
-                        unsigned long long const sLen  = __ldg(ix.seqDelims + subj + 1) - sBase;
+                        unsigned long long const sBase = sbjBase(ix, static_cast<unsigned int>(subj));
+                        unsigned long long const sLen  = sbjLength(ix, static_cast<unsigned int>(subj));
+                        signed char const *      M     = sM + matrixOffset(ix, static_cast<unsigned int>(subj));
                         if (eff > actual)
                         {
                             qB -= static_cast<long long>((eff - actual) / 2);
@@ -435,7 +570,7 @@ __global__ void __launch_bounds__(128) seedKernel(SeedParams P)
                         bool                  pass = false;
                         for (unsigned long long i = 0; i < eff; ++i)
                         {
-                            s += sM[qs[i] * 32 + __ldg(ss + i)];
+                            s += M[qs[i] * 32 + __ldg(ss + i)];
                             if (s < 0)
                                 s = 0;
                             else if (s > mx)
@@ -618,8 +753,9 @@ __device__ __forceinline__ void seedConsumeCursor(SeedParams const & P, signed c
             unsigned long long       eff    = static_cast<unsigned long long>(L * P.preScoring);
             if (eff < actual)
                 eff = actual;
-            unsigned long long const sBase = __ldg(ix.seqDelims + subj);
-            unsigned long long const sLen  = __ldg(ix.seqDelims + subj + 1) - sBase;
+            unsigned long long const sBase = sbjBase(ix, static_cast<unsigned int>(subj));
+            unsigned long long const sLen  = sbjLength(ix, static_cast<unsigned int>(subj));
+            signed char const *      M     = sM + matrixOffset(ix, static_cast<unsigned int>(subj));
             if (eff > actual)
             {
                 qB -= static_cast<long long>((eff - actual) / 2);
@@ -644,7 +780,7 @@ __device__ __forceinline__ void seedConsumeCursor(SeedParams const & P, signed c
             int                   sc = 0, mx = 0;
             for (unsigned long long i = 0; i < eff; ++i)
             {
-                sc += sM[qs[i] * 32 + __ldg(ss + i)];
+                sc += M[qs[i] * 32 + __ldg(ss + i)];
                 if (sc < 0)
                     sc = 0;
                 else if (sc > mx)
@@ -724,8 +860,8 @@ __device__ __forceinline__ bool seedNextStart(unsigned char const * trans, unsig
 // Only the exact chain, the adaptive elongation and the running `hitsThisSeq` stay serial.
 __global__ void __launch_bounds__(128) seedWarpKernel(SeedParams P)
 {
-    __shared__ signed char sM[1024];
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x)
+    __shared__ signed char sM[2048];
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x)
         sM[i] = P.matrix[i];
     __syncthreads();
 
@@ -736,26 +872,31 @@ __global__ void __launch_bounds__(128) seedWarpKernel(SeedParams P)
     unsigned int const       q    = P.active[w];
     DevIndex const &         ix   = P.ix;
     unsigned int const       F    = P.Q.F;
-    unsigned long long const qb   = P.Q.offs[q];
-    unsigned int const       len  = static_cast<unsigned int>(P.Q.offs[q + 1] - qb);
-    unsigned int const       L    = P.seedLength;
-    unsigned int const       redN = ix.sigma - 1;
+    unsigned long long const qb      = P.Q.offs[q];
+    unsigned int const       origLen = static_cast<unsigned int>(P.Q.offs[q + 1] - qb);
+    unsigned int const       L       = P.seedLength;
+    unsigned int const       redN    = ix.sigma - 1;
 
     unsigned long long nAfter = 0, nFailed = 0; // per lane
-    if (len >= L)
+    if (qryFrameLen(P.Q, origLen, 0) >= L)
     {
-        unsigned long long       hitsThisSeq = 0;
-        unsigned long long const needlesSum  = static_cast<unsigned long long>(F) * len;
-        bool const               half        = P.halfExact && P.maxSeedDist != 0;
-        unsigned int const       h1          = half ? L / 2 : L;
-        unsigned int const       n2          = L - h1;
+        unsigned long long hitsThisSeq = 0;
+        unsigned long long needlesSum  = 0;
+        for (unsigned int f = 0; f < F; ++f)
+            needlesSum += qryFrameLen(P.Q, origLen, f);
+        unsigned long long needlesPos = 0;
+        bool const         half       = P.halfExact && P.maxSeedDist != 0;
+        unsigned int const h1         = half ? L / 2 : L;
+        unsigned int const n2         = L - h1;
 
         for (unsigned int f = 0; f < F; ++f)
         {
+            unsigned int const len = qryFrameLen(P.Q, origLen, f);
+            if (len < L)
+                continue;
             unsigned int const    qryId = q * F + f;
-            unsigned char const * trans = P.Q.trans + F * qb + static_cast<unsigned long long>(f) * len;
-            unsigned char const * red   = P.Q.red + F * qb + static_cast<unsigned long long>(f) * len;
-            unsigned long long const needlesPos = static_cast<unsigned long long>(f) * len;
+            unsigned char const * trans = P.Q.trans + F * qb + static_cast<unsigned long long>(f) * origLen;
+            unsigned char const * red   = P.Q.red + F * qb + static_cast<unsigned long long>(f) * origLen;
 
             for (unsigned int seedBegin = 0;; seedBegin += P.seedOffset)
             {
@@ -789,6 +930,7 @@ __global__ void __launch_bounds__(128) seedWarpKernel(SeedParams P)
                     }
                 }
             }
+            needlesPos += len;
         }
     }
     seedFlushCounters(P, lane, nAfter, nFailed);
@@ -815,10 +957,11 @@ struct SeedScratch
 
 __global__ void __launch_bounds__(32 * kSeedBlockWarps) seedBlockKernel(SeedParams P, SeedScratch S)
 {
-    __shared__ signed char  sM[1024];
+    __shared__ signed char  sM[2048];
     __shared__ unsigned int sSeed[kSeedBlockMaxSeeds]; // frame << 24 | seedBegin
     __shared__ unsigned int sNumSeeds;
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x)
+    __shared__ unsigned long long sNeedlesPos[8], sNeedlesSum;
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x)
         sM[i] = P.matrix[i];
 
     unsigned int const lane = threadIdx.x & 31u;
@@ -827,21 +970,30 @@ __global__ void __launch_bounds__(32 * kSeedBlockWarps) seedBlockKernel(SeedPara
     unsigned int const       q    = P.active[b];
     DevIndex const &         ix   = P.ix;
     unsigned int const       F    = P.Q.F;
-    unsigned long long const qb   = P.Q.offs[q];
-    unsigned int const       len  = static_cast<unsigned int>(P.Q.offs[q + 1] - qb);
-    unsigned int const       L    = P.seedLength;
-    unsigned int const       redN = ix.sigma - 1;
-    bool const               half = P.halfExact && P.maxSeedDist != 0;
-    unsigned int const       h1   = half ? L / 2 : L;
-    unsigned int const       n2   = L - h1;
+    unsigned long long const qb      = P.Q.offs[q];
+    unsigned int const       origLen = static_cast<unsigned int>(P.Q.offs[q + 1] - qb);
+    unsigned int const       L       = P.seedLength;
+    unsigned int const       redN    = ix.sigma - 1;
+    bool const               half    = P.halfExact && P.maxSeedDist != 0;
+    unsigned int const       h1      = half ? L / 2 : L;
+    unsigned int const       n2      = L - h1;
 
     if (threadIdx.x == 0)
     {
-        unsigned int n = 0;
-        if (len >= L)
+        unsigned int       n   = 0;
+        unsigned long long pos = 0, sum = 0;
+        for (unsigned int f = 0; f < F; ++f)
+            sum += qryFrameLen(P.Q, origLen, f);
+        sNeedlesSum = sum;
+        if (qryFrameLen(P.Q, origLen, 0) >= L)
             for (unsigned int f = 0; f < F; ++f)
             {
-                unsigned char const * trans = P.Q.trans + F * qb + static_cast<unsigned long long>(f) * len;
+                unsigned int const len = qryFrameLen(P.Q, origLen, f);
+                sNeedlesPos[f]         = pos;
+                if (len < L)
+                    continue;
+                pos += len;
+                unsigned char const * trans = P.Q.trans + F * qb + static_cast<unsigned long long>(f) * origLen;
                 for (unsigned int seedBegin = 0;; seedBegin += P.seedOffset)
                 {
                     if (!seedNextStart(trans, len, L, P.unknownRank, seedBegin))
@@ -863,7 +1015,7 @@ __global__ void __launch_bounds__(32 * kSeedBlockWarps) seedBlockKernel(SeedPara
     {
         unsigned int const    f         = sSeed[k] >> 24;
         unsigned int const    seedBegin = sSeed[k] & 0xffffffu;
-        unsigned char const * red       = P.Q.red + F * qb + static_cast<unsigned long long>(f) * len;
+        unsigned char const * red       = P.Q.red + F * qb + static_cast<unsigned long long>(f) * origLen;
         Cursor                E[kMaxHalf2 + 1];
         int const             K   = seedExactChain(ix, red, seedBegin, h1, n2, E);
         unsigned int          out = 0;
@@ -895,19 +1047,20 @@ __global__ void __launch_bounds__(32 * kSeedBlockWarps) seedBlockKernel(SeedPara
         return;
     unsigned long long nAfter = 0, nFailed = 0;
     unsigned long long hitsThisSeq = 0;
-    unsigned long long const needlesSum = static_cast<unsigned long long>(F) * len;
+    unsigned long long const needlesSum = sNeedlesSum;
     for (unsigned int k = 0; k < nSeeds; ++k)
     {
         unsigned int const    f         = sSeed[k] >> 24;
         unsigned int const    seedBegin = sSeed[k] & 0xffffffu;
-        unsigned char const * trans     = P.Q.trans + F * qb + static_cast<unsigned long long>(f) * len;
-        unsigned char const * red       = P.Q.red + F * qb + static_cast<unsigned long long>(f) * len;
+        unsigned int const    len       = qryFrameLen(P.Q, origLen, f);
+        unsigned char const * trans     = P.Q.trans + F * qb + static_cast<unsigned long long>(f) * origLen;
+        unsigned char const * red       = P.Q.red + F * qb + static_cast<unsigned long long>(f) * origLen;
         unsigned int const    n         = myCnt[k];
         for (unsigned int ci = 0; ci < n; ++ci)
         {
             Cursor const cursor = myCur[static_cast<unsigned long long>(k) * S.maxLeaves + ci];
             seedConsumeCursor(P, sM, lane, q * F + f, trans, red, len, seedBegin, cursor, hitsThisSeq, needlesSum,
-                              static_cast<unsigned long long>(f) * len, nAfter, nFailed);
+                              sNeedlesPos[f], nAfter, nFailed);
         }
     }
     seedFlushCounters(P, lane, nAfter, nFailed);

@@ -1,4 +1,4 @@
-// lambda3_b200 -- host program with the lambda3 searchp / searchn command line.
+// lambda3_b200 -- host program with the lambda3 searchp / searchn / searchbs command line.
 //
 // Replaces the loop body of the reference's realMain() (src/search.cpp:345-477) by calls through the C
 // ABI (include/lambda_b200.h): load the reference's own .lba index, read the query FASTA, hand large
@@ -28,7 +28,7 @@ namespace
 struct Options
 {
     uint32_t    domain = LGPU_DOMAIN_PROTEIN;
-    std::string query, index, output = "output.m8", profile = "none";
+    std::string query, index, output = "output.m8", profile = "none", inputAlphabet = "auto";
     int         verbosity = 1;
     int         threads   = 1; // only used for the reference's records_per_batch formula
     int         gpus      = 1;
@@ -50,7 +50,8 @@ bool endsWith(std::string const & s, char const * suf)
 
 void usage()
 {
-    std::puts("lambda3_b200 searchp|searchn -q QUERY.fasta -i INDEX.lba [-o output.m8] [OPTIONS]\n"
+    std::puts("lambda3_b200 searchp|searchn|searchbs -q QUERY.fasta -i INDEX.lba [-o output.m8] [OPTIONS]\n"
+              "  -a, --input-alphabet   auto|dna5|aminoacid (searchp; dna queries are translated: BLASTX/TBLASTX)\n"
               "  -p, --profile          none|fast|sensitive|pairs-default|pairs-sensitive\n"
               "  -e, --e-value          maximum e-value (default 0.01; -1 = off)\n"
               "      --bit-score        minimum bit score (default -1 = off)\n"
@@ -81,7 +82,7 @@ void parse(int argc, char ** argv, Options & o)
     else if (cmd == "searchn")
         o.domain = LGPU_DOMAIN_NUCLEOTIDE;
     else if (cmd == "searchbs")
-        die("searchbs is not implemented by the GPU path yet; use the reference binary");
+        o.domain = LGPU_DOMAIN_BISULFITE;
     else if (cmd == "-h" || cmd == "--help")
     {
         usage();
@@ -109,6 +110,7 @@ void parse(int argc, char ** argv, Options & o)
         else if (a == "-i" || a == "--index") o.index = need(i);
         else if (a == "-o" || a == "--output") o.output = need(i);
         else if (a == "-p" || a == "--profile") need(i);
+        else if (a == "-a" || a == "--input-alphabet") o.inputAlphabet = need(i);
         else if (a == "-e" || a == "--e-value") o.params.max_evalue = std::atof(need(i));
         else if (a == "--bit-score") o.params.min_bit_score = std::atoi(need(i));
         else if (a == "--percent-identity") o.params.id_cutoff = std::atoi(need(i));
@@ -139,6 +141,10 @@ void parse(int argc, char ** argv, Options & o)
     }
     if (o.query.empty() || o.index.empty())
         die("-q and -i are required");
+    if (o.inputAlphabet != "auto" && o.inputAlphabet != "dna5" && o.inputAlphabet != "aminoacid")
+        die("Invalid argument to --input-alphabet");
+    if (o.domain != LGPU_DOMAIN_PROTEIN && o.inputAlphabet != "auto")
+        die("--input-alphabet is a searchp option");
     if (!endsWith(o.output, ".m8"))
         die("only BLAST tabular output (.m8) is produced by the GPU path; other formats stay with the reference");
     if (std::ifstream(o.output).good())
@@ -152,14 +158,57 @@ struct Fasta
     std::vector<uint64_t>    offsets{0};
 };
 
-Fasta readFasta(std::string const & path, uint32_t domain)
+// detectSeqFileAlphabet (src/shared_misc.hpp:83-110): the first sequence decides
+uint32_t detectAlphabet(std::string const & path)
+{
+    std::ifstream in(path, std::ios::binary);
+    if (!in)
+        die("cannot open query file " + path);
+    std::string line, seq;
+    bool        have = false;
+    while (std::getline(in, line))
+    {
+        if (!line.empty() && line.back() == '\r')
+            line.pop_back();
+        if (line.empty())
+            continue;
+        if (line[0] == '>')
+        {
+            if (have)
+                break;
+            have = true;
+        }
+        else if (have)
+            seq += line;
+    }
+    auto const allIn = [&](char const * set) {
+        for (char c : seq)
+            if (!std::strchr(set, c))
+                return false;
+        return true;
+    };
+    if (allIn("ACGTUNacgtun"))
+        return LGPU_ALPH_DNA5;
+    if (allIn("ACGTUNRYKMSWBDHVacgtunrykmswbdhv"))
+    {
+        std::fprintf(stderr, "\nWARNING: You query file was detected as non-standard DNA, but it could be AminoAcid, too.\n"
+                             "To explicitly read as AminoAcid, add '--query-alphabet aminoacid'.\n"
+                             "To ignore and disable this warning, add '--query-alphabet dna5'.\n");
+        return LGPU_ALPH_DNA5;
+    }
+    if (allIn("ABCDEFGHIJKLMNOPQRSTUVWXYZ*abcdefghijklmnopqrstuvwxyz"))
+        return LGPU_ALPH_AMINO_ACID;
+    die("Your query file contains illegal characters in the first sequence.");
+}
+
+Fasta readFasta(std::string const & path, bool aminoAcid)
 {
     std::ifstream in(path, std::ios::binary);
     if (!in)
         die("cannot open query file " + path);
     // char -> rank like BioC++ (aa27: unknown -> X; dna5: unknown -> N, U -> T)
     uint8_t tab[256];
-    if (domain == LGPU_DOMAIN_PROTEIN)
+    if (aminoAcid)
     {
         std::memset(tab, 23, sizeof(tab));
         char const * alph = "ABCDEFGHIJKLMNOPQRSTUVWXYZ*";
@@ -276,7 +325,14 @@ int main(int argc, char ** argv)
         die(lgpu_last_error(nullptr));
     lgpu_index_desc const * desc = lgpu_lba_desc(lba);
     double const            t1   = now();
-    Fasta const             f    = readFasta(o.query, o.domain);
+    // query alphabet: fixed for searchn / searchbs, given or auto-detected for searchp (src/search.cpp:209-216)
+    uint32_t qryAlph = LGPU_ALPH_DNA5;
+    if (o.domain == LGPU_DOMAIN_PROTEIN)
+        qryAlph = o.inputAlphabet == "dna5"        ? static_cast<uint32_t>(LGPU_ALPH_DNA5)
+                  : o.inputAlphabet == "aminoacid" ? static_cast<uint32_t>(LGPU_ALPH_AMINO_ACID)
+                                                   : detectAlphabet(o.query);
+    o.params.query_alph = qryAlph;
+    Fasta const             f    = readFasta(o.query, qryAlph == LGPU_ALPH_AMINO_ACID);
     uint64_t const          nQ   = f.ids.size();
     double const            t2   = now();
     if (o.verbosity >= 2)

@@ -174,6 +174,47 @@ def nucl_reads(db, offs, n_reads: int, length: int, seed: int = 5, sub=0.03, bis
     return q.reshape(-1), np.arange(n_reads + 1, dtype=np.int64) * length
 
 
+# one codon per amino acid (canonical genetic code) for back-translation of synthetic proteins
+_CODON = {"A": "GCT", "R": "CGT", "N": "AAT", "D": "GAT", "C": "TGT", "Q": "CAA", "E": "GAA", "G": "GGT", "H": "CAT",
+          "I": "ATT", "L": "CTT", "K": "AAA", "M": "ATG", "F": "TTT", "P": "CCT", "S": "TCT", "T": "ACT", "W": "TGG",
+          "Y": "TAT", "V": "GTT"}
+_SYN = {"A": "GCN", "R": "CGN", "G": "GGN", "L": "CTN", "P": "CCN", "S": "TCN", "T": "ACN", "V": "GTN"}  # 4-fold sites
+
+
+def back_translate(rng, prot):
+    """ASCII protein -> ASCII nucleotides; 4-fold degenerate third positions are randomised."""
+    tab = np.zeros((256, 3), np.uint8)
+    four = np.zeros(256, bool)
+    for a, c in _CODON.items():
+        tab[ord(a)] = np.frombuffer(c.encode(), np.uint8)
+        four[ord(a)] = a in _SYN
+    out = tab[prot].copy()
+    m = four[prot]
+    out[m, 2] = NT[rng.integers(0, 4, int(m.sum()))]
+    return out.reshape(-1)
+
+
+def revcomp(nt):
+    return _COMP[nt[::-1]]
+
+
+def coding_nucl_seqs(rng, prots, offs, flank=(0, 30), rc_every=2):
+    """every protein back-translated into its own nucleotide sequence with random flanks (so that all
+    three frames occur); every `rc_every`-th one reverse-complemented"""
+    seqs = []
+    for i in range(len(offs) - 1):
+        p = prots[offs[i]:offs[i + 1]]
+        a = NT[rng.integers(0, 4, int(rng.integers(flank[0], flank[1] + 1)))]
+        b = NT[rng.integers(0, 4, int(rng.integers(flank[0], flank[1] + 1)))]
+        s = np.concatenate([a, back_translate(rng, p), b])
+        if rc_every and i % rc_every == 1:
+            s = revcomp(s)
+        seqs.append(s)
+    no = np.zeros(len(seqs) + 1, np.int64)
+    np.cumsum([len(x) for x in seqs], out=no[1:])
+    return np.concatenate(seqs), no
+
+
 def write_fasta(path: str, seqs, offs, prefix: str, width: int = 0):
     """Write one record per sequence, `>prefixN` ids (no spaces), sequence on a single line."""
     n = len(offs) - 1

@@ -56,7 +56,47 @@ struct Index
     std::unique_ptr<lgpu::LbaFile> file;
     lgpu_index_desc                d{};
     uint64_t                       dbTotalLength = 0;
+    // the reference's transSbjSeqs (src/shared_definitions.hpp:246-255): the stored sequences, each one
+    // twice for bisulfite indexes (views::duplicate), or their six-frame translations (translate_join)
+    uint32_t              sbjFrames = 1;
+    std::vector<uint8_t>  tSeqs;   // translated subjects only
+    std::vector<uint64_t> tDelims; // 6 * n_seqs + 1
+
+    uint8_t const * sbjSeq(uint64_t subjId) const
+    {
+        return sbjFrames == 6 ? tSeqs.data() + tDelims[subjId] : d.seqs + d.seq_delims[subjId / sbjFrames];
+    }
+    uint64_t sbjLen(uint64_t subjId) const
+    {
+        if (sbjFrames == 6)
+            return tDelims[subjId + 1] - tDelims[subjId];
+        return d.seq_delims[subjId / sbjFrames + 1] - d.seq_delims[subjId / sbjFrames];
+    }
 };
+
+// one translated frame of a dna5 sequence (BIO ranges/views/translate_single.hpp:95-150, canonical code)
+static void translateFrame(uint8_t const * nt, uint64_t len, uint32_t frame, std::vector<uint8_t> & out)
+{
+    uint64_t const n = lgpu::translatedFrameLength(len, frame);
+    uint64_t const o = frame % 3;
+    for (uint64_t k = 0; k < n; ++k)
+    {
+        uint8_t a, b, c;
+        if (frame < 3)
+        {
+            a = nt[3 * k + o];
+            b = nt[3 * k + o + 1];
+            c = nt[3 * k + o + 2];
+        }
+        else
+        {
+            a = lgpu::kDna5Complement[nt[len - 3 * k - o - 1]];
+            b = lgpu::kDna5Complement[nt[len - 3 * k - o - 2]];
+            c = lgpu::kDna5Complement[nt[len - 3 * k - o - 3]];
+        }
+        out.push_back(lgpu::kDna5Translate[(a * 5 + b) * 5 + c]);
+    }
+}
 
 // ---------------------------------------------------------------------------------------------
 // FM index primitives
@@ -180,29 +220,44 @@ static uint8_t const * reductionTable(uint32_t redAlph)
         case LGPU_ALPH_MURPHY10: return lgpu::kAa27ToMurphy10;
         case LGPU_ALPH_AMINO_ACID: return identity27;
         case LGPU_ALPH_DNA4: return dna5to4;
+        case LGPU_ALPH_DNA3BS: return dna5to4; // then mapped per frame direction, see makeQueries
         default: return nullptr;
     }
 }
 
-static Queries makeQueries(uint32_t domain, uint32_t redAlph, uint8_t const * res, uint64_t const * offs, uint64_t n)
+static Queries makeQueries(DomainInfo const & di, uint32_t redAlph, uint8_t const * res, uint64_t const * offs, uint64_t n)
 {
-    Queries          q;
-    DomainInfo const di  = lgpu::domainInfo(domain);
-    uint8_t const *  red = reductionTable(redAlph);
-    q.nFrames            = di.qryNumFrames;
-    q.n                  = n;
+    Queries         q;
+    uint8_t const * red = reductionTable(redAlph);
+    q.nFrames           = di.qryNumFrames;
+    q.n                 = n;
     q.offs.push_back(0);
+    std::vector<uint8_t> frame;
     for (uint64_t i = 0; i < n; ++i)
     {
         uint64_t const len = offs[i + 1] - offs[i];
         q.origLen.push_back(static_cast<uint32_t>(len));
         for (uint32_t f = 0; f < q.nFrames; ++f)
         {
-            for (uint64_t k = 0; k < len; ++k)
+            // protein: the query itself; nucleotide: (fwd, rc); translated: six frames; bisulfite:
+            // (fwd, fwd, rc, rc), each pair reduced with the forward (C->T) and the reverse (G->A)
+            // bisulfite alphabet alternately (src/shared_definitions.hpp:257-281,
+            // src/view_reduce_to_bisulfite.hpp:51-52,133-135)
+            bool const           bs          = redAlph == LGPU_ALPH_DNA3BS;
+            static uint8_t const bsTab[2][4] = {{0, 1, 2, 1}, {3, 4, 3, 5}};
+            frame.clear();
+            if (di.qFrameMode == 2)
+                translateFrame(res + offs[i], len, f, frame);
+            else
             {
-                uint8_t r = (f == 0) ? res[offs[i] + k] : lgpu::kDna5Complement[res[offs[i] + len - 1 - k]];
+                bool const revComp = di.qFrameMode == 3 ? (f >= 2) : (di.qFrameMode == 1 && f == 1);
+                for (uint64_t k = 0; k < len; ++k)
+                    frame.push_back(!revComp ? res[offs[i] + k] : lgpu::kDna5Complement[res[offs[i] + len - 1 - k]]);
+            }
+            for (uint8_t r : frame)
+            {
                 q.trans.push_back(r);
-                q.red.push_back(red[r]);
+                q.red.push_back(bs ? bsTab[f % 2][red[r]] : red[r]);
             }
             q.offs.push_back(q.trans.size());
         }
@@ -222,9 +277,11 @@ struct Ctx
     DomainInfo    di;
 };
 
-static inline int scoreOf(Scoring const & sc, uint8_t a, uint8_t b)
+// scoring matrix for a (frame-expanded) subject: bisulfite subjects with odd id were converted in the
+// reverse direction and use the reverse matrix (src/search_algo.hpp:464-466,1098,1249)
+static inline int8_t const * matrixFor(Ctx const & c, uint32_t subjId)
 {
-    return sc.matrix[a * 32 + b];
+    return (c.p.domain == LGPU_DOMAIN_BISULFITE && (subjId & 1u)) ? c.sc.matrixRev : c.sc.matrix;
 }
 
 static bool seedLooksPromising(Ctx const & c, Queries const & q, lgpu_search_opts const & so, lgpu_match const & m)
@@ -235,7 +292,8 @@ static bool seedLooksPromising(Ctx const & c, Queries const & q, lgpu_search_opt
     uint64_t const          actual  = m.qry_end - m.qry_start;
     uint64_t                effLen  = std::max<uint64_t>(static_cast<uint64_t>(so.seed_length * c.p.pre_scoring), actual);
     uint64_t const          qLen    = q.offs[m.qry_id + 1] - q.offs[m.qry_id];
-    uint64_t const          sLen    = d.seq_delims[m.subj_id + 1] - d.seq_delims[m.subj_id];
+    uint64_t const          sLen    = c.idx->sbjLen(m.subj_id);
+    int8_t const *          M       = matrixFor(c, m.subj_id);
     if (effLen > actual)
     {
         qBegin -= (effLen - actual) / 2;
@@ -250,13 +308,13 @@ static bool seedLooksPromising(Ctx const & c, Queries const & q, lgpu_search_opt
         effLen = std::min({static_cast<uint64_t>(qLen - qBegin), static_cast<uint64_t>(sLen - sBegin), effLen});
     }
     uint8_t const * qs     = q.trans.data() + q.offs[m.qry_id] + qBegin;
-    uint8_t const * ss     = d.seqs + d.seq_delims[m.subj_id] + sBegin;
+    uint8_t const * ss     = c.idx->sbjSeq(m.subj_id) + sBegin;
     int             s      = 0;
     int             maxS   = 0;
     int const       thresh = static_cast<int>(c.p.pre_scoring_thresh * effLen);
     for (uint64_t i = 0; i < effLen; ++i)
     {
-        s += scoreOf(c.sc, qs[i], ss[i]);
+        s += M[qs[i] * 32 + ss[i]];
         if (s < 0)
             s = 0;
         else if (s > maxS)
@@ -438,7 +496,7 @@ static void widenAndMerge(Ctx const & c, Queries const & q, std::vector<lgpu_mat
     for (lgpu_match & m : ms)
     {
         uint64_t const qLen = q.offs[m.qry_id + 1] - q.offs[m.qry_id];
-        uint64_t const sLen = d.seq_delims[m.subj_id + 1] - d.seq_delims[m.subj_id];
+        uint64_t const sLen = c.idx->sbjLen(m.subj_id);
         uint64_t       s0   = (m.subj_start < m.qry_start) ? 0 : m.subj_start - m.qry_start;
         m.qry_start         = 0;
         m.qry_end           = static_cast<uint32_t>(qLen);
@@ -486,8 +544,10 @@ struct DpResult
 };
 
 // query = columns (outer loop), subject window = rows (inner loop)
-static DpResult alignLocal(Scoring const & sc, uint8_t const * qs, uint32_t nq, uint8_t const * ts, uint32_t nt,
-                           bool withTrace, std::vector<uint8_t> & T, std::vector<int> & buf)
+// `M` = 32-strided score matrix [query residue][subject residue]; `bsStats`: bisulfite rule for
+// "identical" columns (src/evaluate_bisulfite_alignment.hpp:97)
+static DpResult alignLocal(Scoring const & sc, int8_t const * M, bool bsStats, uint8_t const * qs, uint32_t nq,
+                           uint8_t const * ts, uint32_t nt, bool withTrace, std::vector<uint8_t> & T, std::vector<int> & buf)
 {
     constexpr int NEG = -16384; // INT16_MIN / 2 (SQ/align/dp_cell.h:144-146)
     int const     go = sc.gapOpenSeqan, ge = sc.gapExtend;
@@ -510,7 +570,7 @@ static DpResult alignLocal(Scoring const & sc, uint8_t const * qs, uint32_t nq, 
         int v = NEG, sUp = 0;
         Scur[0] = 0;
         Hcur[0] = NEG;
-        int8_t const * row = sc.matrix + qs[i - 1] * 32;
+        int8_t const * row = M + qs[i - 1] * 32;
         for (uint32_t j = 1; j <= nt; ++j)
         {
             int     diag = Sprev[j - 1] + row[ts[j - 1]];
@@ -581,8 +641,9 @@ static DpResult alignLocal(Scoring const & sc, uint8_t const * qs, uint32_t nq, 
     };
     auto diagStats = [&](uint32_t ii, uint32_t jj) { // residues consumed by a diagonal step ending at (ii, jj)
         uint8_t const a = qs[ii - 1], b = ts[jj - 1];
-        if (a == b) ++r.nMatch; else ++r.nMismatch;
-        if (sc.matrix[a * 32 + b] > 0) ++r.nPositive;
+        bool const isMatch = bsStats ? (M[a * 32 + b] == M[a * 32 + a]) : (a == b);
+        if (isMatch) ++r.nMatch; else ++r.nMismatch;
+        if (M[a * 32 + b] > 0) ++r.nPositive;
     };
     while (i > 0 && j > 0 && tv != 0)
     {
@@ -635,7 +696,7 @@ static inline void windowOf(Ctx const & c, Queries const & q, lgpu_match const &
     lgpu_index_desc const & d = c.idx->d;
     qs                        = q.trans.data() + q.offs[m.qry_id] + m.qry_start;
     nq                        = m.qry_end - m.qry_start;
-    ts                        = d.seqs + d.seq_delims[m.subj_id / c.di.sbjNumFrames] + m.subj_start;
+    ts                        = c.idx->sbjSeq(m.subj_id) + m.subj_start;
     nt                        = m.subj_end - m.subj_start;
 }
 
@@ -654,9 +715,31 @@ static lgpu_hit makeHit(Ctx const & c, Queries const & q, lgpu_match const & m, 
     h.score   = r.score;
     h.n_match = r.nMatch; h.n_mismatch = r.nMismatch; h.n_gap_open = r.nGapOpen; h.n_gap_ext = r.nGapExt;
     h.n_positive = r.nPositive; h.aln_len = r.alnLen;
-    if (c.p.domain == LGPU_DOMAIN_NUCLEOTIDE)
-        h.q_frame = (m.qry_id % 2) ? -1 : 1;
+    // _setFrames (src/search_algo.hpp:769-814)
+    h.q_frame = 0;
     h.s_frame = 0;
+    if (c.di.qIsTranslated)
+    {
+        h.q_frame = static_cast<int8_t>((m.qry_id % 3) + 1);
+        if (m.qry_id % 6 > 2)
+            h.q_frame = static_cast<int8_t>(-h.q_frame);
+    }
+    else if (c.p.domain == LGPU_DOMAIN_BISULFITE)
+    {
+        h.q_frame = static_cast<int8_t>((m.qry_id % 2) + 1);
+        if (m.qry_id % 4 > 1)
+            h.q_frame = static_cast<int8_t>(-h.q_frame);
+    }
+    else if (c.p.domain == LGPU_DOMAIN_NUCLEOTIDE)
+        h.q_frame = (m.qry_id % 2) ? -1 : 1;
+    if (c.di.sIsTranslated)
+    {
+        h.s_frame = static_cast<int8_t>((m.subj_id % 3) + 1);
+        if (m.subj_id % 6 > 2)
+            h.s_frame = static_cast<int8_t>(-h.s_frame);
+    }
+    else if (c.p.domain == LGPU_DOMAIN_BISULFITE)
+        h.s_frame = static_cast<int8_t>((m.subj_id % 2) + 1);
     h.phase   = phase;
     return h;
 }
@@ -675,7 +758,9 @@ static void extendMatches(Ctx const & c, Queries const & q, std::vector<lgpu_mat
         windowOf(c, q, m, qs, nq, ts, nt);
         ++st.n_extensions_score;
         st.cells_score += static_cast<uint64_t>(nq) * nt;
-        DpResult const r1   = alignLocal(c.sc, qs, nq, ts, nt, false, T, buf);
+        int8_t const * M    = matrixFor(c, m.subj_id);
+        bool const     bs   = c.p.domain == LGPU_DOMAIN_BISULFITE;
+        DpResult const r1   = alignLocal(c.sc, M, bs, qs, nq, ts, nt, false, T, buf);
         uint32_t const qLen = q.origLen[m.qry_id / q.nFrames];
         double bits = 0, evalue = 0;
         if (c.p.min_bit_score >= 0)
@@ -690,7 +775,7 @@ static void extendMatches(Ctx const & c, Queries const & q, std::vector<lgpu_mat
         }
         ++st.n_extensions_trace;
         st.cells_trace += static_cast<uint64_t>(nq) * nt;
-        DpResult const r2 = alignLocal(c.sc, qs, nq, ts, nt, true, T, buf);
+        DpResult const r2 = alignLocal(c.sc, M, bs, qs, nq, ts, nt, true, T, buf);
         lgpu_hit       h  = makeHit(c, q, m, r2, phase);
         float const identity = static_cast<float>(100.0 * static_cast<float>(h.n_match) / static_cast<float>(h.aln_len));
         if (identity < c.p.id_cutoff) { ++st.hits_failed_identity; continue; }
@@ -704,7 +789,7 @@ static void extendMatches(Ctx const & c, Queries const & q, std::vector<lgpu_mat
 static int searchAll(Ctx const & c, uint8_t const * res, uint64_t const * offs, uint64_t n, std::vector<lgpu_hit> & hits,
                      lgpu_stats & st)
 {
-    Queries              q = makeQueries(c.p.domain, c.idx->d.red_alph, res, offs, n);
+    Queries              q = makeQueries(c.di, c.idx->d.red_alph, res, offs, n);
     lgpu::EValueComputer ev(c.sc.ka, c.idx->dbTotalLength, c.di.qIsTranslated);
     std::vector<uint8_t>    active(n, 1);
     std::vector<lgpu_match> ms;
@@ -757,7 +842,21 @@ orc_handle * orc_open(char const * path)
         h->idx.file.reset(new lgpu::LbaFile(path));
         h->idx.d = h->idx.file->desc;
         // dbTotalLength = sum of reduced subject lengths (src/search_algo.hpp:317-318)
-        h->idx.dbTotalLength = h->idx.d.n_residues * lgpu::domainInfo(h->idx.d.red_alph == LGPU_ALPH_DNA3BS ? 2 : 0).sbjNumFrames;
+        lgpu_index_desc const & d = h->idx.d;
+        h->idx.sbjFrames          = d.red_alph == LGPU_ALPH_DNA3BS ? 2 : 1;
+        h->idx.dbTotalLength      = d.n_residues * h->idx.sbjFrames;
+        if (d.trans_alph == LGPU_ALPH_AMINO_ACID && d.orig_alph == LGPU_ALPH_DNA5)
+        {
+            h->idx.sbjFrames = 6;
+            h->idx.tDelims.push_back(0);
+            for (uint64_t sq = 0; sq < d.n_seqs; ++sq)
+                for (uint32_t f = 0; f < 6; ++f)
+                {
+                    orc::translateFrame(d.seqs + d.seq_delims[sq], d.seq_delims[sq + 1] - d.seq_delims[sq], f, h->idx.tSeqs);
+                    h->idx.tDelims.push_back(h->idx.tSeqs.size());
+                }
+            h->idx.dbTotalLength = h->idx.tSeqs.size();
+        }
     }
     catch (std::exception const & e)
     {
@@ -776,7 +875,7 @@ static int makeCtx(orc::Ctx & c, orc_handle const * h, lgpu_params const * p)
 {
     c.idx = &h->idx;
     c.p   = *p;
-    c.di  = lgpu::domainInfo(p->domain);
+    c.di  = lgpu::domainInfo(p->domain, h->idx.d.orig_alph, p->query_alph);
     return lgpu::makeScoring(c.sc, *p);
 }
 
@@ -797,7 +896,7 @@ int orc_seed(orc_handle * h, lgpu_params const * p, uint8_t const * res, uint64_
 {
     orc::Ctx c;
     if (int rc = makeCtx(c, h, p)) return rc;
-    orc::Queries         q = orc::makeQueries(p->domain, h->idx.d.red_alph, res, offs, n);
+    orc::Queries         q = orc::makeQueries(c.di, h->idx.d.red_alph, res, offs, n);
     std::vector<uint8_t> active(n, 1);
     h->matches.clear();
     orc::seedQueries(c, q, phase == 1 ? p->opts0 : p->opts, active, h->matches, *st);
@@ -811,7 +910,7 @@ int orc_merge(orc_handle * h, lgpu_params const * p, uint8_t const * res, uint64
 {
     orc::Ctx c;
     if (int rc = makeCtx(c, h, p)) return rc;
-    orc::Queries q = orc::makeQueries(p->domain, h->idx.d.red_alph, res, offs, n);
+    orc::Queries q = orc::makeQueries(c.di, h->idx.d.red_alph, res, offs, n);
     h->matches.assign(in, in + nIn);
     orc::widenAndMerge(c, q, h->matches, *st);
     *out  = h->matches.data();
@@ -824,7 +923,7 @@ int orc_extend(orc_handle * h, lgpu_params const * p, uint8_t const * res, uint6
 {
     orc::Ctx c;
     if (int rc = makeCtx(c, h, p)) return rc;
-    orc::Queries         q = orc::makeQueries(p->domain, h->idx.d.red_alph, res, offs, n);
+    orc::Queries         q = orc::makeQueries(c.di, h->idx.d.red_alph, res, offs, n);
     std::vector<uint8_t> T;
     std::vector<int>     buf;
     for (uint64_t i = 0; i < nWin; ++i)
@@ -832,7 +931,8 @@ int orc_extend(orc_handle * h, lgpu_params const * p, uint8_t const * res, uint6
         uint8_t const *qs, *ts;
         uint32_t       nq, nt;
         orc::windowOf(c, q, win[i], qs, nq, ts, nt);
-        orc::DpResult r = orc::alignLocal(c.sc, qs, nq, ts, nt, withTrace != 0, T, buf);
+        orc::DpResult r = orc::alignLocal(c.sc, orc::matrixFor(c, win[i].subj_id), p->domain == LGPU_DOMAIN_BISULFITE, qs, nq,
+                                          ts, nt, withTrace != 0, T, buf);
         if (scores) scores[i] = r.score;
         if (hitsOut && withTrace) hitsOut[i] = orc::makeHit(c, q, win[i], r, 0);
     }

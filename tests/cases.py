@@ -7,7 +7,23 @@ CASES = [
     ("prot_family", 0, ["none", "sensitive"]),
     ("prot_diverged", 0, ["none"]),
     ("nucl", 1, ["none", "fast", "sensitive"]),
+    ("bisulfite", 2, ["none", "fast", "sensitive"]),
+    ("blastx", 0, ["none", "sensitive"]),
+    ("tblastn", 0, ["none", "sensitive"]),
+    ("tblastx", 0, ["none"]),
 ]
+# cases whose queries are nucleotides searched against a protein / translated index (BLASTX, TBLASTX):
+# lgpu_params.query_alph = LGPU_ALPH_DNA5, residues encoded as dna5 ranks
+DNA_QUERY_CASES = {"blastx", "tblastx"}
+
+
+def query_alph(case):
+    return 3 if case in DNA_QUERY_CASES else 0
+
+
+def query_encoding(case, domain):
+    """`domain` argument for encode(): 0 = aa27 ranks, otherwise dna5 ranks"""
+    return 1 if case in DNA_QUERY_CASES else domain
 CASE_PROFILES = [(c, d, p) for c, d, ps in CASES for p in ps]
 FUNNEL = ["hits_after_seeding", "hits_failed_pre_extend", "hits_failed_evalue", "hits_failed_bitscore",
           "hits_failed_identity", "hits_duplicate", "hits_duplicate2", "hits_abundant", "hits_final", "pairs",

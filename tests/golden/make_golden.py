@@ -82,6 +82,43 @@ def with_random_queries(rng_seed, q, qoffs, n_random, length):
     return q2, qo2
 
 
+def main_bs():
+    # bisulfite: C->T converted reads (95 %), 1 % errors, odd reads reverse-complemented
+    db, offs = synth.nucl_db(4, 50_000, seed=131)
+    q, qo = synth.nucl_reads(db, offs, 160, 100, seed=132, bisulfite=True)
+    # the last 48 reads get 8 % extra substitutions (phase 2, e-value failures), plus 8 unrelated reads
+    rng = np.random.default_rng(133)
+    q = q.copy().reshape(160, 100)
+    m = rng.random((48, 100)) < 0.08
+    tail = q[112:]
+    tail[m] = synth.NT[rng.integers(0, 4, int(m.sum()))]
+    q = np.concatenate([q.reshape(-1), synth.NT[rng.integers(0, 4, 8 * 100)]])
+    qo = np.arange(169, dtype=np.int64) * 100
+    run_case("bisulfite", "bs", db, offs, q, qo, ["none", "fast", "sensitive"])
+
+
+def main_translated():
+    rng = np.random.default_rng(140)
+    # BLASTX: protein database, nucleotide queries coding for mutated protein windows (+ random reads)
+    db, offs = synth.protein_db(300, seed=141)
+    qp, qpo = synth.protein_queries(db, offs, 40, 90, seed=142, sub=(0.10, 0.25))
+    qn, qno = synth.coding_nucl_seqs(rng, qp, qpo, flank=(0, 12))
+    extra = synth.NT[rng.integers(0, 4, 6 * 250)]
+    qn = np.concatenate([qn, extra, synth.NT[rng.integers(0, 4, 20)]])
+    qno = np.concatenate([qno, qno[-1] + np.arange(1, 7, dtype=np.int64) * 250, [qno[-1] + 6 * 250 + 20]])
+    run_case("blastx", "p", db, offs, qn, qno, ["none", "sensitive"])
+    # TBLASTN: nucleotide database (coding sequences on both strands), protein queries
+    pdb, poffs = synth.protein_db(120, seed=143)
+    ndb, noffs = synth.coding_nucl_seqs(rng, pdb, poffs, flank=(0, 40))
+    qp, qpo = synth.protein_queries(pdb, poffs, 40, 80, seed=144, sub=(0.10, 0.25))
+    qp, qpo = with_random_queries(145, qp, qpo, 5, 80)
+    run_case("tblastn", "p", ndb, noffs, qp, qpo, ["none", "sensitive"])
+    # TBLASTX: the same nucleotide database, nucleotide queries
+    qp, qpo = synth.protein_queries(pdb, poffs, 30, 70, seed=146, sub=(0.10, 0.20))
+    qn, qno = synth.coding_nucl_seqs(rng, qp, qpo, flank=(0, 9))
+    run_case("tblastx", "p", ndb, noffs, qn, qno, ["none"])
+
+
 def main():
     # protein, flat database; queries: mutated windows + a few random ones + one shorter than a seed
     db, offs = synth.protein_db(500, seed=101)
@@ -106,4 +143,11 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if "--bs-only" in sys.argv:
+        main_bs()
+    elif "--translated-only" in sys.argv:
+        main_translated()
+    else:
+        main()
+        main_bs()
+        main_translated()

@@ -8,7 +8,7 @@ import pytest
 
 import lambda_b200
 import orc
-from cases import CASE_PROFILES, CASES, FUNNEL, load_golden
+from cases import CASE_PROFILES, CASES, FUNNEL, load_golden, query_alph, query_encoding
 from lambda_b200 import synth
 from lambda_b200._abi import MATCH_DT
 
@@ -22,7 +22,17 @@ HIT_INT_FIELDS = ["q_id", "s_id", "q_start", "q_end", "s_start", "s_end", "q_len
 def _load(gdir, case, domain):
     path = os.path.join(gdir, case, "db.lba")
     ids, data, offs = lambda_b200.read_fasta(os.path.join(gdir, case, "q.fasta"))
-    return path, ids, lambda_b200.encode(data, domain), offs
+    return path, ids, lambda_b200.encode(data, query_encoding(case, domain)), offs
+
+
+def _pair(ix, o, case, domain, profile="none", **kw):
+    """a Searcher and the oracle's parameter block for the same case (query alphabet included)"""
+    s = lambda_b200.Searcher(ix, domain, profile, query_alph=query_alph(case), **kw)
+    p = o.params(domain, profile)
+    p.query_alph = query_alph(case)
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return s, p
 
 
 def _sorted(m):
@@ -58,8 +68,7 @@ def test_seeding_matches_oracle(golden_dir, case, domain, profile, mode, monkeyp
     path, ids, res, offs = _load(golden_dir, case, domain)
     o = orc.Oracle(path)
     ix = lambda_b200.Index.load(path)
-    s = lambda_b200.Searcher(ix, domain, profile)
-    p = o.params(domain, profile)
+    s, p = _pair(ix, o, case, domain, profile)
     for phase in (1, 2):
         m_gpu, st_gpu = s.seed(res, offs, phase)
         m_cpu, st_cpu = o.seed(p, res, offs, phase)
@@ -85,8 +94,7 @@ def test_extension_matches_oracle(golden_dir, case, domain, trace, monkeypatch):
     path, ids, res, offs = _load(golden_dir, case, domain)
     o = orc.Oracle(path)
     ix = lambda_b200.Index.load(path)
-    s = lambda_b200.Searcher(ix, domain)
-    p = o.params(domain)
+    s, p = _pair(ix, o, case, domain)
     m, _ = o.seed(p, res, offs, 2)
     win, _ = o.merge(p, res, offs, m)
     # add ragged / degenerate windows: partial queries, 1-row windows, windows at subject ends
@@ -96,6 +104,12 @@ def test_extension_matches_oracle(golden_dir, case, domain, trace, monkeypatch):
     one = win[: min(len(win), 5)].copy()
     one["subj_end"] = one["subj_start"] + 1
     win = np.concatenate([win, extra, one]).astype(MATCH_DT)
+    if domain == 2:
+        # bisulfite: the same windows against the other conversion of the subject (other scoring matrix);
+        # seeding never pairs these, the stage API may
+        flip = win.copy()
+        flip["subj_id"] ^= 1
+        win = np.concatenate([win, flip]).astype(MATCH_DT)
     sc_gpu, _ = s.extend_scores(res, offs, win)
     sc_cpu, h_cpu = o.extend(p, res, offs, win, True)
     assert (sc_gpu == sc_cpu).all()
@@ -201,7 +215,7 @@ def test_search_reproduces_reference_output(golden_dir, case, domain, profile, m
     monkeypatch.setenv("LAMBDA_B200_SEED", mode)
     path, ids, res, offs = _load(golden_dir, case, domain)
     ix = lambda_b200.Index.load(path)
-    s = lambda_b200.Searcher(ix, domain, profile)
+    s = lambda_b200.Searcher(ix, domain, profile, query_alph=query_alph(case))
     hits, st = s.search(res, offs)
     ref, funnel = load_golden(golden_dir, case, profile)
     assert sorted(s.m8(hits, ids)) == sorted(ref)
@@ -245,11 +259,13 @@ CLI = os.path.join(ROOT, "bin", "lambda3_b200")
 
 @pytest.mark.skipif(not os.path.exists(CLI), reason="bin/lambda3_b200 not built")
 @pytest.mark.parametrize("case,domain,profile", [("prot_flat", 0, "none"), ("prot_diverged", 0, "none"),
-                                                 ("prot_family", 0, "sensitive"), ("nucl", 1, "none")])
+                                                 ("prot_family", 0, "sensitive"), ("nucl", 1, "none"),
+                                                 ("bisulfite", 2, "none"), ("blastx", 0, "none"),
+                                                 ("tblastn", 0, "sensitive"), ("tblastx", 0, "none")])
 def test_cli_output_is_byte_identical_to_reference(golden_dir, tmp_path, case, domain, profile):
     """the host program keeps the lambda3 command line and reproduces the reference's -t 1 file, in order"""
     out = tmp_path / "out.m8"
-    cmd = [CLI, "searchp" if domain == 0 else "searchn", "-q", os.path.join(golden_dir, case, "q.fasta"), "-i",
+    cmd = [CLI, ("searchp", "searchn", "searchbs")[domain], "-q", os.path.join(golden_dir, case, "q.fasta"), "-i",
            os.path.join(golden_dir, case, "db.lba"), "-o", str(out), "-t", "1", "--version-to-outputfile", "0", "-v", "2"]
     if profile != "none":
         cmd += ["-p", profile]

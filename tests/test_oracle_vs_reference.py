@@ -6,15 +6,16 @@ import numpy as np
 import pytest
 
 import orc
-from cases import CASE_PROFILES, FUNNEL, load_golden
+from cases import CASE_PROFILES, FUNNEL, load_golden, query_alph, query_encoding
 
 
 @pytest.mark.parametrize("case,domain,profile", CASE_PROFILES)
 def test_oracle_reproduces_reference(golden_dir, case, domain, profile):
     o = orc.Oracle(os.path.join(golden_dir, case, "db.lba"))
     ids, data, offs = orc.read_fasta(os.path.join(golden_dir, case, "q.fasta"))
-    res = orc.encode(data, domain)
+    res = orc.encode(data, query_encoding(case, domain))
     p = o.params(domain, profile)
+    p.query_alph = query_alph(case)
     hits, st = o.search(p, res, offs)
     lines = o.m8(p, hits, ids)
     ref, funnel = load_golden(golden_dir, case, profile)
