@@ -203,7 +203,7 @@ struct lgpu_ctx
     bool                       dpxOk = false; // scoring fits the int8 profile of the DPX kernel
     unsigned int               streams = 1;  // sub-batches in flight per lgpu_search_batch call (LAMBDA_B200_STREAMS)
     std::vector<std::unique_ptr<lgpu_ctx>> workers;
-    int                        seedMode = 0; // LAMBDA_B200_SEED=thread|warp|block forces one seeding kernel (tests); 0 = auto
+    int                        seedMode = 0; // LAMBDA_B200_SEED=thread|warp|block|spec forces one seeding kernel (tests); 0 = auto
     DevBuf<unsigned long long> dSeedCursors;
     DevBuf<unsigned int>       dSeedCounts;
     DevBuf<unsigned char>      dTrace;
@@ -427,7 +427,7 @@ static uint64_t runSeeding(lgpu_ctx & c, lgpu_search_opts const & so, unsigned i
                                          ? c.di.qryNumFrames * ((maxActiveLen - so.seed_length) / so.seed_offset + 1)
                                          : 1;
         size_t const scratchCursors = static_cast<size_t>(nActive) * maxSeeds * maxLeaves;
-        bool const   blockPerQuery  = c.seedMode != 1 && c.seedMode != 2 && nActive <= 4096 &&
+        bool const   blockPerQuery  = c.seedMode != 1 && c.seedMode != 2 && c.seedMode != 4 && nActive <= 4096 &&
                                    maxSeeds <= static_cast<unsigned int>(kSeedBlockMaxSeeds) && maxActiveLen < (1u << 24) &&
                                    scratchCursors * sizeof(Cursor) <= (1ull << 30);
         if (blockPerQuery || c.seedMode == 3)
@@ -443,10 +443,13 @@ static uint64_t runSeeding(lgpu_ctx & c, lgpu_search_opts const & so, unsigned i
             S.maxLeaves = maxLeaves;
             seedBlockKernel<<<nActive, 32 * kSeedBlockWarps, 0, c.stream>>>(P, S);
         }
-        else if ((halfMode && c.seedMode != 1) || c.seedMode == 2)
+        else if (c.seedMode == 2)
             seedWarpKernel<<<gridFor(static_cast<unsigned long long>(nActive) * 32, 128), 128, 0, c.stream>>>(P);
-        else
+        else if (c.seedMode == 1)
             seedKernel<<<gridFor(nActive, 128), 128, 0, c.stream>>>(P);
+        else
+            seedSpecKernel<<<gridFor(static_cast<unsigned long long>(nActive) * 32, 32 * kSpecWarps), 32 * kSpecWarps, 0,
+                             c.stream>>>(P);
         LGPU_CUDA(cudaGetLastError());
         if (st)
             st->kernel_launches += 1;
@@ -1282,7 +1285,7 @@ static std::unique_ptr<lgpu_ctx> lgpu::makeContext(lgpu_index const * ix, lgpu_p
     LGPU_CUDA(cudaMemcpy(c->dMatrix.p + 1024, c->scoring.matrixRev, 1024, cudaMemcpyHostToDevice));
     c->dCounters.reserve(8);
     if (char const * e = std::getenv("LAMBDA_B200_SEED"))
-        c->seedMode = !std::strcmp(e, "thread") ? 1 : !std::strcmp(e, "warp") ? 2 : !std::strcmp(e, "block") ? 3 : 0;
+        c->seedMode = !std::strcmp(e, "thread") ? 1 : !std::strcmp(e, "warp") ? 2 : !std::strcmp(e, "block") ? 3 : !std::strcmp(e, "spec") ? 4 : 0;
     if (char const * e = std::getenv("LAMBDA_B200_TRACE"))
         c->forceScalarTrace = !std::strcmp(e, "scalar");
     // the packed kernel stores (score - gapOpen) as int8 profile bytes with -128 reserved for "null"

@@ -698,45 +698,84 @@ __device__ __forceinline__ Cursor seedLeaf(DevIndex const & ix, Cursor const * E
     return mine;
 }
 
-// Everything the reference does with one cursor of one seed (src/search_algo.hpp:674-757), executed by a
-// full warp: adaptive elongation (uniform), abundance cut, then locate + pre-scoring 32 rows at a time.
-__device__ __forceinline__ void seedConsumeCursor(SeedParams const & P, signed char const * sM, unsigned int lane,
-                                                  unsigned int qryId, unsigned char const * trans, unsigned char const * red,
-                                                  unsigned int len, unsigned int seedBegin, Cursor cursor,
-                                                  unsigned long long & hitsThisSeq, unsigned long long needlesSum,
-                                                  unsigned long long needlesPos, unsigned long long & nAfter,
-                                                  unsigned long long & nFailed)
+// seedLooksPromising (src/search_algo.hpp:427-481): ungapped running-maximum score on the seed diagonal
+// over max(seedLength * preScoring, seedLen) residues centred on the seed, clipped to both sequences.
+__device__ __forceinline__ bool seedPreScore(SeedParams const & P, signed char const * sM, unsigned char const * trans,
+                                             unsigned int len, unsigned int seedBegin, unsigned int seedLen,
+                                             unsigned long long subj, unsigned long long pos)
 {
-    DevIndex const &   ix      = P.ix;
-    unsigned int const L       = P.seedLength;
-    unsigned int const ltMask  = (1u << lane) - 1u;
-    unsigned int       seedLen = L;
-    if (P.adaptive)
+    DevIndex const &         ix     = P.ix;
+    long long                qB     = seedBegin;
+    long long                sB     = static_cast<long long>(pos);
+    unsigned long long const actual = seedLen;
+    unsigned long long       eff    = static_cast<unsigned long long>(P.seedLength * P.preScoring);
+    if (eff < actual)
+        eff = actual;
+    unsigned long long const sBase = sbjBase(ix, static_cast<unsigned int>(subj));
+    unsigned long long const sLen  = sbjLength(ix, static_cast<unsigned int>(subj));
+    signed char const *      M     = sM + matrixOffset(ix, static_cast<unsigned int>(subj));
+    if (eff > actual)
     {
-        unsigned long long desired = 1;
-        if (hitsThisSeq < P.maxMatches)
+        qB -= static_cast<long long>((eff - actual) / 2);
+        sB -= static_cast<long long>((eff - actual) / 2);
+        long long const mn = qB < sB ? qB : sB;
+        if (mn < 0)
         {
-            unsigned long long remaining = (needlesSum - needlesPos - seedBegin) / P.seedOffset;
-            if (remaining < 1)
-                remaining = 1;
-            desired = (P.maxMatches - hitsThisSeq) * 10ull / remaining;
-            if (desired == 0)
-                desired = 1;
+            qB -= mn;
+            sB -= mn;
+            eff += mn;
         }
-        unsigned long long oldCount = cursor.len;
-        while (seedBegin + seedLen < len)
-        {
-            Cursor const n = fmExtendRight(ix, cursor, red[seedBegin + seedLen] + 1u);
-            if (n.len < desired && n.len < oldCount)
-                break;
-            cursor   = n;
-            oldCount = n.len;
-            ++seedLen;
-        }
+        unsigned long long const qRem = static_cast<unsigned long long>(len) - qB;
+        unsigned long long const sRem = sLen - sB;
+        if (qRem < eff)
+            eff = qRem;
+        if (sRem < eff)
+            eff = sRem;
     }
-    if (cursor.len > 10ull * P.maxMatches)
-        return;
+    int const             thresh = static_cast<int>(P.preScoringThresh * static_cast<double>(eff));
+    unsigned char const * qs     = trans + qB;
+    unsigned char const * ss     = ix.seqs + sBase + sB;
+    int                   sc = 0, mx = 0;
+    for (unsigned long long i = 0; i < eff; ++i)
+    {
+        sc += M[qs[i] * 32 + __ldg(ss + i)];
+        if (sc < 0)
+            sc = 0;
+        else if (sc > mx)
+            mx = sc;
+        if (mx >= thresh)
+            return true;
+    }
+    return false;
+}
 
+// desiredOccs of the adaptive seed elongation (src/search_algo.hpp:683-701)
+__device__ __forceinline__ unsigned long long seedDesiredOccs(SeedParams const & P, unsigned long long hitsThisSeq,
+                                                              unsigned long long needlesSum, unsigned long long needlesPos,
+                                                              unsigned int seedBegin)
+{
+    unsigned long long desired = 1;
+    if (hitsThisSeq < P.maxMatches)
+    {
+        unsigned long long remaining = (needlesSum - needlesPos - seedBegin) / P.seedOffset;
+        if (remaining < 1)
+            remaining = 1;
+        desired = (P.maxMatches - hitsThisSeq) * 10ull / remaining;
+        if (desired == 0)
+            desired = 1;
+    }
+    return desired;
+}
+
+// locate + pre-scoring of all occurrences of one (already elongated) cursor, 32 rows at a time
+__device__ __forceinline__ void seedConsumeRows(SeedParams const & P, signed char const * sM, unsigned int lane,
+                                                unsigned int qryId, unsigned char const * trans, unsigned int len,
+                                                unsigned int seedBegin, Cursor cursor, unsigned int seedLen,
+                                                unsigned long long & hitsThisSeq, unsigned long long & nAfter,
+                                                unsigned long long & nFailed)
+{
+    DevIndex const &   ix     = P.ix;
+    unsigned int const ltMask = (1u << lane) - 1u;
     for (unsigned long long row0 = 0; row0 < cursor.len; row0 += 32)
     {
         bool const         act  = row0 + lane < cursor.len;
@@ -747,50 +786,7 @@ __device__ __forceinline__ void seedConsumeCursor(SeedParams const & P, signed c
             fmLocate(ix, cursor.lb + row0 + lane, subj, pos);
             pos -= seedLen;
             ++nAfter;
-            long long                qB     = seedBegin;
-            long long                sB     = static_cast<long long>(pos);
-            unsigned long long const actual = seedLen;
-            unsigned long long       eff    = static_cast<unsigned long long>(L * P.preScoring);
-            if (eff < actual)
-                eff = actual;
-            unsigned long long const sBase = sbjBase(ix, static_cast<unsigned int>(subj));
-            unsigned long long const sLen  = sbjLength(ix, static_cast<unsigned int>(subj));
-            signed char const *      M     = sM + matrixOffset(ix, static_cast<unsigned int>(subj));
-            if (eff > actual)
-            {
-                qB -= static_cast<long long>((eff - actual) / 2);
-                sB -= static_cast<long long>((eff - actual) / 2);
-                long long const mn = qB < sB ? qB : sB;
-                if (mn < 0)
-                {
-                    qB -= mn;
-                    sB -= mn;
-                    eff += mn;
-                }
-                unsigned long long const qRem = static_cast<unsigned long long>(len) - qB;
-                unsigned long long const sRem = sLen - sB;
-                if (qRem < eff)
-                    eff = qRem;
-                if (sRem < eff)
-                    eff = sRem;
-            }
-            int const             thresh = static_cast<int>(P.preScoringThresh * static_cast<double>(eff));
-            unsigned char const * qs     = trans + qB;
-            unsigned char const * ss     = ix.seqs + sBase + sB;
-            int                   sc = 0, mx = 0;
-            for (unsigned long long i = 0; i < eff; ++i)
-            {
-                sc += M[qs[i] * 32 + __ldg(ss + i)];
-                if (sc < 0)
-                    sc = 0;
-                else if (sc > mx)
-                    mx = sc;
-                if (mx >= thresh)
-                {
-                    pass = true;
-                    break;
-                }
-            }
+            pass = seedPreScore(P, sM, trans, len, seedBegin, seedLen, subj, pos);
             if (!pass)
                 ++nFailed;
         }
@@ -819,6 +815,258 @@ __device__ __forceinline__ void seedConsumeCursor(SeedParams const & P, signed c
             }
             hitsThisSeq += cnt;
         }
+    }
+}
+
+// Everything the reference does with one cursor of one seed (src/search_algo.hpp:674-757), executed by a
+// full warp: adaptive elongation (uniform), abundance cut, then locate + pre-scoring 32 rows at a time.
+__device__ __forceinline__ void seedConsumeCursor(SeedParams const & P, signed char const * sM, unsigned int lane,
+                                                  unsigned int qryId, unsigned char const * trans, unsigned char const * red,
+                                                  unsigned int len, unsigned int seedBegin, Cursor cursor,
+                                                  unsigned long long & hitsThisSeq, unsigned long long needlesSum,
+                                                  unsigned long long needlesPos, unsigned long long & nAfter,
+                                                  unsigned long long & nFailed)
+{
+    DevIndex const & ix      = P.ix;
+    unsigned int     seedLen = P.seedLength;
+    if (P.adaptive)
+    {
+        unsigned long long const desired  = seedDesiredOccs(P, hitsThisSeq, needlesSum, needlesPos, seedBegin);
+        unsigned long long       oldCount = cursor.len;
+        while (seedBegin + seedLen < len)
+        {
+            Cursor const n = fmExtendRight(ix, cursor, red[seedBegin + seedLen] + 1u);
+            if (n.len < desired && n.len < oldCount)
+                break;
+            cursor   = n;
+            oldCount = n.len;
+            ++seedLen;
+        }
+    }
+    if (cursor.len > 10ull * P.maxMatches)
+        return;
+    seedConsumeRows(P, sM, lane, qryId, trans, len, seedBegin, cursor, seedLen, hitsThisSeq, nAfter, nFailed);
+}
+
+// ---------------------------------------------------------------------------------------------
+// speculative consumption of up to 32 cursors at once
+// ---------------------------------------------------------------------------------------------
+// The reference consumes the cursors of a query strictly one after the other because the adaptive
+// elongation of cursor i looks at hitsThisSeq, the number of hits all earlier cursors produced
+// (src/search_algo.hpp:683-703).  That number only enters through `desired`, and `desired` only decides
+// the elongation at steps where the occurrence count drops to a non-zero value.  So every lane elongates
+// its own cursor with the hitsThisSeq known at the start of the round and remembers for which interval
+// [lo, hi] of `desired` it would have taken exactly the same decisions; the occurrences of all lanes are
+// located and pre-scored together (flattened, 32 rows at a time, results parked in shared memory); a warp
+// scan then yields the true hitsThisSeq in front of every lane, and the longest prefix of lanes whose true
+// `desired` lies inside their interval is committed.  The first lane of a round is never speculative, so
+// every round commits at least one cursor; the others are retried.  Results are identical to the serial
+// order; the dependent-load chain of a query shrinks by up to 32x.
+constexpr int kSpecRowCap = 256; // rows (occurrences) one round can park; 10 * maxMatches = 250 by default
+
+struct SpecScratch
+{
+    unsigned int  subj[kSpecRowCap];
+    unsigned int  pos[kSpecRowCap];
+    unsigned int  cnt[32];
+    unsigned int  passBits[kSpecRowCap / 32];
+    unsigned char owner[kSpecRowCap];
+};
+
+__device__ __forceinline__ unsigned int warpInclusiveScan(unsigned int v, unsigned int lane)
+{
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1)
+    {
+        unsigned int const n = __shfl_up_sync(0xffffffffu, v, off);
+        if (lane >= static_cast<unsigned int>(off))
+            v += n;
+    }
+    return v;
+}
+
+// `mine` (len 0 = none) is this lane's cursor of the seed starting at `seedBegin` in frame `f`; lanes are
+// in the reference's consumption order.  hitsThisSeq stays uniform across the warp.
+__device__ __forceinline__ void seedConsumeChunkSpec(SeedParams const & P, signed char const * sM, SpecScratch & S,
+                                                     unsigned int lane, unsigned int q, unsigned long long qb,
+                                                     unsigned int origLen, unsigned long long needlesSum, Cursor mine,
+                                                     unsigned int f, unsigned int seedBegin, unsigned long long needlesPosF,
+                                                     unsigned long long & hitsThisSeq, unsigned long long & nAfter,
+                                                     unsigned long long & nFailed)
+{
+    DevIndex const &   ix     = P.ix;
+    unsigned int const F      = P.Q.F;
+    unsigned int const L      = P.seedLength;
+    unsigned int const ltMask = (1u << lane) - 1u;
+    unsigned int       pending = __ballot_sync(0xffffffffu, mine.len != 0);
+    if (!pending)
+        return;
+    unsigned int const    len = qryFrameLen(P.Q, origLen, f);
+    unsigned char const * red = P.Q.red + F * qb + static_cast<unsigned long long>(f) * origLen;
+
+    bool               haveEl = false;
+    Cursor             el     = mine;
+    unsigned int       elLen  = L;
+    unsigned long long lo = 1, hi = ~0ull;
+    while (pending)
+    {
+        unsigned long long const hits0     = hitsThisSeq;
+        bool const               isPending = (pending >> lane) & 1u;
+        if (isPending)
+        {
+            unsigned long long const desired =
+              P.adaptive ? seedDesiredOccs(P, hits0, needlesSum, needlesPosF, seedBegin) : 1ull;
+            if (!haveEl || desired < lo || desired > hi)
+            {
+                el    = mine;
+                elLen = L;
+                lo    = 1;
+                hi    = ~0ull;
+                if (P.adaptive)
+                {
+                    unsigned long long oldCount = el.len;
+                    while (seedBegin + elLen < len)
+                    {
+                        Cursor const n = fmExtendRight(ix, el, red[seedBegin + elLen] + 1u);
+                        if (n.len < oldCount)
+                        {
+                            if (n.len < desired)
+                            {
+                                lo = max(lo, n.len + 1); // same stop for every desired > n.len
+                                break;
+                            }
+                            hi = min(hi, n.len); // same continuation for every desired <= n.len
+                        }
+                        el       = n;
+                        oldCount = n.len;
+                        ++elLen;
+                    }
+                }
+                haveEl = true;
+            }
+        }
+        __syncwarp();
+        // over-abundant cursors are dropped (src/search_algo.hpp:729): no rows, but still validated in order
+        unsigned int const rows = (isPending && el.len <= 10ull * P.maxMatches) ? static_cast<unsigned int>(el.len) : 0u;
+        unsigned int const incl = warpInclusiveScan(rows, lane);
+        int const          head = __ffs(pending) - 1;
+        unsigned int const base0 = __shfl_sync(0xffffffffu, incl - rows, head);
+        bool const         inChunk   = isPending && (incl - base0 <= static_cast<unsigned int>(kSpecRowCap));
+        unsigned int const chunkMask = __ballot_sync(0xffffffffu, inChunk);
+        if (!((chunkMask >> head) & 1u))
+        {
+            // the head alone has more rows than a round can park; it is not speculative -> emit directly
+            Cursor hc;
+            hc.lb                      = __shfl_sync(0xffffffffu, el.lb, head);
+            hc.len                     = __shfl_sync(0xffffffffu, el.len, head);
+            unsigned int const hLen    = __shfl_sync(0xffffffffu, elLen, head);
+            unsigned int const hf      = __shfl_sync(0xffffffffu, f, head);
+            unsigned int const hsb     = __shfl_sync(0xffffffffu, seedBegin, head);
+            unsigned char const * htr  = P.Q.trans + F * qb + static_cast<unsigned long long>(hf) * origLen;
+            seedConsumeRows(P, sM, lane, q * F + hf, htr, qryFrameLen(P.Q, origLen, hf), hsb, hc, hLen, hitsThisSeq, nAfter,
+                            nFailed);
+            pending &= ~(1u << head);
+            continue;
+        }
+        int const          last = 31 - __clz(chunkMask);
+        unsigned int const R    = __shfl_sync(0xffffffffu, incl, last) - base0;
+        S.cnt[lane]             = 0;
+        __syncwarp();
+        for (unsigned int r0 = 0; r0 < R; r0 += 32)
+        {
+            unsigned int const r      = r0 + lane;
+            bool const         act    = r < R;
+            unsigned int const target = base0 + (act ? r : 0u);
+            // owner = first lane whose inclusive row count exceeds the row number
+            int j = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1)
+            {
+                unsigned int const v = __shfl_sync(0xffffffffu, incl, j + step - 1);
+                if (v <= target)
+                    j += step;
+            }
+            unsigned int const       oExcl = __shfl_sync(0xffffffffu, incl - rows, j);
+            unsigned long long const oLb   = __shfl_sync(0xffffffffu, el.lb, j);
+            unsigned int const       oLen  = __shfl_sync(0xffffffffu, elLen, j);
+            unsigned int const       oSb   = __shfl_sync(0xffffffffu, seedBegin, j);
+            unsigned int const       oF    = __shfl_sync(0xffffffffu, f, j);
+            bool                     pass  = false;
+            if (act)
+            {
+                unsigned long long subj, pos;
+                fmLocate(ix, oLb + (target - oExcl), subj, pos);
+                pos -= oLen;
+                unsigned char const * tr = P.Q.trans + F * qb + static_cast<unsigned long long>(oF) * origLen;
+                pass       = seedPreScore(P, sM, tr, qryFrameLen(P.Q, origLen, oF), oSb, oLen, subj, pos);
+                S.subj[r]  = static_cast<unsigned int>(subj);
+                S.pos[r]   = static_cast<unsigned int>(pos);
+                S.owner[r] = static_cast<unsigned char>(j);
+                if (pass)
+                    atomicAdd(&S.cnt[j], 1u);
+            }
+            unsigned int const pm = __ballot_sync(0xffffffffu, pass);
+            if (lane == 0)
+                S.passBits[r0 >> 5] = pm;
+        }
+        __syncwarp();
+        // ---- validation: true hitsThisSeq in front of every lane ----
+        unsigned int const myPass   = inChunk ? S.cnt[lane] : 0u;
+        unsigned int const inclPass = warpInclusiveScan(myPass, lane);
+        bool               ok       = true;
+        if (inChunk && P.adaptive)
+        {
+            unsigned long long const d = seedDesiredOccs(P, hits0 + inclPass - myPass, needlesSum, needlesPosF, seedBegin);
+            ok                         = d >= lo && d <= hi;
+        }
+        unsigned int const bad        = __ballot_sync(0xffffffffu, !ok) & chunkMask & ~(1u << head);
+        unsigned int const commitMask = bad ? (chunkMask & ((1u << (__ffs(bad) - 1)) - 1u)) : chunkMask;
+        int const          lastC      = 31 - __clz(commitMask);
+        unsigned int const Rc         = __shfl_sync(0xffffffffu, incl, lastC) - base0;
+        unsigned int const hitsAdd    = __shfl_sync(0xffffffffu, inclPass, lastC);
+        if (hitsAdd)
+        {
+            unsigned long long slot0 = 0;
+            if (lane == 0)
+                slot0 = atomicAdd(&P.counters[0], static_cast<unsigned long long>(hitsAdd));
+            slot0            = __shfl_sync(0xffffffffu, slot0, 0);
+            unsigned int run = 0;
+            for (unsigned int r0 = 0; r0 < Rc; r0 += 32)
+            {
+                unsigned int const r  = r0 + lane;
+                unsigned int       pm = S.passBits[r0 >> 5];
+                if (Rc - r0 < 32)
+                    pm &= (1u << (Rc - r0)) - 1u;
+                int const          j    = (r < Rc) ? static_cast<int>(S.owner[r]) : head;
+                unsigned int const oLen = __shfl_sync(0xffffffffu, elLen, j);
+                unsigned int const oSb  = __shfl_sync(0xffffffffu, seedBegin, j);
+                unsigned int const oF   = __shfl_sync(0xffffffffu, f, j);
+                if ((pm >> lane) & 1u)
+                {
+                    unsigned long long const slot = slot0 + run + __popc(pm & ltMask);
+                    if (slot < P.cap)
+                    {
+                        lgpu_match m;
+                        m.qry_id     = q * F + oF;
+                        m.subj_id    = S.subj[r];
+                        m.qry_start  = oSb;
+                        m.qry_end    = oSb + oLen;
+                        m.subj_start = S.pos[r];
+                        m.subj_end   = S.pos[r] + oLen;
+                        P.out[slot]  = m;
+                    }
+                }
+                run += __popc(pm);
+            }
+        }
+        if (lane == 0)
+        {
+            nAfter += Rc;
+            nFailed += Rc - hitsAdd;
+        }
+        hitsThisSeq += hitsAdd;
+        pending &= ~commitMask;
+        __syncwarp();
     }
 }
 
@@ -937,6 +1185,123 @@ __global__ void __launch_bounds__(128) seedWarpKernel(SeedParams P)
 }
 
 // ---------------------------------------------------------------------------------------------
+// seeding, one WARP per query, cursors consumed speculatively 32 at a time (the default)
+// ---------------------------------------------------------------------------------------------
+// Exact seeds (phase 1): the 32 lanes take 32 consecutive seeds of the query, each lane walks its own
+// exact chain (all lanes issue their LF steps together: 32 independent block reads per instruction
+// instead of 32 threads diverged over LF / locate / pre-scoring), then seedConsumeChunkSpec.
+// Half-exact seeds (phase 2): per seed the exact chain is computed by all lanes, the leaves of the
+// mismatch tree are evaluated 32 at a time and handed to seedConsumeChunkSpec in leaf order.
+constexpr int kSpecWarps = 4;
+
+__global__ void __launch_bounds__(32 * kSpecWarps) seedSpecKernel(SeedParams P)
+{
+    __shared__ signed char sM[2048];
+    __shared__ SpecScratch sS[kSpecWarps];
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x)
+        sM[i] = P.matrix[i];
+    __syncthreads();
+
+    unsigned int const lane = threadIdx.x & 31u;
+    unsigned int const w    = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= P.nActive)
+        return;
+    SpecScratch &            S       = sS[threadIdx.x >> 5];
+    unsigned int const       q       = P.active[w];
+    DevIndex const &         ix      = P.ix;
+    unsigned int const       F       = P.Q.F;
+    unsigned long long const qb      = P.Q.offs[q];
+    unsigned int const       origLen = static_cast<unsigned int>(P.Q.offs[q + 1] - qb);
+    unsigned int const       L       = P.seedLength;
+    unsigned int const       redN    = ix.sigma - 1;
+
+    unsigned long long nAfter = 0, nFailed = 0; // per lane
+    if (qryFrameLen(P.Q, origLen, 0) >= L)
+    {
+        unsigned long long hitsThisSeq = 0;
+        unsigned long long needlesSum  = 0;
+        for (unsigned int f = 0; f < F; ++f)
+            needlesSum += qryFrameLen(P.Q, origLen, f);
+        unsigned long long needlesPos = 0;
+        bool const         half       = P.halfExact && P.maxSeedDist != 0;
+        unsigned int const h1         = half ? L / 2 : L;
+        unsigned int const n2         = L - h1;
+
+        for (unsigned int f = 0; f < F; ++f)
+        {
+            unsigned int const len = qryFrameLen(P.Q, origLen, f);
+            if (len < L)
+                continue;
+            unsigned char const * trans = P.Q.trans + F * qb + static_cast<unsigned long long>(f) * origLen;
+            unsigned char const * red   = P.Q.red + F * qb + static_cast<unsigned long long>(f) * origLen;
+            if (!half)
+            {
+                unsigned int seedBegin = 0;
+                bool         more      = true;
+                while (more)
+                {
+                    // the next 32 seed starts (every lane runs the same scan and keeps its own)
+                    unsigned int mySeed = 0xffffffffu;
+                    for (unsigned int t = 0; t < 32; ++t)
+                    {
+                        if (!seedNextStart(trans, len, L, P.unknownRank, seedBegin))
+                        {
+                            more = false;
+                            break;
+                        }
+                        if (lane == t)
+                            mySeed = seedBegin;
+                        seedBegin += P.seedOffset;
+                    }
+                    Cursor c;
+                    c.lb  = 0;
+                    c.len = 0;
+                    if (mySeed != 0xffffffffu)
+                    {
+                        c.len = ix.nRows;
+                        for (unsigned int i = 0; i < L && c.len != 0; ++i)
+                            c = fmExtendRight(ix, c, red[mySeed + i] + 1u);
+                    }
+                    else
+                        mySeed = 0;
+                    __syncwarp();
+                    seedConsumeChunkSpec(P, sM, S, lane, q, qb, origLen, needlesSum, c, f, mySeed, needlesPos, hitsThisSeq,
+                                         nAfter, nFailed);
+                }
+            }
+            else
+            {
+                for (unsigned int seedBegin = 0;; seedBegin += P.seedOffset)
+                {
+                    if (!seedNextStart(trans, len, L, P.unknownRank, seedBegin))
+                        break;
+                    Cursor    E[kMaxHalf2 + 1];
+                    int const K = seedExactChain(ix, red, seedBegin, h1, n2, E);
+                    if (K < 0)
+                        continue;
+                    int const          kMax     = (K < static_cast<int>(n2) - 1) ? K : static_cast<int>(n2) - 1;
+                    bool const         hasExact = (K == static_cast<int>(n2));
+                    unsigned int const nLeaves  = static_cast<unsigned int>(kMax + 1) * (redN - 1) + (hasExact ? 1u : 0u);
+                    for (unsigned int base = 0; base < nLeaves; base += 32)
+                    {
+                        Cursor mine;
+                        mine.lb  = 0;
+                        mine.len = 0;
+                        if (base + lane < nLeaves)
+                            mine = seedLeaf(ix, E, red, seedBegin, h1, n2, kMax, hasExact, redN, base + lane);
+                        __syncwarp();
+                        seedConsumeChunkSpec(P, sM, S, lane, q, qb, origLen, needlesSum, mine, f, seedBegin, needlesPos,
+                                             hitsThisSeq, nAfter, nFailed);
+                    }
+                }
+            }
+            needlesPos += len;
+        }
+    }
+    seedFlushCounters(P, lane, nAfter, nFailed);
+}
+
+// ---------------------------------------------------------------------------------------------
 // seeding, one BLOCK per query (few queries: latency matters, not throughput)
 // ---------------------------------------------------------------------------------------------
 // The cursors of different seeds do not depend on each other -- only their consumption does (through
@@ -960,6 +1325,7 @@ __global__ void __launch_bounds__(32 * kSeedBlockWarps) seedBlockKernel(SeedPara
     __shared__ signed char  sM[2048];
     __shared__ unsigned int sSeed[kSeedBlockMaxSeeds]; // frame << 24 | seedBegin
     __shared__ unsigned int sNumSeeds;
+    __shared__ SpecScratch  sSpec;
     __shared__ unsigned long long sNeedlesPos[8], sNeedlesSum;
     for (int i = threadIdx.x; i < 2048; i += blockDim.x)
         sM[i] = P.matrix[i];
@@ -1042,26 +1408,42 @@ __global__ void __launch_bounds__(32 * kSeedBlockWarps) seedBlockKernel(SeedPara
     }
     __syncthreads();
 
-    // ---- phase B: warp 0 consumes the seeds in order ----
+    // ---- phase B: warp 0 consumes the parked cursors in order, 32 at a time (speculatively) ----
     if (warp != 0)
         return;
     unsigned long long nAfter = 0, nFailed = 0;
     unsigned long long hitsThisSeq = 0;
     unsigned long long const needlesSum = sNeedlesSum;
-    for (unsigned int k = 0; k < nSeeds; ++k)
+    unsigned int k = 0, ci = 0;
+    for (;;)
     {
-        unsigned int const    f         = sSeed[k] >> 24;
-        unsigned int const    seedBegin = sSeed[k] & 0xffffffu;
-        unsigned int const    len       = qryFrameLen(P.Q, origLen, f);
-        unsigned char const * trans     = P.Q.trans + F * qb + static_cast<unsigned long long>(f) * origLen;
-        unsigned char const * red       = P.Q.red + F * qb + static_cast<unsigned long long>(f) * origLen;
-        unsigned int const    n         = myCnt[k];
-        for (unsigned int ci = 0; ci < n; ++ci)
+        Cursor mine;
+        mine.lb  = 0;
+        mine.len = 0;
+        unsigned int myF = 0, mySb = 0, got = 0;
+        while (got < 32 && k < nSeeds)
         {
-            Cursor const cursor = myCur[static_cast<unsigned long long>(k) * S.maxLeaves + ci];
-            seedConsumeCursor(P, sM, lane, q * F + f, trans, red, len, seedBegin, cursor, hitsThisSeq, needlesSum,
-                              sNeedlesPos[f], nAfter, nFailed);
+            unsigned int const n    = myCnt[k];
+            unsigned int const take = min(n - ci, 32u - got);
+            if (lane >= got && lane < got + take)
+            {
+                mine = myCur[static_cast<unsigned long long>(k) * S.maxLeaves + ci + (lane - got)];
+                myF  = sSeed[k] >> 24;
+                mySb = sSeed[k] & 0xffffffu;
+            }
+            got += take;
+            ci += take;
+            if (ci == n)
+            {
+                ++k;
+                ci = 0;
+            }
         }
+        if (!got)
+            break;
+        __syncwarp();
+        seedConsumeChunkSpec(P, sM, sSpec, lane, q, qb, origLen, needlesSum, mine, myF, mySb, sNeedlesPos[myF], hitsThisSeq,
+                             nAfter, nFailed);
     }
     seedFlushCounters(P, lane, nAfter, nFailed);
 }

@@ -17,7 +17,7 @@
 #define CHECK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { fprintf(stderr, "%s: %s\n", #x, cudaGetErrorString(e)); return 1; } } while (0)
 
 constexpr int ITER = 64;
-constexpr int ILP  = 4;
+constexpr int ILP  = 8;
 
 __device__ __forceinline__ unsigned long long mix(unsigned long long x)
 {
@@ -41,7 +41,7 @@ __global__ void gather(unsigned char const * __restrict__ buf, unsigned long lon
         for (int i = 0; i < ILP; ++i)
         {
             unsigned long long const h = mix(seed + tid * (ITER * ILP) + it * ILP + i);
-            unsigned long long const u = h % nUnits;
+            unsigned long long const u = h & (nUnits - 1); // nUnits is a power of two
             if (MODE == 0)
             {
                 uint4 const * p = reinterpret_cast<uint4 const *>(buf + u * 32);
@@ -66,7 +66,7 @@ __global__ void gather(unsigned char const * __restrict__ buf, unsigned long lon
             else if (MODE == 3)
             {
                 unsigned char const *      b = buf + u * 80;
-                unsigned int const         s = static_cast<unsigned int>(h >> 40) % 11u;
+                unsigned int const         s = (static_cast<unsigned int>(h >> 40) & 7u) + 1u;
                 unsigned int const         c = __ldg(reinterpret_cast<unsigned int const *>(b) + s);
                 unsigned long long const * pl = reinterpret_cast<unsigned long long const *>(b + 48);
                 acc += c + (__ldg(pl) ^ __ldg(pl + 1) ^ __ldg(pl + 2) ^ __ldg(pl + 3));
@@ -74,7 +74,7 @@ __global__ void gather(unsigned char const * __restrict__ buf, unsigned long lon
             else
             {
                 unsigned char const * b = buf + u * 64;
-                unsigned int const    s = static_cast<unsigned int>(h >> 40) % 11u;
+                unsigned int const    s = (static_cast<unsigned int>(h >> 40) & 7u) + 1u;
                 uint4 const *         p = reinterpret_cast<uint4 const *>(b);
                 uint4 const           a = __ldg(p), d = __ldg(p + 1);
                 unsigned int const    c = __ldg(reinterpret_cast<unsigned short const *>(b + 32) + s);
@@ -90,7 +90,9 @@ template <int MODE>
 static int run(char const * name, unsigned char const * buf, unsigned long long bytes, unsigned unit, unsigned useful,
                unsigned long long * out, int sms, bool last)
 {
-    unsigned long long const nUnits = bytes / unit;
+    unsigned long long nUnits = 1;
+    while (nUnits * 2 * unit <= bytes)
+        nUnits *= 2;
     int const blocks = sms * 64, threads = 256;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);

@@ -60,7 +60,7 @@ def test_fm_rank_and_locate(golden_dir, case, domain):
     ix.close()
 
 
-@pytest.mark.parametrize("mode", ["thread", "warp", "block"])
+@pytest.mark.parametrize("mode", ["thread", "warp", "block", "spec"])
 @pytest.mark.parametrize("case,domain,profile", CASE_PROFILES)
 def test_seeding_matches_oracle(golden_dir, case, domain, profile, mode, monkeypatch):
     """all three seeding kernels (thread / warp / block per query) against the oracle, both phases"""
@@ -209,7 +209,7 @@ def test_score_kernel_all_length_classes(golden_dir):
     s.close(); ix.close(); o.close()
 
 
-@pytest.mark.parametrize("mode", ["auto", "thread", "warp"])
+@pytest.mark.parametrize("mode", ["auto", "thread", "warp", "spec"])
 @pytest.mark.parametrize("case,domain,profile", CASE_PROFILES)
 def test_search_reproduces_reference_output(golden_dir, case, domain, profile, mode, monkeypatch):
     monkeypatch.setenv("LAMBDA_B200_SEED", mode)
