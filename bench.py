@@ -248,7 +248,7 @@ def main():
     workload = (f"{wl}: {args.n_queries}x{args.qlen}{W['unit']} synthetic queries vs {args.n_seqs}-seq {W['what']}, "
                 f"default profile")
     cfg = {"workload": workload, "queries_per_gpu": args.n_queries, "query_len": args.qlen, "index_seqs": args.n_seqs,
-           "profile": "none", "sharding": f"queries x{n_gpus}, index replicated", "streams_per_gpu": 2,
+           "profile": "none", "sharding": f"queries x{n_gpus}, index replicated", "streams_per_gpu": 3,
            "l2_policy": "inputs larger than L2 (index and per-step trace/DP working sets are GBs)"}
     cores = os.cpu_count() or 1
 
@@ -290,7 +290,7 @@ def main():
     t0 = time.time()
     ix = lambda_b200.Index.load(os.path.join(d, "db.lba"), device=local_rank, keep_ids=(rank == 0))
     log(f"rank {rank}: index in HBM: {ix.device_bytes / 1e9:.2f} GB, load {time.time() - t0:.1f}s")
-    s = lambda_b200.Searcher(ix, W["domain"])              # default: 2 sub-batches in flight
+    s = lambda_b200.Searcher(ix, W["domain"])              # default: 3 sub-batches in flight
     s_serial = lambda_b200.Searcher(ix, W["domain"], streams=1)  # strictly serial: per-kernel timing / roofline
     q_ascii, qoffs = make_queries(wl, d, args.n_queries, args.qlen, seed=1000 + rank)
     res = lambda_b200.encode(q_ascii, W["dom"])

@@ -32,10 +32,11 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise ImportError(f"{LIB_PATH} is missing: build it with `python -m lambda_b200.build` "
+    path = os.environ.get("LAMBDA_B200_LIB", LIB_PATH)  # kernel experiments: an alternative build of the same library
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: build it with `python -m lambda_b200.build` "
                           "(lambda_b200 has no CPU fallback)")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int
     lib.lgpu_version.restype = i32
     lib.lgpu_lba_open.argtypes = [C.POINTER(vp), C.c_char_p]

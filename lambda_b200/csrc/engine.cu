@@ -200,7 +200,9 @@ struct lgpu_ctx
     DevBuf<int>                dScores, dScores2, dMinBit, dMinEval;
     DevBuf<unsigned int>       dWork, dBestPos, dBoundary, dOrder, dOrderB, dClassInfo, dSegStart, dSegStartB, dJobHead, dJobPos, dJobs;
     DevBuf<unsigned long long> dClassKeys, dClassKeysB;
-    bool                       dpxOk = false; // scoring fits the int8 profile of the DPX kernel
+    bool                       dpxOk = false; // scoring fits the int8 profile of the DPX kernels
+    unsigned int               dpxBlocksPerSM = 32; // resident warps of the DP score kernel per SM (LAMBDA_B200_DPX_OCC)
+    bool                       dpxScoreOk = false; // ... and every matrix entry >= gap open (score kernel: profile bytes >= 0)
     unsigned int               streams = 1;  // sub-batches in flight per lgpu_search_batch call (LAMBDA_B200_STREAMS)
     std::vector<std::unique_ptr<lgpu_ctx>> workers;
     int                        seedMode = 0; // LAMBDA_B200_SEED=thread|warp|block|spec forces one seeding kernel (tests); 0 = auto
@@ -598,7 +600,7 @@ static void launchDpx(lgpu_ctx & c, DpxParams P, unsigned int maxNt)
     LGPU_CUDA(cudaFuncSetAttribute(swScoreDpxKernel<T, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if (smem > 227 * 1024)
         throw CudaError("DPX score kernel: window too long for shared memory");
-    unsigned int const grid = std::min<unsigned int>(P.nJobs, static_cast<unsigned int>(c.numSMs) * 32);
+    unsigned int const grid = std::min<unsigned int>(P.nJobs, static_cast<unsigned int>(c.numSMs) * c.dpxBlocksPerSM);
     swScoreDpxKernel<T, K><<<grid, 32, smem, c.stream>>>(P);
     LGPU_CUDA(cudaGetLastError());
 }
@@ -665,7 +667,7 @@ static void runScorePass(lgpu_ctx & c, lgpu_match const * dTasks, unsigned int n
         unsigned int const cnt = info[cls], maxNt = info[NC + cls], nJobs = info[2 * NC + cls];
         if (cnt == 0)
             continue;
-        bool const scalar = (cls == kNumDpxClasses) || !c.dpxOk;
+        bool const scalar = (cls == kNumDpxClasses) || !c.dpxScoreOk;
         if (!scalar)
         {
             DpxParams P{};
@@ -1154,7 +1156,14 @@ static void searchBatch(lgpu_ctx & c, lgpu_query_batch const & qb, lgpu_hits * o
     else
     {
         while (c.workers.size() < nW)
+        {
             c.workers.push_back(makeContext(c.index, c.params));
+            // Sub-batches share the GPU: the ALU-bound DP score kernel leaves shared memory and warp slots
+            // for the memory-bound stages (seeding, trace fill, traceback) of the other sub-batches
+            // (measured: profiles/r1_sweep_streams.jsonl).
+            if (!std::getenv("LAMBDA_B200_DPX_OCC"))
+                c.workers.back()->dpxBlocksPerSM = 10;
+        }
         std::vector<std::vector<uint64_t>> subOffs(nW);
         std::vector<lgpu_stats>            wst(nW);
         std::vector<std::string>           err(nW);
@@ -1286,9 +1295,12 @@ static std::unique_ptr<lgpu_ctx> lgpu::makeContext(lgpu_index const * ix, lgpu_p
     c->dCounters.reserve(8);
     if (char const * e = std::getenv("LAMBDA_B200_SEED"))
         c->seedMode = !std::strcmp(e, "thread") ? 1 : !std::strcmp(e, "warp") ? 2 : !std::strcmp(e, "block") ? 3 : !std::strcmp(e, "spec") ? 4 : 0;
+    if (char const * e = std::getenv("LAMBDA_B200_DPX_OCC"))
+        c->dpxBlocksPerSM = static_cast<unsigned int>(std::max(1, std::min(32, std::atoi(e))));
     if (char const * e = std::getenv("LAMBDA_B200_TRACE"))
         c->forceScalarTrace = !std::strcmp(e, "scalar");
     // the packed kernel stores (score - gapOpen) as int8 profile bytes with -128 reserved for "null"
+    bool nonNeg = true;
     c->dpxOk = c->scoring.alphSize < 32 && c->scoring.gapOpenSeqan <= c->scoring.gapExtend && c->scoring.gapExtend <= 0;
     for (int a = 0; a < c->scoring.alphSize; ++a)
         for (int b = 0; b < c->scoring.alphSize; ++b)
@@ -1297,7 +1309,11 @@ static std::unique_ptr<lgpu_ctx> lgpu::makeContext(lgpu_index const * ix, lgpu_p
             int const w = c->scoring.matrixRev[a * 32 + b] - c->scoring.gapOpenSeqan;
             if (v < -127 || v > 127 || w < -127 || w > 127)
                 c->dpxOk = false;
+            if (v < 0 || w < 0)
+                nonNeg = false;
         }
+    // the score kernel adds the profile bytes with a plain 32-bit add: they must not be negative
+    c->dpxScoreOk = c->dpxOk && (LGPU_DPX_FORM == 0 || nonNeg);
     return c;
 }
 
@@ -1433,7 +1449,7 @@ int lgpu_ctx_create(lgpu_ctx ** out, lgpu_index const * ix, lgpu_params const * 
     return guarded(nullptr, [&] {
         auto c = makeContext(ix, *p);
         // sub-batches in flight per search call; worker contexts are created on first use
-        c->streams = 2;
+        c->streams = 3;
         if (char const * e = std::getenv("LAMBDA_B200_STREAMS"))
             c->streams = static_cast<unsigned int>(std::max(1, std::min(8, std::atoi(e))));
         *out = c.release();

@@ -2,25 +2,33 @@
 //
 // Same recurrence as the reference's SIMD pass (_performAlignment<withTrace=false>,
 // src/search_algo.hpp:1246; SQ/align/dp_formula_affine.h:66-126), restated so that one cell update is
-// five VIADDMNMX/VIADD.16x2 + one VIMNMX on two int16 lanes, plus one PRMT that builds the operand:
+// four half-rate DPX instructions + one full-rate VIMNMX + half a VIMNMX3 on two int16 lanes, one PRMT that builds the
+// operand and one plain 32-bit add that runs on the other (FMA/IMAD) pipe:
 //
-//   W     = H + go                         ("tmp": the only form H is stored in)
-//   t     = max(Wdiag + sub'', E, 0)       VIADDMNMX.S16x2.RELU   sub'' = M[q][s] - go   (one int8 profile byte)
-//   u     = t + go                         VIADD.16x2
-//   W     = max(F + go, u)                 VIADDMNMX.S16x2        (= max(t, F) + go = H + go)
-//   F'    = max(F + ge, u)                 VIADDMNMX.S16x2        (valid because go <= ge)
-//   E'    = max(E + ge, W)                 VIADDMNMX.S16x2
-//   best  = max(best, W)                   VIMNMX.S16x2           score = best - go
+//   E^ = E - go, F^ = F - go                 (the gap states are kept shifted; E^, F^ >= 0)
+//   y   = Hdiag + sub'                       IADD (32 bit)          sub' = M[q][s] - go  (one profile byte, >= 0)
+//   t   = max(y, E^)                         VIMNMX.S16x2 (full rate)
+//   Ht  = max(t + go, 0)                     VIADDMNMX.S16x2.RELU   = max(Hdiag + sub, E, 0)
+//   H   = max(F^ + go, Ht)                   VIADDMNMX.S16x2
+//   F^' = max(F^ + ge, Ht)                   VIADDMNMX.S16x2        (= max(F^ + ge, H) because go <= ge;
+//                                                                    the only op on the row's dependency chain)
+//   E^' = max(E^ + ge, H)                    VIADDMNMX.S16x2
+//   best = max(best, H, H of the next cell)  VIMNMX3.S16x2 every other cell
+//
+// The 32-bit add is exact on both halves because H >= 0 and sub' >= 0 (checked on the host: every matrix
+// entry >= go), so the low half never carries.  Negative gap states never matter (H is clamped at 0 and
+// E', F' are then dominated by H + go), so starting E^ = F^ = 0 instead of -inf changes nothing.
 //
 // Work decomposition: a group of T threads (8/16/32) owns one alignment.  The query is cut into 2T
 // strips of K columns; thread p holds strip p in the low int16 half and strip p + T in the high half
 // of every register, so both halves are always busy on different cells of the SAME alignment (no
 // pairing of alignments, no length mismatch).  Strip v works on subject row j = s - v at step s: the
 // 2T strips form an anti-diagonal wavefront, and the only communication per step is the rotation of
-// (W, F) of a strip's last column to the next strip (two shuffles).  Rows outside the window and
-// columns past the query end use a "null" profile entry of -128: it can never raise a cell above a
-// value that already exists, so no masking is needed anywhere in the inner loop and all groups of a
-// warp can simply run for the longest window among them.
+// (H, F^) of a strip's last column to the next strip (two shuffles).  Rows outside the window and
+// columns past the query end use a "null" profile entry sub' = 0 (a substitution score of go): such a
+// cell is max(Hdiag + go, E, F, 0), which can never exceed a value that already exists and leaves the
+// all-zero state in front of the window untouched, so no masking is needed anywhere in the inner loop
+// and all groups of a warp can simply run for the longest window among them.
 //
 // Shared memory per group: the query profile P[code][word][strip] (int8, row stride a multiple of 32
 // words so the 4-byte loads of a warp are bank-conflict free) and the padded subject window.
@@ -72,6 +80,21 @@ __host__ __device__ constexpr int dpxRowWords(int T, int K)
 // share one profile
 constexpr unsigned int kDpxSegShift = 20;
 
+// Inner-loop formulation (compile-time experiment switch; see the header comment):
+//   0  W = H + go stored, 6.5 ALU-pipe instructions per cell pair, profile null = -128
+//   1  shifted gap states, VIMNMX3 on the row's dependency chain (3 ops deep), 5.5 per cell pair
+//   2  shifted gap states, one op on the dependency chain, 6.0 per cell pair
+#ifndef LGPU_DPX_FORM
+#define LGPU_DPX_FORM 0
+#endif
+#if LGPU_DPX_FORM == 0
+constexpr unsigned int kDpxNullWord = 0x80808080u;
+constexpr int          kDpxNullVal  = -128;
+#else
+constexpr unsigned int kDpxNullWord = 0u; // null: sub' = 0
+constexpr int          kDpxNullVal  = 0;
+#endif
+
 // A job = up to G = 32/T consecutive (sorted) alignments of the SAME query: the warp builds the query
 // profile once in shared memory and its G groups run one alignment each against it.
 template <int T, int K>
@@ -93,7 +116,6 @@ __global__ void __launch_bounds__(32) swScoreDpxKernel(DpxParams P)
 
     unsigned int const go2  = (static_cast<unsigned int>(P.go) & 0xffffu) * 0x10001u;
     unsigned int const ge2  = (static_cast<unsigned int>(P.ge) & 0xffffu) * 0x10001u;
-    unsigned int const neg2 = 0xC000C000u; // -16384 in both halves
 
     for (;;)
     {
@@ -151,7 +173,7 @@ __global__ void __launch_bounds__(32) swScoreDpxKernel(DpxParams P)
             unsigned int const rem = idx % ROWW;
             unsigned int const w   = rem / (2 * T);
             unsigned int const v   = rem % (2 * T);
-            unsigned int       word = 0x80808080u; // null = -128
+            unsigned int       word = kDpxNullWord;
             if (c != nullCode && w < KW)
             {
                 word = 0;
@@ -160,7 +182,7 @@ __global__ void __launch_bounds__(32) swScoreDpxKernel(DpxParams P)
                 {
                     unsigned int const r = w * 4 + b;
                     unsigned int const i = v * K + r;
-                    int                val = -128;
+                    int                val = kDpxNullVal;
                     if (r < K && i < nq)
                         val = static_cast<int>(M[qs[i] * 32 + c]) - P.go;
                     word |= (static_cast<unsigned int>(val) & 0xffu) << (8 * b);
@@ -179,15 +201,21 @@ __global__ void __launch_bounds__(32) swScoreDpxKernel(DpxParams P)
         }
         __syncwarp();
 
-        unsigned int E[K], W[K];
+#if LGPU_DPX_FORM == 0
+        unsigned int const neg2 = 0xC000C000u; // -16384 in both halves
+        unsigned int const init = go2, initE = neg2, border = go2, borderF = neg2;
+#else
+        unsigned int const init = 0u, initE = 0u, border = 0u, borderF = 0u;
+#endif
+        unsigned int E[K], H[K]; // form 0: H holds W = H + go
 #pragma unroll
         for (int r = 0; r < K; ++r)
         {
-            E[r] = neg2;
-            W[r] = go2; // H = 0
+            E[r] = initE;
+            H[r] = init;
         }
-        unsigned int best = go2;
-        unsigned int outW = go2, outF = neg2, diagIn = go2;
+        unsigned int best = init;
+        unsigned int outH = init, outF = initE, diagIn = init;
 
         // profile words of the current step (software pipelined one step ahead)
         unsigned int wl[KW], wh[KW];
@@ -215,35 +243,50 @@ __global__ void __launch_bounds__(32) swScoreDpxKernel(DpxParams P)
                     nh[k] = prof[cHi * ROWW + k * 2 * T + T + gl];
                 }
             }
-            // (W, F) of the left strip's last column for the row this strip works on now
-            unsigned int inW = __shfl_sync(0xffffffffu, outW, (lane - 1) & (T - 1), T);
+            // (H, F^) of the left strip's last column for the row this strip works on now
+            unsigned int inH = __shfl_sync(0xffffffffu, outH, (lane - 1) & (T - 1), T);
             unsigned int inF = __shfl_sync(0xffffffffu, outF, (lane - 1) & (T - 1), T);
             if (gl == 0)
             {
                 // strip 0 sees the matrix border (H = 0, no horizontal gap); strip T continues strip T-1
-                inW = prmt(go2, inW, 0x5410);
-                inF = prmt(neg2, inF, 0x5410);
+                inH = prmt(border, inH, 0x5410);
+                inF = prmt(borderF, inF, 0x5410);
             }
-            unsigned int diag = diagIn; // W of the left strip at the previous row
-            diagIn            = inW;
+            unsigned int diag = diagIn; // H of the left strip at the previous row
+            diagIn            = inH;
             unsigned int F    = inF;
 #pragma unroll
             for (int r = 0; r < K; ++r)
             {
-                // {sext(lo byte), sext(hi byte)} of column r: selector nibble bit 3 replicates the sign
+                // {lo byte, hi byte} of column r, each widened to 16 bits (values are 0 .. 127)
                 unsigned int const b   = r & 3;
                 unsigned int const sel = ((0xCu + b) << 12) | ((4u + b) << 8) | ((8u + b) << 4) | b;
                 unsigned int const sub = prmt(wl[r >> 2], wh[r >> 2], sel);
+#if LGPU_DPX_FORM == 0
                 unsigned int const t   = __viaddmax_s16x2_relu(diag, sub, E[r]);
                 unsigned int const u   = __vadd2(t, go2);
-                unsigned int const w   = __viaddmax_s16x2(F, go2, u);
+                unsigned int const h   = __viaddmax_s16x2(F, go2, u);
                 F                      = __viaddmax_s16x2(F, ge2, u);
-                E[r]                   = __viaddmax_s16x2(E[r], ge2, w);
-                diag                   = W[r];
-                W[r]                   = w;
-                best                   = __vmaxs2(best, w);
+                E[r]                   = __viaddmax_s16x2(E[r], ge2, h);
+#elif LGPU_DPX_FORM == 1
+                unsigned int const y   = diag + sub; // both halves non-negative: no carry across the halves
+                unsigned int const m   = __vimax3_s16x2(y, E[r], F);
+                unsigned int const h   = __viaddmax_s16x2_relu(m, go2, 0u);
+                F                      = __viaddmax_s16x2(F, ge2, h);
+                E[r]                   = __viaddmax_s16x2(E[r], ge2, h);
+#else
+                unsigned int const y   = diag + sub; // both halves non-negative: no carry across the halves
+                unsigned int const t   = __vmaxs2(y, E[r]);
+                unsigned int const ht  = __viaddmax_s16x2_relu(t, go2, 0u); // max(Hdiag + sub, E, 0)
+                unsigned int const h   = __viaddmax_s16x2(F, go2, ht);      // ... and F
+                F                      = __viaddmax_s16x2(F, ge2, ht);      // = max(F^ + ge, H) because go <= ge
+                E[r]                   = __viaddmax_s16x2(E[r], ge2, h);
+#endif
+                diag                   = H[r];
+                H[r]                   = h;
+                best                   = __vmaxs2(best, h);
             }
-            outW = W[K - 1];
+            outH = H[K - 1];
             outF = F;
 #pragma unroll
             for (int k = 0; k < KW; ++k)
@@ -258,7 +301,7 @@ __global__ void __launch_bounds__(32) swScoreDpxKernel(DpxParams P)
         for (int off = T / 2; off > 0; off >>= 1)
             b = max(b, __shfl_xor_sync(0xffffffffu, b, off));
         if (valid && gl == 0)
-            P.scores[task] = b - P.go;
+            P.scores[task] = b - (LGPU_DPX_FORM == 0 ? P.go : 0);
     }
 }
 
