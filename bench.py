@@ -49,11 +49,19 @@ WORKLOADS = {
     # BASELINE.json configs[2]: n_seqs = chromosomes of 1 Mbp each (200 Mbp)
     "searchn": dict(domain="nucleotide", dom=1, mk="mkindexn", search="searchn", n_seqs=200, n_queries=1_000_000,
                     qlen=150, unit="bp", what="x1Mbp synthetic nucleotide index (dna4), match 2 / mismatch -3"),
+    # BASELINE.json configs[4]: bisulfite reads vs a 50 Mbp genome (the index holds the C->T and G->A texts)
+    "searchbs": dict(domain="bisulfite", dom=2, mk="mkindexbs", search="searchbs", n_seqs=50, n_queries=500_000,
+                     qlen=100, unit="bp", what="x1Mbp synthetic genome, bisulfite index (dna3bs), C->T converted reads"),
+    # BASELINE.json configs[3] (parity mode): real length distribution against the searchp index
+    "searchp_real": dict(domain="protein", dom=0, mk="mkindexp", search="searchp", n_seqs=5_000_000, n_queries=10_000,
+                         qlen=0, unit="aa", what="synthetic protein index (Li10), BLOSUM62, log-normal query lengths "
+                                                  "(median 270, 50..2000)", index_of="searchp"),
 }
 CHROM_LEN = 1_000_000
 
 
 def workload_dir(wl, n_seqs, seed):
+    wl = WORKLOADS[wl].get("index_of", wl)
     key = hashlib.sha1(f"{wl}-flat-{n_seqs}-{seed}-v2".encode()).hexdigest()[:12]
     return os.path.join(CACHE, f"{wl}_{n_seqs}_{key}")
 
@@ -84,7 +92,7 @@ def ensure_index(wl, n_seqs, seed=1):
             raise RuntimeError(f"{REF} missing: run `python -c 'import __graft_entry__ as g; g.build()'` where "
                                "/root/reference is available (the binary travels with the repo snapshot)")
         t0 = time.time()
-        if wl == "searchp":
+        if W["dom"] == 0:
             db, offs = synth.protein_db(n_seqs, seed=seed)
         else:
             db, offs = synth.nucl_db(n_seqs, CHROM_LEN, seed=seed)
@@ -117,6 +125,22 @@ def make_queries(wl, d, n_queries, qlen, seed):
     seq_start = rec_start[:-1] + idlen
     rng = np.random.default_rng(seed)
     lens = np.diff(offs)
+    if qlen == 0:
+        # real length distribution: every query is a mutated window of a database sequence at least as long
+        want = synth._protein_lengths(rng, n_queries)
+        order = np.argsort(lens)
+        first = np.searchsorted(lens[order], want)  # sequences order[first:] are long enough
+        pick = order[first + (rng.random(n_queries) * (len(order) - first)).astype(np.int64)]
+        start = seq_start[pick] + (rng.random(n_queries) * (lens[pick] - want + 1)).astype(np.int64)
+        qoffs = np.zeros(n_queries + 1, np.uint64)
+        np.cumsum(want, out=qoffs[1:].view(np.int64))
+        out = np.empty(int(qoffs[-1]), np.uint8)
+        for i in range(n_queries):
+            seq = np.array(fa[start[i]:start[i] + want[i]])
+            m = rng.random(len(seq)) < rng.uniform(0.15, 0.20)
+            seq[m] = synth._random_residues(rng, int(m.sum()))
+            out[int(qoffs[i]):int(qoffs[i + 1])] = seq
+        return out, qoffs
     elig = np.nonzero(lens >= qlen)[0]
     pick = elig[rng.integers(0, len(elig), n_queries)]
     start = seq_start[pick] + (rng.random(n_queries) * (lens[pick] - qlen + 1)).astype(np.int64)
@@ -125,6 +149,14 @@ def make_queries(wl, d, n_queries, qlen, seed):
     for b in range(0, n_queries, step):
         e = min(n_queries, b + step)
         q[b:e] = fa[start[b:e, None] + np.arange(qlen)[None, :]]
+    if wl == "searchbs":
+        conv = (q == ord("C")) & (rng.random(q.shape, dtype=np.float32) < 0.95)
+        q[conv] = ord("T")
+        m = rng.random(q.shape, dtype=np.float32) < 0.01
+        q[m] = synth.NT[rng.integers(0, 4, int(m.sum()), dtype=np.uint8)]
+        odd = np.arange(n_queries) % 2 == 1
+        q[odd] = synth._COMP[q[odd][:, ::-1]]
+        return q.reshape(-1), np.arange(n_queries + 1, dtype=np.uint64) * qlen
     if wl == "searchn":
         m = rng.random(q.shape, dtype=np.float32) < 0.03
         q[m] = synth.NT[rng.integers(0, 4, int(m.sum()), dtype=np.uint8)]
@@ -238,6 +270,7 @@ def main():
     args.n_seqs = args.n_seqs or int(os.environ.get("LAMBDA_B200_NSEQS", W["n_seqs"]))
     args.n_queries = args.n_queries or int(os.environ.get("LAMBDA_B200_NQUERIES", W["n_queries"]))
     args.qlen = args.qlen or W["qlen"]
+    qdesc = f"{args.qlen}{W['unit']}" if args.qlen else f"(50..2000){W['unit']}"
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -245,7 +278,7 @@ def main():
     if world > 1 and args.gpus != world:
         log(f"--gpus {args.gpus} != WORLD_SIZE {world}; using WORLD_SIZE")
     n_gpus = world
-    workload = (f"{wl}: {args.n_queries}x{args.qlen}{W['unit']} synthetic queries vs {args.n_seqs}-seq {W['what']}, "
+    workload = (f"{W['search']}: {args.n_queries}x{qdesc} synthetic queries vs {args.n_seqs}-seq {W['what']}, "
                 f"default profile")
     cfg = {"workload": workload, "queries_per_gpu": args.n_queries, "query_len": args.qlen, "index_seqs": args.n_seqs,
            "profile": "none", "sharding": f"queries x{n_gpus}, index replicated", "streams_per_gpu": 3,

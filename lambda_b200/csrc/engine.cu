@@ -614,6 +614,11 @@ struct MaxOp
 // window length); up to 32/T consecutive alignments of one query form a job of the packed DPX kernel
 // (one shared query profile per warp).  Whatever does not fit the packed kernel (queries > 2048,
 // windows > 8192, exotic scoring) runs on the scalar wavefront kernel.
+using DpxLaunchFn = void (*)(lgpu_ctx &, DpxParams, unsigned int);
+#define LGPU_DPX_LAUNCH_ENTRY(T, K) &launchDpx<T, K>,
+static DpxLaunchFn const kDpxLaunch[kNumDpxClasses] = {LGPU_DPX_CLASSES(LGPU_DPX_LAUNCH_ENTRY)};
+#undef LGPU_DPX_LAUNCH_ENTRY
+
 static void runScorePass(lgpu_ctx & c, lgpu_match const * dTasks, unsigned int n, int * dScores, lgpu_stats * st)
 {
     if (n == 0)
@@ -685,20 +690,7 @@ static void runScorePass(lgpu_ctx & c, lgpu_match const * dTasks, unsigned int n
             P.nCodes      = static_cast<unsigned int>(c.scoring.alphSize) + 1;
             P.workCounter = c.dWork.p + cls;
             P.scores      = dScores;
-            switch (cls)
-            {
-                case 0: launchDpx<8, 4>(c, P, maxNt); break;
-                case 1: launchDpx<8, 8>(c, P, maxNt); break;
-                case 2: launchDpx<8, 12>(c, P, maxNt); break;
-                case 3: launchDpx<8, 16>(c, P, maxNt); break;
-                case 4: launchDpx<8, 20>(c, P, maxNt); break;
-                case 5: launchDpx<8, 24>(c, P, maxNt); break;
-                case 6: launchDpx<8, 32>(c, P, maxNt); break;
-                case 7: launchDpx<16, 24>(c, P, maxNt); break;
-                case 8: launchDpx<16, 32>(c, P, maxNt); break;
-                case 9: launchDpx<32, 24>(c, P, maxNt); break;
-                default: launchDpx<32, 32>(c, P, maxNt); break;
-            }
+            kDpxLaunch[cls](c, P, maxNt);
         }
         else
         {

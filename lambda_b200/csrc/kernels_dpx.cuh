@@ -75,7 +75,7 @@ __host__ __device__ constexpr int dpxRowWords(int T, int K)
     return (((K + 3) / 4) * 2 * T + 31) / 32 * 32 + ((T == 32) ? 0 : 8);
 }
 
-// sort key = class << 60 | (qryId << 1 | matrix selector) << 20 | min(nt, 2^20 - 1); the selector is the
+// sort key = class << 58 | (qryId << 1 | matrix selector) << 20 | min(nt, 2^20 - 1); the selector is the
 // subject parity in bisulfite mode (reverse matrix for odd subjects), else 0: all alignments of a job
 // share one profile
 constexpr unsigned int kDpxSegShift = 20;
@@ -309,22 +309,37 @@ __global__ void __launch_bounds__(32) swScoreDpxKernel(DpxParams P)
 // classification of tasks into (T, K) classes
 // ---------------------------------------------------------------------------------------------
 
-constexpr int kNumDpxClasses = 11;
-// columns covered by class c = 2 * T * K
+// (T, K) classes of the packed kernel, ascending by the columns they cover (2 * T * K).  Fine steps
+// (16 columns) where protein lengths concentrate, so that a query wastes few padded columns.
+#define LGPU_DPX_CLASSES(X)                                                                                        \
+    X(8, 4) X(8, 6) X(8, 8) X(8, 9) X(8, 10) X(8, 11) X(8, 12) X(8, 13) X(8, 14) X(8, 15) X(8, 16) X(8, 17)       \
+    X(8, 18) X(8, 19) X(8, 20) X(8, 21) X(8, 22) X(8, 23) X(8, 24) X(8, 26) X(8, 28) X(8, 30) X(8, 32)            \
+    X(16, 20) X(16, 24) X(16, 28) X(16, 32) X(32, 20) X(32, 24) X(32, 28) X(32, 32)
+
+struct DpxClass
+{
+    int T, K;
+};
+#define LGPU_DPX_CLASS_ENTRY(T, K) {T, K},
+__host__ __device__ inline DpxClass dpxClass(int cls)
+{
+    constexpr DpxClass tab[] = {LGPU_DPX_CLASSES(LGPU_DPX_CLASS_ENTRY)};
+    return tab[cls];
+}
+#define LGPU_DPX_CLASS_COUNT(T, K) +1
+constexpr int kNumDpxClasses = 0 LGPU_DPX_CLASSES(LGPU_DPX_CLASS_COUNT);
+static_assert(kNumDpxClasses < 63, "class id must fit the sort key");
+constexpr unsigned int kDpxClassShift = 58; // sort key: class in the top 6 bits
+
 __host__ __device__ inline int dpxClassOf(unsigned int nq)
 {
-    if (nq <= 64) return 0;    // T=8  K=4
-    if (nq <= 128) return 1;   // T=8  K=8
-    if (nq <= 192) return 2;   // T=8  K=12
-    if (nq <= 256) return 3;   // T=8  K=16
-    if (nq <= 320) return 4;   // T=8  K=20
-    if (nq <= 384) return 5;   // T=8  K=24
-    if (nq <= 512) return 6;   // T=8  K=32
-    if (nq <= 768) return 7;   // T=16 K=24
-    if (nq <= 1024) return 8;  // T=16 K=32
-    if (nq <= 1536) return 9;  // T=32 K=24
-    if (nq <= 2048) return 10; // T=32 K=32
-    return kNumDpxClasses;     // too long: scalar wavefront kernel
+    for (int c = 0; c < kNumDpxClasses; ++c)
+    {
+        DpxClass const k = dpxClass(c);
+        if (nq <= static_cast<unsigned int>(2 * k.T * k.K))
+            return c;
+    }
+    return kNumDpxClasses; // too long: scalar wavefront kernel
 }
 
 constexpr unsigned int kDpxMaxWindow = 8192; // longer windows go to the scalar kernel
@@ -332,7 +347,7 @@ constexpr unsigned int kDpxMaxWindow = 8192; // longer windows go to the scalar 
 // alignments per job (= groups per warp) of each class; the scalar class has one alignment per job
 __host__ __device__ inline unsigned int dpxGroupsOf(int cls)
 {
-    return cls <= 6 ? 4u : (cls <= 8 ? 2u : 1u);
+    return cls < kNumDpxClasses ? static_cast<unsigned int>(32 / dpxClass(cls).T) : 1u;
 }
 
 // key (see kDpxSegShift); also per-class counts / max window / total cells
@@ -352,7 +367,7 @@ __global__ void classifyKernel(lgpu_match const * tasks, unsigned int n, unsigne
         if (nt > kDpxMaxWindow)
             c = kNumDpxClasses;
         unsigned long long const seg = (static_cast<unsigned long long>(tasks[t].qry_id) << 1) | (tasks[t].subj_id & bsMode);
-        keys[t] = (static_cast<unsigned long long>(c) << 60) | (seg << kDpxSegShift) |
+        keys[t] = (static_cast<unsigned long long>(c) << kDpxClassShift) | (seg << kDpxSegShift) |
                   (nt < (1u << kDpxSegShift) ? nt : (1u << kDpxSegShift) - 1u);
         idx[t]  = t;
         myCells = static_cast<unsigned long long>(nq) * nt;
@@ -428,7 +443,7 @@ __global__ void jobHeadKernel(unsigned long long const * keys, unsigned int cons
     unsigned int const t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n)
         return;
-    int const          cls = static_cast<int>(keys[t] >> 60);
+    int const          cls = static_cast<int>(keys[t] >> kDpxClassShift);
     unsigned int const h   = ((t - segStart[t]) % dpxGroupsOf(cls)) == 0 ? 1u : 0u;
     head[t]                = h;
     if (h)

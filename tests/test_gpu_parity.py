@@ -161,8 +161,10 @@ def test_score_kernel_all_length_classes(golden_dir):
     rng = np.random.default_rng(7)
     db, offs = synth.protein_db(500, seed=101)
     lens = np.diff(offs)
-    qlens = [1, 2, 7, 33, 64, 65, 100, 128, 129, 190, 192, 193, 250, 256, 257, 300, 320, 321, 384, 385, 500, 512,
-             513, 700, 768, 769, 1000, 1024, 1025, 1500, 1536, 1537, 2000, 2048, 2049, 2300]
+    # one length inside every class (columns = 2*T*K, kernels_dpx.cuh LGPU_DPX_CLASSES) plus the class edges
+    qlens = [1, 2, 7, 33, 64, 65, 96, 100, 128, 129, 144, 150, 160, 170, 176, 190, 192, 193, 208, 220, 224, 240, 250,
+             256, 257, 272, 288, 300, 304, 305, 320, 321, 336, 350, 352, 368, 384, 385, 416, 440, 448, 480, 500, 512,
+             513, 640, 700, 768, 769, 896, 1000, 1024, 1025, 1280, 1500, 1536, 1537, 1792, 2000, 2048, 2049, 2300]
     qs, qo, wins = [], [0], []
     for qi, L in enumerate(qlens):
         sid = int(rng.integers(0, len(lens)))
