@@ -33,6 +33,7 @@
 #include "host_finalize.hpp"
 #include "host_params.hpp"
 #include "kernels_dpx.cuh"
+#include "kernels_ckpt_trace.cuh"
 #include "kernels_dpx_trace.cuh"
 #include "kernels_extend.cuh"
 #include "kernels_fm.cuh"
@@ -214,6 +215,8 @@ struct lgpu_ctx
     DevBuf<unsigned int>       dPlanes;      // (H, dE|dF) planes of the packed trace kernel
     DevBuf<lgpu_match>         dTasksScalar;
     bool                       forceScalarTrace = false; // LAMBDA_B200_TRACE=scalar (tests)
+    bool                       planeTrace = true;        // stored (H, dE, dF) planes; LAMBDA_B200_TRACE=ckpt: checkpoints + tile recomputation
+    DevBuf<unsigned int>       dFirstBlk;
 
     // pinned staging
     PinnedBuf<lgpu_match> hTasks;
@@ -795,6 +798,130 @@ static void launchDpxTrace(lgpu_ctx & c, DpxTraceParams P, unsigned int maxNt)
     LGPU_CUDA(cudaGetLastError());
 }
 
+template <int T, int K>
+static void launchCkTrace(lgpu_ctx & c, CkTraceParams P, unsigned int maxNt)
+{
+    constexpr int G = 32 / T;
+    P.winCap        = (maxNt + 4 * T + 127) / 128 * 128;
+    size_t const smem = static_cast<size_t>(G) * (static_cast<size_t>(P.nCodes) * dpxRowWords(T, K) * 4 + P.winCap + 32 +
+                                                  static_cast<size_t>(T) * ckRecWords(K) * 4);
+    LGPU_CUDA(cudaFuncSetAttribute(swTraceCkKernel<T, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (smem > 227 * 1024)
+        throw CudaError("checkpoint trace kernel: window too long for shared memory");
+    unsigned int const nJobs = (P.nTasks + G - 1) / G;
+    unsigned int const grid  = std::min<unsigned int>(nJobs, static_cast<unsigned int>(c.numSMs) * 32);
+    swTraceCkKernel<T, K><<<grid, 32, smem, c.stream>>>(P);
+    LGPU_CUDA(cudaGetLastError());
+}
+template <int K>
+static void launchCkTracebackK(TracebackCkParams const & TP, unsigned int cnt, cudaStream_t s)
+{
+    LGPU_CUDA(cudaFuncSetAttribute(tracebackCkKernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, ckTbSmemBytes(K)));
+    tracebackCkKernel<K><<<gridFor(cnt, kCkTbThreads), kCkTbThreads, ckTbSmemBytes(K), s>>>(TP);
+}
+static void launchCkTraceback(int K, TracebackCkParams const & TP, unsigned int cnt, cudaStream_t s)
+{
+    switch (K)
+    {
+        case 4: launchCkTracebackK<4>(TP, cnt, s); break;
+        case 8: launchCkTracebackK<8>(TP, cnt, s); break;
+        case 10: launchCkTracebackK<10>(TP, cnt, s); break;
+        case 12: launchCkTracebackK<12>(TP, cnt, s); break;
+        case 16: launchCkTracebackK<16>(TP, cnt, s); break;
+        case 20: launchCkTracebackK<20>(TP, cnt, s); break;
+        case 24: launchCkTracebackK<24>(TP, cnt, s); break;
+        case 32: launchCkTracebackK<32>(TP, cnt, s); break;
+        default: throw CudaError("checkpoint traceback: unsupported K");
+    }
+}
+using CkLaunchFn = void (*)(lgpu_ctx &, CkTraceParams, unsigned int);
+#define LGPU_CK_LAUNCH_ENTRY(T, K) &launchCkTrace<T, K>,
+static CkLaunchFn const kCkLaunch[kNumCkClasses] = {LGPU_CK_CLASSES(LGPU_CK_LAUNCH_ENTRY)};
+#undef LGPU_CK_LAUNCH_ENTRY
+
+// DP pass 2 on checkpoints (kernels_ckpt_trace.cuh) for the tasks in `lists[cls]`; results land in c.dHits
+static void runTraceCk(lgpu_ctx & c, lgpu_match const * tasks, size_t n, lgpu_match const * dTasks,
+                       std::vector<std::vector<unsigned int>> const & lists, lgpu_stats * st)
+{
+    constexpr uint64_t kMaxCkWords = (16ull << 30) / 4; // per launch; checkpoints are ~0.7 B per DP cell
+    std::vector<unsigned long long> ckOff(n, 0);
+    c.dOrder.reserve(n);
+    c.dTraceOff.reserve(n);
+    c.dScores2.reserve(n);
+    c.dBestPos.reserve(n);
+    c.dFirstBlk.reserve(n);
+    for (int cls = 0; cls < kNumCkClasses; ++cls)
+    {
+        std::vector<unsigned int> const & L = lists[cls];
+        if (L.empty())
+            continue;
+        DpxClass const k = ckClass(cls);
+        size_t         begin = 0;
+        while (begin < L.size())
+        {
+            uint64_t     words = 0;
+            unsigned int maxNt = 0;
+            size_t       end   = begin;
+            while (end < L.size())
+            {
+                unsigned int const nt = tasks[L[end]].subj_end - tasks[L[end]].subj_start;
+                uint64_t const     w  = ckWords(k.T, k.K, nt);
+                if (end > begin && words + w > kMaxCkWords)
+                    break;
+                ckOff[L[end]] = words;
+                words += w;
+                maxNt = std::max(maxNt, nt);
+                ++end;
+            }
+            unsigned int const cnt = static_cast<unsigned int>(end - begin);
+            c.dPlanes.reserve(words);
+            LGPU_CUDA(cudaMemcpyAsync(c.dOrder.p, L.data() + begin, cnt * 4ull, cudaMemcpyHostToDevice, c.stream));
+            LGPU_CUDA(cudaMemcpyAsync(c.dTraceOff.p, ckOff.data(), n * 8ull, cudaMemcpyHostToDevice, c.stream));
+            LGPU_CUDA(cudaMemsetAsync(c.dWork.p, 0, 4, c.stream));
+            CkTraceParams P{};
+            P.ix          = c.index->dev;
+            P.Q           = c.Q;
+            P.tasks       = dTasks;
+            P.order       = c.dOrder.p;
+            P.nTasks      = cnt;
+            P.matrix      = c.dMatrix.p;
+            P.go          = c.scoring.gapOpenSeqan;
+            P.ge          = c.scoring.gapExtend;
+            P.nCodes      = static_cast<unsigned int>(c.scoring.alphSize) + 1;
+            P.workCounter = c.dWork.p;
+            P.ck          = c.dPlanes.p;
+            P.ckOff       = c.dTraceOff.p;
+            P.scores      = c.dScores2.p;
+            P.bestCol     = c.dBestPos.p;
+            P.firstBlk    = c.dFirstBlk.p;
+            kCkLaunch[cls](c, P, maxNt);
+            TracebackCkParams TP{};
+            TP.ix       = c.index->dev;
+            TP.Q        = c.Q;
+            TP.tasks    = dTasks;
+            TP.order    = c.dOrder.p;
+            TP.nTasks   = cnt;
+            TP.matrix   = c.dMatrix.p;
+            TP.go       = c.scoring.gapOpenSeqan;
+            TP.ge       = c.scoring.gapExtend;
+            TP.T        = static_cast<unsigned int>(k.T);
+            TP.K        = static_cast<unsigned int>(k.K);
+            TP.scores   = c.dScores2.p;
+            TP.bestCol  = c.dBestPos.p;
+            TP.firstBlk = c.dFirstBlk.p;
+            TP.ck       = c.dPlanes.p;
+            TP.ckOff    = c.dTraceOff.p;
+            TP.out      = c.dHits.p;
+            launchCkTraceback(k.K, TP, cnt, c.stream);
+            LGPU_CUDA(cudaGetLastError());
+            LGPU_CUDA(cudaStreamSynchronize(c.stream)); // the order / offset staging arrays are reused by the next chunk
+            if (st)
+                st->kernel_launches += 2;
+            begin = end;
+        }
+    }
+}
+
 // DP pass 2 + traceback for `n` tasks (host copy `tasks`, device copy dTasks); hostOut[i] <-> tasks[i].
 // Alignments whose query fits 64 x 32 columns run on the packed DPX trace kernel (one warp each, planes
 // of (H, dE, dF) instead of trace bytes); the rest on the scalar wavefront kernel.
@@ -807,25 +934,35 @@ static void runTracePass(lgpu_ctx & c, lgpu_match const * tasks, size_t n, lgpu_
     int const  D      = c.scoring.gapExtend - c.scoring.gapOpenSeqan;
     bool const dpxOk  = c.dpxOk && D >= 0 && D <= 14 && !c.forceScalarTrace;
     uint64_t   cells  = 0;
-    std::vector<std::vector<unsigned int>> lists(kNumTraceClasses + 1);
+    bool const useCk        = !c.planeTrace;
+    int const  nPackedClass = useCk ? kNumCkClasses : kNumTraceClasses;
+    std::vector<std::vector<unsigned int>> lists(std::max(kNumCkClasses, kNumTraceClasses) + 1);
     for (size_t i = 0; i < n; ++i)
     {
         unsigned int const nq = tasks[i].qry_end - tasks[i].qry_start, nt = tasks[i].subj_end - tasks[i].subj_start;
         cells += static_cast<uint64_t>(nq) * nt;
-        int cls = dpxTraceClassOf(nq);
-        if (!dpxOk || nt > kDpxMaxWindow)
-            cls = kNumTraceClasses;
+        int cls = useCk ? ckClassOf(nq) : dpxTraceClassOf(nq);
+        if (!dpxOk || nt > kDpxMaxWindow || cls == nPackedClass)
+            cls = static_cast<int>(lists.size()) - 1;
         lists[cls].push_back(static_cast<unsigned int>(i));
     }
     c.dHits.reserve(n);
     c.hHits.reserve(n);
     c.dWork.reserve(kNumDpxClasses + 2);
+    bool anyCk = false;
+    if (useCk)
+    {
+        for (int cls = 0; cls < kNumCkClasses; ++cls)
+            anyCk = anyCk || !lists[cls].empty();
+        if (anyCk)
+            runTraceCk(c, tasks, n, dTasks, lists, st);
+    }
 
     // ---- packed classes ----
     constexpr uint64_t kMaxPlaneWords = (16ull << 30) / 4;
     std::vector<unsigned long long> planeOff(n, 0);
     bool                            anyDpx = false;
-    for (int cls = 0; cls < kNumTraceClasses; ++cls)
+    for (int cls = 0; cls < kNumTraceClasses && !useCk; ++cls)
     {
         std::vector<unsigned int> const & L = lists[cls];
         if (L.empty())
@@ -911,17 +1048,17 @@ static void runTracePass(lgpu_ctx & c, lgpu_match const * tasks, size_t n, lgpu_
             begin = end;
         }
     }
-    if (anyDpx)
+    if (anyDpx || anyCk)
     {
         LGPU_CUDA(cudaMemcpyAsync(c.hHits.p, c.dHits.p, n * sizeof(lgpu_hit), cudaMemcpyDeviceToHost, c.stream));
         LGPU_CUDA(cudaStreamSynchronize(c.stream));
-        for (int cls = 0; cls < kNumTraceClasses; ++cls)
+        for (int cls = 0; cls < nPackedClass; ++cls)
             for (unsigned int i : lists[cls])
                 hostOut[i] = c.hHits.p[i];
     }
 
     // ---- scalar class ----
-    std::vector<unsigned int> const & LS = lists[kNumTraceClasses];
+    std::vector<unsigned int> const & LS = lists.back();
     if (!LS.empty())
     {
         std::vector<lgpu_match> sub(LS.size());
@@ -1290,7 +1427,10 @@ static std::unique_ptr<lgpu_ctx> lgpu::makeContext(lgpu_index const * ix, lgpu_p
     if (char const * e = std::getenv("LAMBDA_B200_DPX_OCC"))
         c->dpxBlocksPerSM = static_cast<unsigned int>(std::max(1, std::min(32, std::atoi(e))));
     if (char const * e = std::getenv("LAMBDA_B200_TRACE"))
+    {
         c->forceScalarTrace = !std::strcmp(e, "scalar");
+        c->planeTrace       = std::strcmp(e, "ckpt") != 0;
+    }
     // the packed kernel stores (score - gapOpen) as int8 profile bytes with -128 reserved for "null"
     bool nonNeg = true;
     c->dpxOk = c->scoring.alphSize < 32 && c->scoring.gapOpenSeqan <= c->scoring.gapExtend && c->scoring.gapExtend <= 0;

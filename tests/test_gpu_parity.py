@@ -85,11 +85,11 @@ def test_seeding_matches_oracle(golden_dir, case, domain, profile, mode, monkeyp
     s.close(); ix.close(); o.close()
 
 
-@pytest.mark.parametrize("trace", ["dpx", "scalar"])
+@pytest.mark.parametrize("trace", ["ckpt", "planes", "scalar"])
 @pytest.mark.parametrize("case,domain", [(c, d) for c, d, _ in CASES])
 def test_extension_matches_oracle(golden_dir, case, domain, trace, monkeypatch):
     """DP pass 1 scores and the full pass-2 records (coordinates + statistics) for both trace paths:
-    packed DPX planes and the scalar trace-byte kernel"""
+    packed DPX planes (default), checkpoints + tile recomputation, and the scalar trace-byte kernel"""
     monkeypatch.setenv("LAMBDA_B200_TRACE", trace)
     path, ids, res, offs = _load(golden_dir, case, domain)
     o = orc.Oracle(path)
@@ -119,7 +119,7 @@ def test_extension_matches_oracle(golden_dir, case, domain, trace, monkeypatch):
     s.close(); ix.close(); o.close()
 
 
-@pytest.mark.parametrize("trace", ["dpx", "scalar"])
+@pytest.mark.parametrize("trace", ["ckpt", "planes", "scalar"])
 def test_extension_long_queries_multi_block(golden_dir, trace, monkeypatch):
     """queries longer than one 32*K column block (boundary row path) and long merged windows"""
     monkeypatch.setenv("LAMBDA_B200_TRACE", trace)
