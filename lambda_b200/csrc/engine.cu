@@ -16,6 +16,7 @@
 //
 // No CPU fallback exists: if CUDA is unavailable every entry point fails with LGPU_ERR_CUDA.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -28,6 +29,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cuda_runtime.h>
+#include <unistd.h>
 
 #include "../../include/lambda_b200.h"
 #include "host_finalize.hpp"
@@ -141,6 +143,111 @@ static T * uploadNew(T const * host, size_t n)
     if (n)
         LGPU_CUDA(cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice));
     return d;
+}
+
+// Host -> device copies of the index blobs.  The source is the mmap'd .lba (pageable page cache): a plain
+// cudaMemcpy moves it through the driver's small staging buffer at a few GB/s.  Here several host
+// threads copy 16 MiB chunks into their own pinned double buffers and push them with cudaMemcpyAsync, so
+// the page-cache reads of all threads and the PCIe transfers overlap.
+struct UploadJob
+{
+    unsigned char *       dst;
+    unsigned char const * src;
+    size_t                bytes;
+};
+
+static void runUploads(std::vector<UploadJob> const & jobs, int device)
+{
+    constexpr size_t kChunk = 16u << 20;
+    struct Piece
+    {
+        unsigned char *       dst;
+        unsigned char const * src;
+        size_t                bytes;
+        int                   fd;      // >= 0: the source is a mapped index file, read it with pread()
+        size_t                fileOff;
+    };
+    std::vector<Piece> pieces;
+    for (UploadJob const & j : jobs)
+    {
+        int    fd      = -1;
+        size_t fileOff = 0;
+        if (!lbaLocate(j.src, j.bytes, fd, fileOff))
+            fd = -1;
+        for (size_t off = 0; off < j.bytes; off += kChunk)
+            pieces.push_back({j.dst + off, j.src + off, std::min(kChunk, j.bytes - off), fd, fileOff + off});
+    }
+    if (pieces.empty())
+        return;
+    unsigned int nThreads = 6;
+    if (char const * e = std::getenv("LAMBDA_B200_UPLOAD_THREADS"))
+        nThreads = static_cast<unsigned int>(std::max(1, std::min(32, std::atoi(e))));
+    nThreads = static_cast<unsigned int>(std::min<size_t>(nThreads, pieces.size()));
+    std::atomic<size_t>      next{0};
+    std::vector<std::string> err(nThreads);
+    std::vector<std::thread> th;
+    for (unsigned int t = 0; t < nThreads; ++t)
+        th.emplace_back([&, t] {
+            try
+            {
+                LGPU_CUDA(cudaSetDevice(device));
+                cudaStream_t    st;
+                cudaEvent_t     ev[2];
+                unsigned char * pin[2] = {nullptr, nullptr};
+                LGPU_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+                for (int b = 0; b < 2; ++b)
+                {
+                    LGPU_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&pin[b]), kChunk, cudaHostAllocDefault));
+                    LGPU_CUDA(cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming));
+                }
+                bool used[2] = {false, false};
+                int  b       = 0;
+                for (;;)
+                {
+                    size_t const i = next.fetch_add(1);
+                    if (i >= pieces.size())
+                        break;
+                    if (used[b])
+                        LGPU_CUDA(cudaEventSynchronize(ev[b]));
+                    Piece const & pc   = pieces[i];
+                    bool          done = false;
+                    if (pc.fd >= 0)
+                    {
+                        size_t got = 0;
+                        while (got < pc.bytes)
+                        {
+                            ssize_t const r = pread(pc.fd, pin[b] + got, pc.bytes - got, static_cast<off_t>(pc.fileOff + got));
+                            if (r <= 0)
+                                break;
+                            got += static_cast<size_t>(r);
+                        }
+                        done = got == pc.bytes;
+                    }
+                    if (!done)
+                        std::memcpy(pin[b], pc.src, pc.bytes);
+                    LGPU_CUDA(cudaMemcpyAsync(pieces[i].dst, pin[b], pieces[i].bytes, cudaMemcpyHostToDevice, st));
+                    LGPU_CUDA(cudaEventRecord(ev[b], st));
+                    used[b] = true;
+                    b ^= 1;
+                }
+                LGPU_CUDA(cudaStreamSynchronize(st));
+                for (int k = 0; k < 2; ++k)
+                {
+                    cudaFreeHost(pin[k]);
+                    cudaEventDestroy(ev[k]);
+                }
+                cudaStreamDestroy(st);
+            }
+            catch (std::exception const & e)
+            {
+                err[t] = e.what();
+            }
+        });
+    for (auto & t : th)
+        t.join();
+    for (auto const & e : err)
+        if (!e.empty())
+            throw CudaError("index upload: " + e);
 }
 
 static inline unsigned int gridFor(unsigned long long n, unsigned int block)
@@ -1486,8 +1593,16 @@ int lgpu_index_create(lgpu_index ** out, lgpu_index_desc const * d, int device)
         LGPU_CUDA(cudaSetDevice(device));
         auto ix    = std::make_unique<lgpu_index>();
         ix->device = device;
+        std::vector<UploadJob> pending; // large blobs are copied together by runUploads()
         auto up    = [&](void const * p, uint64_t bytes) -> void * {
-            void * dp = uploadNew(static_cast<unsigned char const *>(p), bytes);
+            void * dp = nullptr;
+            if (bytes < (8u << 20))
+                dp = uploadNew(static_cast<unsigned char const *>(p), bytes);
+            else
+            {
+                LGPU_CUDA(cudaMalloc(&dp, bytes));
+                pending.push_back({static_cast<unsigned char *>(dp), static_cast<unsigned char const *>(p), bytes});
+            }
             ix->allocs.push_back(dp);
             ix->bytes += bytes;
             return dp;
@@ -1504,6 +1619,8 @@ int lgpu_index_create(lgpu_index ** out, lgpu_index_desc const * d, int device)
         dv.bsMode      = d->red_alph == LGPU_ALPH_DNA3BS ? 1 : 0;
         dv.sbjFrames   = d->red_alph == LGPU_ALPH_DNA3BS ? 2 : 1;
         dv.nSeqs       = d->n_seqs;
+        runUploads(pending, device);
+        pending.clear();
         LGPU_CUDA(cudaMemcpyToSymbol(cDna5Translate, kDna5Translate, 125));
         // dbTotalLength = sum of reduced subject lengths (src/search_algo.hpp:317-318)
         ix->dbTotalLength = d->n_residues * (d->red_alph == LGPU_ALPH_DNA3BS ? 2 : 1);
@@ -1525,6 +1642,8 @@ int lgpu_index_create(lgpu_index ** out, lgpu_index_desc const * d, int device)
             ix->bytes += tTotal;
             unsigned char * dComp = static_cast<unsigned char *>(up(kDna5Complement, 5));
             uint64_t const  nFr   = d->n_seqs * 6;
+            runUploads(pending, device);
+            pending.clear();
             translateSubjectsKernel<<<static_cast<unsigned int>(std::min<uint64_t>(std::max<uint64_t>(nFr, 1), 1u << 20)), 128>>>(
               dv.seqs, dv.origDelims, d->n_seqs, dComp, dTd, dT);
             LGPU_CUDA(cudaGetLastError());
@@ -1555,6 +1674,7 @@ int lgpu_index_create(lgpu_index ** out, lgpu_index_desc const * d, int device)
         ix->meta.seq_delims   = nullptr;
         ix->meta.ids          = nullptr;
         ix->meta.id_delims    = nullptr;
+        runUploads(pending, device);
         LGPU_CUDA(cudaDeviceSynchronize());
         *out = ix.release();
     });

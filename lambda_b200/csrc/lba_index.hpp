@@ -11,6 +11,7 @@
 #include <cstdint>
 #include <cstring>
 #include <stdexcept>
+#include <mutex>
 #include <string>
 
 #include <fcntl.h>
@@ -50,6 +51,40 @@ inline uint32_t bitLength(uint32_t v) // required_bits(): number of bits to repr
     return b;
 }
 
+// Registry of the mapped index files, so that a pointer into a mapping can be turned back into
+// (file descriptor, file offset): the uploader then reads the file with pread() straight into pinned
+// memory instead of touching (page-faulting) 4 KiB pages of the mapping one by one.
+struct LbaMapping
+{
+    uint8_t const * base;
+    size_t          size;
+    int             fd;
+};
+inline std::mutex & lbaRegistryMutex()
+{
+    static std::mutex m;
+    return m;
+}
+inline std::vector<LbaMapping> & lbaRegistry()
+{
+    static std::vector<LbaMapping> r;
+    return r;
+}
+// true and (fd, offset) if [p, p + n) lies inside a mapped index file
+inline bool lbaLocate(void const * p, size_t n, int & fd, size_t & offset)
+{
+    std::lock_guard<std::mutex> g(lbaRegistryMutex());
+    uint8_t const *             q = static_cast<uint8_t const *>(p);
+    for (LbaMapping const & m : lbaRegistry())
+        if (q >= m.base && q + n <= m.base + m.size)
+        {
+            fd     = m.fd;
+            offset = static_cast<size_t>(q - m.base);
+            return true;
+        }
+    return false;
+}
+
 class LbaFile
 {
 public:
@@ -74,10 +109,22 @@ public:
         }
         madvise(const_cast<uint8_t *>(base_), size_, MADV_SEQUENTIAL);
         parse();
+        std::lock_guard<std::mutex> g(lbaRegistryMutex());
+        lbaRegistry().push_back({base_, size_, fd_});
     }
 
     ~LbaFile()
     {
+        {
+            std::lock_guard<std::mutex> g(lbaRegistryMutex());
+            auto &                      r = lbaRegistry();
+            for (size_t i = 0; i < r.size(); ++i)
+                if (r[i].base == base_)
+                {
+                    r.erase(r.begin() + static_cast<std::ptrdiff_t>(i));
+                    break;
+                }
+        }
         if (base_)
             munmap(const_cast<uint8_t *>(base_), size_);
         if (fd_ >= 0)

@@ -268,17 +268,21 @@ struct ShardResult
     std::vector<lgpu_hit> hits; // q_id already global
     lgpu_stats            stats{};
     std::string           error;
+    double                tUpload = 0, tSearch = 0, tTeardown = 0; // seconds
 };
 
 void runShard(Options const & o, lgpu_index_desc const * desc, int device, Fasta const & f, uint64_t qBegin, uint64_t qEnd,
               ShardResult & out)
 {
+    double const t0 = now();
     lgpu_index * ix = nullptr;
     if (lgpu_index_create(&ix, desc, device) != LGPU_OK)
     {
         out.error = lgpu_last_error(nullptr);
         return;
     }
+    out.tUpload = now() - t0;
+    double const t1 = now();
     lgpu_ctx * ctx = nullptr;
     if (lgpu_ctx_create(&ctx, ix, &o.params) != LGPU_OK)
     {
@@ -306,8 +310,11 @@ void runShard(Options const & o, lgpu_index_desc const * desc, int device, Fasta
         for (size_t i = old; i < out.hits.size(); ++i)
             out.hits[i].q_id += static_cast<uint32_t>(b);
     }
+    out.tSearch = now() - t1;
+    double const t2 = now();
     lgpu_ctx_destroy(ctx);
     lgpu_index_destroy(ix);
+    out.tTeardown = now() - t2;
 }
 
 } // namespace
@@ -397,7 +404,11 @@ int main(int argc, char ** argv)
 
     if (o.verbosity >= 2)
     {
-        std::printf("Runtime total: %.3fs (search %.3fs incl. index upload, output %.3fs)\n\n", t4 - t0, t3 - t2, t4 - t3);
+        std::printf("Runtime total: %.3fs (search %.3fs incl. index upload, output %.3fs)\n", t4 - t0, t3 - t2, t4 - t3);
+        for (size_t g = 0; g < res.size(); ++g)
+            std::printf("  GPU %zu: CUDA init + index upload %.3fs, search %.3fs, teardown %.3fs\n", g, res[g].tUpload,
+                        res[g].tSearch, res[g].tTeardown);
+        std::printf("\n");
         std::printf("   HITS                             Remaining\n");
         uint64_t rem = total.hits_after_seeding;
         std::printf("   after Seeding               %10llu\n", static_cast<unsigned long long>(rem));

@@ -53,9 +53,10 @@ def main():
             for f in (ours,):
                 if os.path.exists(f):
                     os.remove(f)  # like the reference, lambda3_b200 refuses to overwrite its output
-            dt, _ = run([os.path.join(ROOT, "bin", "lambda3_b200"), W["search"], "-q", qf, "-i", lba, "-o", ours,
-                         "--gpus", str(a.gpus), "-v", "0"])
+            dt, txt = run([os.path.join(ROOT, "bin", "lambda3_b200"), W["search"], "-q", qf, "-i", lba, "-o", ours,
+                           "--gpus", str(a.gpus), "-v", "2"])
             t_ours.append(dt)
+            detail = [l.strip() for l in txt.splitlines() if "Runtime total" in l or "GPU " in l or "Index mapped" in l]
         for _ in range(a.reps):
             if os.path.exists(ref):
                 os.remove(ref)
@@ -65,7 +66,7 @@ def main():
         lo = sorted(open(ours).read().splitlines())
         lr = sorted(open(ref).read().splitlines())
         print(json.dumps({"workload": a.workload, "queries": nq, "gpus": a.gpus, "host_cores": cores,
-                          "lambda3_b200_wall_s": t_ours, "reference_wall_s": t_ref,
+                          "lambda3_b200_wall_s": t_ours, "lambda3_b200_detail": detail, "reference_wall_s": t_ref,
                           "speedup_best_of": min(t_ref) / min(t_ours), "lines_ours": len(lo), "lines_reference": len(lr),
                           "identical": lo == lr}))
 
