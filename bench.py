@@ -439,6 +439,15 @@ def main():
                 "peak_source": peak_src, "traffic": traffic, "gcups": gcups_score,
                 "algorithmic": "10 int16 ops per DP cell x cells of the step / DP pass-1 stage time (CUDA events)"}
 
+    # the other kernels of the step: bound and achieved fraction from the committed ncu capture (static evidence)
+    other = None
+    kp = os.path.join(ROOT, "profiles", f"r1_ncu_kernels_{wl}.json")
+    if os.path.exists(kp):
+        try:
+            other = json.load(open(kp))
+        except Exception:
+            other = None
+
     out = {"metric": f"{wl}_query_seqs_per_s", "value": value, "unit": "queries/s", "n_gpus": n_gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "wall_ms_per_step": wall_res / args.steps,
            "ms_per_step_serial_1_stream": ms_serial / args.steps,
@@ -455,7 +464,7 @@ def main():
            "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": int(res.nbytes + qoffs.nbytes),
                    "d2h_bytes_per_step": int(len(hits) * HIT_DT.itemsize), "ms_per_step": wall_e2e / args.steps,
                    "device_ms_per_step": ms_e2e / args.steps, "timing": "host wall-clock around Searcher.search()"},
-           "gpu_launches": int(st["kernel_launches"])}
+           "gpu_launches": int(st_pipe["kernel_launches"]), "kernels_ncu": other}
 
     # CPU baseline: the unmodified reference on this box's host cores, bounded sample of the same queries
     if not args.no_cpu_baseline and n_gpus == 1 and os.path.exists(REF):
