@@ -32,6 +32,8 @@ struct Options
     int         verbosity = 1;
     int         threads   = 1; // only used for the reference's records_per_batch formula
     int         gpus      = 1;
+    bool        comments  = false; // .m9: BLAST tabular with comment lines
+    bool        versionToOutput = true;
     uint64_t    blockSize = 100000;
     lgpu_params params{};
 };
@@ -50,7 +52,7 @@ bool endsWith(std::string const & s, char const * suf)
 
 void usage()
 {
-    std::puts("lambda3_b200 searchp|searchn|searchbs -q QUERY.fasta -i INDEX.lba [-o output.m8] [OPTIONS]\n"
+    std::puts("lambda3_b200 searchp|searchn|searchbs -q QUERY.fasta -i INDEX.lba [-o output.m8|.m9] [OPTIONS]\n"
               "  -a, --input-alphabet   auto|dna5|aminoacid (searchp; dna queries are translated: BLASTX/TBLASTX)\n"
               "  -p, --profile          none|fast|sensitive|pairs-default|pairs-sensitive\n"
               "  -e, --e-value          maximum e-value (default 0.01; -1 = off)\n"
@@ -135,7 +137,7 @@ void parse(int argc, char ** argv, Options & o)
         else if (a == "--gpus") o.gpus = std::max(1, std::atoi(need(i)));
         else if (a == "--block-size") o.blockSize = std::max<uint64_t>(1, std::strtoull(need(i), nullptr, 10));
         else if (a == "-v" || a == "--verbosity") o.verbosity = std::atoi(need(i));
-        else if (a == "--version-to-outputfile") need(i); // only affects m9/m0/sam headers
+        else if (a == "--version-to-outputfile") o.versionToOutput = std::atoi(need(i)) != 0; // .m9 comment lines
         else if (a == "-h" || a == "--help") { usage(); std::exit(0); }
         else die("unknown option '" + a + "'");
     }
@@ -145,8 +147,9 @@ void parse(int argc, char ** argv, Options & o)
         die("Invalid argument to --input-alphabet");
     if (o.domain != LGPU_DOMAIN_PROTEIN && o.inputAlphabet != "auto")
         die("--input-alphabet is a searchp option");
-    if (!endsWith(o.output, ".m8"))
-        die("only BLAST tabular output (.m8) is produced by the GPU path; other formats stay with the reference");
+    o.comments = endsWith(o.output, ".m9");
+    if (!endsWith(o.output, ".m8") && !o.comments)
+        die("only BLAST tabular output (.m8, .m9) is produced by the GPU path; other formats stay with the reference");
     if (std::ifstream(o.output).good())
         die("the output file already exists: " + o.output); // sharg's create_new validator
 }
@@ -380,6 +383,29 @@ int main(int argc, char ** argv)
         return std::string(desc->ids + desc->id_delims[s], desc->ids + desc->id_delims[s + 1]);
     };
     // the reference chunks the queries per thread first (src/search.cpp:384-385), then into batches
+    // .m9: comment lines in front of every record = query with at least one match
+    // (SQ/blast/blast_tabular_out.h:149-205, version string src/search_output.hpp:309-317)
+    bool const  qTrans  = qryAlph == LGPU_ALPH_DNA5 && desc->trans_alph == LGPU_ALPH_AMINO_ACID;
+    bool const  sTrans  = desc->orig_alph == LGPU_ALPH_DNA5 && desc->trans_alph == LGPU_ALPH_AMINO_ACID;
+    char const * program = desc->trans_alph != LGPU_ALPH_AMINO_ACID ? "BLASTN"
+                           : qTrans ? (sTrans ? "TBLASTX" : "BLASTX")
+                                    : (sTrans ? "TBLASTN" : "BLASTP");
+    std::string const versionLine =
+      o.versionToOutput ? std::string(program) + " 2.2.26+ [created by LAMBDA-3.0.0, see http://seqan.de/lambda and please "
+                                                 "cite correctly in your academic work]"
+                        : std::string(program) + " 2.2.26+ [I/O Module of SeqAn-2.4.1, http://www.seqan.de]";
+    uint64_t nRecords = 0;
+    auto     recordHeader = [&](uint64_t q, size_t nHits) {
+        ++nRecords;
+        if (!o.comments)
+            return;
+        std::fprintf(fo, "# %s\n# Query: %s\n# Database: %s\n", versionLine.c_str(), f.ids[q].c_str(), o.index.c_str());
+        if (nHits)
+            std::fputs("# Fields: query id, subject id, % identity, alignment length, mismatches, gap opens, q. start, q. end, "
+                       "s. start, s. end, evalue, bit score\n", fo);
+        std::fprintf(fo, "# %zu hits found\n", nHits);
+    };
+    // the reference chunks the queries per thread first (src/search.cpp:384-385), then into batches
     for (int t = 0; t < o.threads; ++t)
     {
         uint64_t const cb = nQ * t / o.threads, ce = nQ * (t + 1) / o.threads;
@@ -388,6 +414,12 @@ int main(int argc, char ** argv)
             uint64_t const e = std::min(ce, b + rpb);
             for (int phase = 1; phase <= 2; ++phase)
                 for (uint64_t q = b; q < e; ++q)
+                {
+                    size_t nHits = 0;
+                    for (lgpu_hit const * h : perQuery[q])
+                        nHits += h->phase == phase;
+                    if (nHits)
+                        recordHeader(q, nHits);
                     for (lgpu_hit const * h : perQuery[q])
                         if (h->phase == phase)
                         {
@@ -396,8 +428,11 @@ int main(int argc, char ** argv)
                             if (n > 0)
                                 std::fwrite(line.data(), 1, static_cast<size_t>(n), fo);
                         }
+                }
         }
     }
+    if (o.comments)
+        std::fprintf(fo, "# BLAST processed %llu queries\n", static_cast<unsigned long long>(nRecords));
     std::fclose(fo);
     lgpu_lba_close(lba);
     double const t4 = now();

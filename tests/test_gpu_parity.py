@@ -279,6 +279,22 @@ def test_cli_output_is_byte_identical_to_reference(golden_dir, tmp_path, case, d
     assert subprocess.run(cmd, capture_output=True).returncode != 0
 
 
+@pytest.mark.skipif(not os.path.exists(CLI), reason="bin/lambda3_b200 not built")
+@pytest.mark.parametrize("case,domain", [("prot_flat", 0), ("prot_diverged", 0), ("nucl", 1), ("bisulfite", 2),
+                                         ("blastx", 0), ("tblastn", 0), ("tblastx", 0)])
+def test_cli_m9_is_byte_identical_to_reference(golden_dir, case, domain):
+    """.m9 = tabular with comment lines: program tag of all six BLAST modes, records only for queries with
+    matches, footer with the record count; with and without the version string"""
+    cwd = os.path.join(golden_dir, case)
+    for name, extra in (("none.m9", ["--version-to-outputfile", "0"]), ("none.v1.m9", [])):
+        out = os.path.join(cwd, "cli_" + name)
+        if os.path.exists(out):
+            os.remove(out)
+        subprocess.run([CLI, ("searchp", "searchn", "searchbs")[domain], "-q", "q.fasta", "-i", "db.lba", "-o",
+                        "cli_" + name, "-t", "1", "-v", "0", *extra], check=True, cwd=cwd)
+        assert open(out).read() == open(os.path.join(cwd, name)).read(), name
+
+
 def test_multi_stream_split_is_invisible(golden_dir):
     """large batches are cut into sub-batches running concurrently on several streams / host threads:
     hits, their order and every counter must equal the strictly serial run"""
