@@ -152,6 +152,8 @@ typedef struct
                                            LGPU_ALPH_DNA5 with a protein index = translated query
                                            (BLASTX / TBLASTX, --query-alphabet dna5);
                                            LGPU_ALPH_AMINO_ACID = protein query (BLASTP / TBLASTN) */
+    uint32_t         want_cigar;        /* 1: also return the gapped rows of every hit as run-length
+                                           operations (needed for SAM / pairwise output)          */
 } lgpu_params;
 
 int lgpu_params_default(lgpu_params * out, uint32_t domain, char const * profile);
@@ -201,12 +203,24 @@ typedef struct
     uint8_t  reserved;
     double   bit_score;  /* computeBitScore, SQ/blast/blast_statistics.h:1027        */
     double   evalue;     /* computeEValueThreadSafe, src/search_misc.hpp:57          */
+    uint32_t cigar_off, cigar_len; /* lgpu_params.want_cigar: the gapped rows (alignRow0 / alignRow1 of the
+                                      BlastMatch) as run-length operations cigar_ops[cigar_off ..
+                                      cigar_off + cigar_len), in traceback order (alignment END first)    */
 } lgpu_hit;
+
+/* One run of the alignment: length << 2 | kind, kind 0 = aligned columns (M), 1 = query residues against a
+ * gap in the subject row (I), 2 = subject residues against a gap in the query row (D)
+ * (src/search_output.hpp:116-196 builds the SAM CIGAR from exactly these runs). */
+#define LGPU_CIGAR_M 0u
+#define LGPU_CIGAR_I 1u
+#define LGPU_CIGAR_D 2u
 
 typedef struct
 {
     lgpu_hit const * hits; /* owned by the context until the next search call */
     uint64_t         n;
+    uint32_t const * cigar_ops; /* NULL unless lgpu_params.want_cigar */
+    uint64_t         n_cigar_ops;
 } lgpu_hits;
 
 /* The reference's StatsHolder funnel (src/search_datastructures.hpp:70-215) + device timings. */

@@ -15,7 +15,7 @@ class Params(C.Structure):
                 ("scoring_method", C.c_int32), ("gap_open", C.c_int32), ("gap_extend", C.c_int32),
                 ("match", C.c_int32), ("mismatch", C.c_int32), ("min_bit_score", C.c_int32),
                 ("max_evalue", C.c_double), ("id_cutoff", C.c_int32), ("finalize", C.c_uint32),
-                ("query_alph", C.c_uint32)]
+                ("query_alph", C.c_uint32), ("want_cigar", C.c_uint32)]
 
 
 class IndexDesc(C.Structure):
@@ -35,7 +35,7 @@ class QueryBatch(C.Structure):
 
 
 class Hits(C.Structure):
-    _fields_ = [("hits", C.c_void_p), ("n", C.c_uint64)]
+    _fields_ = [("hits", C.c_void_p), ("n", C.c_uint64), ("cigar_ops", C.c_void_p), ("n_cigar_ops", C.c_uint64)]
 
 
 MATCH_DT = np.dtype([("qry_id", "<u4"), ("subj_id", "<u4"), ("qry_start", "<u4"), ("qry_end", "<u4"),
@@ -44,8 +44,8 @@ HIT_DT = np.dtype([("q_id", "<u4"), ("s_id", "<u4"), ("q_start", "<u4"), ("q_end
                    ("s_end", "<u4"), ("q_len", "<u4"), ("s_len", "<u4"), ("score", "<i4"), ("n_match", "<u4"),
                    ("n_mismatch", "<u4"), ("n_gap_open", "<u4"), ("n_gap_ext", "<u4"), ("n_positive", "<u4"),
                    ("aln_len", "<u4"), ("q_frame", "i1"), ("s_frame", "i1"), ("phase", "u1"), ("reserved", "u1"),
-                   ("bit_score", "<f8"), ("evalue", "<f8")])
-assert HIT_DT.itemsize == 80
+                   ("bit_score", "<f8"), ("evalue", "<f8"), ("cigar_off", "<u4"), ("cigar_len", "<u4")])
+assert HIT_DT.itemsize == 88
 STATS_U64 = ("hits_after_seeding", "hits_failed_pre_extend", "hits_failed_evalue", "hits_failed_bitscore",
              "hits_failed_identity", "hits_duplicate", "hits_duplicate2", "hits_abundant", "hits_final", "pairs",
              "qrys_with_hit", "n_extensions_score", "n_extensions_trace", "cells_score", "cells_trace",

@@ -202,6 +202,10 @@ class Searcher:
         out = Hits()
         st = np.zeros(1, STATS_DT)
         _check(lib.lgpu_search_batch(self._h, C.byref(qb), C.byref(out), _p(st)), self._h)
+        self.last_cigar_ops = None
+        if out.cigar_ops and out.n_cigar_ops:
+            rawc = (C.c_uint32 * out.n_cigar_ops).from_address(out.cigar_ops)
+            self.last_cigar_ops = np.frombuffer(rawc, np.uint32).copy()  # see lgpu_hit.cigar_off / cigar_len
         if not out.n:
             return np.zeros(0, HIT_DT), st[0]
         raw = (C.c_char * (out.n * HIT_DT.itemsize)).from_address(out.hits)

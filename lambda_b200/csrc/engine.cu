@@ -332,6 +332,9 @@ struct lgpu_ctx
 
     // host results
     std::vector<lgpu_hit>   hits;
+    std::vector<uint32_t>   cigar;       // run-length ops of the hits (lgpu_params.want_cigar), see lgpu_hit::cigar_off
+    DevBuf<unsigned int>    dCigarCap, dCigarOff, dCigar;
+    PinnedBuf<unsigned int> hCigarStage;
     std::vector<lgpu_match> matchesHost;
     cudaEvent_t             ev[8]{};
 
@@ -828,6 +831,40 @@ static void runScorePass(lgpu_ctx & c, lgpu_match const * dTasks, unsigned int n
     }
 }
 
+// Second traceback pass for lgpu_params.want_cigar: the first pass left n_gap_open in c.dHits, which bounds the
+// number of runs of every alignment; `launch(emitParams...)` re-walks the same trace and writes the runs.
+// `order` = device list of the `cnt` hit slots handled by this launch (nullptr: slots 0 .. cnt-1).
+template <typename TLaunch>
+static void emitCigars(lgpu_ctx & c, unsigned int const * order, unsigned int cnt, TLaunch && launch, lgpu_stats * st)
+{
+    if (cnt == 0)
+        return;
+    c.dCigarCap.reserve(cnt + 1);
+    c.dCigarOff.reserve(cnt + 1);
+    cigarCapKernel<<<gridFor(cnt, 256), 256, 0, c.stream>>>(c.dHits.p, order, cnt, c.dCigarCap.p);
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, c.dCigarCap.p, c.dCigarOff.p, static_cast<int>(cnt), c.stream);
+    c.dCubTemp.reserve(tb);
+    tb = c.dCubTemp.cap;
+    LGPU_CUDA(cub::DeviceScan::ExclusiveSum(c.dCubTemp.p, tb, c.dCigarCap.p, c.dCigarOff.p, static_cast<int>(cnt), c.stream));
+    unsigned int lastOff = 0, lastCap = 0;
+    LGPU_CUDA(cudaMemcpyAsync(&lastOff, c.dCigarOff.p + (cnt - 1), 4, cudaMemcpyDeviceToHost, c.stream));
+    LGPU_CUDA(cudaMemcpyAsync(&lastCap, c.dCigarCap.p + (cnt - 1), 4, cudaMemcpyDeviceToHost, c.stream));
+    LGPU_CUDA(cudaStreamSynchronize(c.stream));
+    size_t const total = static_cast<size_t>(lastOff) + lastCap;
+    if (c.cigar.size() + total > 0xffffffffull)
+        throw ArgError("too many alignment operations in one batch; use smaller batches with want_cigar");
+    c.dCigar.reserve(total);
+    c.hCigarStage.reserve(total);
+    launch(c.dCigar.p, c.dCigarOff.p, static_cast<unsigned int>(c.cigar.size()));
+    LGPU_CUDA(cudaGetLastError());
+    LGPU_CUDA(cudaMemcpyAsync(c.hCigarStage.p, c.dCigar.p, total * 4, cudaMemcpyDeviceToHost, c.stream));
+    LGPU_CUDA(cudaStreamSynchronize(c.stream));
+    c.cigar.insert(c.cigar.end(), c.hCigarStage.p, c.hCigarStage.p + total);
+    if (st)
+        st->kernel_launches += 3;
+}
+
 // DP pass 2 + traceback on the scalar wavefront kernel (1 trace byte per cell) for `n` tasks
 // (host copy `tasks`, device copy dTasks); results land in c.hHits[0..n)
 static void runTraceScalar(lgpu_ctx & c, lgpu_match const * tasks, size_t n, lgpu_match const * dTasks, lgpu_stats * st)
@@ -884,6 +921,14 @@ static void runTraceScalar(lgpu_ctx & c, lgpu_match const * tasks, size_t n, lgp
         TP.out          = c.dHits.p;
         tracebackKernel<<<gridFor(cnt, 128), 128, 0, c.stream>>>(TP);
         LGPU_CUDA(cudaGetLastError());
+        if (c.params.want_cigar)
+            emitCigars(c, nullptr, cnt, [&](unsigned int * ops, unsigned int const * off, unsigned int base) {
+                TP.emit      = 1;
+                TP.cigarOps  = ops;
+                TP.cigarOff  = off;
+                TP.cigarBase = base;
+                tracebackKernel<<<gridFor(cnt, 128), 128, 0, c.stream>>>(TP);
+            }, st);
         LGPU_CUDA(cudaMemcpyAsync(c.hHits.p + begin, c.dHits.p, cnt * sizeof(lgpu_hit), cudaMemcpyDeviceToHost, c.stream));
         LGPU_CUDA(cudaStreamSynchronize(c.stream));
         if (st)
@@ -1041,7 +1086,7 @@ static void runTracePass(lgpu_ctx & c, lgpu_match const * tasks, size_t n, lgpu_
     int const  D      = c.scoring.gapExtend - c.scoring.gapOpenSeqan;
     bool const dpxOk  = c.dpxOk && D >= 0 && D <= 14 && !c.forceScalarTrace;
     uint64_t   cells  = 0;
-    bool const useCk        = !c.planeTrace;
+    bool const useCk        = !c.planeTrace && !c.params.want_cigar; // the checkpoint traceback has no emit pass
     int const  nPackedClass = useCk ? kNumCkClasses : kNumTraceClasses;
     std::vector<std::vector<unsigned int>> lists(std::max(kNumCkClasses, kNumTraceClasses) + 1);
     for (size_t i = 0; i < n; ++i)
@@ -1149,6 +1194,14 @@ static void runTracePass(lgpu_ctx & c, lgpu_match const * tasks, size_t n, lgpu_
             TP.out       = c.dHits.p;
             tracebackDpxKernel<<<gridFor(cnt, 128), 128, 0, c.stream>>>(TP);
             LGPU_CUDA(cudaGetLastError());
+            if (c.params.want_cigar)
+                emitCigars(c, c.dOrder.p, cnt, [&](unsigned int * ops, unsigned int const * off, unsigned int base) {
+                    TP.emit      = 1;
+                    TP.cigarOps  = ops;
+                    TP.cigarOff  = off;
+                    TP.cigarBase = base;
+                    tracebackDpxKernel<<<gridFor(cnt, 128), 128, 0, c.stream>>>(TP);
+                }, st);
             LGPU_CUDA(cudaStreamSynchronize(c.stream)); // the order / offset staging arrays are reused by the next chunk
             if (st)
                 st->kernel_launches += 2;
@@ -1285,6 +1338,7 @@ static void searchOne(lgpu_ctx & c, BatchView const & qb, lgpu_stats * st)
 {
     LGPU_CUDA(cudaSetDevice(c.index->device));
     c.hits.clear();
+    c.cigar.clear();
     uploadQueries(c, qb, st);
     if (!c.nQueries)
         return;
@@ -1437,14 +1491,20 @@ static void searchBatch(lgpu_ctx & c, lgpu_query_batch const & qb, lgpu_hits * o
             if (!err[w].empty())
                 throw CudaError("worker " + std::to_string(w) + ": " + err[w]);
         c.hits.clear();
+        c.cigar.clear();
         for (unsigned int w = 0; w < nW; ++w)
         {
             lgpu_ctx &     wc   = *c.workers[w];
             uint64_t const b    = all.n * w / nW;
             size_t const   base = c.hits.size();
+            uint32_t const cigarBase = static_cast<uint32_t>(c.cigar.size());
             c.hits.insert(c.hits.end(), wc.hits.begin(), wc.hits.end());
+            c.cigar.insert(c.cigar.end(), wc.cigar.begin(), wc.cigar.end());
             for (size_t i = base; i < c.hits.size(); ++i)
+            {
                 c.hits[i].q_id += static_cast<uint32_t>(b);
+                c.hits[i].cigar_off += cigarBase;
+            }
             LGPU_CUDA(cudaStreamWaitEvent(c.stream, wc.ev[4], 0));
             if (st)
                 addStats(*st, wst[w]);
@@ -1458,8 +1518,10 @@ static void searchBatch(lgpu_ctx & c, lgpu_query_batch const & qb, lgpu_hits * o
         cudaEventElapsedTime(&ms, c.ev[2], c.ev[3]);
         st->ms_total += ms;
     }
-    out->hits = c.hits.data();
-    out->n    = c.hits.size();
+    out->hits        = c.hits.data();
+    out->n           = c.hits.size();
+    out->cigar_ops   = c.params.want_cigar ? c.cigar.data() : nullptr;
+    out->n_cigar_ops = c.params.want_cigar ? c.cigar.size() : 0;
 }
 
 } // namespace lgpu

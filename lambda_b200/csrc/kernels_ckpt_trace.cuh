@@ -714,6 +714,8 @@ __global__ void __launch_bounds__(kCkTbThreads) tracebackCkKernel(TracebackCkPar
     h.reserved   = 0;
     h.bit_score  = 0.0;
     h.evalue     = 0.0;
+    h.cigar_off  = 0;
+    h.cigar_len  = 0;
     P.out[task]  = h;
 #undef LGPU_HH
 #undef LGPU_NN

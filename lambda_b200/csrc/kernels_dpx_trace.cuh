@@ -277,6 +277,11 @@ struct TracebackDpxParams
     unsigned int const *       planes;
     unsigned long long const * planeOff;
     lgpu_hit *                 out; // indexed by task
+    // second pass (lgpu_params.want_cigar): emit the runs of the path instead of the record
+    int                        emit;
+    unsigned int *             cigarOps;  // run << 2 | kind, traceback order
+    unsigned int const *       cigarOff;  // per slot of `order`: first op of the alignment
+    unsigned int               cigarBase; // added to the offsets stored in the records
 };
 
 __global__ void __launch_bounds__(128) tracebackDpxKernel(TracebackDpxParams P)
@@ -351,6 +356,8 @@ __global__ void __launch_bounds__(128) tracebackDpxKernel(TracebackDpxParams P)
             }
     unsigned int const bi = i, bj = j;
     unsigned int nMatch = 0, nMismatch = 0, nPositive = 0, nGapOpen = 0, nGapExt = 0, alnLen = 0;
+    unsigned int nOps = 0;
+    unsigned int * const ops = P.emit ? P.cigarOps + P.cigarOff[t] : nullptr;
 
     if (score > 0 && j > 0)
     {
@@ -363,6 +370,8 @@ __global__ void __launch_bounds__(128) tracebackDpxKernel(TracebackDpxParams P)
         auto flush = [&]() {
             if (run)
             {
+                if (ops)
+                    ops[nOps++] = (run << 2) | static_cast<unsigned int>(last);
                 alnLen += run;
                 if (last != 0)
                 {
@@ -423,6 +432,12 @@ __global__ void __launch_bounds__(128) tracebackDpxKernel(TracebackDpxParams P)
         flush();
     }
 
+    if (P.emit)
+    {
+        P.out[task].cigar_off = P.cigarBase + P.cigarOff[t];
+        P.out[task].cigar_len = nOps;
+        return;
+    }
     lgpu_hit h;
     h.q_id       = q;
     h.s_id       = sId;
@@ -444,6 +459,8 @@ __global__ void __launch_bounds__(128) tracebackDpxKernel(TracebackDpxParams P)
     h.reserved   = 0;
     h.bit_score  = 0.0;
     h.evalue     = 0.0;
+    h.cigar_off  = 0;
+    h.cigar_len  = 0;
     P.out[task]  = h;
 }
 

@@ -364,6 +364,11 @@ struct TracebackParams
     unsigned long long const * traceOff;
     unsigned int               K;            // columns per lane used by the fill kernel (storage: roundup4(K) bytes)
     lgpu_hit *                 out;
+    // second pass (lgpu_params.want_cigar): emit the runs of the path instead of the record
+    int                        emit;
+    unsigned int *             cigarOps;
+    unsigned int const *       cigarOff; // per task
+    unsigned int               cigarBase;
 };
 
 __global__ void __launch_bounds__(128) tracebackKernel(TracebackParams P)
@@ -388,6 +393,8 @@ __global__ void __launch_bounds__(128) tracebackKernel(TracebackParams P)
     unsigned int       i = P.bestPos[2 * task], j = P.bestPos[2 * task + 1];
     unsigned int const bi = i, bj = j;
     unsigned int nMatch = 0, nMismatch = 0, nPositive = 0, nGapOpen = 0, nGapExt = 0, alnLen = 0;
+    unsigned int nOps = 0;
+    unsigned int * const ops = P.emit ? P.cigarOps + P.cigarOff[task] : nullptr;
 
     auto tr = [&](unsigned int ii, unsigned int jj) -> unsigned int {
         // column i-1 lives in strip (i-1) / K at byte (i-1) % K of that strip's KS-byte slot
@@ -405,6 +412,8 @@ __global__ void __launch_bounds__(128) tracebackKernel(TracebackParams P)
         auto flush = [&]() {
             if (run)
             {
+                if (ops)
+                    ops[nOps++] = (run << 2) | static_cast<unsigned int>(last);
                 alnLen += run;
                 if (last != 0)
                 {
@@ -465,6 +474,12 @@ __global__ void __launch_bounds__(128) tracebackKernel(TracebackParams P)
         flush();
     }
 
+    if (P.emit)
+    {
+        P.out[task].cigar_off = P.cigarBase + P.cigarOff[task];
+        P.out[task].cigar_len = nOps;
+        return;
+    }
     lgpu_hit h;
     h.q_id       = q;
     h.s_id       = sId;
@@ -486,7 +501,17 @@ __global__ void __launch_bounds__(128) tracebackKernel(TracebackParams P)
     h.reserved   = 0;
     h.bit_score  = 0.0;
     h.evalue     = 0.0;
+    h.cigar_off  = 0;
+    h.cigar_len  = 0;
     P.out[task]  = h;
+}
+
+// upper bound of the runs of every alignment: gaps and aligned stretches alternate
+__global__ void cigarCapKernel(lgpu_hit const * hits, unsigned int const * order, unsigned int n, unsigned int * cap)
+{
+    unsigned int const t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n)
+        cap[t] = 2u * hits[order ? order[t] : t].n_gap_open + 1u;
 }
 
 // pass-1 filter: keep[t] = score passes both integer thresholds of its query

@@ -33,6 +33,8 @@ struct Options
     int         threads   = 1; // only used for the reference's records_per_batch formula
     int         gpus      = 1;
     bool        comments  = false; // .m9: BLAST tabular with comment lines
+    bool        sam       = false; // .sam (default tags AS NM ae ai qf, --sam-bam-seq uniq, --sam-bam-clip hard)
+    std::string commandLine;
     bool        versionToOutput = true;
     uint64_t    blockSize = 100000;
     lgpu_params params{};
@@ -52,7 +54,7 @@ bool endsWith(std::string const & s, char const * suf)
 
 void usage()
 {
-    std::puts("lambda3_b200 searchp|searchn|searchbs -q QUERY.fasta -i INDEX.lba [-o output.m8|.m9] [OPTIONS]\n"
+    std::puts("lambda3_b200 searchp|searchn|searchbs -q QUERY.fasta -i INDEX.lba [-o output.m8|.m9|.sam] [OPTIONS]\n"
               "  -a, --input-alphabet   auto|dna5|aminoacid (searchp; dna queries are translated: BLASTX/TBLASTX)\n"
               "  -p, --profile          none|fast|sensitive|pairs-default|pairs-sensitive\n"
               "  -e, --e-value          maximum e-value (default 0.01; -1 = off)\n"
@@ -148,8 +150,12 @@ void parse(int argc, char ** argv, Options & o)
     if (o.domain != LGPU_DOMAIN_PROTEIN && o.inputAlphabet != "auto")
         die("--input-alphabet is a searchp option");
     o.comments = endsWith(o.output, ".m9");
-    if (!endsWith(o.output, ".m8") && !o.comments)
-        die("only BLAST tabular output (.m8, .m9) is produced by the GPU path; other formats stay with the reference");
+    o.sam      = endsWith(o.output, ".sam");
+    if (!endsWith(o.output, ".m8") && !o.comments && !o.sam)
+        die("the GPU path writes .m8, .m9 and .sam; .m0 and .bam stay with the reference");
+    o.params.want_cigar = o.sam ? 1u : 0u;
+    for (int i = 0; i < argc; ++i)
+        o.commandLine += (i ? " " : "") + std::string(argv[i]);
     if (std::ifstream(o.output).good())
         die("the output file already exists: " + o.output); // sharg's create_new validator
 }
@@ -269,6 +275,7 @@ double now()
 struct ShardResult
 {
     std::vector<lgpu_hit> hits; // q_id already global
+    std::vector<uint32_t> cigar; // run-length ops of the hits (SAM output)
     lgpu_stats            stats{};
     std::string           error;
     double                tUpload = 0, tSearch = 0, tTeardown = 0; // seconds
@@ -308,10 +315,16 @@ void runShard(Options const & o, lgpu_index_desc const * desc, int device, Fasta
             out.error = lgpu_last_error(ctx);
             break;
         }
-        size_t const old = out.hits.size();
+        size_t const   old       = out.hits.size();
+        uint32_t const cigarBase = static_cast<uint32_t>(out.cigar.size());
         out.hits.insert(out.hits.end(), hits.hits, hits.hits + hits.n);
+        if (hits.cigar_ops)
+            out.cigar.insert(out.cigar.end(), hits.cigar_ops, hits.cigar_ops + hits.n_cigar_ops);
         for (size_t i = old; i < out.hits.size(); ++i)
+        {
             out.hits[i].q_id += static_cast<uint32_t>(b);
+            out.hits[i].cigar_off += cigarBase;
+        }
     }
     out.tSearch = now() - t1;
     double const t2 = now();
@@ -374,6 +387,13 @@ int main(int argc, char ** argv)
     for (auto const & r : res)
         for (auto const & h : r.hits)
             perQuery[h.q_id].push_back(&h);
+    // a hit's run-length ops live in the cigar vector of the shard that produced it
+    auto cigarOf = [&](lgpu_hit const * h) -> uint32_t const * {
+        for (auto const & r : res)
+            if (!r.hits.empty() && h >= r.hits.data() && h < r.hits.data() + r.hits.size())
+                return r.cigar.data() + h->cigar_off;
+        return nullptr;
+    };
     uint64_t const rpb = std::max<uint64_t>(std::min<uint64_t>(nQ / (static_cast<uint64_t>(o.threads) * 10), 10), 1);
     FILE *         fo  = std::fopen(o.output.c_str(), "wb");
     if (!fo)
@@ -405,6 +425,100 @@ int main(int argc, char ** argv)
                        "s. start, s. end, evalue, bit score\n", fo);
         std::fprintf(fo, "# %zu hits found\n", nHits);
     };
+    // ---- SAM (src/search_output.hpp:346-458 header, :482-716 records; defaults of src/search_options.hpp:339-370) ----
+    bool const isBlastN = desc->trans_alph != LGPU_ALPH_AMINO_ACID;
+    if (o.sam)
+    {
+        std::fputs("@HD\tVN:1.4\tGO:query\n", fo);
+        if (o.versionToOutput)
+            std::fprintf(fo, "@PG\tID:lambda\tPN:lambda\tVN:3.0.0\tCL:%s\n", o.commandLine.c_str());
+        std::fputs("@CO\tLambda is a high performance BLAST compatible local aligner, please see http://seqan.de/lambda for "
+                   "more information.\n"
+                   "@CO\tSAM/BAM dialect documentation is available here: https://github.com/seqan/lambda/wiki/Output-Formats\n"
+                   "@CO\tIf you use any results found by Lambda, please cite Hauswedell et al. (2014) doi: "
+                   "10.1093/bioinformatics/btu439\n"
+                   "@CO\tOptional tags as follow\tAS:bit score\tNM:edit distance (in protein space unless BLASTN)\tae:expect "
+                   "value\tai:% identity (in protein space unless BLASTN) \tqf:query frame\n",
+                   fo);
+    }
+    std::string cigarStr, seqStr;
+    auto        samRecord = [&](uint64_t q, lgpu_hit const * h, lgpu_hit const * prev) {
+        uint64_t const qLen = f.offsets[q + 1] - f.offsets[q]; // record.qLength: original query length
+        // POS (src/search_output.hpp:499-510; the qLength in the reverse-frame branch is the reference's)
+        int32_t beginPos = static_cast<int32_t>(h->s_start);
+        if (sTrans)
+        {
+            beginPos = static_cast<int32_t>(h->s_start * 3 + static_cast<uint32_t>(std::abs(h->s_frame)) - 1);
+            if (h->s_frame < 0)
+                beginPos = static_cast<int32_t>(qLen) - beginPos;
+        }
+        unsigned flag = prev ? 256u : 0u;
+        if (h->q_frame < 0)
+            flag |= 16u;
+        // CIGAR (blastMatchOneCigar, :116-196): only for nucleotide queries; hard clips
+        cigarStr.clear();
+        if (isBlastN || qTrans)
+        {
+            unsigned const transFac       = qTrans ? 3 : 1;
+            unsigned const leftFrameClip  = static_cast<unsigned>(std::abs(h->q_frame)) - 1;
+            unsigned const rightFrameClip = qTrans ? static_cast<unsigned>((qLen - leftFrameClip) % 3) : 0;
+            uint64_t const srcLen         = qTrans ? (std::max<uint64_t>(qLen, leftFrameClip) - leftFrameClip) / 3 : qLen;
+            unsigned const leftClip       = h->q_start * transFac;
+            unsigned const rightClip      = static_cast<unsigned>(srcLen - h->q_end) * transFac;
+            std::vector<std::pair<char, unsigned>> el;
+            if (leftFrameClip + leftClip > 0)
+                el.push_back({'H', leftFrameClip + leftClip});
+            uint32_t const * ops = cigarOf(h);
+            for (uint32_t k = h->cigar_len; k-- > 0;) // stored END first
+            {
+                uint32_t const kind = ops[k] & 3u, run = ops[k] >> 2;
+                el.push_back({kind == LGPU_CIGAR_M ? 'M' : kind == LGPU_CIGAR_I ? 'I' : 'D', run * transFac});
+            }
+            if (rightFrameClip + rightClip > 0)
+                el.push_back({'H', rightFrameClip + rightClip});
+            if (h->q_frame < 0)
+                std::reverse(el.begin(), el.end());
+            for (auto const & e : el)
+                cigarStr += std::to_string(e.second) + e.first;
+        }
+        else
+            cigarStr = "*";
+        // SEQ (--sam-bam-seq uniq: only when frame or aligned query range differ from the previous match)
+        bool const writeSeq = !prev || prev->q_frame != h->q_frame || prev->q_start != h->q_start || prev->q_end != h->q_end;
+        seqStr.clear();
+        if (writeSeq && (isBlastN || qTrans))
+        {
+            static char const dna5[] = "ACGNT";
+            uint8_t const *   src    = f.residues.data() + f.offsets[q];
+            uint64_t          b = h->q_start, e = h->q_end; // in the frame's sequence
+            if (qTrans)
+            {
+                uint64_t const shift = static_cast<uint64_t>(std::abs(h->q_frame)) - 1;
+                b                    = 3 * b + shift;
+                e                    = 3 * e + shift;
+            }
+            static uint8_t const comp[5] = {4, 2, 1, 3, 0}; // dna5 ranks A C G N T
+            if (h->q_frame >= 0)
+                for (uint64_t i = b; i < e; ++i)
+                    seqStr += dna5[src[i]];
+            else // the frame is the reverse complement of the original query (_untranslateSequence, :84-109)
+                for (uint64_t i = b; i < e; ++i)
+                    seqStr += dna5[comp[src[qLen - 1 - i]]];
+        }
+        if (seqStr.empty())
+            seqStr = "*";
+        std::string const qName = f.ids[q].substr(0, f.ids[q].find_first_of(" \t\v\f\r\n"));
+        std::string       sName = subjectId(h->s_id);
+        sName                   = sName.substr(0, sName.find(' '));
+        char ev[64];
+        std::snprintf(ev, sizeof(ev), "%g", static_cast<double>(static_cast<float>(h->evalue)));
+        float const identity = static_cast<float>(100.0 * static_cast<float>(h->n_match) / static_cast<float>(h->aln_len));
+        std::fprintf(fo, "%s\t%u\t%s\t%d\t255\t%s\t*\t0\t0\t%s\t*\tae:f:%s\tAS:i:%u\tai:i:%u\tqf:i:%d\tNM:i:%u\n", qName.c_str(),
+                     flag, sName.c_str(), beginPos + 1, cigarStr.c_str(), seqStr.c_str(), ev,
+                     static_cast<unsigned>(static_cast<uint16_t>(h->bit_score)),
+                     static_cast<unsigned>(static_cast<uint8_t>(identity)), static_cast<int>(h->q_frame),
+                     h->aln_len - h->n_match);
+    };
     // the reference chunks the queries per thread first (src/search.cpp:384-385), then into batches
     for (int t = 0; t < o.threads; ++t)
     {
@@ -420,6 +534,17 @@ int main(int argc, char ** argv)
                         nHits += h->phase == phase;
                     if (nHits)
                         recordHeader(q, nHits);
+                    if (o.sam)
+                    {
+                        lgpu_hit const * prev = nullptr;
+                        for (lgpu_hit const * h : perQuery[q])
+                            if (h->phase == phase)
+                            {
+                                samRecord(q, h, prev);
+                                prev = h;
+                            }
+                        continue;
+                    }
                     for (lgpu_hit const * h : perQuery[q])
                         if (h->phase == phase)
                         {

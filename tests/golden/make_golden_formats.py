@@ -1,7 +1,7 @@
 #!/usr/bin/env python
-"""Golden `.m9` files (BLAST tabular with comment lines) from the unmodified reference binary, for the
-committed index / query fixtures of a few cases:  <case>/none.m9 (--version-to-outputfile 0) and
-<case>/none.v1.m9 (default version string).  The reference is run inside the case directory with
+"""Golden `.m9` (BLAST tabular with comment lines) and `.sam` files from the unmodified reference binary, for
+the committed index / query fixtures:  <case>/none.m9, <case>/none.sam (--version-to-outputfile 0) and
+<case>/none.v1.m9 (default version string; the SAM @PG line echoes the command line, so only v0 is kept).  The reference is run inside the case directory with
 `-i db.lba`, because the index path is echoed in the `# Database:` line."""
 import gzip
 import os
@@ -11,8 +11,8 @@ import tempfile
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.path.join(os.path.dirname(os.path.dirname(HERE)), "oracle", "_ref", "lambda3")
-CASES = [("prot_flat", "searchp"), ("prot_diverged", "searchp"), ("nucl", "searchn"), ("bisulfite", "searchbs"),
-         ("blastx", "searchp"), ("tblastn", "searchp"), ("tblastx", "searchp")]
+CASES = [("prot_flat", "searchp"), ("prot_family", "searchp"), ("prot_diverged", "searchp"), ("nucl", "searchn"),
+         ("bisulfite", "searchbs"), ("blastx", "searchp"), ("tblastn", "searchp"), ("tblastx", "searchp")]
 
 for case, cmd in CASES:
     src = os.path.join(HERE, case)
@@ -20,7 +20,8 @@ for case, cmd in CASES:
         with gzip.open(os.path.join(src, "db.lba.gz"), "rb") as fi, open(os.path.join(tmp, "db.lba"), "wb") as fo:
             shutil.copyfileobj(fi, fo)
         shutil.copy(os.path.join(src, "q.fasta"), tmp)
-        for name, extra in (("none.m9", ["--version-to-outputfile", "0"]), ("none.v1.m9", [])):
+        for name, extra in (("none.m9", ["--version-to-outputfile", "0"]), ("none.v1.m9", []),
+                            ("none.sam", ["--version-to-outputfile", "0"])):
             subprocess.check_call([REF, cmd, "-q", "q.fasta", "-i", "db.lba", "-o", name, "-t", "1", "-v", "0", *extra], cwd=tmp)
             shutil.copy(os.path.join(tmp, name), os.path.join(src, name))
             print(case, name, sum(1 for _ in open(os.path.join(src, name))), "lines")

@@ -295,6 +295,48 @@ def test_cli_m9_is_byte_identical_to_reference(golden_dir, case, domain):
         assert open(out).read() == open(os.path.join(cwd, name)).read(), name
 
 
+@pytest.mark.skipif(not os.path.exists(CLI), reason="bin/lambda3_b200 not built")
+@pytest.mark.parametrize("case,domain", [("prot_flat", 0), ("prot_family", 0), ("prot_diverged", 0), ("nucl", 1),
+                                         ("bisulfite", 2), ("blastx", 0), ("tblastn", 0), ("tblastx", 0)])
+def test_cli_sam_is_byte_identical_to_reference(golden_dir, case, domain):
+    """.sam with the reference's default tags / clipping: CIGARs come from the device traceback (run-length
+    operations of the gapped rows), sequences from the query frames; all six BLAST modes"""
+    cwd = os.path.join(golden_dir, case)
+    out = os.path.join(cwd, "cli_none.sam")
+    if os.path.exists(out):
+        os.remove(out)
+    subprocess.run([CLI, ("searchp", "searchn", "searchbs")[domain], "-q", "q.fasta", "-i", "db.lba", "-o",
+                    "cli_none.sam", "-t", "1", "-v", "0", "--version-to-outputfile", "0"], check=True, cwd=cwd)
+    ours, ref = open(out).read().splitlines(), open(os.path.join(cwd, "none.sam")).read().splitlines()
+    assert len(ours) == len(ref)
+    for a, b in zip(ours, ref):
+        assert a == b
+
+
+def test_cigar_runs_are_consistent(golden_dir):
+    """want_cigar through the API: the runs of every hit add up to its coordinates and statistics"""
+    for case, domain in (("prot_family", 0), ("nucl", 1)):
+        path, ids, res, offs = _load(golden_dir, case, domain)
+        ix = lambda_b200.Index.load(path)
+        s = lambda_b200.Searcher(ix, domain, "none", want_cigar=1)
+        hits, st = s.search(res, offs)
+        ops = s.last_cigar_ops
+        assert len(hits) and ops is not None
+        for h in hits:
+            r = ops[h["cigar_off"]:h["cigar_off"] + h["cigar_len"]]
+            kind, run = r & 3, r >> 2
+            assert run[kind != 2].sum() == h["q_end"] - h["q_start"]
+            assert run[kind != 1].sum() == h["s_end"] - h["s_start"]
+            assert run.sum() == h["aln_len"] and (kind != 0).sum() == h["n_gap_open"]
+            assert (kind[1:] != kind[:-1]).all()
+        # the same search without cigars returns the same records
+        s2 = lambda_b200.Searcher(ix, domain, "none")
+        h2, _ = s2.search(res, offs)
+        for f in HIT_INT_FIELDS:
+            assert (h2[f] == hits[f]).all(), f
+        s.close(); s2.close(); ix.close()
+
+
 def test_multi_stream_split_is_invisible(golden_dir):
     """large batches are cut into sub-batches running concurrently on several streams / host threads:
     hits, their order and every counter must equal the strictly serial run"""
