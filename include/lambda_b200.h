@@ -294,6 +294,10 @@ int lgpu_fm_locate(lgpu_index const *, uint64_t const * rows, uint64_t n, uint64
  * Host-side statistics and output helpers (kept on the host like the reference: a10/a14/App. C).
  * ---------------------------------------------------------------------------------------------- */
 int lgpu_bit_score(lgpu_params const *, int32_t raw_score, double * out);
+/* Karlin-Altschul parameters of the scoring scheme (SQ/blast/blast_statistics.h tables) and the substitution
+ * matrix the alignments use (32 x 32 int8, [query rank * 32 + subject rank]); for report-style output. */
+int lgpu_ka_params(lgpu_params const *, double * lambda, double * k, double * h);
+int lgpu_score_matrix(lgpu_params const *, int8_t * out_32x32);
 int lgpu_evalue(lgpu_params const *, int32_t raw_score, uint64_t query_len, uint64_t db_total_len,
                 double * out);
 /* smallest raw score that passes both the bit-score and the e-value filter for this query length */

@@ -65,6 +65,8 @@ def load_library():
     lib.lgpu_fm_rank.argtypes = [vp, vp, vp, u64, vp]
     lib.lgpu_fm_locate.argtypes = [vp, vp, u64, vp, vp]
     lib.lgpu_bit_score.argtypes = [C.POINTER(Params), C.c_int32, C.POINTER(C.c_double)]
+    lib.lgpu_ka_params.argtypes = [C.POINTER(Params)] + [C.POINTER(C.c_double)] * 3
+    lib.lgpu_score_matrix.argtypes = [C.POINTER(Params), vp]
     lib.lgpu_evalue.argtypes = [C.POINTER(Params), C.c_int32, u64, u64, C.POINTER(C.c_double)]
     lib.lgpu_min_raw_score.argtypes = [C.POINTER(Params), u64, u64, C.POINTER(C.c_int32)]
     lib.lgpu_format_m8.argtypes = [C.POINTER(Params), vp, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]

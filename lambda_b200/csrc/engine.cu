@@ -1959,6 +1959,30 @@ int lgpu_bit_score(lgpu_params const * p, int32_t raw, double * out)
     return LGPU_OK;
 }
 
+int lgpu_ka_params(lgpu_params const * p, double * lambda, double * k, double * h)
+{
+    if (!p || !lambda || !k || !h)
+        return LGPU_ERR_ARG;
+    KarlinAltschul const ka = selectKA(*p);
+    if (!ka.valid)
+        return LGPU_ERR_ARG;
+    *lambda = ka.lambda;
+    *k      = ka.K;
+    *h      = ka.H;
+    return LGPU_OK;
+}
+
+int lgpu_score_matrix(lgpu_params const * p, int8_t * out)
+{
+    if (!p || !out)
+        return LGPU_ERR_ARG;
+    Scoring sc;
+    if (makeScoring(sc, *p) != 0)
+        return LGPU_ERR_ARG;
+    std::memcpy(out, sc.matrix, 32 * 32);
+    return LGPU_OK;
+}
+
 int lgpu_evalue(lgpu_params const * p, int32_t raw, uint64_t qLen, uint64_t dbLen, double * out)
 {
     if (!p || !out)

@@ -20,7 +20,10 @@
 #include <thread>
 #include <vector>
 
+#include <cmath>
+
 #include "../../include/lambda_b200.h"
+#include "tables_generated.inc" // alphabets and the genetic code, for the report-style outputs
 
 namespace
 {
@@ -33,6 +36,7 @@ struct Options
     int         threads   = 1; // only used for the reference's records_per_batch formula
     int         gpus      = 1;
     bool        comments  = false; // .m9: BLAST tabular with comment lines
+    bool        report    = false; // .m0: BLAST pairwise report
     bool        sam       = false; // .sam (default tags AS NM ae ai qf, --sam-bam-seq uniq, --sam-bam-clip hard)
     std::string commandLine;
     bool        versionToOutput = true;
@@ -54,7 +58,7 @@ bool endsWith(std::string const & s, char const * suf)
 
 void usage()
 {
-    std::puts("lambda3_b200 searchp|searchn|searchbs -q QUERY.fasta -i INDEX.lba [-o output.m8|.m9|.sam] [OPTIONS]\n"
+    std::puts("lambda3_b200 searchp|searchn|searchbs -q QUERY.fasta -i INDEX.lba [-o output.m0|.m8|.m9|.sam] [OPTIONS]\n"
               "  -a, --input-alphabet   auto|dna5|aminoacid (searchp; dna queries are translated: BLASTX/TBLASTX)\n"
               "  -p, --profile          none|fast|sensitive|pairs-default|pairs-sensitive\n"
               "  -e, --e-value          maximum e-value (default 0.01; -1 = off)\n"
@@ -151,9 +155,10 @@ void parse(int argc, char ** argv, Options & o)
         die("--input-alphabet is a searchp option");
     o.comments = endsWith(o.output, ".m9");
     o.sam      = endsWith(o.output, ".sam");
-    if (!endsWith(o.output, ".m8") && !o.comments && !o.sam)
-        die("the GPU path writes .m8, .m9 and .sam; .m0 and .bam stay with the reference");
-    o.params.want_cigar = o.sam ? 1u : 0u;
+    o.report   = endsWith(o.output, ".m0");
+    if (!endsWith(o.output, ".m8") && !o.comments && !o.sam && !o.report)
+        die("the GPU path writes .m0, .m8, .m9 and .sam; .bam stays with the reference");
+    o.params.want_cigar = (o.sam || o.report) ? 1u : 0u;
     for (int i = 0; i < argc; ++i)
         o.commandLine += (i ? " " : "") + std::string(argv[i]);
     if (std::ifstream(o.output).good())
@@ -519,6 +524,196 @@ int main(int argc, char ** argv)
                      static_cast<unsigned>(static_cast<uint8_t>(identity)), static_cast<int>(h->q_frame),
                      h->aln_len - h->n_match);
     };
+    // ---- .m0: BLAST pairwise report (SQ/blast/blast_report_out.h:296-868) ----
+    bool const bsIndex   = desc->red_alph == LGPU_ALPH_DNA3BS;
+    auto       frameLen  = [](uint64_t len, unsigned f) { uint64_t const o = f % 3; return (std::max(len, o) - o) / 3; };
+    // residue k (as a character) of frame `frame` of a stored sequence: strands for nucleotide searches,
+    // six-frame translation (canonical code) for translated ones, the sequence itself otherwise
+    auto frameChar = [&](uint8_t const * seq, uint64_t len, bool translated, bool nucleotide, int frame, uint64_t k) -> char {
+        if (translated)
+        {
+            uint64_t const pos = 3 * k + static_cast<uint64_t>(std::abs(frame)) - 1;
+            unsigned n1, n2, n3;
+            if (frame > 0)
+            {
+                n1 = seq[pos]; n2 = seq[pos + 1]; n3 = seq[pos + 2];
+            }
+            else
+            {
+                n1 = kDna5Complement[seq[len - pos - 1]]; n2 = kDna5Complement[seq[len - pos - 2]];
+                n3 = kDna5Complement[seq[len - pos - 3]];
+            }
+            return kAa27RankToChar[kDna5Translate[(n1 * 5 + n2) * 5 + n3]];
+        }
+        if (nucleotide)
+            return kDna5RankToChar[frame < 0 ? kDna5Complement[seq[len - 1 - k]] : seq[k]];
+        return kAa27RankToChar[seq[k]];
+    };
+    double  kaLambda = 0, kaK = 0, kaH = 0;
+    int8_t  scoreMat[32 * 32];
+    uint64_t dbLetters = desc->n_residues, dbSeqs = desc->n_seqs;
+    if (o.report)
+    {
+        if (lgpu_ka_params(&o.params, &kaLambda, &kaK, &kaH) != LGPU_OK || lgpu_score_matrix(&o.params, scoreMat) != LGPU_OK)
+            die("no statistics for this scoring scheme");
+        if (sTrans)
+        {
+            dbSeqs *= 6;
+            dbLetters = 0;
+            for (uint64_t sq = 0; sq < desc->n_seqs; ++sq)
+                for (unsigned fr = 0; fr < 6; ++fr)
+                    dbLetters += frameLen(desc->seq_delims[sq + 1] - desc->seq_delims[sq], fr);
+        }
+        else if (bsIndex)
+        {
+            dbSeqs *= 2;
+            dbLetters *= 2;
+        }
+        std::fprintf(fo, "%s\n\n\nReference: Altschul, Stephen F., Thomas L. Madden, Alejandro A. Schaffer,\nJinghui Zhang, Zheng "
+                         "Zhang, Webb Miller, and David J. Lipman (1997),\n\"Gapped BLAST and PSI-BLAST: a new generation of "
+                         "protein database search\nprograms\",  Nucleic Acids Res. 25:3389-3402.\n\n\n\nReference for SeqAn: "
+                         "Doering, A., D. Weese, T. Rausch, K. Reinert (2008): SeqAn --\nAn efficient, generic C++ library for "
+                         "sequence analysis. BMC Bioinformatics,\n9(1), 11. BioMed Central Ltd. doi:10.1186/1471-2105-9-11\n"
+                         "\n\n\nDatabase: %s\n           %llu sequences; %llu total letters\n\n",
+                     versionLine.c_str(), o.index.c_str(), static_cast<unsigned long long>(dbSeqs),
+                     static_cast<unsigned long long>(dbLetters));
+    }
+    auto untranslatePos = [](uint64_t & b, uint64_t & e, int frame, uint64_t len, bool hasFrames, bool hasRevComp) {
+        // _untranslateQPositions / _untranslateSPositions (SQ/blast/blast_base.h:337-420), as in the m8 writer
+        if (!hasRevComp && !hasFrames)
+        {
+            ++b;
+            return;
+        }
+        if (hasFrames)
+        {
+            uint64_t const shift = static_cast<uint64_t>(frame < 0 ? -frame : frame) - 1;
+            b = b * 3 + shift;
+            e = e * 3 + shift;
+        }
+        if (frame > 0)
+            ++b;
+        else
+        {
+            b = len - b;
+            e = len - e + 1;
+        }
+    };
+    std::string row0, row1;
+    auto        reportRecord = [&](uint64_t q, std::vector<lgpu_hit const *> const & ms) {
+        uint64_t const  qLen = f.offsets[q + 1] - f.offsets[q];
+        uint8_t const * qSeq = f.residues.data() + f.offsets[q];
+        std::fprintf(fo, "\nQuery= %s\n\nLength=%llu\n", f.ids[q].c_str(), static_cast<unsigned long long>(qLen));
+        std::fputs("                                                                   Score     E\n"
+                   "Sequences producing significant alignments:                       (Bits)  Value\n\n", fo);
+        for (lgpu_hit const * h : ms)
+        {
+            std::string const sId = subjectId(h->s_id);
+            if (sId.size() <= 66)
+                std::fprintf(fo, "%s%*s", sId.c_str(), static_cast<int>(66 - sId.size()), "");
+            else
+                std::fprintf(fo, "%s...", sId.substr(0, 63).c_str());
+            std::fprintf(fo, " %4li  %.1g\n", static_cast<long>(h->bit_score), h->evalue);
+        }
+        std::fputs("\nALIGNMENTS\n", fo);
+        for (lgpu_hit const * h : ms)
+        {
+            std::string const sId = subjectId(h->s_id);
+            std::fputs("> ", fo);
+            for (size_t beg = 0, end = 0; end < sId.size();)
+            {
+                end += beg == 0 ? 64 : 60;
+                end = std::min(end, sId.size());
+                std::fprintf(fo, "%s\n", sId.substr(beg, end - beg).c_str());
+                beg = end;
+            }
+            std::fprintf(fo, "Length=%u\n\n", h->s_len);
+            float const identity   = static_cast<float>(100.0 * static_cast<float>(h->n_match) / static_cast<float>(h->aln_len));
+            float const similarity = static_cast<float>(100.0 * static_cast<float>(h->n_positive) / static_cast<float>(h->aln_len));
+            unsigned const nGaps   = h->n_gap_open + h->n_gap_ext;
+            std::fprintf(fo, " Score =  %.1f bits (%u), Expect =  %.1g\n Identities = %u/%u (%d%%)", h->bit_score,
+                         static_cast<unsigned>(h->score), h->evalue, h->n_match, h->aln_len,
+                         static_cast<int>(std::lround(identity)));
+            if (!isBlastN)
+                std::fprintf(fo, ", Positives = %u/%u (%d%%)", h->n_positive, h->aln_len, static_cast<int>(std::lround(similarity)));
+            std::fprintf(fo, ", Gaps = %u/%u (%d%%)", nGaps, h->aln_len,
+                         static_cast<int>(std::lround(static_cast<double>(nGaps) * 100 / h->aln_len)));
+            if (isBlastN)
+                std::fprintf(fo, "\n Strand=%s/%s\n\n", h->q_frame == 1 ? "Plus" : "Minus", h->s_frame == 1 ? "Plus" : "Minus");
+            else
+            {
+                if (qTrans || sTrans)
+                    std::fputs("\n Frame = ", fo);
+                if (qTrans && sTrans)
+                    std::fprintf(fo, "%+d/%+d", h->q_frame, h->s_frame);
+                else if (qTrans)
+                    std::fprintf(fo, "%+d", h->q_frame);
+                else if (sTrans)
+                    std::fprintf(fo, "%+d", h->s_frame);
+                std::fputs("\n\n", fo);
+            }
+            // the gapped rows
+            uint64_t const  sOff = desc->seq_delims[h->s_id];
+            uint64_t const  sLen = desc->seq_delims[h->s_id + 1] - sOff;
+            uint8_t const * sSeq = desc->seqs + sOff;
+            row0.clear();
+            row1.clear();
+            uint64_t         qi = h->q_start, si = h->s_start;
+            uint32_t const * ops = cigarOf(h);
+            for (uint32_t k = h->cigar_len; k-- > 0;)
+            {
+                uint32_t const kind = ops[k] & 3u, run = ops[k] >> 2;
+                for (uint32_t r = 0; r < run; ++r)
+                {
+                    row0 += kind == LGPU_CIGAR_D ? '-' : frameChar(qSeq, qLen, qTrans, isBlastN, h->q_frame, qi++);
+                    row1 += kind == LGPU_CIGAR_I ? '-' : frameChar(sSeq, sLen, sTrans, isBlastN, sTrans ? h->s_frame : 1, si++);
+                }
+            }
+            uint64_t effQS = h->q_start, effQE = h->q_end, effSS = h->s_start, effSE = h->s_end;
+            untranslatePos(effQS, effQE, h->q_frame, qLen, qTrans, isBlastN || qTrans);
+            untranslatePos(effSS, effSE, h->s_frame, h->s_len, sTrans, sTrans);
+            int const qStepOne = h->q_frame < 0 ? -1 : 1, sStepOne = h->s_frame < 0 ? -1 : 1;
+            int const qStep = qTrans ? 3 * qStepOne : qStepOne, sStep = sTrans ? 3 * sStepOne : sStepOne;
+            uint64_t const maxPos = std::max(std::max(effQS, effQE), std::max(effSS, effSE));
+            int const      width  = maxPos == 0 ? 1 : static_cast<int>(std::floor(std::log10(static_cast<double>(maxPos))) + 1);
+            long long qPos = 0, sPos = 0;
+            for (uint32_t aPos = 0; aPos < h->aln_len;)
+            {
+                uint32_t const end = std::min<uint32_t>(aPos + 60, h->aln_len);
+                std::fprintf(fo, "Query  %-*d  ", width, static_cast<int>(qPos + static_cast<long long>(effQS)));
+                for (uint32_t i = aPos; i < end; ++i)
+                    if (row0[i] != '-')
+                        qPos += qStep;
+                std::fwrite(row0.data() + aPos, 1, end - aPos, fo);
+                std::fprintf(fo, "  %-*d", width, static_cast<int>(qPos + static_cast<long long>(effQS) - qStepOne));
+                std::fprintf(fo, "\n         %*s", width, "");
+                for (uint32_t i = aPos; i < end; ++i)
+                {
+                    char const a = row0[i], b = row1[i];
+                    char       c = ' ';
+                    if (isBlastN)
+                        c = a == b ? '|' : ' ';
+                    else if (a == b)
+                        c = a;
+                    else if (a != '-' && b != '-' && scoreMat[kAa27CharToRank[static_cast<uint8_t>(a)] * 32 +
+                                                              kAa27CharToRank[static_cast<uint8_t>(b)]] > 0)
+                        c = '+';
+                    std::fputc(c, fo);
+                }
+                std::fprintf(fo, "\nSbjct  %-*d  ", width, static_cast<int>(sPos + static_cast<long long>(effSS)));
+                for (uint32_t i = aPos; i < end; ++i)
+                    if (row1[i] != '-')
+                        sPos += sStep;
+                std::fwrite(row1.data() + aPos, 1, end - aPos, fo);
+                std::fprintf(fo, "  %-*d\n\n", width, static_cast<int>(sPos + static_cast<long long>(effSS) - sStepOne));
+                aPos = end;
+            }
+            std::fputc('\n', fo);
+        }
+        std::fprintf(fo, "\nLambda     K      H\n   %-4.3f   %-5.4f   %-5.4f\n\nGapped\nLambda     K      H\n   %-4.3f   %-5.4f   "
+                         "%-5.4f\n\nEffective search space used: %llu\n\n",
+                     kaLambda, kaK, kaH, kaLambda, kaK, kaH, static_cast<unsigned long long>(qLen * dbLetters));
+    };
     // the reference chunks the queries per thread first (src/search.cpp:384-385), then into batches
     for (int t = 0; t < o.threads; ++t)
     {
@@ -534,6 +729,16 @@ int main(int argc, char ** argv)
                         nHits += h->phase == phase;
                     if (nHits)
                         recordHeader(q, nHits);
+                    if (o.report)
+                    {
+                        std::vector<lgpu_hit const *> ms;
+                        for (lgpu_hit const * h : perQuery[q])
+                            if (h->phase == phase)
+                                ms.push_back(h);
+                        if (!ms.empty())
+                            reportRecord(q, ms);
+                        continue;
+                    }
                     if (o.sam)
                     {
                         lgpu_hit const * prev = nullptr;
@@ -558,6 +763,17 @@ int main(int argc, char ** argv)
     }
     if (o.comments)
         std::fprintf(fo, "# BLAST processed %llu queries\n", static_cast<unsigned long long>(nRecords));
+    if (o.report)
+    {
+        std::fprintf(fo, "\n  Database: %s\n  Number of letters in database: %llu\n  Number of sequences in database:  %llu\n\n\n\n"
+                         "Matrix: ",
+                     o.index.c_str(), static_cast<unsigned long long>(dbLetters), static_cast<unsigned long long>(dbSeqs));
+        if (isBlastN)
+            std::fprintf(fo, " blastn matrix:%d %d", o.params.match, o.params.mismatch);
+        else
+            std::fprintf(fo, "BLOSUM%d", o.params.scoring_method);
+        std::fprintf(fo, "\nGap Penalties: Existence: %d, Extension: %d\n\n", -o.params.gap_open, -o.params.gap_extend);
+    }
     std::fclose(fo);
     lgpu_lba_close(lba);
     double const t4 = now();

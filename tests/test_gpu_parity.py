@@ -313,6 +313,24 @@ def test_cli_sam_is_byte_identical_to_reference(golden_dir, case, domain):
         assert a == b
 
 
+@pytest.mark.skipif(not os.path.exists(CLI), reason="bin/lambda3_b200 not built")
+@pytest.mark.parametrize("case,domain", [("prot_flat", 0), ("prot_family", 0), ("prot_diverged", 0), ("nucl", 1),
+                                         ("bisulfite", 2), ("blastx", 0), ("tblastn", 0), ("tblastx", 0)])
+def test_cli_m0_is_byte_identical_to_reference(golden_dir, case, domain):
+    """.m0 = BLAST pairwise report: gapped rows from the device traceback, frame translation, statistics
+    block, position arithmetic of all six BLAST modes"""
+    cwd = os.path.join(golden_dir, case)
+    out = os.path.join(cwd, "cli_none.m0")
+    if os.path.exists(out):
+        os.remove(out)
+    subprocess.run([CLI, ("searchp", "searchn", "searchbs")[domain], "-q", "q.fasta", "-i", "db.lba", "-o",
+                    "cli_none.m0", "-t", "1", "-v", "0", "--version-to-outputfile", "0"], check=True, cwd=cwd)
+    ours, ref = open(out).read().splitlines(), open(os.path.join(cwd, "none.m0")).read().splitlines()
+    for i, (a, b) in enumerate(zip(ours, ref)):
+        assert a == b, (i, a, b)
+    assert len(ours) == len(ref)
+
+
 def test_cigar_runs_are_consistent(golden_dir):
     """want_cigar through the API: the runs of every hit add up to its coordinates and statistics"""
     for case, domain in (("prot_family", 0), ("nucl", 1)):
