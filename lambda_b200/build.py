@@ -36,7 +36,7 @@ def build(force=False, verbose=False):
     if force or not os.path.exists(CLI) or os.path.getmtime(CLI) < max(os.path.getmtime(main), os.path.getmtime(OUT)):
         os.makedirs(os.path.dirname(CLI), exist_ok=True)
         cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-Wextra", main, "-o", CLI, "-L" + HERE, "-llambda_b200",
-               "-Wl,-rpath,$ORIGIN/../lambda_b200", "-pthread"]
+               "-Wl,-rpath,$ORIGIN/../lambda_b200", "-pthread", "-lz"]
         if verbose:
             print(" ".join(cmd), file=sys.stderr)
         subprocess.check_call(cmd)

@@ -21,6 +21,7 @@
 #include <vector>
 
 #include <cmath>
+#include <zlib.h>
 
 #include "../../include/lambda_b200.h"
 #include "tables_generated.inc" // alphabets and the genetic code, for the report-style outputs
@@ -37,6 +38,7 @@ struct Options
     int         gpus      = 1;
     bool        comments  = false; // .m9: BLAST tabular with comment lines
     bool        report    = false; // .m0: BLAST pairwise report
+    bool        bam       = false; // .bam: the same records, binary + BGZF
     bool        sam       = false; // .sam (default tags AS NM ae ai qf, --sam-bam-seq uniq, --sam-bam-clip hard)
     std::string commandLine;
     bool        versionToOutput = true;
@@ -58,7 +60,7 @@ bool endsWith(std::string const & s, char const * suf)
 
 void usage()
 {
-    std::puts("lambda3_b200 searchp|searchn|searchbs -q QUERY.fasta -i INDEX.lba [-o output.m0|.m8|.m9|.sam] [OPTIONS]\n"
+    std::puts("lambda3_b200 searchp|searchn|searchbs -q QUERY.fasta -i INDEX.lba [-o output.m0|.m8|.m9|.sam|.bam] [OPTIONS]\n"
               "  -a, --input-alphabet   auto|dna5|aminoacid (searchp; dna queries are translated: BLASTX/TBLASTX)\n"
               "  -p, --profile          none|fast|sensitive|pairs-default|pairs-sensitive\n"
               "  -e, --e-value          maximum e-value (default 0.01; -1 = off)\n"
@@ -154,10 +156,11 @@ void parse(int argc, char ** argv, Options & o)
     if (o.domain != LGPU_DOMAIN_PROTEIN && o.inputAlphabet != "auto")
         die("--input-alphabet is a searchp option");
     o.comments = endsWith(o.output, ".m9");
-    o.sam      = endsWith(o.output, ".sam");
+    o.bam      = endsWith(o.output, ".bam");
+    o.sam      = endsWith(o.output, ".sam") || o.bam;
     o.report   = endsWith(o.output, ".m0");
     if (!endsWith(o.output, ".m8") && !o.comments && !o.sam && !o.report)
-        die("the GPU path writes .m0, .m8, .m9 and .sam; .bam stays with the reference");
+        die("supported output formats: .m0, .m8, .m9, .sam, .bam");
     o.params.want_cigar = (o.sam || o.report) ? 1u : 0u;
     for (int i = 0; i < argc; ++i)
         o.commandLine += (i ? " " : "") + std::string(argv[i]);
@@ -340,6 +343,38 @@ void runShard(Options const & o, lgpu_index_desc const * desc, int device, Fasta
 
 } // namespace
 
+// BGZF (SAM/BAM specification 4.1): independent gzip members of <= 64 KiB with the block size in an extra field
+void bgzfWrite(FILE * fo, std::string const & raw)
+{
+    auto block = [&](unsigned char const * p, size_t n) {
+        unsigned char out[65536 + 64];
+        z_stream      zs{};
+        if (deflateInit2(&zs, Z_DEFAULT_COMPRESSION, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK)
+            die("zlib: deflateInit2 failed");
+        zs.next_in   = const_cast<unsigned char *>(p);
+        zs.avail_in  = static_cast<uInt>(n);
+        zs.next_out  = out + 18;
+        zs.avail_out = sizeof(out) - 18 - 8;
+        if (deflate(&zs, Z_FINISH) != Z_STREAM_END)
+            die("zlib: deflate failed");
+        size_t const clen = zs.total_out;
+        deflateEnd(&zs);
+        unsigned char const hdr[18] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0, 0};
+        std::memcpy(out, hdr, 18);
+        size_t const total = 18 + clen + 8;
+        out[16] = static_cast<unsigned char>((total - 1) & 0xff);
+        out[17] = static_cast<unsigned char>((total - 1) >> 8);
+        uint32_t const crc = static_cast<uint32_t>(crc32(crc32(0L, Z_NULL, 0), p, static_cast<uInt>(n)));
+        uint32_t const isz = static_cast<uint32_t>(n);
+        std::memcpy(out + 18 + clen, &crc, 4);
+        std::memcpy(out + 18 + clen + 4, &isz, 4);
+        std::fwrite(out, 1, total, fo);
+    };
+    for (size_t off = 0; off < raw.size(); off += 0xff00)
+        block(reinterpret_cast<unsigned char const *>(raw.data()) + off, std::min<size_t>(0xff00, raw.size() - off));
+    block(nullptr, 0); // end-of-file marker block
+}
+
 int main(int argc, char ** argv)
 {
     Options o;
@@ -432,7 +467,34 @@ int main(int argc, char ** argv)
     };
     // ---- SAM (src/search_output.hpp:346-458 header, :482-716 records; defaults of src/search_options.hpp:339-370) ----
     bool const isBlastN = desc->trans_alph != LGPU_ALPH_AMINO_ACID;
-    if (o.sam)
+    std::string bamRaw; // uncompressed BAM stream
+    auto        put32 = [&](uint32_t v) { bamRaw.append(reinterpret_cast<char const *>(&v), 4); };
+    if (o.bam)
+    {
+        std::string text = "@HD\tVN:1.4\tGO:query\n";
+        if (o.versionToOutput)
+            text += "@PG\tID:lambda\tPN:lambda\tVN:3.0.0\tCL:" + o.commandLine + "\n";
+        text += "@CO\tLambda is a high performance BLAST compatible local aligner, please see http://seqan.de/lambda for "
+                "more information.\n"
+                "@CO\tSAM/BAM dialect documentation is available here: https://github.com/seqan/lambda/wiki/Output-Formats\n"
+                "@CO\tIf you use any results found by Lambda, please cite Hauswedell et al. (2014) doi: "
+                "10.1093/bioinformatics/btu439\n"
+                "@CO\tOptional tags as follow\tAS:bit score\tNM:edit distance (in protein space unless BLASTN)\tae:expect "
+                "value\tai:% identity (in protein space unless BLASTN) \tqf:query frame\n";
+        bamRaw = "BAM\1";
+        put32(static_cast<uint32_t>(text.size()));
+        bamRaw += text;
+        put32(static_cast<uint32_t>(desc->n_seqs));
+        for (uint64_t sq = 0; sq < desc->n_seqs; ++sq)
+        {
+            std::string name = subjectId(static_cast<uint32_t>(sq));
+            name             = name.substr(0, name.find(' '));
+            put32(static_cast<uint32_t>(name.size() + 1));
+            bamRaw.append(name.c_str(), name.size() + 1);
+            put32(static_cast<uint32_t>(desc->seq_delims[sq + 1] - desc->seq_delims[sq]));
+        }
+    }
+    else if (o.sam)
     {
         std::fputs("@HD\tVN:1.4\tGO:query\n", fo);
         if (o.versionToOutput)
@@ -462,6 +524,7 @@ int main(int argc, char ** argv)
             flag |= 16u;
         // CIGAR (blastMatchOneCigar, :116-196): only for nucleotide queries; hard clips
         cigarStr.clear();
+        std::vector<std::pair<char, unsigned>> cigarEl;
         if (isBlastN || qTrans)
         {
             unsigned const transFac       = qTrans ? 3 : 1;
@@ -485,6 +548,7 @@ int main(int argc, char ** argv)
                 std::reverse(el.begin(), el.end());
             for (auto const & e : el)
                 cigarStr += std::to_string(e.second) + e.first;
+            cigarEl = el;
         }
         else
             cigarStr = "*";
@@ -518,6 +582,56 @@ int main(int argc, char ** argv)
         char ev[64];
         std::snprintf(ev, sizeof(ev), "%g", static_cast<double>(static_cast<float>(h->evalue)));
         float const identity = static_cast<float>(100.0 * static_cast<float>(h->n_match) / static_cast<float>(h->aln_len));
+        if (o.bam)
+        {
+            // SAM/BAM specification 4.2; bin from the reference span of the CIGAR (one base without CIGAR)
+            bool const     haveSeq = seqStr != "*";
+            uint32_t const lSeq    = haveSeq ? static_cast<uint32_t>(seqStr.size()) : 0u;
+            int64_t        refLen  = 0;
+            for (auto const & e : cigarEl)
+                if (e.first == 'M' || e.first == 'D')
+                    refLen += e.second;
+            int64_t const beg = beginPos, end = beginPos + std::max<int64_t>(refLen, 1) - 1;
+            uint32_t      bin = 0;
+            if (beg >> 14 == end >> 14) bin = static_cast<uint32_t>(((1 << 15) - 1) / 7 + (beg >> 14));
+            else if (beg >> 17 == end >> 17) bin = static_cast<uint32_t>(((1 << 12) - 1) / 7 + (beg >> 17));
+            else if (beg >> 20 == end >> 20) bin = static_cast<uint32_t>(((1 << 9) - 1) / 7 + (beg >> 20));
+            else if (beg >> 23 == end >> 23) bin = static_cast<uint32_t>(((1 << 6) - 1) / 7 + (beg >> 23));
+            else if (beg >> 26 == end >> 26) bin = static_cast<uint32_t>(((1 << 3) - 1) / 7 + (beg >> 26));
+            std::string rec;
+            auto        r32 = [&](uint32_t v) { rec.append(reinterpret_cast<char const *>(&v), 4); };
+            r32(h->s_id);
+            r32(static_cast<uint32_t>(beginPos));
+            r32((bin << 16) | (255u << 8) | static_cast<uint32_t>(qName.size() + 1));
+            r32((flag << 16) | static_cast<uint32_t>(cigarEl.size()));
+            r32(lSeq);
+            r32(0xffffffffu);
+            r32(0xffffffffu);
+            r32(0);
+            rec.append(qName.c_str(), qName.size() + 1);
+            for (auto const & e : cigarEl)
+                r32((e.second << 4) | (e.first == 'M' ? 0u : e.first == 'I' ? 1u : e.first == 'D' ? 2u : e.first == 'S' ? 4u : 5u));
+            auto code = [](char c) -> unsigned { return c == 'A' ? 1u : c == 'C' ? 2u : c == 'G' ? 4u : c == 'T' ? 8u : 15u; };
+            for (uint32_t i = 0; i < lSeq; i += 2)
+                rec += static_cast<char>((code(seqStr[i]) << 4) | (i + 1 < lSeq ? code(seqStr[i + 1]) : 0u));
+            rec.append(lSeq, static_cast<char>(0xff));
+            float const    evF = static_cast<float>(h->evalue);
+            uint16_t const as  = static_cast<uint16_t>(h->bit_score);
+            uint32_t const nm  = h->aln_len - h->n_match;
+            rec += "aef";
+            rec.append(reinterpret_cast<char const *>(&evF), 4);
+            rec += "ASS";
+            rec.append(reinterpret_cast<char const *>(&as), 2);
+            rec += "aiC";
+            rec += static_cast<char>(static_cast<uint8_t>(identity));
+            rec += "qfc";
+            rec += static_cast<char>(h->q_frame);
+            rec += "NMI";
+            rec.append(reinterpret_cast<char const *>(&nm), 4);
+            put32(static_cast<uint32_t>(rec.size()));
+            bamRaw += rec;
+            return;
+        }
         std::fprintf(fo, "%s\t%u\t%s\t%d\t255\t%s\t*\t0\t0\t%s\t*\tae:f:%s\tAS:i:%u\tai:i:%u\tqf:i:%d\tNM:i:%u\n", qName.c_str(),
                      flag, sName.c_str(), beginPos + 1, cigarStr.c_str(), seqStr.c_str(), ev,
                      static_cast<unsigned>(static_cast<uint16_t>(h->bit_score)),
@@ -763,6 +877,8 @@ int main(int argc, char ** argv)
     }
     if (o.comments)
         std::fprintf(fo, "# BLAST processed %llu queries\n", static_cast<unsigned long long>(nRecords));
+    if (o.bam)
+        bgzfWrite(fo, bamRaw);
     if (o.report)
     {
         std::fprintf(fo, "\n  Database: %s\n  Number of letters in database: %llu\n  Number of sequences in database:  %llu\n\n\n\n"

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Golden `.m9` (BLAST tabular with comment lines) and `.sam` / `.m0` files from the unmodified reference binary, for
+"""Golden `.m9` (BLAST tabular with comment lines) and `.sam` / `.bam` / `.m0` files from the unmodified reference binary, for
 the committed index / query fixtures:  <case>/none.m9, <case>/none.sam (--version-to-outputfile 0) and
 <case>/none.v1.m9 (default version string; the SAM @PG line echoes the command line, so only v0 is kept).  The reference is run inside the case directory with
 `-i db.lba`, because the index path is echoed in the `# Database:` line."""
@@ -21,11 +21,12 @@ for case, cmd in CASES:
             shutil.copyfileobj(fi, fo)
         shutil.copy(os.path.join(src, "q.fasta"), tmp)
         for name, extra in (("none.m9", ["--version-to-outputfile", "0"]), ("none.v1.m9", []),
-                            ("none.sam", ["--version-to-outputfile", "0"]), ("none.m0", ["--version-to-outputfile", "0"])):
+                            ("none.sam", ["--version-to-outputfile", "0"]), ("none.m0", ["--version-to-outputfile", "0"]),
+                            ("none.bam", ["--version-to-outputfile", "0"])):
             subprocess.check_call([REF, cmd, "-q", "q.fasta", "-i", "db.lba", "-o", name, "-t", "1", "-v", "0", *extra], cwd=tmp)
             if name.endswith(".m0"):  # pairwise reports are long: stored gzipped (the test fixture unpacks *.gz)
                 with open(os.path.join(tmp, name), "rb") as fi, gzip.GzipFile(os.path.join(src, name + ".gz"), "wb", 9, mtime=0) as fo:
                     shutil.copyfileobj(fi, fo)
             else:
                 shutil.copy(os.path.join(tmp, name), os.path.join(src, name))
-            print(case, name, sum(1 for _ in open(os.path.join(tmp, name))), "lines")
+            print(case, name, os.path.getsize(os.path.join(tmp, name)), "bytes")

@@ -331,6 +331,28 @@ def test_cli_m0_is_byte_identical_to_reference(golden_dir, case, domain):
     assert len(ours) == len(ref)
 
 
+@pytest.mark.skipif(not os.path.exists(CLI), reason="bin/lambda3_b200 not built")
+@pytest.mark.parametrize("case,domain", [("prot_flat", 0), ("prot_family", 0), ("nucl", 1), ("bisulfite", 2),
+                                         ("blastx", 0), ("tblastn", 0), ("tblastx", 0)])
+def test_cli_bam_content_is_identical_to_reference(golden_dir, case, domain):
+    """.bam: the BGZF blocks may be cut and compressed differently, the uncompressed BAM stream (header,
+    reference dictionary, binary records with CIGAR / 4-bit sequence / typed tags) must be the same bytes"""
+    import gzip
+    cwd = os.path.join(golden_dir, case)
+    out = os.path.join(cwd, "cli_none.bam")
+    if os.path.exists(out):
+        os.remove(out)
+    subprocess.run([CLI, ("searchp", "searchn", "searchbs")[domain], "-q", "q.fasta", "-i", "db.lba", "-o",
+                    "cli_none.bam", "-t", "1", "-v", "0", "--version-to-outputfile", "0"], check=True, cwd=cwd)
+    ours = gzip.open(out, "rb").read()
+    ref = gzip.open(os.path.join(cwd, "none.bam"), "rb").read()
+    assert ours[:4] == b"BAM\x01"
+    if ours != ref:
+        i = next(k for k in range(min(len(ours), len(ref))) if ours[k] != ref[k])
+        raise AssertionError((len(ours), len(ref), i, ours[max(0, i - 40):i + 40], ref[max(0, i - 40):i + 40]))
+    assert open(out, "rb").read()[-28:] == bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+
+
 def test_cigar_runs_are_consistent(golden_dir):
     """want_cigar through the API: the runs of every hit add up to its coordinates and statistics"""
     for case, domain in (("prot_family", 0), ("nucl", 1)):
