@@ -311,6 +311,7 @@ struct lgpu_ctx
     bool                       dpxOk = false; // scoring fits the int8 profile of the DPX kernels
     unsigned int               dpxBlocksPerSM = 32; // resident warps of the DP score kernel per SM (LAMBDA_B200_DPX_OCC)
     bool                       dpxScoreOk = false; // ... and every matrix entry >= gap open (score kernel: profile bytes >= 0)
+    uint64_t                   minSubBatch = 16384; // queries per sub-batch below which a call is not cut further
     unsigned int               streams = 1;  // sub-batches in flight per lgpu_search_batch call (LAMBDA_B200_STREAMS)
     std::vector<std::unique_ptr<lgpu_ctx>> workers;
     int                        seedMode = 0; // LAMBDA_B200_SEED=thread|warp|block|spec forces one seeding kernel (tests); 0 = auto
@@ -334,6 +335,7 @@ struct lgpu_ctx
     std::vector<lgpu_hit>   hits;
     std::vector<uint32_t>   cigar;       // run-length ops of the hits (lgpu_params.want_cigar), see lgpu_hit::cigar_off
     DevBuf<unsigned int>    dCigarCap, dCigarOff, dCigar;
+    DevBuf<unsigned char>   dTraceK;     // per task: K of the packed trace class it ran in
     PinnedBuf<unsigned int> hCigarStage;
     std::vector<lgpu_match> matchesHost;
     cudaEvent_t             ev[8]{};
@@ -1111,47 +1113,47 @@ static void runTracePass(lgpu_ctx & c, lgpu_match const * tasks, size_t n, lgpu_
     }
 
     // ---- packed classes ----
+    // The fill kernels run class by class (K is a template parameter), but ONE traceback launch walks the
+    // alignments of all classes of a group: the traceback of a long alignment is a chain of dependent
+    // loads, and with one launch per class the step would pay the longest chain of every class in turn.
+    // A group = as many (class, alignment) pieces as fit the plane budget of one launch.
     constexpr uint64_t kMaxPlaneWords = (16ull << 30) / 4;
     std::vector<unsigned long long> planeOff(n, 0);
+    std::vector<unsigned char>      kOf(n, 0);
     bool                            anyDpx = false;
-    for (int cls = 0; cls < kNumTraceClasses && !useCk; ++cls)
+    struct Piece
     {
-        std::vector<unsigned int> const & L = lists[cls];
-        if (L.empty())
-            continue;
-        anyDpx      = true;
-        int const K = dpxTraceK(cls);
+        int          cls;
+        size_t       begin, end; // range inside lists[cls]
+        unsigned int maxNt;
+    };
+    std::vector<Piece>        group;
+    std::vector<unsigned int> groupOrder;
+    uint64_t                  groupWords = 0;
+    auto flushGroup = [&]() {
+        if (group.empty())
+            return;
+        unsigned int const total = static_cast<unsigned int>(groupOrder.size());
         c.dOrder.reserve(n);
         c.dTraceOff.reserve(n);
         c.dScores2.reserve(n);
         c.dBestPos.reserve(n);
-        size_t begin = 0;
-        while (begin < L.size())
+        c.dTraceK.reserve(n);
+        c.dPlanes.reserve(groupWords);
+        LGPU_CUDA(cudaMemcpyAsync(c.dOrder.p, groupOrder.data(), total * 4ull, cudaMemcpyHostToDevice, c.stream));
+        LGPU_CUDA(cudaMemcpyAsync(c.dTraceOff.p, planeOff.data(), n * 8ull, cudaMemcpyHostToDevice, c.stream));
+        LGPU_CUDA(cudaMemcpyAsync(c.dTraceK.p, kOf.data(), n, cudaMemcpyHostToDevice, c.stream));
+        unsigned int off = 0;
+        for (Piece const & pc : group)
         {
-            uint64_t     words = 0;
-            unsigned int maxNt = 0;
-            size_t       end   = begin;
-            while (end < L.size())
-            {
-                unsigned int const nt = tasks[L[end]].subj_end - tasks[L[end]].subj_start;
-                uint64_t const     w  = dpxTracePlaneWords(K, nt);
-                if (end > begin && words + w > kMaxPlaneWords)
-                    break;
-                planeOff[L[end]] = words;
-                words += w;
-                maxNt = std::max(maxNt, nt);
-                ++end;
-            }
-            unsigned int const cnt = static_cast<unsigned int>(end - begin);
-            c.dPlanes.reserve(words);
-            LGPU_CUDA(cudaMemcpyAsync(c.dOrder.p, L.data() + begin, cnt * 4ull, cudaMemcpyHostToDevice, c.stream));
-            LGPU_CUDA(cudaMemcpyAsync(c.dTraceOff.p, planeOff.data(), n * 8ull, cudaMemcpyHostToDevice, c.stream));
+            unsigned int const cnt = static_cast<unsigned int>(pc.end - pc.begin);
+            int const          K   = dpxTraceK(pc.cls);
             LGPU_CUDA(cudaMemsetAsync(c.dWork.p, 0, 4, c.stream));
             DpxTraceParams P{};
             P.ix          = c.index->dev;
             P.Q           = c.Q;
             P.tasks       = dTasks;
-            P.order       = c.dOrder.p;
+            P.order       = c.dOrder.p + off;
             P.nTasks      = cnt;
             P.matrix      = c.dMatrix.p;
             P.go          = c.scoring.gapOpenSeqan;
@@ -1164,50 +1166,88 @@ static void runTracePass(lgpu_ctx & c, lgpu_match const * tasks, size_t n, lgpu_
             P.bestCol     = c.dBestPos.p;
             switch (K)
             {
-                case 1: launchDpxTrace<1>(c, P, maxNt); break;
-                case 2: launchDpxTrace<2>(c, P, maxNt); break;
-                case 3: launchDpxTrace<3>(c, P, maxNt); break;
-                case 4: launchDpxTrace<4>(c, P, maxNt); break;
-                case 5: launchDpxTrace<5>(c, P, maxNt); break;
-                case 6: launchDpxTrace<6>(c, P, maxNt); break;
-                case 8: launchDpxTrace<8>(c, P, maxNt); break;
-                case 10: launchDpxTrace<10>(c, P, maxNt); break;
-                case 12: launchDpxTrace<12>(c, P, maxNt); break;
-                case 16: launchDpxTrace<16>(c, P, maxNt); break;
-                case 24: launchDpxTrace<24>(c, P, maxNt); break;
-                default: launchDpxTrace<32>(c, P, maxNt); break;
+                case 1: launchDpxTrace<1>(c, P, pc.maxNt); break;
+                case 2: launchDpxTrace<2>(c, P, pc.maxNt); break;
+                case 3: launchDpxTrace<3>(c, P, pc.maxNt); break;
+                case 4: launchDpxTrace<4>(c, P, pc.maxNt); break;
+                case 5: launchDpxTrace<5>(c, P, pc.maxNt); break;
+                case 6: launchDpxTrace<6>(c, P, pc.maxNt); break;
+                case 8: launchDpxTrace<8>(c, P, pc.maxNt); break;
+                case 10: launchDpxTrace<10>(c, P, pc.maxNt); break;
+                case 12: launchDpxTrace<12>(c, P, pc.maxNt); break;
+                case 16: launchDpxTrace<16>(c, P, pc.maxNt); break;
+                case 24: launchDpxTrace<24>(c, P, pc.maxNt); break;
+                default: launchDpxTrace<32>(c, P, pc.maxNt); break;
             }
-            TracebackDpxParams TP{};
-            TP.ix        = c.index->dev;
-            TP.Q         = c.Q;
-            TP.tasks     = dTasks;
-            TP.order     = c.dOrder.p;
-            TP.nTasks    = cnt;
-            TP.matrix    = c.dMatrix.p;
-            TP.go        = c.scoring.gapOpenSeqan;
-            TP.ge        = c.scoring.gapExtend;
-            TP.K         = static_cast<unsigned int>(K);
-            TP.scores    = c.dScores2.p;
-            TP.bestCol   = c.dBestPos.p;
-            TP.planes    = c.dPlanes.p;
-            TP.planeOff  = c.dTraceOff.p;
-            TP.out       = c.dHits.p;
-            tracebackDpxKernel<<<gridFor(cnt, 128), 128, 0, c.stream>>>(TP);
-            LGPU_CUDA(cudaGetLastError());
-            if (c.params.want_cigar)
-                emitCigars(c, c.dOrder.p, cnt, [&](unsigned int * ops, unsigned int const * off, unsigned int base) {
-                    TP.emit      = 1;
-                    TP.cigarOps  = ops;
-                    TP.cigarOff  = off;
-                    TP.cigarBase = base;
-                    tracebackDpxKernel<<<gridFor(cnt, 128), 128, 0, c.stream>>>(TP);
-                }, st);
-            LGPU_CUDA(cudaStreamSynchronize(c.stream)); // the order / offset staging arrays are reused by the next chunk
+            off += cnt;
             if (st)
-                st->kernel_launches += 2;
+                st->kernel_launches += 1;
+        }
+        TracebackDpxParams TP{};
+        TP.ix        = c.index->dev;
+        TP.Q         = c.Q;
+        TP.tasks     = dTasks;
+        TP.order     = c.dOrder.p;
+        TP.nTasks    = total;
+        TP.matrix    = c.dMatrix.p;
+        TP.go        = c.scoring.gapOpenSeqan;
+        TP.ge        = c.scoring.gapExtend;
+        TP.kOf       = c.dTraceK.p;
+        TP.scores    = c.dScores2.p;
+        TP.bestCol   = c.dBestPos.p;
+        TP.planes    = c.dPlanes.p;
+        TP.planeOff  = c.dTraceOff.p;
+        TP.out       = c.dHits.p;
+        tracebackDpxKernel<<<gridFor(total, 128), 128, 0, c.stream>>>(TP);
+        LGPU_CUDA(cudaGetLastError());
+        if (c.params.want_cigar)
+            emitCigars(c, c.dOrder.p, total, [&](unsigned int * ops, unsigned int const * offs, unsigned int base) {
+                TP.emit      = 1;
+                TP.cigarOps  = ops;
+                TP.cigarOff  = offs;
+                TP.cigarBase = base;
+                tracebackDpxKernel<<<gridFor(total, 128), 128, 0, c.stream>>>(TP);
+            }, st);
+        LGPU_CUDA(cudaStreamSynchronize(c.stream)); // the staging arrays are reused by the next group
+        if (st)
+            st->kernel_launches += 1;
+        group.clear();
+        groupOrder.clear();
+        groupWords = 0;
+    };
+    for (int cls = 0; cls < kNumTraceClasses && !useCk; ++cls)
+    {
+        std::vector<unsigned int> const & L = lists[cls];
+        if (L.empty())
+            continue;
+        anyDpx      = true;
+        int const K = dpxTraceK(cls);
+        size_t    begin = 0;
+        while (begin < L.size())
+        {
+            unsigned int maxNt = 0;
+            size_t       end   = begin;
+            while (end < L.size())
+            {
+                unsigned int const nt = tasks[L[end]].subj_end - tasks[L[end]].subj_start;
+                uint64_t const     w  = dpxTracePlaneWords(K, nt);
+                if (groupWords + w > kMaxPlaneWords && (end > begin || !group.empty()))
+                    break;
+                planeOff[L[end]] = groupWords;
+                kOf[L[end]]      = static_cast<unsigned char>(K);
+                groupWords += w;
+                maxNt = std::max(maxNt, nt);
+                groupOrder.push_back(L[end]);
+                ++end;
+            }
+            if (end > begin)
+                group.push_back({cls, begin, end, maxNt});
+            if (end < L.size()) // budget reached: run what we have, continue with the rest
+                flushGroup();
             begin = end;
         }
     }
+    flushGroup();
     if (anyDpx || anyCk)
     {
         LGPU_CUDA(cudaMemcpyAsync(c.hHits.p, c.dHits.p, n * sizeof(lgpu_hit), cudaMemcpyDeviceToHost, c.stream));
@@ -1438,7 +1478,12 @@ static void searchBatch(lgpu_ctx & c, lgpu_query_batch const & qb, lgpu_hits * o
     std::vector<uint64_t> offs;
     BatchView const       all = viewOf(c, qb, offs);
     LGPU_CUDA(cudaEventRecord(c.ev[2], c.stream));
-    unsigned int const nW = (c.streams > 1 && all.n >= 4096) ? c.streams : 1;
+    // sub-batches below ~16k queries do not fill the GPU any more (measured: 10k real-length queries run
+    // 24.5 ms on one stream, 29.9 ms cut in three); tests force the split with LAMBDA_B200_MIN_SUBBATCH
+    uint64_t const     minSub = c.minSubBatch;
+    unsigned int const nW = (c.streams > 1 && all.n >= 2 * minSub)
+                              ? static_cast<unsigned int>(std::min<uint64_t>(c.streams, all.n / minSub))
+                              : 1;
     if (nW == 1)
     {
         searchOne(c, all, st);
@@ -1766,6 +1811,8 @@ int lgpu_ctx_create(lgpu_ctx ** out, lgpu_index const * ix, lgpu_params const * 
         c->streams = 3;
         if (char const * e = std::getenv("LAMBDA_B200_STREAMS"))
             c->streams = static_cast<unsigned int>(std::max(1, std::min(8, std::atoi(e))));
+        if (char const * e = std::getenv("LAMBDA_B200_MIN_SUBBATCH"))
+            c->minSubBatch = static_cast<uint64_t>(std::max(1, std::atoi(e)));
         *out = c.release();
     });
 }

@@ -271,7 +271,7 @@ struct TracebackDpxParams
     unsigned int               nTasks;
     signed char const *        matrix; // 2 x (32 x 32)
     int                        go, ge;
-    unsigned int               K;
+    unsigned char const *      kOf; // per task: columns per strip of the fill kernel that wrote its planes
     int const *                scores;
     unsigned int const *       bestCol;
     unsigned int const *       planes;
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(128) tracebackDpxKernel(TracebackDpxParams P)
     unsigned char const *    ts   = P.ix.seqs + sbjBase(P.ix, m.subj_id) + m.subj_start;
     signed char const *      M    = P.matrix + matrixOffset(P.ix, m.subj_id);
     unsigned int const       nt   = m.subj_end - m.subj_start;
-    unsigned int const       K    = P.K, KN = (K + 1) / 2;
+    unsigned int const       K    = P.kOf[task], KN = (K + 1) / 2;
     unsigned int const       nSteps = nt + 63;
     unsigned int const *     planeH = P.planes + P.planeOff[task];
     unsigned int const *     planeN = planeH + static_cast<unsigned long long>(nSteps) * 32ull * K;

@@ -377,9 +377,10 @@ def test_cigar_runs_are_consistent(golden_dir):
         s.close(); s2.close(); ix.close()
 
 
-def test_multi_stream_split_is_invisible(golden_dir):
+def test_multi_stream_split_is_invisible(golden_dir, monkeypatch):
     """large batches are cut into sub-batches running concurrently on several streams / host threads:
     hits, their order and every counter must equal the strictly serial run"""
+    monkeypatch.setenv("LAMBDA_B200_MIN_SUBBATCH", "1024")
     path, ids, res, offs = _load(golden_dir, "prot_flat", 0)
     reps = 90  # 57 queries x 90 = 5130 > the 4096-query split threshold
     lens = np.diff(offs.astype(np.int64))
