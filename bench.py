@@ -331,6 +331,7 @@ def main():
     h_offs = torch.from_numpy(qoffs.view(np.int64)).pin_memory()
     d_res = h_res.cuda()
     d_offs = h_offs.cuda()
+    pin_res, pin_offs = h_res.numpy(), h_offs.numpy().view(np.uint64)  # numpy views of the pinned buffers
 
     from lambda_b200.dist import all_gather_hits
 
@@ -343,7 +344,9 @@ def main():
         if resident:
             hits, st = searcher.search(d_res, d_offs)
         else:
-            hits, st = searcher.search(res, qoffs)  # host buffers: H2D of queries + D2H of hits inside
+            # host buffers (pinned): H2D of the queries + D2H of the hit records happen inside the call;
+            # copy=False returns a view of the library's result buffer (valid until the next call)
+            hits, st = searcher.search(pin_res, pin_offs, copy=False)
         g_ms = 0.0
         if world > 1:
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
