@@ -1948,6 +1948,7 @@ int lgpu_extend_trace(lgpu_ctx * c, lgpu_query_batch const * q, lgpu_match const
         checkWindows(*c, win, n);
         c->dUserMatches.reserve(n);
         LGPU_CUDA(cudaMemcpyAsync(c->dUserMatches.p, win, n * sizeof(lgpu_match), cudaMemcpyHostToDevice, c->stream));
+        c->cigar.clear(); // with want_cigar the records index into the context's run buffer of THIS call
         runTracePass(*c, win, n, c->dUserMatches.p, out, stats);
     });
 }
