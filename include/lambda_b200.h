@@ -168,8 +168,8 @@ int          lgpu_ctx_create(lgpu_ctx ** out, lgpu_index const *, lgpu_params co
 void         lgpu_ctx_destroy(lgpu_ctx *);
 /* Number of sub-batches a large lgpu_search_batch() call is cut into; each runs the whole pipeline on
  * its own CUDA stream + host thread so that host-only and latency-bound stretches overlap with the DP
- * kernels of the others (default 2, env LAMBDA_B200_STREAMS; 1 = strictly serial, used for per-kernel
- * timing).  Results do not depend on it. */
+ * kernels of the others (default 3, env LAMBDA_B200_STREAMS; 1 = strictly serial, used for per-kernel
+ * timing; calls with fewer than ~32k queries are not cut).  Results do not depend on it. */
 int          lgpu_ctx_set_streams(lgpu_ctx *, uint32_t n);
 char const * lgpu_last_error(lgpu_ctx const *); /* ctx may be NULL: error of the last failed
                                                    create/open call on this thread */

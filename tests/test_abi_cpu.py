@@ -82,6 +82,24 @@ def test_statistics_known_answers():
     assert e_lo.value > p.max_evalue >= e_hi.value
 
 
+def test_report_helpers_known_answers():
+    """Karlin-Altschul block and substitution matrix used by the .m0 writer (SQ/blast/blast_statistics.h tables)"""
+    lib = lambda_b200.load_library()
+    p = api.default_params("protein")
+    lam, k, h = C.c_double(), C.c_double(), C.c_double()
+    assert lib.lgpu_ka_params(C.byref(p), C.byref(lam), C.byref(k), C.byref(h)) == 0
+    assert (lam.value, k.value, h.value) == (0.267, 0.041, 0.14)
+    m = np.zeros(32 * 32, np.int8)
+    assert lib.lgpu_score_matrix(C.byref(p), C.c_void_p(m.ctypes.data)) == 0
+    aa = "ABCDEFGHIJKLMNOPQRSTUVWXYZ*"
+    sc = lambda a, b: int(m[aa.index(a) * 32 + aa.index(b)])
+    assert (sc("W", "W"), sc("A", "A"), sc("A", "R"), sc("L", "I"), sc("C", "C")) == (11, 4, -1, 2, 9)  # BLOSUM62
+    n = api.default_params("nucleotide")
+    assert lib.lgpu_ka_params(C.byref(n), C.byref(lam), C.byref(k), C.byref(h)) == 0
+    assert (lam.value, k.value, h.value) == (0.625, 0.41, 0.78)
+    assert lib.lgpu_ka_params(None, C.byref(lam), C.byref(k), C.byref(h)) != 0
+
+
 def test_m8_formatting_matches_golden_line():
     lib = lambda_b200.load_library()
     p = api.default_params("protein")
