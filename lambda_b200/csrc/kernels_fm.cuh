@@ -341,6 +341,7 @@ struct SeedParams
     unsigned int const * active; // list of query ids to seed
     unsigned int         nActive;
     unsigned int         seedLength, seedOffset, maxSeedDist, halfExact, adaptive;
+    unsigned int         fullHamming; // max_seed_dist = 1 over the WHOLE seed (seed_half_exact off)
     unsigned int         maxMatches;
     int                  preScoring;
     double               preScoringThresh;
@@ -379,8 +380,8 @@ __global__ void __launch_bounds__(128) seedKernel(SeedParams P)
         for (unsigned int f = 0; f < F; ++f)
             needlesSum += qryFrameLen(P.Q, origLen, f);
         unsigned long long needlesPos = 0;
-        bool const         half       = P.halfExact && P.maxSeedDist != 0;
-        unsigned int const h1         = half ? L / 2 : L;
+        bool const         half       = (P.halfExact && P.maxSeedDist != 0) || P.fullHamming;
+        unsigned int const h1         = P.fullHamming ? 0u : (half ? L / 2 : L);
         unsigned int const n2         = L - h1;
 
         for (unsigned int f = 0; f < F; ++f)
@@ -644,9 +645,12 @@ __device__ __forceinline__ int seedExactChain(DevIndex const & ix, unsigned char
 
 // Leaf `idx` of the half-exact search tree in the reference's (BFS = leaf) order: mismatches below the
 // seed symbol per level going down, the exact cursor, mismatches above the seed symbol going back up.
+// levelOrder (max_seed_dist = 1 without seed_half_exact, FMC search/BacktrackingWithBuffers.h:40-83): the
+// mismatches of level 0, 1, ... in symbol order are delegated as soon as their error budget is used up, the
+// exact cursor is what remains in the buffer at the end.
 __device__ __forceinline__ Cursor seedLeaf(DevIndex const & ix, Cursor const * E, unsigned char const * red,
                                            unsigned int seedBegin, unsigned int h1, unsigned int n2, int kMax, bool hasExact,
-                                           unsigned int redN, unsigned int idx)
+                                           unsigned int redN, unsigned int idx, bool levelOrder = false)
 {
     Cursor mine;
     mine.lb  = 0;
@@ -655,6 +659,20 @@ __device__ __forceinline__ Cursor seedLeaf(DevIndex const & ix, Cursor const * E
     int          lvl   = -1;
     unsigned int r     = 0;
     bool         exact = false;
+    if (levelOrder)
+    {
+        unsigned int const per = redN - 1;
+        if (i < static_cast<unsigned int>(kMax + 1) * per)
+        {
+            lvl                     = static_cast<int>(i / per);
+            unsigned int const k    = i % per;
+            unsigned int const want = red[seedBegin + h1 + lvl];
+            r                       = k < want ? k : k + 1;
+        }
+        else if (hasExact)
+            exact = true;
+    }
+    else
     for (int l = 0; l <= kMax; ++l)
     {
         unsigned int const want = red[seedBegin + h1 + l];
@@ -666,14 +684,14 @@ __device__ __forceinline__ Cursor seedLeaf(DevIndex const & ix, Cursor const * E
         }
         i -= want;
     }
-    if (lvl < 0 && hasExact)
+    if (!levelOrder && lvl < 0 && hasExact)
     {
         if (i == 0)
             exact = true;
         else
             --i;
     }
-    if (lvl < 0 && !exact)
+    if (!levelOrder && lvl < 0 && !exact)
         for (int l = kMax; l >= 0; --l)
         {
             unsigned int const want = red[seedBegin + h1 + l];
@@ -1133,8 +1151,8 @@ __global__ void __launch_bounds__(128) seedWarpKernel(SeedParams P)
         for (unsigned int f = 0; f < F; ++f)
             needlesSum += qryFrameLen(P.Q, origLen, f);
         unsigned long long needlesPos = 0;
-        bool const         half       = P.halfExact && P.maxSeedDist != 0;
-        unsigned int const h1         = half ? L / 2 : L;
+        bool const         half       = (P.halfExact && P.maxSeedDist != 0) || P.fullHamming;
+        unsigned int const h1         = P.fullHamming ? 0u : (half ? L / 2 : L);
         unsigned int const n2         = L - h1;
 
         for (unsigned int f = 0; f < F; ++f)
@@ -1164,7 +1182,7 @@ __global__ void __launch_bounds__(128) seedWarpKernel(SeedParams P)
                     mine.lb  = 0;
                     mine.len = 0;
                     if (base + lane < nLeaves)
-                        mine = seedLeaf(ix, E, red, seedBegin, h1, n2, kMax, hasExact, redN, base + lane);
+                        mine = seedLeaf(ix, E, red, seedBegin, h1, n2, kMax, hasExact, redN, base + lane, P.fullHamming != 0);
                     unsigned int live = __ballot_sync(0xffffffffu, mine.len != 0);
                     while (live)
                     {
@@ -1223,8 +1241,8 @@ __global__ void __launch_bounds__(32 * kSpecWarps) seedSpecKernel(SeedParams P)
         for (unsigned int f = 0; f < F; ++f)
             needlesSum += qryFrameLen(P.Q, origLen, f);
         unsigned long long needlesPos = 0;
-        bool const         half       = P.halfExact && P.maxSeedDist != 0;
-        unsigned int const h1         = half ? L / 2 : L;
+        bool const         half       = (P.halfExact && P.maxSeedDist != 0) || P.fullHamming;
+        unsigned int const h1         = P.fullHamming ? 0u : (half ? L / 2 : L);
         unsigned int const n2         = L - h1;
 
         for (unsigned int f = 0; f < F; ++f)
@@ -1288,7 +1306,7 @@ __global__ void __launch_bounds__(32 * kSpecWarps) seedSpecKernel(SeedParams P)
                         mine.lb  = 0;
                         mine.len = 0;
                         if (base + lane < nLeaves)
-                            mine = seedLeaf(ix, E, red, seedBegin, h1, n2, kMax, hasExact, redN, base + lane);
+                            mine = seedLeaf(ix, E, red, seedBegin, h1, n2, kMax, hasExact, redN, base + lane, P.fullHamming != 0);
                         __syncwarp();
                         seedConsumeChunkSpec(P, sM, S, lane, q, qb, origLen, needlesSum, mine, f, seedBegin, needlesPos,
                                              hitsThisSeq, nAfter, nFailed);
@@ -1340,8 +1358,8 @@ __global__ void __launch_bounds__(32 * kSeedBlockWarps) seedBlockKernel(SeedPara
     unsigned int const       origLen = static_cast<unsigned int>(P.Q.offs[q + 1] - qb);
     unsigned int const       L       = P.seedLength;
     unsigned int const       redN    = ix.sigma - 1;
-    bool const               half    = P.halfExact && P.maxSeedDist != 0;
-    unsigned int const       h1      = half ? L / 2 : L;
+    bool const               half    = (P.halfExact && P.maxSeedDist != 0) || P.fullHamming;
+    unsigned int const       h1      = P.fullHamming ? 0u : (half ? L / 2 : L);
     unsigned int const       n2      = L - h1;
 
     if (threadIdx.x == 0)
@@ -1396,7 +1414,7 @@ __global__ void __launch_bounds__(32 * kSeedBlockWarps) seedBlockKernel(SeedPara
                 mine.lb  = 0;
                 mine.len = 0;
                 if (base + lane < nLeaves)
-                    mine = seedLeaf(ix, E, red, seedBegin, h1, n2, kMax, hasExact, redN, base + lane);
+                    mine = seedLeaf(ix, E, red, seedBegin, h1, n2, kMax, hasExact, redN, base + lane, P.fullHamming != 0);
                 unsigned int const live = __ballot_sync(0xffffffffu, mine.len != 0);
                 if (mine.len != 0)
                     myCur[static_cast<unsigned long long>(k) * S.maxLeaves + out + __popc(live & ((1u << lane) - 1u))] = mine;

@@ -333,15 +333,46 @@ static void seedCursors(Ctx const & c, lgpu_search_opts const & so, uint8_t cons
     Cursor const root{0, d.C[d.sigma], 0};
     if (!(c.p.seed_half_exact && so.max_seed_dist != 0))
     {
-        // search_no_errors: only max_seed_dist == 0 is in scope here
-        Cursor cur = root;
+        // search_impl -> search_backtracking_with_buffers (src/search_algo.hpp:484-494,
+        // FMC search/BacktrackingWithBuffers.h:40-83): Hamming distance over the whole seed
+        auto noErrors = [&](Cursor cur, uint32_t i)
+        {
+            for (; i < so.seed_length; ++i)
+            {
+                cur = extendRight(d, cur, redSeed[i] + 1u);
+                if (cur.len == 0)
+                    return;
+            }
+            out.push_back(cur);
+        };
+        if (so.max_seed_dist == 0)
+        {
+            noErrors(root, 0);
+            return;
+        }
+        uint32_t const                           sigmaAll = d.sigma; // symbols 1 .. sigma-1 (0 = sentinel)
+        std::vector<std::pair<Cursor, uint32_t>> b1, b2;
+        b1.emplace_back(root, 0u);
         for (uint32_t i = 0; i < so.seed_length; ++i)
         {
-            cur = extendRight(d, cur, redSeed[i] + 1u);
-            if (cur.len == 0)
-                return;
+            uint32_t const r = redSeed[i] + 1u;
+            for (auto const & [cu, err] : b1)
+                for (uint32_t s = 1; s < sigmaAll; ++s)
+                {
+                    Cursor const n = extendRight(d, cu, s);
+                    if (n.len == 0)
+                        continue;
+                    uint32_t const e2 = err + (r != s ? 1u : 0u);
+                    if (e2 < so.max_seed_dist)
+                        b2.emplace_back(n, e2);
+                    else
+                        noErrors(n, i + 1);
+                }
+            b1.clear();
+            std::swap(b1, b2);
         }
-        out.push_back(cur);
+        for (auto const & e : b1)
+            out.push_back(e.first);
         return;
     }
     uint32_t const half1 = so.seed_length / 2;

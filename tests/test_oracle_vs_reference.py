@@ -28,6 +28,26 @@ def test_oracle_reproduces_reference(golden_dir, case, domain, profile):
     o.close()
 
 
+@pytest.mark.parametrize("case,domain,name,kw", [("prot_diverged", 0, "nohalf", dict(seed_half_exact=0)),
+                                                 ("prot_diverged", 0, "nohalf_d2", dict(seed_half_exact=0, delta=2)),
+                                                 ("nucl", 1, "nohalf", dict(seed_half_exact=0))])
+def test_oracle_reproduces_reference_seed_variants(golden_dir, case, domain, name, kw):
+    """Hamming distance over the whole seed (search_backtracking_with_buffers), delta 1 and 2"""
+    o = orc.Oracle(os.path.join(golden_dir, case, "db.lba"))
+    ids, data, offs = orc.read_fasta(os.path.join(golden_dir, case, "q.fasta"))
+    res = orc.encode(data, query_encoding(case, domain))
+    p = o.params(domain, "none")
+    p.seed_half_exact = kw["seed_half_exact"]
+    if "delta" in kw:
+        p.opts.max_seed_dist = kw["delta"]
+    hits, st = o.search(p, res, offs)
+    ref, funnel = load_golden(golden_dir, case, name)
+    assert sorted(o.m8(p, hits, ids)) == sorted(ref)
+    for k in FUNNEL:
+        assert int(st[k]) == funnel[k], k
+    o.close()
+
+
 def test_fm_primitives_against_text(golden_dir):
     """rank / locate against brute force on the text reconstructed from the stored sequences"""
     o = orc.Oracle(os.path.join(golden_dir, "prot_flat", "db.lba"))
