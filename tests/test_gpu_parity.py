@@ -379,28 +379,38 @@ def test_cli_bam_content_is_identical_to_reference(golden_dir, case, domain):
     assert open(out, "rb").read()[-28:] == bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
 
 
-def test_cigar_runs_are_consistent(golden_dir):
-    """want_cigar through the API: the runs of every hit add up to its coordinates and statistics"""
+def test_cigar_runs_are_consistent(golden_dir, monkeypatch):
+    """want_cigar through the API: the runs of every hit add up to its coordinates and statistics, and the
+    packed-plane and the scalar trace paths emit the same runs"""
     for case, domain in (("prot_family", 0), ("nucl", 1)):
         path, ids, res, offs = _load(golden_dir, case, domain)
         ix = lambda_b200.Index.load(path)
-        s = lambda_b200.Searcher(ix, domain, "none", want_cigar=1)
-        hits, st = s.search(res, offs)
-        ops = s.last_cigar_ops
-        assert len(hits) and ops is not None
-        for h in hits:
-            r = ops[h["cigar_off"]:h["cigar_off"] + h["cigar_len"]]
-            kind, run = r & 3, r >> 2
-            assert run[kind != 2].sum() == h["q_end"] - h["q_start"]
-            assert run[kind != 1].sum() == h["s_end"] - h["s_start"]
-            assert run.sum() == h["aln_len"] and (kind != 0).sum() == h["n_gap_open"]
-            assert (kind[1:] != kind[:-1]).all()
+        per_mode = {}
+        for trace in ("planes", "scalar"):
+            monkeypatch.setenv("LAMBDA_B200_TRACE", trace)
+            s = lambda_b200.Searcher(ix, domain, "none", want_cigar=1)
+            hits, st = s.search(res, offs)
+            ops = s.last_cigar_ops
+            assert len(hits) and ops is not None
+            runs = []
+            for h in hits:
+                r = ops[h["cigar_off"]:h["cigar_off"] + h["cigar_len"]]
+                kind, run = r & 3, r >> 2
+                assert run[kind != 2].sum() == h["q_end"] - h["q_start"]
+                assert run[kind != 1].sum() == h["s_end"] - h["s_start"]
+                assert run.sum() == h["aln_len"] and (kind != 0).sum() == h["n_gap_open"]
+                assert (kind[1:] != kind[:-1]).all()
+                runs.append(r.tolist())
+            per_mode[trace] = (hits.copy(), runs)
+            s.close()
+        assert per_mode["planes"][1] == per_mode["scalar"][1]
+        monkeypatch.delenv("LAMBDA_B200_TRACE")
         # the same search without cigars returns the same records
         s2 = lambda_b200.Searcher(ix, domain, "none")
         h2, _ = s2.search(res, offs)
         for f in HIT_INT_FIELDS:
-            assert (h2[f] == hits[f]).all(), f
-        s.close(); s2.close(); ix.close()
+            assert (h2[f] == per_mode["planes"][0][f]).all(), f
+        s2.close(); ix.close()
 
 
 def test_multi_stream_split_is_invisible(golden_dir, monkeypatch):
