@@ -339,6 +339,8 @@ struct lgpu_ctx
     PinnedBuf<unsigned int> hCigarStage;
     std::vector<lgpu_match> matchesHost;
     cudaEvent_t             ev[8]{};
+    cudaEvent_t             evSync = nullptr; // blocking-sync event: waiting host threads sleep instead of spinning
+    bool                    blockingSync = false; // LAMBDA_B200_BLOCKING_SYNC=1: sleep instead of spin (measured slower)
 
     DevQueries Q{};
     uint64_t   nQueries = 0, totalResidues = 0;
@@ -351,6 +353,8 @@ struct lgpu_ctx
         for (auto & e : ev)
             if (e)
                 cudaEventDestroy(e);
+        if (evSync)
+            cudaEventDestroy(evSync);
         if (stream)
             cudaStreamDestroy(stream);
     }
@@ -362,6 +366,21 @@ namespace lgpu
 // -------------------------------------------------------------------------------------------------
 // pipeline stages
 // -------------------------------------------------------------------------------------------------
+
+// Wait for the context's stream.  With one process per GPU and several sub-batch threads per process a box
+// runs more waiting host threads than it has cores; LAMBDA_B200_BLOCKING_SYNC=1 lets them sleep on a
+// blocking-sync event instead of spinning.  Measured slower (wake-up latency at ~50 sync points per step:
+// 61.0 vs 58.7 ms on 1 GPU, 66.6 vs 61.8 ms per step on 4 GPUs / 16 cores), so spinning stays the default.
+static inline void syncStream(lgpu_ctx & c)
+{
+    if (c.blockingSync)
+    {
+        LGPU_CUDA(cudaEventRecord(c.evSync, c.stream));
+        LGPU_CUDA(cudaEventSynchronize(c.evSync));
+    }
+    else
+        LGPU_CUDA(cudaStreamSynchronize(c.stream));
+}
 
 struct StageTimer
 {
@@ -573,7 +592,7 @@ static uint64_t runSeeding(lgpu_ctx & c, lgpu_search_opts const & so, unsigned i
             st->kernel_launches += 1;
         unsigned long long cnt[3];
         LGPU_CUDA(cudaMemcpyAsync(cnt, c.dCounters.p, sizeof(cnt), cudaMemcpyDeviceToHost, c.stream));
-        LGPU_CUDA(cudaStreamSynchronize(c.stream));
+        syncStream(c);
         if (cnt[0] <= c.dMatches.cap)
         {
             if (st)
@@ -627,7 +646,7 @@ static uint64_t runMerge(lgpu_ctx & c, lgpu_match const * dIn, uint64_t n, lgpu_
     LGPU_CUDA(cub::DeviceScan::InclusiveSum(c.dCubTemp.p, tb, c.dHead.p, c.dScan.p, nI, c.stream));
     unsigned int nChains = 0;
     LGPU_CUDA(cudaMemcpyAsync(&nChains, c.dScan.p + (n - 1), 4, cudaMemcpyDeviceToHost, c.stream));
-    LGPU_CUDA(cudaStreamSynchronize(c.stream));
+    syncStream(c);
     c.dMerged.reserve(nChains);
     chainEmitKernel<<<g, 256, 0, c.stream>>>(c.dKey1.p, c.dKey2.p, c.dHead.p, c.dScan.p, n, c.Q, c.dMerged.p);
     LGPU_CUDA(cudaGetLastError());
@@ -780,7 +799,7 @@ static void runScorePass(lgpu_ctx & c, lgpu_match const * dTasks, unsigned int n
     unsigned long long cells = 0;
     LGPU_CUDA(cudaMemcpyAsync(info, c.dClassInfo.p, sizeof(info), cudaMemcpyDeviceToHost, c.stream));
     LGPU_CUDA(cudaMemcpyAsync(&cells, c.dCounters.p, 8, cudaMemcpyDeviceToHost, c.stream));
-    LGPU_CUDA(cudaStreamSynchronize(c.stream));
+    syncStream(c);
     unsigned int launches = 7;
     unsigned int taskOff = 0, jobOff = 0;
     for (int cls = 0; cls < NC; ++cls)
@@ -853,7 +872,7 @@ static void emitCigars(lgpu_ctx & c, unsigned int const * order, unsigned int cn
     unsigned int lastOff = 0, lastCap = 0;
     LGPU_CUDA(cudaMemcpyAsync(&lastOff, c.dCigarOff.p + (cnt - 1), 4, cudaMemcpyDeviceToHost, c.stream));
     LGPU_CUDA(cudaMemcpyAsync(&lastCap, c.dCigarCap.p + (cnt - 1), 4, cudaMemcpyDeviceToHost, c.stream));
-    LGPU_CUDA(cudaStreamSynchronize(c.stream));
+    syncStream(c);
     size_t const total = static_cast<size_t>(lastOff) + lastCap;
     if (c.cigar.size() + total > 0xffffffffull)
         throw ArgError("too many alignment operations in one batch; use smaller batches with want_cigar");
@@ -862,7 +881,7 @@ static void emitCigars(lgpu_ctx & c, unsigned int const * order, unsigned int cn
     launch(c.dCigar.p, c.dCigarOff.p, static_cast<unsigned int>(c.cigar.size()));
     LGPU_CUDA(cudaGetLastError());
     LGPU_CUDA(cudaMemcpyAsync(c.hCigarStage.p, c.dCigar.p, total * 4, cudaMemcpyDeviceToHost, c.stream));
-    LGPU_CUDA(cudaStreamSynchronize(c.stream));
+    syncStream(c);
     c.cigar.insert(c.cigar.end(), c.hCigarStage.p, c.hCigarStage.p + total);
     if (st)
         st->kernel_launches += 3;
@@ -933,7 +952,7 @@ static void runTraceScalar(lgpu_ctx & c, lgpu_match const * tasks, size_t n, lgp
                 tracebackKernel<<<gridFor(cnt, 128), 128, 0, c.stream>>>(TP);
             }, st);
         LGPU_CUDA(cudaMemcpyAsync(c.hHits.p + begin, c.dHits.p, cnt * sizeof(lgpu_hit), cudaMemcpyDeviceToHost, c.stream));
-        LGPU_CUDA(cudaStreamSynchronize(c.stream));
+        syncStream(c);
         if (st)
             st->kernel_launches += 2;
         begin = end;
@@ -1069,7 +1088,7 @@ static void runTraceCk(lgpu_ctx & c, lgpu_match const * tasks, size_t n, lgpu_ma
             TP.out      = c.dHits.p;
             launchCkTraceback(k.K, TP, cnt, c.stream);
             LGPU_CUDA(cudaGetLastError());
-            LGPU_CUDA(cudaStreamSynchronize(c.stream)); // the order / offset staging arrays are reused by the next chunk
+            syncStream(c); // the order / offset staging arrays are reused by the next chunk
             if (st)
                 st->kernel_launches += 2;
             begin = end;
@@ -1209,7 +1228,7 @@ static void runTracePass(lgpu_ctx & c, lgpu_match const * tasks, size_t n, lgpu_
                 TP.cigarBase = base;
                 tracebackDpxKernel<<<gridFor(total, 128), 128, 0, c.stream>>>(TP);
             }, st);
-        LGPU_CUDA(cudaStreamSynchronize(c.stream)); // the staging arrays are reused by the next group
+        syncStream(c); // the staging arrays are reused by the next group
         if (st)
             st->kernel_launches += 1;
         group.clear();
@@ -1252,7 +1271,7 @@ static void runTracePass(lgpu_ctx & c, lgpu_match const * tasks, size_t n, lgpu_
     if (anyDpx || anyCk)
     {
         LGPU_CUDA(cudaMemcpyAsync(c.hHits.p, c.dHits.p, n * sizeof(lgpu_hit), cudaMemcpyDeviceToHost, c.stream));
-        LGPU_CUDA(cudaStreamSynchronize(c.stream));
+        syncStream(c);
         for (int cls = 0; cls < nPackedClass; ++cls)
             for (unsigned int i : lists[cls])
                 hostOut[i] = c.hHits.p[i];
@@ -1267,7 +1286,7 @@ static void runTracePass(lgpu_ctx & c, lgpu_match const * tasks, size_t n, lgpu_
             sub[k] = tasks[LS[k]];
         c.dTasksScalar.reserve(sub.size());
         LGPU_CUDA(cudaMemcpyAsync(c.dTasksScalar.p, sub.data(), sub.size() * sizeof(lgpu_match), cudaMemcpyHostToDevice, c.stream));
-        LGPU_CUDA(cudaStreamSynchronize(c.stream));
+        syncStream(c);
         runTraceScalar(c, sub.data(), sub.size(), c.dTasksScalar.p, st);
         for (size_t k = 0; k < LS.size(); ++k)
             hostOut[LS[k]] = c.hHits.p[k];
@@ -1307,7 +1326,7 @@ static void runExtension(lgpu_ctx & c, uint64_t nMatches, uint8_t phase, EValueC
     unsigned long long cnt[2];
     LGPU_CUDA(cudaMemcpyAsync(&nKeep, c.dScan.p + (nTasks - 1), 4, cudaMemcpyDeviceToHost, c.stream));
     LGPU_CUDA(cudaMemcpyAsync(cnt, c.dCounters.p, sizeof(cnt), cudaMemcpyDeviceToHost, c.stream));
-    LGPU_CUDA(cudaStreamSynchronize(c.stream));
+    syncStream(c);
     if (st)
     {
         st->kernel_launches += 3;
@@ -1319,7 +1338,7 @@ static void runExtension(lgpu_ctx & c, uint64_t nMatches, uint8_t phase, EValueC
     // the survivors are few (one per reported hit): a host copy of their descriptors lays out the trace buffer
     c.hTasks.reserve(nKeep);
     LGPU_CUDA(cudaMemcpyAsync(c.hTasks.p, c.dTasks2.p, nKeep * sizeof(lgpu_match), cudaMemcpyDeviceToHost, c.stream));
-    LGPU_CUDA(cudaStreamSynchronize(c.stream));
+    syncStream(c);
     size_t const base = c.hits.size();
     c.hits.resize(base + nKeep);
     runTracePass(c, c.hTasks.p, nKeep, c.dTasks2.p, c.hits.data() + base, st);
@@ -1364,14 +1383,14 @@ static void setThresholds(lgpu_ctx & c, EValueComputer & ev, lgpu_stats * st)
     c.dMinEval.reserve(n);
     LGPU_CUDA(cudaMemcpyAsync(c.dMinBit.p, minBit.data(), n * 4, cudaMemcpyHostToDevice, c.stream));
     LGPU_CUDA(cudaMemcpyAsync(c.dMinEval.p, minEval.data(), n * 4, cudaMemcpyHostToDevice, c.stream));
-    LGPU_CUDA(cudaStreamSynchronize(c.stream));
+    syncStream(c);
 }
 
 static void uploadActive(lgpu_ctx & c, std::vector<unsigned int> const & active)
 {
     c.dActive.reserve(active.size());
     LGPU_CUDA(cudaMemcpyAsync(c.dActive.p, active.data(), active.size() * 4, cudaMemcpyHostToDevice, c.stream));
-    LGPU_CUDA(cudaStreamSynchronize(c.stream));
+    syncStream(c);
 }
 
 // the whole path for one batch on one context / one stream; hits end up in c.hits
@@ -1453,7 +1472,7 @@ static BatchView viewOf(lgpu_ctx & c, lgpu_query_batch const & qb, std::vector<u
         if (qb.on_device)
         {
             LGPU_CUDA(cudaMemcpyAsync(offs.data(), qb.offsets, (qb.n_queries + 1) * 8, cudaMemcpyDeviceToHost, c.stream));
-            LGPU_CUDA(cudaStreamSynchronize(c.stream));
+            syncStream(c);
         }
         else
             std::memcpy(offs.data(), qb.offsets, (qb.n_queries + 1) * 8);
@@ -1630,8 +1649,11 @@ static std::unique_ptr<lgpu_ctx> lgpu::makeContext(lgpu_index const * ix, lgpu_p
         throw UnsupportedError("unsupported scoring configuration");
     LGPU_CUDA(cudaSetDevice(ix->device));
     LGPU_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    for (auto & e : c->ev)
-        LGPU_CUDA(cudaEventCreate(&e));
+    if (char const * e = std::getenv("LAMBDA_B200_BLOCKING_SYNC"))
+        c->blockingSync = std::atoi(e) != 0;
+    for (auto & e : c->ev) // stage timers: waited on by the host as well
+        LGPU_CUDA(cudaEventCreateWithFlags(&e, c->blockingSync ? cudaEventBlockingSync : cudaEventDefault));
+    LGPU_CUDA(cudaEventCreateWithFlags(&c->evSync, cudaEventBlockingSync | cudaEventDisableTiming));
     LGPU_CUDA(cudaDeviceGetAttribute(&c->numSMs, cudaDevAttrMultiProcessorCount, ix->device));
     c->dMatrix.reserve(2048);
     LGPU_CUDA(cudaMemcpy(c->dMatrix.p, c->scoring.matrix, 1024, cudaMemcpyHostToDevice));
@@ -1861,7 +1883,7 @@ int lgpu_seed_batch(lgpu_ctx * c, lgpu_query_batch const * q, int phase, lgpu_ma
         if (nM)
             LGPU_CUDA(cudaMemcpyAsync(c->matchesHost.data(), c->dMatches.p, nM * sizeof(lgpu_match), cudaMemcpyDeviceToHost,
                                       c->stream));
-        LGPU_CUDA(cudaStreamSynchronize(c->stream));
+        syncStream(*c);
         *matches = c->matchesHost.data();
         *n       = nM;
     });
@@ -1886,7 +1908,7 @@ int lgpu_merge_matches(lgpu_ctx * c, lgpu_query_batch const * q, lgpu_match cons
         if (nOut)
             LGPU_CUDA(cudaMemcpyAsync(c->matchesHost.data(), c->dMerged.p, nOut * sizeof(lgpu_match), cudaMemcpyDeviceToHost,
                                       c->stream));
-        LGPU_CUDA(cudaStreamSynchronize(c->stream));
+        syncStream(*c);
         *merged  = c->matchesHost.data();
         *nMerged = nOut;
     });
@@ -1929,7 +1951,7 @@ int lgpu_extend_scores(lgpu_ctx * c, lgpu_query_batch const * q, lgpu_match cons
         c->dScores.reserve(n);
         runScorePass(*c, c->dUserMatches.p, static_cast<unsigned int>(n), c->dScores.p, stats);
         LGPU_CUDA(cudaMemcpyAsync(scores, c->dScores.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
-        LGPU_CUDA(cudaStreamSynchronize(c->stream));
+        syncStream(*c);
     });
 }
 
