@@ -185,35 +185,77 @@ def make_queries(wl, d, n_queries, qlen, seed):
 # ------------------------------------------------------------------------------------------------
 
 class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons of one GPU, sampled DURING the timed region.  NVML in-process (a sample costs
+    well under a millisecond, so even a 0.3 s region gets tens of samples); `nvidia-smi` only if NVML cannot be
+    loaded.  The first sample is taken synchronously in start_sampling() so the handle/driver path is warm."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4), ("hw_power_brake_slowdown", 0x80))
 
     def __init__(self, gpu):
         super().__init__(daemon=True)
-        self.gpu, self.rows, self.stop_flag = gpu, [], False
+        self.gpu, self.rows, self.stop_flag, self.active = self._physical_index(gpu), [], False, False
+        self.nvml, self.handle, self.max_mhz, self.source = None, None, None, "nvidia-smi"
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml, self.source = pynvml, "nvml"
+        except Exception as e:  # noqa: BLE001 - fall back to the command-line tool
+            log(f"NVML unavailable ({e}); sampling clocks with nvidia-smi")
+
+    @staticmethod
+    def _physical_index(local):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [x.strip() for x in vis.split(",") if x.strip()]
+        if local < len(ids) and ids[local].isdigit():
+            return int(ids[local])
+        return local
+
+    def _sample(self):
+        if self.nvml is not None:
+            n = self.nvml
+            mhz = int(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+            try:
+                mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+            except Exception:  # noqa: BLE001 - older binding name
+                mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            return mhz, self.max_mhz, [name for name, bit in self.REASONS if mask & bit]
+        out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+        r = [x.strip() for x in out.strip().split(",")]
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        return int(r[0]), int(r[1]), [nm for nm, v in zip(names, r[2:6]) if v.lower().startswith("active")]
 
     def run(self):
         while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([x.strip() for x in out.strip().split(",")])
-            except Exception:
-                pass
-            time.sleep(0.2)
+            if self.active:
+                try:
+                    self.rows.append(self._sample())
+                except Exception:  # noqa: BLE001 - a failed sample is just missing
+                    pass
+            time.sleep(0.01 if self.nvml is not None else 0.2)
+
+    def begin(self):
+        """call right before the timed region"""
+        self.active = True
+
+    def end(self):
+        """call right after the timed region; with the slow nvidia-smi path make sure at least one sample that
+        STARTED inside the region is waited for"""
+        self.active = False
 
     def summary(self):
         self.stop_flag = True
-        sm = [int(r[0]) for r in self.rows if len(r) >= 6 and r[0].isdigit()]
-        mx = [int(r[1]) for r in self.rows if len(r) >= 6 and r[1].isdigit()]
-        reasons = set()
-        for r in self.rows:
-            if len(r) >= 6:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+        if self.is_alive():
+            self.join(timeout=15)
+        sm = [r[0] for r in self.rows]
+        mx = [r[1] for r in self.rows if r[1]]
+        reasons = sorted({x for r in self.rows for x in r[2]})
         return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": self.source}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -390,14 +432,17 @@ def main():
     for _ in range(args.warmup):
         step(True)
         step(True, s_serial)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
         sampler.start()
+        sampler.begin()
     ms_res, wall_res, st_pipe, hits, total_hits = timed(True, args.steps)
     ms_e2e, wall_e2e, st_e2e, _, _ = timed(False, args.steps)
     # same steps again strictly serial (one stream): per-stage / per-kernel device times for the roofline
     ms_serial, _, st, _, _ = timed(True, args.steps, s_serial)
-    clocks = sampler.summary() if rank == 0 else None
+    if sampler:
+        sampler.end()
+    clocks = sampler.summary() if sampler else None
 
     nq_total = args.n_queries * n_gpus * args.steps
     value = nq_total / (ms_res * 1e-3)
