@@ -474,17 +474,19 @@ def main():
     gcups_trace = cells_trace / args.steps / (ms_trace * 1e-3) / 1e9 if ms_trace > 0 else 0.0
     achieved = gcups_score * 10.0  # 10 int16 ops per cell update (5 add + 5 max), SURVEY §8(d)
     # DRAM traffic of that kernel from the committed `ncu --set full` capture of this workload (per launch)
-    traffic = None
+    traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", f"r1_ncu_score_{wl}.json")
     if os.path.exists(tp):
         try:
             t = json.load(open(tp))
-            traffic = {"dram_bytes": t["dram_bytes_read"] + t["dram_bytes_write"], "source": os.path.relpath(tp, ROOT)}
+            traffic = float(t["dram_bytes_read"] + t["dram_bytes_write"])  # bytes per launch (dram__bytes_read + write)
+            traffic_src = os.path.relpath(tp, ROOT)
         except Exception:
             traffic = None
     roofline = {"kernel": "swScoreDpxKernel<T,K> (DP pass 1, packed int16 DPX)", "bound": "int16-alu", "achieved": achieved,
                 "peak": peak_gops, "unit": "Gop/s (int16)", "frac": (achieved / peak_gops) if peak_gops else None,
-                "peak_source": peak_src, "traffic": traffic, "gcups": gcups_score,
+                "peak_source": peak_src, "traffic": traffic, "traffic_unit": "bytes per launch (DRAM read + write, ncu --set full)",
+                "traffic_source": traffic_src, "gcups": gcups_score,
                 "algorithmic": "10 int16 ops per DP cell x cells of the step / DP pass-1 stage time (CUDA events)"}
 
     # the other kernels of the step: bound and achieved fraction from the committed ncu capture (static evidence)

@@ -29,6 +29,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cuda_runtime.h>
+#include <sched.h>
 #include <unistd.h>
 
 #include "../../include/lambda_b200.h"
@@ -340,7 +341,7 @@ struct lgpu_ctx
     std::vector<lgpu_match> matchesHost;
     cudaEvent_t             ev[8]{};
     cudaEvent_t             evSync = nullptr; // blocking-sync event: waiting host threads sleep instead of spinning
-    bool                    blockingSync = false; // LAMBDA_B200_BLOCKING_SYNC=1: sleep instead of spin (measured slower)
+    int                     syncMode = 0;     // LGPU_SYNC_*: how host threads wait for the stream (LAMBDA_B200_SYNC)
 
     DevQueries Q{};
     uint64_t   nQueries = 0, totalResidues = 0;
@@ -367,19 +368,96 @@ namespace lgpu
 // pipeline stages
 // -------------------------------------------------------------------------------------------------
 
-// Wait for the context's stream.  With one process per GPU and several sub-batch threads per process a box
-// runs more waiting host threads than it has cores; LAMBDA_B200_BLOCKING_SYNC=1 lets them sleep on a
-// blocking-sync event instead of spinning.  Measured slower (wake-up latency at ~50 sync points per step:
-// 61.0 vs 58.7 ms on 1 GPU, 66.6 vs 61.8 ms per step on 4 GPUs / 16 cores), so spinning stays the default.
+// Host waits.  A step has ~50 points where a host thread waits for its stream, and with one process per GPU and
+// three sub-batch threads per process a box may run more waiting threads than it has cores.
+//   spin   cudaStreamSynchronize / cudaEventSynchronize (the driver spins): lowest latency, the measured best
+//          while every waiting thread has a core of its own (58.7 ms per step on 1 GPU, 61.8 ms on 4 GPUs / 16 cores)
+//   block  sleep on a blocking-sync event: measured slower (wake-up latency: 61.0 / 66.6 ms in the same runs)
+//   yield  poll cudaStreamQuery / cudaEventQuery and sched_yield() between polls: behaves like spinning when the
+//          core is not contended (sched_yield returns at once) and hands the core to a runnable thread -- e.g. a
+//          sub-batch thread that has kernels to launch -- when it is
+//   auto   (default) spin, unless the search threads of all ranks on this box outnumber the cores this process may
+//          run on (LOCAL_WORLD_SIZE x threads inside searchOne > sched_getaffinity count): then yield
+// LAMBDA_B200_SYNC=spin|block|yield|auto; LAMBDA_B200_BLOCKING_SYNC=1 is the older spelling of block.
+// Measured (profiles/r1_sweep_hostwait.jsonl, searchp step, 1 GPU): all 16 cores: spin 59.0 ms, yield 59.3 ms;
+// process pinned to 2 cores (3 search threads): spin 63.9 ms, auto (= yield) 64.1 ms, block 66.2 ms.
+enum { LGPU_SYNC_AUTO = 0, LGPU_SYNC_SPIN = 1, LGPU_SYNC_BLOCK = 2, LGPU_SYNC_YIELD = 3 };
+static std::atomic<int> g_searchThreads{0}; // host threads of this process currently inside searchOne
+
+struct SearchThreadScope
+{
+    SearchThreadScope() { g_searchThreads.fetch_add(1, std::memory_order_relaxed); }
+    ~SearchThreadScope() { g_searchThreads.fetch_sub(1, std::memory_order_relaxed); }
+};
+
+static int hostCores()
+{
+    static int const n = [] {
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0)
+            return CPU_COUNT(&set);
+        unsigned int const h = std::thread::hardware_concurrency();
+        return h ? static_cast<int>(h) : 1;
+    }();
+    return n;
+}
+
+static int localWorldSize()
+{
+    static int const n = [] {
+        char const * e = std::getenv("LOCAL_WORLD_SIZE"); // set by torchrun: ranks on this box
+        int const    v = e ? std::atoi(e) : 1;
+        return v > 0 ? v : 1;
+    }();
+    return n;
+}
+
+static inline int effectiveSyncMode(lgpu_ctx const & c)
+{
+    if (c.syncMode != LGPU_SYNC_AUTO)
+        return c.syncMode;
+    int const waiting = std::max(1, g_searchThreads.load(std::memory_order_relaxed)) * localWorldSize();
+    return waiting > hostCores() ? LGPU_SYNC_YIELD : LGPU_SYNC_SPIN;
+}
+
+template <typename Query>
+static inline void pollYield(Query && query)
+{
+    for (unsigned int polls = 0;; ++polls)
+    {
+        cudaError_t const e = query();
+        if (e == cudaSuccess)
+            return;
+        if (e != cudaErrorNotReady)
+            LGPU_CUDA(e);
+        if (polls >= 16)
+            sched_yield();
+    }
+}
+
 static inline void syncStream(lgpu_ctx & c)
 {
-    if (c.blockingSync)
+    switch (effectiveSyncMode(c))
     {
-        LGPU_CUDA(cudaEventRecord(c.evSync, c.stream));
-        LGPU_CUDA(cudaEventSynchronize(c.evSync));
+        case LGPU_SYNC_BLOCK:
+            LGPU_CUDA(cudaEventRecord(c.evSync, c.stream));
+            LGPU_CUDA(cudaEventSynchronize(c.evSync));
+            break;
+        case LGPU_SYNC_YIELD:
+            pollYield([&] { return cudaStreamQuery(c.stream); });
+            break;
+        default:
+            LGPU_CUDA(cudaStreamSynchronize(c.stream));
     }
+}
+
+static inline void waitEvent(lgpu_ctx & c, cudaEvent_t ev)
+{
+    if (effectiveSyncMode(c) == LGPU_SYNC_YIELD)
+        pollYield([&] { return cudaEventQuery(ev); });
     else
-        LGPU_CUDA(cudaStreamSynchronize(c.stream));
+        LGPU_CUDA(cudaEventSynchronize(ev)); // block mode: the events were created with cudaEventBlockingSync
 }
 
 struct StageTimer
@@ -390,7 +468,14 @@ struct StageTimer
     ~StageTimer()
     {
         cudaEventRecord(c.ev[1], c.stream);
-        cudaEventSynchronize(c.ev[1]);
+        try
+        {
+            waitEvent(c, c.ev[1]);
+        }
+        catch (...)
+        {
+            return; // the error is sticky: the next checked call of the stage reports it
+        }
         float ms = 0;
         cudaEventElapsedTime(&ms, c.ev[0], c.ev[1]);
         if (acc)
@@ -1397,6 +1482,7 @@ static void uploadActive(lgpu_ctx & c, std::vector<unsigned int> const & active)
 static void searchOne(lgpu_ctx & c, BatchView const & qb, lgpu_stats * st)
 {
     LGPU_CUDA(cudaSetDevice(c.index->device));
+    SearchThreadScope const scope; // counted by the host-wait policy (effectiveSyncMode)
     c.hits.clear();
     c.cigar.clear();
     uploadQueries(c, qb, st);
@@ -1576,7 +1662,7 @@ static void searchBatch(lgpu_ctx & c, lgpu_query_batch const & qb, lgpu_hits * o
         }
     }
     LGPU_CUDA(cudaEventRecord(c.ev[3], c.stream));
-    LGPU_CUDA(cudaEventSynchronize(c.ev[3]));
+    waitEvent(c, c.ev[3]);
     if (st)
     {
         float ms = 0;
@@ -1650,9 +1736,12 @@ static std::unique_ptr<lgpu_ctx> lgpu::makeContext(lgpu_index const * ix, lgpu_p
     LGPU_CUDA(cudaSetDevice(ix->device));
     LGPU_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     if (char const * e = std::getenv("LAMBDA_B200_BLOCKING_SYNC"))
-        c->blockingSync = std::atoi(e) != 0;
+        c->syncMode = std::atoi(e) != 0 ? LGPU_SYNC_BLOCK : LGPU_SYNC_AUTO;
+    if (char const * e = std::getenv("LAMBDA_B200_SYNC"))
+        c->syncMode = !std::strcmp(e, "spin") ? LGPU_SYNC_SPIN : !std::strcmp(e, "block") ? LGPU_SYNC_BLOCK
+                      : !std::strcmp(e, "yield") ? LGPU_SYNC_YIELD : LGPU_SYNC_AUTO;
     for (auto & e : c->ev) // stage timers: waited on by the host as well
-        LGPU_CUDA(cudaEventCreateWithFlags(&e, c->blockingSync ? cudaEventBlockingSync : cudaEventDefault));
+        LGPU_CUDA(cudaEventCreateWithFlags(&e, c->syncMode == LGPU_SYNC_BLOCK ? cudaEventBlockingSync : cudaEventDefault));
     LGPU_CUDA(cudaEventCreateWithFlags(&c->evSync, cudaEventBlockingSync | cudaEventDisableTiming));
     LGPU_CUDA(cudaDeviceGetAttribute(&c->numSMs, cudaDevAttrMultiProcessorCount, ix->device));
     c->dMatrix.reserve(2048);

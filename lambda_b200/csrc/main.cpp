@@ -24,6 +24,7 @@
 #include <zlib.h>
 
 #include "../../include/lambda_b200.h"
+#include "query_reader.hpp"
 #include "tables_generated.inc" // alphabets and the genetic code, for the report-style outputs
 
 namespace
@@ -178,26 +179,11 @@ struct Fasta
 // detectSeqFileAlphabet (src/shared_misc.hpp:83-110): the first sequence decides
 uint32_t detectAlphabet(std::string const & path)
 {
-    std::ifstream in(path, std::ios::binary);
-    if (!in)
-        die("cannot open query file " + path);
-    std::string line, seq;
-    bool        have = false;
-    while (std::getline(in, line))
-    {
-        if (!line.empty() && line.back() == '\r')
-            line.pop_back();
-        if (line.empty())
-            continue;
-        if (line[0] == '>')
-        {
-            if (have)
-                break;
-            have = true;
-        }
-        else if (have)
-            seq += line;
-    }
+    qio::SeqReader reader(path);
+    qio::Record    rec;
+    if (!reader.next(rec))
+        die("Your query file contains no sequences.");
+    std::string const & seq = rec.seq;
     auto const allIn = [&](char const * set) {
         for (char c : seq)
             if (!std::strchr(set, c))
@@ -218,11 +204,9 @@ uint32_t detectAlphabet(std::string const & path)
     die("Your query file contains illegal characters in the first sequence.");
 }
 
-Fasta readFasta(std::string const & path, bool aminoAcid)
+// FASTA / FASTQ, plain or gzip-compressed (query_reader.hpp); residues become BioC++ ranks
+Fasta readQueries(std::string const & path, bool aminoAcid)
 {
-    std::ifstream in(path, std::ios::binary);
-    if (!in)
-        die("cannot open query file " + path);
     // char -> rank like BioC++ (aa27: unknown -> X; dna5: unknown -> N, U -> T)
     uint8_t tab[256];
     if (aminoAcid)
@@ -247,31 +231,16 @@ Fasta readFasta(std::string const & path, bool aminoAcid)
         }
         tab[static_cast<uint8_t>('U')] = tab[static_cast<uint8_t>('u')] = 4;
     }
-    Fasta       f;
-    std::string line;
-    bool        have = false;
-    while (std::getline(in, line))
+    Fasta          f;
+    qio::SeqReader reader(path);
+    qio::Record    rec;
+    while (reader.next(rec))
     {
-        if (!line.empty() && line.back() == '\r')
-            line.pop_back();
-        if (line.empty())
-            continue;
-        if (line[0] == '>')
-        {
-            if (have)
-                f.offsets.push_back(f.residues.size());
-            f.ids.push_back(line.substr(1));
-            have = true;
-        }
-        else if (have)
-        {
-            for (char c : line)
-                if (c != ' ' && c != '\t')
-                    f.residues.push_back(tab[static_cast<uint8_t>(c)]);
-        }
-    }
-    if (have)
+        f.ids.push_back(rec.id);
+        for (char c : rec.seq)
+            f.residues.push_back(tab[static_cast<uint8_t>(c)]);
         f.offsets.push_back(f.residues.size());
+    }
     return f;
 }
 
@@ -375,7 +344,55 @@ void bgzfWrite(FILE * fo, std::string const & raw)
     block(nullptr, 0); // end-of-file marker block
 }
 
+// `lambda3_b200 dumpq -q FILE [-a auto|dna5|aminoacid]`: parse the query file exactly like a search would and print
+// "alphabet\t<name>" followed by "<id>\t<residues>" per record (no GPU involved; used by the CPU tests)
+static int dumpQueries(int argc, char ** argv)
+{
+    std::string path, alph = "auto";
+    for (int i = 2; i + 1 < argc; i += 2)
+    {
+        if (!std::strcmp(argv[i], "-q") || !std::strcmp(argv[i], "--query"))
+            path = argv[i + 1];
+        else if (!std::strcmp(argv[i], "-a") || !std::strcmp(argv[i], "--input-alphabet"))
+            alph = argv[i + 1];
+        else
+            die(std::string("unknown option '") + argv[i] + "'");
+    }
+    if (path.empty())
+        die("-q is required");
+    uint32_t const a = alph == "dna5" ? static_cast<uint32_t>(LGPU_ALPH_DNA5)
+                       : alph == "aminoacid" ? static_cast<uint32_t>(LGPU_ALPH_AMINO_ACID) : detectAlphabet(path);
+    bool const  aa = a == LGPU_ALPH_AMINO_ACID;
+    Fasta const f  = readQueries(path, aa);
+    char const * letters = aa ? "ABCDEFGHIJKLMNOPQRSTUVWXYZ*" : "ACGNT";
+    std::printf("alphabet\t%s\n", aa ? "aminoacid" : "dna5");
+    for (size_t i = 0; i < f.ids.size(); ++i)
+    {
+        std::string seq;
+        for (uint64_t k = f.offsets[i]; k < f.offsets[i + 1]; ++k)
+            seq.push_back(letters[f.residues[k]]);
+        std::printf("%s\t%s\n", f.ids[i].c_str(), seq.c_str());
+    }
+    return 0;
+}
+
+static int run(int argc, char ** argv);
+
 int main(int argc, char ** argv)
+{
+    try
+    {
+        if (argc >= 2 && !std::strcmp(argv[1], "dumpq"))
+            return dumpQueries(argc, argv);
+        return run(argc, argv);
+    }
+    catch (std::exception const & e) // query parser errors (query_reader.hpp); same exit path as the reference's searchMain
+    {
+        die(e.what());
+    }
+}
+
+static int run(int argc, char ** argv)
 {
     Options o;
     parse(argc, argv, o);
@@ -395,7 +412,7 @@ int main(int argc, char ** argv)
                   : o.inputAlphabet == "aminoacid" ? static_cast<uint32_t>(LGPU_ALPH_AMINO_ACID)
                                                    : detectAlphabet(o.query);
     o.params.query_alph = qryAlph;
-    Fasta const             f    = readFasta(o.query, qryAlph == LGPU_ALPH_AMINO_ACID);
+    Fasta const             f    = readQueries(o.query, qryAlph == LGPU_ALPH_AMINO_ACID);
     uint64_t const          nQ   = f.ids.size();
     double const            t2   = now();
     if (o.verbosity >= 2)
