@@ -308,6 +308,21 @@ int lgpu_min_raw_score(lgpu_params const *, uint64_t query_len, uint64_t db_tota
 int lgpu_format_m8(lgpu_params const *, lgpu_hit const *, char const * q_id, char const * s_id, char * buf,
                    size_t cap);
 
+/* BLAST tabular line with a custom column list (`lambda3 --output-columns`, src/search_options.hpp:224-232,
+ * 710-760).  A column is identified by its index in the reference's BlastMatchField::Enum
+ * (SQ/blast/blast_tabular.h:403-454): lgpu_tabular_column("qseqid") -> 1, "std" -> 0 (expands to the twelve
+ * default columns), unknown label -> -1.  lgpu_tabular_column_label() returns the text the "# Fields:" comment
+ * line of .m9 uses for that column (NULL if out of range), lgpu_tabular_column_supported() whether a line can be
+ * formatted with it: columns the reference itself does not implement print "n/i" like there; the taxonomy
+ * columns (staxids, lcaid, lcataxid) are not supported (the taxonomy of the index is not loaded).
+ * lgpu_format_tabular() returns the line length, LGPU_ERR_ARG for bad arguments / unsupported columns. */
+int          lgpu_tabular_column(char const * option_label);
+char const * lgpu_tabular_column_name(uint32_t column); /* the option label of a column, NULL if out of range */
+char const * lgpu_tabular_column_label(uint32_t column);
+int          lgpu_tabular_column_supported(uint32_t column);
+int          lgpu_format_tabular(lgpu_params const *, lgpu_hit const *, char const * q_id, char const * s_id,
+                                 uint32_t const * columns, size_t n_columns, char * buf, size_t cap);
+
 int lgpu_version(void);
 
 #ifdef __cplusplus

@@ -6,8 +6,8 @@ ctypes and mirrors the reference's search interface (index + options in, BLAST-t
 There is no CPU fallback: importing works anywhere, but every compute call needs the CUDA library
 and a GPU and raises otherwise.
 """
-from ._abi import DOMAIN, HIT_DT, MATCH_DT, STATS_DT, Params, encode, read_fasta  # noqa: F401
+from ._abi import DOMAIN, HIT_DT, MATCH_DT, STATS_DT, Params, encode, read_fasta, read_queries  # noqa: F401
 from .api import Index, LambdaError, Searcher, load_library  # noqa: F401
 
-__all__ = ["Index", "Searcher", "LambdaError", "load_library", "Params", "encode", "read_fasta", "HIT_DT",
+__all__ = ["Index", "Searcher", "LambdaError", "load_library", "Params", "encode", "read_fasta", "read_queries", "HIT_DT",
            "MATCH_DT", "STATS_DT", "DOMAIN"]

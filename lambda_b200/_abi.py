@@ -77,23 +77,72 @@ def encode(seq_bytes: np.ndarray, domain: int) -> np.ndarray:
     return tab[np.ascontiguousarray(seq_bytes, np.uint8)]
 
 
-def read_fasta(path):
-    """Minimal FASTA reader: returns (ids, concatenated ASCII residues uint8, offsets uint64[n+1])."""
-    ids, seqs, cur = [], [], []
+_FASTA_EXT = (".fasta", ".fa", ".fna", ".ffn", ".faa", ".frn", ".fas")
+_FASTQ_EXT = (".fastq", ".fq")
+
+
+def read_queries(path):
+    """Query file reader with the reference's rules (bio::io::seq::reader, src/search_algo.hpp:342-348; the C++ host
+    does the same in csrc/query_reader.hpp): FASTA or FASTQ by file extension, gzip/BGZF detected by magic bytes.
+    Returns (ids, concatenated ASCII residues uint8, offsets uint64[n+1])."""
+    import gzip
+    low = path.lower()
+    for z in (".gz", ".bgzf"):
+        if low.endswith(z):
+            low = low[: -len(z)]
+            break
+    if low.endswith(_FASTA_EXT):
+        fastq = False
+    elif low.endswith(_FASTQ_EXT):
+        fastq = True
+    else:
+        raise ValueError(f"The query file's extension is not handled: {path}")
     with open(path, "rb") as f:
-        for line in f:
-            line = line.rstrip(b"\r\n")
-            if line.startswith(b">"):
-                if ids:
-                    seqs.append(b"".join(cur))
-                ids.append(line[1:].decode())
-                cur = []
-            elif line:
-                cur.append(line)
-    if ids:
-        seqs.append(b"".join(cur))
+        magic = f.read(2)
+    opener = gzip.open if magic == b"\x1f\x8b" else open
+    ids, seqs = [], []
+    with opener(path, "rb") as f:
+        if fastq:
+            while True:
+                head = f.readline()
+                if not head:
+                    break
+                head = head.rstrip(b"\r\n")
+                if not head:
+                    continue
+                if not head.startswith(b"@"):
+                    raise ValueError("ID-line does not begin with '@'.")
+                seq = f.readline().rstrip(b"\r\n")
+                plus = f.readline()
+                qual = f.readline().rstrip(b"\r\n")
+                if not plus.startswith(b"+"):
+                    raise ValueError("Third FastQ record line does not begin with '+'.")
+                if len(qual) != len(seq):
+                    raise ValueError(f"Size mismatch between sequence ({len(seq)}) and qualities ({len(qual)}).")
+                ids.append(head[1:].decode())
+                seqs.append(seq)
+        else:
+            drop = bytes(range(48, 58)) + b" \t\r\n\x0b\x0c"  # digits and white space
+            cur = None
+            for line in f:
+                if line[:1] in (b">", b";"):
+                    if cur is not None:
+                        seqs.append(b"".join(cur))
+                    ids.append(line[1:].rstrip(b"\r\n").decode())
+                    cur = []
+                elif cur is not None:
+                    cur.append(line.translate(None, drop))
+                elif line.strip():
+                    raise ValueError("Record does not begin with '>' or ';'.")
+            if cur is not None:
+                seqs.append(b"".join(cur))
+            if any(len(s) == 0 for s in seqs):
+                raise ValueError("No sequence or no valid sequence characters.")
     offs = np.zeros(len(seqs) + 1, np.uint64)
     if seqs:
         np.cumsum([len(s) for s in seqs], out=offs[1:])
     data = np.frombuffer(b"".join(seqs), np.uint8)
     return ids, data, offs
+
+
+read_fasta = read_queries  # older name

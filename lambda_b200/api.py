@@ -70,6 +70,14 @@ def load_library():
     lib.lgpu_evalue.argtypes = [C.POINTER(Params), C.c_int32, u64, u64, C.POINTER(C.c_double)]
     lib.lgpu_min_raw_score.argtypes = [C.POINTER(Params), u64, u64, C.POINTER(C.c_int32)]
     lib.lgpu_format_m8.argtypes = [C.POINTER(Params), vp, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]
+    lib.lgpu_format_tabular.argtypes = [C.POINTER(Params), vp, C.c_char_p, C.c_char_p, C.POINTER(C.c_uint32), C.c_size_t,
+                                        C.c_char_p, C.c_size_t]
+    lib.lgpu_tabular_column.argtypes = [C.c_char_p]
+    lib.lgpu_tabular_column_label.argtypes = [C.c_uint32]
+    lib.lgpu_tabular_column_label.restype = C.c_char_p
+    lib.lgpu_tabular_column_name.argtypes = [C.c_uint32]
+    lib.lgpu_tabular_column_name.restype = C.c_char_p
+    lib.lgpu_tabular_column_supported.argtypes = [C.c_uint32]
     _lib = lib
     return lib
 
@@ -233,6 +241,28 @@ class Searcher:
             h = hits[i:i + 1]
             n = lib.lgpu_format_m8(C.byref(self.params), _p(h), query_ids[int(h["q_id"][0])].encode(),
                                    sids[int(h["s_id"][0])].encode(), buf, 8192)
+            lines.append(buf.raw[:n].decode())
+        return lines
+
+    def tabular(self, hits, query_ids, columns="std"):
+        """BLAST tabular lines with the column list of `lambda3 --output-columns` (space-separated NCBI specifiers)"""
+        lib = load_library()
+        cols = []
+        for name in columns.split():
+            c = lib.lgpu_tabular_column(name.encode())
+            if c < 0:
+                raise LambdaError(f'Unknown column specifier "{name}".')
+            cols.append(c)
+        arr = (C.c_uint32 * len(cols))(*cols)
+        buf = C.create_string_buffer(16384)
+        sids = self.index.subject_ids
+        lines = []
+        for i in range(len(hits)):
+            h = hits[i:i + 1]
+            n = lib.lgpu_format_tabular(C.byref(self.params), _p(h), query_ids[int(h["q_id"][0])].encode(),
+                                        sids[int(h["s_id"][0])].encode(), arr, len(cols), buf, 16384)
+            if n < 0:
+                raise LambdaError("unsupported column in " + columns)
             lines.append(buf.raw[:n].decode())
         return lines
 

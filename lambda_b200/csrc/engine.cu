@@ -2175,4 +2175,39 @@ int lgpu_format_m8(lgpu_params const * p, lgpu_hit const * h, char const * qId, 
     return formatM8(p->domain, *h, qId, std::strlen(qId), sId, std::strlen(sId), buf, cap);
 }
 
+int lgpu_tabular_column(char const * label)
+{
+    if (!label)
+        return -1;
+    for (int i = 0; i < kNumTabColumns; ++i)
+        if (!std::strcmp(label, tabColumnOptionLabels()[i]))
+            return i;
+    return -1;
+}
+
+char const * lgpu_tabular_column_name(uint32_t column)
+{
+    return column < static_cast<uint32_t>(kNumTabColumns) ? tabColumnOptionLabels()[column] : nullptr;
+}
+
+char const * lgpu_tabular_column_label(uint32_t column)
+{
+    return column < static_cast<uint32_t>(kNumTabColumns) ? tabColumnLabels()[column] : nullptr;
+}
+
+int lgpu_tabular_column_supported(uint32_t column)
+{
+    return column < static_cast<uint32_t>(kNumTabColumns) && column != TAB_S_TAX_IDS && column != TAB_LCA_ID &&
+           column != TAB_LCA_TAX_ID;
+}
+
+int lgpu_format_tabular(lgpu_params const * p, lgpu_hit const * h, char const * qId, char const * sId, uint32_t const * columns,
+                        size_t nColumns, char * buf, size_t cap)
+{
+    if (!p || !h || !qId || !sId || !buf || (!columns && nColumns))
+        return LGPU_ERR_ARG;
+    int const n = formatTabular(p->domain, *h, qId, std::strlen(qId), sId, std::strlen(sId), columns, nColumns, buf, cap);
+    return n < 0 ? LGPU_ERR_ARG : n;
+}
+
 } // extern "C"

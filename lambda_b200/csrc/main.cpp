@@ -11,6 +11,7 @@
 // that batch's phase-2 hits (src/search.cpp:449-457).  We reproduce exactly that order, so the file is
 // byte-identical to `lambda3 search* -t 1`, not merely equal as a multiset.
 #include <algorithm>
+#include <cctype>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -38,6 +39,8 @@ struct Options
     int         threads   = 1; // only used for the reference's records_per_batch formula
     int         gpus      = 1;
     bool        comments  = false; // .m9: BLAST tabular with comment lines
+    std::string outputColumns = "std"; // --output-columns (.m8 / .m9)
+    std::vector<uint32_t> columns;     // ... resolved to BlastMatchField indices
     bool        report    = false; // .m0: BLAST pairwise report
     bool        bam       = false; // .bam: the same records, binary + BGZF
     bool        sam       = false; // .sam (default tags AS NM ae ai qf, --sam-bam-seq uniq, --sam-bam-clip hard)
@@ -61,9 +64,10 @@ bool endsWith(std::string const & s, char const * suf)
 
 void usage()
 {
-    std::puts("lambda3_b200 searchp|searchn|searchbs -q QUERY.fasta -i INDEX.lba [-o output.m0|.m8|.m9|.sam|.bam] [OPTIONS]\n"
+    std::puts("lambda3_b200 searchp|searchn|searchbs -q QUERY.(fasta|fastq)[.gz] -i INDEX.lba [-o output.m0|.m8|.m9|.sam|.bam] [OPTIONS]\n"
               "  -a, --input-alphabet   auto|dna5|aminoacid (searchp; dna queries are translated: BLASTX/TBLASTX)\n"
               "  -p, --profile          none|fast|sensitive|pairs-default|pairs-sensitive\n"
+              "      --output-columns   'std' or space-separated NCBI column specifiers (.m8 / .m9; 'help' lists them)\n"
               "  -e, --e-value          maximum e-value (default 0.01; -1 = off)\n"
               "      --bit-score        minimum bit score (default -1 = off)\n"
               "      --percent-identity minimum identity in percent (default 0)\n"
@@ -122,6 +126,7 @@ void parse(int argc, char ** argv, Options & o)
         else if (a == "-o" || a == "--output") o.output = need(i);
         else if (a == "-p" || a == "--profile") need(i);
         else if (a == "-a" || a == "--input-alphabet") o.inputAlphabet = need(i);
+        else if (a == "--output-columns") o.outputColumns = need(i);
         else if (a == "-e" || a == "--e-value") o.params.max_evalue = std::atof(need(i));
         else if (a == "--bit-score") o.params.min_bit_score = std::atoi(need(i));
         else if (a == "--percent-identity") o.params.id_cutoff = std::atoi(need(i));
@@ -163,6 +168,37 @@ void parse(int argc, char ** argv, Options & o)
     if (!endsWith(o.output, ".m8") && !o.comments && !o.sam && !o.report)
         die("supported output formats: .m0, .m8, .m9, .sam, .bam");
     o.params.want_cigar = (o.sam || o.report) ? 1u : 0u;
+    // --output-columns (src/search_options.hpp:710-760): space-separated NCBI specifiers, "std" = the default twelve
+    if (o.outputColumns == "help")
+    {
+        std::puts("Please specify the columns in this format -oc 'column1 column2', i.e. space-separated and enclosed in "
+                  "single quotes.\nThe specifiers are the same as in NCBI Blast, currently the following are supported:");
+        for (uint32_t c = 0; lgpu_tabular_column_name(c); ++c)
+            if (lgpu_tabular_column_supported(c))
+                std::printf("\t%s%s%s\n", lgpu_tabular_column_name(c), std::strlen(lgpu_tabular_column_name(c)) >= 8 ? "\t" : "\t\t",
+                            lgpu_tabular_column_label(c));
+        std::exit(0);
+    }
+    {
+        std::string tok;
+        auto        flush = [&]() {
+            if (tok.empty())
+                return;
+            int const c = lgpu_tabular_column(tok.c_str());
+            if (c < 0)
+                die("Unknown column specifier \"" + tok + "\". Please see -oc help for valid options.");
+            if (!lgpu_tabular_column_supported(static_cast<uint32_t>(c)))
+                die("column \"" + tok + "\" needs the taxonomy of the index, which lambda3_b200 does not load");
+            o.columns.push_back(static_cast<uint32_t>(c));
+            tok.clear();
+        };
+        for (char ch : o.outputColumns)
+            if (std::isspace(static_cast<unsigned char>(ch)))
+                flush();
+            else
+                tok.push_back(ch);
+        flush();
+    }
     for (int i = 0; i < argc; ++i)
         o.commandLine += (i ? " " : "") + std::string(argv[i]);
     if (std::ifstream(o.output).good())
@@ -478,8 +514,13 @@ static int run(int argc, char ** argv)
             return;
         std::fprintf(fo, "# %s\n# Query: %s\n# Database: %s\n", versionLine.c_str(), f.ids[q].c_str(), o.index.c_str());
         if (nHits)
-            std::fputs("# Fields: query id, subject id, % identity, alignment length, mismatches, gap opens, q. start, q. end, "
-                       "s. start, s. end, evalue, bit score\n", fo);
+        {
+            // _writeFieldLabels (SQ/blast/blast_tabular_out.h): the columns' labels joined by ", "
+            std::fputs("# Fields: ", fo);
+            for (size_t c = 0; c < o.columns.size(); ++c)
+                std::fprintf(fo, "%s%s", c ? ", " : "", lgpu_tabular_column_label(o.columns[c]));
+            std::fputc('\n', fo);
+        }
         std::fprintf(fo, "# %zu hits found\n", nHits);
     };
     // ---- SAM (src/search_output.hpp:346-458 header, :482-716 records; defaults of src/search_options.hpp:339-370) ----
@@ -884,8 +925,8 @@ static int run(int argc, char ** argv)
                     for (lgpu_hit const * h : perQuery[q])
                         if (h->phase == phase)
                         {
-                            int const n = lgpu_format_m8(&o.params, h, f.ids[q].c_str(), subjectId(h->s_id).c_str(),
-                                                         line.data(), line.size());
+                            int const n = lgpu_format_tabular(&o.params, h, f.ids[q].c_str(), subjectId(h->s_id).c_str(),
+                                                              o.columns.data(), o.columns.size(), line.data(), line.size());
                             if (n > 0)
                                 std::fwrite(line.data(), 1, static_cast<size_t>(n), fo);
                         }

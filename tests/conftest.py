@@ -22,7 +22,7 @@ def golden_dir(tmp_path_factory):
     out = tmp_path_factory.mktemp("golden")
     for case in sorted(os.listdir(GOLDEN)):
         src = os.path.join(GOLDEN, case)
-        if not os.path.isdir(src):
+        if not os.path.isdir(src) or case.startswith("_"):
             continue
         dst = out / case
         dst.mkdir()

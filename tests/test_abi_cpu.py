@@ -112,6 +112,38 @@ def test_m8_formatting_matches_golden_line():
     assert buf.raw[:n].decode() == "Q0\tS1856\t80.13\t151\t28\t2\t1\t150\t71\t220\t6e-58\t 216\n"
 
 
+def test_custom_tabular_columns_match_golden_line():
+    """first match line of tests/golden/tblastx/cols.m9 (made by the reference with --output-columns): TBLASTX hit in
+    frames 3/3, coordinates un-translated to nucleotides, unimplemented columns print n/i, accessions n/a"""
+    lib = lambda_b200.load_library()
+    p = api.default_params("protein")
+    h = np.zeros(1, HIT_DT)
+    h["q_start"], h["q_end"], h["s_start"], h["s_end"] = 1, 68, 42, 109
+    h["q_frame"], h["s_frame"], h["q_len"], h["s_len"] = 3, 3, 218, 570
+    h["aln_len"], h["n_match"], h["n_mismatch"], h["n_positive"], h["score"] = 67, 60, 7, 61, 330
+    h["evalue"], h["bit_score"] = 1.2e-33, 131.7
+    from golden.make_golden_columns import COLUMNS
+    cols = [lib.lgpu_tabular_column(c.encode()) for c in COLUMNS.split()]
+    assert min(cols) >= 0 and lib.lgpu_tabular_column(b"nonsense") == -1
+    arr = (C.c_uint32 * len(cols))(*cols)
+    buf = C.create_string_buffer(4096)
+    n = lib.lgpu_format_tabular(C.byref(p), C.c_void_p(h.ctypes.data), b"Q0", b"S104", arr, len(cols), buf, 4096)
+    want = ("Q0\t218\tS104\t570\tQ0\tS104\t89.55\t67\t7\t0\t6\t206\t129\t329\t1e-33\t 132\t330\t67\t89.55\t60\t7\t61"
+            "\t0\t0\t91.04\t3/3\t3\t3\tn/a\tn/a\tn/a\tn/i\tn/i\t1e-33\t 132\t6\t206\t129\t329\n")
+    assert buf.raw[:n].decode() == want
+    # "# Fields:" labels and the unsupported taxonomy columns
+    assert lib.lgpu_tabular_column_label(0).decode().startswith("query id, subject id, % identity")
+    assert lib.lgpu_tabular_column_label(lib.lgpu_tabular_column(b"ppos")).decode() == "% positives"
+    assert lib.lgpu_tabular_column_name(13).decode() == "slen" and lib.lgpu_tabular_column_label(47) is None
+    for name in (b"staxids", b"lcaid", b"lcataxid"):
+        c = lib.lgpu_tabular_column(name)
+        assert c >= 0 and not lib.lgpu_tabular_column_supported(c)
+        one = (C.c_uint32 * 1)(c)
+        assert lib.lgpu_format_tabular(C.byref(p), C.c_void_p(h.ctypes.data), b"Q0", b"S104", one, 1, buf, 4096) < 0
+    # too small a buffer is an error, not a truncated line
+    assert lib.lgpu_format_tabular(C.byref(p), C.c_void_p(h.ctypes.data), b"Q0", b"S104", arr, len(cols), buf, 20) < 0
+
+
 @pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
 def test_compute_fails_loudly_without_gpu(golden_dir):
     with pytest.raises(lambda_b200.LambdaError) as e:

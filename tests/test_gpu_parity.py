@@ -308,6 +308,49 @@ def test_cli_output_is_byte_identical_to_reference(golden_dir, tmp_path, case, d
 @pytest.mark.skipif(not os.path.exists(CLI), reason="bin/lambda3_b200 not built")
 @pytest.mark.parametrize("case,domain", [("prot_flat", 0), ("prot_diverged", 0), ("nucl", 1), ("bisulfite", 2),
                                          ("blastx", 0), ("tblastn", 0), ("tblastx", 0)])
+def test_cli_output_columns_are_byte_identical_to_reference(golden_dir, tmp_path, case, domain):
+    """--output-columns (src/search_options.hpp:224-232,710-760; SQ/blast/blast_tabular_out.h:248-560): custom
+    column list incl. frames, % positives, unimplemented (n/i) and accession (n/a) columns, with .m9 comment lines"""
+    from golden.make_golden_columns import COLUMNS
+    cmd = [CLI, ("searchp", "searchn", "searchbs")[domain], "-q", "q.fasta", "-i", "db.lba", "-o", str(tmp_path / "cols.m9"),
+           "-t", "1", "--version-to-outputfile", "0", "-v", "0", "--output-columns", COLUMNS]
+    subprocess.run(cmd, check=True, capture_output=True, text=True, cwd=os.path.join(golden_dir, case))
+    assert open(tmp_path / "cols.m9").read() == open(os.path.join(golden_dir, case, "cols.m9")).read()
+    # unknown specifiers and the taxonomy columns are refused
+    for bad in ("qseqid nonsense", "std staxids"):
+        r = subprocess.run(cmd[:-1] + [bad, "-o", str(tmp_path / "bad.m8")], capture_output=True, text=True,
+                           cwd=os.path.join(golden_dir, case))
+        assert r.returncode != 0 and not os.path.exists(tmp_path / "bad.m8")
+
+
+@pytest.mark.skipif(not os.path.exists(CLI), reason="bin/lambda3_b200 not built")
+@pytest.mark.parametrize("case,domain", [("prot_flat", 0), ("nucl", 1), ("blastx", 0)])
+@pytest.mark.parametrize("ext", ["fastq", "fq.gz", "fa.gz"])
+def test_cli_reads_fastq_and_gzip_queries(golden_dir, tmp_path, case, domain, ext):
+    """the reference reads its queries through bio::io (FASTA / FASTQ, transparently decompressed;
+    src/search_algo.hpp:342-348) and `lambda3 searchp -q q.fastq.gz` reproduces the golden .m8 (checked when the
+    reader was written); so must the host program"""
+    import gzip
+    ids, data, offs = lambda_b200.read_queries(os.path.join(golden_dir, case, "q.fasta"))
+    seqs = [bytes(data[int(offs[i]):int(offs[i + 1])]).decode() for i in range(len(ids))]
+    if ext.startswith("f") and "q" in ext.split(".")[0]:
+        text = "".join(f"@{i}\n{s}\n+\n{'I' * len(s)}\n" for i, s in zip(ids, seqs))
+    else:
+        text = "".join(f">{i}\n{s}\n" for i, s in zip(ids, seqs))
+    qf = tmp_path / ("q." + ext)
+    with (gzip.open(qf, "wt") if ext.endswith(".gz") else open(qf, "w")) as f:
+        f.write(text)
+    out = tmp_path / "out.m8"
+    cmd = [CLI, ("searchp", "searchn", "searchbs")[domain], "-q", str(qf), "-i", os.path.join(golden_dir, case, "db.lba"),
+           "-o", str(out), "-t", "1", "--version-to-outputfile", "0", "-v", "0"]
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    ref, _ = load_golden(golden_dir, case, "none")
+    assert open(out).read() == "".join(ref)
+
+
+@pytest.mark.skipif(not os.path.exists(CLI), reason="bin/lambda3_b200 not built")
+@pytest.mark.parametrize("case,domain", [("prot_flat", 0), ("prot_diverged", 0), ("nucl", 1), ("bisulfite", 2),
+                                         ("blastx", 0), ("tblastn", 0), ("tblastx", 0)])
 def test_cli_m9_is_byte_identical_to_reference(golden_dir, case, domain):
     """.m9 = tabular with comment lines: program tag of all six BLAST modes, records only for queries with
     matches, footer with the record count; with and without the version string"""
