@@ -306,6 +306,9 @@ def main():
     ap.add_argument("--qlen", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries for the CPU baseline (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--band", type=int, default=0,
+                    help="lgpu_params.window_band: 0 = the reference's rule floor(sqrt(qlen))+1 (parity mode); 16/32/64 = the "
+                         "band sweep of BASELINE configs[3] (non-parity: the reference binary has no such option)")
     args = ap.parse_args()
     wl = args.workload
     W = WORKLOADS[wl]
@@ -324,7 +327,8 @@ def main():
                 f"default profile")
     cfg = {"workload": workload, "queries_per_gpu": args.n_queries, "query_len": args.qlen, "index_seqs": args.n_seqs,
            "profile": "none", "sharding": f"queries x{n_gpus}, index replicated", "streams_per_gpu": 3,
-           "l2_policy": "inputs larger than L2 (index and per-step trace/DP working sets are GBs)"}
+           "l2_policy": "inputs larger than L2 (index and per-step trace/DP working sets are GBs)",
+           "window_band": args.band if args.band else "reference rule floor(sqrt(qlen))+1"}
     cores = os.cpu_count() or 1
 
     if args.impl == "reference":
@@ -365,8 +369,9 @@ def main():
     t0 = time.time()
     ix = lambda_b200.Index.load(os.path.join(d, "db.lba"), device=local_rank, keep_ids=(rank == 0))
     log(f"rank {rank}: index in HBM: {ix.device_bytes / 1e9:.2f} GB, load {time.time() - t0:.1f}s")
-    s = lambda_b200.Searcher(ix, W["domain"])              # default: 3 sub-batches in flight
-    s_serial = lambda_b200.Searcher(ix, W["domain"], streams=1)  # strictly serial: per-kernel timing / roofline
+    kw = {"window_band": args.band} if args.band else {}
+    s = lambda_b200.Searcher(ix, W["domain"], **kw)              # default: 3 sub-batches in flight
+    s_serial = lambda_b200.Searcher(ix, W["domain"], streams=1, **kw)  # strictly serial: per-kernel timing / roofline
     q_ascii, qoffs = make_queries(wl, d, args.n_queries, args.qlen, seed=1000 + rank)
     res = lambda_b200.encode(q_ascii, W["dom"])
     h_res = torch.from_numpy(res).pin_memory()
@@ -517,7 +522,9 @@ def main():
            "gpu_launches": int(st_pipe["kernel_launches"]), "kernels_ncu": other}
 
     # CPU baseline: the unmodified reference on this box's host cores, bounded sample of the same queries
-    if not args.no_cpu_baseline and n_gpus == 1 and os.path.exists(REF):
+    if args.band:
+        out["parity_sample"] = None  # non-parity mode: the reference cannot run with another band
+    elif not args.no_cpu_baseline and n_gpus == 1 and os.path.exists(REF):
         n_sample = args.cpu_sample or min(args.n_queries, max(2000, 2000 * cores))
         qps, wall, phase, ref_lines = run_reference_search(wl, d, q_ascii, qoffs, n_sample, cores, "cpu")
         out["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "reference",

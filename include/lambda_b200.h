@@ -154,6 +154,14 @@ typedef struct
                                            LGPU_ALPH_AMINO_ACID = protein query (BLASTP / TBLASTN) */
     uint32_t         want_cigar;        /* 1: also return the gapped rows of every hit as run-length
                                            operations (needed for SAM / pairwise output)          */
+    uint32_t         window_band;       /* 0: the reference's rule, band = floor(sqrt(query length)) + 1
+                                           (_bandSize, src/search_misc.hpp:46-50); > 0: that many subject
+                                           residues on either side of the seed diagonal's window instead
+                                           (src/search_algo.hpp:929-937).  The DP over the window stays
+                                           unbanded as in the reference (:1102).  Any value other than 0
+                                           leaves parity with the reference binary (it has no such
+                                           option); the oracle restates it for the band sweep of
+                                           BASELINE configs[3].                                   */
 } lgpu_params;
 
 int lgpu_params_default(lgpu_params * out, uint32_t domain, char const * profile);

@@ -15,7 +15,7 @@ class Params(C.Structure):
                 ("scoring_method", C.c_int32), ("gap_open", C.c_int32), ("gap_extend", C.c_int32),
                 ("match", C.c_int32), ("mismatch", C.c_int32), ("min_bit_score", C.c_int32),
                 ("max_evalue", C.c_double), ("id_cutoff", C.c_int32), ("finalize", C.c_uint32),
-                ("query_alph", C.c_uint32), ("want_cigar", C.c_uint32)]
+                ("query_alph", C.c_uint32), ("want_cigar", C.c_uint32), ("window_band", C.c_uint32)]
 
 
 class IndexDesc(C.Structure):

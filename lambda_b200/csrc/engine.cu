@@ -709,7 +709,7 @@ static uint64_t runMerge(lgpu_ctx & c, lgpu_match const * dIn, uint64_t n, lgpu_
     c.dHead.reserve(n);
     c.dScan.reserve(n);
     unsigned int const g = gridFor(n, 256);
-    widenKernel<<<g, 256, 0, c.stream>>>(dIn, n, c.Q, c.index->dev, c.dKey1.p, c.dKey2.p);
+    widenKernel<<<g, 256, 0, c.stream>>>(dIn, n, c.Q, c.index->dev, c.params.window_band, c.dKey1.p, c.dKey2.p);
     iotaKernel<<<g, 256, 0, c.stream>>>(c.dPerm.p, n);
     // LSD: stable sort by the minor key (window start/end), then by the major key (qry, subj)
     size_t tmp1 = 0, tmp2 = 0, tmp3 = 0;

@@ -47,7 +47,7 @@ __device__ __forceinline__ unsigned int isqrtFloor(unsigned int x)
 
 // key1 = (qryId << 32) | subjId ; key2 = (subjStart << 32) | subjEnd   (qryStart/qryEnd are constant
 // per qryId after widening, so the reference's 6-field lexicographic order reduces to these two keys)
-__global__ void widenKernel(lgpu_match const * in, unsigned long long n, DevQueries Q, DevIndex ix,
+__global__ void widenKernel(lgpu_match const * in, unsigned long long n, DevQueries Q, DevIndex ix, unsigned int windowBand,
                             unsigned long long * key1, unsigned long long * key2)
 {
     unsigned long long const t = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
@@ -59,7 +59,9 @@ __global__ void widenKernel(lgpu_match const * in, unsigned long long n, DevQuer
     unsigned long long const qLen = qryFrameLen(Q, static_cast<unsigned int>(Q.offs[q + 1] - Q.offs[q]), m.qry_id % Q.F);
     unsigned long long const sLen = sbjLength(ix, m.subj_id);
     unsigned long long const s0   = (m.subj_start < m.qry_start) ? 0ull : static_cast<unsigned long long>(m.subj_start) - m.qry_start;
-    unsigned long long const band = static_cast<unsigned long long>(isqrtFloor(static_cast<unsigned int>(qLen))) + 1ull;
+    // _bandSize (src/search_misc.hpp:46-50) unless lgpu_params.window_band overrides it
+    unsigned long long const band = windowBand ? static_cast<unsigned long long>(windowBand)
+                                               : static_cast<unsigned long long>(isqrtFloor(static_cast<unsigned int>(qLen))) + 1ull;
     unsigned long long       e    = s0 + qLen + band;
     if (e > sLen)
         e = sLen;

@@ -80,6 +80,8 @@ void usage()
               "      --score-match / --score-mismatch (searchn)\n"
               "  -t, --threads          accepted for compatibility (affects record order only)\n"
               "      --gpus N           shard the queries over N GPUs (default 1)\n"
+              "      --window-band N    subject residues added on either side of a seed's window (0 = lambda3's rule\n"
+              "                         floor(sqrt(query length)) + 1; other values leave parity with lambda3)\n"
               "      --block-size N     queries per device batch (default 100000)\n"
               "  -v, --verbosity        0|1|2\n");
 }
@@ -148,6 +150,7 @@ void parse(int argc, char ** argv, Options & o)
         else if (a == "--score-match") o.params.match = std::atoi(need(i));
         else if (a == "--score-mismatch") o.params.mismatch = std::atoi(need(i));
         else if (a == "-t" || a == "--threads") o.threads = std::max(1, std::atoi(need(i)));
+        else if (a == "--window-band") o.params.window_band = static_cast<uint32_t>(std::max(0, std::atoi(need(i))));
         else if (a == "--gpus") o.gpus = std::max(1, std::atoi(need(i)));
         else if (a == "--block-size") o.blockSize = std::max<uint64_t>(1, std::strtoull(need(i), nullptr, 10));
         else if (a == "-v" || a == "--verbosity") o.verbosity = std::atoi(need(i));

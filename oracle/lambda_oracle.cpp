@@ -531,7 +531,8 @@ static void widenAndMerge(Ctx const & c, Queries const & q, std::vector<lgpu_mat
         uint64_t       s0   = (m.subj_start < m.qry_start) ? 0 : m.subj_start - m.qry_start;
         m.qry_start         = 0;
         m.qry_end           = static_cast<uint32_t>(qLen);
-        uint64_t const band = static_cast<uint64_t>(static_cast<int64_t>(std::sqrt(static_cast<double>(qLen))) + 1);
+        uint64_t const band = c.p.window_band ? static_cast<uint64_t>(c.p.window_band) // lgpu_params.window_band (band sweep)
+                                              : static_cast<uint64_t>(static_cast<int64_t>(std::sqrt(static_cast<double>(qLen))) + 1);
         m.subj_end          = static_cast<uint32_t>(std::min<uint64_t>(s0 + qLen + band, sLen));
         m.subj_start        = static_cast<uint32_t>((band < s0) ? s0 - band : 0);
     }

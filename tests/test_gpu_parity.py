@@ -482,3 +482,30 @@ def test_multi_stream_split_is_invisible(golden_dir, monkeypatch):
             assert (cur[0] == ref[0]).all() and cur[1] == ref[1]
         s.close()
     ix.close()
+
+
+@pytest.mark.parametrize("band", [16, 64])
+@pytest.mark.parametrize("case,domain", [("prot_flat", 0), ("prot_family", 0), ("nucl", 1)])
+def test_window_band_override_matches_oracle(golden_dir, case, domain, band):
+    """lgpu_params.window_band (band sweep of BASELINE configs[3]; non-parity with the reference binary, which has
+    no such option): windows, hit records and funnel counters equal the oracle's with the same override"""
+    path, ids, res, offs = _load(golden_dir, case, domain)
+    ix = lambda_b200.Index.load(path)
+    o = orc.Oracle(path)
+    s, p = _pair(ix, o, case, domain, "none", window_band=band)
+    for phase in (1, 2):
+        m_cpu, _ = o.seed(p, res, offs, phase)
+        w_gpu, _ = s.merge(res, offs, m_cpu)
+        w_cpu, _ = o.merge(p, res, offs, m_cpu)
+        assert len(w_gpu) == len(w_cpu) and (_sorted(w_gpu) == _sorted(w_cpu)).all(), phase
+    h_gpu, st = s.search(res, offs)
+    h_cpu, st2 = o.search(p, res, offs)
+    assert sorted(s.m8(h_gpu, ids)) == sorted(o.m8(p, h_cpu, ids))
+    for k in FUNNEL:
+        assert int(st[k]) == int(st2[k]), k
+    # and it is not the default: the reference-rule search sees other windows
+    p0 = o.params(domain, "none")
+    w0, _ = o.merge(p0, res, offs, o.seed(p0, res, offs, 1)[0])
+    w1, _ = o.merge(p, res, offs, o.seed(p, res, offs, 1)[0])
+    assert w0.tobytes() != w1.tobytes()
+    s.close(); ix.close(); o.close()

@@ -64,3 +64,43 @@ def test_fm_primitives_against_text(golden_dir):
         Cv = np.ctypeslib.as_array(__import__("ctypes").cast(d.C, __import__("ctypes").POINTER(__import__("ctypes").c_uint64)), (d.sigma + 1,))
         assert lo == Cv[s] and hi == Cv[s + 1]
     o.close()
+
+
+def test_window_band_override(golden_dir):
+    """lgpu_params.window_band (the band sweep of BASELINE configs[3]): 0 keeps the reference's
+    floor(sqrt(query length)) + 1 (_bandSize, src/search_misc.hpp:46-50) -- asked for explicitly it must
+    reproduce the default; any other value pads the seed diagonal's window by exactly that many residues
+    (src/search_algo.hpp:929-937) and the whole path stays consistent (more band -> the same or more cells)."""
+    from lambda_b200._abi import MATCH_DT
+    o = orc.Oracle(os.path.join(golden_dir, "prot_flat", "db.lba"))
+    ids, data, offs = orc.read_fasta(os.path.join(golden_dir, "prot_flat", "q.fasta"))
+    res = orc.encode(data, 0)
+    lens = np.diff(offs.astype(np.int64))
+    q = int(np.argmax(lens == lens[0]))  # any query; its length decides the default band
+    qlen = int(lens[q])
+    m = np.zeros(1, MATCH_DT)
+    m["qry_id"], m["subj_id"], m["qry_start"], m["qry_end"], m["subj_start"], m["subj_end"] = q, 3, 10, 20, 200, 210
+    p = o.params(0)
+    w_def, _ = o.merge(p, res, offs, m)
+    p.window_band = int(np.floor(np.sqrt(qlen))) + 1
+    w_same, _ = o.merge(p, res, offs, m)
+    assert w_def.tobytes() == w_same.tobytes()
+    for band in (16, 32, 64):
+        p.window_band = band
+        w, _ = o.merge(p, res, offs, m)
+        assert int(w["subj_start"][0]) == 190 - band and int(w["qry_end"][0]) == qlen
+        assert int(w["subj_end"][0]) == 190 + qlen + band  # subject 3 is longer than that in this fixture
+    # whole path: hits of the default band are reproduced with the explicit band on a same-length query subset
+    same = np.nonzero(lens == qlen)[0][:8]
+    sub_offs = np.zeros(len(same) + 1, np.uint64)
+    sub = []
+    for k, i in enumerate(same):
+        sub.append(res[int(offs[i]):int(offs[i + 1])])
+        sub_offs[k + 1] = sub_offs[k] + np.uint64(len(sub[-1]))
+    sub = np.concatenate(sub)
+    p = o.params(0)
+    h0, st0 = o.search(p, sub, sub_offs)
+    p.window_band = int(np.floor(np.sqrt(qlen))) + 1
+    h1, st1 = o.search(p, sub, sub_offs)
+    assert h0.tobytes() == h1.tobytes() and len(h0) > 0
+    o.close()
