@@ -580,17 +580,20 @@ static void uploadQueries(lgpu_ctx & c, BatchView const & qb, lgpu_stats * st)
             break;
         case LGPU_ALPH_DNA4:
         {
-            // dna5 (A,C,G,N,T) -> dna4 (A,C,G,T).  The reference replaces N by a pseudo-random base whose
-            // value depends on its internal access pattern; we map N to A.
-            unsigned char const t[5] = {0, 1, 2, 0, 3};
+            // dna5 (A,C,G,N,T) -> dna4 (A,C,G,T).  The reference replaces every READ of an N by the next output of a
+            // per-view random generator: N is stored as a marker and resolved by the seeding
+            // kernels exactly like that (n_random.hpp, seedSym / elongSym).
+            unsigned char const t[5] = {0, 1, 2, static_cast<unsigned char>(kNMarker), 3};
             std::memcpy(Q.redTab[0], t, 5);
             break;
         }
         case LGPU_ALPH_DNA3BS:
         {
-            // dna5 -> dna4 (N -> A, as above) -> bisulfite semialphabet: forward (C->T) ranks {A0,C1,G2,T1} for
-            // even frames, reverse (G->A) ranks {A3,C4,G3,T5} for odd frames (src/view_reduce_to_bisulfite.hpp:51-52)
-            unsigned char const fwd[5] = {0, 1, 2, 0, 1}, rev[5] = {3, 4, 3, 3, 5};
+            // dna5 -> dna4 (N -> marker | direction, as above) -> bisulfite semialphabet: forward (C->T) ranks
+            // {A0,C1,G2,T1} for even frames, reverse (G->A) ranks {A3,C4,G3,T5} for odd frames
+            // (src/view_reduce_to_bisulfite.hpp:51-52)
+            unsigned char const fwd[5] = {0, 1, 2, static_cast<unsigned char>(kNMarker), 1},
+                                rev[5] = {3, 4, 3, static_cast<unsigned char>(kNMarker | 1u), 5};
             std::memcpy(Q.redTab[0], fwd, 5);
             std::memcpy(Q.redTab[1], rev, 5);
             break;

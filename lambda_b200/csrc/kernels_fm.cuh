@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/lambda_b200.h"
+#include "n_random.hpp"
 
 namespace lgpu
 {
@@ -256,6 +257,20 @@ __device__ __forceinline__ void setFrames(DevQueries const & Q, DevIndex const &
     sFrame = static_cast<signed char>(sf);
 }
 
+// Reduced query symbol of a seed search / of an elongation step.  An 'N' of a nucleotide query is stored as
+// kNMarker | (frame & 1) and resolved like the reference's views::dna_n_to_random does (n_random.hpp): inside a
+// seed by the number of 'N's in front of it in that seed, in an elongation step always to the first random rank.
+__device__ __forceinline__ unsigned int seedSym(unsigned char const * red, unsigned int seedBegin, unsigned int p, bool bisulfite)
+{
+    unsigned int const s = red[p];
+    return s < kNMarker ? s : redSymbol(red, seedBegin, p, bisulfite);
+}
+__device__ __forceinline__ unsigned int elongSym(unsigned char const * red, unsigned int p, bool bisulfite)
+{
+    unsigned int const s = red[p];
+    return s < kNMarker ? s : redSymbol(red, p, p, bisulfite);
+}
+
 __global__ void prepQueriesKernel(DevQueries Q)
 {
     // one block per query keeps the index math trivial; residues are strided over the block
@@ -411,7 +426,7 @@ __global__ void __launch_bounds__(128) seedKernel(SeedParams P)
                     bool ok = true;
                     for (unsigned int i = 0; i < h1; ++i)
                     {
-                        c = fmExtendRight(ix, c, red[seedBegin + i] + 1u);
+                        c = fmExtendRight(ix, c, seedSym(red, seedBegin, seedBegin + i, ix.bsMode != 0) + 1u);
                         if (c.len == 0)
                         {
                             ok = false;
@@ -424,7 +439,7 @@ __global__ void __launch_bounds__(128) seedKernel(SeedParams P)
                         K    = 0;
                         for (unsigned int i = 0; i < n2; ++i)
                         {
-                            c = fmExtendRight(ix, c, red[seedBegin + h1 + i] + 1u);
+                            c = fmExtendRight(ix, c, seedSym(red, seedBegin, seedBegin + h1 + i, ix.bsMode != 0) + 1u);
                             if (c.len == 0)
                                 break;
                             E[i + 1] = c;
@@ -454,7 +469,7 @@ __global__ void __launch_bounds__(128) seedKernel(SeedParams P)
                                 stage = 1;
                                 continue;
                             }
-                            unsigned int const want = red[seedBegin + h1 + lvl];
+                            unsigned int const want = seedSym(red, seedBegin, seedBegin + h1 + lvl, ix.bsMode != 0);
                             if (r >= want)
                             {
                                 ++lvl;
@@ -466,7 +481,7 @@ __global__ void __launch_bounds__(128) seedKernel(SeedParams P)
                         {
                             stage = 2;
                             lvl   = kMax;
-                            r     = (lvl >= 0) ? red[seedBegin + h1 + lvl] + 1u : 0u;
+                            r     = (lvl >= 0) ? seedSym(red, seedBegin, seedBegin + h1 + lvl, ix.bsMode != 0) + 1u : 0u;
                             if (K == static_cast<int>(n2))
                             {
                                 cursor = E[n2];
@@ -481,7 +496,7 @@ __global__ void __launch_bounds__(128) seedKernel(SeedParams P)
                             if (r >= redN)
                             {
                                 --lvl;
-                                r = (lvl >= 0) ? red[seedBegin + h1 + lvl] + 1u : 0u;
+                                r = (lvl >= 0) ? seedSym(red, seedBegin, seedBegin + h1 + lvl, ix.bsMode != 0) + 1u : 0u;
                                 continue;
                             }
                         }
@@ -489,7 +504,7 @@ __global__ void __launch_bounds__(128) seedKernel(SeedParams P)
                         Cursor c = fmExtendRight(ix, E[lvl], r + 1u);
                         ++r;
                         for (unsigned int l = lvl + 1; c.len != 0 && l < n2; ++l)
-                            c = fmExtendRight(ix, c, red[seedBegin + h1 + l] + 1u);
+                            c = fmExtendRight(ix, c, seedSym(red, seedBegin, seedBegin + h1 + l, ix.bsMode != 0) + 1u);
                         if (c.len != 0)
                         {
                             cursor = c;
@@ -516,7 +531,7 @@ __global__ void __launch_bounds__(128) seedKernel(SeedParams P)
                         unsigned long long oldCount = cursor.len;
                         while (seedBegin + seedLen < len)
                         {
-                            Cursor const n = fmExtendRight(ix, cursor, red[seedBegin + seedLen] + 1u);
+                            Cursor const n = fmExtendRight(ix, cursor, elongSym(red, seedBegin + seedLen, ix.bsMode != 0) + 1u);
                             if (n.len < desired && n.len < oldCount)
                                 break; // keep the previous cursor
                             cursor   = n;
@@ -626,7 +641,7 @@ __device__ __forceinline__ int seedExactChain(DevIndex const & ix, unsigned char
     c.len = ix.nRows;
     for (unsigned int i = 0; i < h1; ++i)
     {
-        c = fmExtendRight(ix, c, red[seedBegin + i] + 1u);
+        c = fmExtendRight(ix, c, seedSym(red, seedBegin, seedBegin + i, ix.bsMode != 0) + 1u);
         if (c.len == 0)
             return -1;
     }
@@ -634,7 +649,7 @@ __device__ __forceinline__ int seedExactChain(DevIndex const & ix, unsigned char
     int K = 0;
     for (unsigned int i = 0; i < n2; ++i)
     {
-        c = fmExtendRight(ix, c, red[seedBegin + h1 + i] + 1u);
+        c = fmExtendRight(ix, c, seedSym(red, seedBegin, seedBegin + h1 + i, ix.bsMode != 0) + 1u);
         if (c.len == 0)
             break;
         E[i + 1] = c;
@@ -666,7 +681,7 @@ __device__ __forceinline__ Cursor seedLeaf(DevIndex const & ix, Cursor const * E
         {
             lvl                     = static_cast<int>(i / per);
             unsigned int const k    = i % per;
-            unsigned int const want = red[seedBegin + h1 + lvl];
+            unsigned int const want = seedSym(red, seedBegin, seedBegin + h1 + lvl, ix.bsMode != 0);
             r                       = k < want ? k : k + 1;
         }
         else if (hasExact)
@@ -675,7 +690,7 @@ __device__ __forceinline__ Cursor seedLeaf(DevIndex const & ix, Cursor const * E
     else
     for (int l = 0; l <= kMax; ++l)
     {
-        unsigned int const want = red[seedBegin + h1 + l];
+        unsigned int const want = seedSym(red, seedBegin, seedBegin + h1 + l, ix.bsMode != 0);
         if (i < want)
         {
             lvl = l;
@@ -694,7 +709,7 @@ __device__ __forceinline__ Cursor seedLeaf(DevIndex const & ix, Cursor const * E
     if (!levelOrder && lvl < 0 && !exact)
         for (int l = kMax; l >= 0; --l)
         {
-            unsigned int const want = red[seedBegin + h1 + l];
+            unsigned int const want = seedSym(red, seedBegin, seedBegin + h1 + l, ix.bsMode != 0);
             unsigned int const cnt  = redN - 1 - want;
             if (i < cnt)
             {
@@ -710,7 +725,7 @@ __device__ __forceinline__ Cursor seedLeaf(DevIndex const & ix, Cursor const * E
     {
         Cursor c = fmExtendRight(ix, E[lvl], r + 1u);
         for (unsigned int l = lvl + 1; c.len != 0 && l < n2; ++l)
-            c = fmExtendRight(ix, c, red[seedBegin + h1 + l] + 1u);
+            c = fmExtendRight(ix, c, seedSym(red, seedBegin, seedBegin + h1 + l, ix.bsMode != 0) + 1u);
         mine = c;
     }
     return mine;
@@ -853,7 +868,7 @@ __device__ __forceinline__ void seedConsumeCursor(SeedParams const & P, signed c
         unsigned long long       oldCount = cursor.len;
         while (seedBegin + seedLen < len)
         {
-            Cursor const n = fmExtendRight(ix, cursor, red[seedBegin + seedLen] + 1u);
+            Cursor const n = fmExtendRight(ix, cursor, elongSym(red, seedBegin + seedLen, ix.bsMode != 0) + 1u);
             if (n.len < desired && n.len < oldCount)
                 break;
             cursor   = n;
@@ -945,7 +960,7 @@ __device__ __forceinline__ void seedConsumeChunkSpec(SeedParams const & P, signe
                     unsigned long long oldCount = el.len;
                     while (seedBegin + elLen < len)
                     {
-                        Cursor const n = fmExtendRight(ix, el, red[seedBegin + elLen] + 1u);
+                        Cursor const n = fmExtendRight(ix, el, elongSym(red, seedBegin + elLen, ix.bsMode != 0) + 1u);
                         if (n.len < oldCount)
                         {
                             if (n.len < desired)
@@ -1278,7 +1293,7 @@ __global__ void __launch_bounds__(32 * kSpecWarps) seedSpecKernel(SeedParams P)
                     {
                         c.len = ix.nRows;
                         for (unsigned int i = 0; i < L && c.len != 0; ++i)
-                            c = fmExtendRight(ix, c, red[mySeed + i] + 1u);
+                            c = fmExtendRight(ix, c, seedSym(red, mySeed, mySeed + i, ix.bsMode != 0) + 1u);
                     }
                     else
                         mySeed = 0;

@@ -43,6 +43,7 @@
 
 #include "../lambda_b200/csrc/host_finalize.hpp"
 #include "../lambda_b200/csrc/host_params.hpp"
+#include "../lambda_b200/csrc/n_random.hpp"
 #include "../lambda_b200/csrc/lba_index.hpp"
 
 namespace orc
@@ -213,7 +214,7 @@ static uint8_t const * reductionTable(uint32_t redAlph)
 {
     static uint8_t const identity27[27] = {0,  1,  2,  3,  4,  5,  6,  7,  8,  9,  10, 11, 12, 13,
                                            14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26};
-    static uint8_t const dna5to4[5]     = {0, 1, 2, 0, 3}; // N would be randomised by the reference (App. G)
+    static uint8_t const dna5to4[5]     = {0, 1, 2, 0, 3}; // N: replaced by the marker in makeQueries (n_random.hpp)
     switch (redAlph)
     {
         case LGPU_ALPH_LI10: return lgpu::kAa27ToLi10;
@@ -254,10 +255,14 @@ static Queries makeQueries(DomainInfo const & di, uint32_t redAlph, uint8_t cons
                 for (uint64_t k = 0; k < len; ++k)
                     frame.push_back(!revComp ? res[offs[i] + k] : lgpu::kDna5Complement[res[offs[i] + len - 1 - k]]);
             }
+            bool const nucl = redAlph == LGPU_ALPH_DNA4 || bs; // views::dna_n_to_random sits in these reduced views only
             for (uint8_t r : frame)
             {
                 q.trans.push_back(r);
-                q.red.push_back(bs ? bsTab[f % 2][red[r]] : red[r]);
+                if (nucl && r == 3) // dna5 'N': randomised per read of the view (n_random.hpp)
+                    q.red.push_back(static_cast<uint8_t>(lgpu::kNMarker | (f & 1u)));
+                else
+                    q.red.push_back(bs ? bsTab[f % 2][red[r]] : red[r]);
             }
             q.offs.push_back(q.trans.size());
         }
@@ -326,11 +331,28 @@ static bool seedLooksPromising(Ctx const & c, Queries const & q, lgpu_search_opt
 }
 
 // all cursors for one seed, in the reference's production order
-static void seedCursors(Ctx const & c, lgpu_search_opts const & so, uint8_t const * redSeed, std::vector<Cursor> & out)
+static void seedCursors(Ctx const & c, lgpu_search_opts const & so, uint8_t const * redSeedRaw, std::vector<Cursor> & out)
 {
     lgpu_index_desc const & d = c.idx->d;
     out.clear();
     Cursor const root{0, d.C[d.sigma], 0};
+    // One instance of views::dna_n_to_random serves this whole seed search: every READ of an 'N' takes the next
+    // random rank (n_random.hpp).  `redSeed` below restates exactly the reads the reference makes, in its order.
+    bool const   bs     = d.red_alph == LGPU_ALPH_DNA3BS;
+    unsigned int nReads = 0;
+    struct SeedReads
+    {
+        uint8_t const * raw;
+        bool            bs;
+        unsigned int *  nReads;
+        uint8_t operator[](uint32_t i) const
+        {
+            uint8_t const s = raw[i];
+            if (s < lgpu::kNMarker)
+                return s;
+            return static_cast<uint8_t>(lgpu::nReducedRank(lgpu::nRandomRank((*nReads)++), bs, s & 1u));
+        }
+    } const redSeed{redSeedRaw, bs, &nReads};
     if (!(c.p.seed_half_exact && so.max_seed_dist != 0))
     {
         // search_impl -> search_backtracking_with_buffers (src/search_algo.hpp:484-494,
@@ -465,7 +487,9 @@ static void seedQueries(Ctx const & c, Queries const & q, lgpu_search_opts const
                     uint64_t oldCount  = cursor.len;
                     while (seedBegin + seedLength < len)
                     {
-                        cursor                  = extendRight(d, cursor, red[seedBegin + seedLength] + 1u);
+                        // a fresh view instance per read: an 'N' here is always the first random rank
+                        cursor = extendRight(d, cursor, lgpu::redSymbol(red, seedBegin + seedLength, seedBegin + seedLength,
+                                                                        d.red_alph == LGPU_ALPH_DNA3BS) + 1u);
                         uint64_t const newCount = cursor.len;
                         if (newCount < desiredOccs && newCount < oldCount)
                         {

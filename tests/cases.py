@@ -36,3 +36,9 @@ def load_golden(gdir, case, profile):
     with open(os.path.join(gdir, case, profile + ".funnel.json")) as f:
         funnel = json.load(f)
     return lines, funnel
+
+
+# queries containing 'N' (tests/golden/make_golden_n.py): <case>/qn.fasta, n.<profile>.m8, n.<profile>.funnel.json
+N_CASES = [("nucl", 1, ["none", "fast", "sensitive"]), ("bisulfite", 2, ["none", "fast", "sensitive"]),
+           ("blastx", 0, ["none"])]
+N_CASE_PROFILES = [(c, d, p) for c, d, ps in N_CASES for p in ps]

@@ -8,7 +8,7 @@ import pytest
 
 import lambda_b200
 import orc
-from cases import CASE_PROFILES, CASES, FUNNEL, load_golden, query_alph, query_encoding
+from cases import CASE_PROFILES, CASES, FUNNEL, N_CASE_PROFILES, load_golden, query_alph, query_encoding
 from lambda_b200 import synth
 from lambda_b200._abi import MATCH_DT
 
@@ -508,4 +508,33 @@ def test_window_band_override_matches_oracle(golden_dir, case, domain, band):
     w0, _ = o.merge(p0, res, offs, o.seed(p0, res, offs, 1)[0])
     w1, _ = o.merge(p, res, offs, o.seed(p, res, offs, 1)[0])
     assert w0.tobytes() != w1.tobytes()
+    s.close(); ix.close(); o.close()
+
+
+@pytest.mark.parametrize("mode", ["auto", "thread", "warp", "block", "spec"])
+@pytest.mark.parametrize("case,domain,profile", N_CASE_PROFILES)
+def test_queries_with_n_reproduce_reference(golden_dir, case, domain, profile, mode, monkeypatch):
+    """'N' in nucleotide queries (lambda_b200/csrc/n_random.hpp): every seeding kernel resolves the
+    'N's like the reference's views::dna_n_to_random; seeds (both phases) equal the oracle's and the whole search
+    reproduces the reference's golden output and funnel"""
+    if mode != "auto":
+        monkeypatch.setenv("LAMBDA_B200_SEED", mode)
+    path = os.path.join(golden_dir, case, "db.lba")
+    ids, data, offs = lambda_b200.read_queries(os.path.join(golden_dir, case, "qn.fasta"))
+    res = lambda_b200.encode(data, query_encoding(case, domain))
+    o = orc.Oracle(path)
+    ix = lambda_b200.Index.load(path)
+    s, p = _pair(ix, o, case, domain, profile)
+    for phase in (1, 2):
+        m_gpu, st_gpu = s.seed(res, offs, phase)
+        m_cpu, st_cpu = o.seed(p, res, offs, phase)
+        assert len(m_gpu) == len(m_cpu) and (_sorted(m_gpu) == _sorted(m_cpu)).all(), phase
+        for k in ("hits_after_seeding", "hits_failed_pre_extend"):
+            assert int(st_gpu[k]) == int(st_cpu[k]), k
+    if mode != "block":  # the block-per-query kernel is a phase-2 tool for small active sets
+        hits, st = s.search(res, offs)
+        ref, funnel = load_golden(golden_dir, case, "n." + profile)
+        assert sorted(s.m8(hits, ids)) == sorted(ref)
+        for k in FUNNEL:
+            assert int(st[k]) == funnel[k], k
     s.close(); ix.close(); o.close()

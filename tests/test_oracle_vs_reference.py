@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import orc
-from cases import CASE_PROFILES, FUNNEL, load_golden, query_alph, query_encoding
+from cases import CASE_PROFILES, FUNNEL, N_CASE_PROFILES, load_golden, query_alph, query_encoding
 
 
 @pytest.mark.parametrize("case,domain,profile", CASE_PROFILES)
@@ -104,3 +104,33 @@ def test_window_band_override(golden_dir):
     h1, st1 = o.search(p, sub, sub_offs)
     assert h0.tobytes() == h1.tobytes() and len(h0) > 0
     o.close()
+
+
+@pytest.mark.parametrize("case,domain,profile", N_CASE_PROFILES)
+def test_oracle_reproduces_reference_with_n_in_queries(golden_dir, case, domain, profile):
+    """'N' in nucleotide queries: during seeding the reference replaces every READ of an 'N' by the next output of
+    a per-view std::mt19937{0xDEADBEEF} (src/view_dna_n_to_random.hpp, SURVEY App. G); restated in
+    lambda_b200/csrc/n_random.hpp.  4 % 'N's + runs of 'N's; lines and every funnel counter must match."""
+    o = orc.Oracle(os.path.join(golden_dir, case, "db.lba"))
+    ids, data, offs = orc.read_fasta(os.path.join(golden_dir, case, "qn.fasta"))
+    assert (data == ord("N")).sum() > 100
+    res = orc.encode(data, query_encoding(case, domain))
+    p = o.params(domain, profile)
+    p.query_alph = query_alph(case)
+    hits, st = o.search(p, res, offs)
+    ref, funnel = load_golden(golden_dir, case, "n." + profile)
+    assert sorted(o.m8(p, hits, ids)) == sorted(ref)
+    for k in FUNNEL:
+        assert int(st[k]) == funnel[k], k
+    o.close()
+
+
+def test_n_random_sequence_is_mt19937():
+    """the packed table of n_random.hpp against a Mersenne twister seeded like the reference's view
+    (numpy's RandomState seeds MT19937 with init_genrand like std::mt19937{seed})"""
+    import ctypes as C
+    rs = np.random.RandomState(0xDEADBEEF)
+    want = [int(x) % 4 for x in rs.randint(0, 2**32, size=64, dtype=np.uint64)]
+    lo, hi = 0xa3736c5835666461, 0xf83739b5e56c0330
+    got = [((lo if k < 32 else hi) >> (2 * (k & 31))) & 3 for k in range(64)]
+    assert got == want
