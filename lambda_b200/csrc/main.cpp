@@ -39,6 +39,7 @@ struct Options
     int         threads   = 1; // only used for the reference's records_per_batch formula
     int         gpus      = 1;
     bool        comments  = false; // .m9: BLAST tabular with comment lines
+    std::string replayHits;            // --replay-hits FILE: format records computed elsewhere (test hook, no search)
     std::string outputColumns = "std"; // --output-columns (.m8 / .m9)
     std::vector<uint32_t> columns;     // ... resolved to BlastMatchField indices
     bool        report    = false; // .m0: BLAST pairwise report
@@ -129,6 +130,7 @@ void parse(int argc, char ** argv, Options & o)
         else if (a == "-p" || a == "--profile") need(i);
         else if (a == "-a" || a == "--input-alphabet") o.inputAlphabet = need(i);
         else if (a == "--output-columns") o.outputColumns = need(i);
+        else if (a == "--replay-hits") o.replayHits = need(i);
         else if (a == "-e" || a == "--e-value") o.params.max_evalue = std::atof(need(i));
         else if (a == "--bit-score") o.params.min_bit_score = std::atoi(need(i));
         else if (a == "--percent-identity") o.params.id_cutoff = std::atoi(need(i));
@@ -458,11 +460,41 @@ static int run(int argc, char ** argv)
         std::printf("Index mapped in %.3fs (%llu subjects), %llu queries read in %.3fs\n", t1 - t0,
                     static_cast<unsigned long long>(desc->n_seqs), static_cast<unsigned long long>(nQ), t2 - t1);
 
-    int const                nShards = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(o.gpus), std::max<uint64_t>(nQ, 1)));
+    int const                nShards = o.replayHits.empty()
+                                         ? static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(o.gpus), std::max<uint64_t>(nQ, 1)))
+                                         : 1;
     std::vector<ShardResult> res(nShards);
+    if (!o.replayHits.empty())
+    {
+        // Test hook: NO search happens here.  The file holds finished records (what lgpu_search_batch returned, or
+        // what the test infrastructure computed) and this program only formats them, so that the five output
+        // writers can be checked against the reference's files on a machine without a GPU.
+        // Layout: "LGPUHITS", u64 n_hits, u64 n_ops, lgpu_stats, n_hits x lgpu_hit, n_ops x u32.
+        FILE * fi = std::fopen(o.replayHits.c_str(), "rb");
+        if (!fi)
+            die("cannot open " + o.replayHits);
+        char     magic[8];
+        uint64_t nHits = 0, nOps = 0;
+        bool     ok    = std::fread(magic, 1, 8, fi) == 8 && !std::memcmp(magic, "LGPUHITS", 8) && std::fread(&nHits, 8, 1, fi) == 1 &&
+                  std::fread(&nOps, 8, 1, fi) == 1 && std::fread(&res[0].stats, sizeof(lgpu_stats), 1, fi) == 1;
+        if (ok)
+        {
+            res[0].hits.resize(nHits);
+            res[0].cigar.resize(nOps);
+            ok = (nHits == 0 || std::fread(res[0].hits.data(), sizeof(lgpu_hit), nHits, fi) == nHits) &&
+                 (nOps == 0 || std::fread(res[0].cigar.data(), 4, nOps, fi) == nOps);
+        }
+        std::fclose(fi);
+        if (!ok)
+            die("malformed hit file " + o.replayHits);
+        for (auto const & h : res[0].hits)
+            if (h.q_id >= nQ || h.s_id >= desc->n_seqs || static_cast<uint64_t>(h.cigar_off) + h.cigar_len > nOps)
+                die("hit file " + o.replayHits + " does not belong to these queries / this index");
+    }
     std::vector<std::thread> th;
-    for (int g = 0; g < nShards; ++g)
-        th.emplace_back(runShard, std::cref(o), desc, g, std::cref(f), nQ * g / nShards, nQ * (g + 1) / nShards, std::ref(res[g]));
+    if (o.replayHits.empty())
+        for (int g = 0; g < nShards; ++g)
+            th.emplace_back(runShard, std::cref(o), desc, g, std::cref(f), nQ * g / nShards, nQ * (g + 1) / nShards, std::ref(res[g]));
     for (auto & t : th)
         t.join();
     lgpu_stats total{};

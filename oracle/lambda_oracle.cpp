@@ -597,6 +597,7 @@ struct DpResult
     uint32_t bi = 0, bj = 0; // end of the alignment (exclusive), query / window
     uint32_t ai = 0, aj = 0; // begin
     uint32_t nMatch = 0, nMismatch = 0, nGapOpen = 0, nGapExt = 0, nPositive = 0, alnLen = 0;
+    std::vector<uint32_t> ops; // run-length operations of the path, traceback order (end first): run << 2 | LGPU_CIGAR_*
 };
 
 // query = columns (outer loop), subject window = rows (inner loop)
@@ -680,6 +681,9 @@ static DpResult alignLocal(Scoring const & sc, int8_t const * M, bool bsStats, u
     auto flush = [&](int kind, uint32_t n) {
         if (n == 0)
             return;
+        // the gapped rows (alignRow0 / alignRow1 of the reference's BlastMatch) as runs: a diagonal run aligns residues,
+        // a horizontal run consumes query residues only (gap in the subject row), a vertical run subject residues only
+        r.ops.push_back((n << 2) | static_cast<uint32_t>(kind == DIAG ? LGPU_CIGAR_M : kind == HORI ? LGPU_CIGAR_I : LGPU_CIGAR_D));
         r.alnLen += n;
         if (kind != DIAG)
         {
@@ -802,7 +806,7 @@ static lgpu_hit makeHit(Ctx const & c, Queries const & q, lgpu_match const & m, 
 
 // iterateMatchesFullSimd for one phase; appends to `hits`
 static void extendMatches(Ctx const & c, Queries const & q, std::vector<lgpu_match> & ms, lgpu::EValueComputer & ev,
-                          uint8_t phase, std::vector<lgpu_hit> & hits, lgpu_stats & st)
+                          uint8_t phase, std::vector<lgpu_hit> & hits, lgpu_stats & st, std::vector<uint32_t> * cigar = nullptr)
 {
     widenAndMerge(c, q, ms, st);
     std::vector<uint8_t> T;
@@ -838,12 +842,18 @@ static void extendMatches(Ctx const & c, Queries const & q, std::vector<lgpu_mat
         // alignStats.alignmentScore is recomputed from the rows by computeAlignmentStats; it equals the DP score
         h.bit_score = lgpu::bitScore(c.sc.ka, h.score);
         h.evalue    = (c.p.max_evalue >= 0) ? evalue : ev.evalue(h.score, qLen);
+        if (cigar && c.p.want_cigar) // lgpu_params.want_cigar: lgpu_hit.cigar_off / cigar_len index the call's run buffer
+        {
+            h.cigar_off = static_cast<uint32_t>(cigar->size());
+            h.cigar_len = static_cast<uint32_t>(r2.ops.size());
+            cigar->insert(cigar->end(), r2.ops.begin(), r2.ops.end());
+        }
         hits.push_back(h);
     }
 }
 
 static int searchAll(Ctx const & c, uint8_t const * res, uint64_t const * offs, uint64_t n, std::vector<lgpu_hit> & hits,
-                     lgpu_stats & st)
+                     lgpu_stats & st, std::vector<uint32_t> * cigar = nullptr)
 {
     Queries              q = makeQueries(c.di, c.idx->d.red_alph, res, offs, n);
     lgpu::EValueComputer ev(c.sc.ka, c.idx->dbTotalLength, c.di.qIsTranslated);
@@ -853,20 +863,20 @@ static int searchAll(Ctx const & c, uint8_t const * res, uint64_t const * offs, 
     if (c.p.iterative_search)
     {
         seedQueries(c, q, c.p.opts0, active, ms, st);
-        extendMatches(c, q, ms, ev, 1, hits, st);
+        extendMatches(c, q, ms, ev, 1, hits, st, cigar);
         for (lgpu_hit const & h : hits)
             active[h.q_id] = 0;
         ms.clear();
         if (std::find(active.begin(), active.end(), 1) != active.end())
         {
             seedQueries(c, q, c.p.opts, active, ms, st);
-            extendMatches(c, q, ms, ev, 2, hits, st);
+            extendMatches(c, q, ms, ev, 2, hits, st, cigar);
         }
     }
     else
     {
         seedQueries(c, q, c.p.opts, active, ms, st);
-        extendMatches(c, q, ms, ev, 2, hits, st);
+        extendMatches(c, q, ms, ev, 2, hits, st, cigar);
     }
     if (c.p.finalize)
         lgpu::finalizeRecords(hits, c.p.max_matches, st);
@@ -887,6 +897,7 @@ struct orc_handle
     orc::Index               idx;
     std::vector<lgpu_match>  matches;
     std::vector<lgpu_hit>    hits;
+    std::vector<uint32_t>    cigar; // run buffer of the last orc_search call (lgpu_params.want_cigar)
     std::string              err;
 };
 
@@ -924,6 +935,13 @@ orc_handle * orc_open(char const * path)
 }
 
 void orc_close(orc_handle * h) { delete h; }
+
+// run buffer of the last orc_search() call made with lgpu_params.want_cigar (see lgpu_hit.cigar_off / cigar_len)
+uint64_t orc_last_cigar(orc_handle * h, uint32_t const ** ops)
+{
+    *ops = h->cigar.data();
+    return h->cigar.size();
+}
 
 lgpu_index_desc const * orc_desc(orc_handle const * h) { return &h->idx.d; }
 
@@ -1003,6 +1021,7 @@ int orc_search(orc_handle * h, lgpu_params const * p, uint8_t const * res, uint6
     if (int rc = makeCtx(c, h, p)) return rc;
     if (threads < 1) threads = 1;
     std::vector<std::vector<lgpu_hit>> parts(threads);
+    std::vector<std::vector<uint32_t>> cigars(threads);
     std::vector<lgpu_stats>            stats(threads);
     std::memset(stats.data(), 0, sizeof(lgpu_stats) * threads);
 #pragma omp parallel for num_threads(threads) schedule(static, 1)
@@ -1013,12 +1032,15 @@ int orc_search(orc_handle * h, lgpu_params const * p, uint8_t const * res, uint6
         std::vector<uint64_t> o(offs + b, offs + e + 1);
         uint64_t const        base = o[0];
         for (auto & x : o) x -= base;
-        orc::searchAll(c, res + base, o.data(), e - b, parts[t], stats[t]);
+        orc::searchAll(c, res + base, o.data(), e - b, parts[t], stats[t], &cigars[t]);
         for (auto & hit : parts[t]) hit.q_id += static_cast<uint32_t>(b);
     }
     h->hits.clear();
+    h->cigar.clear();
     for (int t = 0; t < threads; ++t)
     {
+        for (auto & hit : parts[t]) hit.cigar_off += static_cast<uint32_t>(h->cigar.size());
+        h->cigar.insert(h->cigar.end(), cigars[t].begin(), cigars[t].end());
         h->hits.insert(h->hits.end(), parts[t].begin(), parts[t].end());
         uint64_t const * s = reinterpret_cast<uint64_t const *>(&stats[t]);
         uint64_t *       d = reinterpret_cast<uint64_t *>(st);

@@ -118,6 +118,11 @@ class Oracle:
                                threads, C.byref(out), C.byref(n), _p(st))
         assert rc == 0
         hits = np.frombuffer(C.string_at(out, n.value * HIT_DT.itemsize), HIT_DT).copy() if n.value else np.zeros(0, HIT_DT)
+        # gapped rows as run-length operations (lgpu_params.want_cigar), indexed by lgpu_hit.cigar_off / cigar_len
+        ops = C.POINTER(C.c_uint32)()
+        self.l.orc_last_cigar.restype = C.c_uint64
+        nops = self.l.orc_last_cigar(C.c_void_p(self.h), C.byref(ops))
+        self.last_cigar_ops = np.ctypeslib.as_array(ops, (nops,)).copy() if nops else np.zeros(0, np.uint32)
         return hits, st[0]
 
     def m8(self, p, hits, query_ids):

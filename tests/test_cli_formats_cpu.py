@@ -1,0 +1,107 @@
+"""The five output writers of the command-line host (.m8 .m9 .m0 .sam .bam, --output-columns) checked against the
+reference binary's golden files WITHOUT a GPU: the CPU oracle (test infrastructure) computes the records incl. the
+gapped rows as run-length operations, `lambda3_b200 --replay-hits FILE` only formats them (no search happens in that
+mode).  This pins (a) the writers and (b) the oracle's runs against the reference's SAM CIGARs / pairwise rows.
+The same files are produced from the CUDA path's records in tests/test_gpu_parity.py::test_cli_*."""
+import gzip
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import orc
+from cases import query_alph, query_encoding
+from lambda_b200._abi import HIT_DT, STATS_DT
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "bin", "lambda3_b200")
+pytestmark = pytest.mark.skipif(not os.path.exists(CLI), reason="bin/lambda3_b200 not built")
+CASES = [("prot_flat", 0), ("prot_family", 0), ("prot_diverged", 0), ("nucl", 1), ("bisulfite", 2), ("blastx", 0),
+         ("tblastn", 0), ("tblastx", 0)]
+SUB = ("searchp", "searchn", "searchbs")
+
+
+def write_hit_file(path, hits, stats, ops):
+    with open(path, "wb") as f:
+        f.write(b"LGPUHITS" + struct.pack("<QQ", len(hits), len(ops)))
+        f.write(np.asarray([stats], STATS_DT).tobytes())
+        f.write(np.ascontiguousarray(hits, HIT_DT).tobytes())
+        f.write(np.ascontiguousarray(ops, np.uint32).tobytes())
+
+
+@pytest.fixture(scope="module")
+def replay(golden_dir):
+    """per case: the oracle's records (profile none, want_cigar) as a hit file inside the unpacked golden dir"""
+    made = {}
+
+    def get(case, domain, qfile="q.fasta"):
+        key = (case, qfile)
+        if key not in made:
+            cwd = os.path.join(golden_dir, case)
+            o = orc.Oracle(os.path.join(cwd, "db.lba"))
+            ids, data, offs = orc.read_fasta(os.path.join(cwd, qfile))
+            p = o.params(domain, "none")
+            p.query_alph = query_alph(case)
+            p.want_cigar = 1
+            hits, st = o.search(p, orc.encode(data, query_encoding(case, domain)), offs)
+            path = os.path.join(cwd, qfile + ".hits")
+            write_hit_file(path, hits, st, o.last_cigar_ops)
+            o.close()
+            made[key] = path
+        return made[key]
+    return get
+
+
+def run_cli(golden_dir, case, domain, hits, out, *extra, qfile="q.fasta"):
+    cwd = os.path.join(golden_dir, case)
+    if os.path.exists(os.path.join(cwd, out)):
+        os.remove(os.path.join(cwd, out))
+    subprocess.run([CLI, SUB[domain], "-q", qfile, "-i", "db.lba", "-o", out, "-t", "1", "-v", "0", "--replay-hits", hits,
+                    *extra], check=True, cwd=cwd, capture_output=True)
+    return os.path.join(cwd, out)
+
+
+@pytest.mark.parametrize("case,domain", CASES)
+def test_replayed_m8_m9_sam_m0_equal_reference(golden_dir, replay, case, domain):
+    hits = replay(case, domain)
+    v0 = ["--version-to-outputfile", "0"]
+    for name, extra in (("none.m8", v0), ("none.m9", v0), ("none.v1.m9", []), ("none.sam", v0), ("none.m0", v0)):
+        ref = os.path.join(golden_dir, case, name)
+        if not os.path.exists(ref):
+            continue  # (prot_family has no .m9 fixture)
+        out = run_cli(golden_dir, case, domain, hits, "replay_" + name, *extra)
+        ours, want = open(out).read().splitlines(), open(ref).read().splitlines()
+        for i, (a, b) in enumerate(zip(ours, want)):
+            assert a == b, (name, i, a, b)
+        assert len(ours) == len(want), name
+
+
+@pytest.mark.parametrize("case,domain", [c for c in CASES if c[0] != "prot_diverged"])
+def test_replayed_bam_equals_reference(golden_dir, replay, case, domain):
+    out = run_cli(golden_dir, case, domain, replay(case, domain), "replay_none.bam", "--version-to-outputfile", "0")
+    ours = gzip.open(out, "rb").read()
+    ref = gzip.open(os.path.join(golden_dir, case, "none.bam"), "rb").read()
+    assert ours[:4] == b"BAM\x01" and ours == ref
+
+
+@pytest.mark.parametrize("case,domain", [c for c in CASES if c[0] != "prot_family"])
+def test_replayed_output_columns_equal_reference(golden_dir, replay, case, domain):
+    from golden.make_golden_columns import COLUMNS
+    out = run_cli(golden_dir, case, domain, replay(case, domain), "replay_cols.m9", "--version-to-outputfile", "0",
+                  "--output-columns", COLUMNS)
+    assert open(out).read() == open(os.path.join(golden_dir, case, "cols.m9")).read()
+
+
+def test_replay_refuses_foreign_hit_files(golden_dir, replay, tmp_path):
+    hits = replay("prot_flat", 0)
+    cwd = os.path.join(golden_dir, "nucl")  # other index, other queries
+    r = subprocess.run([CLI, "searchn", "-q", "q.fasta", "-i", "db.lba", "-o", str(tmp_path / "x.m8"), "--replay-hits", hits],
+                       cwd=cwd, capture_output=True, text=True)
+    bad = tmp_path / "bad.hits"
+    bad.write_bytes(b"NOTHITS!" + b"\0" * 64)
+    r2 = subprocess.run([CLI, "searchn", "-q", "q.fasta", "-i", "db.lba", "-o", str(tmp_path / "y.m8"), "--replay-hits", str(bad)],
+                        cwd=cwd, capture_output=True, text=True)
+    assert r2.returncode == 255 and "malformed hit file" in r2.stderr
+    assert r.returncode in (0, 255)  # ids may happen to be in range; a mismatch must not crash
