@@ -31,6 +31,24 @@
 namespace
 {
 
+// SamBamExtraTags (src/search_output.hpp:29-76), in enum order
+enum SamTag { ST_AS, ST_OC, ST_NM, ST_IH, ST_ar, ST_ae, ST_ai, ST_ap, ST_qf, ST_qs, ST_sf, ST_st, ST_ls, ST_lt };
+char const * const kSamTagKeys[14]  = {"AS", "OC", "NM", "IH", "ar", "ae", "ai", "ap", "qf", "qs", "sf", "st", "ls", "lt"};
+char const * const kSamTagDescr[14] = {"bit score",
+                                       "query protein cigar (* for BLASTN)",
+                                       "edit distance (in protein space unless BLASTN)",
+                                       "number of matches this query has",
+                                       "raw score",
+                                       "expect value",
+                                       "% identity (in protein space unless BLASTN) ",
+                                       "% positive (in protein space unless BLASTN)",
+                                       "query frame",
+                                       "query protein sequence (* for BLASTN)",
+                                       "subject frame",
+                                       "subject taxonomy IDs (* if n/a)",
+                                       "lowest common ancestor scientific name",
+                                       "lowest common ancestor taxonomy ID"};
+
 struct Options
 {
     uint32_t    domain = LGPU_DOMAIN_PROTEIN;
@@ -39,6 +57,11 @@ struct Options
     int         threads   = 1; // only used for the reference's records_per_batch formula
     int         gpus      = 1;
     bool        comments  = false; // .m9: BLAST tabular with comment lines
+    // SAM / BAM dialect (src/search_options.hpp:276-370,765-823): tags in the order of SamBamExtraTags::Enum
+    bool        samTags[14] = {true, false, true, false, false, true, true, false, true, false, false, false, false, false};
+    bool        samWithRefHeader = false; // --sam-with-refheader: @SQ lines in .sam (always there in .bam)
+    int         samBamSeq        = 1;     // --sam-bam-seq never|uniq|always = 0|1|2
+    bool        samHardClip      = true;  // --sam-bam-clip hard|soft
     std::string replayHits;            // --replay-hits FILE: format records computed elsewhere (test hook, no search)
     std::string outputColumns = "std"; // --output-columns (.m8 / .m9)
     std::vector<uint32_t> columns;     // ... resolved to BlastMatchField indices
@@ -69,6 +92,8 @@ void usage()
               "  -a, --input-alphabet   auto|dna5|aminoacid (searchp; dna queries are translated: BLASTX/TBLASTX)\n"
               "  -p, --profile          none|fast|sensitive|pairs-default|pairs-sensitive\n"
               "      --output-columns   'std' or space-separated NCBI column specifiers (.m8 / .m9; 'help' lists them)\n"
+              "      --sam-bam-tags     'AS NM ae ai qf' (default) or any of AS OC NM IH ar ae ai ap qf qs sf ('help')\n"
+              "      --sam-bam-seq      always|uniq|never   --sam-bam-clip hard|soft   --sam-with-refheader 0|1\n"
               "  -e, --e-value          maximum e-value (default 0.01; -1 = off)\n"
               "      --bit-score        minimum bit score (default -1 = off)\n"
               "      --percent-identity minimum identity in percent (default 0)\n"
@@ -131,6 +156,60 @@ void parse(int argc, char ** argv, Options & o)
         else if (a == "-a" || a == "--input-alphabet") o.inputAlphabet = need(i);
         else if (a == "--output-columns") o.outputColumns = need(i);
         else if (a == "--replay-hits") o.replayHits = need(i);
+        else if (a == "--sam-with-refheader")
+        {
+            std::string const v = need(i);
+            o.samWithRefHeader  = v == "1" || v == "true";
+        }
+        else if (a == "--sam-bam-seq")
+        {
+            std::string const v = need(i);
+            if (v != "always" && v != "uniq" && v != "never")
+                die("Value " + v + " is not one of [always,uniq,never].");
+            o.samBamSeq = v == "never" ? 0 : v == "uniq" ? 1 : 2;
+        }
+        else if (a == "--sam-bam-clip")
+        {
+            std::string const v = need(i);
+            if (v != "hard" && v != "soft")
+                die("Value " + v + " is not one of [hard,soft].");
+            o.samHardClip = v == "hard";
+        }
+        else if (a == "--sam-bam-tags")
+        {
+            std::string const v = need(i);
+            if (v == "help")
+            {
+                std::puts("Please specify the tags in this format -oc 'tag1 tag2', i.e. space-separated and enclosed in quotes. "
+                          "The order of tags is not preserved.\nThe following specifiers are supported:");
+                for (int t = 0; t < 14; ++t)
+                    std::printf("\t%s\t%s\n", kSamTagKeys[t], kSamTagDescr[t]);
+                std::exit(0);
+            }
+            for (bool & b : o.samTags)
+                b = false;
+            std::string tok;
+            auto        flush = [&]() {
+                if (tok.empty())
+                    return;
+                int found = -1;
+                for (int t = 0; t < 14; ++t)
+                    if (tok == kSamTagKeys[t])
+                        found = t;
+                if (found < 0)
+                    die("Unknown column specifier \"" + tok + "\". Please see \"--sam-bam-tags help\" for valid options.");
+                if (found >= 11)
+                    die("tag \"" + tok + "\" needs the taxonomy of the index, which lambda3_b200 does not load");
+                o.samTags[found] = true;
+                tok.clear();
+            };
+            for (char ch : v)
+                if (std::isspace(static_cast<unsigned char>(ch)))
+                    flush();
+                else
+                    tok.push_back(ch);
+            flush();
+        }
         else if (a == "-e" || a == "--e-value") o.params.max_evalue = std::atof(need(i));
         else if (a == "--bit-score") o.params.min_bit_score = std::atoi(need(i));
         else if (a == "--percent-identity") o.params.id_cutoff = std::atoi(need(i));
@@ -558,11 +637,39 @@ static int run(int argc, char ** argv)
         }
         std::fprintf(fo, "# %zu hits found\n", nHits);
     };
+    // residues of the frames of a stored sequence (used by the SAM tags and the pairwise report)
+    auto       frameLen  = [](uint64_t len, unsigned f) { uint64_t const o = f % 3; return (std::max(len, o) - o) / 3; };
+    // residue k (as a character) of frame `frame` of a stored sequence: strands for nucleotide searches,
+    // six-frame translation (canonical code) for translated ones, the sequence itself otherwise
+    auto frameChar = [&](uint8_t const * seq, uint64_t len, bool translated, bool nucleotide, int frame, uint64_t k) -> char {
+        if (translated)
+        {
+            uint64_t const pos = 3 * k + static_cast<uint64_t>(std::abs(frame)) - 1;
+            unsigned n1, n2, n3;
+            if (frame > 0)
+            {
+                n1 = seq[pos]; n2 = seq[pos + 1]; n3 = seq[pos + 2];
+            }
+            else
+            {
+                n1 = kDna5Complement[seq[len - pos - 1]]; n2 = kDna5Complement[seq[len - pos - 2]];
+                n3 = kDna5Complement[seq[len - pos - 3]];
+            }
+            return kAa27RankToChar[kDna5Translate[(n1 * 5 + n2) * 5 + n3]];
+        }
+        if (nucleotide)
+            return kDna5RankToChar[frame < 0 ? kDna5Complement[seq[len - 1 - k]] : seq[k]];
+        return kAa27RankToChar[seq[k]];
+    };
     // ---- SAM (src/search_output.hpp:346-458 header, :482-716 records; defaults of src/search_options.hpp:339-370) ----
     bool const isBlastN = desc->trans_alph != LGPU_ALPH_AMINO_ACID;
     std::string bamRaw; // uncompressed BAM stream
     auto        put32 = [&](uint32_t v) { bamRaw.append(reinterpret_cast<char const *>(&v), 4); };
-    if (o.bam)
+    auto        refName = [&](uint64_t sq) {
+        std::string name = subjectId(static_cast<uint32_t>(sq));
+        return name.substr(0, name.find(' '));
+    };
+    if (o.sam)
     {
         std::string text = "@HD\tVN:1.4\tGO:query\n";
         if (o.versionToOutput)
@@ -572,37 +679,41 @@ static int run(int argc, char ** argv)
                 "@CO\tSAM/BAM dialect documentation is available here: https://github.com/seqan/lambda/wiki/Output-Formats\n"
                 "@CO\tIf you use any results found by Lambda, please cite Hauswedell et al. (2014) doi: "
                 "10.1093/bioinformatics/btu439\n"
-                "@CO\tOptional tags as follow\tAS:bit score\tNM:edit distance (in protein space unless BLASTN)\tae:expect "
-                "value\tai:% identity (in protein space unless BLASTN) \tqf:query frame\n";
-        bamRaw = "BAM\1";
-        put32(static_cast<uint32_t>(text.size()));
-        bamRaw += text;
-        put32(static_cast<uint32_t>(desc->n_seqs));
-        for (uint64_t sq = 0; sq < desc->n_seqs; ++sq)
+                "@CO\tOptional tags as follow";
+        for (int t = 0; t < 14; ++t)
+            if (o.samTags[t])
+                text += std::string("\t") + kSamTagKeys[t] + ":" + kSamTagDescr[t];
+        text += "\n";
+        // .sam with --sam-with-refheader: the default writeHeader() appends the @SQ lines after the header records
+        if (!o.bam && o.samWithRefHeader)
+            for (uint64_t sq = 0; sq < desc->n_seqs; ++sq)
+                text += "@SQ\tSN:" + refName(sq) + "\tLN:" + std::to_string(desc->seq_delims[sq + 1] - desc->seq_delims[sq]) + "\n";
+        if (o.bam)
         {
-            std::string name = subjectId(static_cast<uint32_t>(sq));
-            name             = name.substr(0, name.find(' '));
-            put32(static_cast<uint32_t>(name.size() + 1));
-            bamRaw.append(name.c_str(), name.size() + 1);
-            put32(static_cast<uint32_t>(desc->seq_delims[sq + 1] - desc->seq_delims[sq]));
+            bamRaw = "BAM\1";
+            put32(static_cast<uint32_t>(text.size()));
+            bamRaw += text;
+            put32(static_cast<uint32_t>(desc->n_seqs));
+            for (uint64_t sq = 0; sq < desc->n_seqs; ++sq)
+            {
+                std::string const name = refName(sq);
+                put32(static_cast<uint32_t>(name.size() + 1));
+                bamRaw.append(name.c_str(), name.size() + 1);
+                put32(static_cast<uint32_t>(desc->seq_delims[sq + 1] - desc->seq_delims[sq]));
+            }
         }
+        else
+            std::fputs(text.c_str(), fo);
     }
-    else if (o.sam)
-    {
-        std::fputs("@HD\tVN:1.4\tGO:query\n", fo);
-        if (o.versionToOutput)
-            std::fprintf(fo, "@PG\tID:lambda\tPN:lambda\tVN:3.0.0\tCL:%s\n", o.commandLine.c_str());
-        std::fputs("@CO\tLambda is a high performance BLAST compatible local aligner, please see http://seqan.de/lambda for "
-                   "more information.\n"
-                   "@CO\tSAM/BAM dialect documentation is available here: https://github.com/seqan/lambda/wiki/Output-Formats\n"
-                   "@CO\tIf you use any results found by Lambda, please cite Hauswedell et al. (2014) doi: "
-                   "10.1093/bioinformatics/btu439\n"
-                   "@CO\tOptional tags as follow\tAS:bit score\tNM:edit distance (in protein space unless BLASTN)\tae:expect "
-                   "value\tai:% identity (in protein space unless BLASTN) \tqf:query frame\n",
-                   fo);
-    }
-    std::string cigarStr, seqStr;
-    auto        samRecord = [&](uint64_t q, lgpu_hit const * h, lgpu_hit const * prev) {
+    using CigarVec = std::vector<std::pair<char, unsigned>>;
+    auto cigarText = [](CigarVec const & el) {
+        std::string t;
+        for (auto const & e : el)
+            t += std::to_string(e.second) + e.first;
+        return t;
+    };
+    std::string seqStr;
+    auto        samRecord = [&](uint64_t q, lgpu_hit const * h, lgpu_hit const * prev, size_t nHits) {
         uint64_t const qLen = f.offsets[q + 1] - f.offsets[q]; // record.qLength: original query length
         // POS (src/search_output.hpp:499-510; the qLength in the reverse-frame branch is the reference's)
         int32_t beginPos = static_cast<int32_t>(h->s_start);
@@ -615,44 +726,92 @@ static int run(int argc, char ** argv)
         unsigned flag = prev ? 256u : 0u;
         if (h->q_frame < 0)
             flag |= 16u;
-        // CIGAR (blastMatchOneCigar, :116-196): only for nucleotide queries; hard clips
-        cigarStr.clear();
-        std::vector<std::pair<char, unsigned>> cigarEl;
-        if (isBlastN || qTrans)
-        {
-            unsigned const transFac       = qTrans ? 3 : 1;
-            unsigned const leftFrameClip  = static_cast<unsigned>(std::abs(h->q_frame)) - 1;
-            unsigned const rightFrameClip = qTrans ? static_cast<unsigned>((qLen - leftFrameClip) % 3) : 0;
-            uint64_t const srcLen         = qTrans ? (std::max<uint64_t>(qLen, leftFrameClip) - leftFrameClip) / 3 : qLen;
+        // CIGARs (blastMatchOneCigar :116-196, blastMatchTwoCigar :199-298).  Clips caused by the frame are always
+        // hard clips, those of the local alignment hard or soft (--sam-bam-clip).  The arithmetic is the
+        // reference's, unsigned wrap-around for untranslated protein queries (frame 0) included.
+        unsigned const leftFrameClip = static_cast<unsigned>(std::abs(h->q_frame)) - 1u;
+        uint64_t const srcLen        = qTrans ? (std::max<uint64_t>(qLen, leftFrameClip) - leftFrameClip) / 3 : qLen; // frame length
+        auto           oneCigar      = [&](unsigned transFac, bool translated) {
+            unsigned const rightFrameClip = translated ? static_cast<unsigned>((static_cast<unsigned>(qLen) - leftFrameClip) % 3) : 0u;
             unsigned const leftClip       = h->q_start * transFac;
             unsigned const rightClip      = static_cast<unsigned>(srcLen - h->q_end) * transFac;
-            std::vector<std::pair<char, unsigned>> el;
-            if (leftFrameClip + leftClip > 0)
-                el.push_back({'H', leftFrameClip + leftClip});
+            CigarVec       el;
+            if (o.samHardClip)
+            {
+                if (leftFrameClip + leftClip > 0)
+                    el.push_back({'H', leftFrameClip + leftClip});
+            }
+            else
+            {
+                if (leftFrameClip > 0)
+                    el.push_back({'H', leftFrameClip});
+                if (leftClip > 0)
+                    el.push_back({'S', leftClip});
+            }
             uint32_t const * ops = cigarOf(h);
             for (uint32_t k = h->cigar_len; k-- > 0;) // stored END first
             {
                 uint32_t const kind = ops[k] & 3u, run = ops[k] >> 2;
                 el.push_back({kind == LGPU_CIGAR_M ? 'M' : kind == LGPU_CIGAR_I ? 'I' : 'D', run * transFac});
             }
-            if (rightFrameClip + rightClip > 0)
-                el.push_back({'H', rightFrameClip + rightClip});
-            if (h->q_frame < 0)
-                std::reverse(el.begin(), el.end());
-            for (auto const & e : el)
-                cigarStr += std::to_string(e.second) + e.first;
-            cigarEl = el;
+            if (o.samHardClip)
+            {
+                if (rightFrameClip + rightClip > 0)
+                    el.push_back({'H', rightFrameClip + rightClip});
+            }
+            else
+            {
+                if (rightClip > 0)
+                    el.push_back({'S', rightClip});
+                if (rightFrameClip > 0)
+                    el.push_back({'H', rightFrameClip});
+            }
+            return el;
+        };
+        CigarVec cigarEl, protEl; // CIGAR column; OC tag (protein space)
+        if (o.samTags[ST_OC])
+        {
+            if (isBlastN)
+                cigarEl = oneCigar(1, false);
+            else if (qTrans)
+            {
+                cigarEl = oneCigar(3, true);
+                // the protein CIGAR of blastMatchTwoCigar: local clips only, never reversed
+                unsigned const leftClip = h->q_start, rightClip = static_cast<unsigned>(srcLen - h->q_end);
+                if (leftClip > 0)
+                    protEl.push_back({o.samHardClip ? 'H' : 'S', leftClip});
+                uint32_t const * ops = cigarOf(h);
+                for (uint32_t k = h->cigar_len; k-- > 0;)
+                {
+                    uint32_t const kind = ops[k] & 3u, run = ops[k] >> 2;
+                    protEl.push_back({kind == LGPU_CIGAR_M ? 'M' : kind == LGPU_CIGAR_I ? 'I' : 'D', run});
+                }
+                if (rightClip > 0)
+                    protEl.push_back({o.samHardClip ? 'H' : 'S', rightClip});
+            }
+            else
+            {
+                protEl = oneCigar(1, false); // BLASTP / TBLASTN: the one CIGAR is the protein CIGAR
+                if (h->q_frame < 0)
+                    std::reverse(protEl.begin(), protEl.end());
+            }
         }
-        else
-            cigarStr = "*";
-        // SEQ (--sam-bam-seq uniq: only when frame or aligned query range differ from the previous match)
-        bool const writeSeq = !prev || prev->q_frame != h->q_frame || prev->q_start != h->q_start || prev->q_end != h->q_end;
+        else if (isBlastN || qTrans)
+            cigarEl = oneCigar(qTrans ? 3 : 1, qTrans);
+        if (h->q_frame < 0)
+            std::reverse(cigarEl.begin(), cigarEl.end());
+        std::string const cigarStr = cigarEl.empty() ? "*" : cigarText(cigarEl);
+        // SEQ (--sam-bam-seq; uniq: only when frame or aligned query range differ from the previous match)
+        bool const writeSeq = o.samBamSeq > 1 ||
+                              (o.samBamSeq == 1 && (!prev || prev->q_frame != h->q_frame || prev->q_start != h->q_start ||
+                                                    prev->q_end != h->q_end));
         seqStr.clear();
         if (writeSeq && (isBlastN || qTrans))
         {
             static char const dna5[] = "ACGNT";
             uint8_t const *   src    = f.residues.data() + f.offsets[q];
-            uint64_t          b = h->q_start, e = h->q_end; // in the frame's sequence
+            // hard clipping: the aligned part; soft clipping: everything the frame covers
+            uint64_t b = o.samHardClip ? h->q_start : 0, e = o.samHardClip ? h->q_end : srcLen; // in the frame's sequence
             if (qTrans)
             {
                 uint64_t const shift = static_cast<uint64_t>(std::abs(h->q_frame)) - 1;
@@ -670,11 +829,27 @@ static int run(int argc, char ** argv)
         if (seqStr.empty())
             seqStr = "*";
         std::string const qName = f.ids[q].substr(0, f.ids[q].find_first_of(" \t\v\f\r\n"));
-        std::string       sName = subjectId(h->s_id);
-        sName                   = sName.substr(0, sName.find(' '));
-        char ev[64];
-        std::snprintf(ev, sizeof(ev), "%g", static_cast<double>(static_cast<float>(h->evalue)));
-        float const identity = static_cast<float>(100.0 * static_cast<float>(h->n_match) / static_cast<float>(h->aln_len));
+        std::string const sName = refName(h->s_id);
+        float const identity   = static_cast<float>(100.0 * static_cast<float>(h->n_match) / static_cast<float>(h->aln_len));
+        float const similarity = static_cast<float>(100.0 * static_cast<float>(h->n_positive) / static_cast<float>(h->aln_len));
+        // qs: the protein sequence the alignment was computed on (* for BLASTN or when SEQ is left out), :672-692
+        std::string qsStr = "*";
+        if (o.samTags[ST_qs] && !isBlastN && writeSeq)
+        {
+            uint64_t const b = o.samHardClip ? h->q_start : 0, e = o.samHardClip ? h->q_end : srcLen;
+            qsStr.clear();
+            for (uint64_t k = b; k < e; ++k)
+                qsStr += frameChar(f.residues.data() + f.offsets[q], qLen, qTrans, false, h->q_frame, k);
+        }
+        std::string const ocStr = protEl.empty() ? "*" : cigarText(protEl);
+        // typed optional fields in the order the reference appends them (:597-719)
+        float const    evF = static_cast<float>(h->evalue);
+        uint16_t const as  = static_cast<uint16_t>(h->bit_score);
+        uint8_t const  ar  = static_cast<uint8_t>(h->score);
+        uint8_t const  ai  = static_cast<uint8_t>(identity);
+        uint16_t const ap  = static_cast<uint16_t>(similarity);
+        uint32_t const nm  = h->aln_len - h->n_match;
+        uint32_t const ih  = static_cast<uint32_t>(nHits);
         if (o.bam)
         {
             // SAM/BAM specification 4.2; bin from the reference span of the CIGAR (one base without CIGAR)
@@ -708,54 +883,47 @@ static int run(int argc, char ** argv)
             for (uint32_t i = 0; i < lSeq; i += 2)
                 rec += static_cast<char>((code(seqStr[i]) << 4) | (i + 1 < lSeq ? code(seqStr[i + 1]) : 0u));
             rec.append(lSeq, static_cast<char>(0xff));
-            float const    evF = static_cast<float>(h->evalue);
-            uint16_t const as  = static_cast<uint16_t>(h->bit_score);
-            uint32_t const nm  = h->aln_len - h->n_match;
-            rec += "aef";
-            rec.append(reinterpret_cast<char const *>(&evF), 4);
-            rec += "ASS";
-            rec.append(reinterpret_cast<char const *>(&as), 2);
-            rec += "aiC";
-            rec += static_cast<char>(static_cast<uint8_t>(identity));
-            rec += "qfc";
-            rec += static_cast<char>(h->q_frame);
-            rec += "NMI";
-            rec.append(reinterpret_cast<char const *>(&nm), 4);
+            auto tagRaw = [&](int t, char type, void const * v, size_t n) {
+                rec += kSamTagKeys[t];
+                rec += type;
+                rec.append(static_cast<char const *>(v), n);
+            };
+            if (o.samTags[ST_ae]) tagRaw(ST_ae, 'f', &evF, 4);
+            if (o.samTags[ST_AS]) tagRaw(ST_AS, 'S', &as, 2);
+            if (o.samTags[ST_ar]) tagRaw(ST_ar, 'C', &ar, 1);
+            if (o.samTags[ST_ai]) tagRaw(ST_ai, 'C', &ai, 1);
+            if (o.samTags[ST_ap]) tagRaw(ST_ap, 'S', &ap, 2);
+            if (o.samTags[ST_qf]) tagRaw(ST_qf, 'c', &h->q_frame, 1);
+            if (o.samTags[ST_sf]) tagRaw(ST_sf, 'c', &h->s_frame, 1);
+            if (o.samTags[ST_qs]) tagRaw(ST_qs, 'Z', qsStr.c_str(), qsStr.size() + 1);
+            if (o.samTags[ST_OC]) tagRaw(ST_OC, 'Z', ocStr.c_str(), ocStr.size() + 1);
+            if (o.samTags[ST_NM]) tagRaw(ST_NM, 'I', &nm, 4);
+            if (o.samTags[ST_IH]) tagRaw(ST_IH, 'I', &ih, 4);
             put32(static_cast<uint32_t>(rec.size()));
             bamRaw += rec;
             return;
         }
-        std::fprintf(fo, "%s\t%u\t%s\t%d\t255\t%s\t*\t0\t0\t%s\t*\tae:f:%s\tAS:i:%u\tai:i:%u\tqf:i:%d\tNM:i:%u\n", qName.c_str(),
-                     flag, sName.c_str(), beginPos + 1, cigarStr.c_str(), seqStr.c_str(), ev,
-                     static_cast<unsigned>(static_cast<uint16_t>(h->bit_score)),
-                     static_cast<unsigned>(static_cast<uint8_t>(identity)), static_cast<int>(h->q_frame),
-                     h->aln_len - h->n_match);
+        std::string line = qName + "\t" + std::to_string(flag) + "\t" + sName + "\t" + std::to_string(beginPos + 1) + "\t255\t" +
+                           cigarStr + "\t*\t0\t0\t" + seqStr + "\t*";
+        char ev[64];
+        std::snprintf(ev, sizeof(ev), "%g", static_cast<double>(evF));
+        auto tagInt = [&](int t, long long v) { line += std::string("\t") + kSamTagKeys[t] + ":i:" + std::to_string(v); };
+        if (o.samTags[ST_ae]) line += std::string("\tae:f:") + ev;
+        if (o.samTags[ST_AS]) tagInt(ST_AS, as);
+        if (o.samTags[ST_ar]) tagInt(ST_ar, ar);
+        if (o.samTags[ST_ai]) tagInt(ST_ai, ai);
+        if (o.samTags[ST_ap]) tagInt(ST_ap, ap);
+        if (o.samTags[ST_qf]) tagInt(ST_qf, h->q_frame);
+        if (o.samTags[ST_sf]) tagInt(ST_sf, h->s_frame);
+        if (o.samTags[ST_qs]) line += "\tqs:Z:" + qsStr;
+        if (o.samTags[ST_OC]) line += "\tOC:Z:" + ocStr;
+        if (o.samTags[ST_NM]) tagInt(ST_NM, nm);
+        if (o.samTags[ST_IH]) tagInt(ST_IH, ih);
+        line += "\n";
+        std::fwrite(line.data(), 1, line.size(), fo);
     };
     // ---- .m0: BLAST pairwise report (SQ/blast/blast_report_out.h:296-868) ----
     bool const bsIndex   = desc->red_alph == LGPU_ALPH_DNA3BS;
-    auto       frameLen  = [](uint64_t len, unsigned f) { uint64_t const o = f % 3; return (std::max(len, o) - o) / 3; };
-    // residue k (as a character) of frame `frame` of a stored sequence: strands for nucleotide searches,
-    // six-frame translation (canonical code) for translated ones, the sequence itself otherwise
-    auto frameChar = [&](uint8_t const * seq, uint64_t len, bool translated, bool nucleotide, int frame, uint64_t k) -> char {
-        if (translated)
-        {
-            uint64_t const pos = 3 * k + static_cast<uint64_t>(std::abs(frame)) - 1;
-            unsigned n1, n2, n3;
-            if (frame > 0)
-            {
-                n1 = seq[pos]; n2 = seq[pos + 1]; n3 = seq[pos + 2];
-            }
-            else
-            {
-                n1 = kDna5Complement[seq[len - pos - 1]]; n2 = kDna5Complement[seq[len - pos - 2]];
-                n3 = kDna5Complement[seq[len - pos - 3]];
-            }
-            return kAa27RankToChar[kDna5Translate[(n1 * 5 + n2) * 5 + n3]];
-        }
-        if (nucleotide)
-            return kDna5RankToChar[frame < 0 ? kDna5Complement[seq[len - 1 - k]] : seq[k]];
-        return kAa27RankToChar[seq[k]];
-    };
     double  kaLambda = 0, kaK = 0, kaH = 0;
     int8_t  scoreMat[32 * 32];
     uint64_t dbLetters = desc->n_residues, dbSeqs = desc->n_seqs;
@@ -952,7 +1120,7 @@ static int run(int argc, char ** argv)
                         for (lgpu_hit const * h : perQuery[q])
                             if (h->phase == phase)
                             {
-                                samRecord(q, h, prev);
+                                samRecord(q, h, prev, nHits);
                                 prev = h;
                             }
                         continue;

@@ -105,3 +105,24 @@ def test_replay_refuses_foreign_hit_files(golden_dir, replay, tmp_path):
                         cwd=cwd, capture_output=True, text=True)
     assert r2.returncode == 255 and "malformed hit file" in r2.stderr
     assert r.returncode in (0, 255)  # ids may happen to be in range; a mismatch must not crash
+
+
+@pytest.mark.parametrize("variant", ["opt_soft.sam", "opt_tags.sam", "opt_tags.bam"])
+@pytest.mark.parametrize("case,domain", CASES)
+def test_replayed_sam_dialect_options_equal_reference(golden_dir, replay, case, domain, variant):
+    """--sam-bam-clip soft, --sam-bam-seq always|never, --sam-with-refheader, --sam-bam-tags with every non-taxonomy
+    tag (src/search_options.hpp:276-370, src/search_output.hpp:116-298,482-719) for all six BLAST modes"""
+    from golden.make_golden_sam_options import VARIANTS
+    out = run_cli(golden_dir, case, domain, replay(case, domain), "replay_" + variant, "--version-to-outputfile", "0",
+                  *VARIANTS[variant])
+    ref = os.path.join(golden_dir, case, variant)
+    if variant.endswith(".bam"):
+        ours, want = gzip.open(out, "rb").read(), gzip.open(ref, "rb").read()
+        if ours != want:
+            i = next(k for k in range(min(len(ours), len(want))) if ours[k] != want[k])
+            raise AssertionError((len(ours), len(want), i, ours[max(0, i - 60):i + 60], want[max(0, i - 60):i + 60]))
+        return
+    ours, want = open(out).read().splitlines(), open(ref).read().splitlines()
+    for i, (a, b) in enumerate(zip(ours, want)):
+        assert a == b, (i, a, b)
+    assert len(ours) == len(want)
