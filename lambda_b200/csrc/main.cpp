@@ -56,6 +56,7 @@ struct Options
     int         verbosity = 1;
     int         threads   = 1; // only used for the reference's records_per_batch formula
     int         gpus      = 1;
+    bool        gzOutput  = false; // output path ends in .gz: the text is gzip-compressed
     bool        comments  = false; // .m9: BLAST tabular with comment lines
     // SAM / BAM dialect (src/search_options.hpp:276-370,765-823): tags in the order of SamBamExtraTags::Enum
     bool        samTags[14] = {true, false, true, false, false, true, true, false, true, false, false, false, false, false};
@@ -245,12 +246,19 @@ void parse(int argc, char ** argv, Options & o)
         die("Invalid argument to --input-alphabet");
     if (o.domain != LGPU_DOMAIN_PROTEIN && o.inputAlphabet != "auto")
         die("--input-alphabet is a searchp option");
-    o.comments = endsWith(o.output, ".m9");
-    o.bam      = endsWith(o.output, ".bam");
-    o.sam      = endsWith(o.output, ".sam") || o.bam;
-    o.report   = endsWith(o.output, ".m0");
-    if (!endsWith(o.output, ".m8") && !o.comments && !o.sam && !o.report)
-        die("supported output formats: .m0, .m8, .m9, .sam, .bam");
+    // the format follows the extension, looked at without a trailing ".gz" (src/search_options.hpp:210-214,684-709)
+    std::string fmtPath = o.output;
+    o.gzOutput          = endsWith(fmtPath, ".gz");
+    if (o.gzOutput)
+        fmtPath.resize(fmtPath.size() - 3);
+    o.comments = endsWith(fmtPath, ".m9");
+    o.bam      = endsWith(fmtPath, ".bam");
+    o.sam      = endsWith(fmtPath, ".sam") || o.bam;
+    o.report   = endsWith(fmtPath, ".m0");
+    if (!endsWith(fmtPath, ".m8") && !o.comments && !o.sam && !o.report)
+        die("supported output formats: .m0, .m8, .m9, .sam, .bam (optionally followed by .gz)");
+    if (o.bam && o.gzOutput)
+        die(".bam is BGZF-compressed already; .bam.gz is not supported");
     o.params.want_cigar = (o.sam || o.report) ? 1u : 0u;
     // --output-columns (src/search_options.hpp:710-760): space-separated NCBI specifiers, "std" = the default twelve
     if (o.outputColumns == "help")
@@ -602,7 +610,10 @@ static int run(int argc, char ** argv)
         return nullptr;
     };
     uint64_t const rpb = std::max<uint64_t>(std::min<uint64_t>(nQ / (static_cast<uint64_t>(o.threads) * 10), 10), 1);
-    FILE *         fo  = std::fopen(o.output.c_str(), "wb");
+    // .gz outputs are formatted into memory and compressed when everything is written
+    char *         gzMem = nullptr;
+    size_t         gzLen = 0;
+    FILE *         fo    = o.gzOutput ? open_memstream(&gzMem, &gzLen) : std::fopen(o.output.c_str(), "wb");
     if (!fo)
         die("cannot create output file " + o.output);
     std::vector<char> line(1 << 16);
@@ -1152,6 +1163,21 @@ static int run(int argc, char ** argv)
         std::fprintf(fo, "\nGap Penalties: Existence: %d, Extension: %d\n\n", -o.params.gap_open, -o.params.gap_extend);
     }
     std::fclose(fo);
+    if (o.gzOutput)
+    {
+        gzFile gz = gzopen(o.output.c_str(), "wb");
+        if (!gz)
+            die("cannot create output file " + o.output);
+        for (size_t off = 0; off < gzLen;)
+        {
+            unsigned const n = static_cast<unsigned>(std::min<size_t>(gzLen - off, 1u << 30));
+            if (gzwrite(gz, gzMem + off, n) != static_cast<int>(n))
+                die("error while writing " + o.output);
+            off += n;
+        }
+        gzclose(gz);
+        std::free(gzMem);
+    }
     lgpu_lba_close(lba);
     double const t4 = now();
 

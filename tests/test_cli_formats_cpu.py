@@ -126,3 +126,11 @@ def test_replayed_sam_dialect_options_equal_reference(golden_dir, replay, case, 
     for i, (a, b) in enumerate(zip(ours, want)):
         assert a == b, (i, a, b)
     assert len(ours) == len(want)
+
+
+@pytest.mark.parametrize("name", ["none.m8", "none.m9", "none.sam", "none.m0"])
+def test_gzip_compressed_outputs(golden_dir, replay, name):
+    """the reference accepts .m0/.m8/.m9/.sam followed by .gz (src/search_options.hpp:210-214); content must be the same"""
+    out = run_cli(golden_dir, "prot_flat", 0, replay("prot_flat", 0), "replay_" + name + ".gz", "--version-to-outputfile", "0")
+    assert open(out, "rb").read(2) == b"\x1f\x8b"
+    assert gzip.open(out, "rt").read() == open(os.path.join(golden_dir, "prot_flat", name)).read()
