@@ -99,7 +99,24 @@ typedef struct
  * src/shared_definitions.hpp:330-379).  The returned object owns the file mapping; `desc` points
  * into it and stays valid until lgpu_lba_close(). */
 typedef struct lgpu_lba lgpu_lba;
+/* Taxonomy stored in the index (index_file::sTaxIds / taxonParentIDs / taxonHeights / taxonNames,
+ * src/shared_definitions.hpp:352-356).  Not read by the search; the host needs it for the lowest common
+ * ancestor of a record (_writeRecord, src/search_algo.hpp:886-908) and the taxonomy columns / tags.
+ * Pointers are NULL / counts 0 when the index was built without taxonomy. */
+typedef struct
+{
+    uint32_t const * s_tax_ids;         /* concatenated tax ids of all subjects                    */
+    uint64_t         n_s_tax_ids;
+    uint64_t const * s_tax_delims;      /* n_seqs + 1 (NULL: no tax ids in the index)              */
+    uint32_t const * taxon_parents;     /* parent of every taxon, indexed by tax id; 0 = unassigned */
+    uint8_t const *  taxon_heights;     /* depth of every taxon                                    */
+    uint64_t         n_taxa;
+    char const *     taxon_names;       /* concatenated scientific names                           */
+    uint64_t const * taxon_name_delims; /* n_taxa + 1 (NULL: no names in the index)                */
+} lgpu_taxonomy;
+
 int                     lgpu_lba_open(lgpu_lba ** out, char const * path);
+lgpu_taxonomy const *   lgpu_lba_taxonomy(lgpu_lba const *);
 lgpu_index_desc const * lgpu_lba_desc(lgpu_lba const *);
 void                    lgpu_lba_close(lgpu_lba *);
 

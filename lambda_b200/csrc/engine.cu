@@ -1797,6 +1797,8 @@ int lgpu_lba_open(lgpu_lba ** out, char const * path)
 
 lgpu_index_desc const * lgpu_lba_desc(lgpu_lba const * l) { return l ? &l->file->desc : nullptr; }
 
+lgpu_taxonomy const * lgpu_lba_taxonomy(lgpu_lba const * l) { return l ? &l->file->tax : nullptr; }
+
 void lgpu_lba_close(lgpu_lba * l) { delete l; }
 
 int lgpu_index_create(lgpu_index ** out, lgpu_index_desc const * d, int device)

@@ -137,11 +137,9 @@ public:
     lgpu_index_desc desc{};
     uint64_t        generation  = 0;
     uint8_t         geneticCode = 0;
-    // taxonomy is carried along but unused on the hot path
-    uint32_t const * sTaxIds = nullptr;
-    uint64_t         nSTaxIds = 0;
-    uint64_t const * sTaxDelims = nullptr;
-    uint64_t         nSTaxDelims = 0;
+    // taxonomy (shared_definitions.hpp:352-356): not used by the search, only by the per-record LCA and the taxonomy
+    // columns / tags of the output (src/search_algo.hpp:886-908)
+    lgpu_taxonomy tax{};
 
 private:
     int             fd_   = -1;
@@ -208,12 +206,18 @@ private:
         if (desc.seq_delims[desc.n_seqs] != desc.n_residues)
             throw LbaError("index file corrupt: last sequence delimiter != residue count");
         // sTaxIds, taxonParentIDs, taxonHeights, taxonNames
-        sTaxIds    = reinterpret_cast<uint32_t const *>(vec(4, nSTaxIds));
-        sTaxDelims = reinterpret_cast<uint64_t const *>(vec(8, nSTaxDelims));
-        vec(4, n); // taxonParentIDs
-        vec(1, n); // taxonHeights
-        vec(1, n); // taxonNames data
-        vec(8, n); // taxonNames delimiters
+        tax.s_tax_ids    = reinterpret_cast<uint32_t const *>(vec(4, tax.n_s_tax_ids));
+        tax.s_tax_delims = reinterpret_cast<uint64_t const *>(vec(8, n));
+        if (n != desc.n_seqs + 1)
+            tax.s_tax_delims = nullptr; // index built without --acc-tax-map (the empty container holds one delimiter)
+        tax.taxon_parents = reinterpret_cast<uint32_t const *>(vec(4, tax.n_taxa));
+        tax.taxon_heights = vec(1, n);
+        if (n != tax.n_taxa)
+            throw LbaError("index file corrupt: taxonomy height / parent count mismatch");
+        tax.taxon_names       = reinterpret_cast<char const *>(vec(1, n));
+        tax.taxon_name_delims = reinterpret_cast<uint64_t const *>(vec(8, n));
+        if (tax.n_taxa == 0 || n != tax.n_taxa + 1)
+            tax.taxon_name_delims = nullptr; // index built without --tax-dump-dir
 
         // index.occ (InterleavedEPRV2.h:272-306)
         uint32_t const redSize = alphabetSize(desc.red_alph);

@@ -63,6 +63,8 @@ struct Options
     bool        samWithRefHeader = false; // --sam-with-refheader: @SQ lines in .sam (always there in .bam)
     int         samBamSeq        = 1;     // --sam-bam-seq never|uniq|always = 0|1|2
     bool        samHardClip      = true;  // --sam-bam-clip hard|soft
+    bool        hasSTaxIds = false; // a taxonomy column / tag was requested (src/search_options.hpp:744-750,806-814)
+    bool        computeLCA = false; // ... one that needs the lowest common ancestor of a record
     std::string replayHits;            // --replay-hits FILE: format records computed elsewhere (test hook, no search)
     std::string outputColumns = "std"; // --output-columns (.m8 / .m9)
     std::vector<uint32_t> columns;     // ... resolved to BlastMatchField indices
@@ -199,8 +201,12 @@ void parse(int argc, char ** argv, Options & o)
                         found = t;
                 if (found < 0)
                     die("Unknown column specifier \"" + tok + "\". Please see \"--sam-bam-tags help\" for valid options.");
-                if (found >= 11)
-                    die("tag \"" + tok + "\" needs the taxonomy of the index, which lambda3_b200 does not load");
+                if (found >= ST_st)
+                {
+                    o.hasSTaxIds = true;
+                    if (found != ST_st)
+                        o.computeLCA = true;
+                }
                 o.samTags[found] = true;
                 tok.clear();
             };
@@ -266,7 +272,8 @@ void parse(int argc, char ** argv, Options & o)
         std::puts("Please specify the columns in this format -oc 'column1 column2', i.e. space-separated and enclosed in "
                   "single quotes.\nThe specifiers are the same as in NCBI Blast, currently the following are supported:");
         for (uint32_t c = 0; lgpu_tabular_column_name(c); ++c)
-            if (lgpu_tabular_column_supported(c))
+            if (lgpu_tabular_column_supported(c) || !std::strcmp(lgpu_tabular_column_name(c), "staxids") ||
+                !std::strcmp(lgpu_tabular_column_name(c), "lcaid") || !std::strcmp(lgpu_tabular_column_name(c), "lcataxid"))
                 std::printf("\t%s%s%s\n", lgpu_tabular_column_name(c), std::strlen(lgpu_tabular_column_name(c)) >= 8 ? "\t" : "\t\t",
                             lgpu_tabular_column_label(c));
         std::exit(0);
@@ -279,8 +286,12 @@ void parse(int argc, char ** argv, Options & o)
             int const c = lgpu_tabular_column(tok.c_str());
             if (c < 0)
                 die("Unknown column specifier \"" + tok + "\". Please see -oc help for valid options.");
-            if (!lgpu_tabular_column_supported(static_cast<uint32_t>(c)))
-                die("column \"" + tok + "\" needs the taxonomy of the index, which lambda3_b200 does not load");
+            if (!lgpu_tabular_column_supported(static_cast<uint32_t>(c))) // staxids / lcaid / lcataxid: formatted here
+            {
+                o.hasSTaxIds = true;
+                if (tok != "staxids")
+                    o.computeLCA = true;
+            }
             o.columns.push_back(static_cast<uint32_t>(c));
             tok.clear();
         };
@@ -532,6 +543,14 @@ static int run(int argc, char ** argv)
     if (lgpu_lba_open(&lba, o.index.c_str()) != LGPU_OK)
         die(lgpu_last_error(nullptr));
     lgpu_index_desc const * desc = lgpu_lba_desc(lba);
+    lgpu_taxonomy const *   tax  = lgpu_lba_taxonomy(lba);
+    // src/search_algo.hpp:303-314
+    if (o.hasSTaxIds && (!tax->s_tax_delims || tax->n_s_tax_ids == 0))
+        die("You requested printing of taxonomic IDs and/or taxonomic binning, but the index does not contain taxonomic "
+            "information. Recreate it and provide --acc-tax-map .");
+    if (o.computeLCA && (tax->n_taxa == 0 || !tax->taxon_name_delims))
+        die("You requested taxonomic binning, but the index does not contain a taxonomic tree. Recreate it and provide "
+            "--tax-dump-dir .");
     double const            t1   = now();
     // query alphabet: fixed for searchn / searchbs, given or auto-detected for searchp (src/search.cpp:209-216)
     uint32_t qryAlph = LGPU_ALPH_DNA5;
@@ -632,6 +651,105 @@ static int run(int argc, char ** argv)
       o.versionToOutput ? std::string(program) + " 2.2.26+ [created by LAMBDA-3.0.0, see http://seqan.de/lambda and please "
                                                  "cite correctly in your academic work]"
                         : std::string(program) + " 2.2.26+ [I/O Module of SeqAn-2.4.1, http://www.seqan.de]";
+    // ---- taxonomy of a record (_writeRecord, src/search_algo.hpp:884-909; computeLCA, src/search_misc.hpp:86-112) ----
+    uint32_t    recLcaTaxId = 0; // of the record that is being written
+    std::string recLcaId;
+    auto        taxIdsOf = [&](uint32_t sId) {
+        return std::pair<uint32_t const *, uint32_t const *>(tax->s_tax_ids + tax->s_tax_delims[sId],
+                                                             tax->s_tax_ids + tax->s_tax_delims[sId + 1]);
+    };
+    auto lca2 = [&](uint32_t n1, uint32_t n2) -> uint32_t {
+        if (n1 == n2)
+            return n1;
+        for (unsigned i = tax->taxon_heights[n1]; i > tax->taxon_heights[n2]; --i) // bring both to the same height
+            n1 = tax->taxon_parents[n1];
+        for (unsigned i = tax->taxon_heights[n2]; i > tax->taxon_heights[n1]; --i)
+            n2 = tax->taxon_parents[n2];
+        while (n1 != 0 && n2 != 0)
+        {
+            if (n1 == n2)
+                return n1;
+            n1 = tax->taxon_parents[n1];
+            n2 = tax->taxon_parents[n2];
+        }
+        die("LCA-computation error: One of the paths didn't lead to root.");
+    };
+    auto computeRecordLca = [&](uint64_t q, int phase) {
+        recLcaTaxId = 0;
+        recLcaId.clear();
+        if (!o.computeLCA)
+            return;
+        for (lgpu_hit const * h : perQuery[q])
+            if (h->phase == phase)
+            {
+                auto const [b, e] = taxIdsOf(h->s_id);
+                if (b != e && tax->taxon_parents[*b] != 0)
+                {
+                    recLcaTaxId = *b;
+                    break;
+                }
+            }
+        if (recLcaTaxId != 0)
+            for (lgpu_hit const * h : perQuery[q])
+                if (h->phase == phase)
+                {
+                    auto const [b, e] = taxIdsOf(h->s_id);
+                    for (uint32_t const * t = b; t != e; ++t)
+                        if (tax->taxon_parents[*t] != 0) // unassigned subjects are ignored
+                            recLcaTaxId = lca2(*t, recLcaTaxId);
+                }
+        recLcaId.assign(tax->taxon_names + tax->taxon_name_delims[recLcaTaxId],
+                        tax->taxon_names + tax->taxon_name_delims[recLcaTaxId + 1]);
+    };
+    // one tabular line: the library formats the ordinary columns, the taxonomy columns are filled in here
+    // (SQ/blast/blast_tabular_out.h:440-492)
+    std::string tabLine;
+    auto        tabularLine = [&](uint64_t q, lgpu_hit const * h) -> std::string const & {
+        tabLine.clear();
+        std::string const sId = subjectId(h->s_id);
+        auto isTax = [](uint32_t c) { return !lgpu_tabular_column_supported(c); };
+        for (size_t i = 0; i < o.columns.size();)
+        {
+            if (i)
+                tabLine += '\t';
+            if (!isTax(o.columns[i]))
+            {
+                size_t j = i;
+                while (j < o.columns.size() && !isTax(o.columns[j]))
+                    ++j;
+                int const n = lgpu_format_tabular(&o.params, h, f.ids[q].c_str(), sId.c_str(), o.columns.data() + i, j - i,
+                                                  line.data(), line.size());
+                if (n <= 0)
+                    die("cannot format a tabular line");
+                tabLine.append(line.data(), static_cast<size_t>(n) - 1); // without the newline
+                i = j;
+                continue;
+            }
+            char const * name = lgpu_tabular_column_name(o.columns[i]);
+            if (!std::strcmp(name, "staxids"))
+            {
+                auto const            be = taxIdsOf(h->s_id);
+                std::vector<uint32_t> ids(be.first, be.second);
+                std::sort(ids.begin(), ids.end()); // "they have to be sorted numerically"
+                if (ids.empty())
+                    tabLine += "n/a";
+                for (size_t k = 0; k < ids.size(); ++k)
+                    tabLine += (k ? ";" : "") + std::to_string(ids[k]);
+            }
+            else if (!std::strcmp(name, "lcaid"))
+            {
+                if (recLcaId.empty())
+                    tabLine += "n/a";
+                for (char c : recLcaId)
+                    tabLine += (c == ' ' || c == '\t') ? '_' : c;
+            }
+            else
+                tabLine += std::to_string(recLcaTaxId);
+            ++i;
+        }
+        tabLine += '\n';
+        return tabLine;
+    };
     uint64_t nRecords = 0;
     auto     recordHeader = [&](uint64_t q, size_t nHits) {
         ++nRecords;
@@ -853,6 +971,16 @@ static int run(int argc, char ** argv)
                 qsStr += frameChar(f.residues.data() + f.offsets[q], qLen, qTrans, false, h->q_frame, k);
         }
         std::string const ocStr = protEl.empty() ? "*" : cigarText(protEl);
+        // st: the subject's tax ids in stored order, * if it has none (:641-662)
+        std::string stStr;
+        if (o.samTags[ST_st])
+        {
+            auto const be = taxIdsOf(h->s_id);
+            for (uint32_t const * t = be.first; t != be.second; ++t)
+                stStr += (t != be.first ? ";" : "") + std::to_string(*t);
+            if (stStr.empty())
+                stStr = "*";
+        }
         // typed optional fields in the order the reference appends them (:597-719)
         float const    evF = static_cast<float>(h->evalue);
         uint16_t const as  = static_cast<uint16_t>(h->bit_score);
@@ -906,6 +1034,9 @@ static int run(int argc, char ** argv)
             if (o.samTags[ST_ap]) tagRaw(ST_ap, 'S', &ap, 2);
             if (o.samTags[ST_qf]) tagRaw(ST_qf, 'c', &h->q_frame, 1);
             if (o.samTags[ST_sf]) tagRaw(ST_sf, 'c', &h->s_frame, 1);
+            if (o.samTags[ST_st]) tagRaw(ST_st, 'Z', stStr.c_str(), stStr.size() + 1);
+            if (o.samTags[ST_ls]) tagRaw(ST_ls, 'Z', recLcaId.c_str(), recLcaId.size() + 1);
+            if (o.samTags[ST_lt]) tagRaw(ST_lt, 'I', &recLcaTaxId, 4);
             if (o.samTags[ST_qs]) tagRaw(ST_qs, 'Z', qsStr.c_str(), qsStr.size() + 1);
             if (o.samTags[ST_OC]) tagRaw(ST_OC, 'Z', ocStr.c_str(), ocStr.size() + 1);
             if (o.samTags[ST_NM]) tagRaw(ST_NM, 'I', &nm, 4);
@@ -926,6 +1057,9 @@ static int run(int argc, char ** argv)
         if (o.samTags[ST_ap]) tagInt(ST_ap, ap);
         if (o.samTags[ST_qf]) tagInt(ST_qf, h->q_frame);
         if (o.samTags[ST_sf]) tagInt(ST_sf, h->s_frame);
+        if (o.samTags[ST_st]) line += "\tst:Z:" + stStr;
+        if (o.samTags[ST_ls]) line += "\tls:Z:" + recLcaId;
+        if (o.samTags[ST_lt]) tagInt(ST_lt, recLcaTaxId);
         if (o.samTags[ST_qs]) line += "\tqs:Z:" + qsStr;
         if (o.samTags[ST_OC]) line += "\tOC:Z:" + ocStr;
         if (o.samTags[ST_NM]) tagInt(ST_NM, nm);
@@ -1114,7 +1248,10 @@ static int run(int argc, char ** argv)
                     for (lgpu_hit const * h : perQuery[q])
                         nHits += h->phase == phase;
                     if (nHits)
+                    {
+                        computeRecordLca(q, phase);
                         recordHeader(q, nHits);
+                    }
                     if (o.report)
                     {
                         std::vector<lgpu_hit const *> ms;
@@ -1139,10 +1276,8 @@ static int run(int argc, char ** argv)
                     for (lgpu_hit const * h : perQuery[q])
                         if (h->phase == phase)
                         {
-                            int const n = lgpu_format_tabular(&o.params, h, f.ids[q].c_str(), subjectId(h->s_id).c_str(),
-                                                              o.columns.data(), o.columns.size(), line.data(), line.size());
-                            if (n > 0)
-                                std::fwrite(line.data(), 1, static_cast<size_t>(n), fo);
+                            std::string const & l = tabularLine(q, h);
+                            std::fwrite(l.data(), 1, l.size(), fo);
                         }
                 }
         }

@@ -134,3 +134,32 @@ def test_gzip_compressed_outputs(golden_dir, replay, name):
     out = run_cli(golden_dir, "prot_flat", 0, replay("prot_flat", 0), "replay_" + name + ".gz", "--version-to-outputfile", "0")
     assert open(out, "rb").read(2) == b"\x1f\x8b"
     assert gzip.open(out, "rt").read() == open(os.path.join(golden_dir, "prot_flat", name)).read()
+
+
+@pytest.mark.parametrize("name", ["tax.m9", "tax.sam", "tax.bam"])
+def test_replayed_taxonomy_columns_and_tags_equal_reference(golden_dir, replay, name):
+    """staxids / lcaid / lcataxid columns and the st / ls / lt tags: the subjects' tax ids from the index, the lowest
+    common ancestor of every record (_writeRecord, src/search_algo.hpp:884-909; computeLCA, src/search_misc.hpp:86-112).
+    Index with taxonomy built by the reference (tests/golden/make_golden_tax.py): subjects without tax id, with two
+    tax ids, names with blanks."""
+    from golden.make_golden_tax import COLUMNS, TAGS
+    extra = ["--output-columns", COLUMNS] if name.endswith(".m9") else ["--sam-bam-tags", TAGS]
+    out = run_cli(golden_dir, "tax", 0, replay("tax", 0), "replay_" + name, "--version-to-outputfile", "0", *extra)
+    ref = os.path.join(golden_dir, "tax", name)
+    if name.endswith(".bam"):
+        assert gzip.open(out, "rb").read() == gzip.open(ref, "rb").read()
+    else:
+        ours, want = open(out).read().splitlines(), open(ref).read().splitlines()
+        for i, (a, b) in enumerate(zip(ours, want)):
+            assert a == b, (i, a, b)
+        assert len(ours) == len(want)
+    assert "root" in open(os.path.join(golden_dir, "tax", "tax.m9")).read()  # the fixture has non-trivial LCAs
+
+
+def test_taxonomy_columns_need_an_index_with_taxonomy(golden_dir, replay, tmp_path):
+    for extra, msg in ((["--output-columns", "std staxids"], "does not contain taxonomic information"),
+                       (["--output-columns", "std lcaid"], "does not contain taxonomic information")):
+        r = subprocess.run([CLI, "searchp", "-q", "q.fasta", "-i", "db.lba", "-o", str(tmp_path / "x.m8"), "--replay-hits",
+                            replay("prot_flat", 0), *extra], cwd=os.path.join(golden_dir, "prot_flat"), capture_output=True,
+                           text=True)
+        assert r.returncode == 255 and msg in r.stderr
