@@ -103,7 +103,7 @@ void usage()
               "  -n, --num-matches      maximum matches per query (default 25)\n"
               "      --seed-length / --seed-offset / --seed-delta           phase-2 seeds\n"
               "      --seed-length0 / --seed-offset0 / --seed-delta0        phase-1 seeds\n"
-              "      --adaptive-seeding 0|1   --seed-half-exact 0|1   --iterative-search 0|1\n"
+              "      --adaptive-seeding 0|1   --seed-half-exact 0|1   --search0 0|1 (phase 1 with the ...0 seeds)\n"
               "      --pre-scoring N    --pre-scoring-threshold X\n"
               "  -s, --scoring-scheme   45|62|80 (searchp)   --score-gap  --score-gap-open\n"
               "      --score-match / --score-mismatch (searchn)\n"
@@ -149,6 +149,15 @@ void parse(int argc, char ** argv, Options & o)
             die(std::string("missing value for ") + argv[i]);
         return argv[++i];
     };
+    // boolean options take 0|1|true|false like the reference's parser
+    auto needBool = [&](int & i) -> bool {
+        std::string const opt = argv[i], v = need(i);
+        if (v == "1" || v == "true")
+            return true;
+        if (v == "0" || v == "false")
+            return false;
+        die("Value parse failed for " + opt + ": Argument " + v + " could not be parsed as type bool.");
+    };
     for (int i = 2; i < argc; ++i)
     {
         std::string const a = argv[i];
@@ -159,11 +168,7 @@ void parse(int argc, char ** argv, Options & o)
         else if (a == "-a" || a == "--input-alphabet") o.inputAlphabet = need(i);
         else if (a == "--output-columns") o.outputColumns = need(i);
         else if (a == "--replay-hits") o.replayHits = need(i);
-        else if (a == "--sam-with-refheader")
-        {
-            std::string const v = need(i);
-            o.samWithRefHeader  = v == "1" || v == "true";
-        }
+        else if (a == "--sam-with-refheader") o.samWithRefHeader = needBool(i);
         else if (a == "--sam-bam-seq")
         {
             std::string const v = need(i);
@@ -227,10 +232,17 @@ void parse(int argc, char ** argv, Options & o)
         else if (a == "--seed-length0") o.params.opts0.seed_length = static_cast<uint32_t>(std::atoi(need(i)));
         else if (a == "--seed-offset0") o.params.opts0.seed_offset = static_cast<uint32_t>(std::atoi(need(i)));
         else if (a == "--seed-delta0") o.params.opts0.max_seed_dist = static_cast<uint32_t>(std::atoi(need(i)));
-        else if (a == "--adaptive-seeding") o.params.adaptive_seeding = static_cast<uint32_t>(std::atoi(need(i)));
-        else if (a == "--seed-half-exact") o.params.seed_half_exact = static_cast<uint32_t>(std::atoi(need(i)));
-        else if (a == "--iterative-search") o.params.iterative_search = static_cast<uint32_t>(std::atoi(need(i)));
-        else if (a == "--pre-scoring") o.params.pre_scoring = std::atoi(need(i));
+        else if (a == "--adaptive-seeding") o.params.adaptive_seeding = needBool(i);
+        else if (a == "--seed-half-exact") o.params.seed_half_exact = needBool(i);
+        // the reference spells it --search0 (src/search_options.hpp:452-456); --iterative-search is kept as an alias
+        else if (a == "--search0" || a == "--iterative-search") o.params.iterative_search = needBool(i);
+        else if (a == "--pre-scoring")
+        {
+            o.params.pre_scoring = std::atoi(need(i));
+            if (o.params.pre_scoring < 1 || o.params.pre_scoring > 10)
+                die("Validation failed for option --pre-scoring: Value " + std::to_string(o.params.pre_scoring) +
+                    " is not in range [1,10].");
+        }
         else if (a == "--pre-scoring-threshold") o.params.pre_scoring_thresh = std::atof(need(i));
         else if (a == "-s" || a == "--scoring-scheme") o.params.scoring_method = std::atoi(need(i));
         else if (a == "--score-gap") o.params.gap_extend = std::atoi(need(i));
@@ -242,7 +254,7 @@ void parse(int argc, char ** argv, Options & o)
         else if (a == "--gpus") o.gpus = std::max(1, std::atoi(need(i)));
         else if (a == "--block-size") o.blockSize = std::max<uint64_t>(1, std::strtoull(need(i), nullptr, 10));
         else if (a == "-v" || a == "--verbosity") o.verbosity = std::atoi(need(i));
-        else if (a == "--version-to-outputfile") o.versionToOutput = std::atoi(need(i)) != 0; // .m9 comment lines
+        else if (a == "--version-to-outputfile") o.versionToOutput = needBool(i); // .m9 comment lines
         else if (a == "-h" || a == "--help") { usage(); std::exit(0); }
         else die("unknown option '" + a + "'");
     }

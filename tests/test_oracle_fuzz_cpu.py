@@ -1,0 +1,91 @@
+"""The oracle against the LIVE reference binary on random small databases with random NON-default options
+(e-value / bit-score / identity cut-offs, -n, seed lengths / offsets / distances of both phases, --search0,
+adaptive seeding, pre-scoring, BLOSUM 45 / 80, gap costs, nucleotide match / mismatch).  The golden files pin the
+profiles; this pins the rest of the option space, including the combinations both sides must refuse (no
+Karlin-Altschul parameters for the scoring scheme).  CPU only; seeds fixed."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import orc
+from lambda_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref", "lambda3")
+pytestmark = pytest.mark.skipif(not os.path.exists(REF), reason="reference binary (oracle/_ref/lambda3) not built")
+
+
+def random_case(seed, tmp):
+    rng = np.random.default_rng(seed)
+    dom = int(rng.integers(0, 2))  # 0 protein, 1 nucleotide
+    if dom == 0:
+        db, offs = synth.protein_db(int(rng.integers(100, 400)), seed=seed, family=bool(rng.integers(0, 2)))
+        q, qo = synth.protein_queries(db, offs, int(rng.integers(10, 40)), int(rng.integers(30, 200)), seed=seed + 1,
+                                      sub=(0.1, 0.35), indel=0.02)
+        mk, se = "mkindexp", "searchp"
+    else:
+        db, offs = synth.nucl_db(3, 20000, seed=seed)
+        q, qo = synth.nucl_reads(db, offs, int(rng.integers(20, 80)), int(rng.integers(40, 200)), seed=seed + 1)
+        mk, se = "mkindexn", "searchn"
+    synth.write_fasta(f"{tmp}/db.fasta", db, offs, "S")
+    synth.write_fasta(f"{tmp}/q.fasta", q, qo, "Q")
+    subprocess.check_call([REF, mk, "-d", f"{tmp}/db.fasta", "-i", f"{tmp}/db.lba", "-v", "0"])
+    o = orc.Oracle(f"{tmp}/db.lba")
+    p = o.params(dom)
+    flags = []
+
+    def opt(flag, field, val):
+        flags.extend([flag, str(val)])
+        setattr(p, field, val)
+
+    if rng.random() < 0.5: opt("-e", "max_evalue", float(rng.choice([1e-5, 1.0, 10.0, 100.0])))
+    if rng.random() < 0.4: opt("-n", "max_matches", int(rng.choice([1, 3, 50, 200])))
+    if rng.random() < 0.3: opt("--bit-score", "min_bit_score", int(rng.choice([30, 50, 80])))
+    if rng.random() < 0.3: opt("--percent-identity", "id_cutoff", int(rng.choice([50, 80, 95])))
+    if rng.random() < 0.4: opt("--adaptive-seeding", "adaptive_seeding", int(rng.integers(0, 2)))
+    if rng.random() < 0.3: opt("--search0", "iterative_search", 0)
+    if rng.random() < 0.4: opt("--pre-scoring", "pre_scoring", int(rng.choice([1, 2, 3])))
+    if rng.random() < 0.3: opt("--pre-scoring-threshold", "pre_scoring_thresh", float(rng.choice([1.0, 1.5, 2.5])))
+    if rng.random() < 0.4:
+        p.opts.seed_length = int(rng.choice([8, 9, 12])) if dom == 0 else int(rng.choice([12, 16, 20]))
+        flags.extend(["--seed-length", str(p.opts.seed_length)])
+    if rng.random() < 0.4:
+        p.opts.seed_offset = int(rng.choice([2, 4, 7]))
+        flags.extend(["--seed-offset", str(p.opts.seed_offset)])
+    if rng.random() < 0.3:
+        p.opts.max_seed_dist = 0
+        flags.extend(["--seed-delta", "0"])
+    if rng.random() < 0.3:
+        p.opts0.seed_length = int(rng.choice([9, 11])) if dom == 0 else int(rng.choice([13, 18]))
+        flags.extend(["--seed-length0", str(p.opts0.seed_length)])
+    if dom == 0 and rng.random() < 0.5: opt("-s", "scoring_method", int(rng.choice([45, 80])))
+    if rng.random() < 0.4:
+        opt("--score-gap", "gap_extend", int(rng.choice([-1, -2])))
+        opt("--score-gap-open", "gap_open", int(rng.choice([-8, -11, -14])) if dom == 0 else int(rng.choice([-3, -5, -8])))
+    if dom == 1 and rng.random() < 0.4:
+        opt("--score-match", "match", int(rng.choice([1, 3])))
+        opt("--score-mismatch", "mismatch", int(rng.choice([-2, -4])))
+    return dom, se, o, p, flags
+
+
+@pytest.mark.parametrize("seed", [1, 2, 4, 6, 7, 9, 10, 13, 14, 17, 21, 22, 23, 24, 25, 29, 30, 35, 38, 39])
+def test_oracle_equals_live_reference_with_random_options(tmp_path, seed):
+    tmp = str(tmp_path)
+    dom, se, o, p, flags = random_case(seed, tmp)
+    r = subprocess.run([REF, se, "-q", f"{tmp}/q.fasta", "-i", f"{tmp}/db.lba", "-o", f"{tmp}/r.m8", "-t", "1",
+                        "--version-to-outputfile", "0", "-v", "0", *flags], capture_output=True, text=True)
+    ids, data, qoffs = orc.read_fasta(f"{tmp}/q.fasta")
+    res = orc.encode(data, dom)
+    if r.returncode != 0:
+        # the only legitimate refusal here: no statistics for the scoring scheme -- the oracle must refuse as well
+        assert "Could not compute Karlin-Altschul-Values" in r.stderr, (flags, r.stderr)
+        with pytest.raises(AssertionError):
+            o.search(p, res, qoffs)
+        o.close()
+        return
+    hits, st = o.search(p, res, qoffs)
+    ref = open(f"{tmp}/r.m8").read().splitlines(True)
+    assert sorted(o.m8(p, hits, ids)) == sorted(ref), flags
+    o.close()

@@ -1,0 +1,37 @@
+"""CUDA path against the oracle on random small databases with random NON-default options (the same generator and
+seeds as tests/test_oracle_fuzz_cpu.py, where the oracle is held to the live reference binary): cut-offs, -n, seed
+lengths / offsets / distances, --search0 off, adaptive seeding off, pre-scoring variants, BLOSUM 45 / 80, gap costs,
+nucleotide scores.  Runs last (file name) because it was written after this round's GPU budget was used up: it has
+not been executed on a GPU by its author."""
+import os
+
+import numpy as np
+import pytest
+
+import lambda_b200
+import orc
+from cases import FUNNEL
+from test_oracle_fuzz_cpu import REF, random_case
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.path.exists(REF), reason="reference binary (index builder) not built")]
+
+
+@pytest.mark.parametrize("seed", [2, 4, 6, 7, 9, 10, 13, 14, 17, 21, 22, 23, 24, 25, 29, 30, 35, 39])
+def test_cuda_path_equals_oracle_with_random_options(tmp_path, seed):
+    tmp = str(tmp_path)
+    dom, se, o, p, flags = random_case(seed, tmp)
+    ids, data, qoffs = lambda_b200.read_queries(f"{tmp}/q.fasta")
+    res = lambda_b200.encode(data, dom)
+    ix = lambda_b200.Index.load(f"{tmp}/db.lba")
+    kw = {k: getattr(p, k) for k in ("max_evalue", "max_matches", "min_bit_score", "id_cutoff", "adaptive_seeding",
+                                     "iterative_search", "pre_scoring", "pre_scoring_thresh", "scoring_method", "gap_open",
+                                     "gap_extend", "match", "mismatch")}
+    kw["opts"] = (p.opts.seed_length, p.opts.max_seed_dist, p.opts.seed_offset)
+    kw["opts0"] = (p.opts0.seed_length, p.opts0.max_seed_dist, p.opts0.seed_offset)
+    s = lambda_b200.Searcher(ix, dom, "none", **kw)
+    h_gpu, st = s.search(res, qoffs)
+    h_cpu, st2 = o.search(p, res, qoffs)
+    assert sorted(s.m8(h_gpu, ids)) == sorted(o.m8(p, h_cpu, ids)), flags
+    for k in FUNNEL:
+        assert int(st[k]) == int(st2[k]), (k, flags)
+    s.close(); ix.close(); o.close()
