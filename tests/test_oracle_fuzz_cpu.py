@@ -89,3 +89,70 @@ def test_oracle_equals_live_reference_with_random_options(tmp_path, seed):
     ref = open(f"{tmp}/r.m8").read().splitlines(True)
     assert sorted(o.m8(p, hits, ids)) == sorted(ref), flags
     o.close()
+
+
+def random_case_other_modes(seed, tmp):
+    """bisulfite / BLASTX / TBLASTN / TBLASTX (seed % 4) with random options; returns what random_case() returns plus the
+    encoding of the query file (0 amino acids, 1 dna5)"""
+    rng = np.random.default_rng(seed)
+    mode = ["bs", "blastx", "tblastn", "tblastx"][seed % 4]
+    qa = enc = dom = 0
+    if mode == "bs":
+        db, offs = synth.nucl_db(3, 20000, seed=seed)
+        q, qo = synth.nucl_reads(db, offs, int(rng.integers(20, 60)), int(rng.integers(50, 150)), seed=seed + 1, bisulfite=True)
+        mk, se, dom, enc = "mkindexbs", "searchbs", 2, 1
+    elif mode == "blastx":
+        db, offs = synth.protein_db(int(rng.integers(100, 300)), seed=seed)
+        qp, qpo = synth.protein_queries(db, offs, int(rng.integers(10, 30)), int(rng.integers(40, 120)), seed=seed + 1,
+                                        sub=(0.1, 0.3))
+        q, qo = synth.coding_nucl_seqs(rng, qp, qpo, flank=(0, 12))
+        mk, se, qa, enc = "mkindexp", "searchp", 3, 1
+    else:
+        pdb, poffs = synth.protein_db(int(rng.integers(60, 150)), seed=seed)
+        db, offs = synth.coding_nucl_seqs(rng, pdb, poffs, flank=(0, 40))
+        qp, qpo = synth.protein_queries(pdb, poffs, int(rng.integers(10, 30)), int(rng.integers(40, 100)), seed=seed + 1,
+                                        sub=(0.1, 0.25))
+        mk, se = "mkindexp", "searchp"
+        if mode == "tblastn":
+            q, qo = qp, qpo
+        else:
+            q, qo = synth.coding_nucl_seqs(rng, qp, qpo, flank=(0, 9))
+            qa, enc = 3, 1
+    synth.write_fasta(f"{tmp}/db.fasta", db, offs, "S")
+    synth.write_fasta(f"{tmp}/q.fasta", q, qo, "Q")
+    subprocess.check_call([REF, mk, "-d", f"{tmp}/db.fasta", "-i", f"{tmp}/db.lba", "-v", "0"])
+    o = orc.Oracle(f"{tmp}/db.lba")
+    p = o.params(dom)
+    p.query_alph = qa
+    flags = []
+
+    def opt(flag, field, val):
+        flags.extend([flag, str(val)])
+        setattr(p, field, val)
+
+    if rng.random() < 0.5: opt("-e", "max_evalue", float(rng.choice([1e-5, 1.0, 10.0])))
+    if rng.random() < 0.4: opt("-n", "max_matches", int(rng.choice([1, 3, 50])))
+    if rng.random() < 0.3: opt("--percent-identity", "id_cutoff", int(rng.choice([50, 80])))
+    if rng.random() < 0.4: opt("--adaptive-seeding", "adaptive_seeding", int(rng.integers(0, 2)))
+    if rng.random() < 0.3: opt("--search0", "iterative_search", 0)
+    if rng.random() < 0.4: opt("--pre-scoring", "pre_scoring", int(rng.choice([1, 2, 3])))
+    if rng.random() < 0.4:
+        p.opts.seed_offset = int(rng.choice([2, 4, 7]))
+        flags.extend(["--seed-offset", str(p.opts.seed_offset)])
+    if rng.random() < 0.3:
+        p.opts.max_seed_dist = 0
+        flags.extend(["--seed-delta", "0"])
+    if dom == 0 and rng.random() < 0.3: opt("-s", "scoring_method", 80)
+    return dom, se, o, p, flags, enc
+
+
+@pytest.mark.parametrize("seed", list(range(100, 116)))
+def test_oracle_equals_live_reference_other_modes(tmp_path, seed):
+    tmp = str(tmp_path)
+    dom, se, o, p, flags, enc = random_case_other_modes(seed, tmp)
+    subprocess.run([REF, se, "-q", f"{tmp}/q.fasta", "-i", f"{tmp}/db.lba", "-o", f"{tmp}/r.m8", "-t", "1",
+                    "--version-to-outputfile", "0", "-v", "0", *flags], check=True, capture_output=True, text=True)
+    ids, data, qoffs = orc.read_fasta(f"{tmp}/q.fasta")
+    hits, st = o.search(p, orc.encode(data, enc), qoffs)
+    assert sorted(o.m8(p, hits, ids)) == sorted(open(f"{tmp}/r.m8").read().splitlines(True)), flags
+    o.close()

@@ -11,7 +11,7 @@ import pytest
 import lambda_b200
 import orc
 from cases import FUNNEL
-from test_oracle_fuzz_cpu import REF, random_case
+from test_oracle_fuzz_cpu import REF, random_case, random_case_other_modes
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.path.exists(REF), reason="reference binary (index builder) not built")]
 
@@ -28,6 +28,26 @@ def test_cuda_path_equals_oracle_with_random_options(tmp_path, seed):
                                      "gap_extend", "match", "mismatch")}
     kw["opts"] = (p.opts.seed_length, p.opts.max_seed_dist, p.opts.seed_offset)
     kw["opts0"] = (p.opts0.seed_length, p.opts0.max_seed_dist, p.opts0.seed_offset)
+    s = lambda_b200.Searcher(ix, dom, "none", **kw)
+    h_gpu, st = s.search(res, qoffs)
+    h_cpu, st2 = o.search(p, res, qoffs)
+    assert sorted(s.m8(h_gpu, ids)) == sorted(o.m8(p, h_cpu, ids)), flags
+    for k in FUNNEL:
+        assert int(st[k]) == int(st2[k]), (k, flags)
+    s.close(); ix.close(); o.close()
+
+
+@pytest.mark.parametrize("seed", list(range(100, 112)))
+def test_cuda_path_equals_oracle_other_modes(tmp_path, seed):
+    """bisulfite / BLASTX / TBLASTN / TBLASTX with random options"""
+    tmp = str(tmp_path)
+    dom, se, o, p, flags, enc = random_case_other_modes(seed, tmp)
+    ids, data, qoffs = lambda_b200.read_queries(f"{tmp}/q.fasta")
+    res = lambda_b200.encode(data, enc)
+    ix = lambda_b200.Index.load(f"{tmp}/db.lba")
+    kw = {k: getattr(p, k) for k in ("max_evalue", "max_matches", "id_cutoff", "adaptive_seeding", "iterative_search",
+                                     "pre_scoring", "scoring_method", "query_alph")}
+    kw["opts"] = (p.opts.seed_length, p.opts.max_seed_dist, p.opts.seed_offset)
     s = lambda_b200.Searcher(ix, dom, "none", **kw)
     h_gpu, st = s.search(res, qoffs)
     h_cpu, st2 = o.search(p, res, qoffs)
