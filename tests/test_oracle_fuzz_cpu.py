@@ -156,3 +156,58 @@ def test_oracle_equals_live_reference_other_modes(tmp_path, seed):
     hits, st = o.search(p, orc.encode(data, enc), qoffs)
     assert sorted(o.m8(p, hits, ids)) == sorted(open(f"{tmp}/r.m8").read().splitlines(True)), flags
     o.close()
+
+
+def random_case_with_n(seed, tmp):
+    """nucleotide (even seeds) / bisulfite (odd seeds) reads with 2-10 % 'N' and random seeding options"""
+    rng = np.random.default_rng(seed)
+    bs = seed % 2 == 1
+    db, offs = synth.nucl_db(3, 20000, seed=seed)
+    q, qo = synth.nucl_reads(db, offs, int(rng.integers(30, 80)), int(rng.integers(50, 180)), seed=seed + 1, bisulfite=bs)
+    q = q.copy()
+    q[rng.random(len(q)) < float(rng.choice([0.02, 0.05, 0.1]))] = ord("N")
+    mk, se, dom = ("mkindexbs", "searchbs", 2) if bs else ("mkindexn", "searchn", 1)
+    synth.write_fasta(f"{tmp}/db.fasta", db, offs, "S")
+    synth.write_fasta(f"{tmp}/q.fasta", q, qo, "Q")
+    subprocess.check_call([REF, mk, "-d", f"{tmp}/db.fasta", "-i", f"{tmp}/db.lba", "-v", "0"])
+    o = orc.Oracle(f"{tmp}/db.lba")
+    p = o.params(dom)
+    flags = []
+
+    def opt(flag, field, val):
+        flags.extend([flag, str(val)])
+        setattr(p, field, val)
+
+    if rng.random() < 0.4: opt("--adaptive-seeding", "adaptive_seeding", int(rng.integers(0, 2)))
+    if rng.random() < 0.3: opt("--search0", "iterative_search", 0)
+    if rng.random() < 0.5:
+        p.opts.seed_length = int(rng.choice([12, 16, 20, 24]))
+        flags.extend(["--seed-length", str(p.opts.seed_length)])
+    if rng.random() < 0.5:
+        p.opts0.seed_length = int(rng.choice([12, 15, 19]))
+        flags.extend(["--seed-length0", str(p.opts0.seed_length)])
+    if rng.random() < 0.4:
+        p.opts.seed_offset = int(rng.choice([2, 4, 7]))
+        flags.extend(["--seed-offset", str(p.opts.seed_offset)])
+    if rng.random() < 0.3:
+        p.opts.max_seed_dist = 0
+        flags.extend(["--seed-delta", "0"])
+    if rng.random() < 0.3: opt("-e", "max_evalue", float(rng.choice([1.0, 100.0])))
+    return dom, se, o, p, flags
+
+
+@pytest.mark.parametrize("seed", list(range(200, 212)))
+def test_oracle_equals_live_reference_with_n_and_random_seeding(tmp_path, seed):
+    """the per-read randomisation of 'N' (lambda_b200/csrc/n_random.hpp) under other seed lengths / offsets / distances,
+    with and without phase 1 and adaptive seeding; lines and the number of located seed hits"""
+    import re
+    tmp = str(tmp_path)
+    dom, se, o, p, flags = random_case_with_n(seed, tmp)
+    r = subprocess.run([REF, se, "-q", f"{tmp}/q.fasta", "-i", f"{tmp}/db.lba", "-o", f"{tmp}/r.m8", "-t", "1",
+                        "--version-to-outputfile", "0", "-v", "2", *flags], check=True, capture_output=True, text=True)
+    after = int(re.search(r"after Seeding\s+(\d+)", re.sub(r"\x1b\[[0-9;]*m", "", r.stdout)).group(1))
+    ids, data, qoffs = orc.read_fasta(f"{tmp}/q.fasta")
+    hits, st = o.search(p, orc.encode(data, 1), qoffs)
+    assert sorted(o.m8(p, hits, ids)) == sorted(open(f"{tmp}/r.m8").read().splitlines(True)), flags
+    assert int(st["hits_after_seeding"]) == after, flags
+    o.close()

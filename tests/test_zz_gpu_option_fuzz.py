@@ -11,7 +11,7 @@ import pytest
 import lambda_b200
 import orc
 from cases import FUNNEL
-from test_oracle_fuzz_cpu import REF, random_case, random_case_other_modes
+from test_oracle_fuzz_cpu import REF, random_case, random_case_other_modes, random_case_with_n
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.path.exists(REF), reason="reference binary (index builder) not built")]
 
@@ -48,6 +48,26 @@ def test_cuda_path_equals_oracle_other_modes(tmp_path, seed):
     kw = {k: getattr(p, k) for k in ("max_evalue", "max_matches", "id_cutoff", "adaptive_seeding", "iterative_search",
                                      "pre_scoring", "scoring_method", "query_alph")}
     kw["opts"] = (p.opts.seed_length, p.opts.max_seed_dist, p.opts.seed_offset)
+    s = lambda_b200.Searcher(ix, dom, "none", **kw)
+    h_gpu, st = s.search(res, qoffs)
+    h_cpu, st2 = o.search(p, res, qoffs)
+    assert sorted(s.m8(h_gpu, ids)) == sorted(o.m8(p, h_cpu, ids)), flags
+    for k in FUNNEL:
+        assert int(st[k]) == int(st2[k]), (k, flags)
+    s.close(); ix.close(); o.close()
+
+
+@pytest.mark.parametrize("seed", list(range(200, 208)))
+def test_cuda_path_equals_oracle_with_n_and_random_seeding(tmp_path, seed):
+    """'N' in nucleotide / bisulfite reads under random seeding options"""
+    tmp = str(tmp_path)
+    dom, se, o, p, flags = random_case_with_n(seed, tmp)
+    ids, data, qoffs = lambda_b200.read_queries(f"{tmp}/q.fasta")
+    res = lambda_b200.encode(data, 1)
+    ix = lambda_b200.Index.load(f"{tmp}/db.lba")
+    kw = {k: getattr(p, k) for k in ("max_evalue", "adaptive_seeding", "iterative_search")}
+    kw["opts"] = (p.opts.seed_length, p.opts.max_seed_dist, p.opts.seed_offset)
+    kw["opts0"] = (p.opts0.seed_length, p.opts0.max_seed_dist, p.opts0.seed_offset)
     s = lambda_b200.Searcher(ix, dom, "none", **kw)
     h_gpu, st = s.search(res, qoffs)
     h_cpu, st2 = o.search(p, res, qoffs)
