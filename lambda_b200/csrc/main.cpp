@@ -166,6 +166,7 @@ void parse(int argc, char ** argv, Options & o)
         else if (a == "-o" || a == "--output") o.output = need(i);
         else if (a == "-p" || a == "--profile") need(i);
         else if (a == "-a" || a == "--input-alphabet") o.inputAlphabet = need(i);
+        else if (a == "--lazy-query") (void)needBool(i); // accepted: the query file is always read completely, same results
         else if (a == "--output-columns") o.outputColumns = need(i);
         else if (a == "--replay-hits") o.replayHits = need(i);
         else if (a == "--sam-with-refheader") o.samWithRefHeader = needBool(i);

@@ -291,7 +291,6 @@ static inline int8_t const * matrixFor(Ctx const & c, uint32_t subjId)
 
 static bool seedLooksPromising(Ctx const & c, Queries const & q, lgpu_search_opts const & so, lgpu_match const & m)
 {
-    lgpu_index_desc const & d       = c.idx->d;
     int64_t                 qBegin  = m.qry_start;
     int64_t                 sBegin  = m.subj_start;
     uint64_t const          actual  = m.qry_end - m.qry_start;
@@ -546,7 +545,6 @@ static inline bool matchEq(lgpu_match const & a, lgpu_match const & b)
 
 static void widenAndMerge(Ctx const & c, Queries const & q, std::vector<lgpu_match> & ms, lgpu_stats & st)
 {
-    lgpu_index_desc const & d      = c.idx->d;
     size_t const            before = ms.size();
     for (lgpu_match & m : ms)
     {
@@ -753,7 +751,6 @@ static DpResult alignLocal(Scoring const & sc, int8_t const * M, bool bsStats, u
 static inline void windowOf(Ctx const & c, Queries const & q, lgpu_match const & m, uint8_t const *& qs, uint32_t & nq,
                             uint8_t const *& ts, uint32_t & nt)
 {
-    lgpu_index_desc const & d = c.idx->d;
     qs                        = q.trans.data() + q.offs[m.qry_id] + m.qry_start;
     nq                        = m.qry_end - m.qry_start;
     ts                        = c.idx->sbjSeq(m.subj_id) + m.subj_start;
