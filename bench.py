@@ -43,6 +43,9 @@ def log(*a):
 # ------------------------------------------------------------------------------------------------
 
 WORKLOADS = {
+    # BASELINE.json configs[0]: the reference's own CPU-runnable case (parity-sized; not a headline bench line)
+    "searchp_small": dict(domain="protein", dom=0, mk="mkindexp", search="searchp", n_seqs=50_000, n_queries=1_000,
+                          qlen=150, unit="aa", what="synthetic protein index (Li10), BLOSUM62"),
     # BASELINE.json configs[1]: the configuration the headline metric is quoted on
     "searchp": dict(domain="protein", dom=0, mk="mkindexp", search="searchp", n_seqs=5_000_000, n_queries=100_000,
                     qlen=300, unit="aa", what="synthetic protein index (Li10), BLOSUM62"),
