@@ -238,3 +238,23 @@ def test_oracle_equals_live_reference_with_n_full_seed_hamming(tmp_path, seed):
     assert sorted(o.m8(p, hits, ids)) == sorted(open(f"{tmp}/r.m8").read().splitlines(True)), flags
     assert int(st["hits_after_seeding"]) == after, flags
     o.close()
+
+
+@pytest.mark.parametrize("case,domain,cmd", [("prot_flat", 0, "searchp"), ("prot_family", 0, "searchp"), ("nucl", 1, "searchn"),
+                                             ("bisulfite", 2, "searchbs"), ("blastx", 0, "searchp"), ("tblastx", 0, "searchp")])
+def test_oracle_equals_live_reference_pairs_sensitive(golden_dir, tmp_path, case, domain, cmd):
+    """the one profile without committed golden files (-p pairs-sensitive: phase 1 off, seeds one symbol shorter than
+    `sensitive`), on the golden inputs against the live reference binary"""
+    from cases import query_alph, query_encoding
+    cwd = os.path.join(golden_dir, case)
+    out = str(tmp_path / "r.m8")
+    subprocess.run([REF, cmd, "-q", "q.fasta", "-i", "db.lba", "-o", out, "-t", "1", "--version-to-outputfile", "0", "-v", "0",
+                    "-p", "pairs-sensitive"], check=True, capture_output=True, cwd=cwd)
+    o = orc.Oracle(os.path.join(cwd, "db.lba"))
+    ids, data, offs = orc.read_fasta(os.path.join(cwd, "q.fasta"))
+    p = o.params(domain, "pairs-sensitive")
+    p.query_alph = query_alph(case)
+    hits, st = o.search(p, orc.encode(data, query_encoding(case, domain)), offs)
+    ref = open(out).read().splitlines(True)
+    assert len(ref) > 0 and sorted(o.m8(p, hits, ids)) == sorted(ref)
+    o.close()

@@ -75,3 +75,24 @@ def test_cuda_path_equals_oracle_with_n_and_random_seeding(tmp_path, seed):
     for k in FUNNEL:
         assert int(st[k]) == int(st2[k]), (k, flags)
     s.close(); ix.close(); o.close()
+
+
+@pytest.mark.parametrize("case,domain", [("prot_flat", 0), ("prot_family", 0), ("nucl", 1), ("bisulfite", 2), ("blastx", 0),
+                                         ("tblastx", 0)])
+def test_cuda_path_equals_oracle_pairs_sensitive(golden_dir, case, domain):
+    """-p pairs-sensitive (the one profile without committed golden files) on the golden inputs"""
+    from cases import query_alph, query_encoding
+    path = os.path.join(golden_dir, case, "db.lba")
+    ids, data, offs = lambda_b200.read_queries(os.path.join(golden_dir, case, "q.fasta"))
+    res = lambda_b200.encode(data, query_encoding(case, domain))
+    o = orc.Oracle(path)
+    ix = lambda_b200.Index.load(path)
+    s = lambda_b200.Searcher(ix, domain, "pairs-sensitive", query_alph=query_alph(case))
+    p = o.params(domain, "pairs-sensitive")
+    p.query_alph = query_alph(case)
+    h_gpu, st = s.search(res, offs)
+    h_cpu, st2 = o.search(p, res, offs)
+    assert sorted(s.m8(h_gpu, ids)) == sorted(o.m8(p, h_cpu, ids))
+    for k in FUNNEL:
+        assert int(st[k]) == int(st2[k]), k
+    s.close(); ix.close(); o.close()
