@@ -168,7 +168,15 @@ void parse(int argc, char ** argv, Options & o)
         else if (a == "-a" || a == "--input-alphabet") o.inputAlphabet = need(i);
         else if (a == "--lazy-query") (void)needBool(i); // accepted: the query file is always read completely, same results
         else if (a == "--output-columns") o.outputColumns = need(i);
-        else if (a == "--replay-hits") o.replayHits = need(i);
+        else if (a == "--replay-hits")
+        {
+            // test hook, not a search mode: only honoured when the test harness asks for it explicitly
+            o.replayHits = need(i);
+            char const * e = std::getenv("LAMBDA_B200_TEST_HOOKS");
+            if (!e || std::strcmp(e, "1"))
+                die("--replay-hits formats records computed elsewhere and performs no search; it is a hook for the output "
+                    "tests (set LAMBDA_B200_TEST_HOOKS=1)");
+        }
         else if (a == "--sam-with-refheader") o.samWithRefHeader = needBool(i);
         else if (a == "--sam-bam-seq")
         {

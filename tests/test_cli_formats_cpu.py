@@ -21,6 +21,7 @@ pytestmark = pytest.mark.skipif(not os.path.exists(CLI), reason="bin/lambda3_b20
 CASES = [("prot_flat", 0), ("prot_family", 0), ("prot_diverged", 0), ("nucl", 1), ("bisulfite", 2), ("blastx", 0),
          ("tblastn", 0), ("tblastx", 0)]
 SUB = ("searchp", "searchn", "searchbs")
+HOOK_ENV = dict(os.environ, LAMBDA_B200_TEST_HOOKS="1")  # --replay-hits is refused without it
 
 
 def write_hit_file(path, hits, stats, ops):
@@ -59,7 +60,7 @@ def run_cli(golden_dir, case, domain, hits, out, *extra, qfile="q.fasta"):
     if os.path.exists(os.path.join(cwd, out)):
         os.remove(os.path.join(cwd, out))
     subprocess.run([CLI, SUB[domain], "-q", qfile, "-i", "db.lba", "-o", out, "-t", "1", "-v", "0", "--replay-hits", hits,
-                    *extra], check=True, cwd=cwd, capture_output=True)
+                    *extra], check=True, cwd=cwd, capture_output=True, env=HOOK_ENV)
     return os.path.join(cwd, out)
 
 
@@ -98,11 +99,15 @@ def test_replay_refuses_foreign_hit_files(golden_dir, replay, tmp_path):
     hits = replay("prot_flat", 0)
     cwd = os.path.join(golden_dir, "nucl")  # other index, other queries
     r = subprocess.run([CLI, "searchn", "-q", "q.fasta", "-i", "db.lba", "-o", str(tmp_path / "x.m8"), "--replay-hits", hits],
-                       cwd=cwd, capture_output=True, text=True)
+                       cwd=cwd, capture_output=True, text=True, env=HOOK_ENV)
     bad = tmp_path / "bad.hits"
     bad.write_bytes(b"NOTHITS!" + b"\0" * 64)
     r2 = subprocess.run([CLI, "searchn", "-q", "q.fasta", "-i", "db.lba", "-o", str(tmp_path / "y.m8"), "--replay-hits", str(bad)],
-                        cwd=cwd, capture_output=True, text=True)
+                        cwd=cwd, capture_output=True, text=True, env=HOOK_ENV)
+    # and without the explicit opt-in the hook does not exist
+    r3 = subprocess.run([CLI, "searchn", "-q", "q.fasta", "-i", "db.lba", "-o", str(tmp_path / "z.m8"), "--replay-hits", hits],
+                        cwd=cwd, capture_output=True, text=True, env={k: v for k, v in os.environ.items() if k != "LAMBDA_B200_TEST_HOOKS"})
+    assert r3.returncode == 255 and "performs no search" in r3.stderr
     assert r2.returncode == 255 and "malformed hit file" in r2.stderr
     assert r.returncode in (0, 255)  # ids may happen to be in range; a mismatch must not crash
 
@@ -161,5 +166,5 @@ def test_taxonomy_columns_need_an_index_with_taxonomy(golden_dir, replay, tmp_pa
                        (["--output-columns", "std lcaid"], "does not contain taxonomic information")):
         r = subprocess.run([CLI, "searchp", "-q", "q.fasta", "-i", "db.lba", "-o", str(tmp_path / "x.m8"), "--replay-hits",
                             replay("prot_flat", 0), *extra], cwd=os.path.join(golden_dir, "prot_flat"), capture_output=True,
-                           text=True)
+                           text=True, env=HOOK_ENV)
         assert r.returncode == 255 and msg in r.stderr
