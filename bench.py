@@ -497,6 +497,22 @@ def main():
                 "traffic_source": traffic_src, "gcups": gcups_score,
                 "algorithmic": "10 int16 ops per DP cell x cells of the step / DP pass-1 stage time (CUDA events)"}
 
+    # DP pass 2 (trace fill + traceback) is the largest stage of the short-read workloads and HBM bound: algorithmic
+    # bytes = 3 B per cell written by the fill (16-bit W + two 4-bit gap deltas) over the stage time (CUDA events),
+    # against the measured copy bandwidth of this pool's B200s (MEASURED_PEAKS.json, else the 6.53 TB/s measured earlier)
+    hbm_peak, hbm_src = 6533.2, "fallback: MEASURED_PEAKS.json value recorded in DESIGN.md"
+    try:
+        hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        hbm_src = "MEASURED_PEAKS.json"
+    except Exception:  # noqa: BLE001 - file is driver-written and may be absent
+        pass
+    trace_gbs = 3.0 * cells_trace / args.steps / (ms_trace * 1e-3) / 1e9 if ms_trace > 0 else 0.0
+    roofline_trace = {"kernel": "swTraceDpxKernel<K> + tracebackDpxKernel (DP pass 2: fill + traceback)", "bound": "hbm",
+                      "achieved": trace_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": trace_gbs / hbm_peak,
+                      "peak_source": hbm_src, "traffic": None,
+                      "algorithmic": "3 B per DP cell of the trace pass / DP pass-2 stage time (CUDA events); the stage also "
+                                     "contains the traceback's scattered reads and the wavefront ramps"}
+
     # the other kernels of the step: bound and achieved fraction from the committed ncu capture (static evidence)
     other = None
     kp = os.path.join(ROOT, "profiles", f"r1_ncu_kernels_{wl}.json")
@@ -518,7 +534,7 @@ def main():
                                                             "hits_duplicate", "hits_failed_evalue", "hits_final",
                                                             "n_extensions_score", "n_extensions_trace")},
            "hits_per_step_all_ranks": total_hits,
-           "clocks": clocks, "roofline": roofline,
+           "clocks": clocks, "roofline": roofline, "roofline_trace": roofline_trace,
            "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": int(res.nbytes + qoffs.nbytes),
                    "d2h_bytes_per_step": int(len(hits) * HIT_DT.itemsize), "ms_per_step": wall_e2e / args.steps,
                    "device_ms_per_step": ms_e2e / args.steps, "timing": "host wall-clock around Searcher.search()"},
