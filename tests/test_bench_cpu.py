@@ -44,3 +44,77 @@ def test_clock_sampler_without_nvml():
     out = s.summary()
     assert set(out) >= {"sm_mhz", "sm_max_mhz", "reasons", "samples", "source"}
     assert out["samples"] == 0 or out["sm_mhz"] > 0
+
+
+FAKE_ENGINE = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, ROOT)
+import lambda_b200, bench
+from lambda_b200._abi import HIT_DT, STATS_DT
+
+torch.cuda.set_device = lambda *a, **k: None
+torch.cuda.synchronize = lambda *a, **k: None
+torch.Tensor.pin_memory = lambda self: self
+torch.Tensor.cuda = lambda self, *a, **k: self
+
+class FakeIndex:
+    device_bytes = 123456789
+    @staticmethod
+    def load(path, device=0, keep_ids=True):
+        return FakeIndex()
+
+class FakeSearcher:
+    def __init__(self, ix, domain, streams=None, **kw):
+        self.kw = kw
+    def search(self, res, offs, copy=True):
+        n = (offs.numel() if hasattr(offs, "numel") else len(offs)) - 1
+        hits = np.zeros(n, HIT_DT)
+        hits["q_id"] = np.arange(n)
+        hits["aln_len"] = 1
+        st = np.zeros(1, STATS_DT)[0]
+        for k, v in dict(ms_total=10.0, ms_seed=1.0, ms_sort_merge=0.5, ms_extend_score=5.0, ms_extend_trace=3.0, ms_h2d=0.1,
+                         ms_host=0.4, cells_score=4e9, cells_trace=3e8, kernel_launches=120, hits_final=n,
+                         n_extensions_score=5 * n, n_extensions_trace=n).items():
+            st[k] = v
+        return hits, st
+    def m8(self, hits, ids):
+        return ["fake\n" for _ in range(len(hits))]
+
+lambda_b200.Index = FakeIndex
+lambda_b200.Searcher = FakeSearcher
+sys.argv = ["bench.py"] + ARGS
+bench.main()
+"""
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="reference binary (oracle/_ref/lambda3) not built")
+@pytest.mark.parametrize("extra", [[], ["--band", "32"], ["--workload", "searchn", "--n-seqs", "3"]])
+def test_our_arm_assembles_the_contract_line_with_a_fake_engine(tmp_path, extra):
+    """everything of bench.py's own arm except the CUDA library: workload generation, timing loop, clocks, roofline
+    objects, cpu_baseline, JSON keys -- with Index / Searcher replaced by stand-ins returning fixed stage times"""
+    env = dict(os.environ, LAMBDA_B200_CACHE=str(tmp_path))
+    args = ["--n-seqs", "2000", "--n-queries", "300", "--steps", "2", "--warmup", "1", "--cpu-sample", "100"] + extra
+    code = f"ROOT = {ROOT!r}\nARGS = {args!r}\n" + FAKE_ENGINE
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "clocks", "roofline", "roofline_trace", "e2e", "gpu_launches"):
+        assert k in d, k
+    assert d["steps"] == 2 and d["warmup"] == 1 and d["n_gpus"] == 1 and d["vs_baseline"] is None
+    assert d["ms_per_step"] == pytest.approx(10.0) and d["value"] == pytest.approx(300 / 0.010)
+    assert d["gpu_launches"] == 240
+    rf = d["roofline"]
+    assert rf["achieved"] == pytest.approx(4e9 / 5e-3 / 1e9 * 10) and rf["frac"] == pytest.approx(rf["achieved"] / rf["peak"])
+    assert rf["traffic"] is None or isinstance(rf["traffic"], float)
+    rt = d["roofline_trace"]
+    assert rt["bound"] == "hbm" and rt["achieved"] == pytest.approx(3 * 3e8 / 3e-3 / 1e9) and 0 < rt["frac"] < 1
+    assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} and d["e2e"]["h2d_bytes_per_step"] > 0
+    assert "workload" in d["config"] and "model" not in d["config"]
+    if "--band" in extra:
+        assert d["config"]["window_band"] == 32 and d["parity_sample"] is None and "cpu_baseline" not in d
+    else:
+        assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["value"] > 0
+        assert d["parity_sample"]["identical"] is False  # the stand-in engine returns nonsense, of course
