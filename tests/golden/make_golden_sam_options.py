@@ -3,6 +3,7 @@
   <case>/opt_soft.sam  --sam-bam-clip soft --sam-bam-seq always --sam-with-refheader 1 + all non-taxonomy tags
   <case>/opt_tags.sam  hard clipping, --sam-bam-seq uniq, all non-taxonomy tags
   <case>/opt_tags.bam  all non-taxonomy tags, --sam-bam-seq never
+  <case>/opt_soft.bam  soft clipping, --sam-bam-seq always, all non-taxonomy tags
 made by the unmodified reference binary, run inside the case directory (-t 1, --version-to-outputfile 0)."""
 import gzip
 import os
@@ -19,6 +20,7 @@ VARIANTS = {
     "opt_soft.sam": ["--sam-bam-clip", "soft", "--sam-bam-seq", "always", "--sam-with-refheader", "1", "--sam-bam-tags", ALL_TAGS],
     "opt_tags.sam": ["--sam-bam-tags", ALL_TAGS],
     "opt_tags.bam": ["--sam-bam-tags", ALL_TAGS, "--sam-bam-seq", "never"],
+    "opt_soft.bam": ["--sam-bam-clip", "soft", "--sam-bam-seq", "always", "--sam-bam-tags", ALL_TAGS],
 }
 
 if __name__ == "__main__":

@@ -112,7 +112,7 @@ def test_replay_refuses_foreign_hit_files(golden_dir, replay, tmp_path):
     assert r.returncode in (0, 255)  # ids may happen to be in range; a mismatch must not crash
 
 
-@pytest.mark.parametrize("variant", ["opt_soft.sam", "opt_tags.sam", "opt_tags.bam"])
+@pytest.mark.parametrize("variant", ["opt_soft.sam", "opt_tags.sam", "opt_tags.bam", "opt_soft.bam"])
 @pytest.mark.parametrize("case,domain", CASES)
 def test_replayed_sam_dialect_options_equal_reference(golden_dir, replay, case, domain, variant):
     """--sam-bam-clip soft, --sam-bam-seq always|never, --sam-with-refheader, --sam-bam-tags with every non-taxonomy
