@@ -173,3 +173,25 @@ def test_lba_reader_parses_golden_index(golden_dir):
     d = lib.lgpu_lba_desc(h).contents
     assert (d.sigma, d.sigma_bits, d.block_bytes, d.planes_offset) == (5, 3, 48, 24)
     lib.lgpu_lba_close(h)
+
+
+def test_header_is_plain_c_and_the_example_client_runs(golden_dir, tmp_path):
+    """include/lambda_b200.h must be consumable from C (the boundary is a C ABI): examples/minimal.c is compiled as strict
+    C99 (-pedantic -Werror), linked against the library and run.  Without a device it must stop at lgpu_index_create with
+    the no-CPU-fallback error (exit code 3); with one it searches two queries."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no C compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "minimal")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(root, "include"),
+                    os.path.join(root, "examples", "minimal.c"), "-L" + os.path.join(root, "lambda_b200"), "-llambda_b200",
+                    "-Wl,-rpath," + os.path.join(root, "lambda_b200"), "-o", exe], check=True, capture_output=True, text=True)
+    r = subprocess.run([exe, os.path.join(golden_dir, "prot_flat", "db.lba")], capture_output=True, text=True)
+    assert "lambda_b200 ABI version 100" in r.stdout and "index: 500 subjects" in r.stdout
+    if _has_gpu():
+        assert r.returncode == 0 and r.stdout.strip().endswith("hits")
+    else:
+        assert r.returncode == 3 and "no CPU fallback" in r.stderr
