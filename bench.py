@@ -87,6 +87,19 @@ def ensure_index(wl, n_seqs, seed=1):
         t0 = time.time()
         while not os.path.exists(done):
             time.sleep(2)
+            try:
+                stale = time.time() - os.path.getmtime(lock) > 1800  # a killed builder leaves its lock behind
+            except OSError:
+                stale = False  # the builder just finished (or failed) and removed it
+            if stale:
+                log("stale lock: the previous builder died; taking over")
+                try:
+                    os.remove(lock)
+                except OSError:
+                    pass
+                return ensure_index(wl, n_seqs, seed)
+            if not os.path.exists(lock) and not os.path.exists(done):
+                return ensure_index(wl, n_seqs, seed)  # the builder failed: try ourselves (and report its error again)
             if time.time() - t0 > 3600:
                 raise RuntimeError("timed out waiting for the index build")
         return d
