@@ -195,3 +195,34 @@ def test_header_is_plain_c_and_the_example_client_runs(golden_dir, tmp_path):
         assert r.returncode == 0 and r.stdout.strip().endswith("hits")
     else:
         assert r.returncode == 3 and "no CPU fallback" in r.stderr
+
+
+def test_integer_score_thresholds_are_exact_boundaries():
+    """The device filter compares raw scores with one integer per query (a10 of SURVEY §8: e-value / bit-score test,
+    src/search_algo.hpp:1252-1281).  For random query lengths, database sizes, cut-offs and scoring schemes the integer
+    from lgpu_min_raw_score must be THE boundary of the double-precision tests: it passes, the score below it fails."""
+    lib = lambda_b200.load_library()
+    rng = np.random.default_rng(7)
+    cases = 0
+    for dom, tweaks in (("protein", [{}, {"scoring_method": 80, "gap_open": -10}, {"scoring_method": 45, "gap_open": -14, "gap_extend": -2}]),
+                        ("nucleotide", [{}, {"match": 3, "mismatch": -4}])):
+        for kw in tweaks:
+            for _ in range(60):
+                p = api.default_params(dom, **kw)
+                p.max_evalue = float(rng.choice([1e-30, 1e-10, 1e-3, 1e-2, 1.0, 10.0, 1000.0]))
+                p.min_bit_score = int(rng.choice([-1, -1, 30, 50, 200]))
+                qlen = int(rng.integers(20, 5000))
+                dblen = int(rng.choice([10_000, 955_200, 1_570_914_953, 200_000_000_000]))
+                mn = C.c_int32()
+                assert lib.lgpu_min_raw_score(C.byref(p), qlen, dblen, C.byref(mn)) == 0
+
+                def passes(score):
+                    e, b = C.c_double(), C.c_double()
+                    lib.lgpu_evalue(C.byref(p), score, qlen, dblen, C.byref(e))
+                    lib.lgpu_bit_score(C.byref(p), score, C.byref(b))
+                    return e.value <= p.max_evalue and (p.min_bit_score < 0 or b.value >= p.min_bit_score)
+                assert passes(mn.value), (dom, kw, qlen, dblen, p.max_evalue, p.min_bit_score, mn.value)
+                if mn.value > 1:
+                    assert not passes(mn.value - 1), (dom, kw, qlen, dblen, p.max_evalue, p.min_bit_score, mn.value)
+                cases += 1
+    assert cases == 300
