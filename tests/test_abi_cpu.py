@@ -226,3 +226,43 @@ def test_integer_score_thresholds_are_exact_boundaries():
                     assert not passes(mn.value - 1), (dom, kw, qlen, dblen, p.max_evalue, p.min_bit_score, mn.value)
                 cases += 1
     assert cases == 300
+
+
+def test_lba_reader_survives_truncated_and_corrupted_files(golden_dir, tmp_path):
+    """the .lba parser works on an untrusted mmap: every truncation must end in LGPU_ERR_IO and random corruption of the
+    length fields must never crash it (run in a child process so that a crash is a test failure, not a dead pytest)"""
+    import subprocess
+    import sys
+    code = r"""
+import ctypes as C, os, sys, numpy as np
+sys.path.insert(0, %r)
+import lambda_b200
+lib = lambda_b200.load_library()
+src = open(%r, 'rb').read()
+tmp = %r
+rng = np.random.default_rng(11)
+vp = C.c_void_p
+def try_open(data):
+    path = os.path.join(tmp, 'x.lba')
+    open(path, 'wb').write(data)
+    h = vp()
+    rc = lib.lgpu_lba_open(C.byref(h), path.encode())
+    if rc == 0:
+        lib.lgpu_lba_close(h)
+    return rc
+assert try_open(src) == 0
+cuts = sorted(set([0, 1, 7, 8, 12, 13, 21, len(src) - 1] + [int(x) for x in rng.integers(0, len(src), 40)]))
+for n in cuts:
+    assert try_open(src[:n]) == -2, n          # LGPU_ERR_IO
+assert try_open(src + b'xx') == -2              # trailing bytes
+bad = 0
+for _ in range(60):
+    d = bytearray(src)
+    pos = int(rng.integers(0, min(len(d), 4096)))   # the header region holds the vector lengths
+    d[pos] ^= 1 << int(rng.integers(0, 8))
+    if try_open(bytes(d)) != 0:
+        bad += 1
+print('ok', bad)
+""" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.join(golden_dir, "prot_flat", "db.lba"), str(tmp_path))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), (r.returncode, r.stdout[-500:], r.stderr[-1500:])
