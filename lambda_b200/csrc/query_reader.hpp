@@ -107,7 +107,10 @@ public:
                     throw std::runtime_error("error while reading " + path_ + ": " + (msg ? msg : "zlib error"));
                 }
                 if (n == 0)
+                {
+                    checkCleanEnd();
                     break;
+                }
                 pos_ = 0;
                 len_ = static_cast<size_t>(n);
             }
@@ -132,8 +135,13 @@ public:
         if (pos_ == len_)
         {
             int const n = gzread(f_, buf_.data(), static_cast<unsigned int>(buf_.size()));
+            if (n < 0)
+                checkCleanEnd();
             if (n <= 0)
+            {
+                checkCleanEnd();
                 return -1;
+            }
             pos_ = 0;
             len_ = static_cast<size_t>(n);
         }
@@ -143,6 +151,15 @@ public:
     size_t lineNo() const { return lineNo_; }
 
 private:
+    // end of data: a compressed stream that stops in the middle (truncated download) is an error, not a short file
+    void checkCleanEnd()
+    {
+        int          err = Z_OK;
+        char const * msg = gzerror(f_, &err);
+        if (err != Z_OK && err != Z_STREAM_END)
+            throw std::runtime_error("error while reading " + path_ + ": " + (msg && *msg ? msg : "truncated or corrupt compressed stream"));
+    }
+
     std::string path_;
     gzFile      f_ = nullptr;
     std::string buf_;

@@ -119,3 +119,34 @@ def test_malformed_input_fails_loudly(tmp_path, name, content, msg):
 def test_missing_file(tmp_path):
     rc, _, err = dumpq(tmp_path / "nope.fasta")
     assert rc == 255 and "Could not open file" in err
+
+
+def test_reader_never_crashes_on_garbage(tmp_path):
+    """random bytes, random cuts of valid files, corrupted gzip streams: a clean error (255) or a parse, never a crash"""
+    import numpy as np
+    rng = np.random.default_rng(5)
+    good_fa = b"".join(b">s%d x\nACGTNNACGT\nACG\n" % i for i in range(50))
+    good_fq = b"".join(b"@r%d\nACGTN\n+\nIIIII\n" % i for i in range(50))
+    blobs = []
+    for _ in range(15):
+        blobs.append(("x.fa", rng.integers(0, 256, int(rng.integers(0, 400)), dtype=np.uint8).tobytes()))
+        blobs.append(("x.fq", rng.integers(0, 256, int(rng.integers(0, 400)), dtype=np.uint8).tobytes()))
+        blobs.append(("x.fa", good_fa[: int(rng.integers(0, len(good_fa)))]))
+        blobs.append(("x.fq", good_fq[: int(rng.integers(0, len(good_fq)))]))
+        z = bytearray(gzip.compress(good_fa))
+        z[int(rng.integers(10, len(z)))] ^= 0xFF
+        blobs.append(("x.fa.gz", bytes(z)))
+        blobs.append(("x.fq.gz", gzip.compress(good_fq)[: int(rng.integers(1, 60))]))
+    for name, data in blobs:
+        p = tmp_path / name
+        p.write_bytes(data)
+        rc, out, err = dumpq(p, "-a", "dna5")
+        assert rc in (0, 255), (name, rc, err[-300:])
+        if rc == 255:
+            assert err.startswith("ERROR: ")
+    # a gzip stream that stops in the middle is an error, not a shorter file
+    whole = gzip.compress(good_fq)
+    p = tmp_path / "cut.fq.gz"
+    p.write_bytes(whole[: len(whole) - 12])
+    rc, out, err = dumpq(p, "-a", "dna5")
+    assert rc == 255 and "cut.fq.gz" in err
