@@ -345,6 +345,7 @@ int          lgpu_tabular_column(char const * option_label);
 char const * lgpu_tabular_column_name(uint32_t column); /* the option label of a column, NULL if out of range */
 char const * lgpu_tabular_column_label(uint32_t column);
 int          lgpu_tabular_column_supported(uint32_t column);
+int          lgpu_tabular_column_implemented(uint32_t column); /* BlastMatchField::implemented: 0 = prints "n/i" */
 int          lgpu_format_tabular(lgpu_params const *, lgpu_hit const *, char const * q_id, char const * s_id,
                                  uint32_t const * columns, size_t n_columns, char * buf, size_t cap);
 

@@ -78,6 +78,7 @@ def load_library():
     lib.lgpu_tabular_column_name.argtypes = [C.c_uint32]
     lib.lgpu_tabular_column_name.restype = C.c_char_p
     lib.lgpu_tabular_column_supported.argtypes = [C.c_uint32]
+    lib.lgpu_tabular_column_implemented.argtypes = [C.c_uint32]
     _lib = lib
     return lib
 

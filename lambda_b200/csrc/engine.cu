@@ -2206,6 +2206,8 @@ int lgpu_tabular_column_supported(uint32_t column)
            column != TAB_LCA_TAX_ID;
 }
 
+int lgpu_tabular_column_implemented(uint32_t column) { return tabColumnImplemented(column) ? 1 : 0; }
+
 int lgpu_format_tabular(lgpu_params const * p, lgpu_hit const * h, char const * qId, char const * sId, uint32_t const * columns,
                         size_t nColumns, char * buf, size_t cap)
 {

@@ -132,6 +132,16 @@ inline char const * const * tabColumnLabels()
       "% subject coverage", "% hsp coverage", "lca id", "lca tax id"};
     return l;
 }
+// BlastMatchField::implemented (SQ/blast/blast_tabular.h:591-642): the columns whose value the writer prints; the
+// others print "n/i"
+inline bool tabColumnImplemented(uint32_t c)
+{
+    static bool const impl[kNumTabColumns] = {true,  true,  false, true,  false, true,  true,  false, false, false, true,  false,
+                                              true,  true,  true,  true,  true,  true,  false, false, true,  true,  true,  true,
+                                              true,  true,  true,  true,  true,  true,  true,  true,  true,  true,  false, true,
+                                              false, false, false, false, false, false, false, false, false, true,  true};
+    return c < static_cast<uint32_t>(kNumTabColumns) && impl[c];
+}
 enum TabColumn : uint32_t
 {
     TAB_STD = 0, TAB_Q_SEQ_ID = 1, TAB_Q_ACC = 3, TAB_Q_LEN = 5, TAB_S_SEQ_ID = 6, TAB_S_ACC = 10, TAB_S_ALLACC = 12,

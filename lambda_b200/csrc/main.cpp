@@ -293,8 +293,7 @@ void parse(int argc, char ** argv, Options & o)
         std::puts("Please specify the columns in this format -oc 'column1 column2', i.e. space-separated and enclosed in "
                   "single quotes.\nThe specifiers are the same as in NCBI Blast, currently the following are supported:");
         for (uint32_t c = 0; lgpu_tabular_column_name(c); ++c)
-            if (lgpu_tabular_column_supported(c) || !std::strcmp(lgpu_tabular_column_name(c), "staxids") ||
-                !std::strcmp(lgpu_tabular_column_name(c), "lcaid") || !std::strcmp(lgpu_tabular_column_name(c), "lcataxid"))
+            if (lgpu_tabular_column_implemented(c)) // like the reference: only the columns with a value
                 std::printf("\t%s%s%s\n", lgpu_tabular_column_name(c), std::strlen(lgpu_tabular_column_name(c)) >= 8 ? "\t" : "\t\t",
                             lgpu_tabular_column_label(c));
         std::exit(0);
