@@ -16,6 +16,11 @@ for wl in searchn searchbs; do
   ( time timeout 600 python bench.py --workload $wl --steps 3 --warmup 3 ) > gpurun_out/bench_$wl.json 2> gpurun_out/bench_$wl.log
   python -c "import json; d=json.load(open('gpurun_out/bench_$wl.json')); print('$wl', d['ms_per_step'], d['stage_ms'], d['parity_sample'])"
 done
+# 2b. never measured on the short-read workloads: the checkpoint trace path (0.7 B/cell instead of 3)
+for wl in searchn searchbs; do
+  LAMBDA_B200_TRACE=ckpt timeout 300 python bench.py --workload $wl --steps 3 --warmup 3 --no-cpu-baseline 2> gpurun_out/ckpt_$wl.log | \
+    python -c "import sys, json; d=json.loads(sys.stdin.read()); print('$wl ckpt', d['ms_per_step'], d['stage_ms'])"
+done
 # 3. per-kernel times of one serial searchn step (fill vs traceback share of the trace stage)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches_searchn.csv \
     python tools/profile_run.py searchn 1 > gpurun_out/ncu_searchn.log 2>&1
