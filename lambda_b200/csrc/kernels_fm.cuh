@@ -1227,7 +1227,9 @@ __global__ void __launch_bounds__(128) seedWarpKernel(SeedParams P)
 // mismatch tree are evaluated 32 at a time and handed to seedConsumeChunkSpec in leaf order.
 constexpr int kSpecWarps = 4;
 
-__global__ void __launch_bounds__(32 * kSpecWarps) seedSpecKernel(SeedParams P)
+// 5 resident blocks (20 warps) per SM: caps the kernel at 96 registers -- what it used before the 'N' handling was added
+// to every symbol read (116 without the bound = one block less per SM); no spills either way (ptxas -v)
+__global__ void __launch_bounds__(32 * kSpecWarps, 5) seedSpecKernel(SeedParams P)
 {
     __shared__ signed char sM[2048];
     __shared__ SpecScratch sS[kSpecWarps];
