@@ -38,6 +38,16 @@ def log(*a):
     print("[bench]", *a, file=sys.stderr, flush=True)
 
 
+def kernel_sources_sha():
+    """identifies the kernel sources a build / an ncu capture belongs to"""
+    h = hashlib.sha1()
+    src = os.path.join(ROOT, "lambda_b200", "csrc")
+    for fn in sorted(os.listdir(src)):
+        if fn.endswith((".cuh", ".cu")):
+            h.update(open(os.path.join(src, fn), "rb").read())
+    return h.hexdigest()[:12]
+
+
 # ------------------------------------------------------------------------------------------------
 # workload
 # ------------------------------------------------------------------------------------------------
@@ -322,6 +332,11 @@ def main():
     ap.add_argument("--qlen", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries for the CPU baseline (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every rank searches its own --n-queries queries; strong: the ranks split ONE batch of "
+                         "--n-queries queries (the reference's only parallel axis, src/search.cpp:379-385)")
+    ap.add_argument("--parity-queries", type=int, default=4000,
+                    help="N > 1: every rank checks the first this-many queries of its shard against the reference binary")
     ap.add_argument("--band", type=int, default=0,
                     help="lgpu_params.window_band: 0 = the reference's rule floor(sqrt(qlen))+1 (parity mode); 16/32/64 = the "
                          "band sweep of BASELINE configs[3] (non-parity: the reference binary has no such option)")
@@ -339,10 +354,14 @@ def main():
     if world > 1 and args.gpus != world:
         log(f"--gpus {args.gpus} != WORLD_SIZE {world}; using WORLD_SIZE")
     n_gpus = world
+    strong = args.scaling == "strong" and n_gpus > 1
     workload = (f"{W['search']}: {args.n_queries}x{qdesc} synthetic queries vs {args.n_seqs}-seq {W['what']}, "
                 f"default profile")
-    cfg = {"workload": workload, "queries_per_gpu": args.n_queries, "query_len": args.qlen, "index_seqs": args.n_seqs,
-           "profile": "none", "sharding": f"queries x{n_gpus}, index replicated", "streams_per_gpu": 3,
+    cfg = {"workload": workload, "queries_per_gpu": args.n_queries // n_gpus if strong else args.n_queries,
+           "queries_total": args.n_queries if strong else args.n_queries * n_gpus,
+           "query_len": args.qlen, "index_seqs": args.n_seqs,
+           "profile": "none", "sharding": (f"one batch of {args.n_queries} queries split over {n_gpus} ranks" if strong else
+                                           f"queries x{n_gpus}") + ", index replicated", "streams_per_gpu": 3,
            "l2_policy": "inputs larger than L2 (index and per-step trace/DP working sets are GBs)",
            "window_band": args.band if args.band else "reference rule floor(sqrt(qlen))+1"}
     cores = os.cpu_count() or 1
@@ -364,7 +383,7 @@ def main():
         sample = f"first {n_sample} of the {args.n_queries} queries per step, lambda3 {wl} -t {cores}, search phase"
         emit(({"impl": "reference", "metric": f"{wl}_query_seqs_per_s", "value": value, "unit": "queries/s",
                           "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
-                          "ms_per_step": 1e3 * sum(walls) / len(walls), "higher_is_better": True, "scaling": "weak",
+                          "ms_per_step": 1e3 * sum(walls) / len(walls), "higher_is_better": True, "scaling": args.scaling,
                           "vs_baseline": None, "dtype": "int16", "data": "synthetic", "config": cfg,
                           "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "reference",
                                            "sample": sample},
@@ -383,12 +402,26 @@ def main():
     if world > 1:
         dist.barrier()
     t0 = time.time()
-    ix = lambda_b200.Index.load(os.path.join(d, "db.lba"), device=local_rank, keep_ids=(rank == 0))
+    ix = lambda_b200.Index.load(os.path.join(d, "db.lba"), device=local_rank, keep_ids=False)
+
+    class _SyntheticIds:  # the benchmark database is written with ids S0, S1, ... (ensure_index)
+        def __getitem__(self, i):
+            return f"S{i}"
+    ix.subject_ids = _SyntheticIds()
     log(f"rank {rank}: index in HBM: {ix.device_bytes / 1e9:.2f} GB, load {time.time() - t0:.1f}s")
     kw = {"window_band": args.band} if args.band else {}
     s = lambda_b200.Searcher(ix, W["domain"], **kw)              # default: 3 sub-batches in flight
     s_serial = lambda_b200.Searcher(ix, W["domain"], streams=1, **kw)  # strictly serial: per-kernel timing / roofline
-    q_ascii, qoffs = make_queries(wl, d, args.n_queries, args.qlen, seed=1000 + rank)
+    if strong:
+        # ONE batch for the whole job (the same on every rank); this rank searches its contiguous shard
+        from lambda_b200.dist import shard_queries
+        q_ascii, qoffs = make_queries(wl, d, args.n_queries, args.qlen, seed=1000)
+        q_ascii, qoffs, first_query = shard_queries(q_ascii, qoffs, rank, world)
+        q_ascii = np.ascontiguousarray(q_ascii)
+    else:
+        q_ascii, qoffs = make_queries(wl, d, args.n_queries, args.qlen, seed=1000 + rank)
+        first_query = rank * args.n_queries
+    n_local = len(qoffs) - 1
     res = lambda_b200.encode(q_ascii, W["dom"])
     h_res = torch.from_numpy(res).pin_memory()
     h_offs = torch.from_numpy(qoffs.view(np.int64)).pin_memory()
@@ -396,11 +429,10 @@ def main():
     d_offs = h_offs.cuda()
     pin_res, pin_offs = h_res.numpy(), h_offs.numpy().view(np.uint64)  # numpy views of the pinned buffers
 
-    from lambda_b200.dist import all_gather_hits
-
-    def gather_hits(hits):
-        """the path's only collective: all ranks exchange their hit records (NCCL all-gather)"""
-        return all_gather_hits(hits, first_query=rank * args.n_queries, to_host=False)[1]
+    # The path's only collective: all ranks exchange their hit records GPU to GPU, straight from the library's device
+    # buffer, with one fixed-capacity NCCL all-gather on a side stream (lambda_b200/dist.py DeviceHitGather).
+    from lambda_b200.dist import DeviceHitGather
+    gather = DeviceHitGather(max(2 * n_local, 1024)) if world > 1 else None
 
     def step(resident, searcher=None):
         searcher = searcher or s
@@ -410,40 +442,51 @@ def main():
             # host buffers (pinned): H2D of the queries + D2H of the hit records happen inside the call;
             # copy=False returns a view of the library's result buffer (valid until the next call)
             hits, st = searcher.search(pin_res, pin_offs, copy=False)
-        g_ms = 0.0
-        if world > 1:
-            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            g0.record()
-            total = gather_hits(hits)
-            g1.record()
-            g1.synchronize()
-            g_ms = g0.elapsed_time(g1)
-        else:
-            total = len(hits)
-        return hits, st, total, g_ms
+        if gather is not None:
+            gather.start(searcher, first_query)  # returns at once; overlaps the next step's search
+        return hits, st
 
     def timed(resident, k, searcher=None):
         """K steps.  Device time = CUDA events recorded by the library on ITS stream around every
-        lgpu_search_batch call (ms_total; torch.cuda.Event only sees torch's stream) + torch events around
-        the NCCL gather; max over ranks.  Host wall-clock around the same region is reported next to it."""
+        lgpu_search_batch call (ms_total; torch.cuda.Event only sees torch's stream) + the exposed tail of the
+        last step's gather (torch events on the gather's side stream; the gathers of the earlier steps run
+        underneath the next search); max over ranks.  Host wall-clock around the same region is reported next to it."""
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        acc, ms = None, 0.0
-        for _ in range(k):
-            hits, st, total, g_ms = step(resident, searcher)
-            ms += float(st["ms_total"]) + g_ms
+        acc, ms, per_step, g_ms = None, 0.0, [], []
+        total = 0
+        for i in range(k):
+            hits, st = step(resident, searcher)
+            ms += float(st["ms_total"])
+            per_step.append(float(st["ms_total"]))
             acc = st.copy() if acc is None else _acc(acc, st)
+            if gather is not None and i + 1 < k:
+                pass  # the gather of this step is waited for by the next start()
+        if gather is not None:
+            tw = time.perf_counter()
+            total = gather.finish()
+            ms += gather.last_ms  # device time of the last gather (events on its stream): the only one not hidden
+            g_ms.append(gather.last_ms)
+            del tw
+        else:
+            total = len(hits)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         wall = (time.perf_counter() - t0) * 1e3
+        mine_ms = ms
         if world > 1:
             t = torch.tensor([ms, wall], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tmin = torch.tensor([mine_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
             ms, wall = float(t[0]), float(t[1])
-        return ms, wall, acc, hits, total
+            spread = (float(tmin[0]) / k, ms / k)
+        else:
+            spread = (ms / k, ms / k)
+        return ms, wall, acc, hits, total, {"rank_ms_per_step_min_max": spread, "gather_device_ms_last": g_ms[-1] if g_ms else 0.0}
 
     def _acc(a, b):
         for n in a.dtype.names:
@@ -457,15 +500,16 @@ def main():
     if sampler:
         sampler.start()
         sampler.begin()
-    ms_res, wall_res, st_pipe, hits, total_hits = timed(True, args.steps)
-    ms_e2e, wall_e2e, st_e2e, _, _ = timed(False, args.steps)
+    ms_res, wall_res, st_pipe, hits, total_hits, tinfo = timed(True, args.steps)
+    hits = hits.copy()
+    ms_e2e, wall_e2e, st_e2e, _, _, tinfo_e2e = timed(False, args.steps)
     # same steps again strictly serial (one stream): per-stage / per-kernel device times for the roofline
-    ms_serial, _, st, _, _ = timed(True, args.steps, s_serial)
+    ms_serial, _, st, _, _, _ = timed(True, args.steps, s_serial)
     if sampler:
         sampler.end()
     clocks = sampler.summary() if sampler else None
 
-    nq_total = args.n_queries * n_gpus * args.steps
+    nq_total = (args.n_queries if strong else args.n_queries * n_gpus) * args.steps
     value = nq_total / (ms_res * 1e-3)
     # end to end = host wall-clock around the public API call (host buffers in, host records out)
     e2e = nq_total / (wall_e2e * 1e-3)
@@ -476,6 +520,28 @@ def main():
         cells_score_all, cells_trace_all = float(t[0]), float(t[1])
     else:
         cells_score_all, cells_trace_all = cells_score, cells_trace
+    # parity: our tabular lines against the unmodified reference run on this box, on a sample of THIS rank's queries
+    parity, ref_run = None, None
+    if not args.band and os.path.exists(REF) and not (args.no_cpu_baseline and n_gpus == 1):
+        if n_gpus == 1:
+            n_sample = args.cpu_sample or min(n_local, max(2000, 2000 * cores))
+            threads = cores
+        else:
+            n_sample = min(n_local, args.parity_queries)
+            threads = max(1, cores // world)
+        qps, wall, phase, ref_lines = run_reference_search(wl, d, q_ascii, qoffs, n_sample, threads, "cpu")
+        ids = [f"Q{i}" for i in range(n_sample)]
+        mine = sorted(s.m8(hits[hits["q_id"] < n_sample], ids))
+        same = mine == sorted(ref_lines)
+        ref_run = (qps, wall, phase, n_sample, threads)
+        parity = {"queries": n_sample, "reference_lines": len(ref_lines), "our_lines": len(mine), "identical": bool(same)}
+        if world > 1:
+            t = torch.tensor([1 if same else 0, len(ref_lines), len(mine)], device="cuda", dtype=torch.int64)
+            tmin = t.clone()
+            dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+            dist.all_reduce(t)
+            parity = {"queries_per_rank": n_sample, "ranks": world, "reference_lines": int(t[1]), "our_lines": int(t[2]),
+                      "identical": bool(int(tmin[0]) == 1), "ranks_identical": int(t[0])}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -494,51 +560,65 @@ def main():
     ms_trace = float(st["ms_extend_trace"]) / args.steps
     gcups_trace = cells_trace / args.steps / (ms_trace * 1e-3) / 1e9 if ms_trace > 0 else 0.0
     achieved = gcups_score * 10.0  # 10 int16 ops per cell update (5 add + 5 max), SURVEY §8(d)
-    # DRAM traffic of that kernel from the committed `ncu --set full` capture of this workload (per launch)
-    traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", f"r1_ncu_score_{wl}.json")
+    # DRAM traffic of that kernel from the committed `ncu --set full` capture of this workload (per launch).  A capture
+    # is only used if it was taken from the kernel sources this run was built from (sha of csrc/*.cuh + engine.cu).
+    ksha = kernel_sources_sha()
+    cap, cap_note = None, "no capture committed for this workload"
+    tp = os.path.join(ROOT, "profiles", f"r2_ncu_kernels_{wl}.json")
     if os.path.exists(tp):
         try:
-            t = json.load(open(tp))
-            traffic = float(t["dram_bytes_read"] + t["dram_bytes_write"])  # bytes per launch (dram__bytes_read + write)
-            traffic_src = os.path.relpath(tp, ROOT)
-        except Exception:
-            traffic = None
-    roofline = {"kernel": "swScoreDpxKernel<T,K> (DP pass 1, packed int16 DPX)", "bound": "int16-alu", "achieved": achieved,
+            cap = json.load(open(tp))
+            if cap.get("kernel_sources_sha") != ksha:
+                cap_note = (f"stale: {os.path.relpath(tp, ROOT)} was captured at kernel sources {cap.get('kernel_sources_sha')} "
+                            f"(git {cap.get('git')}), this run is {ksha}")
+                cap = None
+            else:
+                cap_note = f"{os.path.relpath(tp, ROOT)} (git {cap.get('git')})"
+        except Exception as e:  # noqa: BLE001
+            cap, cap_note = None, f"unreadable capture: {e}"
+
+    traffic = None
+    score_name = [k for k in (cap or {}).get("kernels", []) if k["name"].startswith("swDpxKernel") and not k.get("trace")]
+    if score_name:
+        traffic = float(score_name[0]["dram_bytes"])
+    roofline = {"kernel": "swDpxKernel<T,K,PRIV,false> (DP pass 1, packed int16 DPX)", "bound": "int16-alu", "achieved": achieved,
                 "peak": peak_gops, "unit": "Gop/s (int16)", "frac": (achieved / peak_gops) if peak_gops else None,
                 "peak_source": peak_src, "traffic": traffic, "traffic_unit": "bytes per launch (DRAM read + write, ncu --set full)",
-                "traffic_source": traffic_src, "gcups": gcups_score,
+                "traffic_source": cap_note, "gcups": gcups_score,
                 "algorithmic": "10 int16 ops per DP cell x cells of the step / DP pass-1 stage time (CUDA events)"}
 
-    # DP pass 2 (trace fill + traceback) is the largest stage of the short-read workloads and HBM bound: algorithmic
-    # bytes = 3 B per cell written by the fill (16-bit W + two 4-bit gap deltas) over the stage time (CUDA events),
-    # against the measured copy bandwidth of this pool's B200s (MEASURED_PEAKS.json, else the 6.53 TB/s measured earlier)
+    # DP pass 2 = the same packed recurrence + ONE byte per cell (H mod 256) written to HBM + the traceback.  Two views:
+    # against the int16 ALU peak (10 ops per cell like pass 1: the fill is ALU bound now) and against the HBM copy peak
+    # with the reference's own 1 B per cell (SQ/align/dp_profile.h:122) as algorithmic bytes.
     hbm_peak, hbm_src = 6533.2, "fallback: MEASURED_PEAKS.json value recorded in DESIGN.md"
     try:
         hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
         hbm_src = "MEASURED_PEAKS.json"
     except Exception:  # noqa: BLE001 - file is driver-written and may be absent
         pass
-    trace_gbs = 3.0 * cells_trace / args.steps / (ms_trace * 1e-3) / 1e9 if ms_trace > 0 else 0.0
-    roofline_trace = {"kernel": "swTraceDpxKernel<K> + tracebackDpxKernel (DP pass 2: fill + traceback)", "bound": "hbm",
-                      "achieved": trace_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": trace_gbs / hbm_peak,
-                      "peak_source": hbm_src, "traffic": None,
-                      "algorithmic": "3 B per DP cell of the trace pass / DP pass-2 stage time (CUDA events); the stage also "
-                                     "contains the traceback's scattered reads and the wavefront ramps"}
-
-    # the other kernels of the step: bound and achieved fraction from the committed ncu capture (static evidence)
-    other = None
-    kp = os.path.join(ROOT, "profiles", f"r1_ncu_kernels_{wl}.json")
-    if os.path.exists(kp):
-        try:
-            other = json.load(open(kp))
-        except Exception:
-            other = None
+    trace_gbs = 1.0 * cells_trace / args.steps / (ms_trace * 1e-3) / 1e9 if ms_trace > 0 else 0.0
+    trace_traffic = [k for k in (cap or {}).get("kernels", []) if k["name"].startswith("swDpxKernel") and k.get("trace")]
+    roofline_trace = {"kernel": "swDpxKernel<T,K,true,true> + tracebackResKernel (DP pass 2: fill + traceback)", "bound": "int16-alu",
+                      "achieved": gcups_trace * 10.0, "peak": peak_gops, "unit": "Gop/s (int16)",
+                      "frac": (gcups_trace * 10.0 / peak_gops) if peak_gops else None, "gcups": gcups_trace,
+                      "hbm": {"achieved": trace_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": trace_gbs / hbm_peak,
+                              "peak_source": hbm_src, "algorithmic": "1 B per DP cell (residue plane; the reference's trace "
+                                                                     "matrix is 1 B per cell too) / DP pass-2 stage time"},
+                      "traffic": float(trace_traffic[0]["dram_bytes"]) if trace_traffic else None,
+                      "algorithmic": "10 int16 ops per DP cell x cells of the trace pass / DP pass-2 stage time (CUDA events; the "
+                                     "stage also contains the classification, the traceback and the wavefront ramps)"}
+    other = cap
 
     out = {"metric": f"{wl}_query_seqs_per_s", "value": value, "unit": "queries/s", "n_gpus": n_gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "wall_ms_per_step": wall_res / args.steps,
            "ms_per_step_serial_1_stream": ms_serial / args.steps,
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic", "config": cfg,
+           "higher_is_better": True, "scaling": args.scaling if n_gpus > 1 else "weak", "vs_baseline": None, "dtype": "int16",
+           "data": "synthetic", "config": cfg,
+           "gather": ({"what": "one fixed-capacity NCCL all-gather of the hit records per step, device to device, on a side "
+                               "stream (overlaps the next step); only the last one of the timed region is exposed",
+                       "device_ms_last": tinfo["gather_device_ms_last"], "slot_records": gather.cap,
+                       "regrown": gather.regrown} if gather is not None else None),
+           "rank_ms_per_step_min_max": tinfo["rank_ms_per_step_min_max"],
            "gcups": (cells_score_all + cells_trace_all) / (ms_res * 1e-3) / 1e9,
            "gcups_score_kernel": gcups_score, "gcups_trace_kernel": gcups_trace,
            "stage_ms": {k: float(st[k]) / args.steps for k in ("ms_seed", "ms_sort_merge", "ms_extend_score",
@@ -551,22 +631,15 @@ def main():
            "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": int(res.nbytes + qoffs.nbytes),
                    "d2h_bytes_per_step": int(len(hits) * HIT_DT.itemsize), "ms_per_step": wall_e2e / args.steps,
                    "device_ms_per_step": ms_e2e / args.steps, "timing": "host wall-clock around Searcher.search()"},
-           "gpu_launches": int(st_pipe["kernel_launches"]), "kernels_ncu": other}
+           "gpu_launches": int(st_pipe["kernel_launches"]), "kernel_sources_sha": ksha, "kernels_ncu": other}
 
     # CPU baseline: the unmodified reference on this box's host cores, bounded sample of the same queries
-    if args.band:
-        out["parity_sample"] = None  # non-parity mode: the reference cannot run with another band
-    elif not args.no_cpu_baseline and n_gpus == 1 and os.path.exists(REF):
-        n_sample = args.cpu_sample or min(args.n_queries, max(2000, 2000 * cores))
-        qps, wall, phase, ref_lines = run_reference_search(wl, d, q_ascii, qoffs, n_sample, cores, "cpu")
-        out["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "reference",
-                               "sample": f"first {n_sample} of the {args.n_queries} queries, lambda3 {wl} -t {cores} "
+    out["parity_sample"] = parity
+    if ref_run is not None and n_gpus == 1:
+        qps, wall, phase, n_sample, threads = ref_run
+        out["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": threads, "kind": "reference",
+                               "sample": f"first {n_sample} of the {args.n_queries} queries, lambda3 {wl} -t {threads} "
                                          f"(SSE4 build), reference's own search-phase timer {phase:.2f}s, wall {wall:.2f}s"}
-        # parity on the sample: our tabular lines for the same queries must equal the reference's
-        ids = [f"Q{i}" for i in range(args.n_queries)]
-        mine = sorted(s.m8(hits[hits["q_id"] < n_sample], ids))
-        out["parity_sample"] = {"queries": n_sample, "reference_lines": len(ref_lines), "our_lines": len(mine),
-                                "identical": mine == sorted(ref_lines)}
     emit(out)
     if world > 1:
         dist.destroy_process_group()

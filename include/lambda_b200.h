@@ -277,6 +277,16 @@ typedef struct
  * `stats` is accumulated into (zero it yourself), like the reference's per-thread StatsHolder. */
 int lgpu_search_batch(lgpu_ctx *, lgpu_query_batch const * q, lgpu_hits * out, lgpu_stats * stats);
 
+/* The records of the LAST lgpu_search_batch() call also stay on the device (they are sorted, made unique and cut to
+ * max_matches there -- writeRecords / _writeRecord, src/search_algo.hpp:821-913,1335-1362).
+ * lgpu_ctx_export_hits() copies them into a caller-owned DEVICE buffer of `cap_records` records, query ids rebased by
+ * `first_query` -- the send buffer of the multi-GPU hit gather, so that the records of a shard travel GPU to GPU
+ * without a detour through the host.  *n_out = number of records of the call; nothing is copied if it exceeds
+ * `cap_records`.  The device records carry bit_score = evalue = 0: both are functions of (score, q_len) that the host
+ * computes with its own libm -- lgpu_hits_fill_scores() does that for records in HOST memory (e.g. gathered ones). */
+int lgpu_ctx_export_hits(lgpu_ctx *, void * dev_dst, uint64_t cap_records, uint64_t first_query, uint64_t * n_out);
+int lgpu_hits_fill_scores(lgpu_ctx *, lgpu_hit * host_records, uint64_t n);
+
 /* ------------------------------------------------------------------------------------------------
  * Stage-level entry points (what the reference's unit-less test-suite lacks; used by the parity
  * tests to compare each kernel with the oracle separately).

@@ -58,6 +58,8 @@ def load_library():
     lib.lgpu_last_error.restype = C.c_char_p
     lib.lgpu_last_error.argtypes = [vp]
     lib.lgpu_search_batch.argtypes = [vp, C.POINTER(QueryBatch), C.POINTER(Hits), vp]
+    lib.lgpu_ctx_export_hits.argtypes = [vp, vp, u64, u64, C.POINTER(u64)]
+    lib.lgpu_hits_fill_scores.argtypes = [vp, vp, u64]
     lib.lgpu_seed_batch.argtypes = [vp, C.POINTER(QueryBatch), i32, C.POINTER(vp), C.POINTER(u64), vp]
     lib.lgpu_merge_matches.argtypes = [vp, C.POINTER(QueryBatch), vp, u64, C.POINTER(vp), C.POINTER(u64), vp]
     lib.lgpu_extend_scores.argtypes = [vp, C.POINTER(QueryBatch), vp, u64, vp, vp]
@@ -223,6 +225,20 @@ class Searcher:
         hits = np.frombuffer(raw, HIT_DT)
         return (hits.copy() if copy else hits), st[0]
 
+    def export_hits(self, dev_ptr: int, cap_records: int, first_query: int = 0) -> int:
+        """copy the records of the last search() into a caller-owned DEVICE buffer (the send buffer of the multi-GPU
+        gather), query ids rebased by first_query; returns the number of records (nothing is copied if > cap_records)"""
+        n = C.c_uint64()
+        _check(load_library().lgpu_ctx_export_hits(self._h, C.c_void_p(dev_ptr), cap_records, first_query, C.byref(n)),
+               self._h)
+        return int(n.value)
+
+    def fill_scores(self, hits: np.ndarray) -> np.ndarray:
+        """bit score and e-value of records that came off a device buffer (host arithmetic, like the reference)"""
+        hits = np.ascontiguousarray(hits, HIT_DT)
+        _check(load_library().lgpu_hits_fill_scores(self._h, _p(hits), len(hits)), self._h)
+        return hits
+
     @property
     def query_is_protein(self):
         """protein queries (aa27 ranks) unless the domain or `query_alph` says nucleotides (dna5 ranks)"""
@@ -242,6 +258,8 @@ class Searcher:
             h = hits[i:i + 1]
             n = lib.lgpu_format_m8(C.byref(self.params), _p(h), query_ids[int(h["q_id"][0])].encode(),
                                    sids[int(h["s_id"][0])].encode(), buf, 8192)
+            if n <= 0:
+                raise LambdaError(n, "lgpu_format_m8 failed")
             lines.append(buf.raw[:n].decode())
         return lines
 
@@ -252,7 +270,7 @@ class Searcher:
         for name in columns.split():
             c = lib.lgpu_tabular_column(name.encode())
             if c < 0:
-                raise LambdaError(f'Unknown column specifier "{name}".')
+                raise LambdaError(-1, f'Unknown column specifier "{name}".')
             cols.append(c)
         arr = (C.c_uint32 * len(cols))(*cols)
         buf = C.create_string_buffer(16384)
@@ -263,7 +281,7 @@ class Searcher:
             n = lib.lgpu_format_tabular(C.byref(self.params), _p(h), query_ids[int(h["q_id"][0])].encode(),
                                         sids[int(h["s_id"][0])].encode(), arr, len(cols), buf, 16384)
             if n < 0:
-                raise LambdaError("unsupported column in " + columns)
+                raise LambdaError(n, "unsupported column in " + columns)
             lines.append(buf.raw[:n].decode())
         return lines
 

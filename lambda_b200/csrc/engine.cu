@@ -26,6 +26,7 @@
 #include <thread>
 #include <vector>
 
+#include <cub/device/device_merge_sort.cuh>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cuda_runtime.h>
@@ -36,9 +37,9 @@
 #include "host_finalize.hpp"
 #include "host_params.hpp"
 #include "kernels_dpx.cuh"
-#include "kernels_ckpt_trace.cuh"
 #include "kernels_dpx_trace.cuh"
 #include "kernels_extend.cuh"
+#include "kernels_finalize.cuh"
 #include "kernels_fm.cuh"
 #include "lba_index.hpp"
 
@@ -92,6 +93,25 @@ struct DevBuf
         release();
         size_t const want = std::max<size_t>(n + n / 4, 256);
         LGPU_CUDA(cudaMalloc(reinterpret_cast<void **>(&p), want * sizeof(T)));
+        cap = want;
+    }
+    // like reserve(), but the first `keep` elements survive a reallocation
+    void grow(size_t n, size_t keep, cudaStream_t s)
+    {
+        if (n <= cap)
+            return;
+        T *          old  = p;
+        size_t const want = std::max<size_t>(n + n / 2, 256);
+        T *          np   = nullptr;
+        LGPU_CUDA(cudaMalloc(reinterpret_cast<void **>(&np), want * sizeof(T)));
+        if (old && keep)
+        {
+            LGPU_CUDA(cudaMemcpyAsync(np, old, keep * sizeof(T), cudaMemcpyDeviceToDevice, s));
+            LGPU_CUDA(cudaStreamSynchronize(s));
+        }
+        if (old)
+            cudaFree(old);
+        p   = np;
         cap = want;
     }
 };
@@ -321,11 +341,43 @@ struct lgpu_ctx
     DevBuf<unsigned char>      dTrace;
     DevBuf<unsigned long long> dTraceOff;
     DevBuf<lgpu_hit>           dHits;
-    DevBuf<unsigned int>       dPlanes;      // (H, dE|dF) planes of the packed trace kernel
+    DevBuf<unsigned int>       dPlanes;      // residue planes of DP pass 2 (one byte per cell)
     DevBuf<lgpu_match>         dTasksScalar;
     bool                       forceScalarTrace = false; // LAMBDA_B200_TRACE=scalar (tests)
-    bool                       planeTrace = true;        // stored (H, dE, dF) planes; LAMBDA_B200_TRACE=ckpt: checkpoints + tile recomputation
-    DevBuf<unsigned int>       dFirstBlk;
+    bool                       privProfiles = false; // DP pass 1: one query profile per group (small alphabets) instead of per warp
+    bool                       resTraceOk   = false; // scoring fits the residue-plane trace path (kernels_dpx_trace.cuh)
+    int                        traceTab     = kDpxTabTrace32; // class table of DP pass 2
+    uint64_t                   maxPlaneWords = (16ull << 30) / 4; // residue planes per launch group (LAMBDA_B200_PLANE_MB)
+    DevBuf<unsigned long long> dPlaneWords, dPlaneWordsB;
+    DevBuf<unsigned int>       dScalarSlots, dScalarIdx;
+
+    // records of the batch on the device: all phases appended, then finalised (kernels_finalize.cuh)
+    DevBuf<lgpu_hit>           dAllHits, dFinal;
+    DevBuf<unsigned int>       dQryHasHit, dFinIdx, dFinIdxB, dFinIdx1;
+    DevBuf<unsigned char>      dDropped;
+    uint64_t                   nAll = 0, nFinal = 0;
+    lgpu_hit const *           finalDev = nullptr; // the nFinal records of the last searchOne on the device
+    unsigned int               maxQueryLen = 0;
+    std::unique_ptr<EValueComputer> evc;           // persistent: length adjustments and score tables are cached
+    std::vector<ScoreThresholds>    thrByLen;      // thresholds per query length (direct index), filled lazily
+    std::vector<unsigned char>      thrKnown;
+    std::unordered_map<uint64_t, ScoreThresholds> thrLong; // ... for lengths beyond the table
+    PinnedBuf<int>                  hMinBit, hMinEval;
+    struct ExportPart
+    {
+        lgpu_ctx const * ctx;
+        uint64_t         qBase, cigarBase, n;
+    };
+    std::vector<ExportPart>    lastParts; // where the records of the last lgpu_search_batch live (lgpu_ctx_export_hits)
+
+    // stage timers: event pairs recorded on the stream, read once at the end of the call
+    struct TimerSlot
+    {
+        cudaEvent_t a = nullptr, b = nullptr;
+        float *     acc = nullptr;
+    };
+    std::vector<TimerSlot> timers;
+    size_t                 timersUsed = 0;
 
     // pinned staging
     PinnedBuf<lgpu_match> hTasks;
@@ -336,7 +388,6 @@ struct lgpu_ctx
     std::vector<lgpu_hit>   hits;
     std::vector<uint32_t>   cigar;       // run-length ops of the hits (lgpu_params.want_cigar), see lgpu_hit::cigar_off
     DevBuf<unsigned int>    dCigarCap, dCigarOff, dCigar;
-    DevBuf<unsigned char>   dTraceK;     // per task: K of the packed trace class it ran in
     PinnedBuf<unsigned int> hCigarStage;
     std::vector<lgpu_match> matchesHost;
     cudaEvent_t             ev[8]{};
@@ -354,6 +405,13 @@ struct lgpu_ctx
         for (auto & e : ev)
             if (e)
                 cudaEventDestroy(e);
+        for (auto & t : timers)
+        {
+            if (t.a)
+                cudaEventDestroy(t.a);
+            if (t.b)
+                cudaEventDestroy(t.b);
+        }
         if (evSync)
             cudaEventDestroy(evSync);
         if (stream)
@@ -460,28 +518,46 @@ static inline void waitEvent(lgpu_ctx & c, cudaEvent_t ev)
         LGPU_CUDA(cudaEventSynchronize(ev)); // block mode: the events were created with cudaEventBlockingSync
 }
 
+// Stage times: an event pair per stage instance, recorded on the stream and read once at the end of the call
+// (resolveTimers) -- a timer never makes the host wait.
 struct StageTimer
 {
     lgpu_ctx & c;
-    float *    acc;
-    StageTimer(lgpu_ctx & ctx, float * a) : c(ctx), acc(a) { cudaEventRecord(c.ev[0], c.stream); }
+    int        slot = -1;
+    StageTimer(lgpu_ctx & ctx, float * acc) : c(ctx)
+    {
+        if (!acc)
+            return;
+        if (c.timersUsed == c.timers.size())
+        {
+            lgpu_ctx::TimerSlot t;
+            if (cudaEventCreate(&t.a) != cudaSuccess || cudaEventCreate(&t.b) != cudaSuccess)
+                return;
+            c.timers.push_back(t);
+        }
+        slot                = static_cast<int>(c.timersUsed++);
+        c.timers[slot].acc  = acc;
+        cudaEventRecord(c.timers[slot].a, c.stream);
+    }
     ~StageTimer()
     {
-        cudaEventRecord(c.ev[1], c.stream);
-        try
-        {
-            waitEvent(c, c.ev[1]);
-        }
-        catch (...)
-        {
-            return; // the error is sticky: the next checked call of the stage reports it
-        }
-        float ms = 0;
-        cudaEventElapsedTime(&ms, c.ev[0], c.ev[1]);
-        if (acc)
-            *acc += ms;
+        if (slot >= 0)
+            cudaEventRecord(c.timers[slot].b, c.stream);
     }
 };
+
+// call after the stream has been synchronised
+static void resolveTimers(lgpu_ctx & c)
+{
+    for (size_t i = 0; i < c.timersUsed; ++i)
+    {
+        float ms = 0;
+        if (c.timers[i].acc && cudaEventElapsedTime(&ms, c.timers[i].a, c.timers[i].b) == cudaSuccess)
+            *c.timers[i].acc += ms;
+        c.timers[i].acc = nullptr;
+    }
+    c.timersUsed = 0;
+}
 
 static void checkParams(lgpu_params const & p, lgpu_index_desc const & d)
 {
@@ -549,6 +625,9 @@ static void uploadQueries(lgpu_ctx & c, BatchView const & qb, lgpu_stats * st)
     if (c.qOffsHost[0] != 0)
         throw ArgError("query offsets must start at 0");
     c.totalResidues      = c.qOffsHost[qb.n];
+    c.maxQueryLen        = 0;
+    for (uint64_t i = 0; i < qb.n; ++i)
+        c.maxQueryLen = std::max(c.maxQueryLen, static_cast<unsigned int>(c.qOffsHost[i + 1] - c.qOffsHost[i]));
     unsigned int const F = c.di.qryNumFrames;
     c.dQOrig.reserve(c.totalResidues);
     c.dQOffs.reserve(qb.n + 1);
@@ -802,7 +881,7 @@ static ExtParams baseExtParams(lgpu_ctx & c, lgpu_match const * dTasks, unsigned
     P.matrix      = c.dMatrix.p;
     P.go          = c.scoring.gapOpenSeqan;
     P.ge          = c.scoring.gapExtend;
-    c.dWork.reserve(kNumDpxClasses + 2);
+    c.dWork.reserve(kMaxDpxClasses + 3);
     P.workCounter = c.dWork.p;
     P.order       = nullptr;
     P.maxRows     = std::max(dims.maxT, 1u);
@@ -814,17 +893,17 @@ static ExtParams baseExtParams(lgpu_ctx & c, lgpu_match const * dTasks, unsigned
     return P;
 }
 
-template <int T, int K>
+template <int T, int K, bool PRIV, bool TRACE>
 static void launchDpx(lgpu_ctx & c, DpxParams P, unsigned int maxNt)
 {
-    constexpr int G = 32 / T;
-    P.winCap        = (maxNt + 4 * T + 127) / 128 * 128;
-    size_t const smem = static_cast<size_t>(P.nCodes) * dpxRowWords(T, K) * 4 + static_cast<size_t>(G) * (P.winCap + 32);
-    LGPU_CUDA(cudaFuncSetAttribute(swScoreDpxKernel<T, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    P.winCap          = (maxNt + 4 * T + 127) / 128 * 128;
+    size_t const smem = dpxSmemBytes(T, K, PRIV, P.nCodes, P.winCap);
     if (smem > 227 * 1024)
-        throw CudaError("DPX score kernel: window too long for shared memory");
-    unsigned int const grid = std::min<unsigned int>(P.nJobs, static_cast<unsigned int>(c.numSMs) * c.dpxBlocksPerSM);
-    swScoreDpxKernel<T, K><<<grid, 32, smem, c.stream>>>(P);
+        throw CudaError("DPX kernel: window too long for shared memory");
+    LGPU_CUDA(cudaFuncSetAttribute(swDpxKernel<T, K, PRIV, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    unsigned int const perSM = TRACE ? 32u : c.dpxBlocksPerSM;
+    unsigned int const grid  = std::min<unsigned int>(P.nJobs, static_cast<unsigned int>(c.numSMs) * perSM);
+    swDpxKernel<T, K, PRIV, TRACE><<<grid, 32, smem, c.stream>>>(P);
     LGPU_CUDA(cudaGetLastError());
 }
 
@@ -833,87 +912,116 @@ struct MaxOp
     __host__ __device__ unsigned int operator()(unsigned int a, unsigned int b) const { return a > b ? a : b; }
 };
 
-// DP pass 1: scores into dScores[0..n).  Alignments are sorted by (length class of the query, query,
-// window length); up to 32/T consecutive alignments of one query form a job of the packed DPX kernel
-// (one shared query profile per warp).  Whatever does not fit the packed kernel (queries > 2048,
-// windows > 8192, exotic scoring) runs on the scalar wavefront kernel.
 using DpxLaunchFn = void (*)(lgpu_ctx &, DpxParams, unsigned int);
-#define LGPU_DPX_LAUNCH_ENTRY(T, K) &launchDpx<T, K>,
-static DpxLaunchFn const kDpxLaunch[kNumDpxClasses] = {LGPU_DPX_CLASSES(LGPU_DPX_LAUNCH_ENTRY)};
-#undef LGPU_DPX_LAUNCH_ENTRY
+#define LGPU_DPX_LAUNCH_SHARED(T, K) &launchDpx<T, K, false, false>,
+#define LGPU_DPX_LAUNCH_PRIV(T, K) &launchDpx<T, K, true, false>,
+#define LGPU_DPX_LAUNCH_TRACE(T, K) &launchDpx<T, K, true, true>,
+static DpxLaunchFn const kDpxLaunchShared[kNumDpxClasses]      = {LGPU_DPX_CLASSES(LGPU_DPX_LAUNCH_SHARED)};
+static DpxLaunchFn const kDpxLaunchPriv[kNumDpxPrivClasses]    = {LGPU_DPX_PRIV_CLASSES(LGPU_DPX_LAUNCH_PRIV)};
+static DpxLaunchFn const kDpxLaunchPrivTr[kNumDpxPrivClasses]  = {LGPU_DPX_PRIV_CLASSES(LGPU_DPX_LAUNCH_TRACE)};
+static DpxLaunchFn const kDpxLaunchTrace32[kNumDpxTr32Classes] = {LGPU_DPX_TRACE32_CLASSES(LGPU_DPX_LAUNCH_TRACE)};
+#undef LGPU_DPX_LAUNCH_SHARED
+#undef LGPU_DPX_LAUNCH_PRIV
+#undef LGPU_DPX_LAUNCH_TRACE
 
+constexpr int kClsSlots = kMaxDpxClasses + 1; // per-class arrays: the packed classes of a table + the scalar class
+
+static DpxParams baseDpxParams(lgpu_ctx & c, lgpu_match const * dTasks, unsigned int n)
+{
+    DpxParams P{};
+    P.ix      = c.index->dev;
+    P.Q       = c.Q;
+    P.tasks   = dTasks;
+    P.nSorted = n;
+    P.matrix  = c.dMatrix.p;
+    P.go      = c.scoring.gapOpenSeqan;
+    P.ge      = c.scoring.gapExtend;
+    P.nCodes  = static_cast<unsigned int>(c.scoring.alphSize) + 1;
+    return P;
+}
+
+// DP pass 1: scores into dScores[0..n).  Alignments are sorted by length class of the query, then -- shared
+// profiles -- by (query, window length): up to 32/T consecutive alignments of one query form a job of the packed
+// kernel; or -- private profiles (small alphabets) -- by window length alone: any 32/T consecutive alignments form
+// a job.  Whatever does not fit the packed kernel (queries > 2048, windows > 8192, exotic scoring) runs on the scalar
+// wavefront kernel.
 static void runScorePass(lgpu_ctx & c, lgpu_match const * dTasks, unsigned int n, int * dScores, lgpu_stats * st)
 {
     if (n == 0)
         return;
     StageTimer t(c, st ? &st->ms_extend_score : nullptr);
-    constexpr int NC = kNumDpxClasses + 1;
+    bool const priv = c.privProfiles;
+    int const  tab  = priv ? kDpxTabPriv : kDpxTabShared;
+    int const  NP   = dpxNumClasses(tab); // packed classes; class NP = scalar
+    constexpr int NC = kClsSlots;
     c.dClassKeys.reserve(n);
     c.dClassKeysB.reserve(n);
     c.dOrder.reserve(n);
     c.dOrderB.reserve(n);
-    c.dSegStart.reserve(n);
-    c.dSegStartB.reserve(n);
-    c.dJobHead.reserve(n);
-    c.dJobPos.reserve(n);
-    c.dJobs.reserve(n);
     c.dClassInfo.reserve(3 * NC + 4);
     c.dCounters.reserve(8);
     c.dWork.reserve(NC + 1);
     LGPU_CUDA(cudaMemsetAsync(c.dClassInfo.p, 0, (3 * NC + 4) * 4, c.stream));
     LGPU_CUDA(cudaMemsetAsync(c.dCounters.p, 0, 8 * sizeof(unsigned long long), c.stream));
     LGPU_CUDA(cudaMemsetAsync(c.dWork.p, 0, (NC + 1) * 4, c.stream));
-    unsigned int const g = gridFor(n, 256);
+    unsigned int const g  = gridFor(n, 256);
     int const          nI = static_cast<int>(n);
-    classifyKernel<<<g, 256, 0, c.stream>>>(dTasks, n, c.index->dev.bsMode, c.dClassKeys.p, c.dOrder.p, c.dClassInfo.p, c.dClassInfo.p + NC,
-                                            c.dClassInfo.p + 3 * NC, c.dCounters.p);
+    classifyKernel<<<g, 256, 0, c.stream>>>(dTasks, n, c.index->dev.bsMode, tab, c.dClassKeys.p, c.dOrder.p, c.dClassInfo.p,
+                                            c.dClassInfo.p + NC, c.dClassInfo.p + 3 * NC, c.dCounters.p, nullptr);
     size_t t1 = 0, t2 = 0, t3 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, t1, c.dClassKeys.p, c.dClassKeysB.p, c.dOrder.p, c.dOrderB.p, nI, 0, 64, c.stream);
-    cub::DeviceScan::InclusiveScan(nullptr, t2, c.dSegStart.p, c.dSegStartB.p, MaxOp(), nI, c.stream);
-    cub::DeviceScan::InclusiveSum(nullptr, t3, c.dJobHead.p, c.dJobPos.p, nI, c.stream);
+    if (!priv)
+    {
+        c.dSegStart.reserve(n);
+        c.dSegStartB.reserve(n);
+        c.dJobHead.reserve(n);
+        c.dJobPos.reserve(n);
+        c.dJobs.reserve(n);
+        cub::DeviceScan::InclusiveScan(nullptr, t2, c.dSegStart.p, c.dSegStartB.p, MaxOp(), nI, c.stream);
+        cub::DeviceScan::InclusiveSum(nullptr, t3, c.dJobHead.p, c.dJobPos.p, nI, c.stream);
+    }
     c.dCubTemp.reserve(std::max(t1, std::max(t2, t3)));
     size_t tb = c.dCubTemp.cap;
     LGPU_CUDA(cub::DeviceRadixSort::SortPairs(c.dCubTemp.p, tb, c.dClassKeys.p, c.dClassKeysB.p, c.dOrder.p, c.dOrderB.p, nI, 0, 64,
                                               c.stream));
-    segFlagKernel<<<g, 256, 0, c.stream>>>(c.dClassKeysB.p, c.dOrderB.p, dTasks, n, c.dSegStart.p);
-    tb = c.dCubTemp.cap;
-    LGPU_CUDA(cub::DeviceScan::InclusiveScan(c.dCubTemp.p, tb, c.dSegStart.p, c.dSegStartB.p, MaxOp(), nI, c.stream));
-    jobHeadKernel<<<g, 256, 0, c.stream>>>(c.dClassKeysB.p, c.dSegStartB.p, n, c.dJobHead.p, c.dClassInfo.p + 2 * NC);
-    tb = c.dCubTemp.cap;
-    LGPU_CUDA(cub::DeviceScan::InclusiveSum(c.dCubTemp.p, tb, c.dJobHead.p, c.dJobPos.p, nI, c.stream));
-    jobEmitKernel<<<g, 256, 0, c.stream>>>(c.dJobHead.p, c.dJobPos.p, n, c.dJobs.p);
+    unsigned int launches = 1 + 1;
+    if (!priv)
+    {
+        segFlagKernel<<<g, 256, 0, c.stream>>>(c.dClassKeysB.p, c.dOrderB.p, dTasks, n, c.dSegStart.p);
+        tb = c.dCubTemp.cap;
+        LGPU_CUDA(cub::DeviceScan::InclusiveScan(c.dCubTemp.p, tb, c.dSegStart.p, c.dSegStartB.p, MaxOp(), nI, c.stream));
+        jobHeadKernel<<<g, 256, 0, c.stream>>>(c.dClassKeysB.p, c.dSegStartB.p, n, c.dJobHead.p, c.dClassInfo.p + 2 * NC);
+        tb = c.dCubTemp.cap;
+        LGPU_CUDA(cub::DeviceScan::InclusiveSum(c.dCubTemp.p, tb, c.dJobHead.p, c.dJobPos.p, nI, c.stream));
+        jobEmitKernel<<<g, 256, 0, c.stream>>>(c.dJobHead.p, c.dJobPos.p, n, c.dJobs.p);
+        launches += 5;
+    }
     LGPU_CUDA(cudaGetLastError());
     unsigned int       info[3 * NC + 1];
     unsigned long long cells = 0;
     LGPU_CUDA(cudaMemcpyAsync(info, c.dClassInfo.p, sizeof(info), cudaMemcpyDeviceToHost, c.stream));
     LGPU_CUDA(cudaMemcpyAsync(&cells, c.dCounters.p, 8, cudaMemcpyDeviceToHost, c.stream));
     syncStream(c);
-    unsigned int launches = 7;
     unsigned int taskOff = 0, jobOff = 0;
-    for (int cls = 0; cls < NC; ++cls)
+    for (int cls = 0; cls <= NP; ++cls)
     {
-        unsigned int const cnt = info[cls], maxNt = info[NC + cls], nJobs = info[2 * NC + cls];
+        unsigned int const cnt = info[cls], maxNt = info[NC + cls];
         if (cnt == 0)
             continue;
-        bool const scalar = (cls == kNumDpxClasses) || !c.dpxScoreOk;
+        bool const         scalar = (cls == NP) || !c.dpxScoreOk;
+        unsigned int const nJobs  = priv ? (cnt + dpxGroupsOf(tab, cls) - 1) / dpxGroupsOf(tab, cls) : info[2 * NC + cls];
         if (!scalar)
         {
-            DpxParams P{};
-            P.ix          = c.index->dev;
-            P.Q           = c.Q;
-            P.tasks       = dTasks;
+            DpxParams P   = baseDpxParams(c, dTasks, n);
             P.order       = c.dOrderB.p;
             P.keys        = c.dClassKeysB.p;
-            P.nSorted     = n;
-            P.jobs        = c.dJobs.p + jobOff;
+            P.jobs        = priv ? nullptr : c.dJobs.p + jobOff;
             P.nJobs       = nJobs;
-            P.matrix      = c.dMatrix.p;
-            P.go          = c.scoring.gapOpenSeqan;
-            P.ge          = c.scoring.gapExtend;
-            P.nCodes      = static_cast<unsigned int>(c.scoring.alphSize) + 1;
+            P.slotBase    = taskOff;
+            P.nSlots      = cnt;
             P.workCounter = c.dWork.p + cls;
             P.scores      = dScores;
-            kDpxLaunch[cls](c, P, maxNt);
+            (priv ? kDpxLaunchPriv[cls] : kDpxLaunchShared[cls])(c, P, maxNt);
         }
         else
         {
@@ -931,7 +1039,7 @@ static void runScorePass(lgpu_ctx & c, lgpu_match const * dTasks, unsigned int n
         }
         ++launches;
         taskOff += cnt;
-        jobOff += nJobs;
+        jobOff += priv ? 0u : nJobs;
     }
     if (st)
     {
@@ -975,9 +1083,10 @@ static void emitCigars(lgpu_ctx & c, unsigned int const * order, unsigned int cn
         st->kernel_launches += 3;
 }
 
-// DP pass 2 + traceback on the scalar wavefront kernel (1 trace byte per cell) for `n` tasks
-// (host copy `tasks`, device copy dTasks); results land in c.hHits[0..n)
-static void runTraceScalar(lgpu_ctx & c, lgpu_match const * tasks, size_t n, lgpu_match const * dTasks, lgpu_stats * st)
+// DP pass 2 + traceback on the scalar wavefront kernel (1 trace byte per cell) for `n` tasks (host copy `tasks`,
+// device copy dTasks); the record of task t lands in c.dHits[outIdx[t]] (outIdx = nullptr: c.dHits[t])
+static void runTraceScalar(lgpu_ctx & c, lgpu_match const * tasks, size_t n, lgpu_match const * dTasks, unsigned int const * dOutIdx,
+                           lgpu_stats * st)
 {
     TaskDims const dims = taskDims(tasks, n);
     int const      K    = chooseK(dims.maxQ);
@@ -988,8 +1097,6 @@ static void runTraceScalar(lgpu_ctx & c, lgpu_match const * tasks, size_t n, lgp
     c.dScores2.reserve(n);
     c.dBestPos.reserve(2 * n);
     c.dTraceOff.reserve(n);
-    c.dHits.reserve(n);
-    c.hHits.reserve(n);
     size_t begin = 0;
     while (begin < n)
     {
@@ -1028,356 +1135,213 @@ static void runTraceScalar(lgpu_ctx & c, lgpu_match const * tasks, size_t n, lgp
         TP.trace        = c.dTrace.p;
         TP.traceOff     = c.dTraceOff.p;
         TP.K            = static_cast<unsigned int>(K);
-        TP.out          = c.dHits.p;
+        TP.out          = c.dHits.p + (dOutIdx ? 0 : begin);
+        TP.outIndex     = dOutIdx ? dOutIdx + begin : nullptr;
         tracebackKernel<<<gridFor(cnt, 128), 128, 0, c.stream>>>(TP);
         LGPU_CUDA(cudaGetLastError());
         if (c.params.want_cigar)
-            emitCigars(c, nullptr, cnt, [&](unsigned int * ops, unsigned int const * off, unsigned int base) {
-                TP.emit      = 1;
-                TP.cigarOps  = ops;
-                TP.cigarOff  = off;
-                TP.cigarBase = base;
-                tracebackKernel<<<gridFor(cnt, 128), 128, 0, c.stream>>>(TP);
+        {
+            // the emit pass addresses the records through a slot list
+            c.dScalarSlots.reserve(cnt);
+            if (dOutIdx)
+                LGPU_CUDA(cudaMemcpyAsync(c.dScalarSlots.p, dOutIdx + begin, cnt * 4ull, cudaMemcpyDeviceToDevice, c.stream));
+            else
+                iotaFromKernel<<<gridFor(cnt, 256), 256, 0, c.stream>>>(c.dScalarSlots.p, cnt, static_cast<unsigned int>(begin));
+            TracebackParams TE = TP;
+            TE.out             = c.dHits.p;
+            TE.outIndex        = c.dScalarSlots.p;
+            emitCigars(c, c.dScalarSlots.p, cnt, [&](unsigned int * ops, unsigned int const * off, unsigned int base) {
+                TE.emit      = 1;
+                TE.cigarOps  = ops;
+                TE.cigarOff  = off;
+                TE.cigarBase = base;
+                tracebackKernel<<<gridFor(cnt, 128), 128, 0, c.stream>>>(TE);
             }, st);
-        LGPU_CUDA(cudaMemcpyAsync(c.hHits.p + begin, c.dHits.p, cnt * sizeof(lgpu_hit), cudaMemcpyDeviceToHost, c.stream));
-        syncStream(c);
+        }
+        syncStream(c); // offs / the trace buffer are reused by the next chunk
         if (st)
             st->kernel_launches += 2;
         begin = end;
     }
 }
 
-template <int K>
-static void launchDpxTrace(lgpu_ctx & c, DpxTraceParams P, unsigned int maxNt)
-{
-    P.winCap          = (maxNt + 4 * 32 + 127) / 128 * 128;
-    size_t const smem = static_cast<size_t>(P.nCodes) * dpxRowWords(32, K) * 4 + P.winCap;
-    LGPU_CUDA(cudaFuncSetAttribute(swTraceDpxKernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    if (smem > 227 * 1024)
-        throw CudaError("DPX trace kernel: window too long for shared memory");
-    unsigned int const grid = std::min<unsigned int>(P.nTasks, static_cast<unsigned int>(c.numSMs) * 32);
-    swTraceDpxKernel<K><<<grid, 32, smem, c.stream>>>(P);
-    LGPU_CUDA(cudaGetLastError());
-}
-
-template <int T, int K>
-static void launchCkTrace(lgpu_ctx & c, CkTraceParams P, unsigned int maxNt)
-{
-    constexpr int G = 32 / T;
-    P.winCap        = (maxNt + 4 * T + 127) / 128 * 128;
-    size_t const smem = static_cast<size_t>(G) * (static_cast<size_t>(P.nCodes) * dpxRowWords(T, K) * 4 + P.winCap + 32 +
-                                                  static_cast<size_t>(T) * ckRecWords(K) * 4);
-    LGPU_CUDA(cudaFuncSetAttribute(swTraceCkKernel<T, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    if (smem > 227 * 1024)
-        throw CudaError("checkpoint trace kernel: window too long for shared memory");
-    unsigned int const nJobs = (P.nTasks + G - 1) / G;
-    unsigned int const grid  = std::min<unsigned int>(nJobs, static_cast<unsigned int>(c.numSMs) * 32);
-    swTraceCkKernel<T, K><<<grid, 32, smem, c.stream>>>(P);
-    LGPU_CUDA(cudaGetLastError());
-}
-template <int K>
-static void launchCkTracebackK(TracebackCkParams const & TP, unsigned int cnt, cudaStream_t s)
-{
-    LGPU_CUDA(cudaFuncSetAttribute(tracebackCkKernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, ckTbSmemBytes(K)));
-    tracebackCkKernel<K><<<gridFor(cnt, kCkTbThreads), kCkTbThreads, ckTbSmemBytes(K), s>>>(TP);
-}
-static void launchCkTraceback(int K, TracebackCkParams const & TP, unsigned int cnt, cudaStream_t s)
-{
-    switch (K)
-    {
-        case 4: launchCkTracebackK<4>(TP, cnt, s); break;
-        case 8: launchCkTracebackK<8>(TP, cnt, s); break;
-        case 10: launchCkTracebackK<10>(TP, cnt, s); break;
-        case 12: launchCkTracebackK<12>(TP, cnt, s); break;
-        case 16: launchCkTracebackK<16>(TP, cnt, s); break;
-        case 20: launchCkTracebackK<20>(TP, cnt, s); break;
-        case 24: launchCkTracebackK<24>(TP, cnt, s); break;
-        case 32: launchCkTracebackK<32>(TP, cnt, s); break;
-        default: throw CudaError("checkpoint traceback: unsupported K");
-    }
-}
-using CkLaunchFn = void (*)(lgpu_ctx &, CkTraceParams, unsigned int);
-#define LGPU_CK_LAUNCH_ENTRY(T, K) &launchCkTrace<T, K>,
-static CkLaunchFn const kCkLaunch[kNumCkClasses] = {LGPU_CK_CLASSES(LGPU_CK_LAUNCH_ENTRY)};
-#undef LGPU_CK_LAUNCH_ENTRY
-
-// DP pass 2 on checkpoints (kernels_ckpt_trace.cuh) for the tasks in `lists[cls]`; results land in c.dHits
-static void runTraceCk(lgpu_ctx & c, lgpu_match const * tasks, size_t n, lgpu_match const * dTasks,
-                       std::vector<std::vector<unsigned int>> const & lists, lgpu_stats * st)
-{
-    constexpr uint64_t kMaxCkWords = (16ull << 30) / 4; // per launch; checkpoints are ~0.7 B per DP cell
-    std::vector<unsigned long long> ckOff(n, 0);
-    c.dOrder.reserve(n);
-    c.dTraceOff.reserve(n);
-    c.dScores2.reserve(n);
-    c.dBestPos.reserve(n);
-    c.dFirstBlk.reserve(n);
-    for (int cls = 0; cls < kNumCkClasses; ++cls)
-    {
-        std::vector<unsigned int> const & L = lists[cls];
-        if (L.empty())
-            continue;
-        DpxClass const k = ckClass(cls);
-        size_t         begin = 0;
-        while (begin < L.size())
-        {
-            uint64_t     words = 0;
-            unsigned int maxNt = 0;
-            size_t       end   = begin;
-            while (end < L.size())
-            {
-                unsigned int const nt = tasks[L[end]].subj_end - tasks[L[end]].subj_start;
-                uint64_t const     w  = ckWords(k.T, k.K, nt);
-                if (end > begin && words + w > kMaxCkWords)
-                    break;
-                ckOff[L[end]] = words;
-                words += w;
-                maxNt = std::max(maxNt, nt);
-                ++end;
-            }
-            unsigned int const cnt = static_cast<unsigned int>(end - begin);
-            c.dPlanes.reserve(words);
-            LGPU_CUDA(cudaMemcpyAsync(c.dOrder.p, L.data() + begin, cnt * 4ull, cudaMemcpyHostToDevice, c.stream));
-            LGPU_CUDA(cudaMemcpyAsync(c.dTraceOff.p, ckOff.data(), n * 8ull, cudaMemcpyHostToDevice, c.stream));
-            LGPU_CUDA(cudaMemsetAsync(c.dWork.p, 0, 4, c.stream));
-            CkTraceParams P{};
-            P.ix          = c.index->dev;
-            P.Q           = c.Q;
-            P.tasks       = dTasks;
-            P.order       = c.dOrder.p;
-            P.nTasks      = cnt;
-            P.matrix      = c.dMatrix.p;
-            P.go          = c.scoring.gapOpenSeqan;
-            P.ge          = c.scoring.gapExtend;
-            P.nCodes      = static_cast<unsigned int>(c.scoring.alphSize) + 1;
-            P.workCounter = c.dWork.p;
-            P.ck          = c.dPlanes.p;
-            P.ckOff       = c.dTraceOff.p;
-            P.scores      = c.dScores2.p;
-            P.bestCol     = c.dBestPos.p;
-            P.firstBlk    = c.dFirstBlk.p;
-            kCkLaunch[cls](c, P, maxNt);
-            TracebackCkParams TP{};
-            TP.ix       = c.index->dev;
-            TP.Q        = c.Q;
-            TP.tasks    = dTasks;
-            TP.order    = c.dOrder.p;
-            TP.nTasks   = cnt;
-            TP.matrix   = c.dMatrix.p;
-            TP.go       = c.scoring.gapOpenSeqan;
-            TP.ge       = c.scoring.gapExtend;
-            TP.T        = static_cast<unsigned int>(k.T);
-            TP.K        = static_cast<unsigned int>(k.K);
-            TP.scores   = c.dScores2.p;
-            TP.bestCol  = c.dBestPos.p;
-            TP.firstBlk = c.dFirstBlk.p;
-            TP.ck       = c.dPlanes.p;
-            TP.ckOff    = c.dTraceOff.p;
-            TP.out      = c.dHits.p;
-            launchCkTraceback(k.K, TP, cnt, c.stream);
-            LGPU_CUDA(cudaGetLastError());
-            syncStream(c); // the order / offset staging arrays are reused by the next chunk
-            if (st)
-                st->kernel_launches += 2;
-            begin = end;
-        }
-    }
-}
-
-// DP pass 2 + traceback for `n` tasks (host copy `tasks`, device copy dTasks); hostOut[i] <-> tasks[i].
-// Alignments whose query fits 64 x 32 columns run on the packed DPX trace kernel (one warp each, planes
-// of (H, dE, dF) instead of trace bytes); the rest on the scalar wavefront kernel.
-static void runTracePass(lgpu_ctx & c, lgpu_match const * tasks, size_t n, lgpu_match const * dTasks, lgpu_hit * hostOut,
-                         lgpu_stats * st)
+// DP pass 2 + traceback for the `n` alignments dTasks[0..n) (device); the record of task t lands in c.dHits[t].
+// Everything is laid out on the device: the alignments are classified and sorted by (class, window length), a scan of
+// the plane sizes gives every alignment its residue plane, one fill launch per class and ONE traceback launch walk
+// them.  The host reads back the class counts once (launch configuration, plane buffer size).  Alignments outside
+// the packed kernels' range (queries > 2048 columns, windows > 8192, exotic scoring) take the scalar path.
+static void runTracePass(lgpu_ctx & c, lgpu_match const * dTasks, unsigned int n, lgpu_stats * st)
 {
     if (n == 0)
         return;
     StageTimer t(c, st ? &st->ms_extend_trace : nullptr);
-    int const  D      = c.scoring.gapExtend - c.scoring.gapOpenSeqan;
-    bool const dpxOk  = c.dpxOk && D >= 0 && D <= 14 && !c.forceScalarTrace;
-    uint64_t   cells  = 0;
-    bool const useCk        = !c.planeTrace && !c.params.want_cigar; // the checkpoint traceback has no emit pass
-    int const  nPackedClass = useCk ? kNumCkClasses : kNumTraceClasses;
-    std::vector<std::vector<unsigned int>> lists(std::max(kNumCkClasses, kNumTraceClasses) + 1);
-    for (size_t i = 0; i < n; ++i)
-    {
-        unsigned int const nq = tasks[i].qry_end - tasks[i].qry_start, nt = tasks[i].subj_end - tasks[i].subj_start;
-        cells += static_cast<uint64_t>(nq) * nt;
-        int cls = useCk ? ckClassOf(nq) : dpxTraceClassOf(nq);
-        if (!dpxOk || nt > kDpxMaxWindow || cls == nPackedClass)
-            cls = static_cast<int>(lists.size()) - 1;
-        lists[cls].push_back(static_cast<unsigned int>(i));
-    }
     c.dHits.reserve(n);
-    c.hHits.reserve(n);
-    c.dWork.reserve(kNumDpxClasses + 2);
-    bool anyCk = false;
-    if (useCk)
+    c.dWork.reserve(kClsSlots + 2);
+    if (!c.resTraceOk || c.forceScalarTrace)
     {
-        for (int cls = 0; cls < kNumCkClasses; ++cls)
-            anyCk = anyCk || !lists[cls].empty();
-        if (anyCk)
-            runTraceCk(c, tasks, n, dTasks, lists, st);
-    }
-
-    // ---- packed classes ----
-    // The fill kernels run class by class (K is a template parameter), but ONE traceback launch walks the
-    // alignments of all classes of a group: the traceback of a long alignment is a chain of dependent
-    // loads, and with one launch per class the step would pay the longest chain of every class in turn.
-    // A group = as many (class, alignment) pieces as fit the plane budget of one launch.
-    constexpr uint64_t kMaxPlaneWords = (16ull << 30) / 4;
-    std::vector<unsigned long long> planeOff(n, 0);
-    std::vector<unsigned char>      kOf(n, 0);
-    bool                            anyDpx = false;
-    struct Piece
-    {
-        int          cls;
-        size_t       begin, end; // range inside lists[cls]
-        unsigned int maxNt;
-    };
-    std::vector<Piece>        group;
-    std::vector<unsigned int> groupOrder;
-    uint64_t                  groupWords = 0;
-    auto flushGroup = [&]() {
-        if (group.empty())
-            return;
-        unsigned int const total = static_cast<unsigned int>(groupOrder.size());
-        c.dOrder.reserve(n);
-        c.dTraceOff.reserve(n);
-        c.dScores2.reserve(n);
-        c.dBestPos.reserve(n);
-        c.dTraceK.reserve(n);
-        c.dPlanes.reserve(groupWords);
-        LGPU_CUDA(cudaMemcpyAsync(c.dOrder.p, groupOrder.data(), total * 4ull, cudaMemcpyHostToDevice, c.stream));
-        LGPU_CUDA(cudaMemcpyAsync(c.dTraceOff.p, planeOff.data(), n * 8ull, cudaMemcpyHostToDevice, c.stream));
-        LGPU_CUDA(cudaMemcpyAsync(c.dTraceK.p, kOf.data(), n, cudaMemcpyHostToDevice, c.stream));
-        unsigned int off = 0;
-        for (Piece const & pc : group)
+        // no packed path for this scoring scheme: everything on the scalar kernel
+        std::vector<lgpu_match> host(n);
+        LGPU_CUDA(cudaMemcpyAsync(host.data(), dTasks, n * sizeof(lgpu_match), cudaMemcpyDeviceToHost, c.stream));
+        syncStream(c);
+        runTraceScalar(c, host.data(), n, dTasks, nullptr, st);
+        if (st)
         {
-            unsigned int const cnt = static_cast<unsigned int>(pc.end - pc.begin);
-            int const          K   = dpxTraceK(pc.cls);
-            LGPU_CUDA(cudaMemsetAsync(c.dWork.p, 0, 4, c.stream));
-            DpxTraceParams P{};
-            P.ix          = c.index->dev;
-            P.Q           = c.Q;
-            P.tasks       = dTasks;
-            P.order       = c.dOrder.p + off;
-            P.nTasks      = cnt;
-            P.matrix      = c.dMatrix.p;
-            P.go          = c.scoring.gapOpenSeqan;
-            P.ge          = c.scoring.gapExtend;
-            P.nCodes      = static_cast<unsigned int>(c.scoring.alphSize) + 1;
-            P.workCounter = c.dWork.p;
-            P.planes      = c.dPlanes.p;
-            P.planeOff    = c.dTraceOff.p;
-            P.scores      = c.dScores2.p;
-            P.bestCol     = c.dBestPos.p;
-            switch (K)
+            st->n_extensions_trace += n;
+            st->cells_trace += taskDims(host.data(), n).cells;
+        }
+        return;
+    }
+    int const     tab = c.traceTab;
+    int const     NP  = dpxNumClasses(tab);
+    constexpr int NC  = kClsSlots;
+    c.dClassKeys.reserve(n);
+    c.dClassKeysB.reserve(n);
+    c.dOrder.reserve(n);
+    c.dOrderB.reserve(n);
+    c.dPlaneWords.reserve(n);
+    c.dPlaneWordsB.reserve(n);
+    c.dTraceOff.reserve(n);
+    c.dScores2.reserve(n);
+    c.dBestPos.reserve(n);
+    c.dClassInfo.reserve(3 * NC + 4);
+    c.dCounters.reserve(8);
+    LGPU_CUDA(cudaMemsetAsync(c.dClassInfo.p, 0, (3 * NC + 4) * 4, c.stream));
+    LGPU_CUDA(cudaMemsetAsync(c.dCounters.p, 0, 8 * sizeof(unsigned long long), c.stream));
+    LGPU_CUDA(cudaMemsetAsync(c.dWork.p, 0, (NC + 1) * 4, c.stream));
+    unsigned int const g  = gridFor(n, 256);
+    int const          nI = static_cast<int>(n);
+    classifyKernel<<<g, 256, 0, c.stream>>>(dTasks, n, c.index->dev.bsMode, tab, c.dClassKeys.p, c.dOrder.p, c.dClassInfo.p,
+                                            c.dClassInfo.p + NC, c.dClassInfo.p + 3 * NC, c.dCounters.p, c.dPlaneWords.p);
+    size_t t1 = 0, t2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, t1, c.dClassKeys.p, c.dClassKeysB.p, c.dOrder.p, c.dOrderB.p, nI, 0, 64, c.stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, t2, c.dPlaneWordsB.p, c.dTraceOff.p, nI, c.stream);
+    c.dCubTemp.reserve(std::max(t1, t2));
+    size_t tb = c.dCubTemp.cap;
+    LGPU_CUDA(cub::DeviceRadixSort::SortPairs(c.dCubTemp.p, tb, c.dClassKeys.p, c.dClassKeysB.p, c.dOrder.p, c.dOrderB.p, nI, 0, 64,
+                                              c.stream));
+    gatherU64Kernel<<<g, 256, 0, c.stream>>>(c.dPlaneWords.p, c.dOrderB.p, n, c.dPlaneWordsB.p);
+    tb = c.dCubTemp.cap;
+    LGPU_CUDA(cub::DeviceScan::ExclusiveSum(c.dCubTemp.p, tb, c.dPlaneWordsB.p, c.dTraceOff.p, nI, c.stream));
+    LGPU_CUDA(cudaGetLastError());
+    unsigned int       info[3 * NC + 1];
+    unsigned long long cells = 0, lastOff = 0, lastWords = 0;
+    LGPU_CUDA(cudaMemcpyAsync(info, c.dClassInfo.p, sizeof(info), cudaMemcpyDeviceToHost, c.stream));
+    LGPU_CUDA(cudaMemcpyAsync(&cells, c.dCounters.p, 8, cudaMemcpyDeviceToHost, c.stream));
+    LGPU_CUDA(cudaMemcpyAsync(&lastOff, c.dTraceOff.p + (n - 1), 8, cudaMemcpyDeviceToHost, c.stream));
+    LGPU_CUDA(cudaMemcpyAsync(&lastWords, c.dPlaneWordsB.p + (n - 1), 8, cudaMemcpyDeviceToHost, c.stream));
+    syncStream(c);
+    if (st)
+        st->kernel_launches += 2 + 2;
+    unsigned int classStart[NC + 1];
+    classStart[0] = 0;
+    for (int cls = 0; cls < NC; ++cls)
+        classStart[cls + 1] = classStart[cls] + info[cls];
+    unsigned int const nPacked = classStart[NP];
+    uint64_t const     total   = lastOff + lastWords;
+
+    // groups of sorted slots whose planes fit the budget of one launch (almost always one group)
+    uint64_t const kMaxPlaneWords = c.maxPlaneWords;
+    struct Group
+    {
+        unsigned int b, e;
+        uint64_t     base, words;
+    };
+    std::vector<Group> groups;
+    if (nPacked)
+    {
+        if (total <= kMaxPlaneWords)
+            groups.push_back({0u, nPacked, 0ull, total});
+        else
+        {
+            std::vector<unsigned long long> off(nPacked + 1);
+            LGPU_CUDA(cudaMemcpyAsync(off.data(), c.dTraceOff.p, nPacked * 8ull, cudaMemcpyDeviceToHost, c.stream));
+            syncStream(c);
+            off[nPacked] = total;
+            unsigned int b = 0;
+            while (b < nPacked)
             {
-                case 1: launchDpxTrace<1>(c, P, pc.maxNt); break;
-                case 2: launchDpxTrace<2>(c, P, pc.maxNt); break;
-                case 3: launchDpxTrace<3>(c, P, pc.maxNt); break;
-                case 4: launchDpxTrace<4>(c, P, pc.maxNt); break;
-                case 5: launchDpxTrace<5>(c, P, pc.maxNt); break;
-                case 6: launchDpxTrace<6>(c, P, pc.maxNt); break;
-                case 8: launchDpxTrace<8>(c, P, pc.maxNt); break;
-                case 10: launchDpxTrace<10>(c, P, pc.maxNt); break;
-                case 12: launchDpxTrace<12>(c, P, pc.maxNt); break;
-                case 16: launchDpxTrace<16>(c, P, pc.maxNt); break;
-                case 24: launchDpxTrace<24>(c, P, pc.maxNt); break;
-                default: launchDpxTrace<32>(c, P, pc.maxNt); break;
+                unsigned int e = b + 1;
+                while (e < nPacked && off[e + 1] - off[b] <= kMaxPlaneWords)
+                    ++e;
+                groups.push_back({b, e, off[b], off[e] - off[b]});
+                b = e;
             }
-            off += cnt;
+        }
+    }
+    for (Group const & gr : groups)
+    {
+        c.dPlanes.reserve(gr.words);
+        for (int cls = 0; cls < NP; ++cls)
+        {
+            unsigned int const lo = std::max(classStart[cls], gr.b), hi = std::min(classStart[cls + 1], gr.e);
+            if (lo >= hi)
+                continue;
+            unsigned int const G = dpxGroupsOf(tab, cls);
+            LGPU_CUDA(cudaMemsetAsync(c.dWork.p + cls, 0, 4, c.stream));
+            DpxParams P    = baseDpxParams(c, dTasks, n);
+            P.order        = c.dOrderB.p;
+            P.keys         = c.dClassKeysB.p;
+            P.nJobs        = (hi - lo + G - 1) / G;
+            P.slotBase     = lo;
+            P.nSlots       = hi - lo;
+            P.workCounter  = c.dWork.p + cls;
+            P.scores       = c.dScores2.p;
+            P.planes       = c.dPlanes.p;
+            P.planeOff     = c.dTraceOff.p;
+            P.planeOffBase = gr.base;
+            P.bestCol      = c.dBestPos.p;
+            (tab == kDpxTabPriv ? kDpxLaunchPrivTr[cls] : kDpxLaunchTrace32[cls])(c, P, info[NC + cls]);
             if (st)
                 st->kernel_launches += 1;
         }
-        TracebackDpxParams TP{};
-        TP.ix        = c.index->dev;
-        TP.Q         = c.Q;
-        TP.tasks     = dTasks;
-        TP.order     = c.dOrder.p;
-        TP.nTasks    = total;
-        TP.matrix    = c.dMatrix.p;
-        TP.go        = c.scoring.gapOpenSeqan;
-        TP.ge        = c.scoring.gapExtend;
-        TP.kOf       = c.dTraceK.p;
-        TP.scores    = c.dScores2.p;
-        TP.bestCol   = c.dBestPos.p;
-        TP.planes    = c.dPlanes.p;
-        TP.planeOff  = c.dTraceOff.p;
-        TP.out       = c.dHits.p;
-        tracebackDpxKernel<<<gridFor(total, 128), 128, 0, c.stream>>>(TP);
+        TracebackResParams TP{};
+        TP.ix           = c.index->dev;
+        TP.Q            = c.Q;
+        TP.tasks        = dTasks;
+        TP.order        = c.dOrderB.p;
+        TP.keys         = c.dClassKeysB.p;
+        TP.slotFirst    = gr.b;
+        TP.nSlots       = gr.e - gr.b;
+        TP.tab          = tab;
+        TP.matrix       = c.dMatrix.p;
+        TP.go           = c.scoring.gapOpenSeqan;
+        TP.ge           = c.scoring.gapExtend;
+        TP.scores       = c.dScores2.p;
+        TP.bestCol      = c.dBestPos.p;
+        TP.planes       = c.dPlanes.p;
+        TP.planeOff     = c.dTraceOff.p;
+        TP.planeOffBase = gr.base;
+        TP.out          = c.dHits.p;
+        unsigned int const tbGrid = gridFor(static_cast<unsigned long long>(TP.nSlots) * 32, 32 * kTbWarps);
+        tracebackResKernel<<<tbGrid, 32 * kTbWarps, 0, c.stream>>>(TP);
         LGPU_CUDA(cudaGetLastError());
+        if (st)
+            st->kernel_launches += 1;
         if (c.params.want_cigar)
-            emitCigars(c, c.dOrder.p, total, [&](unsigned int * ops, unsigned int const * offs, unsigned int base) {
+            emitCigars(c, c.dOrderB.p + gr.b, TP.nSlots, [&](unsigned int * ops, unsigned int const * offs, unsigned int base) {
                 TP.emit      = 1;
                 TP.cigarOps  = ops;
                 TP.cigarOff  = offs;
                 TP.cigarBase = base;
-                tracebackDpxKernel<<<gridFor(total, 128), 128, 0, c.stream>>>(TP);
+                tracebackResKernel<<<tbGrid, 32 * kTbWarps, 0, c.stream>>>(TP);
             }, st);
-        syncStream(c); // the staging arrays are reused by the next group
-        if (st)
-            st->kernel_launches += 1;
-        group.clear();
-        groupOrder.clear();
-        groupWords = 0;
-    };
-    for (int cls = 0; cls < kNumTraceClasses && !useCk; ++cls)
-    {
-        std::vector<unsigned int> const & L = lists[cls];
-        if (L.empty())
-            continue;
-        anyDpx      = true;
-        int const K = dpxTraceK(cls);
-        size_t    begin = 0;
-        while (begin < L.size())
-        {
-            unsigned int maxNt = 0;
-            size_t       end   = begin;
-            while (end < L.size())
-            {
-                unsigned int const nt = tasks[L[end]].subj_end - tasks[L[end]].subj_start;
-                uint64_t const     w  = dpxTracePlaneWords(K, nt);
-                if (groupWords + w > kMaxPlaneWords && (end > begin || !group.empty()))
-                    break;
-                planeOff[L[end]] = groupWords;
-                kOf[L[end]]      = static_cast<unsigned char>(K);
-                groupWords += w;
-                maxNt = std::max(maxNt, nt);
-                groupOrder.push_back(L[end]);
-                ++end;
-            }
-            if (end > begin)
-                group.push_back({cls, begin, end, maxNt});
-            if (end < L.size()) // budget reached: run what we have, continue with the rest
-                flushGroup();
-            begin = end;
-        }
-    }
-    flushGroup();
-    if (anyDpx || anyCk)
-    {
-        LGPU_CUDA(cudaMemcpyAsync(c.hHits.p, c.dHits.p, n * sizeof(lgpu_hit), cudaMemcpyDeviceToHost, c.stream));
-        syncStream(c);
-        for (int cls = 0; cls < nPackedClass; ++cls)
-            for (unsigned int i : lists[cls])
-                hostOut[i] = c.hHits.p[i];
     }
 
-    // ---- scalar class ----
-    std::vector<unsigned int> const & LS = lists.back();
-    if (!LS.empty())
+    // ---- scalar class: the last slots of the sorted order ----
+    unsigned int const nScalar = n - nPacked;
+    if (nScalar)
     {
-        std::vector<lgpu_match> sub(LS.size());
-        for (size_t k = 0; k < LS.size(); ++k)
-            sub[k] = tasks[LS[k]];
-        c.dTasksScalar.reserve(sub.size());
-        LGPU_CUDA(cudaMemcpyAsync(c.dTasksScalar.p, sub.data(), sub.size() * sizeof(lgpu_match), cudaMemcpyHostToDevice, c.stream));
+        c.dTasksScalar.reserve(nScalar);
+        gatherTasksKernel<<<gridFor(nScalar, 256), 256, 0, c.stream>>>(dTasks, c.dOrderB.p + nPacked, nScalar, c.dTasksScalar.p);
+        std::vector<lgpu_match> sub(nScalar);
+        LGPU_CUDA(cudaMemcpyAsync(sub.data(), c.dTasksScalar.p, nScalar * sizeof(lgpu_match), cudaMemcpyDeviceToHost, c.stream));
         syncStream(c);
-        runTraceScalar(c, sub.data(), sub.size(), c.dTasksScalar.p, st);
-        for (size_t k = 0; k < LS.size(); ++k)
-            hostOut[LS[k]] = c.hHits.p[k];
+        // the sorted order is not needed by the scalar kernels' scratch arrays, but its tail is the output index
+        c.dScalarIdx.reserve(nScalar);
+        LGPU_CUDA(cudaMemcpyAsync(c.dScalarIdx.p, c.dOrderB.p + nPacked, nScalar * 4ull, cudaMemcpyDeviceToDevice, c.stream));
+        runTraceScalar(c, sub.data(), nScalar, c.dTasksScalar.p, c.dScalarIdx.p, st);
+        if (st)
+            st->kernel_launches += 1;
     }
     if (st)
     {
@@ -1386,8 +1350,8 @@ static void runTracePass(lgpu_ctx & c, lgpu_match const * tasks, size_t n, lgpu_
     }
 }
 
-// iterateMatches for one phase: c.dMatches[0..nMatches) -> hits appended to c.hits
-static void runExtension(lgpu_ctx & c, uint64_t nMatches, uint8_t phase, EValueComputer & ev, lgpu_stats * st)
+// iterateMatches for one phase: c.dMatches[0..nMatches) -> records appended to c.dAllHits (device)
+static void runExtension(lgpu_ctx & c, uint64_t nMatches, uint8_t phase, lgpu_stats * st)
 {
     uint64_t const nTasks = runMerge(c, c.dMatches.p, nMatches, st);
     if (nTasks == 0)
@@ -1423,116 +1387,243 @@ static void runExtension(lgpu_ctx & c, uint64_t nMatches, uint8_t phase, EValueC
     }
     if (nKeep == 0)
         return;
-    // the survivors are few (one per reported hit): a host copy of their descriptors lays out the trace buffer
-    c.hTasks.reserve(nKeep);
-    LGPU_CUDA(cudaMemcpyAsync(c.hTasks.p, c.dTasks2.p, nKeep * sizeof(lgpu_match), cudaMemcpyDeviceToHost, c.stream));
-    syncStream(c);
-    size_t const base = c.hits.size();
-    c.hits.resize(base + nKeep);
-    runTracePass(c, c.hTasks.p, nKeep, c.dTasks2.p, c.hits.data() + base, st);
+    runTracePass(c, c.dTasks2.p, nKeep, st);
 
-    // host: doubles, identity cut-off (src/search_algo.hpp:1308-1322)
-    HostTimer ht(st ? &st->ms_host : nullptr);
-    size_t    out = base;
-    for (size_t i = base; i < base + nKeep; ++i)
+    // identity cut-off, phase, "query is done" flags (src/search_algo.hpp:1308-1322); survivors join the batch's records
+    c.dAllHits.grow(c.nAll + nKeep, c.nAll, c.stream);
+    c.dHead.reserve(nKeep);
+    c.dScan.reserve(nKeep);
+    LGPU_CUDA(cudaMemsetAsync(c.dCounters.p, 0, 8, c.stream));
+    unsigned int const g2 = gridFor(nKeep, 256);
+    postTraceKernel<<<g2, 256, 0, c.stream>>>(c.dHits.p, nKeep, c.params.id_cutoff, phase, c.dHead.p, c.dQryHasHit.p, c.dCounters.p);
+    if (st)
+        st->kernel_launches += 1;
+    if (c.params.id_cutoff > 0)
     {
-        lgpu_hit h = c.hits[i];
-        float const identity = static_cast<float>(100.0 * static_cast<float>(h.n_match) / static_cast<float>(h.aln_len));
-        if (identity < c.params.id_cutoff)
+        tb = 0;
+        cub::DeviceScan::InclusiveSum(nullptr, tb, c.dHead.p, c.dScan.p, static_cast<int>(nKeep), c.stream);
+        c.dCubTemp.reserve(tb);
+        tb = c.dCubTemp.cap;
+        LGPU_CUDA(cub::DeviceScan::InclusiveSum(c.dCubTemp.p, tb, c.dHead.p, c.dScan.p, static_cast<int>(nKeep), c.stream));
+        appendHitsKernel<<<g2, 256, 0, c.stream>>>(c.dHits.p, c.dHead.p, c.dScan.p, nKeep, c.dAllHits.p + c.nAll);
+        unsigned int       nOk = 0;
+        unsigned long long nFailed = 0;
+        LGPU_CUDA(cudaMemcpyAsync(&nOk, c.dScan.p + (nKeep - 1), 4, cudaMemcpyDeviceToHost, c.stream));
+        LGPU_CUDA(cudaMemcpyAsync(&nFailed, c.dCounters.p, 8, cudaMemcpyDeviceToHost, c.stream));
+        syncStream(c);
+        c.nAll += nOk;
+        if (st)
         {
-            if (st)
-                ++st->hits_failed_identity;
-            continue;
+            st->kernel_launches += 2;
+            st->hits_failed_identity += nFailed;
         }
-        h.phase     = phase;
-        h.bit_score = ev.bits(h.score);
-        h.evalue    = ev.evalue(h.score, h.q_len);
-        c.hits[out++] = h;
     }
-    c.hits.resize(out);
+    else
+    {
+        // an identity below 0 does not exist: every record survives, in task order
+        LGPU_CUDA(cudaMemcpyAsync(c.dAllHits.p + c.nAll, c.dHits.p, nKeep * sizeof(lgpu_hit), cudaMemcpyDeviceToDevice, c.stream));
+        c.nAll += nKeep;
+    }
 }
 
-static void setThresholds(lgpu_ctx & c, EValueComputer & ev, lgpu_stats * st)
+// per-query integer thresholds of the pass-1 filter; the per-length values are cached across batches
+static void setThresholds(lgpu_ctx & c, lgpu_stats * st)
 {
-    HostTimer        ht(st ? &st->ms_host : nullptr);
-    uint64_t const   n = c.nQueries;
-    std::vector<int> minBit(n), minEval(n);
-    std::unordered_map<uint64_t, ScoreThresholds> cache;
+    HostTimer            ht(st ? &st->ms_host : nullptr);
+    uint64_t const       n = c.nQueries;
+    constexpr uint64_t   kDirect = 1u << 16;
+    if (c.thrByLen.empty())
+    {
+        c.thrByLen.resize(kDirect);
+        c.thrKnown.assign(kDirect, 0);
+    }
+    c.hMinBit.reserve(n);
+    c.hMinEval.reserve(n);
     for (uint64_t q = 0; q < n; ++q)
     {
-        uint64_t const len = c.qOffsHost[q + 1] - c.qOffsHost[q];
-        auto           it  = cache.find(len);
-        if (it == cache.end())
-            it = cache.emplace(len, scoreThresholds(c.params, ev, len)).first;
-        minBit[q]  = it->second.minBit;
-        minEval[q] = it->second.minEval;
+        uint64_t const  len = c.qOffsHost[q + 1] - c.qOffsHost[q];
+        ScoreThresholds t;
+        if (len < kDirect)
+        {
+            if (!c.thrKnown[len])
+            {
+                c.thrByLen[len] = scoreThresholds(c.params, *c.evc, len);
+                c.thrKnown[len] = 1;
+            }
+            t = c.thrByLen[len];
+        }
+        else
+        {
+            auto it = c.thrLong.find(len);
+            if (it == c.thrLong.end())
+                it = c.thrLong.emplace(len, scoreThresholds(c.params, *c.evc, len)).first;
+            t = it->second;
+        }
+        c.hMinBit.p[q]  = t.minBit;
+        c.hMinEval.p[q] = t.minEval;
     }
     c.dMinBit.reserve(n);
     c.dMinEval.reserve(n);
-    LGPU_CUDA(cudaMemcpyAsync(c.dMinBit.p, minBit.data(), n * 4, cudaMemcpyHostToDevice, c.stream));
-    LGPU_CUDA(cudaMemcpyAsync(c.dMinEval.p, minEval.data(), n * 4, cudaMemcpyHostToDevice, c.stream));
-    syncStream(c);
+    LGPU_CUDA(cudaMemcpyAsync(c.dMinBit.p, c.hMinBit.p, n * 4, cudaMemcpyHostToDevice, c.stream));
+    LGPU_CUDA(cudaMemcpyAsync(c.dMinEval.p, c.hMinEval.p, n * 4, cudaMemcpyHostToDevice, c.stream));
 }
 
-static void uploadActive(lgpu_ctx & c, std::vector<unsigned int> const & active)
+// iterativeSearchPre/Post (src/search_algo.hpp:1391-1460): the queries without a reported hit after phase 1 form
+// the active list of phase 2; built on the device, the host learns its size and the longest active query
+static unsigned int buildActiveList(lgpu_ctx & c, unsigned int & maxLen, lgpu_stats * st)
 {
-    c.dActive.reserve(active.size());
-    LGPU_CUDA(cudaMemcpyAsync(c.dActive.p, active.data(), active.size() * 4, cudaMemcpyHostToDevice, c.stream));
+    unsigned int const n = static_cast<unsigned int>(c.nQueries);
+    unsigned int const g = gridFor(n, 256);
+    c.dHead.reserve(n);
+    c.dScan.reserve(n);
+    c.dClassInfo.reserve(4);
+    LGPU_CUDA(cudaMemsetAsync(c.dClassInfo.p, 0, 4, c.stream));
+    notDoneKernel<<<g, 256, 0, c.stream>>>(c.dQryHasHit.p, n, c.dHead.p);
+    size_t tb = 0;
+    cub::DeviceScan::InclusiveSum(nullptr, tb, c.dHead.p, c.dScan.p, static_cast<int>(n), c.stream);
+    c.dCubTemp.reserve(tb);
+    tb = c.dCubTemp.cap;
+    LGPU_CUDA(cub::DeviceScan::InclusiveSum(c.dCubTemp.p, tb, c.dHead.p, c.dScan.p, static_cast<int>(n), c.stream));
+    activeEmitKernel<<<g, 256, 0, c.stream>>>(c.dHead.p, c.dScan.p, c.dQOffs.p, n, c.dActive.p, c.dClassInfo.p);
+    LGPU_CUDA(cudaGetLastError());
+    unsigned int nActive = 0;
+    maxLen               = 0;
+    LGPU_CUDA(cudaMemcpyAsync(&nActive, c.dScan.p + (n - 1), 4, cudaMemcpyDeviceToHost, c.stream));
+    LGPU_CUDA(cudaMemcpyAsync(&maxLen, c.dClassInfo.p, 4, cudaMemcpyDeviceToHost, c.stream));
     syncStream(c);
+    if (st)
+        st->kernel_launches += 3;
+    return nActive;
 }
 
-// the whole path for one batch on one context / one stream; hits end up in c.hits
+// writeRecords / _writeRecord on the device (kernels_finalize.cuh): c.dAllHits[0..nAll) -> c.finalDev[0..nFinal)
+static void finalizeOnDevice(lgpu_ctx & c, lgpu_stats * st)
+{
+    c.finalDev = c.dAllHits.p;
+    c.nFinal   = c.nAll;
+    if (!c.params.finalize || c.nAll == 0)
+        return;
+    if (c.nAll >= (1ull << 31))
+        throw ArgError("too many records in one batch; use smaller query batches");
+    unsigned int const n  = static_cast<unsigned int>(c.nAll);
+    int const          nI = static_cast<int>(n);
+    unsigned int const g  = gridFor(n, 256);
+    c.dFinIdx.reserve(n);
+    c.dFinIdx1.reserve(n);
+    c.dDropped.reserve(n);
+    c.dSegStart.reserve(n);
+    c.dSegStartB.reserve(n);
+    c.dHead.reserve(n);
+    c.dScan.reserve(n);
+    c.dFinal.reserve(n);
+    LGPU_CUDA(cudaMemsetAsync(c.dCounters.p, 0, 8 * sizeof(unsigned long long), c.stream));
+    iotaKernel<<<g, 256, 0, c.stream>>>(c.dFinIdx.p, n);
+    RecordLess const less1{c.dAllHits.p};
+    RankLess const   less2{c.dAllHits.p, c.dDropped.p};
+    size_t           t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+    cub::DeviceMergeSort::StableSortKeys(nullptr, t1, c.dFinIdx.p, nI, less1, c.stream);
+    cub::DeviceMergeSort::StableSortKeys(nullptr, t2, c.dFinIdx.p, nI, less2, c.stream);
+    cub::DeviceScan::InclusiveScan(nullptr, t3, c.dSegStart.p, c.dSegStartB.p, MaxOp(), nI, c.stream);
+    cub::DeviceScan::InclusiveSum(nullptr, t4, c.dHead.p, c.dScan.p, nI, c.stream);
+    c.dCubTemp.reserve(std::max(std::max(t1, t2), std::max(t3, t4)));
+    size_t tb = c.dCubTemp.cap;
+    LGPU_CUDA(cub::DeviceMergeSort::StableSortKeys(c.dCubTemp.p, tb, c.dFinIdx.p, nI, less1, c.stream));
+    markDuplicatesKernel<<<g, 256, 0, c.stream>>>(c.dAllHits.p, c.dFinIdx.p, n, c.dDropped.p, c.dCounters.p);
+    LGPU_CUDA(cudaMemcpyAsync(c.dFinIdx1.p, c.dFinIdx.p, n * 4ull, cudaMemcpyDeviceToDevice, c.stream));
+    tb = c.dCubTemp.cap;
+    LGPU_CUDA(cub::DeviceMergeSort::StableSortKeys(c.dCubTemp.p, tb, c.dFinIdx.p, nI, less2, c.stream));
+    queryHeadKernel<<<g, 256, 0, c.stream>>>(c.dAllHits.p, c.dFinIdx.p, c.dDropped.p, n, c.dSegStart.p);
+    tb = c.dCubTemp.cap;
+    LGPU_CUDA(cub::DeviceScan::InclusiveScan(c.dCubTemp.p, tb, c.dSegStart.p, c.dSegStartB.p, MaxOp(), nI, c.stream));
+    rankCutKernel<<<g, 256, 0, c.stream>>>(c.dFinIdx.p, c.dDropped.p, c.dSegStartB.p, n, c.params.max_matches, c.dHead.p,
+                                           c.dCounters.p + 1);
+    tb = c.dCubTemp.cap;
+    LGPU_CUDA(cub::DeviceScan::InclusiveSum(c.dCubTemp.p, tb, c.dHead.p, c.dScan.p, nI, c.stream));
+    gatherFinalKernel<<<g, 256, 0, c.stream>>>(c.dAllHits.p, c.dFinIdx.p, c.dHead.p, c.dScan.p, n, c.dFinal.p);
+    countPairsKernel<<<g, 256, 0, c.stream>>>(c.dAllHits.p, c.dFinIdx1.p, c.dDropped.p, n, c.dCounters.p + 3);
+    LGPU_CUDA(cudaGetLastError());
+    unsigned long long cnt[4];
+    unsigned int       nFin = 0;
+    LGPU_CUDA(cudaMemcpyAsync(cnt, c.dCounters.p, sizeof(cnt), cudaMemcpyDeviceToHost, c.stream));
+    LGPU_CUDA(cudaMemcpyAsync(&nFin, c.dScan.p + (n - 1), 4, cudaMemcpyDeviceToHost, c.stream));
+    syncStream(c);
+    c.finalDev = c.dFinal.p;
+    c.nFinal   = nFin;
+    if (st)
+    {
+        st->kernel_launches += 7 + 4;
+        st->hits_duplicate2 += cnt[0];
+        st->hits_abundant += cnt[1];
+        st->qrys_with_hit += cnt[2];
+        st->pairs += cnt[3];
+        st->hits_final += nFin;
+    }
+}
+
+// the whole path for one batch on one context / one stream; records end up in c.finalDev (device) and c.hits (host)
 static void searchOne(lgpu_ctx & c, BatchView const & qb, lgpu_stats * st)
 {
     LGPU_CUDA(cudaSetDevice(c.index->device));
     SearchThreadScope const scope; // counted by the host-wait policy (effectiveSyncMode)
     c.hits.clear();
     c.cigar.clear();
+    c.nAll       = 0;
+    c.nFinal     = 0;
+    c.finalDev   = nullptr;
+    c.timersUsed = 0;
     uploadQueries(c, qb, st);
     if (!c.nQueries)
         return;
-    EValueComputer ev(c.scoring.ka, c.index->dbTotalLength, c.di.qIsTranslated);
-    setThresholds(c, ev, st);
-    std::vector<unsigned int> active(c.nQueries);
-    for (uint64_t i = 0; i < c.nQueries; ++i)
-        active[i] = static_cast<unsigned int>(i);
-    uploadActive(c, active);
-    auto const maxLen = [&](std::vector<unsigned int> const & a) {
-        uint64_t m = 0;
-        for (unsigned int q : a)
-            m = std::max(m, c.qOffsHost[q + 1] - c.qOffsHost[q]);
-        return static_cast<unsigned int>(m);
-    };
+    if (!c.evc)
+        c.evc = std::make_unique<EValueComputer>(c.scoring.ka, c.index->dbTotalLength, c.di.qIsTranslated);
+    setThresholds(c, st);
+    unsigned int const n = static_cast<unsigned int>(c.nQueries);
+    c.dActive.reserve(n);
+    c.dQryHasHit.reserve(n);
+    iotaKernel<<<gridFor(n, 256), 256, 0, c.stream>>>(c.dActive.p, n);
+    LGPU_CUDA(cudaMemsetAsync(c.dQryHasHit.p, 0, n * 4ull, c.stream));
+    if (st)
+        st->kernel_launches += 1;
     if (c.params.iterative_search)
     {
-        uint64_t nM = runSeeding(c, c.params.opts0, c.dActive.p, static_cast<unsigned int>(active.size()), maxLen(active), st);
-        runExtension(c, nM, 1, ev, st);
-        // iterativeSearchPre/Post: queries with at least one surviving hit are done
-        std::vector<uint8_t> ok(c.nQueries, 0);
-        for (lgpu_hit const & h : c.hits)
-            ok[h.q_id] = 1;
-        active.clear();
-        for (uint64_t i = 0; i < c.nQueries; ++i)
-            if (!ok[i])
-                active.push_back(static_cast<unsigned int>(i));
-        if (!active.empty())
+        uint64_t nM = runSeeding(c, c.params.opts0, c.dActive.p, n, c.maxQueryLen, st);
+        runExtension(c, nM, 1, st);
+        unsigned int       maxLen  = 0;
+        unsigned int const nActive = buildActiveList(c, maxLen, st);
+        if (nActive)
         {
-            uploadActive(c, active);
-            nM = runSeeding(c, c.params.opts, c.dActive.p, static_cast<unsigned int>(active.size()), maxLen(active), st);
-            runExtension(c, nM, 2, ev, st);
+            nM = runSeeding(c, c.params.opts, c.dActive.p, nActive, maxLen, st);
+            runExtension(c, nM, 2, st);
         }
     }
     else
     {
-        uint64_t const nM = runSeeding(c, c.params.opts, c.dActive.p, static_cast<unsigned int>(active.size()), maxLen(active), st);
-        runExtension(c, nM, 2, ev, st);
+        uint64_t const nM = runSeeding(c, c.params.opts, c.dActive.p, n, c.maxQueryLen, st);
+        runExtension(c, nM, 2, st);
     }
-    lgpu_stats dummy{};
-    if (c.params.finalize)
+    finalizeOnDevice(c, st);
+    // records to the host; the doubles (bit score, e-value) come from the host's tables
+    if (c.nFinal)
     {
+        c.hHits.reserve(c.nFinal);
+        {
+            StageTimer t(c, st ? &st->ms_d2h : nullptr);
+            LGPU_CUDA(cudaMemcpyAsync(c.hHits.p, c.finalDev, c.nFinal * sizeof(lgpu_hit), cudaMemcpyDeviceToHost, c.stream));
+        }
+        syncStream(c);
         HostTimer ht(st ? &st->ms_host : nullptr);
-        finalizeRecords(c.hits, c.params.max_matches, st ? *st : dummy);
+        c.hits.resize(c.nFinal);
+        for (uint64_t i = 0; i < c.nFinal; ++i)
+        {
+            lgpu_hit h  = c.hHits.p[i];
+            h.bit_score = c.evc->bitsCached(h.score);
+            h.evalue    = c.evc->evalueCached(h.score, h.q_len);
+            c.hits[i]   = h;
+        }
     }
+    else
+        syncStream(c);
+    resolveTimers(c);
 }
 
 static std::unique_ptr<lgpu_ctx> makeContext(lgpu_index const * ix, lgpu_params const & p);
@@ -1593,9 +1684,11 @@ static void searchBatch(lgpu_ctx & c, lgpu_query_batch const & qb, lgpu_hits * o
     unsigned int const nW = (c.streams > 1 && all.n >= 2 * minSub)
                               ? static_cast<unsigned int>(std::min<uint64_t>(c.streams, all.n / minSub))
                               : 1;
+    c.lastParts.clear();
     if (nW == 1)
     {
         searchOne(c, all, st);
+        c.lastParts.push_back({&c, 0ull, 0ull, c.nFinal});
     }
     else
     {
@@ -1652,6 +1745,7 @@ static void searchBatch(lgpu_ctx & c, lgpu_query_batch const & qb, lgpu_hits * o
             uint64_t const b    = all.n * w / nW;
             size_t const   base = c.hits.size();
             uint32_t const cigarBase = static_cast<uint32_t>(c.cigar.size());
+            c.lastParts.push_back({&wc, b, static_cast<uint64_t>(cigarBase), wc.nFinal});
             c.hits.insert(c.hits.end(), wc.hits.begin(), wc.hits.end());
             c.cigar.insert(c.cigar.end(), wc.cigar.begin(), wc.cigar.end());
             for (size_t i = base; i < c.hits.size(); ++i)
@@ -1758,10 +1852,8 @@ static std::unique_ptr<lgpu_ctx> lgpu::makeContext(lgpu_index const * ix, lgpu_p
     if (char const * e = std::getenv("LAMBDA_B200_TRACE"))
     {
         c->forceScalarTrace = !std::strcmp(e, "scalar");
-        c->planeTrace       = std::strcmp(e, "ckpt") != 0;
     }
     // the packed kernel stores (score - gapOpen) as int8 profile bytes with -128 reserved for "null"
-    bool nonNeg = true;
     c->dpxOk = c->scoring.alphSize < 32 && c->scoring.gapOpenSeqan <= c->scoring.gapExtend && c->scoring.gapExtend <= 0;
     for (int a = 0; a < c->scoring.alphSize; ++a)
         for (int b = 0; b < c->scoring.alphSize; ++b)
@@ -1770,11 +1862,29 @@ static std::unique_ptr<lgpu_ctx> lgpu::makeContext(lgpu_index const * ix, lgpu_p
             int const w = c->scoring.matrixRev[a * 32 + b] - c->scoring.gapOpenSeqan;
             if (v < -127 || v > 127 || w < -127 || w > 127)
                 c->dpxOk = false;
-            if (v < 0 || w < 0)
-                nonNeg = false;
         }
-    // the score kernel adds the profile bytes with a plain 32-bit add: they must not be negative
-    c->dpxScoreOk = c->dpxOk && (LGPU_DPX_FORM == 0 || nonNeg);
+    c->dpxScoreOk = c->dpxOk;
+    // Small alphabets (nucleotide / bisulfite searches: about one alignment per read) build one query profile per
+    // group instead of one per warp, so the groups of a warp can carry different reads.  LAMBDA_B200_PROFILE=
+    // shared|private forces either (tests).
+    c->privProfiles = c->scoring.alphSize + 1 <= 8;
+    if (char const * e = std::getenv("LAMBDA_B200_PROFILE"))
+        c->privProfiles = !std::strcmp(e, "private") ? true : !std::strcmp(e, "shared") ? false : c->privProfiles;
+    c->traceTab = c->privProfiles ? kDpxTabPriv : kDpxTabTrace32;
+    // residue-plane traceback: neighbouring cells must differ by less than half the residue range
+    {
+        int mx = -128, mn = 127;
+        for (int a = 0; a < c->scoring.alphSize; ++a)
+            for (int b = 0; b < c->scoring.alphSize; ++b)
+            {
+                mx = std::max(mx, std::max<int>(c->scoring.matrix[a * 32 + b], c->scoring.matrixRev[a * 32 + b]));
+                mn = std::min(mn, std::min<int>(c->scoring.matrix[a * 32 + b], c->scoring.matrixRev[a * 32 + b]));
+            }
+        int const go = c->scoring.gapOpenSeqan;
+        c->resTraceOk = c->dpxOk && go < 0 && c->scoring.gapExtend <= 0 && mx - go <= 127 && 2 * (mx - go) - mn < 256;
+    }
+    if (char const * e = std::getenv("LAMBDA_B200_PLANE_MB")) // tests: force several launch groups
+        c->maxPlaneWords = static_cast<uint64_t>(std::max(1, std::atoi(e))) * (1u << 20) / 4;
     return c;
 }
 
@@ -1953,31 +2063,73 @@ int lgpu_search_batch(lgpu_ctx * c, lgpu_query_batch const * q, lgpu_hits * out,
     return guarded(&c->err, [&] { searchBatch(*c, *q, out, stats); });
 }
 
+int lgpu_ctx_export_hits(lgpu_ctx * c, void * devDst, uint64_t capRecords, uint64_t firstQuery, uint64_t * nOut)
+{
+    if (!c || !nOut || (capRecords && !devDst))
+        return LGPU_ERR_ARG;
+    return guarded(&c->err, [&] {
+        LGPU_CUDA(cudaSetDevice(c->index->device));
+        uint64_t total = 0;
+        for (auto const & part : c->lastParts)
+            total += part.n;
+        *nOut = total;
+        if (total > capRecords)
+            return; // the caller learns the size it needs and calls again
+        lgpu_hit * dst = static_cast<lgpu_hit *>(devDst);
+        uint64_t   off = 0;
+        for (auto const & part : c->lastParts)
+        {
+            if (part.n)
+                exportHitsKernel<<<gridFor(part.n, 256), 256, 0, c->stream>>>(part.ctx->finalDev, part.n,
+                                                                               static_cast<unsigned int>(firstQuery + part.qBase),
+                                                                               static_cast<unsigned int>(part.cigarBase), dst + off);
+            off += part.n;
+        }
+        LGPU_CUDA(cudaGetLastError());
+        syncStream(*c);
+    });
+}
+
+int lgpu_hits_fill_scores(lgpu_ctx * c, lgpu_hit * hits, uint64_t n)
+{
+    if (!c || (n && !hits))
+        return LGPU_ERR_ARG;
+    return guarded(&c->err, [&] {
+        if (!c->evc)
+            c->evc = std::make_unique<EValueComputer>(c->scoring.ka, c->index->dbTotalLength, c->di.qIsTranslated);
+        for (uint64_t i = 0; i < n; ++i)
+        {
+            hits[i].bit_score = c->evc->bitsCached(hits[i].score);
+            hits[i].evalue    = c->evc->evalueCached(hits[i].score, hits[i].q_len);
+        }
+    });
+}
+
 int lgpu_seed_batch(lgpu_ctx * c, lgpu_query_batch const * q, int phase, lgpu_match const ** matches, uint64_t * n,
                     lgpu_stats * stats)
 {
     if (!c || !q || !matches || !n || (phase != 1 && phase != 2))
         return LGPU_ERR_ARG;
     return guarded(&c->err, [&] {
+        c->timersUsed = 0;
         LGPU_CUDA(cudaSetDevice(c->index->device));
         {
             std::vector<uint64_t> offsTmp;
             uploadQueries(*c, viewOf(*c, *q, offsTmp), stats);
         }
-        std::vector<unsigned int> active(c->nQueries);
-        for (uint64_t i = 0; i < c->nQueries; ++i)
-            active[i] = static_cast<unsigned int>(i);
-        uploadActive(*c, active);
-        uint64_t maxLen = 0;
-        for (uint64_t i = 0; i < c->nQueries; ++i)
-            maxLen = std::max(maxLen, c->qOffsHost[i + 1] - c->qOffsHost[i]);
+        unsigned int const nQ = static_cast<unsigned int>(c->nQueries);
+        c->dActive.reserve(nQ);
+        if (nQ)
+            iotaKernel<<<gridFor(nQ, 256), 256, 0, c->stream>>>(c->dActive.p, nQ);
+        uint64_t const maxLen = c->maxQueryLen;
         uint64_t const nM = runSeeding(*c, phase == 1 ? c->params.opts0 : c->params.opts, c->dActive.p,
-                                       static_cast<unsigned int>(active.size()), static_cast<unsigned int>(maxLen), stats);
+                                       nQ, static_cast<unsigned int>(maxLen), stats);
         c->matchesHost.resize(nM);
         if (nM)
             LGPU_CUDA(cudaMemcpyAsync(c->matchesHost.data(), c->dMatches.p, nM * sizeof(lgpu_match), cudaMemcpyDeviceToHost,
                                       c->stream));
         syncStream(*c);
+        resolveTimers(*c);
         *matches = c->matchesHost.data();
         *n       = nM;
     });
@@ -1989,6 +2141,7 @@ int lgpu_merge_matches(lgpu_ctx * c, lgpu_query_batch const * q, lgpu_match cons
     if (!c || !q || !merged || !nMerged || (nIn && !in))
         return LGPU_ERR_ARG;
     return guarded(&c->err, [&] {
+        c->timersUsed = 0;
         LGPU_CUDA(cudaSetDevice(c->index->device));
         {
             std::vector<uint64_t> offsTmp;
@@ -2003,6 +2156,7 @@ int lgpu_merge_matches(lgpu_ctx * c, lgpu_query_batch const * q, lgpu_match cons
             LGPU_CUDA(cudaMemcpyAsync(c->matchesHost.data(), c->dMerged.p, nOut * sizeof(lgpu_match), cudaMemcpyDeviceToHost,
                                       c->stream));
         syncStream(*c);
+        resolveTimers(*c);
         *merged  = c->matchesHost.data();
         *nMerged = nOut;
     });
@@ -2032,6 +2186,7 @@ int lgpu_extend_scores(lgpu_ctx * c, lgpu_query_batch const * q, lgpu_match cons
     if (!c || !q || (n && (!win || !scores)))
         return LGPU_ERR_ARG;
     return guarded(&c->err, [&] {
+        c->timersUsed = 0;
         LGPU_CUDA(cudaSetDevice(c->index->device));
         {
             std::vector<uint64_t> offsTmp;
@@ -2046,6 +2201,7 @@ int lgpu_extend_scores(lgpu_ctx * c, lgpu_query_batch const * q, lgpu_match cons
         runScorePass(*c, c->dUserMatches.p, static_cast<unsigned int>(n), c->dScores.p, stats);
         LGPU_CUDA(cudaMemcpyAsync(scores, c->dScores.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
         syncStream(*c);
+        resolveTimers(*c);
     });
 }
 
@@ -2055,6 +2211,7 @@ int lgpu_extend_trace(lgpu_ctx * c, lgpu_query_batch const * q, lgpu_match const
     if (!c || !q || (n && (!win || !out)))
         return LGPU_ERR_ARG;
     return guarded(&c->err, [&] {
+        c->timersUsed = 0;
         LGPU_CUDA(cudaSetDevice(c->index->device));
         {
             std::vector<uint64_t> offsTmp;
@@ -2066,7 +2223,10 @@ int lgpu_extend_trace(lgpu_ctx * c, lgpu_query_batch const * q, lgpu_match const
         c->dUserMatches.reserve(n);
         LGPU_CUDA(cudaMemcpyAsync(c->dUserMatches.p, win, n * sizeof(lgpu_match), cudaMemcpyHostToDevice, c->stream));
         c->cigar.clear(); // with want_cigar the records index into the context's run buffer of THIS call
-        runTracePass(*c, win, n, c->dUserMatches.p, out, stats);
+        runTracePass(*c, c->dUserMatches.p, static_cast<unsigned int>(n), stats);
+        LGPU_CUDA(cudaMemcpyAsync(out, c->dHits.p, n * sizeof(lgpu_hit), cudaMemcpyDeviceToHost, c->stream));
+        syncStream(*c);
+        resolveTimers(*c);
     });
 }
 

@@ -85,6 +85,13 @@ __global__ void iotaKernel(unsigned int * p, unsigned long long n)
         p[t] = static_cast<unsigned int>(t);
 }
 
+__global__ void iotaFromKernel(unsigned int * p, unsigned int n, unsigned int first)
+{
+    unsigned int const t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n)
+        p[t] = first + t;
+}
+
 // After sorting, windows of one (qry, subj) pair form chains: element t continues the chain of t-1
 // iff same pair and end[t-1] >= start[t] (the reference's forward pass compares the untouched
 // end of the left element with the untouched start of the right one).  The reference's forward +
@@ -366,6 +373,7 @@ struct TracebackParams
     unsigned long long const * traceOff;
     unsigned int               K;            // columns per lane used by the fill kernel (storage: roundup4(K) bytes)
     lgpu_hit *                 out;
+    unsigned int const *       outIndex;     // record of task t goes to out[outIndex[t]] (nullptr: out[t])
     // second pass (lgpu_params.want_cigar): emit the runs of the path instead of the record
     int                        emit;
     unsigned int *             cigarOps;
@@ -476,10 +484,11 @@ __global__ void __launch_bounds__(128) tracebackKernel(TracebackParams P)
         flush();
     }
 
+    unsigned int const outSlot = P.outIndex ? P.outIndex[task] : task;
     if (P.emit)
     {
-        P.out[task].cigar_off = P.cigarBase + P.cigarOff[task];
-        P.out[task].cigar_len = nOps;
+        P.out[outSlot].cigar_off = P.cigarBase + P.cigarOff[task];
+        P.out[outSlot].cigar_len = nOps;
         return;
     }
     lgpu_hit h;
@@ -505,7 +514,15 @@ __global__ void __launch_bounds__(128) tracebackKernel(TracebackParams P)
     h.evalue     = 0.0;
     h.cigar_off  = 0;
     h.cigar_len  = 0;
-    P.out[task]  = h;
+    P.out[outSlot] = h;
+}
+
+// out[t] = in[idx[t]]
+__global__ void gatherTasksKernel(lgpu_match const * in, unsigned int const * idx, unsigned int n, lgpu_match * out)
+{
+    unsigned int const t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n)
+        out[t] = in[idx[t]];
 }
 
 // upper bound of the runs of every alignment: gaps and aligned stretches alternate

@@ -110,7 +110,9 @@ def test_our_arm_assembles_the_contract_line_with_a_fake_engine(tmp_path, extra)
     assert rf["achieved"] == pytest.approx(4e9 / 5e-3 / 1e9 * 10) and rf["frac"] == pytest.approx(rf["achieved"] / rf["peak"])
     assert rf["traffic"] is None or isinstance(rf["traffic"], float)
     rt = d["roofline_trace"]
-    assert rt["bound"] == "hbm" and rt["achieved"] == pytest.approx(3 * 3e8 / 3e-3 / 1e9) and 0 < rt["frac"] < 1
+    assert rt["bound"] == "int16-alu" and rt["achieved"] == pytest.approx(3e8 / 3e-3 / 1e9 * 10) and 0 < rt["frac"] < 1
+    assert rt["hbm"]["achieved"] == pytest.approx(1 * 3e8 / 3e-3 / 1e9) and 0 < rt["hbm"]["frac"] < 1  # 1 B per cell
+    assert d["kernel_sources_sha"] and d["scaling"] == "weak"
     assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} and d["e2e"]["h2d_bytes_per_step"] > 0
     assert "workload" in d["config"] and "model" not in d["config"]
     if "--band" in extra:

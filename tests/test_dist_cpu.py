@@ -6,7 +6,7 @@ import numpy as np
 import torch.multiprocessing as mp
 
 from lambda_b200._abi import HIT_DT
-from lambda_b200.dist import all_gather_hits, shard_queries, shard_range
+from lambda_b200.dist import DeviceHitGather, all_gather_hits, shard_queries, shard_range
 
 
 def _free_port():
@@ -48,6 +48,65 @@ def _worker(rank, world, port, n_queries, q):
     ok = ok and t2 == (len(expect) - len(expect[expect["q_id"] < shard_range(n_queries, 0, world)[1]]))
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
+
+
+class _FakeSearcher:
+    """stands in for lambda_b200.Searcher.export_hits: 'device' records are a numpy array, the destination a CPU tensor"""
+
+    def __init__(self, hits):
+        self.hits = hits
+
+    def export_hits(self, dev_ptr, cap_records, first_query):
+        import ctypes
+        if len(self.hits) <= cap_records and len(self.hits):
+            h = self.hits.copy()
+            h["q_id"] += first_query
+            ctypes.memmove(dev_ptr, h.ctypes.data, h.nbytes)
+        return len(self.hits)
+
+
+def _worker_device_gather(rank, world, port, n_queries, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    expect = []
+    for r in range(world):
+        rb, re = shard_range(n_queries, r, world)
+        h = _fake_hits(rb, re - rb, seed=100 + r)
+        h["q_id"] += rb
+        expect.append(h)
+    expect = np.concatenate(expect)
+    b, e = shard_range(n_queries, rank, world)
+    mine = _fake_hits(b, e - b, seed=100 + rank)
+    ok = True
+    for cap in (4 * n_queries, 3):  # roomy slots; slots that overflow and are grown collectively
+        g = DeviceHitGather(cap)
+        for _ in range(2):  # the buffers are reused step after step
+            g.start(_FakeSearcher(mine), first_query=b)
+            total = g.finish()
+            got = g.records()
+            ok = ok and total == len(expect) and len(got) == len(expect) and (got == expect).all()
+        ok = ok and (g.regrown == (0 if cap > 3 else 1))
+    g = DeviceHitGather(8)
+    g.start(_FakeSearcher(np.zeros(0, HIT_DT) if rank == 0 else mine[:5]), first_query=b)
+    ok = ok and g.finish() == 5 * (world - 1) and len(g.records()) == 5 * (world - 1)
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_device_hit_gather_gloo_world2():
+    """the fixed-capacity gather (count in the first word of every slot) incl. the collective regrow on overflow"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_device_gather, args=(r, 2, port, 37, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == {0: True, 1: True}
 
 
 def test_all_gather_hits_gloo_world2():

@@ -10,7 +10,7 @@ import lambda_b200
 import orc
 from cases import CASE_PROFILES, CASES, FUNNEL, N_CASE_PROFILES, load_golden, query_alph, query_encoding
 from lambda_b200 import synth
-from lambda_b200._abi import MATCH_DT
+from lambda_b200._abi import HIT_DT, MATCH_DT
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -111,12 +111,16 @@ def test_full_seed_hamming_search(golden_dir, case, domain, mode, monkeypatch):
     s.close(); ix.close(); o.close()
 
 
-@pytest.mark.parametrize("trace", ["ckpt", "planes", "scalar"])
+@pytest.mark.parametrize("trace,prof", [("planes", "auto"), ("planes", "private"), ("planes", "shared"), ("scalar", "auto")])
 @pytest.mark.parametrize("case,domain", [(c, d) for c, d, _ in CASES])
-def test_extension_matches_oracle(golden_dir, case, domain, trace, monkeypatch):
-    """DP pass 1 scores and the full pass-2 records (coordinates + statistics) for both trace paths:
-    packed DPX planes (default), checkpoints + tile recomputation, and the scalar trace-byte kernel"""
+def test_extension_matches_oracle(golden_dir, case, domain, trace, prof, monkeypatch):
+    """DP pass 1 scores and the full pass-2 records (coordinates + statistics) for both trace paths -- residue planes
+    (default) and the scalar trace-byte kernel -- and for both ways of filling a warp: one query profile per warp
+    (alignments of one query share it) and one per group (alignments of different queries side by side)"""
     monkeypatch.setenv("LAMBDA_B200_TRACE", trace)
+    monkeypatch.setenv("LAMBDA_B200_PROFILE", prof)
+    if prof == "private":
+        monkeypatch.setenv("LAMBDA_B200_PLANE_MB", "1")  # several launch groups of residue planes
     path, ids, res, offs = _load(golden_dir, case, domain)
     o = orc.Oracle(path)
     ix = lambda_b200.Index.load(path)
@@ -145,10 +149,11 @@ def test_extension_matches_oracle(golden_dir, case, domain, trace, monkeypatch):
     s.close(); ix.close(); o.close()
 
 
-@pytest.mark.parametrize("trace", ["ckpt", "planes", "scalar"])
-def test_extension_long_queries_multi_block(golden_dir, trace, monkeypatch):
+@pytest.mark.parametrize("trace,prof", [("planes", "auto"), ("planes", "private"), ("scalar", "auto")])
+def test_extension_long_queries_multi_block(golden_dir, trace, prof, monkeypatch):
     """queries longer than one 32*K column block (boundary row path) and long merged windows"""
     monkeypatch.setenv("LAMBDA_B200_TRACE", trace)
+    monkeypatch.setenv("LAMBDA_B200_PROFILE", prof)
     path = os.path.join(golden_dir, "prot_flat", "db.lba")
     o = orc.Oracle(path)
     ix = lambda_b200.Index.load(path)
@@ -178,9 +183,12 @@ def test_extension_long_queries_multi_block(golden_dir, trace, monkeypatch):
     s.close(); ix.close(); o.close()
 
 
-def test_score_kernel_all_length_classes(golden_dir):
-    """DP pass 1 over every (T, K) class of the packed DPX kernel plus the scalar fallback (> 2048),
-    with ragged windows (1 .. 2000 rows), related and unrelated pairs"""
+@pytest.mark.parametrize("prof", ["shared", "private"])
+def test_score_kernel_all_length_classes(golden_dir, prof, monkeypatch):
+    """DP pass 1 and pass 2 over every (T, K) class of the packed DPX kernels plus the scalar fallback (> 2048),
+    with ragged windows (1 .. 2000 rows), related and unrelated pairs; "private": the groups of a warp carry
+    alignments of DIFFERENT queries (mixed-query warps, the layout of the short-read searches)"""
+    monkeypatch.setenv("LAMBDA_B200_PROFILE", prof)
     path = os.path.join(golden_dir, "prot_flat", "db.lba")
     o = orc.Oracle(path)
     ix = lambda_b200.Index.load(path)
@@ -537,4 +545,47 @@ def test_queries_with_n_reproduce_reference(golden_dir, case, domain, profile, m
         assert sorted(s.m8(hits, ids)) == sorted(ref)
         for k in FUNNEL:
             assert int(st[k]) == funnel[k], k
+    s.close(); ix.close(); o.close()
+
+
+@pytest.mark.parametrize("case,domain,profile", [("prot_family", 0, "pairs-default"), ("prot_flat", 0, "none"),
+                                                 ("nucl", 1, "sensitive"), ("bisulfite", 2, "none")])
+def test_device_records_export_and_finalisation(golden_dir, case, domain, profile, monkeypatch):
+    """_writeRecord runs on the device (sort / unique / top-N): order, records and every counter (incl. pairs and
+    queries-with-hit) equal the oracle's host implementation; lgpu_ctx_export_hits hands the same records out of the
+    device buffer (query ids rebased, doubles filled in by lgpu_hits_fill_scores) -- also when the call was cut into
+    sub-batches; id_cutoff and max_matches exercise the compaction paths"""
+    import torch
+    path, ids, res, offs = _load(golden_dir, case, domain)
+    ix = lambda_b200.Index.load(path)
+    o = orc.Oracle(path)
+    for kw in ({}, {"id_cutoff": 60, "max_matches": 3}, {"finalize": 0}):
+        s, p = _pair(ix, o, case, domain, profile, **kw)
+        h_gpu, st_gpu = s.search(res, offs)
+        h_cpu, st_cpu = o.search(p, res, offs)
+        if kw.get("finalize", 1):
+            assert len(h_gpu) == len(h_cpu)
+            for f in HIT_INT_FIELDS + ["phase", "bit_score", "evalue"]:
+                assert (h_gpu[f] == h_cpu[f]).all(), (kw, f)
+        else:
+            assert sorted(s.m8(h_gpu, ids)) == sorted(o.m8(p, h_cpu, ids))
+        for k in FUNNEL:
+            assert int(st_gpu[k]) == int(st_cpu[k]), (kw, k)
+        # the same records straight from the device
+        buf = torch.zeros((len(h_gpu) + 1) * HIT_DT.itemsize, dtype=torch.uint8, device="cuda")
+        assert s.export_hits(buf.data_ptr(), 0, 7) == len(h_gpu)  # too small a buffer: only the count
+        n = s.export_hits(buf.data_ptr(), len(h_gpu) + 1, 1000)
+        dev = s.fill_scores(buf[: n * HIT_DT.itemsize].cpu().numpy().view(HIT_DT).copy())
+        assert n == len(h_gpu) and (dev["q_id"] == h_gpu["q_id"] + 1000).all()
+        dev["q_id"] -= 1000
+        assert (dev == h_gpu).all()
+        s.close()
+    # sub-batches: the export concatenates the workers' device buffers in query order
+    monkeypatch.setenv("LAMBDA_B200_MIN_SUBBATCH", "8")
+    s = lambda_b200.Searcher(ix, domain, profile, streams=3)
+    h, _ = s.search(res, offs)
+    buf = torch.zeros(max(len(h), 1) * HIT_DT.itemsize, dtype=torch.uint8, device="cuda")
+    n = s.export_hits(buf.data_ptr(), len(h), 0)
+    dev = s.fill_scores(buf[: n * HIT_DT.itemsize].cpu().numpy().view(HIT_DT).copy())
+    assert n == len(h) and (dev == h).all()
     s.close(); ix.close(); o.close()
