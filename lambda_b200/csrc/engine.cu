@@ -18,10 +18,13 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -298,11 +301,16 @@ struct lgpu_index
     uint64_t                 bytes         = 0;
     uint64_t                 dbTotalLength = 0;
     std::vector<uint64_t>    sbjDelimsHost; // host copy of dev.seqDelims (window checks of the stage API)
+    // depth-k prefix tables of the seeding kernels (kernels_fm.cuh seedPrefixCursor), built on first use
+    mutable std::mutex                      prefixMutex;
+    mutable std::map<unsigned int, uint2 *> prefixTabs;
     ~lgpu_index()
     {
         cudaSetDevice(device);
         for (void * p : allocs)
             cudaFree(p);
+        for (auto & kv : prefixTabs)
+            cudaFree(kv.second);
     }
 };
 
@@ -336,6 +344,8 @@ struct lgpu_ctx
     unsigned int               streams = 1;  // sub-batches in flight per lgpu_search_batch call (LAMBDA_B200_STREAMS)
     std::vector<std::unique_ptr<lgpu_ctx>> workers;
     int                        seedMode = 0; // LAMBDA_B200_SEED=thread|warp|block|spec forces one seeding kernel (tests); 0 = auto
+    bool                       seedTextElong = true; // unique cursors: locate once, compare texts (LAMBDA_B200_SEED_TEXT=0: LF steps)
+    bool                       seedPrefix    = true; // prefix table in front of the exact part of a seed (LAMBDA_B200_SEED_PREFIX=0: off)
     DevBuf<unsigned long long> dSeedCursors;
     DevBuf<unsigned int>       dSeedCounts;
     DevBuf<unsigned char>      dTrace;
@@ -384,8 +394,9 @@ struct lgpu_ctx
     PinnedBuf<lgpu_hit>   hHits;
     PinnedBuf<int>        hThresh;
 
-    // host results
-    std::vector<lgpu_hit>   hits;
+    // host results: the records of the last call (pinned; sub-batch workers write their slices directly)
+    PinnedBuf<lgpu_hit>     hResult;
+    uint64_t                nResult = 0;
     std::vector<uint32_t>   cigar;       // run-length ops of the hits (lgpu_params.want_cigar), see lgpu_hit::cigar_off
     DevBuf<unsigned int>    dCigarCap, dCigarOff, dCigar;
     PinnedBuf<unsigned int> hCigarStage;
@@ -688,6 +699,42 @@ static void uploadQueries(lgpu_ctx & c, BatchView const & qb, lgpu_stats * st)
         st->kernel_launches += 1;
 }
 
+// Depth of the prefix table for a seed whose exactly matched part has h1 symbols: as deep as 2^21 entries allow.
+static unsigned int prefixDepth(lgpu_index const & ix, unsigned int h1)
+{
+    uint64_t const A = ix.dev.sigma - 1;
+    if (A < 2 || ix.dev.nRows >= (1ull << 32))
+        return 0;
+    unsigned int k = 0;
+    uint64_t     n = 1;
+    while (k < h1 && n * A <= (1ull << 21))
+    {
+        n *= A;
+        ++k;
+    }
+    return k >= 2 ? k : 0;
+}
+
+static uint2 const * prefixTable(lgpu_index const & ix, unsigned int k, cudaStream_t stream)
+{
+    if (k == 0)
+        return nullptr;
+    std::lock_guard<std::mutex> lock(ix.prefixMutex);
+    auto it = ix.prefixTabs.find(k);
+    if (it != ix.prefixTabs.end())
+        return it->second;
+    uint64_t n = 1;
+    for (unsigned int i = 0; i < k; ++i)
+        n *= ix.dev.sigma - 1;
+    uint2 * tab = nullptr;
+    LGPU_CUDA(cudaMalloc(reinterpret_cast<void **>(&tab), n * sizeof(uint2)));
+    prefixTableKernel<<<gridFor(n, 128), 128, 0, stream>>>(ix.dev, k, static_cast<unsigned int>(n), tab);
+    LGPU_CUDA(cudaGetLastError());
+    LGPU_CUDA(cudaStreamSynchronize(stream));
+    ix.prefixTabs.emplace(k, tab);
+    return tab;
+}
+
 // search(): returns number of matches now in c.dMatches
 static uint64_t runSeeding(lgpu_ctx & c, lgpu_search_opts const & so, unsigned int const * dActive, unsigned int nActive,
                            unsigned int maxActiveLen, lgpu_stats * st)
@@ -720,6 +767,16 @@ static uint64_t runSeeding(lgpu_ctx & c, lgpu_search_opts const & so, unsigned i
         P.out              = c.dMatches.p;
         P.cap              = c.dMatches.cap;
         P.counters         = c.dCounters.p;
+        {
+            bool const         halfM = so.max_seed_dist != 0 && c.params.seed_half_exact;
+            unsigned int const h1    = P.fullHamming ? 0u : (halfM ? so.seed_length / 2 : so.seed_length);
+            P.prefixK                = c.seedPrefix ? prefixDepth(*c.index, h1) : 0u;
+            P.prefixTab              = prefixTable(*c.index, P.prefixK, c.stream);
+            P.textElong              = c.seedTextElong ? 1u : 0u;
+            for (int par = 0; par < 2; ++par)
+                for (int r = 0; r < 32; ++r)
+                    P.sbjRed[par][r] = c.Q.redTab[par][r] >= kNMarker ? 0xffu : c.Q.redTab[par][r];
+        }
         // Few queries (typically the phase-2 leftovers): latency matters -> one block per query, the seeds
         // of a query searched by 16 warps in parallel.  Many queries: throughput matters -> one warp per
         // query for half-exact seeds (wide search tree per seed), one thread per query for exact seeds
@@ -1560,22 +1617,21 @@ static void finalizeOnDevice(lgpu_ctx & c, lgpu_stats * st)
     }
 }
 
-// the whole path for one batch on one context / one stream; records end up in c.finalDev (device) and c.hits (host)
-static void searchOne(lgpu_ctx & c, BatchView const & qb, lgpu_stats * st)
+// the device part of the path for one batch on one context / one stream; the records end up in c.finalDev[0..nFinal)
+static void searchDevice(lgpu_ctx & c, BatchView const & qb, lgpu_stats * st)
 {
     LGPU_CUDA(cudaSetDevice(c.index->device));
     SearchThreadScope const scope; // counted by the host-wait policy (effectiveSyncMode)
-    c.hits.clear();
     c.cigar.clear();
     c.nAll       = 0;
     c.nFinal     = 0;
     c.finalDev   = nullptr;
     c.timersUsed = 0;
     uploadQueries(c, qb, st);
-    if (!c.nQueries)
-        return;
     if (!c.evc)
         c.evc = std::make_unique<EValueComputer>(c.scoring.ka, c.index->dbTotalLength, c.di.qIsTranslated);
+    if (!c.nQueries)
+        return;
     setThresholds(c, st);
     unsigned int const n = static_cast<unsigned int>(c.nQueries);
     c.dActive.reserve(n);
@@ -1602,27 +1658,31 @@ static void searchOne(lgpu_ctx & c, BatchView const & qb, lgpu_stats * st)
         runExtension(c, nM, 2, st);
     }
     finalizeOnDevice(c, st);
-    // records to the host; the doubles (bit score, e-value) come from the host's tables
+}
+
+// Second half of a search: the nFinal records of searchDevice() to `dst` (pinned host memory of the calling context),
+// query ids / cigar offsets rebased for sub-batches; the doubles (bit score, e-value) come from the host's tables.
+static void fetchRecords(lgpu_ctx & c, lgpu_hit * dst, uint32_t qBase, uint32_t cigarBase, lgpu_stats * st)
+{
+    LGPU_CUDA(cudaSetDevice(c.index->device));
     if (c.nFinal)
     {
-        c.hHits.reserve(c.nFinal);
-        {
-            StageTimer t(c, st ? &st->ms_d2h : nullptr);
-            LGPU_CUDA(cudaMemcpyAsync(c.hHits.p, c.finalDev, c.nFinal * sizeof(lgpu_hit), cudaMemcpyDeviceToHost, c.stream));
-        }
-        syncStream(c);
+        StageTimer t(c, st ? &st->ms_d2h : nullptr);
+        LGPU_CUDA(cudaMemcpyAsync(dst, c.finalDev, c.nFinal * sizeof(lgpu_hit), cudaMemcpyDeviceToHost, c.stream));
+    }
+    syncStream(c);
+    if (c.nFinal)
+    {
         HostTimer ht(st ? &st->ms_host : nullptr);
-        c.hits.resize(c.nFinal);
         for (uint64_t i = 0; i < c.nFinal; ++i)
         {
-            lgpu_hit h  = c.hHits.p[i];
-            h.bit_score = c.evc->bitsCached(h.score);
-            h.evalue    = c.evc->evalueCached(h.score, h.q_len);
-            c.hits[i]   = h;
+            lgpu_hit & h = dst[i];
+            h.bit_score  = c.evc->bitsCached(h.score);
+            h.evalue     = c.evc->evalueCached(h.score, h.q_len);
+            h.q_id += qBase;
+            h.cigar_off += cigarBase;
         }
     }
-    else
-        syncStream(c);
     resolveTimers(c);
 }
 
@@ -1685,9 +1745,13 @@ static void searchBatch(lgpu_ctx & c, lgpu_query_batch const & qb, lgpu_hits * o
                               ? static_cast<unsigned int>(std::min<uint64_t>(c.streams, all.n / minSub))
                               : 1;
     c.lastParts.clear();
+    c.nResult = 0;
     if (nW == 1)
     {
-        searchOne(c, all, st);
+        searchDevice(c, all, st);
+        c.hResult.reserve(c.nFinal);
+        fetchRecords(c, c.hResult.p, 0, 0, st);
+        c.nResult = c.nFinal;
         c.lastParts.push_back({&c, 0ull, 0ull, c.nFinal});
     }
     else
@@ -1704,59 +1768,133 @@ static void searchBatch(lgpu_ctx & c, lgpu_query_batch const & qb, lgpu_hits * o
         std::vector<std::vector<uint64_t>> subOffs(nW);
         std::vector<lgpu_stats>            wst(nW);
         std::vector<std::string>           err(nW);
-        std::vector<std::thread>           th;
         std::memset(wst.data(), 0, sizeof(lgpu_stats) * nW);
-        for (unsigned int w = 0; w < nW; ++w)
+        // every worker thread runs stage 1 (device) of its sub-batch, waits until all record counts are known, then
+        // stage 2: its records straight into its slice of the call's result buffer
+        struct Gate
+        {
+            std::mutex              m;
+            std::condition_variable cv;
+            unsigned int            arrived = 0;
+            bool                    open    = false;
+        } gate;
+        std::vector<uint64_t> recOff(nW + 1, 0), cigOff(nW + 1, 0);
+        std::vector<std::thread> th;
+        struct Joiner // an exception while spawning must not destroy joinable threads
+        {
+            std::vector<std::thread> & t;
+            ~Joiner()
+            {
+                for (auto & x : t)
+                    if (x.joinable())
+                        x.join();
+            }
+        } joiner{th};
+        std::vector<BatchView> views(nW);
+        for (unsigned int w = 0; w < nW; ++w) // everything that may fail before a thread exists
         {
             uint64_t const b = all.n * w / nW, e = all.n * (w + 1) / nW;
             subOffs[w].assign(all.offsets + b, all.offsets + e + 1);
             uint64_t const base = subOffs[w][0];
             for (auto & x : subOffs[w])
                 x -= base;
-            BatchView v;
-            v.residues    = all.residues + base;
-            v.resOnDevice = all.resOnDevice;
-            v.offsets     = subOffs[w].data();
-            v.n           = e - b;
-            lgpu_ctx * wc = c.workers[w].get();
-            LGPU_CUDA(cudaStreamWaitEvent(wc->stream, c.ev[2], 0));
-            th.emplace_back([wc, v, w, &wst, &err] {
+            views[w].residues    = all.residues + base;
+            views[w].resOnDevice = all.resOnDevice;
+            views[w].offsets     = subOffs[w].data();
+            views[w].n           = e - b;
+            LGPU_CUDA(cudaStreamWaitEvent(c.workers[w]->stream, c.ev[2], 0));
+        }
+        th.reserve(nW);
+        for (unsigned int w = 0; w < nW; ++w)
+        {
+            uint64_t const  b  = all.n * w / nW;
+            BatchView const v  = views[w];
+            lgpu_ctx *      wc = c.workers[w].get();
+            try
+            {
+            th.emplace_back([&, wc, v, w, b, nW] {
                 try
                 {
-                    searchOne(*wc, v, &wst[w]);
+                    searchDevice(*wc, v, &wst[w]);
+                }
+                catch (std::exception const & ex)
+                {
+                    err[w]     = ex.what();
+                    wc->nFinal = 0;
+                }
+                {
+                    // the last thread to arrive lays out the result buffer
+                    std::unique_lock<std::mutex> lock(gate.m);
+                    if (++gate.arrived >= nW)
+                    {
+                        try
+                        {
+                            for (unsigned int k = 0; k < nW; ++k)
+                            {
+                                recOff[k + 1] = recOff[k] + c.workers[k]->nFinal;
+                                cigOff[k + 1] = cigOff[k] + c.workers[k]->cigar.size();
+                            }
+                            if (cigOff[nW] > 0xffffffffull)
+                                throw ArgError("too many alignment operations in one batch; use smaller batches with want_cigar");
+                            cudaSetDevice(c.index->device);
+                            c.hResult.reserve(recOff[nW]);
+                        }
+                        catch (std::exception const & ex)
+                        {
+                            err[w] = ex.what();
+                        }
+                        gate.open = true;
+                        gate.cv.notify_all();
+                    }
+                    else
+                        gate.cv.wait(lock, [&] { return gate.open; });
+                }
+                bool anyErr = false;
+                for (auto const & e2 : err)
+                    anyErr = anyErr || !e2.empty();
+                if (anyErr)
+                    return;
+                try
+                {
+                    fetchRecords(*wc, c.hResult.p + recOff[w], static_cast<uint32_t>(b), static_cast<uint32_t>(cigOff[w]), &wst[w]);
                     LGPU_CUDA(cudaEventRecord(wc->ev[4], wc->stream));
                 }
-                catch (std::exception const & e)
+                catch (std::exception const & ex)
                 {
-                    err[w] = e.what();
+                    err[w] = ex.what();
                 }
             });
+            }
+            catch (std::exception const & ex) // the thread could not be started: let the others through the gate
+            {
+                std::unique_lock<std::mutex> lock(gate.m);
+                for (unsigned int k = w; k < nW; ++k)
+                    err[k] = std::string("could not start a worker thread: ") + ex.what();
+                gate.arrived += nW - w;
+                if (gate.arrived >= nW)
+                {
+                    gate.open = true;
+                    gate.cv.notify_all();
+                }
+                break;
+            }
         }
         for (auto & t : th)
             t.join();
         for (unsigned int w = 0; w < nW; ++w)
             if (!err[w].empty())
                 throw CudaError("worker " + std::to_string(w) + ": " + err[w]);
-        c.hits.clear();
         c.cigar.clear();
         for (unsigned int w = 0; w < nW; ++w)
         {
-            lgpu_ctx &     wc   = *c.workers[w];
-            uint64_t const b    = all.n * w / nW;
-            size_t const   base = c.hits.size();
-            uint32_t const cigarBase = static_cast<uint32_t>(c.cigar.size());
-            c.lastParts.push_back({&wc, b, static_cast<uint64_t>(cigarBase), wc.nFinal});
-            c.hits.insert(c.hits.end(), wc.hits.begin(), wc.hits.end());
+            lgpu_ctx & wc = *c.workers[w];
+            c.lastParts.push_back({&wc, all.n * w / nW, cigOff[w], wc.nFinal});
             c.cigar.insert(c.cigar.end(), wc.cigar.begin(), wc.cigar.end());
-            for (size_t i = base; i < c.hits.size(); ++i)
-            {
-                c.hits[i].q_id += static_cast<uint32_t>(b);
-                c.hits[i].cigar_off += cigarBase;
-            }
             LGPU_CUDA(cudaStreamWaitEvent(c.stream, wc.ev[4], 0));
             if (st)
                 addStats(*st, wst[w]);
         }
+        c.nResult = recOff[nW];
     }
     LGPU_CUDA(cudaEventRecord(c.ev[3], c.stream));
     waitEvent(c, c.ev[3]);
@@ -1766,8 +1904,8 @@ static void searchBatch(lgpu_ctx & c, lgpu_query_batch const & qb, lgpu_hits * o
         cudaEventElapsedTime(&ms, c.ev[2], c.ev[3]);
         st->ms_total += ms;
     }
-    out->hits        = c.hits.data();
-    out->n           = c.hits.size();
+    out->hits        = c.hResult.p;
+    out->n           = c.nResult;
     out->cigar_ops   = c.params.want_cigar ? c.cigar.data() : nullptr;
     out->n_cigar_ops = c.params.want_cigar ? c.cigar.size() : 0;
 }
@@ -1847,6 +1985,10 @@ static std::unique_ptr<lgpu_ctx> lgpu::makeContext(lgpu_index const * ix, lgpu_p
     c->dCounters.reserve(8);
     if (char const * e = std::getenv("LAMBDA_B200_SEED"))
         c->seedMode = !std::strcmp(e, "thread") ? 1 : !std::strcmp(e, "warp") ? 2 : !std::strcmp(e, "block") ? 3 : !std::strcmp(e, "spec") ? 4 : 0;
+    if (char const * e = std::getenv("LAMBDA_B200_SEED_TEXT"))
+        c->seedTextElong = std::atoi(e) != 0;
+    if (char const * e = std::getenv("LAMBDA_B200_SEED_PREFIX"))
+        c->seedPrefix = std::atoi(e) != 0;
     if (char const * e = std::getenv("LAMBDA_B200_DPX_OCC"))
         c->dpxBlocksPerSM = static_cast<unsigned int>(std::max(1, std::min(32, std::atoi(e))));
     if (char const * e = std::getenv("LAMBDA_B200_TRACE"))

@@ -108,6 +108,9 @@ __host__ __device__ constexpr unsigned long long dpxPlaneWords(int T, int K, uns
 // profile.  Private profiles: segment = 0 and window = 2^20 - 1 - min(nt, 2^20 - 1): longest windows first.
 constexpr unsigned int kDpxSegShift   = 20;
 constexpr unsigned int kDpxClassShift = 58; // class in the top 6 bits
+#ifndef LGPU_DPX_BEST2
+#define LGPU_DPX_BEST2 1
+#endif
 constexpr unsigned int kDpxNullWord   = 0x80808080u;
 constexpr int          kDpxNullVal    = -128;
 
@@ -252,7 +255,9 @@ __global__ void __launch_bounds__(32) swDpxKernel(DpxParams P)
             if constexpr (TRACE)
                 CB[r] = go2; // per-column maximum of W
         }
-        unsigned int best = go2;
+        // two running maxima: a single one fuses into VIMNMX3 (the half-rate DPX pipe, like the recurrence itself);
+        // two independent plain VIMNMX.S16x2 can issue on the other pipe
+        unsigned int best = go2, best1 = go2;
         unsigned int outW = go2, outF = neg2, diagIn = go2;
         unsigned int * const plane = TRACE && valid ? P.planes + (P.planeOff[slot] - P.planeOffBase) : nullptr;
 
@@ -310,6 +315,8 @@ __global__ void __launch_bounds__(32) swDpxKernel(DpxParams P)
                 W[r]                   = w;
                 if constexpr (TRACE)
                     CB[r] = __vmaxs2(CB[r], w);
+                else if (LGPU_DPX_BEST2 && (r & 1))
+                    best1 = __vmaxs2(best1, w);
                 else
                     best = __vmaxs2(best, w);
             }
@@ -364,6 +371,7 @@ __global__ void __launch_bounds__(32) swDpxKernel(DpxParams P)
         else
         {
             // reduce over the group: both halves, all T threads
+            best  = __vmaxs2(best, best1);
             int b = max(static_cast<int>(static_cast<short>(best & 0xffffu)), static_cast<int>(best) >> 16);
 #pragma unroll
             for (int off = T / 2; off > 0; off >>= 1)

@@ -365,6 +365,14 @@ struct SeedParams
     lgpu_match *         out;
     unsigned long long   cap;
     unsigned long long * counters; // [0] matches emitted, [1] hitsAfterSeeding, [2] hitsFailedPreExtendTest
+    // depth-k prefix table: cursor of every k-mer over the reduced alphabet, in place of the first k LF steps of a seed's
+    // exactly matched part (the same cursor the steps would produce); nullptr = none
+    uint2 const *        prefixTab;
+    unsigned int         prefixK;
+    // A cursor with ONE occurrence is elongated by locating it once and comparing query and subject text directly (each
+    // further LF step would just test the next subject residue); textElong = 0 keeps the rank steps
+    unsigned int         textElong;
+    unsigned char        sbjRed[2][32]; // subject residue -> reduced rank, per subject parity (bisulfite); 0xff = unknown
 };
 
 constexpr int kMaxHalf2 = 16; // longest supported second seed half (seed length <= 32)
@@ -631,20 +639,63 @@ __global__ void __launch_bounds__(128) seedKernel(SeedParams P)
 // warp-cooperative building blocks (shared by the warp-per-query and block-per-query kernels)
 // ---------------------------------------------------------------------------------------------
 
+// cursor after the first `n` symbols of the seed starting at seedBegin, through the prefix table where it applies
+__device__ __forceinline__ Cursor seedPrefixCursor(SeedParams const & P, unsigned char const * red, unsigned int seedBegin,
+                                                   unsigned int n)
+{
+    DevIndex const & ix = P.ix;
+    Cursor           c;
+    c.lb           = 0;
+    c.len          = ix.nRows;
+    unsigned int i = 0;
+    if (P.prefixTab && n >= P.prefixK)
+    {
+        unsigned int       code = 0;
+        unsigned int const A    = ix.sigma - 1;
+        for (; i < P.prefixK; ++i)
+            code = code * A + seedSym(red, seedBegin, seedBegin + i, ix.bsMode != 0);
+        uint2 const e = __ldg(P.prefixTab + code);
+        c.lb          = e.x;
+        c.len         = e.y;
+    }
+    for (; i < n && c.len != 0; ++i)
+        c = fmExtendRight(ix, c, seedSym(red, seedBegin, seedBegin + i, ix.bsMode != 0) + 1u);
+    return c;
+}
+
+// tab[code] = cursor of the k-mer `code` (base sigma-1 digits, first symbol most significant); len 0 = does not occur
+__global__ void prefixTableKernel(DevIndex ix, unsigned int k, unsigned int nEntries, uint2 * tab)
+{
+    unsigned int const t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nEntries)
+        return;
+    unsigned int const A = ix.sigma - 1;
+    unsigned int       div = 1;
+    for (unsigned int i = 1; i < k; ++i)
+        div *= A;
+    Cursor c;
+    c.lb              = 0;
+    c.len             = ix.nRows;
+    unsigned int rest = t;
+    for (unsigned int i = 0; i < k && c.len != 0; ++i)
+    {
+        unsigned int const sym = rest / div;
+        rest -= sym * div;
+        div = div > 1 ? div / A : 1;
+        c   = fmExtendRight(ix, c, sym + 1u);
+    }
+    tab[t] = make_uint2(static_cast<unsigned int>(c.lb), static_cast<unsigned int>(c.len));
+}
+
 // Exact chain of one seed: E[0] = cursor after the exactly matched first half, E[i+1] = E[i] extended by
 // the (h1+i)-th seed symbol.  Returns the deepest non-empty level K (-1: the first half does not occur).
-__device__ __forceinline__ int seedExactChain(DevIndex const & ix, unsigned char const * red, unsigned int seedBegin,
+__device__ __forceinline__ int seedExactChain(SeedParams const & P, unsigned char const * red, unsigned int seedBegin,
                                               unsigned int h1, unsigned int n2, Cursor * E)
 {
-    Cursor c;
-    c.lb  = 0;
-    c.len = ix.nRows;
-    for (unsigned int i = 0; i < h1; ++i)
-    {
-        c = fmExtendRight(ix, c, seedSym(red, seedBegin, seedBegin + i, ix.bsMode != 0) + 1u);
-        if (c.len == 0)
-            return -1;
-    }
+    DevIndex const & ix = P.ix;
+    Cursor           c  = seedPrefixCursor(P, red, seedBegin, h1);
+    if (c.len == 0)
+        return -1;
     E[0]  = c;
     int K = 0;
     for (unsigned int i = 0; i < n2; ++i)
@@ -941,6 +992,9 @@ __device__ __forceinline__ void seedConsumeChunkSpec(SeedParams const & P, signe
     Cursor             el     = mine;
     unsigned int       elLen  = L;
     unsigned long long lo = 1, hi = ~0ull;
+    // text mode: the cursor has ONE occurrence, already located: subject tSubj, seed start tStart
+    bool               elText = false;
+    unsigned int       tSubj = 0, tStart = 0;
     while (pending)
     {
         unsigned long long const hits0     = hitsThisSeq;
@@ -951,21 +1005,25 @@ __device__ __forceinline__ void seedConsumeChunkSpec(SeedParams const & P, signe
               P.adaptive ? seedDesiredOccs(P, hits0, needlesSum, needlesPosF, seedBegin) : 1ull;
             if (!haveEl || desired < lo || desired > hi)
             {
-                el    = mine;
-                elLen = L;
-                lo    = 1;
-                hi    = ~0ull;
+                el     = mine;
+                elLen  = L;
+                lo     = 1;
+                hi     = ~0ull;
+                elText = false;
                 if (P.adaptive)
                 {
                     unsigned long long oldCount = el.len;
-                    while (seedBegin + elLen < len)
+                    bool               stopped  = false;
+                    // LF steps while the cursor has several occurrences (all of them, if text mode is off)
+                    while (seedBegin + elLen < len && (el.len > 1 || !P.textElong))
                     {
                         Cursor const n = fmExtendRight(ix, el, elongSym(red, seedBegin + elLen, ix.bsMode != 0) + 1u);
                         if (n.len < oldCount)
                         {
                             if (n.len < desired)
                             {
-                                lo = max(lo, n.len + 1); // same stop for every desired > n.len
+                                lo      = max(lo, n.len + 1); // same stop for every desired > n.len
+                                stopped = true;
                                 break;
                             }
                             hi = min(hi, n.len); // same continuation for every desired <= n.len
@@ -973,6 +1031,63 @@ __device__ __forceinline__ void seedConsumeChunkSpec(SeedParams const & P, signe
                         el       = n;
                         oldCount = n.len;
                         ++elLen;
+                    }
+                    if (!stopped && seedBegin + elLen < len)
+                    {
+                        // ONE occurrence left: every further LF step would only test whether the next subject residue
+                        // equals the next query symbol (count 1 -> 1: go on; 1 -> 0 < desired: stop, `lo` stays >= 1).
+                        // Locate it once and compare the texts instead.
+                        unsigned long long subj, pos;
+                        fmLocate(ix, el.lb, subj, pos); // pos = one past the seed's end in the subject
+                        unsigned long long const sBase  = sbjBase(ix, static_cast<unsigned int>(subj));
+                        unsigned long long const sLen   = sbjLength(ix, static_cast<unsigned int>(subj));
+                        unsigned char const *    rt     = P.sbjRed[subj & ix.bsMode];
+                        unsigned int const       len0   = elLen;
+                        bool                     replay = false;
+                        while (seedBegin + elLen < len)
+                        {
+                            unsigned long long const sp = pos + (elLen - len0);
+                            if (sp >= sLen)
+                                break; // the sentinel behind the subject matches no query symbol
+                            unsigned int const rs = rt[__ldg(ix.seqs + sBase + sp)];
+                            if (rs == 0xffu)
+                            {
+                                replay = true; // a residue whose index symbol this table does not know
+                                break;
+                            }
+                            if (rs != elongSym(red, seedBegin + elLen, ix.bsMode != 0))
+                                break;
+                            ++elLen;
+                        }
+                        if (!replay)
+                        {
+                            elText = true;
+                            tSubj  = static_cast<unsigned int>(subj);
+                            tStart = static_cast<unsigned int>(pos - len0);
+                        }
+                        else
+                        {
+                            // rare: redo the matched stretch with LF steps and go on as the reference does
+                            for (unsigned int t = len0; t < elLen; ++t)
+                                el = fmExtendRight(ix, el, elongSym(red, seedBegin + t, ix.bsMode != 0) + 1u);
+                            oldCount = el.len;
+                            while (seedBegin + elLen < len)
+                            {
+                                Cursor const n = fmExtendRight(ix, el, elongSym(red, seedBegin + elLen, ix.bsMode != 0) + 1u);
+                                if (n.len < oldCount)
+                                {
+                                    if (n.len < desired)
+                                    {
+                                        lo = max(lo, n.len + 1);
+                                        break;
+                                    }
+                                    hi = min(hi, n.len);
+                                }
+                                el       = n;
+                                oldCount = n.len;
+                                ++elLen;
+                            }
+                        }
                     }
                 }
                 haveEl = true;
@@ -1024,12 +1139,18 @@ __device__ __forceinline__ void seedConsumeChunkSpec(SeedParams const & P, signe
             unsigned int const       oLen  = __shfl_sync(0xffffffffu, elLen, j);
             unsigned int const       oSb   = __shfl_sync(0xffffffffu, seedBegin, j);
             unsigned int const       oF    = __shfl_sync(0xffffffffu, f, j);
+            bool const               oText = __shfl_sync(0xffffffffu, elText ? 1 : 0, j) != 0;
+            unsigned int const       oTS   = __shfl_sync(0xffffffffu, tSubj, j);
+            unsigned int const       oTP   = __shfl_sync(0xffffffffu, tStart, j);
             bool                     pass  = false;
             if (act)
             {
-                unsigned long long subj, pos;
-                fmLocate(ix, oLb + (target - oExcl), subj, pos);
-                pos -= oLen;
+                unsigned long long subj = oTS, pos = oTP;
+                if (!oText)
+                {
+                    fmLocate(ix, oLb + (target - oExcl), subj, pos);
+                    pos -= oLen;
+                }
                 unsigned char const * tr = P.Q.trans + F * qb + static_cast<unsigned long long>(oF) * origLen;
                 pass       = seedPreScore(P, sM, tr, qryFrameLen(P.Q, origLen, oF), oSb, oLen, subj, pos);
                 S.subj[r]  = static_cast<unsigned int>(subj);
@@ -1185,7 +1306,7 @@ __global__ void __launch_bounds__(128) seedWarpKernel(SeedParams P)
                     break;
                 // exact chain, computed redundantly by all lanes (same addresses -> one transaction)
                 Cursor    E[kMaxHalf2 + 1];
-                int const K = seedExactChain(ix, red, seedBegin, h1, n2, E);
+                int const K = seedExactChain(P, red, seedBegin, h1, n2, E);
                 if (K < 0)
                     continue;
                 int const          kMax     = (K < static_cast<int>(n2) - 1) ? K : static_cast<int>(n2) - 1;
@@ -1292,11 +1413,7 @@ __global__ void __launch_bounds__(32 * kSpecWarps, 5) seedSpecKernel(SeedParams 
                     c.lb  = 0;
                     c.len = 0;
                     if (mySeed != 0xffffffffu)
-                    {
-                        c.len = ix.nRows;
-                        for (unsigned int i = 0; i < L && c.len != 0; ++i)
-                            c = fmExtendRight(ix, c, seedSym(red, mySeed, mySeed + i, ix.bsMode != 0) + 1u);
-                    }
+                        c = seedPrefixCursor(P, red, mySeed, L);
                     else
                         mySeed = 0;
                     __syncwarp();
@@ -1311,7 +1428,7 @@ __global__ void __launch_bounds__(32 * kSpecWarps, 5) seedSpecKernel(SeedParams 
                     if (!seedNextStart(trans, len, L, P.unknownRank, seedBegin))
                         break;
                     Cursor    E[kMaxHalf2 + 1];
-                    int const K = seedExactChain(ix, red, seedBegin, h1, n2, E);
+                    int const K = seedExactChain(P, red, seedBegin, h1, n2, E);
                     if (K < 0)
                         continue;
                     int const          kMax     = (K < static_cast<int>(n2) - 1) ? K : static_cast<int>(n2) - 1;
@@ -1418,7 +1535,7 @@ __global__ void __launch_bounds__(32 * kSeedBlockWarps) seedBlockKernel(SeedPara
         unsigned int const    seedBegin = sSeed[k] & 0xffffffu;
         unsigned char const * red       = P.Q.red + F * qb + static_cast<unsigned long long>(f) * origLen;
         Cursor                E[kMaxHalf2 + 1];
-        int const             K   = seedExactChain(ix, red, seedBegin, h1, n2, E);
+        int const             K   = seedExactChain(P, red, seedBegin, h1, n2, E);
         unsigned int          out = 0;
         if (K >= 0)
         {

@@ -245,9 +245,13 @@ def test_score_kernel_all_length_classes(golden_dir, prof, monkeypatch):
     s.close(); ix.close(); o.close()
 
 
-@pytest.mark.parametrize("mode", ["auto", "thread", "warp", "spec"])
+@pytest.mark.parametrize("mode", ["auto", "thread", "warp", "spec", "plain"])
 @pytest.mark.parametrize("case,domain,profile", CASE_PROFILES)
 def test_search_reproduces_reference_output(golden_dir, case, domain, profile, mode, monkeypatch):
+    if mode == "plain":  # the default kernels without the prefix table and without text-mode elongation
+        monkeypatch.setenv("LAMBDA_B200_SEED_TEXT", "0")
+        monkeypatch.setenv("LAMBDA_B200_SEED_PREFIX", "0")
+        mode = "auto"
     monkeypatch.setenv("LAMBDA_B200_SEED", mode)
     path, ids, res, offs = _load(golden_dir, case, domain)
     ix = lambda_b200.Index.load(path)
