@@ -2152,6 +2152,26 @@ int lgpu_index_create(lgpu_index ** out, lgpu_index_desc const * d, int device)
         ix->meta.id_delims    = nullptr;
         runUploads(pending, device);
         LGPU_CUDA(cudaDeviceSynchronize());
+        char const * const ve = std::getenv("LAMBDA_B200_VALIDATE");
+        if (!ve || std::atoi(ve) != 0)
+        {
+            // O(size) consistency checks of the uploaded blobs (kernels_fm.cuh validateIndexKernel)
+            unsigned int * dFlags = nullptr;
+            unsigned int   flags  = 0;
+            LGPU_CUDA(cudaMalloc(reinterpret_cast<void **>(&dFlags), 4));
+            LGPU_CUDA(cudaMemset(dFlags, 0, 4));
+            int sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+            validateIndexKernel<<<static_cast<unsigned int>(sms) * 16, 256>>>(dv, d->n_blocks, d->n_ssa, d->n_csa_sb,
+                                                                                d->n_seqs * dv.sbjFrames, dFlags);
+            cudaError_t const e1 = cudaMemcpy(&flags, dFlags, 4, cudaMemcpyDeviceToHost);
+            cudaFree(dFlags);
+            LGPU_CUDA(e1);
+            if (flags)
+                throw LbaError(std::string("index file corrupt:") + ((flags & 1u) ? " occ block counts are inconsistent;" : "") +
+                               ((flags & 2u) ? " CSA bit vector ranks outside the sampled suffix array;" : "") +
+                               ((flags & 4u) ? " sampled suffix array names a sequence / position that does not exist;" : ""));
+        }
         *out = ix.release();
     });
 }

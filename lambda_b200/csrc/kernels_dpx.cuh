@@ -109,7 +109,7 @@ __host__ __device__ constexpr unsigned long long dpxPlaneWords(int T, int K, uns
 constexpr unsigned int kDpxSegShift   = 20;
 constexpr unsigned int kDpxClassShift = 58; // class in the top 6 bits
 #ifndef LGPU_DPX_BEST2
-#define LGPU_DPX_BEST2 1
+#define LGPU_DPX_BEST2 0
 #endif
 constexpr unsigned int kDpxNullWord   = 0x80808080u;
 constexpr int          kDpxNullVal    = -128;
@@ -255,8 +255,9 @@ __global__ void __launch_bounds__(32) swDpxKernel(DpxParams P)
             if constexpr (TRACE)
                 CB[r] = go2; // per-column maximum of W
         }
-        // two running maxima: a single one fuses into VIMNMX3 (the half-rate DPX pipe, like the recurrence itself);
-        // two independent plain VIMNMX.S16x2 can issue on the other pipe
+        // LGPU_DPX_BEST2 (experiment, off): two running maxima -- a single one fuses into VIMNMX3 on the half-rate DPX
+        // pipe, two independent plain VIMNMX.S16x2 can issue on the other pipe.  Measured slower (searchp DP pass 1
+        // 38.2 vs 35.2 ms, profiles/r2_dp_best2.json): ptxas gives up the 10-fold unrolled software pipeline.
         unsigned int best = go2, best1 = go2;
         unsigned int outW = go2, outF = neg2, diagIn = go2;
         unsigned int * const plane = TRACE && valid ? P.planes + (P.planeOff[slot] - P.planeOffBase) : nullptr;

@@ -194,6 +194,56 @@ __global__ void fmLocateKernel(DevIndex ix, unsigned long long const * rows, uns
         fmLocate(ix, rows[i], subj[i], pos[i]);
 }
 
+// Cross-checks of an uploaded index that are O(size) and therefore run here, not in the host parser (a corrupt or
+// crafted file must not make the search kernels read out of bounds): flags |= 1 occ block counts do not continue the
+// previous block, 2 a CSA super block ranks outside the sampled suffix array, 4 a sampled entry names a sequence or a
+// position that does not exist.
+__global__ void validateIndexKernel(DevIndex ix, unsigned long long nBlocks, unsigned long long nSsa, unsigned long long nCsaSb,
+                                    unsigned long long nFrameSubjects, unsigned int * flags)
+{
+    unsigned long long const stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+    unsigned int             bad    = 0;
+    unsigned long long const fullBlocks = ix.nRows / 64; // blocks 0 .. fullBlocks-1 hold 64 BWT symbols each
+    for (unsigned long long b = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; b + 1 < nBlocks && b < fullBlocks;
+         b += stride)
+    {
+        if (((b + 1) & ((1ull << 26) - 1)) == 0)
+            continue; // the counts restart with every super block (2^32 symbols)
+        unsigned char const * cur = ix.occ + b * ix.blockBytes;
+        unsigned char const * nxt = cur + ix.blockBytes;
+        for (unsigned int s = 0; s < ix.sigma; ++s)
+        {
+            unsigned int const c0 = __ldg(reinterpret_cast<unsigned int const *>(cur) + s);
+            unsigned int const c1 = __ldg(reinterpret_cast<unsigned int const *>(nxt) + s);
+            if (c1 != c0 + static_cast<unsigned int>(__popcll(fmSymbolMask(ix, cur, s))))
+                bad |= 1u;
+        }
+    }
+    for (unsigned long long k = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; k < nCsaSb; k += stride)
+    {
+        CsaSuperDev const * sb = ix.csa + k;
+        unsigned long long  r  = ldg64(&sb->entry);
+        unsigned int        in = 0;
+        for (unsigned int w = 0; w < 4; ++w)
+        {
+            if (__ldg(&sb->blocks[w]) != in)
+                bad |= 2u;
+            in += static_cast<unsigned int>(__popcll(ldg64(&sb->bits[w])));
+        }
+        if (r + in > nSsa)
+            bad |= 2u;
+    }
+    for (unsigned long long k = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; k < nSsa; k += stride)
+    {
+        unsigned long long const v    = __ldg(ix.ssa + k);
+        unsigned long long const subj = v >> ix.bitsForPos;
+        if (subj >= nFrameSubjects || (v & ix.posMask) > sbjLength(ix, static_cast<unsigned int>(subj)))
+            bad |= 4u;
+    }
+    if (bad)
+        atomicOr(flags, bad);
+}
+
 // ---------------------------------------------------------------------------------------------
 // query preparation: frames (reverse complement) and alphabet reduction
 // ---------------------------------------------------------------------------------------------

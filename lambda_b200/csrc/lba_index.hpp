@@ -13,6 +13,7 @@
 #include <stdexcept>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include <fcntl.h>
 #include <sys/mman.h>
@@ -99,16 +100,28 @@ public:
             throw LbaError("cannot open index file " + path);
         struct stat st;
         if (fstat(fd_, &st) != 0)
+        {
+            release();
             throw LbaError("cannot stat index file " + path);
+        }
         size_ = static_cast<size_t>(st.st_size);
         base_ = static_cast<uint8_t const *>(mmap(nullptr, size_, PROT_READ, MAP_PRIVATE, fd_, 0));
         if (base_ == MAP_FAILED)
         {
             base_ = nullptr;
+            release();
             throw LbaError("cannot mmap index file " + path);
         }
         madvise(const_cast<uint8_t *>(base_), size_, MADV_SEQUENTIAL);
-        parse();
+        try
+        {
+            parse();
+        }
+        catch (...)
+        {
+            release(); // the destructor does not run for a throwing constructor
+            throw;
+        }
         std::lock_guard<std::mutex> g(lbaRegistryMutex());
         lbaRegistry().push_back({base_, size_, fd_});
     }
@@ -125,10 +138,7 @@ public:
                     break;
                 }
         }
-        if (base_)
-            munmap(const_cast<uint8_t *>(base_), size_);
-        if (fd_ >= 0)
-            ::close(fd_);
+        release();
     }
 
     LbaFile(LbaFile const &)             = delete;
@@ -142,6 +152,16 @@ public:
     lgpu_taxonomy tax{};
 
 private:
+    void release()
+    {
+        if (base_)
+            munmap(const_cast<uint8_t *>(base_), size_);
+        if (fd_ >= 0)
+            ::close(fd_);
+        base_ = nullptr;
+        fd_   = -1;
+    }
+
     int             fd_   = -1;
     uint8_t const * base_ = nullptr;
     size_t          size_ = 0;
@@ -167,13 +187,29 @@ private:
         return p;
     }
 
+    // n * elem bytes; the product cannot wrap (a count taken from the file is checked against the bytes that are left)
+    uint8_t const * blobN(uint64_t n, uint64_t elem)
+    {
+        if (elem && n > (size_ - pos_) / elem)
+            throw LbaError("index file truncated");
+        return blob(n * elem);
+    }
+
     // `u64 n` + n * elem bytes
     uint8_t const * vec(uint64_t elem, uint64_t & n)
     {
         n = get<uint64_t>();
-        if (elem && n > (size_ - pos_) / elem)
-            throw LbaError("index file truncated");
-        return blob(n * elem);
+        return blobN(n, elem);
+    }
+
+    // delimiters of a concatenated container: non-decreasing, the last one = size of the payload
+    static void checkDelims(uint64_t const * d, uint64_t n, uint64_t payload, char const * what)
+    {
+        if (n == 0 || d[0] != 0 || d[n - 1] != payload)
+            throw LbaError(std::string("index file corrupt: ") + what + " delimiters do not match their payload");
+        for (uint64_t i = 1; i < n; ++i)
+            if (d[i] < d[i - 1])
+                throw LbaError(std::string("index file corrupt: ") + what + " delimiters are not sorted");
     }
 
     void parse()
@@ -194,6 +230,7 @@ private:
         uint64_t n;
         // ids: concatenated_sequences<std::string> = data string + delimiters
         desc.ids       = reinterpret_cast<char const *>(vec(1, n));
+        uint64_t const nIdBytes = n;
         desc.id_delims = reinterpret_cast<uint64_t const *>(vec(8, n));
         uint64_t const nIdDelims = n;
         // seqs: custom save (shared_definitions.hpp:290-307) = u64 n + n bytes; then delimiters
@@ -205,19 +242,40 @@ private:
         desc.n_seqs = n - 1;
         if (desc.seq_delims[desc.n_seqs] != desc.n_residues)
             throw LbaError("index file corrupt: last sequence delimiter != residue count");
+        checkDelims(desc.id_delims, nIdDelims, nIdBytes, "id");
+        checkDelims(desc.seq_delims, n, desc.n_residues, "sequence");
         // sTaxIds, taxonParentIDs, taxonHeights, taxonNames
         tax.s_tax_ids    = reinterpret_cast<uint32_t const *>(vec(4, tax.n_s_tax_ids));
         tax.s_tax_delims = reinterpret_cast<uint64_t const *>(vec(8, n));
         if (n != desc.n_seqs + 1)
+        {
+            if (tax.n_s_tax_ids != 0)
+                throw LbaError("index file corrupt: taxonomy ids without one delimiter per subject");
             tax.s_tax_delims = nullptr; // index built without --acc-tax-map (the empty container holds one delimiter)
+        }
+        else
+            checkDelims(tax.s_tax_delims, n, tax.n_s_tax_ids, "taxonomy id");
         tax.taxon_parents = reinterpret_cast<uint32_t const *>(vec(4, tax.n_taxa));
         tax.taxon_heights = vec(1, n);
         if (n != tax.n_taxa)
             throw LbaError("index file corrupt: taxonomy height / parent count mismatch");
-        tax.taxon_names       = reinterpret_cast<char const *>(vec(1, n));
-        tax.taxon_name_delims = reinterpret_cast<uint64_t const *>(vec(8, n));
+        tax.taxon_names = reinterpret_cast<char const *>(vec(1, n));
+        uint64_t const nNameBytes = n;
+        tax.taxon_name_delims     = reinterpret_cast<uint64_t const *>(vec(8, n));
         if (tax.n_taxa == 0 || n != tax.n_taxa + 1)
             tax.taxon_name_delims = nullptr; // index built without --tax-dump-dir
+        else
+            checkDelims(tax.taxon_name_delims, n, nNameBytes, "taxon name");
+        // every tax id / parent must index the taxon arrays (the host walks them for the lowest common ancestor)
+        if (tax.n_taxa)
+        {
+            for (uint64_t i = 0; i < tax.n_s_tax_ids; ++i)
+                if (tax.s_tax_ids[i] >= tax.n_taxa)
+                    throw LbaError("index file corrupt: subject tax id outside the taxonomy");
+            for (uint64_t i = 0; i < tax.n_taxa; ++i)
+                if (tax.taxon_parents[i] >= tax.n_taxa)
+                    throw LbaError("index file corrupt: taxon parent outside the taxonomy");
+        }
 
         // index.occ (InterleavedEPRV2.h:272-306)
         uint32_t const redSize = alphabetSize(desc.red_alph);
@@ -229,9 +287,9 @@ private:
         if (version != 1)
             throw LbaError("occ table was not written with cereal's binary fast path (version != 1)");
         desc.n_blocks     = get<uint64_t>();
-        desc.occ_blocks   = blob(desc.n_blocks * desc.block_bytes);
+        desc.occ_blocks   = blobN(desc.n_blocks, desc.block_bytes);
         desc.n_super      = get<uint64_t>();
-        desc.super_blocks = reinterpret_cast<uint64_t const *>(blob(desc.n_super * desc.sigma * 8));
+        desc.super_blocks = reinterpret_cast<uint64_t const *>(blobN(desc.n_super, static_cast<uint64_t>(desc.sigma) * 8));
         desc.C            = reinterpret_cast<uint64_t const *>(blob((desc.sigma + 1) * 8));
 
         // index.csa (CSA.h:115-118, BitvectorCompact.h:112-143)
@@ -240,7 +298,7 @@ private:
         if (version != 1)
             throw LbaError("csa bit vector was not written with cereal's binary fast path");
         desc.n_csa_sb          = get<uint64_t>();
-        desc.csa_bv            = blob(desc.n_csa_sb * 48);
+        desc.csa_bv            = blobN(desc.n_csa_sb, 48);
         desc.sampling_rate     = get<uint64_t>();
         desc.bits_for_position = get<uint64_t>();
         uint64_t const mask    = get<uint64_t>();
@@ -249,9 +307,26 @@ private:
             throw LbaError("index file corrupt: bad CSA position mask");
         if (pos_ != size_)
             throw LbaError("index file has " + std::to_string(size_ - pos_) + " trailing bytes");
-        // size() of the index = C.back() must be addressable in the block array
-        if (desc.C[desc.sigma] / 64 >= desc.n_blocks)
+        // size() of the index = C.back() must be addressable in the block array, the super-block rows and the CSA's
+        // bit vector (bit i of the vector lives at position i + 1)
+        uint64_t const nRows = desc.C[desc.sigma];
+        if (nRows / 64 >= desc.n_blocks)
             throw LbaError("index file corrupt: occ blocks do not cover the BWT");
+        if (desc.n_super == 0 || (nRows >> 32) >= desc.n_super)
+            throw LbaError("index file corrupt: occ super blocks do not cover the BWT");
+        for (uint32_t s2 = 0; s2 < desc.sigma; ++s2)
+            if (desc.C[s2] > desc.C[s2 + 1])
+                throw LbaError("index file corrupt: C array is not sorted");
+        if (nRows / 256 >= desc.n_csa_sb)
+            throw LbaError("index file corrupt: CSA bit vector does not cover the BWT");
+        // sequences of the index text: two conversions per subject (bisulfite), six frames (translated subjects)
+        uint64_t const perSubject = desc.red_alph == LGPU_ALPH_DNA3BS ? 2
+                                    : (desc.trans_alph == LGPU_ALPH_AMINO_ACID && desc.orig_alph == LGPU_ALPH_DNA5) ? 6 : 1;
+        if (desc.n_seqs > (1ull << (64 - desc.bits_for_position)) / perSubject)
+            throw LbaError("index file corrupt: sequence ids do not fit the CSA entries");
+        // The O(n) part of the cross-checks -- every sampled suffix-array entry names an existing (sequence, position),
+        // every CSA super block ranks inside the sampled array -- runs on the device after the upload
+        // (validateIndexKernel, engine.cu), where it costs a fraction of a millisecond.
     }
 };
 

@@ -472,36 +472,56 @@ void runShard(Options const & o, lgpu_index_desc const * desc, int device, Fasta
 } // namespace
 
 // BGZF (SAM/BAM specification 4.1): independent gzip members of <= 64 KiB with the block size in an extra field
-void bgzfWrite(FILE * fo, std::string const & raw)
+void bgzfBlock(FILE * fo, unsigned char const * p, size_t n)
 {
-    auto block = [&](unsigned char const * p, size_t n) {
-        unsigned char out[65536 + 64];
-        z_stream      zs{};
-        if (deflateInit2(&zs, Z_DEFAULT_COMPRESSION, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK)
-            die("zlib: deflateInit2 failed");
-        zs.next_in   = const_cast<unsigned char *>(p);
-        zs.avail_in  = static_cast<uInt>(n);
-        zs.next_out  = out + 18;
-        zs.avail_out = sizeof(out) - 18 - 8;
-        if (deflate(&zs, Z_FINISH) != Z_STREAM_END)
-            die("zlib: deflate failed");
-        size_t const clen = zs.total_out;
-        deflateEnd(&zs);
-        unsigned char const hdr[18] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0, 0};
-        std::memcpy(out, hdr, 18);
-        size_t const total = 18 + clen + 8;
-        out[16] = static_cast<unsigned char>((total - 1) & 0xff);
-        out[17] = static_cast<unsigned char>((total - 1) >> 8);
-        uint32_t const crc = static_cast<uint32_t>(crc32(crc32(0L, Z_NULL, 0), p, static_cast<uInt>(n)));
-        uint32_t const isz = static_cast<uint32_t>(n);
-        std::memcpy(out + 18 + clen, &crc, 4);
-        std::memcpy(out + 18 + clen + 4, &isz, 4);
-        std::fwrite(out, 1, total, fo);
-    };
-    for (size_t off = 0; off < raw.size(); off += 0xff00)
-        block(reinterpret_cast<unsigned char const *>(raw.data()) + off, std::min<size_t>(0xff00, raw.size() - off));
-    block(nullptr, 0); // end-of-file marker block
+    unsigned char out[65536 + 64];
+    z_stream      zs{};
+    if (deflateInit2(&zs, Z_DEFAULT_COMPRESSION, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK)
+        die("zlib: deflateInit2 failed");
+    zs.next_in   = const_cast<unsigned char *>(p);
+    zs.avail_in  = static_cast<uInt>(n);
+    zs.next_out  = out + 18;
+    zs.avail_out = sizeof(out) - 18 - 8;
+    if (deflate(&zs, Z_FINISH) != Z_STREAM_END)
+        die("zlib: deflate failed");
+    size_t const clen = zs.total_out;
+    deflateEnd(&zs);
+    unsigned char const hdr[18] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0, 0};
+    std::memcpy(out, hdr, 18);
+    size_t const total = 18 + clen + 8;
+    out[16] = static_cast<unsigned char>((total - 1) & 0xff);
+    out[17] = static_cast<unsigned char>((total - 1) >> 8);
+    uint32_t const crc = static_cast<uint32_t>(crc32(crc32(0L, Z_NULL, 0), p, static_cast<uInt>(n)));
+    uint32_t const isz = static_cast<uint32_t>(n);
+    std::memcpy(out + 18 + clen, &crc, 4);
+    std::memcpy(out + 18 + clen + 4, &isz, 4);
+    std::fwrite(out, 1, total, fo);
 }
+
+// Writes the full 0xff00-byte blocks of `raw` (everything, if `final`) and keeps the rest: the BAM stream goes out
+// block by block instead of being held in memory until the end.
+void bgzfDrain(FILE * fo, std::string & raw, bool final)
+{
+    size_t off = 0;
+    while (raw.size() - off >= 0xff00 || (final && off < raw.size()))
+    {
+        size_t const n = std::min<size_t>(0xff00, raw.size() - off);
+        bgzfBlock(fo, reinterpret_cast<unsigned char const *>(raw.data()) + off, n);
+        off += n;
+    }
+    raw.erase(0, off);
+    if (final)
+        bgzfBlock(fo, nullptr, 0); // end-of-file marker block
+}
+
+// stdio stream that compresses into a .gz file while it is written (no copy of the output in memory)
+static ssize_t gzCookieWrite(void * c, char const * buf, size_t n)
+{
+    int const w = gzwrite(static_cast<gzFile>(c), buf, static_cast<unsigned>(std::min<size_t>(n, 1u << 30)));
+    return w <= 0 ? 0 : w; // 0 = error for stdio
+}
+static int gzCookieClose(void * c) { return gzclose(static_cast<gzFile>(c)) == Z_OK ? 0 : -1; }
+
 
 // `lambda3_b200 dumpq -q FILE [-a auto|dna5|aminoacid]`: parse the query file exactly like a search would and print
 // "alphabet\t<name>" followed by "<id>\t<residues>" per record (no GPU involved; used by the CPU tests)
@@ -649,12 +669,38 @@ static int run(int argc, char ** argv)
         return nullptr;
     };
     uint64_t const rpb = std::max<uint64_t>(std::min<uint64_t>(nQ / (static_cast<uint64_t>(o.threads) * 10), 10), 1);
-    // .gz outputs are formatted into memory and compressed when everything is written
-    char *         gzMem = nullptr;
-    size_t         gzLen = 0;
-    FILE *         fo    = o.gzOutput ? open_memstream(&gzMem, &gzLen) : std::fopen(o.output.c_str(), "wb");
+    // .gz outputs are compressed while they are written
+    FILE * fo = nullptr;
+    if (o.gzOutput)
+    {
+        gzFile gz = gzopen(o.output.c_str(), "wb");
+        if (gz)
+        {
+            cookie_io_functions_t io{};
+            io.write = gzCookieWrite;
+            io.close = gzCookieClose;
+            fo       = fopencookie(gz, "w", io);
+            if (!fo)
+                gzclose(gz);
+        }
+    }
+    else
+        fo = std::fopen(o.output.c_str(), "wb");
     if (!fo)
         die("cannot create output file " + o.output);
+    // a failed write (disk full, I/O error) must not leave a truncated file behind a zero exit code
+    auto checkOutput = [&](bool closing) {
+        bool bad = std::ferror(fo) != 0;
+        if (closing)
+            bad = (std::fclose(fo) != 0) || bad;
+        if (bad)
+        {
+            if (!closing)
+                std::fclose(fo);
+            std::remove(o.output.c_str());
+            die("error while writing " + o.output + " (disk full?); the partial file was removed");
+        }
+    };
     std::vector<char> line(1 << 16);
     auto              subjectId = [&](uint32_t s) {
         return std::string(desc->ids + desc->id_delims[s], desc->ids + desc->id_delims[s + 1]);
@@ -1063,6 +1109,7 @@ static int run(int argc, char ** argv)
             if (o.samTags[ST_IH]) tagRaw(ST_IH, 'I', &ih, 4);
             put32(static_cast<uint32_t>(rec.size()));
             bamRaw += rec;
+            bgzfDrain(fo, bamRaw, false);
             return;
         }
         std::string line = qName + "\t" + std::to_string(flag) + "\t" + sName + "\t" + std::to_string(beginPos + 1) + "\t255\t" +
@@ -1305,7 +1352,7 @@ static int run(int argc, char ** argv)
     if (o.comments)
         std::fprintf(fo, "# BLAST processed %llu queries\n", static_cast<unsigned long long>(nRecords));
     if (o.bam)
-        bgzfWrite(fo, bamRaw);
+        bgzfDrain(fo, bamRaw, true);
     if (o.report)
     {
         std::fprintf(fo, "\n  Database: %s\n  Number of letters in database: %llu\n  Number of sequences in database:  %llu\n\n\n\n"
@@ -1317,22 +1364,7 @@ static int run(int argc, char ** argv)
             std::fprintf(fo, "BLOSUM%d", o.params.scoring_method);
         std::fprintf(fo, "\nGap Penalties: Existence: %d, Extension: %d\n\n", -o.params.gap_open, -o.params.gap_extend);
     }
-    std::fclose(fo);
-    if (o.gzOutput)
-    {
-        gzFile gz = gzopen(o.output.c_str(), "wb");
-        if (!gz)
-            die("cannot create output file " + o.output);
-        for (size_t off = 0; off < gzLen;)
-        {
-            unsigned const n = static_cast<unsigned>(std::min<size_t>(gzLen - off, 1u << 30));
-            if (gzwrite(gz, gzMem + off, n) != static_cast<int>(n))
-                die("error while writing " + o.output);
-            off += n;
-        }
-        gzclose(gz);
-        std::free(gzMem);
-    }
+    checkOutput(true);
     lgpu_lba_close(lba);
     double const t4 = now();
 
