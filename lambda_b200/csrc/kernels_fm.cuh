@@ -1433,6 +1433,64 @@ __global__ void __launch_bounds__(32 * kSpecWarps, 5) seedSpecKernel(SeedParams 
         unsigned int const h1         = P.fullHamming ? 0u : (half ? L / 2 : L);
         unsigned int const n2         = L - h1;
 
+        if (!half)
+        {
+            // Exact seeds: the 32 lanes take the next 32 seeds of the query in the reference's order -- across frame
+            // borders, so that short reads (9 - 16 seeds per frame) still fill the warp.  Every lane runs the same
+            // scan and keeps its own (frame, seed start, needlesPos of that frame).
+            unsigned int       f = 0, seedBegin = 0;
+            unsigned long long npos = 0;
+            bool               more = true;
+            while (more)
+            {
+                unsigned int       mySeed = 0xffffffffu, myF = 0;
+                unsigned long long myNpos = 0;
+                for (unsigned int t = 0; t < 32 && more; ++t)
+                {
+                    for (;;)
+                    {
+                        if (f >= F)
+                        {
+                            more = false;
+                            break;
+                        }
+                        unsigned int const len = qryFrameLen(P.Q, origLen, f);
+                        if (len < L)
+                        {
+                            ++f; // too short a frame is skipped without advancing needlesPos (search_algo.hpp:637)
+                            seedBegin = 0;
+                            continue;
+                        }
+                        unsigned char const * trans = P.Q.trans + F * qb + static_cast<unsigned long long>(f) * origLen;
+                        if (seedNextStart(trans, len, L, P.unknownRank, seedBegin))
+                            break;
+                        npos += len;
+                        ++f;
+                        seedBegin = 0;
+                    }
+                    if (!more)
+                        break;
+                    if (lane == t)
+                    {
+                        mySeed = seedBegin;
+                        myF    = f;
+                        myNpos = npos;
+                    }
+                    seedBegin += P.seedOffset;
+                }
+                Cursor c;
+                c.lb  = 0;
+                c.len = 0;
+                if (mySeed != 0xffffffffu)
+                    c = seedPrefixCursor(P, P.Q.red + F * qb + static_cast<unsigned long long>(myF) * origLen, mySeed, L);
+                else
+                    mySeed = 0;
+                __syncwarp();
+                seedConsumeChunkSpec(P, sM, S, lane, q, qb, origLen, needlesSum, c, myF, mySeed, myNpos, hitsThisSeq, nAfter,
+                                     nFailed);
+            }
+        }
+        else
         for (unsigned int f = 0; f < F; ++f)
         {
             unsigned int const len = qryFrameLen(P.Q, origLen, f);
@@ -1440,38 +1498,6 @@ __global__ void __launch_bounds__(32 * kSpecWarps, 5) seedSpecKernel(SeedParams 
                 continue;
             unsigned char const * trans = P.Q.trans + F * qb + static_cast<unsigned long long>(f) * origLen;
             unsigned char const * red   = P.Q.red + F * qb + static_cast<unsigned long long>(f) * origLen;
-            if (!half)
-            {
-                unsigned int seedBegin = 0;
-                bool         more      = true;
-                while (more)
-                {
-                    // the next 32 seed starts (every lane runs the same scan and keeps its own)
-                    unsigned int mySeed = 0xffffffffu;
-                    for (unsigned int t = 0; t < 32; ++t)
-                    {
-                        if (!seedNextStart(trans, len, L, P.unknownRank, seedBegin))
-                        {
-                            more = false;
-                            break;
-                        }
-                        if (lane == t)
-                            mySeed = seedBegin;
-                        seedBegin += P.seedOffset;
-                    }
-                    Cursor c;
-                    c.lb  = 0;
-                    c.len = 0;
-                    if (mySeed != 0xffffffffu)
-                        c = seedPrefixCursor(P, red, mySeed, L);
-                    else
-                        mySeed = 0;
-                    __syncwarp();
-                    seedConsumeChunkSpec(P, sM, S, lane, q, qb, origLen, needlesSum, c, f, mySeed, needlesPos, hitsThisSeq,
-                                         nAfter, nFailed);
-                }
-            }
-            else
             {
                 for (unsigned int seedBegin = 0;; seedBegin += P.seedOffset)
                 {
