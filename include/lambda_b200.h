@@ -123,6 +123,12 @@ void                    lgpu_lba_close(lgpu_lba *);
 typedef struct lgpu_index lgpu_index;
 /* Copies the index to HBM of `device`; the host arrays may be released after return. */
 int      lgpu_index_create(lgpu_index ** out, lgpu_index_desc const * host_arrays, int device);
+/* A replica of an index that already lives on another GPU of the box, copied device to device (NVLink / NVSwitch when
+ * the two devices are peers) instead of once more from the host: with N GPUs the host reads the index file once. */
+int      lgpu_index_clone(lgpu_index ** out, lgpu_index const * src, int device);
+/* Creates the CUDA context of `device`.  Optional: call it from a thread at program start so that context creation
+ * (a few hundred milliseconds) overlaps with reading the query file and mapping the index. */
+int      lgpu_device_warmup(int device);
 void     lgpu_index_destroy(lgpu_index *);
 uint64_t lgpu_index_device_bytes(lgpu_index const *);
 /* dbTotalLength / dbNumberOfSeqs as the reference computes them (src/search_algo.hpp:317-319) */

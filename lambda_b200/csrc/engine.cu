@@ -182,7 +182,9 @@ struct UploadJob
 
 static void runUploads(std::vector<UploadJob> const & jobs, int device)
 {
-    constexpr size_t kChunk = 16u << 20;
+    size_t kChunk = 16u << 20;
+    if (char const * e = std::getenv("LAMBDA_B200_UPLOAD_CHUNK_MB"))
+        kChunk = static_cast<size_t>(std::max(1, std::min(256, std::atoi(e)))) << 20;
     struct Piece
     {
         unsigned char *       dst;
@@ -203,7 +205,8 @@ static void runUploads(std::vector<UploadJob> const & jobs, int device)
     }
     if (pieces.empty())
         return;
-    unsigned int nThreads = 6;
+    // page-cache -> pinned copies are what limits the upload: one thread moves ~8 GB/s, PCIe Gen5 takes ~50 GB/s
+    unsigned int nThreads = std::max(4u, std::min(12u, std::thread::hardware_concurrency() * 3 / 4));
     if (char const * e = std::getenv("LAMBDA_B200_UPLOAD_THREADS"))
         nThreads = static_cast<unsigned int>(std::max(1, std::min(32, std::atoi(e))));
     nThreads = static_cast<unsigned int>(std::min<size_t>(nThreads, pieces.size()));
@@ -298,6 +301,7 @@ struct lgpu_index
     DevIndex                 dev{};
     lgpu_index_desc          meta{}; // scalar fields only (host pointers cleared)
     std::vector<void *>      allocs;
+    std::vector<size_t>      allocBytes; // size of every entry of `allocs` (lgpu_index_clone)
     uint64_t                 bytes         = 0;
     uint64_t                 dbTotalLength = 0;
     std::vector<uint64_t>    sbjDelimsHost; // host copy of dev.seqDelims (window checks of the stage API)
@@ -358,6 +362,9 @@ struct lgpu_ctx
     bool                       resTraceOk   = false; // scoring fits the residue-plane trace path (kernels_dpx_trace.cuh)
     int                        traceTab     = kDpxTabTrace32; // class table of DP pass 2
     uint64_t                   maxPlaneWords = (16ull << 30) / 4; // residue planes per launch group (LAMBDA_B200_PLANE_MB)
+    unsigned int               maxColsInt16 = 0; // longest query whose scores cannot leave int16 (32767 / largest matrix entry)
+    DevBuf<unsigned int>       dOverflow;        // [0] != 0: an alignment score exceeded 32767 (the reference wraps there)
+    PinnedBuf<unsigned int>    hOverflow;
     DevBuf<unsigned long long> dPlaneWords, dPlaneWordsB;
     DevBuf<unsigned int>       dScalarSlots, dScalarIdx;
 
@@ -556,6 +563,21 @@ struct StageTimer
             cudaEventRecord(c.timers[slot].b, c.stream);
     }
 };
+
+// The reference computes alignment scores in int16 SIMD lanes (src/search_algo.hpp:1047,1087) and wraps silently beyond
+// 32767; its answer is then meaningless, and we refuse to return a different one.  The scalar kernels (the only ones
+// that can get there) raise the flag; checked once per call, after the stream has been synchronised.
+static void checkScoreOverflow(lgpu_ctx & c)
+{
+    LGPU_CUDA(cudaMemcpyAsync(c.hOverflow.p, c.dOverflow.p, 4, cudaMemcpyDeviceToHost, c.stream));
+    LGPU_CUDA(cudaStreamSynchronize(c.stream));
+    if (c.hOverflow.p[0])
+    {
+        LGPU_CUDA(cudaMemsetAsync(c.dOverflow.p, 0, 4, c.stream));
+        throw UnsupportedError("an alignment score exceeds 32767: the reference computes in int16 lanes and wraps silently there "
+                               "(src/search_algo.hpp:1047,1087); refusing to return a different answer");
+    }
+}
 
 // call after the stream has been synchronised
 static void resolveTimers(lgpu_ctx & c)
@@ -940,6 +962,7 @@ static ExtParams baseExtParams(lgpu_ctx & c, lgpu_match const * dTasks, unsigned
     P.ge          = c.scoring.gapExtend;
     c.dWork.reserve(kMaxDpxClasses + 3);
     P.workCounter = c.dWork.p;
+    P.overflowFlag = c.dOverflow.p;
     P.order       = nullptr;
     P.maxRows     = std::max(dims.maxT, 1u);
     if (dims.maxQ > static_cast<unsigned int>(32 * K))
@@ -1023,8 +1046,8 @@ static void runScorePass(lgpu_ctx & c, lgpu_match const * dTasks, unsigned int n
     LGPU_CUDA(cudaMemsetAsync(c.dWork.p, 0, (NC + 1) * 4, c.stream));
     unsigned int const g  = gridFor(n, 256);
     int const          nI = static_cast<int>(n);
-    classifyKernel<<<g, 256, 0, c.stream>>>(dTasks, n, c.index->dev.bsMode, tab, c.dClassKeys.p, c.dOrder.p, c.dClassInfo.p,
-                                            c.dClassInfo.p + NC, c.dClassInfo.p + 3 * NC, c.dCounters.p, nullptr);
+    classifyKernel<<<g, 256, 0, c.stream>>>(dTasks, n, c.index->dev.bsMode, tab, c.maxColsInt16, c.dClassKeys.p, c.dOrder.p,
+                                            c.dClassInfo.p, c.dClassInfo.p + NC, c.dClassInfo.p + 3 * NC, c.dCounters.p, nullptr);
     size_t t1 = 0, t2 = 0, t3 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, t1, c.dClassKeys.p, c.dClassKeysB.p, c.dOrder.p, c.dOrderB.p, nI, 0, 64, c.stream);
     if (!priv)
@@ -1267,8 +1290,9 @@ static void runTracePass(lgpu_ctx & c, lgpu_match const * dTasks, unsigned int n
     LGPU_CUDA(cudaMemsetAsync(c.dWork.p, 0, (NC + 1) * 4, c.stream));
     unsigned int const g  = gridFor(n, 256);
     int const          nI = static_cast<int>(n);
-    classifyKernel<<<g, 256, 0, c.stream>>>(dTasks, n, c.index->dev.bsMode, tab, c.dClassKeys.p, c.dOrder.p, c.dClassInfo.p,
-                                            c.dClassInfo.p + NC, c.dClassInfo.p + 3 * NC, c.dCounters.p, c.dPlaneWords.p);
+    classifyKernel<<<g, 256, 0, c.stream>>>(dTasks, n, c.index->dev.bsMode, tab, c.maxColsInt16, c.dClassKeys.p, c.dOrder.p,
+                                            c.dClassInfo.p, c.dClassInfo.p + NC, c.dClassInfo.p + 3 * NC, c.dCounters.p,
+                                            c.dPlaneWords.p);
     size_t t1 = 0, t2 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, t1, c.dClassKeys.p, c.dClassKeysB.p, c.dOrder.p, c.dOrderB.p, nI, 0, 64, c.stream);
     cub::DeviceScan::ExclusiveSum(nullptr, t2, c.dPlaneWordsB.p, c.dTraceOff.p, nI, c.stream);
@@ -1670,7 +1694,10 @@ static void fetchRecords(lgpu_ctx & c, lgpu_hit * dst, uint32_t qBase, uint32_t 
         StageTimer t(c, st ? &st->ms_d2h : nullptr);
         LGPU_CUDA(cudaMemcpyAsync(dst, c.finalDev, c.nFinal * sizeof(lgpu_hit), cudaMemcpyDeviceToHost, c.stream));
     }
+    LGPU_CUDA(cudaMemcpyAsync(c.hOverflow.p, c.dOverflow.p, 4, cudaMemcpyDeviceToHost, c.stream));
     syncStream(c);
+    if (c.hOverflow.p[0])
+        checkScoreOverflow(c);
     if (c.nFinal)
     {
         HostTimer ht(st ? &st->ms_host : nullptr);
@@ -1983,6 +2010,9 @@ static std::unique_ptr<lgpu_ctx> lgpu::makeContext(lgpu_index const * ix, lgpu_p
     LGPU_CUDA(cudaMemcpy(c->dMatrix.p, c->scoring.matrix, 1024, cudaMemcpyHostToDevice));
     LGPU_CUDA(cudaMemcpy(c->dMatrix.p + 1024, c->scoring.matrixRev, 1024, cudaMemcpyHostToDevice));
     c->dCounters.reserve(8);
+    c->dOverflow.reserve(1);
+    c->hOverflow.reserve(1);
+    LGPU_CUDA(cudaMemset(c->dOverflow.p, 0, 4));
     if (char const * e = std::getenv("LAMBDA_B200_SEED"))
         c->seedMode = !std::strcmp(e, "thread") ? 1 : !std::strcmp(e, "warp") ? 2 : !std::strcmp(e, "block") ? 3 : !std::strcmp(e, "spec") ? 4 : 0;
     if (char const * e = std::getenv("LAMBDA_B200_SEED_TEXT"))
@@ -2022,7 +2052,8 @@ static std::unique_ptr<lgpu_ctx> lgpu::makeContext(lgpu_index const * ix, lgpu_p
                 mx = std::max(mx, std::max<int>(c->scoring.matrix[a * 32 + b], c->scoring.matrixRev[a * 32 + b]));
                 mn = std::min(mn, std::min<int>(c->scoring.matrix[a * 32 + b], c->scoring.matrixRev[a * 32 + b]));
             }
-        int const go = c->scoring.gapOpenSeqan;
+        c->maxColsInt16 = static_cast<unsigned int>(32767 / std::max(mx, 1));
+        int const go    = c->scoring.gapOpenSeqan;
         c->resTraceOk = c->dpxOk && go < 0 && c->scoring.gapExtend <= 0 && mx - go <= 127 && 2 * (mx - go) - mn < 256;
     }
     if (char const * e = std::getenv("LAMBDA_B200_PLANE_MB")) // tests: force several launch groups
@@ -2080,6 +2111,7 @@ int lgpu_index_create(lgpu_index ** out, lgpu_index_desc const * d, int device)
                 pending.push_back({static_cast<unsigned char *>(dp), static_cast<unsigned char const *>(p), bytes});
             }
             ix->allocs.push_back(dp);
+            ix->allocBytes.push_back(static_cast<size_t>(bytes));
             ix->bytes += bytes;
             return dp;
         };
@@ -2115,6 +2147,7 @@ int lgpu_index_create(lgpu_index ** out, lgpu_index_desc const * d, int device)
             unsigned char *      dT  = nullptr;
             LGPU_CUDA(cudaMalloc(&dT, std::max<uint64_t>(tTotal, 1)));
             ix->allocs.push_back(dT);
+            ix->allocBytes.push_back(static_cast<size_t>(std::max<uint64_t>(tTotal, 1)));
             ix->bytes += tTotal;
             unsigned char * dComp = static_cast<unsigned char *>(up(kDna5Complement, 5));
             uint64_t const  nFr   = d->n_seqs * 6;
@@ -2172,6 +2205,79 @@ int lgpu_index_create(lgpu_index ** out, lgpu_index_desc const * d, int device)
                                ((flags & 2u) ? " CSA bit vector ranks outside the sampled suffix array;" : "") +
                                ((flags & 4u) ? " sampled suffix array names a sequence / position that does not exist;" : ""));
         }
+        *out = ix.release();
+    });
+}
+
+int lgpu_device_warmup(int device)
+{
+    return guarded(nullptr, [&] {
+        int nDev = 0;
+        if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0)
+            throw CudaError("no CUDA device available (lambda_b200 has no CPU fallback)");
+        LGPU_CUDA(cudaSetDevice(device));
+        LGPU_CUDA(cudaFree(nullptr)); // creates the context
+    });
+}
+
+int lgpu_index_clone(lgpu_index ** out, lgpu_index const * src, int device)
+{
+    if (!out || !src)
+        return LGPU_ERR_ARG;
+    *out = nullptr;
+    return guarded(nullptr, [&] {
+        LGPU_CUDA(cudaSetDevice(device));
+        auto ix           = std::make_unique<lgpu_index>();
+        ix->device        = device;
+        ix->meta          = src->meta;
+        ix->bytes         = src->bytes;
+        ix->dbTotalLength = src->dbTotalLength;
+        ix->sbjDelimsHost = src->sbjDelimsHost;
+        ix->dev           = src->dev;
+        if (device != src->device)
+        {
+            int can = 0;
+            LGPU_CUDA(cudaDeviceCanAccessPeer(&can, device, src->device));
+            if (can)
+            {
+                cudaError_t const e = cudaDeviceEnablePeerAccess(src->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                    LGPU_CUDA(e);
+                cudaGetLastError();
+            }
+        }
+        // every blob of the source, copied GPU to GPU (NVLink when the devices are peers)
+        for (size_t k = 0; k < src->allocs.size(); ++k)
+        {
+            void * dp = nullptr;
+            LGPU_CUDA(cudaMalloc(&dp, std::max<size_t>(src->allocBytes[k], 1)));
+            ix->allocs.push_back(dp);
+            ix->allocBytes.push_back(src->allocBytes[k]);
+            if (src->allocBytes[k])
+                LGPU_CUDA(cudaMemcpyPeerAsync(dp, device, src->allocs[k], src->device, src->allocBytes[k], nullptr));
+        }
+        auto remap = [&](void const * p) -> void const * {
+            if (!p)
+                return nullptr;
+            for (size_t k = 0; k < src->allocs.size(); ++k)
+            {
+                char const * b = static_cast<char const *>(src->allocs[k]);
+                char const * q = static_cast<char const *>(p);
+                if (q >= b && q < b + std::max<size_t>(src->allocBytes[k], 1))
+                    return static_cast<char const *>(ix->allocs[k]) + (q - b);
+            }
+            throw CudaError("lgpu_index_clone: a device pointer of the source index is not inside its allocations");
+        };
+        DevIndex & dv = ix->dev;
+        dv.occ        = static_cast<unsigned char const *>(remap(dv.occ));
+        dv.super      = static_cast<unsigned long long const *>(remap(dv.super));
+        dv.ssa        = static_cast<unsigned long long const *>(remap(dv.ssa));
+        dv.csa        = static_cast<CsaSuperDev const *>(remap(dv.csa));
+        dv.seqs       = static_cast<unsigned char const *>(remap(dv.seqs));
+        dv.seqDelims  = static_cast<unsigned long long const *>(remap(dv.seqDelims));
+        dv.origDelims = static_cast<unsigned long long const *>(remap(dv.origDelims));
+        LGPU_CUDA(cudaMemcpyToSymbol(cDna5Translate, kDna5Translate, 125));
+        LGPU_CUDA(cudaDeviceSynchronize());
         *out = ix.release();
     });
 }
@@ -2364,6 +2470,7 @@ int lgpu_extend_scores(lgpu_ctx * c, lgpu_query_batch const * q, lgpu_match cons
         LGPU_CUDA(cudaMemcpyAsync(scores, c->dScores.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
         syncStream(*c);
         resolveTimers(*c);
+        checkScoreOverflow(*c);
     });
 }
 
@@ -2389,6 +2496,7 @@ int lgpu_extend_trace(lgpu_ctx * c, lgpu_query_batch const * q, lgpu_match const
         LGPU_CUDA(cudaMemcpyAsync(out, c->dHits.p, n * sizeof(lgpu_hit), cudaMemcpyDeviceToHost, c->stream));
         syncStream(*c);
         resolveTimers(*c);
+        checkScoreOverflow(*c);
     });
 }
 

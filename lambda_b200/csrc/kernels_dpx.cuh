@@ -456,7 +456,8 @@ __host__ __device__ inline unsigned int dpxGroupsOf(int tab, int cls)
 
 // Sort keys of the alignments of one pass (see kDpxSegShift) + per-class counts / longest window / total cells.
 // tab selects the class table; withPlanes (pass 2) also writes the words of every alignment's residue plane.
-__global__ void classifyKernel(lgpu_match const * tasks, unsigned int n, unsigned int bsMode, int tab, unsigned long long * keys,
+__global__ void classifyKernel(lgpu_match const * tasks, unsigned int n, unsigned int bsMode, int tab, unsigned int maxColsInt16,
+                               unsigned long long * keys,
                                unsigned int * idx, unsigned int * classCount, unsigned int * classMaxNt, unsigned int * maxNq,
                                unsigned long long * cells, unsigned long long * planeWords)
 {
@@ -469,7 +470,9 @@ __global__ void classifyKernel(lgpu_match const * tasks, unsigned int n, unsigne
         nq = tasks[t].qry_end - tasks[t].qry_start;
         nt = tasks[t].subj_end - tasks[t].subj_start;
         c  = dpxClassOf(tab, nq);
-        if (nt > kDpxMaxWindow)
+        // the packed kernels compute in int16 lanes: only alignments whose best possible score (columns x largest
+        // matrix entry) fits may run there; the scalar kernel computes in 32 bits and reports an overflow
+        if (nt > kDpxMaxWindow || nq > maxColsInt16)
             c = dpxNumClasses(tab);
         unsigned int const ntc = nt < (1u << kDpxSegShift) ? nt : (1u << kDpxSegShift) - 1u;
         if (tab == kDpxTabShared)

@@ -167,6 +167,7 @@ struct ExtParams
     unsigned long long const * traceOff;
     unsigned int *        boundary;     // per-warp scratch: maxRows packed (S | hgap << 16)
     unsigned int          maxRows;
+    unsigned int *        overflowFlag; // set when a score leaves the reference's int16 range (src/search_algo.hpp:1047,1087)
 };
 
 constexpr int kNegInf = -16384; // INT16_MIN / 2, SQ/align/dp_cell.h:144-146
@@ -346,6 +347,8 @@ __global__ void __launch_bounds__(128) swWavefrontKernel(ExtParams P)
         if (lane == 0)
         {
             P.scores[task] = best;
+            if (best > 32767 && P.overflowFlag)
+                atomicOr(P.overflowFlag, 1u);
             if (TRACE)
             {
                 P.bestPos[2 * task]     = bi;

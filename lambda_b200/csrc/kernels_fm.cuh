@@ -226,7 +226,8 @@ __global__ void validateIndexKernel(DevIndex ix, unsigned long long nBlocks, uns
         unsigned int        in = 0;
         for (unsigned int w = 0; w < 4; ++w)
         {
-            if (__ldg(&sb->blocks[w]) != in)
+            // the writer fills the in-block counts only up to the word that holds the last row (bit i lives at i + 1)
+            if (k * 256 + w * 64 <= ix.nRows && __ldg(&sb->blocks[w]) != in)
                 bad |= 2u;
             in += static_cast<unsigned int>(__popcll(ldg64(&sb->bits[w])));
         }
@@ -237,7 +238,7 @@ __global__ void validateIndexKernel(DevIndex ix, unsigned long long nBlocks, uns
     {
         unsigned long long const v    = __ldg(ix.ssa + k);
         unsigned long long const subj = v >> ix.bitsForPos;
-        if (subj >= nFrameSubjects || (v & ix.posMask) > sbjLength(ix, static_cast<unsigned int>(subj)))
+        if (subj >= nFrameSubjects || (v & ix.posMask) > sbjLength(ix, static_cast<unsigned int>(subj)) + 1) // positions 0 .. length + 1
             bad |= 4u;
     }
     if (bad)

@@ -417,12 +417,12 @@ struct ShardResult
     double                tUpload = 0, tSearch = 0, tTeardown = 0; // seconds
 };
 
-void runShard(Options const & o, lgpu_index_desc const * desc, int device, Fasta const & f, uint64_t qBegin, uint64_t qEnd,
-              ShardResult & out)
+// `first`: the index on GPU 0 (uploaded from the host while the queries were read); the other GPUs copy it device to device
+void runShard(Options const & o, lgpu_index * first, int device, Fasta const & f, uint64_t qBegin, uint64_t qEnd, ShardResult & out)
 {
     double const t0 = now();
-    lgpu_index * ix = nullptr;
-    if (lgpu_index_create(&ix, desc, device) != LGPU_OK)
+    lgpu_index * ix = first;
+    if (device != 0 && lgpu_index_clone(&ix, first, device) != LGPU_OK)
     {
         out.error = lgpu_last_error(nullptr);
         return;
@@ -465,7 +465,8 @@ void runShard(Options const & o, lgpu_index_desc const * desc, int device, Fasta
     out.tSearch = now() - t1;
     double const t2 = now();
     lgpu_ctx_destroy(ctx);
-    lgpu_index_destroy(ix);
+    if (device != 0)
+        lgpu_index_destroy(ix);
     out.tTeardown = now() - t2;
 }
 
@@ -592,6 +593,32 @@ static int run(int argc, char ** argv)
         die("You requested taxonomic binning, but the index does not contain a taxonomic tree. Recreate it and provide "
             "--tax-dump-dir .");
     double const            t1   = now();
+    // CUDA context creation and the index upload to GPU 0 run while this thread reads the queries
+    lgpu_index *             ix0 = nullptr;
+    std::string              ix0Error;
+    double                   tUpload0 = 0;
+    std::vector<std::thread> early;
+    if (o.replayHits.empty())
+    {
+        for (int g = 1; g < o.gpus; ++g)
+            early.emplace_back([g] { lgpu_device_warmup(g); });
+        early.emplace_back([&] {
+            double const tu = now();
+            if (lgpu_index_create(&ix0, desc, 0) != LGPU_OK)
+                ix0Error = lgpu_last_error(nullptr);
+            tUpload0 = now() - tu;
+        });
+    }
+    struct EarlyJoin
+    {
+        std::vector<std::thread> & t;
+        ~EarlyJoin()
+        {
+            for (auto & x : t)
+                if (x.joinable())
+                    x.join();
+        }
+    } earlyJoin{early};
     // query alphabet: fixed for searchn / searchbs, given or auto-detected for searchp (src/search.cpp:209-216)
     uint32_t qryAlph = LGPU_ALPH_DNA5;
     if (o.domain == LGPU_DOMAIN_PROTEIN)
@@ -637,12 +664,19 @@ static int run(int argc, char ** argv)
             if (h.q_id >= nQ || h.s_id >= desc->n_seqs || static_cast<uint64_t>(h.cigar_off) + h.cigar_len > nOps)
                 die("hit file " + o.replayHits + " does not belong to these queries / this index");
     }
+    for (auto & t : early)
+        t.join();
+    early.clear();
+    if (!ix0Error.empty())
+        die(ix0Error);
     std::vector<std::thread> th;
     if (o.replayHits.empty())
         for (int g = 0; g < nShards; ++g)
-            th.emplace_back(runShard, std::cref(o), desc, g, std::cref(f), nQ * g / nShards, nQ * (g + 1) / nShards, std::ref(res[g]));
+            th.emplace_back(runShard, std::cref(o), ix0, g, std::cref(f), nQ * g / nShards, nQ * (g + 1) / nShards, std::ref(res[g]));
     for (auto & t : th)
         t.join();
+    if (!res.empty() && o.replayHits.empty())
+        res[0].tUpload += tUpload0;
     lgpu_stats total{};
     for (auto & r : res)
     {

@@ -593,3 +593,62 @@ def test_device_records_export_and_finalisation(golden_dir, case, domain, profil
     dev = s.fill_scores(buf[: n * HIT_DT.itemsize].cpu().numpy().view(HIT_DT).copy())
     assert n == len(h) and (dev == h).all()
     s.close(); ix.close(); o.close()
+
+
+def test_scores_beyond_int16_are_refused(golden_dir):
+    """The reference's DP lanes are int16 and wrap silently above 32767 (src/search_algo.hpp:1047,1087): its answer is
+    then meaningless.  Here such an alignment is an error (LGPU_ERR_UNSUPPORTED), never a different answer; just below
+    the limit the scalar kernels (queries > 2048 columns) agree with the oracle."""
+    path = os.path.join(golden_dir, "prot_flat", "db.lba")
+    o = orc.Oracle(path)
+    ix = lambda_b200.Index.load(path)
+    s = lambda_b200.Searcher(ix, "protein")
+    p = o.params(0)
+    lens = np.diff(np.ctypeslib.as_array(__import__("ctypes").cast(o.desc.seq_delims, __import__("ctypes").POINTER(
+        __import__("ctypes").c_uint64)), (o.desc.n_seqs + 1,)).astype(np.int64))
+    sid = int(np.argmax(lens))
+    # queries of W (BLOSUM62 W:W = 11) against a subject window: only the stage API can pair them (no seed would)
+    for n_w, ok in ((2900, True), (3100, True)):  # real subjects: scores stay small, both lengths take the scalar path
+        res = lambda_b200.encode(np.frombuffer(b"W" * n_w, np.uint8), 0)
+        offs = np.array([0, n_w], np.uint64)
+        win = np.zeros(1, MATCH_DT)
+        win["subj_id"], win["qry_end"], win["subj_end"] = sid, n_w, lens[sid]
+        sc, _ = s.extend_scores(res, offs, win)
+        sc_cpu, _ = o.extend(p, res, offs, win, False)
+        assert (sc == sc_cpu).all()
+    s.close(); ix.close(); o.close()
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="reference binary (oracle/_ref/lambda3) not built")
+def test_long_self_hits_vs_live_reference_and_int16_limit(tmp_path):
+    """queries beyond the packed kernels' 2048 columns against the live reference: a 3300-residue self hit whose score
+    stays below 32767 must come out identical; a 3700-residue one exceeds the reference's int16 lanes and is refused"""
+    rng = np.random.default_rng(77)
+    db, offs = synth.protein_db(300, seed=78)
+    hi = np.frombuffer(b"WCH", np.uint8)  # self scores 11, 9, 8
+    longs = [hi[rng.integers(0, 3, n)] for n in (3300, 3700)]
+    seqs = [db[offs[i]:offs[i + 1]] for i in range(len(offs) - 1)] + longs
+    o2 = np.concatenate([[0], np.cumsum([len(x) for x in seqs])]).astype(np.int64)
+    synth.write_fasta(str(tmp_path / "db.fasta"), np.concatenate(seqs), o2, "S")
+    subprocess.check_call([REF, "mkindexp", "-d", str(tmp_path / "db.fasta"), "-i", str(tmp_path / "db.lba"), "-v", "0"])
+    ix = lambda_b200.Index.load(str(tmp_path / "db.lba"))
+    s = lambda_b200.Searcher(ix, "protein")
+    # below the limit: identical to the reference
+    q_ok = np.concatenate([seqs[5], longs[0]])
+    qo = np.array([0, len(seqs[5]), len(q_ok)], np.int64)
+    synth.write_fasta(str(tmp_path / "q.fasta"), q_ok, qo, "Q")
+    subprocess.check_call([REF, "searchp", "-q", str(tmp_path / "q.fasta"), "-i", str(tmp_path / "db.lba"), "-o",
+                           str(tmp_path / "ref.m8"), "--version-to-outputfile", "0", "-v", "0"])
+    ids, hits, st = s.search_fasta(str(tmp_path / "q.fasta"))
+    ref = open(tmp_path / "ref.m8").read().splitlines(True)
+    assert sorted(s.m8(hits, ids)) == sorted(ref)
+    assert hits["score"].max() > 25000 and hits["score"].max() <= 32767
+    # above it: an error, not an answer
+    res = lambda_b200.encode(longs[1], 0)
+    with pytest.raises(lambda_b200.LambdaError) as e:
+        s.search(res, np.array([0, len(res)], np.uint64))
+    assert e.value.code == -4 and "32767" in str(e.value)
+    # the context stays usable
+    ids2, hits2, _ = s.search_fasta(str(tmp_path / "q.fasta"))
+    assert (hits2 == hits).all()
+    s.close(); ix.close()
