@@ -321,6 +321,7 @@ struct lgpu_index
 struct lgpu_ctx
 {
     lgpu_index const * index = nullptr;
+    int                device = 0;
     lgpu_params        params{};
     Scoring            scoring;
     DomainInfo         di;
@@ -419,7 +420,7 @@ struct lgpu_ctx
     ~lgpu_ctx()
     {
         if (index)
-            cudaSetDevice(index->device);
+            cudaSetDevice(device); // not index->device: the index may already be gone (e.g. garbage-collected first)
         for (auto & e : ev)
             if (e)
                 cudaEventDestroy(e);
@@ -1988,6 +1989,7 @@ static std::unique_ptr<lgpu_ctx> lgpu::makeContext(lgpu_index const * ix, lgpu_p
     checkParams(p, ix->meta);
     auto c    = std::make_unique<lgpu_ctx>();
     c->index  = ix;
+    c->device = ix->device;
     c->params = p;
     c->di     = domainInfo(p.domain, ix->meta.orig_alph, p.query_alph);
     int rc    = makeScoring(c->scoring, p);

@@ -595,10 +595,9 @@ def test_device_records_export_and_finalisation(golden_dir, case, domain, profil
     s.close(); ix.close(); o.close()
 
 
-def test_scores_beyond_int16_are_refused(golden_dir):
-    """The reference's DP lanes are int16 and wrap silently above 32767 (src/search_algo.hpp:1047,1087): its answer is
-    then meaningless.  Here such an alignment is an error (LGPU_ERR_UNSUPPORTED), never a different answer; just below
-    the limit the scalar kernels (queries > 2048 columns) agree with the oracle."""
+def test_queries_beyond_the_int16_column_limit_take_the_scalar_path(golden_dir):
+    """32767 / 11 = 2978 columns is the longest BLOSUM62 query whose scores cannot leave the packed kernels' int16
+    lanes; longer ones (and everything > 2048 columns) run on the 32-bit scalar kernels and agree with the oracle"""
     path = os.path.join(golden_dir, "prot_flat", "db.lba")
     o = orc.Oracle(path)
     ix = lambda_b200.Index.load(path)
