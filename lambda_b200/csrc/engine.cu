@@ -722,7 +722,8 @@ static void uploadQueries(lgpu_ctx & c, BatchView const & qb, lgpu_stats * st)
         st->kernel_launches += 1;
 }
 
-// Depth of the prefix table for a seed whose exactly matched part has h1 symbols: as deep as 2^21 entries allow.
+// Depth of the prefix table for a seed whose exactly matched part has h1 symbols: as deep as 2^22 entries (32 MB,
+// L2-resident next to the packed occurrence blocks of a short-read index) allow.
 static unsigned int prefixDepth(lgpu_index const & ix, unsigned int h1)
 {
     uint64_t const A = ix.dev.sigma - 1;
@@ -730,7 +731,7 @@ static unsigned int prefixDepth(lgpu_index const & ix, unsigned int h1)
         return 0;
     unsigned int k = 0;
     uint64_t     n = 1;
-    while (k < h1 && n * A <= (1ull << 21))
+    while (k < h1 && n * A <= (1ull << 22))
     {
         n *= A;
         ++k;
@@ -2187,6 +2188,38 @@ int lgpu_index_create(lgpu_index ** out, lgpu_index_desc const * d, int device)
         ix->meta.id_delims    = nullptr;
         runUploads(pending, device);
         LGPU_CUDA(cudaDeviceSynchronize());
+        // re-pack the occurrence table: one aligned sector (or line) per rank; LAMBDA_B200_OCC_PACK=0 keeps the file's layout
+        dv.occP = nullptr;
+        dv.mid  = nullptr;
+        char const * const pe = std::getenv("LAMBDA_B200_OCC_PACK");
+        if ((!pe || std::atoi(pe) != 0) && d->n_blocks)
+        {
+            unsigned int const need = 8 * d->sigma_bits + 2 * (d->sigma - 1);
+            dv.pCntOff              = 8 * d->sigma_bits;
+            dv.pStride              = need <= 32 ? 32u : need <= 64 ? 64u : (need + 63) / 64 * 64;
+            uint64_t const nGroups  = (d->n_blocks + 1023) / 1024;
+            unsigned char *      dP = nullptr;
+            unsigned long long * dM = nullptr;
+            LGPU_CUDA(cudaMalloc(reinterpret_cast<void **>(&dP), d->n_blocks * dv.pStride));
+            ix->allocs.push_back(dP);
+            ix->allocBytes.push_back(d->n_blocks * dv.pStride);
+            LGPU_CUDA(cudaMalloc(reinterpret_cast<void **>(&dM), nGroups * d->sigma * 8));
+            ix->allocs.push_back(dM);
+            ix->allocBytes.push_back(nGroups * d->sigma * 8);
+            ix->bytes += d->n_blocks * dv.pStride + nGroups * d->sigma * 8;
+            PackOccParams PP{};
+            PP.ix      = dv;
+            PP.nBlocks = d->n_blocks;
+            for (unsigned int s2 = 0; s2 < d->sigma; ++s2)
+                PP.C[s2] = d->C[s2];
+            PP.occP = dP;
+            PP.mid  = dM;
+            packOccKernel<<<gridFor(d->n_blocks, 256), 256>>>(PP);
+            LGPU_CUDA(cudaGetLastError());
+            LGPU_CUDA(cudaDeviceSynchronize());
+            dv.occP = dP;
+            dv.mid  = dM;
+        }
         char const * const ve = std::getenv("LAMBDA_B200_VALIDATE");
         if (!ve || std::atoi(ve) != 0)
         {
@@ -2278,6 +2311,8 @@ int lgpu_index_clone(lgpu_index ** out, lgpu_index const * src, int device)
         dv.seqs       = static_cast<unsigned char const *>(remap(dv.seqs));
         dv.seqDelims  = static_cast<unsigned long long const *>(remap(dv.seqDelims));
         dv.origDelims = static_cast<unsigned long long const *>(remap(dv.origDelims));
+        dv.occP       = static_cast<unsigned char const *>(remap(dv.occP));
+        dv.mid        = static_cast<unsigned long long const *>(remap(dv.mid));
         LGPU_CUDA(cudaMemcpyToSymbol(cDna5Translate, kDna5Translate, 125));
         LGPU_CUDA(cudaDeviceSynchronize());
         *out = ix.release();

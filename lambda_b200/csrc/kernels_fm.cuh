@@ -58,6 +58,16 @@ struct DevIndex
     unsigned int               blockBytes, planesOff, sigma, sigmaBits;
     unsigned int               singleSuper; // 1: only one super block -> folded into Cbase
     unsigned long long         Cbase[32];   // C[s] (+ superBlocks[0][s] if singleSuper)
+    // Occurrence table re-packed at index creation (packOccKernel) so that a rank touches ONE aligned 32-byte sector
+    // (dna4: 24 B of bit planes + 4 x u16 counts) or one 64-byte line (Li10: 32 B planes + 10 x u16; dna3bs): the
+    // reference's 48- / 80-byte blocks at 8-byte alignment straddle two to four sectors for the same 28 / 36 bytes.
+    // Same arithmetic (FMC occtable/InterleavedEPRV2.h:81-86,211-216): counts are kept relative to groups of 1024
+    // blocks (u16), `mid` holds C[s] + super block + count in front of every group.  Symbol 0 (the sentinel) is only
+    // ranked by locate steps that run into a sequence border and keeps using the original blocks.
+    unsigned char const *      occP;    // nullptr: not packed
+    unsigned long long const * mid;     // [group][sigma]
+    unsigned int               pStride; // 32 or 64
+    unsigned int               pCntOff; // 8 * sigmaBits
 };
 
 __device__ __forceinline__ unsigned long long ldg64(void const * p)
@@ -98,8 +108,34 @@ __device__ __forceinline__ unsigned long long fmSymbolMask(DevIndex const & ix, 
     return mask;
 }
 
+// bit mask of the positions of `symb` inside a packed block (planes at the start of the block)
+__device__ __forceinline__ unsigned long long fmSymbolMaskPacked(DevIndex const & ix, unsigned char const * b, unsigned int symb)
+{
+    unsigned long long mask = ~0ull;
+#pragma unroll
+    for (unsigned int p = 0; p < 5; ++p)
+        if (p < ix.sigmaBits)
+        {
+            unsigned long long const plane = ldg64(b + 8 * p);
+            mask &= ((symb >> p) & 1u) ? plane : ~plane;
+        }
+    return mask;
+}
+
+__device__ __forceinline__ unsigned long long fmRankPacked(DevIndex const & ix, unsigned long long idx, unsigned int symb)
+{
+    unsigned char const *    b    = ix.occP + (idx >> 6) * ix.pStride;
+    unsigned int const       cnt  = __ldg(reinterpret_cast<unsigned short const *>(b + ix.pCntOff) + (symb - 1u));
+    unsigned long long const mask = fmSymbolMaskPacked(ix, b, symb);
+    unsigned int const       bit  = static_cast<unsigned int>(idx) & 63u;
+    unsigned int const       pc   = bit ? __popcll(mask << (64u - bit)) : 0u;
+    return __ldg(ix.mid + (idx >> 16) * ix.sigma + symb) + cnt + pc;
+}
+
 __device__ __forceinline__ unsigned long long fmRank(DevIndex const & ix, unsigned long long idx, unsigned int symb)
 {
+    if (ix.occP && symb != 0)
+        return fmRankPacked(ix, idx, symb);
     unsigned char const *    b    = ix.occ + (idx >> 6) * ix.blockBytes;
     unsigned int const       cnt  = __ldg(reinterpret_cast<unsigned int const *>(b) + symb);
     unsigned long long const mask = fmSymbolMask(ix, b, symb);
@@ -115,6 +151,28 @@ __device__ __forceinline__ unsigned long long fmRank(DevIndex const & ix, unsign
 // one LF step from BWT row idx: rank of the symbol found at idx
 __device__ __forceinline__ unsigned long long fmRankSymbol(DevIndex const & ix, unsigned long long idx)
 {
+    if (ix.occP)
+    {
+        unsigned char const * pb   = ix.occP + (idx >> 6) * ix.pStride;
+        unsigned int const    bit  = static_cast<unsigned int>(idx) & 63u;
+        unsigned int          symb = 0;
+        unsigned long long    mask = ~0ull;
+#pragma unroll
+        for (unsigned int p = 0; p < 5; ++p)
+            if (p < ix.sigmaBits)
+            {
+                unsigned long long const plane = ldg64(pb + 8 * p);
+                unsigned int const       v     = static_cast<unsigned int>(plane >> bit) & 1u;
+                symb |= v << p;
+                mask &= v ? plane : ~plane;
+            }
+        if (symb != 0)
+        {
+            unsigned int const cnt = __ldg(reinterpret_cast<unsigned short const *>(pb + ix.pCntOff) + (symb - 1u));
+            unsigned int const pc  = bit ? __popcll(mask << (64u - bit)) : 0u;
+            return __ldg(ix.mid + (idx >> 16) * ix.sigma + symb) + cnt + pc;
+        }
+    }
     unsigned char const * b    = ix.occ + (idx >> 6) * ix.blockBytes;
     unsigned int const    bit  = static_cast<unsigned int>(idx) & 63u;
     unsigned int          symb = 0;
@@ -172,6 +230,43 @@ __device__ __forceinline__ Cursor fmExtendRight(DevIndex const & ix, Cursor c, u
     n.lb  = lb;
     n.len = fmRank(ix, c.lb + c.len, symb) - lb;
     return n;
+}
+
+// packed block b = bit planes + u16 counts of symbols 1 .. sigma-1 relative to the first block of its group of 1024;
+// mid[g][s] = C[s] + super block + count in front of group g  (C passed by value: Cbase may already contain the super block)
+struct PackOccParams
+{
+    DevIndex             ix;
+    unsigned long long   nBlocks;
+    unsigned long long   C[32];
+    unsigned char *      occP;
+    unsigned long long * mid;
+};
+
+__global__ void packOccKernel(PackOccParams P)
+{
+    DevIndex const &         ix = P.ix;
+    unsigned long long const b  = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+    if (b >= P.nBlocks)
+        return;
+    unsigned long long const b0   = b & ~1023ull;
+    unsigned char const *    src  = ix.occ + b * ix.blockBytes;
+    unsigned char const *    src0 = ix.occ + b0 * ix.blockBytes;
+    unsigned char *          dst  = P.occP + b * ix.pStride;
+    for (unsigned int p = 0; p < ix.sigmaBits; ++p)
+        reinterpret_cast<unsigned long long *>(dst)[p] = ldg64(src + ix.planesOff + 8 * p);
+    for (unsigned int s = 1; s < ix.sigma; ++s)
+    {
+        unsigned int const c  = __ldg(reinterpret_cast<unsigned int const *>(src) + s);
+        unsigned int const c0 = __ldg(reinterpret_cast<unsigned int const *>(src0) + s);
+        reinterpret_cast<unsigned short *>(dst + ix.pCntOff)[s - 1] = static_cast<unsigned short>(c - c0);
+        if (b == b0)
+            P.mid[(b >> 10) * ix.sigma + s] = P.C[s] + __ldg(ix.super + (b >> 26) * ix.sigma + s) + c0;
+    }
+    if (b == b0)
+        P.mid[(b >> 10) * ix.sigma] = 0;
+    for (unsigned int k = ix.pCntOff + 2 * (ix.sigma - 1); k < ix.pStride; ++k)
+        dst[k] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
