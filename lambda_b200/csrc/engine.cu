@@ -72,6 +72,20 @@ struct UnsupportedError : std::runtime_error
 
 static thread_local std::string g_lastError;
 
+// LAMBDA_B200_TRACE_TIMES=1: wall-clock marks on stderr (where does a cold first call spend its time?)
+static void traceTime(char const * label)
+{
+    static int const on = [] {
+        char const * e = std::getenv("LAMBDA_B200_TRACE_TIMES");
+        return e && std::atoi(e) != 0 ? 1 : 0;
+    }();
+    if (!on)
+        return;
+    static auto const t0 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[lgpu %9.3f ms] %s\n",
+                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), label);
+}
+
 // growable device buffer
 template <typename T>
 struct DevBuf
@@ -1440,7 +1454,9 @@ static void runExtension(lgpu_ctx & c, uint64_t nMatches, uint8_t phase, lgpu_st
     if (nTasks == 0)
         return;
     c.dScores.reserve(nTasks);
+    traceTime("extension: merged");
     runScorePass(c, c.dMerged.p, static_cast<unsigned int>(nTasks), c.dScores.p, st);
+    traceTime("extension: score pass launched");
 
     // filter on the device with per-query integer thresholds
     c.dHead.reserve(nTasks);
@@ -1470,7 +1486,9 @@ static void runExtension(lgpu_ctx & c, uint64_t nMatches, uint8_t phase, lgpu_st
     }
     if (nKeep == 0)
         return;
+    traceTime("extension: filtered");
     runTracePass(c, c.dTasks2.p, nKeep, st);
+    traceTime("extension: trace pass launched");
 
     // identity cut-off, phase, "query is done" flags (src/search_algo.hpp:1308-1322); survivors join the batch's records
     c.dAllHits.grow(c.nAll + nKeep, c.nAll, c.stream);
@@ -1653,6 +1671,7 @@ static void searchDevice(lgpu_ctx & c, BatchView const & qb, lgpu_stats * st)
     c.nFinal     = 0;
     c.finalDev   = nullptr;
     c.timersUsed = 0;
+    traceTime("search: start");
     uploadQueries(c, qb, st);
     if (!c.evc)
         c.evc = std::make_unique<EValueComputer>(c.scoring.ka, c.index->dbTotalLength, c.di.qIsTranslated);
@@ -1669,7 +1688,9 @@ static void searchDevice(lgpu_ctx & c, BatchView const & qb, lgpu_stats * st)
     if (c.params.iterative_search)
     {
         uint64_t nM = runSeeding(c, c.params.opts0, c.dActive.p, n, c.maxQueryLen, st);
+        traceTime("search: phase 1 seeded");
         runExtension(c, nM, 1, st);
+        traceTime("search: phase 1 extended");
         unsigned int       maxLen  = 0;
         unsigned int const nActive = buildActiveList(c, maxLen, st);
         if (nActive)
@@ -1683,7 +1704,9 @@ static void searchDevice(lgpu_ctx & c, BatchView const & qb, lgpu_stats * st)
         uint64_t const nM = runSeeding(c, c.params.opts, c.dActive.p, n, c.maxQueryLen, st);
         runExtension(c, nM, 2, st);
     }
+    traceTime("search: phases done");
     finalizeOnDevice(c, st);
+    traceTime("search: finalised");
 }
 
 // Second half of a search: the nFinal records of searchDevice() to `dst` (pinned host memory of the calling context),
@@ -1713,6 +1736,7 @@ static void fetchRecords(lgpu_ctx & c, lgpu_hit * dst, uint32_t qBase, uint32_t 
         }
     }
     resolveTimers(c);
+    traceTime("search: records on the host");
 }
 
 static std::unique_ptr<lgpu_ctx> makeContext(lgpu_index const * ix, lgpu_params const & p);
@@ -2061,6 +2085,7 @@ static std::unique_ptr<lgpu_ctx> lgpu::makeContext(lgpu_index const * ix, lgpu_p
     }
     if (char const * e = std::getenv("LAMBDA_B200_PLANE_MB")) // tests: force several launch groups
         c->maxPlaneWords = static_cast<uint64_t>(std::max(1, std::atoi(e))) * (1u << 20) / 4;
+    traceTime("context created");
     return c;
 }
 
@@ -2101,6 +2126,7 @@ int lgpu_index_create(lgpu_index ** out, lgpu_index_desc const * d, int device)
         if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0)
             throw CudaError("no CUDA device available (lambda_b200 has no CPU fallback)");
         LGPU_CUDA(cudaSetDevice(device));
+        traceTime("index: context ready");
         auto ix    = std::make_unique<lgpu_index>();
         ix->device = device;
         std::vector<UploadJob> pending; // large blobs are copied together by runUploads()
@@ -2186,8 +2212,10 @@ int lgpu_index_create(lgpu_index ** out, lgpu_index_desc const * d, int device)
         ix->meta.seq_delims   = nullptr;
         ix->meta.ids          = nullptr;
         ix->meta.id_delims    = nullptr;
+        traceTime("index: allocations done, uploading");
         runUploads(pending, device);
         LGPU_CUDA(cudaDeviceSynchronize());
+        traceTime("index: uploaded");
         // re-pack the occurrence table: one aligned sector (or line) per rank; LAMBDA_B200_OCC_PACK=0 keeps the file's layout
         dv.occP = nullptr;
         dv.mid  = nullptr;
@@ -2220,6 +2248,7 @@ int lgpu_index_create(lgpu_index ** out, lgpu_index_desc const * d, int device)
             dv.occP = dP;
             dv.mid  = dM;
         }
+        traceTime("index: packed");
         char const * const ve = std::getenv("LAMBDA_B200_VALIDATE");
         if (!ve || std::atoi(ve) != 0)
         {
@@ -2315,6 +2344,7 @@ int lgpu_index_clone(lgpu_index ** out, lgpu_index const * src, int device)
         dv.mid        = static_cast<unsigned long long const *>(remap(dv.mid));
         LGPU_CUDA(cudaMemcpyToSymbol(cDna5Translate, kDna5Translate, 125));
         LGPU_CUDA(cudaDeviceSynchronize());
+        traceTime("index: validated");
         *out = ix.release();
     });
 }

@@ -1496,7 +1496,10 @@ constexpr int kSpecWarps = 4;
 
 // 5 resident blocks (20 warps) per SM: caps the kernel at 96 registers -- what it used before the 'N' handling was added
 // to every symbol read (116 without the bound = one block less per SM); no spills either way (ptxas -v)
-__global__ void __launch_bounds__(32 * kSpecWarps, 5) seedSpecKernel(SeedParams P)
+#ifndef LGPU_SPEC_MINBLOCKS
+#define LGPU_SPEC_MINBLOCKS 5
+#endif
+__global__ void __launch_bounds__(32 * kSpecWarps, LGPU_SPEC_MINBLOCKS) seedSpecKernel(SeedParams P)
 {
     __shared__ signed char sM[2048];
     __shared__ SpecScratch sS[kSpecWarps];
