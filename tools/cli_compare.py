@@ -26,6 +26,9 @@ def run(cmd):
     if p.returncode != 0:
         sys.stderr.write(p.stdout[-2000:] + p.stderr[-2000:])
         raise SystemExit(f"{cmd[0]} failed with {p.returncode}")
+    for line in p.stderr.splitlines():  # LAMBDA_B200_TRACE_TIMES=1: where a cold call spends its time
+        if line.startswith("[lgpu"):
+            sys.stderr.write(line + "\n")
     return dt, p.stdout + p.stderr
 
 
