@@ -494,8 +494,11 @@ def main():
         return a
 
     for _ in range(args.warmup):
-        step(True)
+        hits_w, _ = step(True)
         step(True, s_serial)
+    if gather is not None:
+        gather.finish()
+        gather.fit(len(hits_w))  # slots sized for what the ranks really produce (collective, before the timed region)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()

@@ -2099,6 +2099,7 @@ int lgpu_lba_open(lgpu_lba ** out, char const * path)
     if (!out || !path)
         return LGPU_ERR_ARG;
     *out = nullptr;
+    traceTime("lba: open");
     return guarded(nullptr, [&] {
         auto l  = std::make_unique<lgpu_lba>();
         l->file = std::make_unique<LbaFile>(path);
@@ -2117,6 +2118,7 @@ int lgpu_index_create(lgpu_index ** out, lgpu_index_desc const * d, int device)
     if (!out || !d)
         return LGPU_ERR_ARG;
     *out = nullptr;
+    traceTime("index: create called");
     return guarded(nullptr, [&] {
         if (d->index_type != LGPU_INDEX_FM)
             throw UnsupportedError("only unidirectional FM indexes are supported");
@@ -2156,8 +2158,10 @@ int lgpu_index_create(lgpu_index ** out, lgpu_index_desc const * d, int device)
         dv.bsMode      = d->red_alph == LGPU_ALPH_DNA3BS ? 1 : 0;
         dv.sbjFrames   = d->red_alph == LGPU_ALPH_DNA3BS ? 2 : 1;
         dv.nSeqs       = d->n_seqs;
+        traceTime("index: device memory allocated");
         runUploads(pending, device);
         pending.clear();
+        traceTime("index: main blobs uploaded");
         LGPU_CUDA(cudaMemcpyToSymbol(cDna5Translate, kDna5Translate, 125));
         // dbTotalLength = sum of reduced subject lengths (src/search_algo.hpp:317-318)
         ix->dbTotalLength = d->n_residues * (d->red_alph == LGPU_ALPH_DNA3BS ? 2 : 1);

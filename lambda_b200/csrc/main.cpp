@@ -580,6 +580,15 @@ static int run(int argc, char ** argv)
     if (o.verbosity >= 1)
         std::printf("LAMBDA (B200 engine) - the Local Aligner for Massive Biological DatA\n\n");
 
+    // Driver initialisation costs time per VISIBLE device (seconds on an 8-GPU box without persistence mode): unless the
+    // user chose the devices, show the process only the GPUs it is going to use.
+    if (!std::getenv("CUDA_VISIBLE_DEVICES") && o.replayHits.empty())
+    {
+        std::string vis;
+        for (int g = 0; g < o.gpus; ++g)
+            vis += (g ? "," : "") + std::to_string(g);
+        setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 1);
+    }
     lgpu_lba * lba = nullptr;
     if (lgpu_lba_open(&lba, o.index.c_str()) != LGPU_OK)
         die(lgpu_last_error(nullptr));

@@ -115,6 +115,19 @@ class DeviceHitGather:
         self.send = t.zeros(self.slot, dtype=t.uint8, device=self.device)
         self.recv = t.zeros(self.world * self.slot, dtype=t.uint8, device=self.device)
 
+    def fit(self, n_local: int, slack: float = 1.25):
+        """Collective, outside any timed region: size the slots for the largest per-rank record count seen so far
+        (times `slack`) -- the gather moves whole slots, so a tight slot is a cheap gather.  A later overflow is still
+        handled by finish()."""
+        t, dist = self.torch, self.dist
+        need = t.tensor([int(n_local)], dtype=t.int64, device=self.device)
+        if self.world > 1:
+            dist.all_reduce(need, op=dist.ReduceOp.MAX)
+        if self.cuda:
+            self.stream.synchronize()
+        self.pending = False
+        self._alloc(max(int(int(need.item()) * slack), 1024))
+
     def _exchange(self):
         t, dist = self.torch, self.dist
         self.send[:8].view(t.int64).fill_(self.n_local)

@@ -88,6 +88,11 @@ def _worker_device_gather(rank, world, port, n_queries, q):
             got = g.records()
             ok = ok and total == len(expect) and len(got) == len(expect) and (got == expect).all()
         ok = ok and (g.regrown == (0 if cap > 3 else 1))
+    g = DeviceHitGather(4 * n_queries)
+    g.fit(len(mine))  # collective: slots for the largest contribution
+    ok = ok and g.cap >= len(mine) and g.cap < 4 * n_queries + 1024
+    g.start(_FakeSearcher(mine), first_query=b)
+    ok = ok and g.finish() == len(expect) and (g.records() == expect).all()
     g = DeviceHitGather(8)
     g.start(_FakeSearcher(np.zeros(0, HIT_DT) if rank == 0 else mine[:5]), first_query=b)
     ok = ok and g.finish() == 5 * (world - 1) and len(g.records()) == 5 * (world - 1)
