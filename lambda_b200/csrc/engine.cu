@@ -643,10 +643,10 @@ static void checkParams(lgpu_params const & p, lgpu_index_desc const & d)
     {
         if (o->seed_length == 0 || o->seed_length > 2 * kMaxHalf2 || o->seed_offset == 0)
             throw ArgError("seed length must be in [1,32] and seed offset > 0");
-        if (o->max_seed_dist > 1)
-            throw UnsupportedError("seed distances > 1 are not implemented (reference default profiles use 0 or 1)");
-        if (o->max_seed_dist == 1 && !p.seed_half_exact && o->seed_length > kMaxHalf2)
-            throw UnsupportedError("max_seed_dist = 1 without seed_half_exact supports seeds up to 16 residues");
+        if (o->max_seed_dist > 2)
+            throw UnsupportedError("seed distances > 2 are not implemented (reference default profiles use 0 or 1)");
+        if (o->max_seed_dist >= 1 && !p.seed_half_exact && o->seed_length > kMaxHalf2)
+            throw UnsupportedError("max_seed_dist > 0 without seed_half_exact supports seeds up to 16 residues");
     }
     if (p.max_matches == 0)
         throw ArgError("max_matches must be > 0");
@@ -795,7 +795,7 @@ static uint64_t runSeeding(lgpu_ctx & c, lgpu_search_opts const & so, unsigned i
         P.seedOffset       = so.seed_offset;
         P.maxSeedDist      = so.max_seed_dist;
         P.halfExact        = c.params.seed_half_exact;
-        P.fullHamming      = (so.max_seed_dist == 1 && !c.params.seed_half_exact) ? 1u : 0u;
+        P.fullHamming      = (so.max_seed_dist >= 1 && !c.params.seed_half_exact) ? 1u : 0u;
         P.adaptive         = c.params.adaptive_seeding;
         P.maxMatches       = c.params.max_matches;
         P.preScoring       = c.params.pre_scoring;
@@ -821,7 +821,8 @@ static uint64_t runSeeding(lgpu_ctx & c, lgpu_search_opts const & so, unsigned i
         // (most independent chains in flight).
         bool const         halfMode  = so.max_seed_dist != 0 && c.params.seed_half_exact;
         unsigned int const n2        = P.fullHamming ? so.seed_length : (halfMode ? so.seed_length - so.seed_length / 2 : 0);
-        unsigned int const maxLeaves = (c.index->dev.sigma - 2) * n2 + 1;
+        unsigned int const A         = c.index->dev.sigma - 1;
+        unsigned int const maxLeaves = (A - 1) * n2 + 1 + (so.max_seed_dist >= 2 ? n2 * (n2 - 1) / 2 * (A - 1) * (A - 1) : 0u);
         unsigned int const maxSeeds  = maxActiveLen >= so.seed_length
                                          ? c.di.qryNumFrames * ((maxActiveLen - so.seed_length) / so.seed_offset + 1)
                                          : 1;
@@ -844,7 +845,7 @@ static uint64_t runSeeding(lgpu_ctx & c, lgpu_search_opts const & so, unsigned i
         }
         else if (c.seedMode == 2)
             seedWarpKernel<<<gridFor(static_cast<unsigned long long>(nActive) * 32, 128), 128, 0, c.stream>>>(P);
-        else if (c.seedMode == 1 && !P.fullHamming) // the thread-per-query kernel has no level-order search tree
+        else if (c.seedMode == 1 && !P.fullHamming && so.max_seed_dist < 2) // the thread-per-query kernel: no level order, one mismatch
             seedKernel<<<gridFor(nActive, 128), 128, 0, c.stream>>>(P);
         else
             seedSpecKernel<<<gridFor(static_cast<unsigned long long>(nActive) * 32, 32 * kSpecWarps), 32 * kSpecWarps, 0,

@@ -928,6 +928,156 @@ __device__ __forceinline__ Cursor seedLeaf(DevIndex const & ix, Cursor const * E
     return mine;
 }
 
+// ---- seeds with up to TWO mismatches (max_seed_dist = 2) ---------------------------------------------------------
+// number of strings of length m within Hamming distance <= b (b <= 2) of a given one over an alphabet of A symbols
+__device__ __forceinline__ unsigned int hammingBall(unsigned int m, unsigned int b, unsigned int A)
+{
+    unsigned int n = 1;
+    if (b >= 1)
+        n += m * (A - 1);
+    if (b >= 2)
+        n += m * (m - 1) / 2 * (A - 1) * (A - 1);
+    return n;
+}
+
+// How many leaves the enumeration below produces for one seed (empty ones included: a lane finds out by walking).
+__device__ __forceinline__ unsigned int seedNumLeaves2(unsigned int n2, unsigned int A, bool levelOrder)
+{
+    (void) levelOrder; // both orders enumerate the whole ball
+    return hammingBall(n2, 2, A);
+}
+
+// the mismatch (level, symbol) number `i` of the "down then back up" order over levels 0 .. nLevels-1 WITHOUT the
+// exact string: symbols below the seed symbol per level going down, then symbols above it per level going back up
+__device__ __forceinline__ void seedOneMismatch(unsigned char const * red, unsigned int seedBegin, unsigned int h1, bool bs,
+                                                unsigned int nLevels, unsigned int A, unsigned int i, int & lvl, unsigned int & r)
+{
+    lvl = -1;
+    r   = 0;
+    for (unsigned int l = 0; l < nLevels; ++l)
+    {
+        unsigned int const want = seedSym(red, seedBegin, seedBegin + h1 + l, bs);
+        if (i < want)
+        {
+            lvl = static_cast<int>(l);
+            r   = i;
+            return;
+        }
+        i -= want;
+    }
+    for (int l = static_cast<int>(nLevels) - 1; l >= 0; --l)
+    {
+        unsigned int const want = seedSym(red, seedBegin, seedBegin + h1 + l, bs);
+        unsigned int const cnt  = A - 1 - want;
+        if (i < cnt)
+        {
+            lvl = l;
+            r   = want + 1 + i;
+            return;
+        }
+        i -= cnt;
+    }
+}
+
+// Leaf `idx` of the search tree of a seed part of n2 symbols with up to two mismatches, in the reference's production
+// order; E[l] = cursor of the exactly matched first l symbols (levels 0 .. K non-empty).
+//   levelOrder = false (seed_half_exact, src/search_algo.hpp:538-604): breadth-first with ordered children = the strings
+//     of the Hamming ball in LEXICOGRAPHIC order; unranked position by position with the ball sizes.
+//   levelOrder = true (FMC search/BacktrackingWithBuffers.h:40-83): a branch is delegated to the exact search as soon
+//     as its error budget is used up, i.e. at the level of its SECOND mismatch: level by level, for every buffered
+//     one-mismatch prefix (they sit in the buffer in lexicographic order) the mismatching symbols in order; what is
+//     left in the buffer at the end -- the strings with at most one mismatch, lexicographically -- comes last.
+__device__ __forceinline__ Cursor seedLeaf2(DevIndex const & ix, Cursor const * E, int K, unsigned char const * red,
+                                            unsigned int seedBegin, unsigned int h1, unsigned int n2, unsigned int A,
+                                            unsigned int idx, bool levelOrder)
+{
+    bool const bs = ix.bsMode != 0;
+    Cursor     none;
+    none.lb  = 0;
+    none.len = 0;
+    int          l1 = -1, l2 = -1; // mismatch levels (l1 < l2), -1 = none
+    unsigned int r1 = 0, r2 = 0;
+    if (!levelOrder)
+    {
+        unsigned int b = 2, i = idx;
+        for (unsigned int pos = 0; pos < n2 && b > 0; ++pos)
+        {
+            unsigned int const m     = n2 - pos - 1;
+            unsigned int const want  = seedSym(red, seedBegin, seedBegin + h1 + pos, bs);
+            unsigned int const sub   = hammingBall(m, b - 1, A); // leaves below one mismatching symbol here
+            unsigned int const below = want * sub;
+            unsigned int       sym   = want;
+            if (i < below)
+            {
+                sym = i / sub;
+                i -= sym * sub;
+            }
+            else
+            {
+                i -= below;
+                unsigned int const exact = hammingBall(m, b, A);
+                if (i >= exact)
+                {
+                    i -= exact;
+                    sym = want + 1 + i / sub;
+                    i %= sub;
+                }
+            }
+            if (sym != want)
+            {
+                if (l1 < 0) { l1 = static_cast<int>(pos); r1 = sym; }
+                else        { l2 = static_cast<int>(pos); r2 = sym; }
+                --b;
+            }
+        }
+    }
+    else
+    {
+        unsigned int const per2  = (A - 1) * (A - 1);
+        unsigned int const nTwo  = n2 * (n2 - 1) / 2 * per2;
+        if (idx < nTwo)
+        {
+            // second mismatch at level i: i * (A-1) one-mismatch prefixes, A-1 symbols each
+            unsigned int i = 1, t = idx;
+            while (t >= i * per2)
+            {
+                t -= i * per2;
+                ++i;
+            }
+            unsigned int const p    = t / (A - 1), k = t % (A - 1);
+            unsigned int const want = seedSym(red, seedBegin, seedBegin + h1 + i, bs);
+            l2                      = static_cast<int>(i);
+            r2                      = k < want ? k : k + 1;
+            seedOneMismatch(red, seedBegin, h1, bs, i, A, p, l1, r1);
+        }
+        else
+        {
+            // at most one mismatch, lexicographically: one-mismatch strings below the seed, the seed, those above
+            unsigned int       t     = idx - nTwo;
+            unsigned int       below = 0;
+            for (unsigned int l = 0; l < n2; ++l)
+                below += seedSym(red, seedBegin, seedBegin + h1 + l, bs);
+            if (t < below)
+                seedOneMismatch(red, seedBegin, h1, bs, n2, A, t, l1, r1);
+            else if (t > below)
+                seedOneMismatch(red, seedBegin, h1, bs, n2, A, t - 1, l1, r1);
+        }
+    }
+    // walk: exact prefix up to the first mismatch comes from the chain
+    int const first = l1 >= 0 ? l1 : static_cast<int>(n2);
+    if (first > K)
+        return none; // the exactly matched prefix does not occur
+    if (l1 < 0)
+        return E[n2];
+    Cursor c = fmExtendRight(ix, E[l1], r1 + 1u);
+    for (unsigned int l = static_cast<unsigned int>(l1) + 1; c.len != 0 && l < n2; ++l)
+    {
+        unsigned int const sym = (static_cast<int>(l) == l2) ? r2 : seedSym(red, seedBegin, seedBegin + h1 + l, bs);
+        c                      = fmExtendRight(ix, c, sym + 1u);
+    }
+    return c;
+}
+
 // seedLooksPromising (src/search_algo.hpp:427-481): ungapped running-maximum score on the seed diagonal
 // over max(seedLength * preScoring, seedLen) residues centred on the seed, clipped to both sequences.
 __device__ __forceinline__ bool seedPreScore(SeedParams const & P, signed char const * sM, unsigned char const * trans,
@@ -1457,14 +1607,16 @@ __global__ void __launch_bounds__(128) seedWarpKernel(SeedParams P)
                     continue;
                 int const          kMax     = (K < static_cast<int>(n2) - 1) ? K : static_cast<int>(n2) - 1;
                 bool const         hasExact = (K == static_cast<int>(n2));
-                unsigned int const nLeaves  = static_cast<unsigned int>(kMax + 1) * (redN - 1) + (hasExact ? 1u : 0u);
+                unsigned int const nLeaves  = P.maxSeedDist >= 2 ? seedNumLeaves2(n2, redN, P.fullHamming != 0)
+                                                                  : static_cast<unsigned int>(kMax + 1) * (redN - 1) + (hasExact ? 1u : 0u);
                 for (unsigned int base = 0; base < nLeaves; base += 32)
                 {
                     Cursor mine;
                     mine.lb  = 0;
                     mine.len = 0;
                     if (base + lane < nLeaves)
-                        mine = seedLeaf(ix, E, red, seedBegin, h1, n2, kMax, hasExact, redN, base + lane, P.fullHamming != 0);
+                        mine = P.maxSeedDist >= 2 ? seedLeaf2(ix, E, K, red, seedBegin, h1, n2, redN, base + lane, P.fullHamming != 0)
+                                                      : seedLeaf(ix, E, red, seedBegin, h1, n2, kMax, hasExact, redN, base + lane, P.fullHamming != 0);
                     unsigned int live = __ballot_sync(0xffffffffu, mine.len != 0);
                     while (live)
                     {
@@ -1494,10 +1646,12 @@ __global__ void __launch_bounds__(128) seedWarpKernel(SeedParams P)
 // mismatch tree are evaluated 32 at a time and handed to seedConsumeChunkSpec in leaf order.
 constexpr int kSpecWarps = 4;
 
-// 5 resident blocks (20 warps) per SM: caps the kernel at 96 registers -- what it used before the 'N' handling was added
-// to every symbol read (116 without the bound = one block less per SM); no spills either way (ptxas -v)
+// Resident blocks per SM: the kernel is bound by the latency of dependent random reads, so warps in flight count more
+// than registers.  8 blocks (32 warps, 64 registers, ~0.5 KB of spills that stay in L1) measured 17.6 / 18.0 ms of
+// seeding on searchn / searchbs against 20.1 / 20.1 ms with 6 blocks (80 registers) and 23.0 / 23.0 ms with 5 blocks
+// (96 registers, no spills) -- profiles/r2_spec_occupancy_ab.json.
 #ifndef LGPU_SPEC_MINBLOCKS
-#define LGPU_SPEC_MINBLOCKS 5
+#define LGPU_SPEC_MINBLOCKS 8
 #endif
 __global__ void __launch_bounds__(32 * kSpecWarps, LGPU_SPEC_MINBLOCKS) seedSpecKernel(SeedParams P)
 {
@@ -1608,14 +1762,16 @@ __global__ void __launch_bounds__(32 * kSpecWarps, LGPU_SPEC_MINBLOCKS) seedSpec
                         continue;
                     int const          kMax     = (K < static_cast<int>(n2) - 1) ? K : static_cast<int>(n2) - 1;
                     bool const         hasExact = (K == static_cast<int>(n2));
-                    unsigned int const nLeaves  = static_cast<unsigned int>(kMax + 1) * (redN - 1) + (hasExact ? 1u : 0u);
+                    unsigned int const nLeaves  = P.maxSeedDist >= 2 ? seedNumLeaves2(n2, redN, P.fullHamming != 0)
+                                                                  : static_cast<unsigned int>(kMax + 1) * (redN - 1) + (hasExact ? 1u : 0u);
                     for (unsigned int base = 0; base < nLeaves; base += 32)
                     {
                         Cursor mine;
                         mine.lb  = 0;
                         mine.len = 0;
                         if (base + lane < nLeaves)
-                            mine = seedLeaf(ix, E, red, seedBegin, h1, n2, kMax, hasExact, redN, base + lane, P.fullHamming != 0);
+                            mine = P.maxSeedDist >= 2 ? seedLeaf2(ix, E, K, red, seedBegin, h1, n2, redN, base + lane, P.fullHamming != 0)
+                                                      : seedLeaf(ix, E, red, seedBegin, h1, n2, kMax, hasExact, redN, base + lane, P.fullHamming != 0);
                         __syncwarp();
                         seedConsumeChunkSpec(P, sM, S, lane, q, qb, origLen, needlesSum, mine, f, seedBegin, needlesPos,
                                              hitsThisSeq, nAfter, nFailed);
@@ -1716,14 +1872,16 @@ __global__ void __launch_bounds__(32 * kSeedBlockWarps) seedBlockKernel(SeedPara
         {
             int const          kMax     = (K < static_cast<int>(n2) - 1) ? K : static_cast<int>(n2) - 1;
             bool const         hasExact = (K == static_cast<int>(n2));
-            unsigned int const nLeaves  = static_cast<unsigned int>(kMax + 1) * (redN - 1) + (hasExact ? 1u : 0u);
+            unsigned int const nLeaves  = P.maxSeedDist >= 2 ? seedNumLeaves2(n2, redN, P.fullHamming != 0)
+                                                                  : static_cast<unsigned int>(kMax + 1) * (redN - 1) + (hasExact ? 1u : 0u);
             for (unsigned int base = 0; base < nLeaves; base += 32)
             {
                 Cursor mine;
                 mine.lb  = 0;
                 mine.len = 0;
                 if (base + lane < nLeaves)
-                    mine = seedLeaf(ix, E, red, seedBegin, h1, n2, kMax, hasExact, redN, base + lane, P.fullHamming != 0);
+                    mine = P.maxSeedDist >= 2 ? seedLeaf2(ix, E, K, red, seedBegin, h1, n2, redN, base + lane, P.fullHamming != 0)
+                                                      : seedLeaf(ix, E, red, seedBegin, h1, n2, kMax, hasExact, redN, base + lane, P.fullHamming != 0);
                 unsigned int const live = __ballot_sync(0xffffffffu, mine.len != 0);
                 if (mine.len != 0)
                     myCur[static_cast<unsigned long long>(k) * S.maxLeaves + out + __popc(live & ((1u << lane) - 1u))] = mine;

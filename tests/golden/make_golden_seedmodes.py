@@ -2,7 +2,8 @@
 """Golden outputs of the unmodified reference for the seed-search variants outside its profiles
 (src/search_algo.hpp:484-494 -> FMC search/BacktrackingWithBuffers.h): Hamming distance over the WHOLE seed,
   <case>/nohalf.m8        --seed-half-exact 0                       (phase 2: 11-mers, one mismatch anywhere)
-  <case>/nohalf_d2.m8     --seed-half-exact 0 --seed-delta 2        (CPU oracle only; the GPU path rejects delta > 1)
+  <case>/nohalf_d2.m8     --seed-half-exact 0 --seed-delta 2        (two mismatches anywhere)
+  <case>/half_d2.m8       --seed-delta 2                            (half-exact seeds, two mismatches in the second half)
 plus the funnel counters, for the committed fixtures of two cases."""
 import gzip
 import json
@@ -22,7 +23,8 @@ for case, cmd in (("prot_diverged", "searchp"), ("nucl", "searchn")):
         with gzip.open(os.path.join(src, "db.lba.gz"), "rb") as fi, open(os.path.join(tmp, "db.lba"), "wb") as fo:
             shutil.copyfileobj(fi, fo)
         for name, extra in (("nohalf", ["--seed-half-exact", "0"]),
-                            ("nohalf_d2", ["--seed-half-exact", "0", "--seed-delta", "2"])):
+                            ("nohalf_d2", ["--seed-half-exact", "0", "--seed-delta", "2"]),
+                            ("half_d2", ["--seed-delta", "2"])):
             if case == "nucl" and name == "nohalf_d2":
                 continue
             out = os.path.join(tmp, name + ".m8")

@@ -105,9 +105,40 @@ def test_full_seed_hamming_search(golden_dir, case, domain, mode, monkeypatch):
     assert sorted(s.m8(hits, ids)) == sorted(ref)
     for k in FUNNEL:
         assert int(st[k]) == funnel[k], k
-    # two mismatches are not implemented on the device: refused, not approximated
+    # three mismatches are not implemented on the device: refused, not approximated
     with pytest.raises(lambda_b200.LambdaError):
-        lambda_b200.Searcher(ix, domain, "none", seed_half_exact=0, opts=(11, 2, 3))
+        lambda_b200.Searcher(ix, domain, "none", seed_half_exact=0, opts=(11, 3, 3))
+    s.close(); ix.close(); o.close()
+
+
+@pytest.mark.parametrize("mode", ["auto", "warp", "block", "spec"])
+@pytest.mark.parametrize("case,domain,half,name", [("prot_diverged", 0, 0, "nohalf_d2"), ("prot_diverged", 0, 1, "half_d2"),
+                                                   ("nucl", 1, 1, "half_d2"), ("nucl", 1, 0, None)])
+def test_two_mismatch_seeds(golden_dir, case, domain, half, name, mode, monkeypatch):
+    """--seed-delta 2 on the device: the leaves of the two-mismatch search tree in the reference's production order,
+    for half-exact seeds (breadth-first = lexicographic) and for Hamming distance over the whole seed (level order of
+    search_backtracking_with_buffers); seeding against the oracle, the whole search against the reference's files"""
+    monkeypatch.setenv("LAMBDA_B200_SEED", mode)
+    path, ids, res, offs = _load(golden_dir, case, domain)
+    o = orc.Oracle(path)
+    ix = lambda_b200.Index.load(path)
+    L, off = (11, 3) if domain == 0 else (14, 7)
+    s, p = _pair(ix, o, case, domain, seed_half_exact=half, opts=(L, 2, off))
+    p.opts.seed_length, p.opts.max_seed_dist, p.opts.seed_offset = L, 2, off
+    m_gpu, st_gpu = s.seed(res, offs, 2)
+    m_cpu, st_cpu = o.seed(p, res, offs, 2)
+    assert len(m_gpu) == len(m_cpu) and (_sorted(m_gpu) == _sorted(m_cpu)).all()
+    for k in ("hits_after_seeding", "hits_failed_pre_extend"):
+        assert int(st_gpu[k]) == int(st_cpu[k]), k
+    hits, st = s.search(res, offs)
+    if name is not None:
+        ref, funnel = load_golden(golden_dir, case, name)
+        assert sorted(s.m8(hits, ids)) == sorted(ref)
+        for k in FUNNEL:
+            assert int(st[k]) == funnel[k], k
+    else:
+        h_cpu, st_cpu = o.search(p, res, offs)
+        assert sorted(s.m8(hits, ids)) == sorted(o.m8(p, h_cpu, ids))
     s.close(); ix.close(); o.close()
 
 

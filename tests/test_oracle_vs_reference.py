@@ -30,7 +30,9 @@ def test_oracle_reproduces_reference(golden_dir, case, domain, profile):
 
 @pytest.mark.parametrize("case,domain,name,kw", [("prot_diverged", 0, "nohalf", dict(seed_half_exact=0)),
                                                  ("prot_diverged", 0, "nohalf_d2", dict(seed_half_exact=0, delta=2)),
-                                                 ("nucl", 1, "nohalf", dict(seed_half_exact=0))])
+                                                 ("nucl", 1, "nohalf", dict(seed_half_exact=0)),
+                                                 ("prot_diverged", 0, "half_d2", dict(seed_half_exact=1, delta=2)),
+                                                 ("nucl", 1, "half_d2", dict(seed_half_exact=1, delta=2))])
 def test_oracle_reproduces_reference_seed_variants(golden_dir, case, domain, name, kw):
     """Hamming distance over the whole seed (search_backtracking_with_buffers), delta 1 and 2"""
     o = orc.Oracle(os.path.join(golden_dir, case, "db.lba"))
