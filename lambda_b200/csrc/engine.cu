@@ -402,6 +402,13 @@ struct lgpu_ctx
     };
     std::vector<ExportPart>    lastParts; // where the records of the last lgpu_search_batch live (lgpu_ctx_export_hits)
 
+    // side streams for the per-class launches of the DP passes (classStream / joinClassStreams)
+    static constexpr int kAux = 3;
+    cudaStream_t         aux[kAux]{};
+    cudaEvent_t          auxDone[kAux]{};
+    unsigned int         auxUsed      = 0;
+    bool                 classStreams = true; // LAMBDA_B200_CLASS_STREAMS=0: every class on the context's stream
+
     // stage timers: event pairs recorded on the stream, read once at the end of the call
     struct TimerSlot
     {
@@ -438,6 +445,13 @@ struct lgpu_ctx
         for (auto & e : ev)
             if (e)
                 cudaEventDestroy(e);
+        for (int i = 0; i < kAux; ++i)
+        {
+            if (auxDone[i])
+                cudaEventDestroy(auxDone[i]);
+            if (aux[i])
+                cudaStreamDestroy(aux[i]);
+        }
         for (auto & t : timers)
         {
             if (t.a)
@@ -875,8 +889,8 @@ static uint64_t runMerge(lgpu_ctx & c, lgpu_match const * dIn, uint64_t n, lgpu_
 {
     if (n == 0)
         return 0;
-    if (n >= (1ull << 32))
-        throw CudaError("more than 2^32 seed matches in one batch; use smaller query batches");
+    if (n >= (1ull << 31)) // the CUB primitives below take int item counts
+        throw ArgError("more than 2^31 seed matches in one batch; use smaller query batches");
     StageTimer t(c, st ? &st->ms_sort_merge : nullptr);
     c.dKey1.reserve(n);
     c.dKey2.reserve(n);
@@ -991,7 +1005,7 @@ static ExtParams baseExtParams(lgpu_ctx & c, lgpu_match const * dTasks, unsigned
 }
 
 template <int T, int K, bool PRIV, bool TRACE>
-static void launchDpx(lgpu_ctx & c, DpxParams P, unsigned int maxNt)
+static void launchDpx(lgpu_ctx & c, DpxParams P, unsigned int maxNt, cudaStream_t stream)
 {
     P.winCap          = (maxNt + 4 * T + 127) / 128 * 128;
     size_t const smem = dpxSmemBytes(T, K, PRIV, P.nCodes, P.winCap);
@@ -1000,7 +1014,7 @@ static void launchDpx(lgpu_ctx & c, DpxParams P, unsigned int maxNt)
     LGPU_CUDA(cudaFuncSetAttribute(swDpxKernel<T, K, PRIV, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     unsigned int const perSM = TRACE ? 32u : c.dpxBlocksPerSM;
     unsigned int const grid  = std::min<unsigned int>(P.nJobs, static_cast<unsigned int>(c.numSMs) * perSM);
-    swDpxKernel<T, K, PRIV, TRACE><<<grid, 32, smem, c.stream>>>(P);
+    swDpxKernel<T, K, PRIV, TRACE><<<grid, 32, smem, stream>>>(P);
     LGPU_CUDA(cudaGetLastError());
 }
 
@@ -1009,7 +1023,7 @@ struct MaxOp
     __host__ __device__ unsigned int operator()(unsigned int a, unsigned int b) const { return a > b ? a : b; }
 };
 
-using DpxLaunchFn = void (*)(lgpu_ctx &, DpxParams, unsigned int);
+using DpxLaunchFn = void (*)(lgpu_ctx &, DpxParams, unsigned int, cudaStream_t);
 #define LGPU_DPX_LAUNCH_SHARED(T, K) &launchDpx<T, K, false, false>,
 #define LGPU_DPX_LAUNCH_PRIV(T, K) &launchDpx<T, K, true, false>,
 #define LGPU_DPX_LAUNCH_TRACE(T, K) &launchDpx<T, K, true, true>,
@@ -1021,7 +1035,39 @@ static DpxLaunchFn const kDpxLaunchTrace32[kNumDpxTr32Classes] = {LGPU_DPX_TRACE
 #undef LGPU_DPX_LAUNCH_PRIV
 #undef LGPU_DPX_LAUNCH_TRACE
 
-constexpr int kClsSlots = kMaxDpxClasses + 1; // per-class arrays: the packed classes of a table + the scalar class
+constexpr int kClsSlots = kMaxDpxClasses + 1;
+
+// The (T, K) classes of a pass are independent launches.  With many classes of few alignments each (real length
+// distributions: 31 classes for 164 k alignments) one launch after the other leaves most SMs idle at the tail of
+// every class, so the classes go round-robin onto a few side streams: callers launch after the host has waited for
+// the context's stream (all inputs are ready) and call joinClassStreams() before anything that consumes the results.
+static cudaStream_t classStream(lgpu_ctx & c, unsigned int k, unsigned int nClasses)
+{
+    if (nClasses < 3 || !c.classStreams)
+        return c.stream;
+    if (!c.aux[0])
+        for (int i = 0; i < lgpu_ctx::kAux; ++i)
+        {
+            LGPU_CUDA(cudaStreamCreateWithFlags(&c.aux[i], cudaStreamNonBlocking));
+            LGPU_CUDA(cudaEventCreateWithFlags(&c.auxDone[i], cudaEventDisableTiming));
+        }
+    unsigned int const slot = k % (lgpu_ctx::kAux + 1);
+    if (slot == 0)
+        return c.stream;
+    c.auxUsed |= 1u << (slot - 1);
+    return c.aux[slot - 1];
+}
+
+static void joinClassStreams(lgpu_ctx & c)
+{
+    for (int i = 0; i < lgpu_ctx::kAux; ++i)
+        if (c.auxUsed & (1u << i))
+        {
+            LGPU_CUDA(cudaEventRecord(c.auxDone[i], c.aux[i]));
+            LGPU_CUDA(cudaStreamWaitEvent(c.stream, c.auxDone[i], 0));
+        }
+    c.auxUsed = 0;
+} // per-class arrays: the packed classes of a table + the scalar class
 
 static DpxParams baseDpxParams(lgpu_ctx & c, lgpu_match const * dTasks, unsigned int n)
 {
@@ -1046,6 +1092,8 @@ static void runScorePass(lgpu_ctx & c, lgpu_match const * dTasks, unsigned int n
 {
     if (n == 0)
         return;
+    if (n >= (1u << 31))
+        throw ArgError("more than 2^31 alignments in one batch; use smaller query batches");
     StageTimer t(c, st ? &st->ms_extend_score : nullptr);
     bool const priv = c.privProfiles;
     int const  tab  = priv ? kDpxTabPriv : kDpxTabShared;
@@ -1099,13 +1147,16 @@ static void runScorePass(lgpu_ctx & c, lgpu_match const * dTasks, unsigned int n
     LGPU_CUDA(cudaMemcpyAsync(info, c.dClassInfo.p, sizeof(info), cudaMemcpyDeviceToHost, c.stream));
     LGPU_CUDA(cudaMemcpyAsync(&cells, c.dCounters.p, 8, cudaMemcpyDeviceToHost, c.stream));
     syncStream(c);
-    unsigned int taskOff = 0, jobOff = 0;
+    unsigned int taskOff = 0, jobOff = 0, nNonEmpty = 0, kLaunch = 0;
+    for (int cls = 0; cls <= NP; ++cls)
+        nNonEmpty += info[cls] ? 1u : 0u;
     for (int cls = 0; cls <= NP; ++cls)
     {
         unsigned int const cnt = info[cls], maxNt = info[NC + cls];
         if (cnt == 0)
             continue;
         bool const         scalar = (cls == NP) || !c.dpxScoreOk;
+        cudaStream_t const cs     = scalar ? c.stream : classStream(c, kLaunch++, nNonEmpty);
         unsigned int const nJobs  = priv ? (cnt + dpxGroupsOf(tab, cls) - 1) / dpxGroupsOf(tab, cls) : info[2 * NC + cls];
         if (!scalar)
         {
@@ -1118,7 +1169,7 @@ static void runScorePass(lgpu_ctx & c, lgpu_match const * dTasks, unsigned int n
             P.nSlots      = cnt;
             P.workCounter = c.dWork.p + cls;
             P.scores      = dScores;
-            (priv ? kDpxLaunchPriv[cls] : kDpxLaunchShared[cls])(c, P, maxNt);
+            (priv ? kDpxLaunchPriv[cls] : kDpxLaunchShared[cls])(c, P, maxNt, cs);
         }
         else
         {
@@ -1138,6 +1189,7 @@ static void runScorePass(lgpu_ctx & c, lgpu_match const * dTasks, unsigned int n
         taskOff += cnt;
         jobOff += priv ? 0u : nJobs;
     }
+    joinClassStreams(c);
     if (st)
     {
         st->kernel_launches += launches;
@@ -1271,6 +1323,8 @@ static void runTracePass(lgpu_ctx & c, lgpu_match const * dTasks, unsigned int n
 {
     if (n == 0)
         return;
+    if (n >= (1u << 31))
+        throw ArgError("more than 2^31 alignments in one batch; use smaller query batches");
     StageTimer t(c, st ? &st->ms_extend_trace : nullptr);
     c.dHits.reserve(n);
     c.dWork.reserve(kClsSlots + 2);
@@ -1366,16 +1420,23 @@ static void runTracePass(lgpu_ctx & c, lgpu_match const * dTasks, unsigned int n
             }
         }
     }
+    unsigned int nNonEmpty = 0;
+    for (int cls = 0; cls < NP; ++cls)
+        nNonEmpty += info[cls] ? 1u : 0u;
     for (Group const & gr : groups)
     {
         c.dPlanes.reserve(gr.words);
+        unsigned int kLaunch = 0;
         for (int cls = 0; cls < NP; ++cls)
         {
             unsigned int const lo = std::max(classStart[cls], gr.b), hi = std::min(classStart[cls + 1], gr.e);
             if (lo >= hi)
                 continue;
             unsigned int const G = dpxGroupsOf(tab, cls);
-            LGPU_CUDA(cudaMemsetAsync(c.dWork.p + cls, 0, 4, c.stream));
+            // one launch group: the host has just waited for the stream, so the classes may fan out over side streams;
+            // several groups reuse the plane buffer one after the other and stay on the context's stream
+            cudaStream_t const cs = groups.size() == 1 ? classStream(c, kLaunch++, nNonEmpty) : c.stream;
+            LGPU_CUDA(cudaMemsetAsync(c.dWork.p + cls, 0, 4, cs));
             DpxParams P    = baseDpxParams(c, dTasks, n);
             P.order        = c.dOrderB.p;
             P.keys         = c.dClassKeysB.p;
@@ -1388,10 +1449,11 @@ static void runTracePass(lgpu_ctx & c, lgpu_match const * dTasks, unsigned int n
             P.planeOff     = c.dTraceOff.p;
             P.planeOffBase = gr.base;
             P.bestCol      = c.dBestPos.p;
-            (tab == kDpxTabPriv ? kDpxLaunchPrivTr[cls] : kDpxLaunchTrace32[cls])(c, P, info[NC + cls]);
+            (tab == kDpxTabPriv ? kDpxLaunchPrivTr[cls] : kDpxLaunchTrace32[cls])(c, P, info[NC + cls], cs);
             if (st)
                 st->kernel_launches += 1;
         }
+        joinClassStreams(c);
         TracebackResParams TP{};
         TP.ix           = c.index->dev;
         TP.Q            = c.Q;
@@ -2043,6 +2105,8 @@ static std::unique_ptr<lgpu_ctx> lgpu::makeContext(lgpu_index const * ix, lgpu_p
     LGPU_CUDA(cudaMemset(c->dOverflow.p, 0, 4));
     if (char const * e = std::getenv("LAMBDA_B200_SEED"))
         c->seedMode = !std::strcmp(e, "thread") ? 1 : !std::strcmp(e, "warp") ? 2 : !std::strcmp(e, "block") ? 3 : !std::strcmp(e, "spec") ? 4 : 0;
+    if (char const * e = std::getenv("LAMBDA_B200_CLASS_STREAMS"))
+        c->classStreams = std::atoi(e) != 0;
     if (char const * e = std::getenv("LAMBDA_B200_SEED_TEXT"))
         c->seedTextElong = std::atoi(e) != 0;
     if (char const * e = std::getenv("LAMBDA_B200_SEED_PREFIX"))
@@ -2532,6 +2596,8 @@ int lgpu_extend_scores(lgpu_ctx * c, lgpu_query_batch const * q, lgpu_match cons
             std::vector<uint64_t> offsTmp;
             uploadQueries(*c, viewOf(*c, *q, offsTmp), stats);
         }
+        if (n >= (1ull << 31))
+            throw ArgError("more than 2^31 windows in one call");
         if (n == 0)
             return;
         checkWindows(*c, win, n);
@@ -2558,6 +2624,8 @@ int lgpu_extend_trace(lgpu_ctx * c, lgpu_query_batch const * q, lgpu_match const
             std::vector<uint64_t> offsTmp;
             uploadQueries(*c, viewOf(*c, *q, offsTmp), stats);
         }
+        if (n >= (1ull << 31))
+            throw ArgError("more than 2^31 windows in one call");
         if (n == 0)
             return;
         checkWindows(*c, win, n);

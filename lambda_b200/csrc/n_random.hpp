@@ -12,7 +12,7 @@
 //   * every elongation step reads ONE symbol from a fresh instance (`redQrySeqs[i][seedBegin + seedLength]`,
 //     :708): an 'N' there is always kNRandom(0) = C.
 // Pre-scoring and the DP use the unreduced query, where 'N' stays 'N'.
-// The table below is the first 64 outputs of std::mt19937{0xDEADBEEF} % 4 (generated with libstdc++; mt19937 is
+// The table below is the first 256 outputs of std::mt19937{0xDEADBEEF} % 4 (generated with libstdc++; mt19937 is
 // fully specified by the C++ standard), packed two bits each.  Shared by the CUDA kernels and the CPU oracle.
 #pragma once
 
@@ -32,9 +32,11 @@ constexpr unsigned int kNMarker = 0x80u; // reduced-query byte of an 'N': kNMark
 // dna4 rank (A=0 C=1 G=2 T=3) of the k-th 'N' read through one view instance
 LGPU_HD inline unsigned int nRandomRank(unsigned int k)
 {
-    unsigned long long const lo = 0xa3736c5835666461ull, hi = 0xf83739b5e56c0330ull;
-    k &= 63u; // seeds are far shorter than 64 symbols
-    return static_cast<unsigned int>(((k < 32u ? lo : hi) >> (2u * (k & 31u))) & 3ull);
+    // 256 outputs, 32 per word (numpy: MT19937()._legacy_seeding(0xDEADBEEF).random_raw(256) % 4 gives the same)
+    unsigned long long const t[8] = {0xa3736c5835666461ull, 0xf83739b5e56c0330ull, 0x8a0d496c4d639a57ull, 0x6a968fce7c214217ull,
+                                     0x2c7b0190e28dee09ull, 0x7d47edbd2d3f94deull, 0xee9d805c62b94c97ull, 0x4e7974c9cd6db936ull};
+    k &= 255u; // a seed search reads far fewer symbols than that
+    return static_cast<unsigned int>((t[k >> 5] >> (2u * (k & 31u))) & 3ull);
 }
 
 // reduced-alphabet rank of a randomised 'N': dna4 itself, or the bisulfite reduction of the frame's direction
