@@ -224,6 +224,8 @@ static void runUploads(std::vector<UploadJob> const & jobs, int device)
     if (char const * e = std::getenv("LAMBDA_B200_UPLOAD_THREADS"))
         nThreads = static_cast<unsigned int>(std::max(1, std::min(32, std::atoi(e))));
     nThreads = static_cast<unsigned int>(std::min<size_t>(nThreads, pieces.size()));
+    char const * const um           = std::getenv("LAMBDA_B200_UPLOAD_MODE");
+    bool const         registerMode = um && !std::strcmp(um, "register");
     std::atomic<size_t>      next{0};
     std::vector<std::string> err(nThreads);
     std::vector<std::thread> th;
@@ -252,6 +254,22 @@ static void runUploads(std::vector<UploadJob> const & jobs, int device)
                         LGPU_CUDA(cudaEventSynchronize(ev[b]));
                     Piece const & pc   = pieces[i];
                     bool          done = false;
+                    if (registerMode && pc.fd >= 0)
+                    {
+                        // experiment (LAMBDA_B200_UPLOAD_MODE=register): pin the mapped pages themselves and let the copy
+                        // engine read the page cache directly -- no host-side copy at all
+                        void * const src = const_cast<unsigned char *>(pc.src);
+                        if (cudaHostRegister(src, pc.bytes, cudaHostRegisterReadOnly) == cudaSuccess)
+                        {
+                            cudaError_t const e1 = cudaMemcpyAsync(pc.dst, src, pc.bytes, cudaMemcpyHostToDevice, st);
+                            cudaError_t const e2 = cudaStreamSynchronize(st);
+                            cudaHostUnregister(src);
+                            LGPU_CUDA(e1);
+                            LGPU_CUDA(e2);
+                            continue;
+                        }
+                        cudaGetLastError();
+                    }
                     if (pc.fd >= 0)
                     {
                         size_t got = 0;
