@@ -405,11 +405,13 @@ struct DpxClass
     X(8, 4) X(8, 5) X(8, 6) X(8, 7) X(8, 8) X(8, 9) X(8, 10) X(8, 12) X(8, 14) X(8, 16) X(8, 20) X(8, 24)          \
     X(8, 28) X(8, 32) X(16, 20) X(16, 24) X(16, 28) X(16, 32) X(32, 20) X(32, 24) X(32, 28) X(32, 32)
 
-// Pass 2 of protein searches: one warp per alignment (survivors of the e-value filter are about one per query, so
-// there is no profile to share), 64 strips of K columns
+// Pass 2 of protein searches: survivors of the e-value filter are about one per query, so there is no profile to
+// share and every group builds its own (28 rows: 10.8 KB for 16 x 10 columns).  Two alignments per warp (T = 16) up to
+// 1024 columns: a 31-step ramp instead of 63 and twice the cell pairs per step to spread the per-step overhead over
+// (loads, shuffles, stores) compared with one warp per alignment, which remains for the long queries.
 #define LGPU_DPX_TRACE32_CLASSES(X)                                                                                \
-    X(32, 1) X(32, 2) X(32, 3) X(32, 4) X(32, 5) X(32, 6) X(32, 8) X(32, 10) X(32, 12) X(32, 16) X(32, 20)         \
-    X(32, 24) X(32, 28) X(32, 32)
+    X(16, 2) X(16, 3) X(16, 4) X(16, 5) X(16, 6) X(16, 7) X(16, 8) X(16, 9) X(16, 10) X(16, 11) X(16, 12)          \
+    X(16, 14) X(16, 16) X(16, 20) X(16, 24) X(16, 28) X(16, 32) X(32, 20) X(32, 24) X(32, 28) X(32, 32)
 
 #define LGPU_DPX_CLASS_ENTRY(T, K) {T, K},
 #define LGPU_DPX_CLASS_COUNT(T, K) +1
@@ -420,7 +422,7 @@ constexpr int kMaxDpxClasses     = kNumDpxClasses; // the longest table
 static_assert(kNumDpxClasses < 63 && kNumDpxPrivClasses <= kMaxDpxClasses && kNumDpxTr32Classes <= kMaxDpxClasses,
               "class id must fit the sort key / the per-class arrays");
 
-// class tables: 0 = shared-profile score classes, 1 = private-profile classes, 2 = one-warp trace classes
+// class tables: 0 = shared-profile score classes, 1 = private-profile classes, 2 = pass-2 classes of protein searches
 enum { kDpxTabShared = 0, kDpxTabPriv = 1, kDpxTabTrace32 = 2 };
 __host__ __device__ inline int dpxNumClasses(int tab)
 {

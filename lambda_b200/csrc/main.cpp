@@ -11,6 +11,7 @@
 // that batch's phase-2 hits (src/search.cpp:449-457).  We reproduce exactly that order, so the file is
 // byte-identical to `lambda3 search* -t 1`, not merely equal as a multiset.
 #include <algorithm>
+#include <atomic>
 #include <cctype>
 #include <chrono>
 #include <cstdio>
@@ -812,8 +813,50 @@ static int run(int argc, char ** argv)
     };
     // one tabular line: the library formats the ordinary columns, the taxonomy columns are filled in here
     // (SQ/blast/blast_tabular_out.h:440-492)
+    // Lines without taxonomy columns depend on nothing but their record: they are formatted up front by several threads
+    // (the formatter is as long as the search on the benchmark workload), the writer below only copies them out.
+    bool plainColumns = !o.sam && !o.report;
+    for (uint32_t c : o.columns)
+        plainColumns = plainColumns && lgpu_tabular_column_supported(c);
+    std::vector<std::vector<std::string>> preLines(res.size());
+    if (plainColumns)
+    {
+        unsigned int const nFmt = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+        for (size_t g = 0; g < res.size(); ++g)
+        {
+            preLines[g].resize(res[g].hits.size());
+            std::vector<std::thread> ft;
+            std::atomic<bool>        failed{false};
+            for (unsigned int t = 0; t < nFmt; ++t)
+                ft.emplace_back([&, g, t] {
+                    std::vector<char> buf(1 << 16);
+                    size_t const      n = res[g].hits.size(), b = n * t / nFmt, e = n * (t + 1) / nFmt;
+                    for (size_t i = b; i < e; ++i)
+                    {
+                        lgpu_hit const &  h   = res[g].hits[i];
+                        std::string const sId = subjectId(h.s_id);
+                        int const len = lgpu_format_tabular(&o.params, &h, f.ids[h.q_id].c_str(), sId.c_str(), o.columns.data(),
+                                                            o.columns.size(), buf.data(), buf.size());
+                        if (len <= 0)
+                        {
+                            failed = true;
+                            return;
+                        }
+                        preLines[g][i].assign(buf.data(), static_cast<size_t>(len));
+                    }
+                });
+            for (auto & t : ft)
+                t.join();
+            if (failed)
+                die("cannot format a tabular line");
+        }
+    }
     std::string tabLine;
     auto        tabularLine = [&](uint64_t q, lgpu_hit const * h) -> std::string const & {
+        if (plainColumns)
+            for (size_t g = 0; g < res.size(); ++g)
+                if (!res[g].hits.empty() && h >= res[g].hits.data() && h < res[g].hits.data() + res[g].hits.size())
+                    return preLines[g][static_cast<size_t>(h - res[g].hits.data())];
         tabLine.clear();
         std::string const sId = subjectId(h->s_id);
         auto isTax = [](uint32_t c) { return !lgpu_tabular_column_supported(c); };
