@@ -405,13 +405,13 @@ struct DpxClass
     X(8, 4) X(8, 5) X(8, 6) X(8, 7) X(8, 8) X(8, 9) X(8, 10) X(8, 12) X(8, 14) X(8, 16) X(8, 20) X(8, 24)          \
     X(8, 28) X(8, 32) X(16, 20) X(16, 24) X(16, 28) X(16, 32) X(32, 20) X(32, 24) X(32, 28) X(32, 32)
 
-// Pass 2 of protein searches: survivors of the e-value filter are about one per query, so there is no profile to
-// share and every group builds its own (28 rows: 10.8 KB for 16 x 10 columns).  Two alignments per warp (T = 16) up to
-// 1024 columns: a 31-step ramp instead of 63 and twice the cell pairs per step to spread the per-step overhead over
-// (loads, shuffles, stores) compared with one warp per alignment, which remains for the long queries.
+// Pass 2 of protein searches: one warp per alignment (survivors of the e-value filter are about one per query, so
+// there is no profile to share), 64 strips of K columns.  Tried: two alignments per warp (T = 16, K = 2 .. 32: 31-step
+// ramp, twice the cell pairs per step) -- no faster on the 300-aa benchmark (trace stage 7.05 vs 7.03 ms) and slower on
+// the real length distribution (2.69 vs 2.26 ms): two 10.8 KB profiles per warp cost more than the shorter ramp saves.
 #define LGPU_DPX_TRACE32_CLASSES(X)                                                                                \
-    X(16, 2) X(16, 3) X(16, 4) X(16, 5) X(16, 6) X(16, 7) X(16, 8) X(16, 9) X(16, 10) X(16, 11) X(16, 12)          \
-    X(16, 14) X(16, 16) X(16, 20) X(16, 24) X(16, 28) X(16, 32) X(32, 20) X(32, 24) X(32, 28) X(32, 32)
+    X(32, 1) X(32, 2) X(32, 3) X(32, 4) X(32, 5) X(32, 6) X(32, 8) X(32, 10) X(32, 12) X(32, 16) X(32, 20)         \
+    X(32, 24) X(32, 28) X(32, 32)
 
 #define LGPU_DPX_CLASS_ENTRY(T, K) {T, K},
 #define LGPU_DPX_CLASS_COUNT(T, K) +1
