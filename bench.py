@@ -361,7 +361,8 @@ def main():
            "queries_total": args.n_queries if strong else args.n_queries * n_gpus,
            "query_len": args.qlen, "index_seqs": args.n_seqs,
            "profile": "none", "sharding": (f"one batch of {args.n_queries} queries split over {n_gpus} ranks" if strong else
-                                           f"queries x{n_gpus}") + ", index replicated", "streams_per_gpu": 3,
+                                           f"queries x{n_gpus}") + ", index replicated",
+           "streams_per_gpu": "library default: 1 sub-batch in flight for protein searches, 4 for nucleotide / bisulfite",
            "l2_policy": "inputs larger than L2 (index and per-step trace/DP working sets are GBs)",
            "window_band": args.band if args.band else "reference rule floor(sqrt(qlen))+1"}
     cores = os.cpu_count() or 1
@@ -410,7 +411,7 @@ def main():
     ix.subject_ids = _SyntheticIds()
     log(f"rank {rank}: index in HBM: {ix.device_bytes / 1e9:.2f} GB, load {time.time() - t0:.1f}s")
     kw = {"window_band": args.band} if args.band else {}
-    s = lambda_b200.Searcher(ix, W["domain"], **kw)              # default: 3 sub-batches in flight
+    s = lambda_b200.Searcher(ix, W["domain"], **kw)              # default number of sub-batches in flight
     s_serial = lambda_b200.Searcher(ix, W["domain"], streams=1, **kw)  # strictly serial: per-kernel timing / roofline
     if strong:
         # ONE batch for the whole job (the same on every rank); this rank searches its contiguous shard

@@ -198,9 +198,10 @@ typedef struct lgpu_ctx lgpu_ctx;
 int          lgpu_ctx_create(lgpu_ctx ** out, lgpu_index const *, lgpu_params const *);
 void         lgpu_ctx_destroy(lgpu_ctx *);
 /* Number of sub-batches a large lgpu_search_batch() call is cut into; each runs the whole pipeline on
- * its own CUDA stream + host thread so that host-only and latency-bound stretches overlap with the DP
- * kernels of the others (default 3, env LAMBDA_B200_STREAMS; 1 = strictly serial, used for per-kernel
- * timing; calls with fewer than ~32k queries are not cut).  Results do not depend on it. */
+ * its own CUDA stream + host thread so that host-only and latency-bound stretches overlap with the
+ * kernels of the others (default: 1 for protein searches, whose host part is under a millisecond now that the
+ * records are finalised on the device, 4 for nucleotide / bisulfite searches; env LAMBDA_B200_STREAMS; 1 = strictly
+ * serial, used for per-kernel timing; calls with fewer than ~32k queries are not cut).  Results do not depend on it. */
 int          lgpu_ctx_set_streams(lgpu_ctx *, uint32_t n);
 char const * lgpu_last_error(lgpu_ctx const *); /* ctx may be NULL: error of the last failed
                                                    create/open call on this thread */

@@ -2456,8 +2456,11 @@ int lgpu_ctx_create(lgpu_ctx ** out, lgpu_index const * ix, lgpu_params const * 
     *out = nullptr;
     return guarded(nullptr, [&] {
         auto c = makeContext(ix, *p);
-        // sub-batches in flight per search call; worker contexts are created on first use
-        c->streams = 3;
+        // Sub-batches in flight per search call (worker contexts are created on first use).  With the records finalised
+        // on the device the host part of a protein step is under a millisecond and one stream is fastest (searchp
+        // 51.7 ms against 53.8 ms with three); a short-read step still has ~10 ms of host work per million records to
+        // hide (searchn 55.5 ms with four against 61.4 ms with one) -- profiles/r2_sweep_streams.jsonl.
+        c->streams = p->domain == LGPU_DOMAIN_PROTEIN ? 1 : 4;
         if (char const * e = std::getenv("LAMBDA_B200_STREAMS"))
             c->streams = static_cast<unsigned int>(std::max(1, std::min(8, std::atoi(e))));
         if (char const * e = std::getenv("LAMBDA_B200_MIN_SUBBATCH"))

@@ -1547,6 +1547,44 @@ __device__ __forceinline__ bool seedNextStart(unsigned char const * trans, unsig
     return seedBegin <= len - L;
 }
 
+// The same for a whole warp at once (all lanes call it with the same arguments): the "skip this start" test of 32
+// positions is one coalesced load and a ballot, kept in `bits` for the word `word` of the frame (callers reset
+// word = ~0u when the frame changes); finding the next start is then bit arithmetic instead of a loop of dependent
+// byte loads that every lane repeats.
+__device__ __forceinline__ bool seedNextStartWarp(unsigned char const * trans, unsigned int len, unsigned int L,
+                                                  unsigned int unknownRank, unsigned int & seedBegin, unsigned int lane,
+                                                  unsigned int & word, unsigned int & bits)
+{
+    unsigned int const last = len - L; // the last possible start is taken without the test
+    for (;;)
+    {
+        if (seedBegin >= last)
+            return seedBegin <= last;
+        unsigned int const w = seedBegin >> 5;
+        if (w != word)
+        {
+            unsigned int const p    = (w << 5) + lane;
+            bool               skip = false;
+            if (p < last)
+            {
+                unsigned int const a = trans[p];
+                skip                 = a == unknownRank || a == trans[p + 1];
+            }
+            bits = __ballot_sync(0xffffffffu, skip);
+            word = w;
+        }
+        unsigned int const off  = seedBegin & 31u;
+        unsigned int const keep = ~(bits >> off);                 // 1 = a start that is not skipped (bits beyond the word: 1)
+        unsigned int const k    = static_cast<unsigned int>(__ffs(keep)) - 1u; // keep != 0: the shift fills with zeros unless off = 0
+        if (keep != 0 && k < 32u - off)
+        {
+            seedBegin += k;
+            return seedBegin <= last;
+        }
+        seedBegin = (w + 1u) << 5;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // seeding, one WARP per query
 // ---------------------------------------------------------------------------------------------
@@ -1692,6 +1730,7 @@ __global__ void __launch_bounds__(32 * kSpecWarps, LGPU_SPEC_MINBLOCKS) seedSpec
             // borders, so that short reads (9 - 16 seeds per frame) still fill the warp.  Every lane runs the same
             // scan and keeps its own (frame, seed start, needlesPos of that frame).
             unsigned int       f = 0, seedBegin = 0;
+            unsigned int       scanWord = ~0u, scanBits = 0; // cached "skip" bits of 32 start positions (seedNextStartWarp)
             unsigned long long npos = 0;
             bool               more = true;
             while (more)
@@ -1712,14 +1751,16 @@ __global__ void __launch_bounds__(32 * kSpecWarps, LGPU_SPEC_MINBLOCKS) seedSpec
                         {
                             ++f; // too short a frame is skipped without advancing needlesPos (search_algo.hpp:637)
                             seedBegin = 0;
+                            scanWord  = ~0u;
                             continue;
                         }
                         unsigned char const * trans = P.Q.trans + F * qb + static_cast<unsigned long long>(f) * origLen;
-                        if (seedNextStart(trans, len, L, P.unknownRank, seedBegin))
+                        if (seedNextStartWarp(trans, len, L, P.unknownRank, seedBegin, lane, scanWord, scanBits))
                             break;
                         npos += len;
                         ++f;
                         seedBegin = 0;
+                        scanWord  = ~0u;
                     }
                     if (!more)
                         break;
