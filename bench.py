@@ -494,10 +494,11 @@ def main():
             a[n] += b[n]
         return a
 
+    hits_w = None
     for _ in range(args.warmup):
         hits_w, _ = step(True)
         step(True, s_serial)
-    if gather is not None:
+    if gather is not None and hits_w is not None:
         gather.finish()
         gather.fit(len(hits_w))  # slots sized for what the ranks really produce (collective, before the timed region)
     sampler = ClockSampler(local_rank) if rank == 0 else None
