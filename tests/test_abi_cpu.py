@@ -266,3 +266,75 @@ print('ok', bad)
 """ % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.join(golden_dir, "prot_flat", "db.lba"), str(tmp_path))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.startswith("ok"), (r.returncode, r.stdout[-500:], r.stderr[-1500:])
+
+
+def _lba_layout(data):
+    """offsets of the fields of a generation-0 FM .lba (csrc/lba_index.hpp parse())"""
+    import struct
+    pos, out = 13, {}
+
+    def vec(name, elem):
+        nonlocal pos
+        n = struct.unpack_from("<Q", data, pos)[0]
+        out[name] = (pos, pos + 8, n)  # (offset of the count, offset of the payload, count)
+        pos += 8 + n * elem
+
+    for name, elem in (("ids", 1), ("id_delims", 8), ("seqs", 1), ("seq_delims", 8), ("s_tax_ids", 4), ("s_tax_delims", 8),
+                       ("taxon_parents", 4), ("taxon_heights", 1), ("taxon_names", 1), ("taxon_name_delims", 8)):
+        vec(name, elem)
+    out["occ_version"] = pos
+    out["n_blocks"] = pos + 4
+    return out
+
+
+def test_lba_reader_rejects_crafted_inconsistencies(golden_dir, tmp_path):
+    """counts that wrap when multiplied, delimiters that are not sorted or do not end at their payload, tax ids and
+    parents outside the taxonomy: LGPU_ERR_IO, whatever the rest of the file looks like"""
+    import struct
+    lib = lambda_b200.load_library()
+
+    def try_open(data):
+        path = str(tmp_path / "x.lba")
+        open(path, "wb").write(bytes(data))
+        h = C.c_void_p()
+        rc = lib.lgpu_lba_open(C.byref(h), path.encode())
+        msg = lib.lgpu_last_error(None).decode() if rc else ""
+        if rc == 0:
+            lib.lgpu_lba_close(h)
+        return rc, msg
+
+    src = open(os.path.join(golden_dir, "tax", "db.lba"), "rb").read()
+    lay = _lba_layout(src)
+    assert try_open(src)[0] == 0
+    assert lay["s_tax_ids"][2] > 0 and lay["taxon_parents"][2] > 0  # the fixture has a taxonomy
+
+    def put64(d, off, v):
+        struct.pack_into("<Q", d, off, v)
+
+    def put32(d, off, v):
+        struct.pack_into("<I", d, off, v)
+
+    cases = {}
+    d = bytearray(src); _, pay, n = lay["seq_delims"]
+    a, b = struct.unpack_from("<QQ", d, pay + 8)
+    put64(d, pay + 8, b); put64(d, pay + 16, a)                     # two sequence delimiters swapped
+    cases["sequence delimiters are not sorted"] = d
+    d = bytearray(src); _, pay, n = lay["id_delims"]
+    put64(d, pay + 8 * (n - 1), struct.unpack_from("<Q", d, pay + 8 * (n - 1))[0] - 1)  # ids end before their payload
+    cases["id delimiters do not match"] = d
+    d = bytearray(src); _, pay, n = lay["s_tax_ids"]
+    put32(d, pay, lay["taxon_parents"][2] + 5)                      # a subject's tax id beyond the taxonomy
+    cases["subject tax id outside"] = d
+    d = bytearray(src); _, pay, n = lay["taxon_parents"]
+    put32(d, pay + 4 * (n - 1), 0x7fffffff)                         # a parent beyond the taxonomy
+    cases["taxon parent outside"] = d
+    d = bytearray(src); _, pay, n = lay["s_tax_delims"]
+    put64(d, pay + 8 * (n - 1), lay["s_tax_ids"][2] + 3)            # tax id delimiters past their payload
+    cases["taxonomy id delimiters do not match"] = d
+    d = bytearray(src)
+    block_bytes = 80                                                 # Li10: 11 counts + pad + 4 planes
+    put64(d, lay["n_blocks"], (1 << 64) // block_bytes + 2)          # n_blocks * block_bytes wraps to a small number
+    cases["truncated"] = d
+    for what, data in cases.items():
+        rc, msg = try_open(data)
+        assert rc == -2 and what in msg, (what, rc, msg)

@@ -168,3 +168,29 @@ def test_taxonomy_columns_need_an_index_with_taxonomy(golden_dir, replay, tmp_pa
                             replay("prot_flat", 0), *extra], cwd=os.path.join(golden_dir, "prot_flat"), capture_output=True,
                            text=True, env=HOOK_ENV)
         assert r.returncode == 255 and msg in r.stderr
+
+
+@pytest.mark.parametrize("out", ["out_full.m8", "out_full.sam", "out_full.bam", "out_full.m8.gz"])
+def test_failed_writes_are_errors_not_truncated_files(golden_dir, replay, out):
+    """a write error (here: the file-size limit, which behaves like a full disk) must end in a non-zero exit code and must
+    not leave a truncated output file behind"""
+    import resource
+    import signal
+    case, domain = "prot_family", 0
+    hits = replay(case, domain)
+    cwd = os.path.join(golden_dir, case)
+    if os.path.exists(os.path.join(cwd, out)):
+        os.remove(os.path.join(cwd, out))
+
+    def limit():
+        signal.signal(signal.SIGXFSZ, signal.SIG_IGN)  # write() fails with EFBIG instead of killing the process
+        resource.setrlimit(resource.RLIMIT_FSIZE, (512, 512))
+
+    r = subprocess.run([CLI, SUB[domain], "-q", "q.fasta", "-i", "db.lba", "-o", out, "-t", "1", "-v", "0", "--replay-hits", hits],
+                       cwd=cwd, capture_output=True, env=HOOK_ENV, preexec_fn=limit, text=True)
+    assert r.returncode != 0
+    assert "error while writing" in (r.stdout + r.stderr)
+    assert not os.path.exists(os.path.join(cwd, out))
+    # the same command without the limit works
+    path = run_cli(golden_dir, case, domain, hits, out)
+    assert os.path.getsize(path) > 512
