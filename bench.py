@@ -621,7 +621,9 @@ def main():
            "data": "synthetic", "config": cfg,
            "gather": ({"what": "one fixed-capacity NCCL all-gather of the hit records per step, device to device, on a side "
                                "stream (overlaps the next step); only the last one of the timed region is exposed",
-                       "device_ms_last": tinfo["gather_device_ms_last"], "slot_records": gather.cap,
+                       "device_ms_last": tinfo["gather_device_ms_last"],
+                       "gather_ms_per_step": tinfo["gather_device_ms_last"] / args.steps,  # what the timed region pays per step
+                       "slot_records": gather.cap,
                        "regrown": gather.regrown} if gather is not None else None),
            "rank_ms_per_step_min_max": tinfo["rank_ms_per_step_min_max"],
            "gcups": (cells_score_all + cells_trace_all) / (ms_res * 1e-3) / 1e9,

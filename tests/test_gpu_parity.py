@@ -682,3 +682,44 @@ def test_long_self_hits_vs_live_reference_and_int16_limit(tmp_path):
     ids2, hits2, _ = s.search_fasta(str(tmp_path / "q.fasta"))
     assert (hits2 == hits).all()
     s.close(); ix.close()
+
+
+def test_device_side_index_validation(golden_dir, tmp_path):
+    """corruption that the host parser cannot see in O(1) -- an occurrence count that does not continue its predecessor,
+    a sampled suffix-array entry naming a sequence that does not exist, a CSA super block ranking outside the sampled
+    array -- is caught by the cross-checks that run on the device after the upload: LGPU_ERR_IO, not a wild read"""
+    import struct
+    from test_abi_cpu import _lba_layout
+    src = open(os.path.join(golden_dir, "prot_flat", "db.lba"), "rb").read()
+    lay = _lba_layout(src)
+    sigma, block_bytes = 11, 80
+    n_blocks = struct.unpack_from("<Q", src, lay["n_blocks"])[0]
+    occ = lay["n_blocks"] + 8
+    pos = occ + n_blocks * block_bytes
+    n_super = struct.unpack_from("<Q", src, pos)[0]
+    pos += 8 + n_super * sigma * 8 + (sigma + 1) * 8
+    n_ssa = struct.unpack_from("<Q", src, pos)[0]
+    ssa = pos + 8
+    csa = ssa + n_ssa * 8 + 4 + 8  # version, super block count
+
+    def load(data):
+        path = str(tmp_path / "x.lba")
+        open(path, "wb").write(bytes(data))
+        ix = lambda_b200.Index.load(path)
+        ix.close()
+
+    load(src)
+    cases = []
+    d = bytearray(src)
+    struct.pack_into("<I", d, occ + 7 * block_bytes + 4 * 3, struct.unpack_from("<I", d, occ + 7 * block_bytes + 4 * 3)[0] + 1)
+    cases.append(("occ block counts", d))
+    d = bytearray(src)
+    struct.pack_into("<Q", d, ssa + 8 * 17, (1 << 63) | 5)
+    cases.append(("sampled suffix array", d))
+    d = bytearray(src)
+    struct.pack_into("<Q", d, csa + 48 * 3, n_ssa + 1000)
+    cases.append(("CSA bit vector", d))
+    for what, data in cases:
+        with pytest.raises(lambda_b200.LambdaError) as e:
+            load(data)
+        assert e.value.code == -2 and what in str(e.value), (what, str(e.value))
